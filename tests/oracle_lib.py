@@ -1,0 +1,176 @@
+"""ctypes binding of the CPU oracle (oracle/libfem_oracle.so).
+
+Test infrastructure only: imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py.  Never imported by the product.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ORACLE_DIR = os.path.join(os.path.dirname(_HERE), "oracle")
+_LIB = None
+
+LAGRANGE, DG_LEGENDRE, DG_LEGENDRE_HIER = 0, 1, 2
+NUMBERING_YASP, NUMBERING_ADAPTIVE_LEAF = 0, 1
+
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_lp = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+_bp = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    so = os.path.join(_ORACLE_DIR, "libfem_oracle.so")
+    src = os.path.join(_ORACLE_DIR, "fem_oracle.cpp")
+    if not os.path.exists(so) or (os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(so)):
+        subprocess.check_call(["make", "-C", _ORACLE_DIR, "-s"])
+    L = C.CDLL(so)
+    L.fo_space_create.restype = C.c_void_p
+    L.fo_space_create.argtypes = [C.c_int, _ip, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.fo_space_destroy.argtypes = [C.c_void_p]
+    L.fo_space_size.restype = C.c_int64
+    L.fo_space_size.argtypes = [C.c_void_p]
+    L.fo_space_local_size.restype = C.c_int
+    L.fo_space_local_size.argtypes = [C.c_void_p]
+    L.fo_space_elements.restype = C.c_int64
+    L.fo_space_elements.argtypes = [C.c_void_p]
+    L.fo_space_dofmap.argtypes = [C.c_void_p, C.c_int64, _lp]
+    L.fo_space_multiindex.argtypes = [C.c_void_p, _ip]
+    L.fo_quadrature.restype = C.c_int
+    L.fo_quadrature.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.fo_legendre.restype = C.c_double
+    L.fo_legendre.argtypes = [C.c_int, C.c_double, C.c_int]
+    L.fo_shape_evaluate.argtypes = [C.c_void_p, _dp, _dp, _dp]
+    L.fo_operator_create.restype = C.c_void_p
+    L.fo_operator_create.argtypes = [C.c_void_p, _dp, _ip]
+    L.fo_operator_destroy.argtypes = [C.c_void_p]
+    L.fo_operator_set_threads.argtypes = [C.c_void_p, C.c_int]
+    L.fo_operator_apply.argtypes = [C.c_void_p, _dp, _dp, C.c_int]
+    L.fo_operator_apply_box.argtypes = [C.c_void_p, _dp, _dp, C.c_int, _ip, _ip]
+    L.fo_dirichlet.argtypes = [C.c_void_p, _bp, _dp]
+    L.fo_cg.restype = C.c_int
+    L.fo_cg.argtypes = [C.c_void_p, _dp, _dp, C.c_double, C.c_int, C.c_int, C.c_void_p]
+    L.fo_dot.restype = C.c_double
+    L.fo_dot.argtypes = [_dp, _dp, C.c_int64]
+    L.fo_interpolate.argtypes = [C.c_void_p, C.c_int, _dp]
+    L.fo_l2error.restype = C.c_double
+    L.fo_l2error.argtypes = [C.c_void_p, _dp, C.c_int]
+    L.fo_assemble_dense.argtypes = [C.c_void_p, _dp]
+    L.fo_time_apply.restype = C.c_double
+    L.fo_time_apply.argtypes = [C.c_void_p, _dp, _dp, C.c_int, C.c_int]
+    _LIB = L
+    return L
+
+
+class Space:
+    def __init__(self, n, lo, hi, kind, order, numbering=NUMBERING_YASP, interior_order=0, surface_order=0):
+        self.dim = len(n)
+        self.n = np.ascontiguousarray(n, dtype=np.int32)
+        self.lo = np.ascontiguousarray(lo, dtype=np.float64)
+        self.hi = np.ascontiguousarray(hi, dtype=np.float64)
+        self.kind, self.order = kind, order
+        self._h = lib().fo_space_create(self.dim, self.n, self.lo, self.hi, kind, order, numbering,
+                                        interior_order, surface_order)
+        self.size = lib().fo_space_size(self._h)
+        self.local_size = lib().fo_space_local_size(self._h)
+        self.elements = lib().fo_space_elements(self._h)
+
+    def dofmap(self, e):
+        out = np.empty(self.local_size, dtype=np.int64)
+        lib().fo_space_dofmap(self._h, e, out)
+        return out
+
+    def multiindex(self):
+        out = np.empty((self.local_size, 3), dtype=np.int32)
+        lib().fo_space_multiindex(self._h, out)
+        return out
+
+    def shape(self, x):
+        x3 = np.zeros(3)
+        x3[:len(x)] = x
+        phi = np.empty(self.local_size)
+        dphi = np.empty((self.local_size, 3))
+        lib().fo_shape_evaluate(self._h, x3, phi, dphi)
+        return phi, dphi
+
+    def interpolate(self, data):
+        out = np.zeros(self.size)
+        lib().fo_interpolate(self._h, data, out)
+        return out
+
+    def l2error(self, u, data):
+        return lib().fo_l2error(self._h, np.ascontiguousarray(u), data)
+
+    def __del__(self):
+        try:
+            lib().fo_space_destroy(self._h)
+        except Exception:
+            pass
+
+
+class Operator:
+    """ADR integrands (see fem_oracle.cpp): eps, b, c, gamma, beta + flags."""
+
+    def __init__(self, space, eps=1.0, b=(0.0, 0.0, 0.0), c=0.0, gamma=0.0, beta=0.0, dirichlet_mask=0, data=0,
+                 skeleton=False, boundary=False, strong_dirichlet=False, threads=1):
+        self.space = space
+        bb = list(b) + [0.0] * (3 - len(b))
+        params = np.array([eps, bb[0], bb[1], bb[2], c, gamma, beta], dtype=np.float64)
+        iparams = np.array([dirichlet_mask, data, int(skeleton), int(boundary), int(strong_dirichlet)], dtype=np.int32)
+        self._h = lib().fo_operator_create(space._h, params, iparams)
+        if threads > 1:
+            lib().fo_operator_set_threads(self._h, threads)
+
+    def apply(self, u, linear=False):
+        w = np.empty(self.space.size)
+        lib().fo_operator_apply(self._h, np.ascontiguousarray(u, dtype=np.float64), w, int(linear))
+        return w
+
+    def apply_box(self, u, lo, hi, linear=False):
+        w = np.empty(self.space.size)
+        lo3 = np.array(list(lo) + [0] * (3 - len(lo)), dtype=np.int32)
+        hi3 = np.array(list(hi) + [1] * (3 - len(hi)), dtype=np.int32)
+        lib().fo_operator_apply_box(self._h, np.ascontiguousarray(u, dtype=np.float64), w, int(linear), lo3, hi3)
+        return w
+
+    def dirichlet(self):
+        mask = np.zeros(self.space.size, dtype=np.uint8)
+        vals = np.zeros(self.space.size)
+        lib().fo_dirichlet(self._h, mask, vals)
+        return mask, vals
+
+    def cg(self, b, x0, eps, maxit, tolcrit=0):
+        x = np.array(x0, dtype=np.float64, copy=True)
+        hist = np.zeros(max(maxit, 1))
+        it = lib().fo_cg(self._h, np.ascontiguousarray(b, dtype=np.float64), x, eps, maxit, tolcrit,
+                         hist.ctypes.data_as(C.c_void_p))
+        return it, x, hist[:abs(it)]
+
+    def assemble_dense(self):
+        n = self.space.size
+        A = np.empty((n, n))
+        lib().fo_assemble_dense(self._h, A)
+        return A
+
+    def time_apply(self, u, linear=False, reps=3):
+        w = np.empty(self.space.size)
+        return lib().fo_time_apply(self._h, np.ascontiguousarray(u, dtype=np.float64), w, int(linear), reps)
+
+    def __del__(self):
+        try:
+            lib().fo_operator_destroy(self._h)
+        except Exception:
+            pass
+
+
+def quadrature(dim, order):
+    n = lib().fo_quadrature(dim, order, None, None)
+    x = np.empty((n, 3))
+    w = np.empty(n)
+    lib().fo_quadrature(dim, order, x.ctypes.data_as(C.c_void_p), w.ctypes.data_as(C.c_void_p))
+    return x, w
