@@ -1,0 +1,560 @@
+// capi.cu -- C ABI (include/b200fem.h) over the CUDA kernels.  Host logic only: handles, tables, launch
+// configuration, the CG driver, halo exchange.  No CPU compute fallback exists: every compute entry point needs a
+// CUDA device and reports B200FEM_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/b200fem.h"
+#include "dg_kronecker.cuh"
+#include "dg_quadrature.cuh"
+#include "halo.cuh"
+#include "integrands.cuh"
+#include "kron_tables.hpp"
+#include "lagrange_quadrature.cuh"
+#include "tables.hpp"
+#include "vec_kernels.cuh"
+
+using namespace b200fem;
+
+static thread_local std::string g_error;
+static int fail(int code, const std::string& msg) { g_error = msg; return code; }
+#define CUDA_OK(expr)                                                                                   \
+  do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return fail(B200FEM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); } while (0)
+#define REQUIRE(cond, code, msg) do { if (!(cond)) return fail(code, msg); } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------
+struct b200fem_ctx {
+  int device = 0; cudaStream_t stream = nullptr; bool own_stream = false;
+  NcclApi nccl; void* comm = nullptr; bool own_comm = false; int rank = 0, world = 1;
+};
+struct b200fem_mesh {
+  b200fem_ctx* ctx; int dim; int gn[3]; double lo[3], hi[3], h[3];
+  int proc[3], pc[3];            // process grid and this rank's coordinates
+  BoxDev box;                    // local box incl. ghost layers (ghost layers only used by DG spaces)
+  int olo[3], ohi[3];            // owned range in global element coordinates
+};
+struct b200fem_space {
+  b200fem_mesh* mesh; int kind, order, numbering, n1, nb; long long size, elements;
+  BoxDev box;                    // DG: mesh box with ghosts; Lagrange: owned elements only
+  Tab1D tab; std::vector<int> perm;
+  LagrangeLayoutDev lay; long long* d_lattice_map = nullptr; std::vector<long long> lattice_map;
+};
+struct b200fem_operator {
+  b200fem_space* sp; b200fem_model model; int kernel_pref = B200FEM_KERNEL_AUTO; bool communicate = true;
+  unsigned q_interior = 0, q_surface = 0;
+  int* d_perm = nullptr; double* d_bvec = nullptr; uint8_t* d_dmask = nullptr; double* d_dvals = nullptr; uint8_t* d_aux = nullptr;
+  std::vector<uint8_t> h_dmask; std::vector<double> h_dvals;
+  double *d_u = nullptr, *d_w = nullptr;                       // staging for the host-pointer API
+  double *d_h = nullptr, *d_r = nullptr, *d_p = nullptr, *d_x = nullptr, *d_b = nullptr, *d_partial = nullptr, *d_sums = nullptr, *d_hist = nullptr;
+  CgState* d_cg = nullptr; int hist_cap = 0;
+  HaloPlan halo;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evx0 = nullptr, evx1 = nullptr; b200fem_timing timing{};
+};
+
+extern "C" const char* b200fem_last_error(void) { return g_error.c_str(); }
+extern "C" int b200fem_version(void) { return 100; }
+
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int b200fem_ctx_create(int device, void* stream, b200fem_ctx** out) {
+  REQUIRE(out, B200FEM_ERR_INVALID, "ctx_create: out is null");
+  int count = 0; cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) return fail(B200FEM_ERR_CUDA, "no CUDA device available: this library has no CPU fallback");
+  REQUIRE(device >= 0 && device < count, B200FEM_ERR_INVALID, "ctx_create: bad device index");
+  CUDA_OK(cudaSetDevice(device));
+  auto* c = new b200fem_ctx; c->device = device;
+  if (stream) c->stream = (cudaStream_t)stream; else { CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+  *out = c; return B200FEM_OK;
+}
+extern "C" int b200fem_ctx_destroy(b200fem_ctx* c) {
+  if (!c) return B200FEM_OK;
+  if (c->own_comm && c->comm && c->nccl.ok()) c->nccl.CommDestroy(c->comm);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c; return B200FEM_OK;
+}
+extern "C" int b200fem_ctx_synchronize(b200fem_ctx* c) { REQUIRE(c, B200FEM_ERR_INVALID, "null ctx"); CUDA_OK(cudaSetDevice(c->device)); CUDA_OK(cudaStreamSynchronize(c->stream)); return B200FEM_OK; }
+extern "C" int b200fem_malloc(b200fem_ctx* c, int64_t bytes, void** dev) { REQUIRE(c && dev, B200FEM_ERR_INVALID, "malloc: null"); CUDA_OK(cudaSetDevice(c->device)); CUDA_OK(cudaMalloc(dev, (size_t)bytes)); return B200FEM_OK; }
+extern "C" int b200fem_free(b200fem_ctx* c, void* dev) { REQUIRE(c, B200FEM_ERR_INVALID, "free: null"); CUDA_OK(cudaSetDevice(c->device)); CUDA_OK(cudaFree(dev)); return B200FEM_OK; }
+extern "C" int b200fem_memcpy_h2d(b200fem_ctx* c, void* dev, const void* host, int64_t bytes) {
+  REQUIRE(c, B200FEM_ERR_INVALID, "null ctx"); CUDA_OK(cudaMemcpyAsync(dev, host, (size_t)bytes, cudaMemcpyHostToDevice, c->stream)); CUDA_OK(cudaStreamSynchronize(c->stream)); return B200FEM_OK; }
+extern "C" int b200fem_memcpy_d2h(b200fem_ctx* c, void* host, const void* dev, int64_t bytes) {
+  REQUIRE(c, B200FEM_ERR_INVALID, "null ctx"); CUDA_OK(cudaMemcpyAsync(host, dev, (size_t)bytes, cudaMemcpyDeviceToHost, c->stream)); CUDA_OK(cudaStreamSynchronize(c->stream)); return B200FEM_OK; }
+
+// ---------------------------------------------------------------------------------------------------------------
+static int make_mesh(b200fem_ctx* ctx, int dim, const int32_t* n, const double* lo, const double* hi, const int32_t* proc, int rank, b200fem_mesh** out) {
+  REQUIRE(ctx && n && lo && hi && out, B200FEM_ERR_INVALID, "mesh: null argument");
+  REQUIRE(dim == 2 || dim == 3, B200FEM_ERR_NOT_IMPLEMENTED, "mesh: dim must be 2 or 3");
+  auto* m = new b200fem_mesh; m->ctx = ctx; m->dim = dim;
+  int world = 1;
+  for (int d = 0; d < 3; ++d) {
+    m->gn[d] = d < dim ? n[d] : 1; m->lo[d] = d < dim ? lo[d] : 0.0; m->hi[d] = d < dim ? hi[d] : 1.0;
+    m->proc[d] = (proc && d < dim) ? proc[d] : 1; world *= m->proc[d];
+    if (m->gn[d] < 1 || !(m->hi[d] > m->lo[d]) || m->proc[d] < 1 || m->proc[d] > m->gn[d]) { delete m; return fail(B200FEM_ERR_INVALID, "mesh: bad extents"); }
+    m->h[d] = (m->hi[d] - m->lo[d]) / m->gn[d];
+  }
+  if (rank < 0 || rank >= world) { delete m; return fail(B200FEM_ERR_INVALID, "mesh: rank outside process grid"); }
+  m->pc[0] = rank % m->proc[0]; m->pc[1] = (rank / m->proc[0]) % m->proc[1]; m->pc[2] = rank / (m->proc[0] * m->proc[1]);
+  BoxDev& b = m->box; b.dim = dim;
+  for (int d = 0; d < 3; ++d) {
+    // block distribution: the first (gn % proc) ranks along an axis get one extra cell
+    const int q = m->gn[d] / m->proc[d], r = m->gn[d] % m->proc[d], c = m->pc[d];
+    m->olo[d] = c * q + std::min(c, r); m->ohi[d] = m->olo[d] + q + (c < r ? 1 : 0);
+    const int glo = m->olo[d] > 0 ? 1 : 0, ghi = m->ohi[d] < m->gn[d] ? 1 : 0;      // overlap 1 where a neighbour rank exists
+    b.origin[d] = m->olo[d] - glo; b.n[d] = (m->ohi[d] - m->olo[d]) + glo + ghi;
+    b.own_lo[d] = glo; b.own_hi[d] = glo + (m->ohi[d] - m->olo[d]);
+    b.gn[d] = m->gn[d]; b.lo[d] = m->lo[d]; b.h[d] = m->h[d];
+  }
+  *out = m; return B200FEM_OK;
+}
+extern "C" int b200fem_mesh_cartesian(b200fem_ctx* ctx, int dim, const int32_t* n, const double* lo, const double* hi, b200fem_mesh** out) {
+  return make_mesh(ctx, dim, n, lo, hi, nullptr, 0, out);
+}
+extern "C" int b200fem_mesh_cartesian_distributed(b200fem_ctx* ctx, int dim, const int32_t* n, const double* lo, const double* hi, const int32_t* proc, int rank, b200fem_mesh** out) {
+  REQUIRE(proc, B200FEM_ERR_INVALID, "mesh: proc is null");
+  return make_mesh(ctx, dim, n, lo, hi, proc, rank, out);
+}
+extern "C" int b200fem_mesh_destroy(b200fem_mesh* m) { delete m; return B200FEM_OK; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// AdaptiveLeafIndexSet first-touch numbering of the Lagrange lattice (gridpart/adaptiveleafindexset.hh:884-906)
+static void build_adaptive_leaf_map(b200fem_space* s) {
+  const BoxDev& b = s->box; const int dim = b.dim, k = s->order;
+  const long long L0 = s->lay.lattice[0], L1 = s->lay.lattice[1], L2 = s->lay.lattice[2];
+  s->lattice_map.assign((size_t)(L0 * L1 * L2), -1);
+  long long cnt[4] = {0, 0, 0, 0}, type_off[4] = {0, 0, 0, 0}, counter[4] = {0, 0, 0, 0};
+  for (int sft = 0; sft < (1 << dim); ++sft) { if (s->lay.group_offset[sft] < 0) continue; long long c = 1; for (int d = 0; d < 3; ++d) c *= s->lay.group_dims[sft][d]; cnt[__builtin_popcount(sft)] += c; }
+  for (int p = 1; p <= dim; ++p) type_off[p] = type_off[p - 1] + cnt[p - 1];
+  // sub-entities of the cube in reference-element order, as lattice offsets in {0,1,2}
+  std::vector<std::array<int, 3>> subs[4];
+  for (int v = 0; v < (1 << dim); ++v) { std::array<int, 3> a = {0, 0, 0}; for (int d = 0; d < dim; ++d) a[d] = 2 * ((v >> d) & 1); subs[0].push_back(a); }
+  if (dim == 2) { subs[1] = {{0, 1, 0}, {2, 1, 0}, {1, 0, 0}, {1, 2, 0}}; subs[2] = {{1, 1, 0}}; }
+  if (dim == 3) {
+    subs[1] = {{0, 0, 1}, {2, 0, 1}, {0, 2, 1}, {2, 2, 1}, {0, 1, 0}, {2, 1, 0}, {1, 0, 0}, {1, 2, 0}, {0, 1, 2}, {2, 1, 2}, {1, 0, 2}, {1, 2, 2}};
+    subs[2] = {{0, 1, 1}, {2, 1, 1}, {1, 0, 1}, {1, 2, 1}, {1, 1, 0}, {1, 1, 2}};
+    subs[3] = {{1, 1, 1}};
+  }
+  for (int e2 = 0; e2 < b.n[2]; ++e2) for (int e1 = 0; e1 < b.n[1]; ++e1) for (int e0 = 0; e0 < b.n[0]; ++e0) {
+    const int ec[3] = {e0, e1, e2};
+    for (int cd = 0; cd <= dim; ++cd) { const int pd = dim - cd; if (k == 1 && pd != 0) continue;
+      for (auto& a : subs[pd]) {
+        long long g[3] = {0, 0, 0}; for (int d = 0; d < dim; ++d) g[d] = (long long)k * ec[d] + (k == 1 ? a[d] / 2 : a[d]);
+        long long& slot = s->lattice_map[(size_t)(g[0] + L0 * (g[1] + L1 * g[2]))];
+        if (slot < 0) slot = type_off[pd] + counter[pd]++;
+      } }
+  }
+}
+
+extern "C" int b200fem_space_create(b200fem_mesh* mesh, int kind, int order, int numbering, b200fem_space** out) {
+  REQUIRE(mesh && out, B200FEM_ERR_INVALID, "space_create: null argument");
+  REQUIRE(kind >= 0 && kind <= 2, B200FEM_ERR_INVALID, "space_create: unknown space kind");
+  try {
+    auto s = std::unique_ptr<b200fem_space>(new b200fem_space);
+    s->mesh = mesh; s->kind = kind; s->order = order; s->numbering = numbering; s->n1 = order + 1;
+    const int dim = mesh->dim; s->nb = 1; for (int d = 0; d < dim; ++d) s->nb *= s->n1;
+    s->box = mesh->box;
+    if (kind == B200FEM_LAGRANGE) {
+      REQUIRE(order == 1 || order == 2, B200FEM_ERR_NOT_IMPLEMENTED, "Lagrange spaces: order 1 and 2 only");
+      BoxDev& b = s->box;      // continuous spaces need no ghost elements: the local box is the owned box
+      for (int d = 0; d < 3; ++d) { b.origin[d] = mesh->olo[d]; b.n[d] = mesh->ohi[d] - mesh->olo[d]; b.own_lo[d] = 0; b.own_hi[d] = b.n[d]; }
+      LagrangeLayoutDev& L = s->lay; L.order = order; L.lattice_map = nullptr;
+      for (int d = 0; d < 3; ++d) L.lattice[d] = d < dim ? (long long)order * b.n[d] + 1 : 1;
+      long long off = 0;
+      for (int sft = 0; sft < 8; ++sft) { L.group_offset[sft] = -1; for (int d = 0; d < 3; ++d) L.group_dims[sft][d] = 1; }
+      for (int pc = 0; pc <= dim; ++pc) for (int sft = 0; sft < (1 << dim); ++sft) {
+        if (__builtin_popcount(sft) != pc || (order == 1 && sft != 0)) continue;
+        L.group_offset[sft] = off; long long c = 1;
+        for (int d = 0; d < 3; ++d) { L.group_dims[sft][d] = d < dim ? b.n[d] + (((sft >> d) & 1) ? 0 : 1) : 1; c *= L.group_dims[sft][d]; }
+        off += c;
+      }
+      s->size = off; s->elements = (long long)b.n[0] * b.n[1] * b.n[2];
+      s->tab = tabulate_1d(Basis::Lagrange, order, gauss_points_for_order(2 * order));
+      if (numbering == B200FEM_NUMBERING_ADAPTIVE_LEAF) {
+        build_adaptive_leaf_map(s.get());
+        CUDA_OK(cudaSetDevice(mesh->ctx->device));
+        CUDA_OK(cudaMalloc(&s->d_lattice_map, s->lattice_map.size() * sizeof(long long)));
+        CUDA_OK(cudaMemcpy(s->d_lattice_map, s->lattice_map.data(), s->lattice_map.size() * sizeof(long long), cudaMemcpyHostToDevice));
+        L.lattice_map = s->d_lattice_map;
+      }
+    } else {
+      REQUIRE(order >= 1 && order <= 5, B200FEM_ERR_NOT_IMPLEMENTED, "DG Legendre spaces: orders 1..5");
+      REQUIRE(dim == 3, B200FEM_ERR_NOT_IMPLEMENTED, "DG Legendre spaces: 3-D boxes only");
+      const BoxDev& b = s->box;
+      s->elements = (long long)b.n[0] * b.n[1] * b.n[2]; s->size = s->elements * s->nb;
+      s->tab = tabulate_1d(Basis::Legendre, order, gauss_points_for_order(2 * order));
+      s->perm = legendre_local_permutation(dim, order, kind == B200FEM_DG_LEGENDRE_HIER);
+    }
+    *out = s.release(); return B200FEM_OK;
+  } catch (const std::exception& ex) { return fail(B200FEM_ERR_INVALID, ex.what()); }
+}
+extern "C" int b200fem_space_destroy(b200fem_space* s) { if (s && s->d_lattice_map) cudaFree(s->d_lattice_map); delete s; return B200FEM_OK; }
+extern "C" int b200fem_space_size(b200fem_space* s, int64_t* size) { REQUIRE(s && size, B200FEM_ERR_INVALID, "null"); *size = s->size; return B200FEM_OK; }
+extern "C" int b200fem_space_local_size(b200fem_space* s, int32_t* nb) { REQUIRE(s && nb, B200FEM_ERR_INVALID, "null"); *nb = s->nb; return B200FEM_OK; }
+extern "C" int b200fem_space_elements(b200fem_space* s, int64_t* n) { REQUIRE(s && n, B200FEM_ERR_INVALID, "null"); *n = s->elements; return B200FEM_OK; }
+extern "C" int b200fem_space_dofmap(b200fem_space* s, int64_t e, int64_t* out) {
+  REQUIRE(s && out, B200FEM_ERR_INVALID, "null"); REQUIRE(e >= 0 && e < s->elements, B200FEM_ERR_INVALID, "dofmap: element out of range");
+  if (s->kind != B200FEM_LAGRANGE) { for (int j = 0; j < s->nb; ++j) out[j] = e * s->nb + j; return B200FEM_OK; }
+  const BoxDev& b = s->box; const int n1 = s->n1, k = s->order;
+  const int ec[3] = {(int)(e % b.n[0]), (int)((e / b.n[0]) % b.n[1]), (int)(e / ((long long)b.n[0] * b.n[1]))};
+  LagrangeLayoutDev L = s->lay; L.lattice_map = s->lattice_map.empty() ? nullptr : s->lattice_map.data();
+  for (int l = 0; l < s->nb; ++l) {                      // local numbering: coordinate 0 fastest (genericlagrangepoints.hh:862-876)
+    const int a0 = l % n1, a1 = (l / n1) % n1, a2 = b.dim == 3 ? l / (n1 * n1) : 0;
+    out[l] = lagrange_dof(L, (long long)k * ec[0] + a0, (long long)k * ec[1] + a1, b.dim == 3 ? (long long)k * ec[2] + a2 : 0);
+  }
+  return B200FEM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+template <int N> static DgTabDev<N> make_tab(const Tab1D& t) {
+  DgTabDev<N> T;
+  for (int i = 0; i < N * N; ++i) { T.B[i] = t.B[i]; T.G[i] = t.G[i]; }
+  for (int i = 0; i < N; ++i) { T.x[i] = t.x[i]; T.w[i] = t.w[i]; T.phi[0][i] = t.phi0[i]; T.phi[1][i] = t.phi1[i]; T.dphi[0][i] = t.dphi0[i]; T.dphi[1][i] = t.dphi1[i]; }
+  return T;
+}
+static AdrIntegrands make_integrands(const b200fem_operator* op, bool with_data) { AdrIntegrands I; I.m = op->model; I.dim = op->sp->box.dim; I.with_data = with_data; return I; }
+
+static bool default_quadrature(const b200fem_operator* op) {
+  const int k = op->sp->order;
+  const int mi = gauss_points_for_order(op->q_interior ? (int)op->q_interior : 2 * k), ms = gauss_points_for_order(op->q_surface ? (int)op->q_surface : 2 * k + 1);
+  return mi == k + 1 && ms == k + 1;
+}
+
+template <int N> static int launch_dg_quadrature(b200fem_operator* op, const double* u, double* w, const double* bvec, bool with_data) {
+  using Cfg = DgQuadCfg<N>; const BoxDev& b = op->sp->box;
+  const long long n_owned = (long long)(b.own_hi[0] - b.own_lo[0]) * (b.own_hi[1] - b.own_lo[1]) * (b.own_hi[2] - b.own_lo[2]);
+  auto kern = dg_quadrature_kernel<N, AdrIntegrands>;
+  CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes()));
+  const unsigned grid = (unsigned)((n_owned + Cfg::EB - 1) / Cfg::EB);
+  kern<<<grid, Cfg::kThreads, Cfg::smem_bytes(), op->sp->mesh->ctx->stream>>>(make_tab<N>(op->sp->tab), b, make_integrands(op, with_data), op->d_perm, u, w, bvec, n_owned);
+  CUDA_OK(cudaGetLastError()); return B200FEM_OK;
+}
+template <int N, int TX, int TY, int TZ> static int launch_dg_kronecker(b200fem_operator* op, const double* u, double* w, const double* bvec) {
+  using Cfg = KronCfg<N, TX, TY, TZ>; const BoxDev& b = op->sp->box;
+  KronHost kh = build_kron_tables(op->sp->tab, op->model, b.dim, b.h);
+  KronTabDev<N> K;
+  for (int d = 0; d < 3; ++d) for (int i = 0; i < N * N; ++i) { K.S[d][i] = kh.S[d][i]; K.Dlo[d][i] = kh.Dlo[d][i]; K.Dhi[d][i] = kh.Dhi[d][i]; K.L[d][i] = kh.L[d][i]; K.R[d][i] = kh.R[d][i]; }
+  const int tx = (b.own_hi[0] - b.own_lo[0] + TX - 1) / TX, ty = (b.own_hi[1] - b.own_lo[1] + TY - 1) / TY, tz = (b.own_hi[2] - b.own_lo[2] + TZ - 1) / TZ;
+  auto kern = dg_kronecker_kernel<N, TX, TY, TZ>;
+  CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes()));
+  kern<<<(unsigned)(tx * ty * tz), Cfg::kThreads, Cfg::smem_bytes(), op->sp->mesh->ctx->stream>>>(K, b, op->d_perm, u, w, bvec, tx, ty);
+  CUDA_OK(cudaGetLastError()); return B200FEM_OK;
+}
+template <int N> static int launch_lagrange(b200fem_operator* op, const double* u, double* w, bool with_data) {
+  const BoxDev& b = op->sp->box; cudaStream_t st = op->sp->mesh->ctx->stream;
+  CUDA_OK(cudaMemsetAsync(w, 0, sizeof(double) * (size_t)op->sp->size, st));                 // w.clear() (galerkin.hh:1463)
+  AdrIntegrands I = make_integrands(op, with_data);
+  int launches = 1;
+  if (b.dim == 3) {
+    using Cfg = DgQuadCfg<N>; auto kern = lagrange3d_quadrature_kernel<N, AdrIntegrands>;
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes()));
+    for (int c = 0; c < 8; ++c) {
+      const int c0 = c & 1, c1 = (c >> 1) & 1, c2 = c >> 2;
+      const int m0 = (b.n[0] - c0 + 1) / 2, m1 = (b.n[1] - c1 + 1) / 2, m2 = (b.n[2] - c2 + 1) / 2;
+      const long long nc = (long long)m0 * m1 * m2; if (nc <= 0) continue;
+      kern<<<(unsigned)((nc + Cfg::EB - 1) / Cfg::EB), Cfg::kThreads, Cfg::smem_bytes(), st>>>(make_tab<N>(op->sp->tab), b, I, op->sp->lay, u, w, c0, c1, c2, m0, m1, nc);
+      ++launches;
+    }
+  } else {
+    for (int c = 0; c < 4; ++c) {
+      const int c0 = c & 1, c1 = c >> 1; const int m0 = (b.n[0] - c0 + 1) / 2, m1 = (b.n[1] - c1 + 1) / 2;
+      const long long nc = (long long)m0 * m1; if (nc <= 0) continue;
+      lagrange2d_quadrature_kernel<N, AdrIntegrands><<<(unsigned)((nc + 127) / 128), 128, 0, st>>>(make_tab<N>(op->sp->tab), b, I, op->sp->lay, u, w, c0, c1, m0, nc);
+      ++launches;
+    }
+  }
+  CUDA_OK(cudaGetLastError());
+  op->timing.launches_per_apply = launches;
+  return B200FEM_OK;
+}
+
+static int ensure_bvec(b200fem_operator* op);
+
+// one operator application on device vectors, without halo exchange
+static int apply_local(b200fem_operator* op, const double* u, double* w, bool linear) {
+  b200fem_space* s = op->sp; cudaStream_t st = s->mesh->ctx->stream;
+  const long long n = s->size; const int N = s->n1;
+  REQUIRE(default_quadrature(op), B200FEM_ERR_NOT_IMPLEMENTED, "only quadrature orders that select the (order+1)-point Gauss rule are implemented on the device");
+  if (s->kind == B200FEM_LAGRANGE) {
+    REQUIRE(!op->model.has_skeleton, B200FEM_ERR_NOT_IMPLEMENTED, "skeleton integrands on continuous spaces");
+    int rc = N == 2 ? launch_lagrange<2>(op, u, w, !linear) : launch_lagrange<3>(op, u, w, !linear);
+    if (rc) return rc;
+    op->timing.kernel = B200FEM_KERNEL_QUADRATURE;
+    return B200FEM_OK;
+  }
+  const bool kron_ok = op->model.gamma == 0.0 && (N == 2 || N == 3);
+  int kernel = op->kernel_pref;
+  if (kernel == B200FEM_KERNEL_AUTO) kernel = kron_ok ? B200FEM_KERNEL_KRONECKER : B200FEM_KERNEL_QUADRATURE;
+  if (kernel == B200FEM_KERNEL_KRONECKER) {
+    REQUIRE(kron_ok, B200FEM_ERR_INVALID, "Kronecker kernel needs a linear model and order <= 2");
+    const double* bvec = nullptr;
+    if (!linear && op->model.data) { int rc = ensure_bvec(op); if (rc) return rc; bvec = op->d_bvec; }
+    int rc = N == 2 ? launch_dg_kronecker<2, 8, 8, 4>(op, u, w, bvec) : launch_dg_kronecker<3, 8, 4, 4>(op, u, w, bvec);
+    if (rc) return rc;
+  } else {
+    int rc = B200FEM_ERR_NOT_IMPLEMENTED;
+    const bool with_data = !linear;
+    switch (N) {
+      case 2: rc = launch_dg_quadrature<2>(op, u, w, nullptr, with_data); break;
+      case 3: rc = launch_dg_quadrature<3>(op, u, w, nullptr, with_data); break;
+      case 4: rc = launch_dg_quadrature<4>(op, u, w, nullptr, with_data); break;
+      case 5: rc = launch_dg_quadrature<5>(op, u, w, nullptr, with_data); break;
+      case 6: rc = launch_dg_quadrature<6>(op, u, w, nullptr, with_data); break;
+      default: return fail(B200FEM_ERR_NOT_IMPLEMENTED, "DG order > 5");
+    }
+    if (rc) return rc;
+  }
+  (void)n; (void)st;
+  op->timing.kernel = kernel; op->timing.launches_per_apply = 1;
+  return B200FEM_OK;
+}
+
+// b = -L[0], evaluated once by the quadrature kernel with the data terms switched on
+static int ensure_bvec(b200fem_operator* op) {
+  if (op->d_bvec) return B200FEM_OK;
+  b200fem_space* s = op->sp; cudaStream_t st = s->mesh->ctx->stream; const size_t bytes = sizeof(double) * (size_t)s->size;
+  double* zero_u = nullptr; double* bv = nullptr;
+  CUDA_OK(cudaMalloc(&zero_u, bytes)); CUDA_OK(cudaMalloc(&bv, bytes));
+  CUDA_OK(cudaMemsetAsync(zero_u, 0, bytes, st)); CUDA_OK(cudaMemsetAsync(bv, 0, bytes, st));
+  const int saved = op->kernel_pref; op->kernel_pref = B200FEM_KERNEL_QUADRATURE;
+  int rc = apply_local(op, zero_u, bv, /*linear=*/false);
+  op->kernel_pref = saved;
+  if (rc) { cudaFree(zero_u); cudaFree(bv); return rc; }
+  negate_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(bv, s->size);
+  CUDA_OK(cudaGetLastError()); CUDA_OK(cudaStreamSynchronize(st)); CUDA_OK(cudaFree(zero_u));
+  op->d_bvec = bv; return B200FEM_OK;
+}
+
+static int apply_dev_impl(b200fem_operator* op, const double* u, double* w, bool linear) {
+  b200fem_space* s = op->sp; cudaStream_t st = s->mesh->ctx->stream;
+  CUDA_OK(cudaSetDevice(s->mesh->ctx->device));
+  if (op->d_bvec == nullptr && !linear && op->model.data && s->kind != B200FEM_LAGRANGE) { /* built lazily inside apply_local when needed */ }
+  CUDA_OK(cudaEventRecord(op->ev0, st));
+  int rc = apply_local(op, u, w, linear); if (rc) return rc;
+  if (op->model.strong_dirichlet && op->d_dmask) {
+    dirichlet_sub_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(u, w, op->d_dmask, linear ? nullptr : op->d_dvals, s->size);
+    CUDA_OK(cudaGetLastError()); op->timing.launches_per_apply += 1;
+  }
+  if (op->communicate && s->mesh->ctx->world > 1) {
+    CUDA_OK(cudaEventRecord(op->evx0, st));
+    rc = halo_exchange(op->halo, s->mesh->ctx->nccl, s->mesh->ctx->comm, w, s->kind == B200FEM_LAGRANGE, st); if (rc) return fail(B200FEM_ERR_COMM, "halo exchange failed");
+    CUDA_OK(cudaEventRecord(op->evx1, st));
+  }
+  CUDA_OK(cudaEventRecord(op->ev1, st));
+  op->timing.applies += 1;
+  return B200FEM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+static void mark_dirichlet(b200fem_operator* op) {
+  // DirichletConstraints::updateDirichletDofs (schemes/dirichletconstraints.hh:435-554): all Lagrange nodes on boundary
+  // faces whose side is flagged; values g(x_node).  Host-side, closed form over the boundary lattice.
+  b200fem_space* s = op->sp; const BoxDev& b = s->box; const int dim = b.dim, k = s->order;
+  op->h_dmask.assign((size_t)s->size, 0); op->h_dvals.assign((size_t)s->size, 0.0);
+  LagrangeLayoutDev L = s->lay; L.lattice_map = s->lattice_map.empty() ? nullptr : s->lattice_map.data();
+  const long long L0 = L.lattice[0], L1 = L.lattice[1], L2 = L.lattice[2];
+  for (long long g2 = 0; g2 < L2; ++g2) for (long long g1 = 0; g1 < L1; ++g1) for (long long g0 = 0; g0 < L0; ++g0) {
+    const long long g[3] = {g0, g1, g2}; bool on = false;
+    for (int d = 0; d < dim; ++d) {
+      const long long gg = (long long)k * b.origin[d] + g[d];            // global lattice coordinate
+      if (gg == 0 && ((op->model.dirichlet_mask >> (2 * d)) & 1)) on = true;
+      if (gg == (long long)k * b.gn[d] && ((op->model.dirichlet_mask >> (2 * d + 1)) & 1)) on = true;
+    }
+    if (!on) continue;
+    double x[3] = {0, 0, 0}; for (int d = 0; d < dim; ++d) x[d] = b.lo[d] + b.h[d] * (b.origin[d] + (double)g[d] / k);
+    double val = 0;
+    if (op->model.data == 1) val = std::sin(x[0] * x[1]);
+    else if (op->model.data == 2) { val = 1; for (int d = 0; d < dim; ++d) val *= std::sin(M_PI * x[d]); }
+    const long long dof = lagrange_dof(L, g0, g1, g2);
+    op->h_dmask[(size_t)dof] = 1; op->h_dvals[(size_t)dof] = val;
+  }
+}
+
+extern "C" int b200fem_operator_create(b200fem_space* s, const b200fem_model* model, b200fem_operator** out) {
+  REQUIRE(s && model && out, B200FEM_ERR_INVALID, "operator_create: null argument");
+  REQUIRE(!(model->strong_dirichlet && s->kind != B200FEM_LAGRANGE), B200FEM_ERR_INVALID, "strong Dirichlet constraints need a Lagrange space");
+  CUDA_OK(cudaSetDevice(s->mesh->ctx->device));
+  auto* op = new b200fem_operator; op->sp = s; op->model = *model;
+  if (s->kind != B200FEM_LAGRANGE) {
+    CUDA_OK(cudaMalloc(&op->d_perm, sizeof(int) * s->perm.size()));
+    CUDA_OK(cudaMemcpy(op->d_perm, s->perm.data(), sizeof(int) * s->perm.size(), cudaMemcpyHostToDevice));
+  }
+  if (model->strong_dirichlet) {
+    mark_dirichlet(op);
+    CUDA_OK(cudaMalloc(&op->d_dmask, (size_t)s->size)); CUDA_OK(cudaMalloc(&op->d_dvals, sizeof(double) * (size_t)s->size));
+    CUDA_OK(cudaMemcpy(op->d_dmask, op->h_dmask.data(), (size_t)s->size, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(op->d_dvals, op->h_dvals.data(), sizeof(double) * (size_t)s->size, cudaMemcpyHostToDevice));
+  }
+  CUDA_OK(cudaEventCreate(&op->ev0)); CUDA_OK(cudaEventCreate(&op->ev1)); CUDA_OK(cudaEventCreate(&op->evx0)); CUDA_OK(cudaEventCreate(&op->evx1));
+  if (s->mesh->ctx->world > 1) {
+    int rc = halo_plan_build(op->halo, s->mesh->proc, s->mesh->pc, s->box, s->kind == B200FEM_LAGRANGE, s->kind == B200FEM_LAGRANGE ? s->order : 0, s->nb, s->lay, s->size, &op->d_aux);
+    if (rc) { delete op; return fail(B200FEM_ERR_COMM, "halo plan failed"); }
+  }
+  *out = op; return B200FEM_OK;
+}
+extern "C" int b200fem_operator_destroy(b200fem_operator* op) {
+  if (!op) return B200FEM_OK;
+  for (void* p : {(void*)op->d_perm, (void*)op->d_bvec, (void*)op->d_dmask, (void*)op->d_dvals, (void*)op->d_aux, (void*)op->d_u, (void*)op->d_w, (void*)op->d_h, (void*)op->d_r,
+                  (void*)op->d_p, (void*)op->d_x, (void*)op->d_b, (void*)op->d_partial, (void*)op->d_sums, (void*)op->d_hist, (void*)op->d_cg}) if (p) cudaFree(p);
+  halo_plan_free(op->halo);
+  for (cudaEvent_t e : {op->ev0, op->ev1, op->evx0, op->evx1}) if (e) cudaEventDestroy(e);
+  delete op; return B200FEM_OK;
+}
+static int ensure_staging(b200fem_operator* op) {
+  const size_t bytes = sizeof(double) * (size_t)op->sp->size;
+  if (!op->d_u) CUDA_OK(cudaMalloc(&op->d_u, bytes));
+  if (!op->d_w) CUDA_OK(cudaMalloc(&op->d_w, bytes));
+  return B200FEM_OK;
+}
+static int apply_host(b200fem_operator* op, const double* u, double* w, bool linear) {
+  REQUIRE(op && u && w, B200FEM_ERR_INVALID, "apply: null argument");
+  b200fem_space* s = op->sp; cudaStream_t st = s->mesh->ctx->stream; const size_t bytes = sizeof(double) * (size_t)s->size;
+  CUDA_OK(cudaSetDevice(s->mesh->ctx->device));
+  int rc = ensure_staging(op); if (rc) return rc;
+  CUDA_OK(cudaMemcpyAsync(op->d_u, u, bytes, cudaMemcpyHostToDevice, st));
+  rc = apply_dev_impl(op, op->d_u, op->d_w, linear); if (rc) return rc;
+  CUDA_OK(cudaMemcpyAsync(w, op->d_w, bytes, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  return B200FEM_OK;
+}
+extern "C" int b200fem_operator_apply(b200fem_operator* op, const double* u, double* w) { return apply_host(op, u, w, false); }
+extern "C" int b200fem_operator_apply_linear(b200fem_operator* op, const double* u, double* w) { return apply_host(op, u, w, true); }
+extern "C" int b200fem_operator_apply_dev(b200fem_operator* op, const double* u, double* w, int linear) {
+  REQUIRE(op && u && w, B200FEM_ERR_INVALID, "apply_dev: null argument"); return apply_dev_impl(op, u, w, linear != 0);
+}
+extern "C" int b200fem_operator_load_vector(b200fem_operator* op, double* b_host) {
+  REQUIRE(op && b_host, B200FEM_ERR_INVALID, "load_vector: null argument");
+  b200fem_space* s = op->sp; cudaStream_t st = s->mesh->ctx->stream; const size_t bytes = sizeof(double) * (size_t)s->size;
+  CUDA_OK(cudaSetDevice(s->mesh->ctx->device));
+  int rc = ensure_staging(op); if (rc) return rc;
+  CUDA_OK(cudaMemsetAsync(op->d_u, 0, bytes, st));
+  const int saved = op->kernel_pref; op->kernel_pref = B200FEM_KERNEL_QUADRATURE;
+  rc = apply_dev_impl(op, op->d_u, op->d_w, false); op->kernel_pref = saved; if (rc) return rc;
+  negate_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(op->d_w, s->size);
+  CUDA_OK(cudaMemcpyAsync(b_host, op->d_w, bytes, cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st));
+  return B200FEM_OK;
+}
+extern "C" int b200fem_operator_set_communicate(b200fem_operator* op, int c) { REQUIRE(op, B200FEM_ERR_INVALID, "null"); op->communicate = c != 0; return B200FEM_OK; }
+extern "C" int b200fem_operator_set_quadrature_orders(b200fem_operator* op, unsigned qi, unsigned qs) { REQUIRE(op, B200FEM_ERR_INVALID, "null"); op->q_interior = qi; op->q_surface = qs; return B200FEM_OK; }
+extern "C" int b200fem_operator_set_kernel(b200fem_operator* op, int k) { REQUIRE(op && k >= 0 && k <= 2, B200FEM_ERR_INVALID, "set_kernel: bad kernel id"); op->kernel_pref = k; return B200FEM_OK; }
+extern "C" int b200fem_operator_dirichlet(b200fem_operator* op, uint8_t* mask, double* values) {
+  REQUIRE(op && mask && values, B200FEM_ERR_INVALID, "null");
+  if (op->h_dmask.empty()) { std::fill(mask, mask + op->sp->size, 0); return B200FEM_OK; }
+  std::copy(op->h_dmask.begin(), op->h_dmask.end(), mask); std::copy(op->h_dvals.begin(), op->h_dvals.end(), values); return B200FEM_OK;
+}
+extern "C" int b200fem_operator_timing(b200fem_operator* op, b200fem_timing* out) {
+  REQUIRE(op && out, B200FEM_ERR_INVALID, "null");
+  if (op->timing.applies > 0) {
+    CUDA_OK(cudaEventSynchronize(op->ev1)); float ms = 0; CUDA_OK(cudaEventElapsedTime(&ms, op->ev0, op->ev1)); op->timing.last_apply_ms = ms;
+    if (op->communicate && op->sp->mesh->ctx->world > 1) { CUDA_OK(cudaEventElapsedTime(&ms, op->evx0, op->evx1)); op->timing.last_exchange_ms = ms; }
+  }
+  *out = op->timing; return B200FEM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// dot over primary dofs + global sum (function/common/scalarproducts.hh:115-127): two-stage device reduction,
+// then ncclAllReduce on the scalar when there is more than one rank
+static int reduce_sums(b200fem_operator* op, int count) {
+  b200fem_ctx* c = op->sp->mesh->ctx;
+  for (int i = 0; i < count; ++i) reduce_final_kernel<<<1, kRedThreads, 0, c->stream>>>(op->d_partial + (size_t)i * kRedBlocks, kRedBlocks, op->d_sums + i);
+  CUDA_OK(cudaGetLastError());
+  if (c->world > 1) { if (c->nccl.AllReduce(op->d_sums, op->d_sums, (size_t)count, /*ncclDouble*/ 8, /*ncclSum*/ 0, c->comm, c->stream) != 0) return fail(B200FEM_ERR_COMM, "ncclAllReduce failed"); }
+  return B200FEM_OK;
+}
+static int ensure_cg_buffers(b200fem_operator* op, int maxit) {
+  const size_t bytes = sizeof(double) * (size_t)op->sp->size;
+  if (!op->d_h) { CUDA_OK(cudaMalloc(&op->d_h, bytes)); CUDA_OK(cudaMalloc(&op->d_r, bytes)); CUDA_OK(cudaMalloc(&op->d_p, bytes)); }
+  if (!op->d_partial) { CUDA_OK(cudaMalloc(&op->d_partial, sizeof(double) * 2 * kRedBlocks)); CUDA_OK(cudaMalloc(&op->d_sums, sizeof(double) * 4)); CUDA_OK(cudaMalloc(&op->d_cg, sizeof(CgState))); }
+  if (maxit > op->hist_cap) { if (op->d_hist) cudaFree(op->d_hist); CUDA_OK(cudaMalloc(&op->d_hist, sizeof(double) * (size_t)std::max(maxit, 1))); op->hist_cap = std::max(maxit, 1); }
+  return B200FEM_OK;
+}
+extern "C" int b200fem_dot_dev(b200fem_operator* op, const double* x, const double* y, double* result) {
+  REQUIRE(op && x && y && result, B200FEM_ERR_INVALID, "dot: null argument");
+  b200fem_ctx* c = op->sp->mesh->ctx; CUDA_OK(cudaSetDevice(c->device));
+  int rc = ensure_cg_buffers(op, 1); if (rc) return rc;
+  dot_partial_kernel<<<kRedBlocks, kRedThreads, 0, c->stream>>>(x, y, op->d_aux, op->sp->size, op->d_partial);
+  rc = reduce_sums(op, 1); if (rc) return rc;
+  CUDA_OK(cudaMemcpyAsync(result, op->d_sums, sizeof(double), cudaMemcpyDeviceToHost, c->stream)); CUDA_OK(cudaStreamSynchronize(c->stream));
+  return B200FEM_OK;
+}
+extern "C" int b200fem_axpy_dev(b200fem_operator* op, double alpha, const double* x, double* y) {
+  REQUIRE(op && x && y, B200FEM_ERR_INVALID, "axpy: null argument");
+  axpy_kernel<<<kRedBlocks, kRedThreads, 0, op->sp->mesh->ctx->stream>>>(alpha, x, y, op->sp->size); CUDA_OK(cudaGetLastError()); return B200FEM_OK;
+}
+
+// LinearSolver::cg (solver/linear/cg.hh:18-117), unpreconditioned, on the homogeneous linear part of the operator
+extern "C" int b200fem_cg_solve_dev(b200fem_operator* op, const double* b, double* x, double epsilon, int maxit, int tolcrit, int* iterations, double* history) {
+  REQUIRE(op && b && x && iterations, B200FEM_ERR_INVALID, "cg: null argument");
+  REQUIRE(tolcrit >= 0 && tolcrit <= 2, B200FEM_ERR_INVALID, "cg: unknown tolerance criterion");
+  b200fem_space* s = op->sp; b200fem_ctx* c = s->mesh->ctx; cudaStream_t st = c->stream; const long long n = s->size;
+  CUDA_OK(cudaSetDevice(c->device));
+  int rc = ensure_cg_buffers(op, maxit); if (rc) return rc;
+  CgState init{}; init.epsilon = epsilon; init.max_iterations = maxit; init.tol_criteria = tolcrit;
+  CUDA_OK(cudaMemcpyAsync(op->d_cg, &init, sizeof(CgState), cudaMemcpyHostToDevice, st));
+  rc = apply_dev_impl(op, x, op->d_h, true); if (rc) return rc;                                              // h = A x
+  cg_init_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(op->d_h, b, op->d_r, op->d_p, op->d_aux, n, op->d_partial, op->d_partial + kRedBlocks);
+  rc = reduce_sums(op, 2); if (rc) return rc;
+  cg_init_final_kernel<<<1, 32, 0, st>>>(op->d_sums, op->d_cg);
+  CgState host{}; const int chunk = 16;
+  for (int it = 0; it < maxit;) {
+    const int upto = std::min(maxit, it + chunk);
+    for (; it < upto; ++it) {
+      if (it > 0) cg_update_p_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(op->d_p, op->d_r, n, op->d_cg);
+      rc = apply_dev_impl(op, op->d_p, op->d_h, true); if (rc) return rc;                                     // h = A q
+      cg_dot_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(op->d_p, op->d_h, op->d_aux, n, op->d_partial, op->d_cg);
+      rc = reduce_sums(op, 1); if (rc) return rc;
+      cg_alpha_kernel<<<1, 32, 0, st>>>(op->d_sums, op->d_cg);
+      cg_update_xr_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(x, op->d_r, op->d_p, op->d_h, op->d_aux, n, op->d_partial, op->d_cg);
+      rc = reduce_sums(op, 1); if (rc) return rc;
+      cg_residual_kernel<<<1, 32, 0, st>>>(op->d_sums, op->d_cg, op->d_hist);
+    }
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpyAsync(&host, op->d_cg, sizeof(CgState), cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st));
+    if (host.done) break;
+  }
+  if (maxit <= 0) { CUDA_OK(cudaMemcpyAsync(&host, op->d_cg, sizeof(CgState), cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st)); }
+  REQUIRE(std::isfinite(host.residual), B200FEM_ERR_INVALID, "cg: residual is not finite (alpha/beta NaN, cf. cg.hh:74,91)");
+  if (history && host.iterations > 0) { CUDA_OK(cudaMemcpyAsync(history, op->d_hist, sizeof(double) * host.iterations, cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st)); }
+  *iterations = (host.iterations < maxit) ? host.iterations : -host.iterations;                                // cg.hh:116
+  return B200FEM_OK;
+}
+extern "C" int b200fem_cg_solve(b200fem_operator* op, const double* b_host, double* x_host, double epsilon, int maxit, int tolcrit, int* iterations, double* history) {
+  REQUIRE(op && b_host && x_host && iterations, B200FEM_ERR_INVALID, "cg: null argument");
+  b200fem_space* s = op->sp; cudaStream_t st = s->mesh->ctx->stream; const size_t bytes = sizeof(double) * (size_t)s->size;
+  CUDA_OK(cudaSetDevice(s->mesh->ctx->device));
+  if (!op->d_x) { CUDA_OK(cudaMalloc(&op->d_x, bytes)); CUDA_OK(cudaMalloc(&op->d_b, bytes)); }
+  CUDA_OK(cudaMemcpyAsync(op->d_x, x_host, bytes, cudaMemcpyHostToDevice, st)); CUDA_OK(cudaMemcpyAsync(op->d_b, b_host, bytes, cudaMemcpyHostToDevice, st));
+  int rc = b200fem_cg_solve_dev(op, op->d_b, op->d_x, epsilon, maxit, tolcrit, iterations, history); if (rc) return rc;
+  CUDA_OK(cudaMemcpyAsync(x_host, op->d_x, bytes, cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st));
+  return B200FEM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int b200fem_ctx_set_nccl(b200fem_ctx* c, void* comm, int rank, int world) {
+  REQUIRE(c && comm, B200FEM_ERR_INVALID, "set_nccl: null argument");
+  if (!c->nccl.load()) return fail(B200FEM_ERR_COMM, "libnccl.so.2 not loadable");
+  c->comm = comm; c->own_comm = false; c->rank = rank; c->world = world; return B200FEM_OK;
+}
+extern "C" int b200fem_nccl_unique_id(void* out128) {
+  REQUIRE(out128, B200FEM_ERR_INVALID, "null"); NcclApi api; if (!api.load()) return fail(B200FEM_ERR_COMM, "libnccl.so.2 not loadable");
+  if (api.GetUniqueId(out128) != 0) return fail(B200FEM_ERR_COMM, "ncclGetUniqueId failed"); return B200FEM_OK;
+}
+extern "C" int b200fem_nccl_init(b200fem_ctx* c, const void* id128, int rank, int world) {
+  REQUIRE(c && id128, B200FEM_ERR_INVALID, "nccl_init: null argument");
+  if (!c->nccl.load()) return fail(B200FEM_ERR_COMM, "libnccl.so.2 not loadable");
+  CUDA_OK(cudaSetDevice(c->device));
+  NcclUniqueId id; std::memcpy(&id, id128, 128);
+  if (c->nccl.CommInitRank(&c->comm, world, id, rank) != 0) return fail(B200FEM_ERR_COMM, "ncclCommInitRank failed");
+  c->own_comm = true; c->rank = rank; c->world = world; return B200FEM_OK;
+}
+extern "C" int b200fem_communicate_dev(b200fem_operator* op, double* v) {
+  REQUIRE(op && v, B200FEM_ERR_INVALID, "communicate: null argument");
+  b200fem_ctx* c = op->sp->mesh->ctx; if (c->world <= 1) return B200FEM_OK;
+  if (halo_exchange(op->halo, c->nccl, c->comm, v, op->sp->kind == B200FEM_LAGRANGE, c->stream) != 0) return fail(B200FEM_ERR_COMM, "halo exchange failed");
+  return B200FEM_OK;
+}

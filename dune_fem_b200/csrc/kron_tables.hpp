@@ -1,0 +1,61 @@
+// kron_tables.hpp -- 1-D operator matrices of the Kronecker (constant-coefficient, uniform box) form of the
+// SIPG/upwind advection-diffusion-reaction operator.  Built from the same 1-D tabulations and Gauss weights the
+// quadrature kernel uses, i.e. every entry is the quadrature sum the reference would compute
+// (dune/fem/schemes/galerkin.hh:332-360, 475-537 with the integrands of pydemo/advectiondiffusion.py:33-60),
+// factored along the axes.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <vector>
+#include "../../include/b200fem.h"
+#include "tables.hpp"
+
+namespace b200fem {
+
+struct KronHost {
+  int n = 0;
+  std::vector<double> S[3], Dlo[3], Dhi[3], L[3], R[3];   // n*n each, row = test index, col = trial index
+};
+
+inline KronHost build_kron_tables(const Tab1D& t, const b200fem_model& m, int dim, const double* h) {
+  KronHost k; const int n = t.n; k.n = n;
+  double detJ = 1; for (int d = 0; d < dim; ++d) detJ *= h[d];
+  // 1-D quadrature matrices
+  std::vector<double> K1(n * n, 0.0), C1(n * n, 0.0);
+  for (int q = 0; q < t.m; ++q) for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) {
+    K1[i * n + j] += t.w[q] * t.G[q * n + i] * t.G[q * n + j];
+    C1[i * n + j] += t.w[q] * t.G[q * n + i] * t.B[q * n + j];
+  }
+  for (int d = 0; d < 3; ++d) {
+    k.S[d].assign(n * n, 0.0); k.Dlo[d].assign(n * n, 0.0); k.Dhi[d].assign(n * n, 0.0); k.L[d].assign(n * n, 0.0); k.R[d].assign(n * n, 0.0);
+    if (d >= dim) continue;
+    const double hd = h[d], area = detJ / hd;
+    const double pen = m.eps * m.beta / hd, e2 = m.eps / (2 * hd);
+    const double hbp = std::max(m.b[d], 0.0), hbm = std::max(-m.b[d], 0.0);
+    for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) {
+      const double p0i = t.phi0[i], p1i = t.phi1[i], d0i = t.dphi0[i], d1i = t.dphi1[i];
+      const double p0j = t.phi0[j], p1j = t.phi1[j], d0j = t.dphi0[j], d1j = t.dphi1[j];
+      double vol = detJ * (m.eps / (hd * hd) * K1[i * n + j] - m.b[d] / hd * C1[i * n + j]);
+      if (d == 0 && i == j) vol += m.c * detJ;
+      double HH = 0, LL = 0, Lm = 0, Rm = 0, BH = 0, BL = 0;
+      if (m.has_skeleton) {
+        HH = area * ((pen + hbp) * p1i * p1j - e2 * p1i * d1j - e2 * d1i * p1j);
+        Rm = area * (-(pen + hbm) * p1i * p0j - e2 * p1i * d0j + e2 * d1i * p0j);
+        Lm = area * (-(pen + hbp) * p0i * p1j + e2 * p0i * d1j - e2 * d0i * p1j);
+        LL = area * ((pen + hbm) * p0i * p0j + e2 * p0i * d0j + e2 * d0i * p0j);
+      }
+      if (m.has_boundary) {
+        if ((m.dirichlet_mask >> (2 * d + 1)) & 1) BH = area * (pen + hbp) * p1i * p1j;
+        if ((m.dirichlet_mask >> (2 * d)) & 1)     BL = area * (pen + hbm) * p0i * p0j;
+      }
+      k.S[d][i * n + j] = vol + HH + LL;
+      k.Dhi[d][i * n + j] = BH - HH;
+      k.Dlo[d][i * n + j] = BL - LL;
+      k.L[d][i * n + j] = Lm;
+      k.R[d][i * n + j] = Rm;
+    }
+  }
+  return k;
+}
+
+}  // namespace b200fem

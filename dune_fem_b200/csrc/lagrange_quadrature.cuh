@@ -1,0 +1,186 @@
+// lagrange_quadrature.cuh -- generic matrix-free apply for continuous Lagrange Q_k spaces (k = 1, 2) on cubes.
+//
+// Same per-element work as the DG kernel (element_integrals), but local->global maps follow
+// IndexSetDofMapper::mapEach (dune/fem/space/mapper/indexsetdofmapper.hh:414-427): dof blocks ordered by geometry
+// type (vertices, edges, faces, cells; :504-515), index inside a block = indexSet.subIndex.  On a Cartesian box the
+// YaspGrid index is closed-form, so no index arrays are read; the AdaptiveLeafIndexSet numbering
+// (gridpart/adaptiveleafindexset.hh:884-906) uses a precomputed lattice->dof table instead.
+//
+// Scatter: the reference guards addLocalDofs with a shared_mutex (galerkin.hh:963-991).  Here elements are split
+// into 2^dim colours (parity of the element coordinates); elements of one colour share no dof, so each colour is
+// one launch doing plain read-modify-write -- deterministic, no atomics (colour order = summation order).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "dg_quadrature.cuh"
+
+namespace b200fem {
+
+struct LagrangeLayoutDev {
+  int order;                        // 1 or 2
+  long long group_offset[8];        // per "shift" bit set (directions the sub-entity extends in)
+  long long group_dims[8][3];
+  long long lattice[3];             // lattice extents k*n+1
+  const long long* lattice_map;     // optional: lattice index -> dof (adaptive-leaf numbering), else null
+};
+
+__host__ __device__ inline long long lagrange_dof(const LagrangeLayoutDev& L, const long long g0, const long long g1, const long long g2) {
+  if (L.lattice_map) return L.lattice_map[g0 + L.lattice[0] * (g1 + L.lattice[1] * g2)];
+  int s = 0; long long c0 = g0, c1 = g1, c2 = g2;
+  if (L.order == 2) { s = (int)(g0 & 1) | ((int)(g1 & 1) << 1) | ((int)(g2 & 1) << 2); c0 >>= 1; c1 >>= 1; c2 >>= 1; }
+  return L.group_offset[s] + c0 + L.group_dims[s][0] * (c1 + L.group_dims[s][1] * c2);
+}
+
+// ------------------------------------------------------------------ 3-D: N*N threads per element, shared-memory tensors
+template <int N, class Integrands>
+__global__ void __launch_bounds__(DgQuadCfg<N>::kThreads)
+lagrange3d_quadrature_kernel(const __grid_constant__ DgTabDev<N> T, const __grid_constant__ BoxDev box,
+                             const __grid_constant__ Integrands I, const __grid_constant__ LagrangeLayoutDev L,
+                             const double* __restrict__ u, double* __restrict__ w,
+                             int c0, int c1, int c2, int m0, int m1, long long n_colour) {
+  using Cfg = DgQuadCfg<N>;
+  constexpr int N2 = Cfg::N2, N3 = Cfg::N3, EB = Cfg::EB, ELEM = Cfg::kElemDoubles;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* smem = reinterpret_cast<double*>(smem_raw);
+  int* ecs = reinterpret_cast<int*>(smem + (size_t)EB * ELEM);       // 4 ints per slot: coords + active flag
+
+  const int tid = threadIdx.x, es = tid / N2, lt = tid % N2;
+  const long long oe = (long long)blockIdx.x * EB + es;
+  const bool active = oe < n_colour;
+  int lc[3] = {0, 0, 0};
+  if (active) {
+    lc[0] = box.own_lo[0] + 2 * (int)(oe % m0) + c0;
+    lc[1] = box.own_lo[1] + 2 * (int)((oe / m0) % m1) + c1;
+    lc[2] = box.own_lo[2] + 2 * (int)(oe / ((long long)m0 * m1)) + c2;
+  }
+  const long long e = lc[0] + (long long)box.n[0] * (lc[1] + (long long)box.n[1] * lc[2]);
+  if (lt == 0) { ecs[4 * es] = lc[0]; ecs[4 * es + 1] = lc[1]; ecs[4 * es + 2] = lc[2]; ecs[4 * es + 3] = active; }
+  __syncthreads();
+  const int k = N - 1;
+  for (int idx = tid; idx < EB * N3; idx += blockDim.x) {            // gather (getLocalDofs)
+    const int s2 = idx / N3, t = idx % N3;
+    if (ecs[4 * s2 + 3]) {
+      const int i0 = t / N2, i1 = (t / N) % N, i2 = t % N;
+      smem[(size_t)s2 * ELEM + t] = u[lagrange_dof(L, (long long)k * ecs[4 * s2] + i0, (long long)k * ecs[4 * s2 + 1] + i1, (long long)k * ecs[4 * s2 + 2] + i2)];
+    }
+  }
+  __syncthreads();
+  double* U = smem + (size_t)es * ELEM;
+  element_integrals<N, Integrands>(T, box, I, nullptr, u, active, lc, e, lt, U, U + N3, U + 2 * N3);
+  for (int idx = tid; idx < EB * N3; idx += blockDim.x) {            // coloured scatter-add (addLocalDofs)
+    const int s2 = idx / N3, t = idx % N3;
+    if (ecs[4 * s2 + 3]) {
+      const int i0 = t / N2, i1 = (t / N) % N, i2 = t % N;
+      const long long g = lagrange_dof(L, (long long)k * ecs[4 * s2] + i0, (long long)k * ecs[4 * s2 + 1] + i1, (long long)k * ecs[4 * s2 + 2] + i2);
+      w[g] += smem[(size_t)s2 * ELEM + N3 + t];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ 2-D: one thread per element, registers only
+template <int N, class Integrands>
+__global__ void __launch_bounds__(128)
+lagrange2d_quadrature_kernel(const __grid_constant__ DgTabDev<N> T, const __grid_constant__ BoxDev box,
+                             const __grid_constant__ Integrands I, const __grid_constant__ LagrangeLayoutDev L,
+                             const double* __restrict__ u, double* __restrict__ w, int c0, int c1, int m0, long long n_colour) {
+  const long long oe = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (oe >= n_colour) return;
+  constexpr int k = N - 1;
+  const int lc[2] = {box.own_lo[0] + 2 * (int)(oe % m0) + c0, box.own_lo[1] + 2 * (int)(oe / m0) + c1};
+  const double hh[2] = {box.h[0], box.h[1]};
+  const double detJ = hh[0] * hh[1];
+  double ul[N][N], wl[N][N];            // [i1][i0]
+  long long dof[N][N];
+#pragma unroll
+  for (int i1 = 0; i1 < N; ++i1)
+#pragma unroll
+    for (int i0 = 0; i0 < N; ++i0) { dof[i1][i0] = lagrange_dof(L, (long long)k * lc[0] + i0, (long long)k * lc[1] + i1, 0); ul[i1][i0] = u[dof[i1][i0]]; wl[i1][i0] = 0; }
+
+  // interior integral (galerkin.hh:332-360), sum-factorised in registers
+  double tb[N][N], tg[N][N];            // [q0][i1]
+#pragma unroll
+  for (int q0 = 0; q0 < N; ++q0)
+#pragma unroll
+    for (int i1 = 0; i1 < N; ++i1) { double a = 0, b = 0;
+#pragma unroll
+      for (int i0 = 0; i0 < N; ++i0) { a = fma(T.B[q0 * N + i0], ul[i1][i0], a); b = fma(T.G[q0 * N + i0], ul[i1][i0], b); }
+      tb[q0][i1] = a; tg[q0][i1] = b; }
+  double zs[N][N], zx[N][N], zy[N][N];  // [q0][i1] after testing along axis 1
+#pragma unroll
+  for (int q0 = 0; q0 < N; ++q0) {
+    double rs[N], rx[N], ry[N];
+#pragma unroll
+    for (int q1 = 0; q1 < N; ++q1) {
+      PointValue pv; pv.u = 0; pv.du[0] = pv.du[1] = pv.du[2] = 0;
+#pragma unroll
+      for (int i1 = 0; i1 < N; ++i1) { pv.u = fma(T.B[q1 * N + i1], tb[q0][i1], pv.u); pv.du[0] = fma(T.B[q1 * N + i1], tg[q0][i1], pv.du[0]); pv.du[1] = fma(T.G[q1 * N + i1], tb[q0][i1], pv.du[1]); }
+      pv.du[0] /= hh[0]; pv.du[1] /= hh[1];
+      double xq[3] = {box.lo[0] + hh[0] * ((box.origin[0] + lc[0]) + T.x[q0]), box.lo[1] + hh[1] * ((box.origin[1] + lc[1]) + T.x[q1]), 0.0};
+      PointRange r = I.interior(xq, pv);
+      const double wq = T.w[q0] * T.w[q1] * detJ;
+      rs[q1] = r.s * wq; rx[q1] = r.F[0] * wq / hh[0]; ry[q1] = r.F[1] * wq / hh[1];
+    }
+#pragma unroll
+    for (int i1 = 0; i1 < N; ++i1) { double a = 0, b = 0;
+#pragma unroll
+      for (int q1 = 0; q1 < N; ++q1) { a = fma(T.B[q1 * N + i1], rs[q1], a); a = fma(T.G[q1 * N + i1], ry[q1], a); b = fma(T.B[q1 * N + i1], rx[q1], b); }
+      zs[q0][i1] = a; zx[q0][i1] = b; }
+  }
+#pragma unroll
+  for (int i1 = 0; i1 < N; ++i1)
+#pragma unroll
+    for (int i0 = 0; i0 < N; ++i0) { double a = 0;
+#pragma unroll
+      for (int q0 = 0; q0 < N; ++q0) { a = fma(T.B[q0 * N + i0], zs[q0][i1], a); a = fma(T.G[q0 * N + i0], zx[q0][i1], a); }
+      wl[i1][i0] += a; }
+  (void)zy;
+
+  // boundary integrals (galerkin.hh:414-435) on domain-boundary edges
+  if (I.m.has_boundary) {
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      const int d = f >> 1, s = f & 1, a = 1 - d;
+      const int gc = box.origin[d] + lc[d];
+      if ((s == 0 && gc != 0) || (s == 1 && gc != box.gn[d] - 1)) continue;
+      double tv[N], td[N];               // trace coefficients along the edge (index along axis a)
+#pragma unroll
+      for (int ia = 0; ia < N; ++ia) { double v = 0, dv = 0;
+#pragma unroll
+        for (int id = 0; id < N; ++id) { const double uu = d == 0 ? ul[ia][id] : ul[id][ia]; v = fma(T.phi[s][id], uu, v); dv = fma(T.dphi[s][id], uu, dv); }
+        tv[ia] = v; td[ia] = dv; }
+      const double area = detJ / hh[d];
+      double rv[N], rd[N];
+#pragma unroll
+      for (int ia = 0; ia < N; ++ia) rv[ia] = rd[ia] = 0;
+#pragma unroll
+      for (int q = 0; q < N; ++q) {
+        PointValue pv; pv.u = 0; pv.du[0] = pv.du[1] = pv.du[2] = 0; double dn = 0, dt = 0;
+#pragma unroll
+        for (int ia = 0; ia < N; ++ia) { pv.u = fma(T.B[q * N + ia], tv[ia], pv.u); dn = fma(T.B[q * N + ia], td[ia], dn); dt = fma(T.G[q * N + ia], tv[ia], dt); }
+        pv.du[d] = dn / hh[d]; pv.du[a] = dt / hh[a];
+        double xq[3] = {0, 0, 0};
+        xq[d] = box.lo[d] + hh[d] * (gc + s); xq[a] = box.lo[a] + hh[a] * ((box.origin[a] + lc[a]) + T.x[q]);
+        PointRange r = I.boundary(d, s, hh[d], xq, pv);
+        const double wq = T.w[q] * area;
+#pragma unroll
+        for (int ia = 0; ia < N; ++ia) {
+          rv[ia] = fma(T.B[q * N + ia], r.s * wq, rv[ia]); rv[ia] = fma(T.G[q * N + ia], r.F[a] * wq / hh[a], rv[ia]);
+          rd[ia] = fma(T.B[q * N + ia], r.F[d] * wq / hh[d], rd[ia]);
+        }
+      }
+#pragma unroll
+      for (int ia = 0; ia < N; ++ia)
+#pragma unroll
+        for (int id = 0; id < N; ++id) {
+          const double add = T.phi[s][id] * rv[ia] + T.dphi[s][id] * rd[ia];
+          if (d == 0) wl[ia][id] += add; else wl[id][ia] += add;
+        }
+    }
+  }
+#pragma unroll
+  for (int i1 = 0; i1 < N; ++i1)
+#pragma unroll
+    for (int i0 = 0; i0 < N; ++i0) w[dof[i1][i0]] += wl[i1][i0];
+}
+
+}  // namespace b200fem

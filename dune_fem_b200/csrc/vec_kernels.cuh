@@ -1,0 +1,139 @@
+// vec_kernels.cuh -- BLAS-1 and the CG recurrence on device dof vectors.
+//
+// Restates solver/linear/cg.hh:18-117 (sign conventions r = Ax - b, p = b - Ax, p <- beta p - r) with the vector
+// sweeps of function/blockvectors/defaultblockvectors.hh:39-150 fused: per iteration the reference makes ~9 sweeps
+// (128 B/dof); here it is  [p <- beta p - r] , [h = A p] , [<p,h>] , [x += a p ; r += a h ; <r,r>]  with all scalars
+// (alpha, beta, residual, convergence flag, iteration count) resident on the device so that the loop needs no
+// host round trip.  Dot products are two-stage, fixed-grid reductions with warp shuffles: deterministic.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace b200fem {
+
+constexpr int kRedBlocks = 592;     // 4 per SM on 148 SMs
+constexpr int kRedThreads = 256;
+
+// device-resident CG state
+struct CgState {
+  double residual, prev_residual, qdoth, alpha, beta, tolerance, bnorm2;
+  int iterations, done, max_iterations, tol_criteria;
+  double epsilon;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double block_sum(double v) {
+  __shared__ double part[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) part[wid] = v;
+  __syncthreads();
+  v = (threadIdx.x < (blockDim.x >> 5)) ? part[threadIdx.x] : 0.0;
+  if (wid == 0) v = warp_sum(v);
+  return v;    // valid in thread 0
+}
+
+// partial[b] = sum over this block's grid-stride range of x*y restricted to primary dofs (mask may be null)
+__global__ void __launch_bounds__(kRedThreads) dot_partial_kernel(const double* __restrict__ x, const double* __restrict__ y,
+                                                                  const uint8_t* __restrict__ aux, long long n, double* __restrict__ partial) {
+  double s = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    if (!aux || !aux[i]) s = fma(x[i], y[i], s);
+  s = block_sum(s);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+__global__ void __launch_bounds__(kRedThreads) reduce_final_kernel(const double* __restrict__ partial, int nparts, double* __restrict__ out) {
+  double s = 0;
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) s += partial[i];
+  s = block_sum(s);
+  if (threadIdx.x == 0) *out = s;
+}
+__global__ void axpy_kernel(double alpha, const double* __restrict__ x, double* __restrict__ y, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] = fma(alpha, x[i], y[i]);
+}
+__global__ void negate_kernel(double* __restrict__ x, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) x[i] = -x[i];
+}
+
+// ---- CG pieces ----
+// r = h - b ; p = b - h ; partial <p,p>          (cg.hh:39-60)
+__global__ void __launch_bounds__(kRedThreads) cg_init_kernel(const double* __restrict__ h, const double* __restrict__ b, double* __restrict__ r,
+                                                              double* __restrict__ p, const uint8_t* __restrict__ aux, long long n,
+                                                              double* __restrict__ partial, double* __restrict__ partial_b) {
+  double s = 0, sb = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double hv = h[i], bv = b[i];
+    r[i] = hv - bv; const double pv = bv - hv; p[i] = pv;
+    if (!aux || !aux[i]) { s = fma(pv, pv, s); sb = fma(bv, bv, sb); }
+  }
+  s = block_sum(s); if (threadIdx.x == 0) partial[blockIdx.x] = s;
+  sb = block_sum(sb); if (threadIdx.x == 0) partial_b[blockIdx.x] = sb;
+}
+// residual = sum partial ; tolerance = eps^2 * {1 | <b,b> | residual}     (cg.hh:60-67). sums[0..1] hold the
+// (already globally reduced) values.
+__global__ void cg_init_final_kernel(const double* __restrict__ sums, CgState* st) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    st->residual = sums[0]; st->bnorm2 = sums[1]; st->prev_residual = 0;
+    const double scale = st->tol_criteria == 1 ? sums[1] : st->tol_criteria == 2 ? sums[0] : 1.0;
+    st->tolerance = st->epsilon * st->epsilon * scale;
+    st->iterations = 0;
+    st->done = !(st->residual > st->tolerance) || st->max_iterations <= 0;
+  }
+}
+// p <- beta p - r, beta = residual / prevResidual       (cg.hh:72-85, unpreconditioned: q aliases p)
+__global__ void cg_update_p_kernel(double* __restrict__ p, const double* __restrict__ r, long long n, const CgState* st) {
+  if (st->done) return;
+  const double beta = st->residual / st->prev_residual;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = p[i] * beta - r[i];
+}
+__global__ void __launch_bounds__(kRedThreads) cg_dot_kernel(const double* __restrict__ x, const double* __restrict__ y, const uint8_t* __restrict__ aux,
+                                                             long long n, double* __restrict__ partial, const CgState* st) {
+  if (st->done) return;
+  double s = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    if (!aux || !aux[i]) s = fma(x[i], y[i], s);
+  s = block_sum(s);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+// sums[0] = <q,h> (globally reduced): alpha = residual / <q,h>          (cg.hh:89-90)
+__global__ void cg_alpha_kernel(const double* __restrict__ sums, CgState* st) {
+  if (threadIdx.x == 0 && blockIdx.x == 0 && !st->done) { st->qdoth = sums[0]; st->alpha = st->residual / sums[0]; }
+}
+// x += alpha q ; r += alpha h ; partial <r,r>                              (cg.hh:92, 103-107)
+__global__ void __launch_bounds__(kRedThreads) cg_update_xr_kernel(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
+                                                                   const double* __restrict__ h, const uint8_t* __restrict__ aux, long long n,
+                                                                   double* __restrict__ partial, const CgState* st) {
+  if (st->done) return;
+  const double alpha = st->alpha;
+  double s = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    x[i] = fma(alpha, p[i], x[i]);
+    const double rv = fma(alpha, h[i], r[i]); r[i] = rv;
+    if (!aux || !aux[i]) s = fma(rv, rv, s);
+  }
+  s = block_sum(s);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+// prev = residual ; residual = <r,r> ; ++iterations ; convergence test     (cg.hh:70, 106-107, 116)
+__global__ void cg_residual_kernel(const double* __restrict__ sums, CgState* st, double* __restrict__ history) {
+  if (threadIdx.x == 0 && blockIdx.x == 0 && !st->done) {
+    st->prev_residual = st->residual; st->residual = sums[0];
+    if (history) history[st->iterations] = sqrt(sums[0]);
+    st->iterations += 1;
+    if (!(st->residual > st->tolerance) || st->iterations >= st->max_iterations) st->done = 1;
+  }
+}
+
+// strong Dirichlet rows: w_d = u_d - g_d   (schemes/dirichletwrapper.hh:101-105; Operation::sub)
+__global__ void dirichlet_sub_kernel(const double* __restrict__ u, double* __restrict__ w, const uint8_t* __restrict__ mask,
+                                     const double* __restrict__ g, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    if (mask[i]) w[i] = u[i] - (g ? g[i] : 0.0);
+}
+
+}  // namespace b200fem

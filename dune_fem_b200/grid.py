@@ -1,0 +1,59 @@
+"""Grid views.  Mirrors dune.grid.structuredGrid(lo, hi, n) (YaspGrid) as used by pydemo/advectiondiffusion.py:113."""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi as capi
+
+
+class Context:
+    """Device context (one per process and GPU).  stream: optional cudaStream_t as int (e.g. torch stream)."""
+    _default = {}
+
+    def __init__(self, device=0, stream=None):
+        self.handle = C.c_void_p()
+        capi.check(capi.lib().b200fem_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(self.handle)))
+        self.device = device
+        self.rank, self.world = 0, 1
+
+    @classmethod
+    def default(cls, device=0):
+        if device not in cls._default:
+            cls._default[device] = Context(device)
+        return cls._default[device]
+
+    def synchronize(self):
+        capi.check(capi.lib().b200fem_ctx_synchronize(self.handle))
+
+    def init_nccl(self, unique_id: bytes, rank: int, world: int):
+        buf = C.create_string_buffer(unique_id, 128)
+        capi.check(capi.lib().b200fem_nccl_init(self.handle, buf, rank, world))
+        self.rank, self.world = rank, world
+
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        capi.check(capi.lib().b200fem_nccl_unique_id(buf))
+        return buf.raw
+
+
+class GridView:
+    def __init__(self, lo, hi, n, ctx=None, proc=None, rank=0):
+        self.ctx = ctx or Context.default()
+        self.dim = len(n)
+        self.n, self.lo, self.hi = list(n), list(lo), list(hi)
+        n_a = (C.c_int32 * 3)(*(list(n) + [1] * (3 - self.dim)))
+        lo_a = (C.c_double * 3)(*(list(lo) + [0.0] * (3 - self.dim)))
+        hi_a = (C.c_double * 3)(*(list(hi) + [1.0] * (3 - self.dim)))
+        self.handle = C.c_void_p()
+        if proc is None:
+            capi.check(capi.lib().b200fem_mesh_cartesian(self.ctx.handle, self.dim, n_a, lo_a, hi_a, C.byref(self.handle)))
+        else:
+            p_a = (C.c_int32 * 3)(*(list(proc) + [1] * (3 - len(proc))))
+            capi.check(capi.lib().b200fem_mesh_cartesian_distributed(self.ctx.handle, self.dim, n_a, lo_a, hi_a, p_a, rank,
+                                                                     C.byref(self.handle)))
+        self.proc, self.rank = proc, rank
+
+
+def structuredGrid(lo, hi, n, ctx=None, proc=None, rank=0):
+    return GridView(lo, hi, n, ctx=ctx, proc=proc, rank=rank)

@@ -1,0 +1,82 @@
+"""Galerkin operators.  Mirrors dune.fem.operator.galerkin (python/dune/fem/operator/__init__.py:77-207) and the C++
+Dune::Fem::GalerkinOperator interface it registers (dune/fempy/py/operator.hh:207-280): __call__(u, w),
+setCommunicate, setQuadratureOrders, plus the affine shift b = -L[0] (:347-350)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi as capi
+
+
+class GalerkinOperator:
+    def __init__(self, space, eps=1.0, b=(0.0, 0.0, 0.0), c=0.0, gamma=0.0, beta=None, dirichlet_mask=0, data=0,
+                 skeleton=None, boundary=None, strong_dirichlet=False, kernel=capi.KERNEL_AUTO):
+        self.space = space
+        is_dg = space.kind != capi.LAGRANGE
+        m = capi.Model()
+        m.eps = eps
+        bb = list(b) + [0.0] * (3 - len(b))
+        m.b[0], m.b[1], m.b[2] = bb
+        m.c, m.gamma = c, gamma
+        m.beta = 20.0 * space.order ** 2 if beta is None else beta     # pydemo/advectiondiffusion.py:41
+        m.dirichlet_mask, m.data = dirichlet_mask, data
+        m.has_skeleton = int(is_dg if skeleton is None else skeleton)
+        m.has_boundary = int(is_dg if boundary is None else boundary)
+        m.strong_dirichlet = int(strong_dirichlet)
+        self.model = m
+        self.handle = C.c_void_p()
+        capi.check(capi.lib().b200fem_operator_create(space.handle, C.byref(m), C.byref(self.handle)))
+        if kernel != capi.KERNEL_AUTO:
+            self.setKernel(kernel)
+
+    # --- Dune::Fem::Operator interface (operator/common/operator.hh:55) ---
+    def __call__(self, u, w):
+        capi.check(capi.lib().b200fem_operator_apply(self.handle, capi.ptr(u), capi.ptr(w)))
+
+    def applyLinear(self, u, w):
+        capi.check(capi.lib().b200fem_operator_apply_linear(self.handle, capi.ptr(u), capi.ptr(w)))
+
+    def apply_dev(self, u_ptr, w_ptr, linear=False):
+        capi.check(capi.lib().b200fem_operator_apply_dev(self.handle, C.c_void_p(u_ptr), C.c_void_p(w_ptr), int(linear)))
+
+    def loadVector(self):
+        bvec = np.empty(self.space.size)
+        capi.check(capi.lib().b200fem_operator_load_vector(self.handle, capi.ptr(bvec)))
+        return bvec
+
+    def setCommunicate(self, communicate):
+        capi.check(capi.lib().b200fem_operator_set_communicate(self.handle, int(communicate)))
+
+    def setQuadratureOrders(self, interior, surface):
+        capi.check(capi.lib().b200fem_operator_set_quadrature_orders(self.handle, interior, surface))
+
+    def setKernel(self, kernel):
+        capi.check(capi.lib().b200fem_operator_set_kernel(self.handle, kernel))
+
+    def dirichlet(self):
+        mask = np.zeros(self.space.size, dtype=np.uint8)
+        vals = np.zeros(self.space.size)
+        capi.check(capi.lib().b200fem_operator_dirichlet(self.handle, capi.ptr(mask), capi.ptr(vals)))
+        return mask, vals
+
+    def timing(self):
+        t = capi.Timing()
+        capi.check(capi.lib().b200fem_operator_timing(self.handle, C.byref(t)))
+        return {"last_apply_ms": t.last_apply_ms, "last_exchange_ms": t.last_exchange_ms, "applies": t.applies,
+                "kernel": t.kernel, "launches_per_apply": t.launches_per_apply}
+
+    def dot_dev(self, x_ptr, y_ptr):
+        r = C.c_double()
+        capi.check(capi.lib().b200fem_dot_dev(self.handle, C.c_void_p(x_ptr), C.c_void_p(y_ptr), C.byref(r)))
+        return r.value
+
+    def communicate_dev(self, v_ptr):
+        capi.check(capi.lib().b200fem_communicate_dev(self.handle, C.c_void_p(v_ptr)))
+
+    @property
+    def nonlinear(self):
+        return self.model.gamma != 0.0
+
+
+def galerkin(space, **kwargs):
+    return GalerkinOperator(space, **kwargs)

@@ -1,0 +1,148 @@
+/* b200fem.h -- C ABI of the B200-native matrix-free Galerkin operator + CG.
+ *
+ * This is the drop-in boundary for DUNE-FEM's hot path.  Every entry
+ * point names the reference interface it replaces (paths relative to
+ * /root/reference/dune/fem).  Conventions: extern "C", opaque handles, caller-owned
+ * arrays, return 0 on success and a negative b200fem_status on error (no exceptions
+ * cross the ABI; b200fem_last_error() returns the message of the calling thread's last
+ * failure).  A handle is not re-entrant (same contract as galerkin.hh:1498-1500).
+ * There is no CPU fallback: every compute entry point fails with B200FEM_ERR_CUDA
+ * when no CUDA device is usable.
+ */
+#ifndef B200FEM_H
+#define B200FEM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200fem_ctx b200fem_ctx;           /* device + stream + scratch            */
+typedef struct b200fem_mesh b200fem_mesh;         /* Cartesian YaspGrid-equivalent (rank-local box of a global grid) */
+typedef struct b200fem_space b200fem_space;       /* DiscreteFunctionSpace                */
+typedef struct b200fem_operator b200fem_operator; /* GalerkinOperator (+DirichletWrapper) */
+
+enum b200fem_status {
+  B200FEM_OK = 0,
+  B200FEM_ERR_INVALID = -1,        /* DUNE_THROW(InvalidStateException) analogue */
+  B200FEM_ERR_NOT_IMPLEMENTED = -2,/* DUNE_THROW(NotImplemented) analogue        */
+  B200FEM_ERR_CUDA = -3,           /* CUDA runtime / no device                   */
+  B200FEM_ERR_COMM = -4            /* NCCL / peer access                         */
+};
+
+/* space kinds: python/dune/fem/space/_spaces.py:106 (lagrange), :183-229 (dglegendre, hierarchical flag) */
+enum b200fem_space_kind { B200FEM_LAGRANGE = 0, B200FEM_DG_LEGENDRE = 1, B200FEM_DG_LEGENDRE_HIER = 2 };
+/* sub-entity numbering of Lagrange dofs: YaspGrid leaf index set or AdaptiveLeafIndexSet first-touch order
+ * (gridpart/adaptiveleafindexset.hh:884-906) */
+enum b200fem_numbering { B200FEM_NUMBERING_YASP = 0, B200FEM_NUMBERING_ADAPTIVE_LEAF = 1 };
+/* which device kernel evaluates the operator */
+enum b200fem_kernel {
+  B200FEM_KERNEL_AUTO = 0,       /* fastest kernel that is valid for the model                              */
+  B200FEM_KERNEL_QUADRATURE = 1, /* generic: gather, basis evaluation at quadrature points, integrand, axpy */
+  B200FEM_KERNEL_KRONECKER = 2   /* linear constant-coefficient models on uniform boxes: 1-D operator form  */
+};
+/* solver/parameter.hh:21-295 "fem.solver.errormeasure" */
+enum b200fem_tolerance { B200FEM_TOL_ABSOLUTE = 0, B200FEM_TOL_RELATIVE = 1, B200FEM_TOL_RESIDUAL_REDUCTION = 2 };
+
+/* Integrands (schemes/integrands.hh:152-375): the advection-diffusion-reaction family of the
+ * BASELINE configs, i.e. the UFL form of pydemo/advectiondiffusion.py:33-60 plus c*u + gamma*u^3:
+ *   interior  s = c u + gamma u^3 - f,   F = eps grad u - b u
+ *   skeleton  eps beta/he [u][v] - eps {grad u}.n [v] - eps [u]{grad v}.n + [hatb u][v]
+ *   boundary  -eps grad g.n v + dD (eps beta/hbnd (u-g) + hatb u + (b.n-hatb) g) v
+ * data: 0 g=f=0, 1 g=sin(x0 x1), 2 g=prod sin(pi x_k); f is chosen so that g solves the PDE. */
+typedef struct b200fem_model {
+  double eps, b[3], c, gamma, beta;
+  int32_t dirichlet_mask;   /* bit 2*axis+side: side carries Dirichlet data (weak for DG, strong for Lagrange) */
+  int32_t data;
+  int32_t has_skeleton, has_boundary;
+  int32_t strong_dirichlet; /* wrap in DirichletWrapperOperator (schemes/dirichletwrapper.hh:101-105) */
+} b200fem_model;
+
+typedef struct b200fem_timing {
+  double last_apply_ms;     /* device time of the last apply (CUDA events on the operator's stream) */
+  double last_exchange_ms;  /* halo exchange share, cf. exchangeTime() space/common/communicationmanager.hh:203-209 */
+  int64_t applies;          /* cf. gridSizeInterior()/call counters galerkin.hh:822,1479 */
+  int32_t kernel;           /* b200fem_kernel actually used */
+  int32_t launches_per_apply;
+} b200fem_timing;
+
+const char* b200fem_last_error(void);
+int b200fem_version(void);
+
+/* MPIManager / device selection (misc/mpimanager.hh:352-461).  `stream` may be NULL (own stream) or a cudaStream_t. */
+int b200fem_ctx_create(int device, void* stream, b200fem_ctx** out);
+int b200fem_ctx_destroy(b200fem_ctx* ctx);
+int b200fem_ctx_synchronize(b200fem_ctx* ctx);
+/* plain device buffers for callers without their own allocator */
+int b200fem_malloc(b200fem_ctx* ctx, int64_t bytes, void** dev);
+int b200fem_free(b200fem_ctx* ctx, void* dev);
+int b200fem_memcpy_h2d(b200fem_ctx* ctx, void* dev, const void* host, int64_t bytes);
+int b200fem_memcpy_d2h(b200fem_ctx* ctx, void* host, const void* dev, int64_t bytes);
+
+/* YaspGrid< dim > on [lo,hi] with n cells per axis (replaces the GridPart handed to the space,
+ * gridpart/common/gridpart.hh).  The distributed variant describes this rank's box of a global grid that is
+ * split into proc[0] x proc[1] x proc[2] boxes (rank = c0 + proc0*(c1 + proc1*c2)); DG spaces then carry one
+ * layer of ghost elements (overlap 1). */
+int b200fem_mesh_cartesian(b200fem_ctx* ctx, int dim, const int32_t* n, const double* lo, const double* hi, b200fem_mesh** out);
+int b200fem_mesh_cartesian_distributed(b200fem_ctx* ctx, int dim, const int32_t* n_global, const double* lo, const double* hi,
+                                       const int32_t* proc, int rank, b200fem_mesh** out);
+int b200fem_mesh_destroy(b200fem_mesh* mesh);
+
+/* DiscreteFunctionSpace (space/lagrange/space.hh:129-353, space/discontinuousgalerkin/legendre.hh) */
+int b200fem_space_create(b200fem_mesh* mesh, int kind, int order, int numbering, b200fem_space** out);
+int b200fem_space_destroy(b200fem_space* space);
+int b200fem_space_size(b200fem_space* space, int64_t* size);            /* space.size()                               */
+int b200fem_space_local_size(b200fem_space* space, int32_t* nb);        /* blockMapper().maxNumDofs()                 */
+int b200fem_space_elements(b200fem_space* space, int64_t* n);
+/* blockMapper().map(entity, out) (space/mapper/indexsetdofmapper.hh:414-427, codimensionmapper.hh:121-131) */
+int b200fem_space_dofmap(b200fem_space* space, int64_t element, int64_t* out);
+
+/* GalerkinOperator(dSpace, rSpace, integrands) (schemes/galerkin.hh:1383-1504) */
+int b200fem_operator_create(b200fem_space* space, const b200fem_model* model, b200fem_operator** out);
+int b200fem_operator_destroy(b200fem_operator* op);
+/* operator()(u, w) (galerkin.hh:1430-1433; operator/common/operator.hh:55): w = L[u], host dof vectors in the
+ * reference layout (function/blockvectors/defaultblockvectors.hh:284-294). Copies u to the device, runs the
+ * kernels, copies w back. */
+int b200fem_operator_apply(b200fem_operator* op, const double* u_host, double* w_host);
+/* the homogeneous linear part A u = L[u] - L[0] (what a Krylov solver applies; SURVEY.md 8a row I') */
+int b200fem_operator_apply_linear(b200fem_operator* op, const double* u_host, double* w_host);
+/* device-pointer variant; linear != 0 selects A u.  Asynchronous on the context's stream. */
+int b200fem_operator_apply_dev(b200fem_operator* op, const double* u_dev, double* w_dev, int linear);
+/* b = -L[0] (python/dune/fem/operator/__init__.py:347-350) */
+int b200fem_operator_load_vector(b200fem_operator* op, double* b_host);
+int b200fem_operator_set_communicate(b200fem_operator* op, int communicate);                    /* galerkin.hh:1409 */
+int b200fem_operator_set_quadrature_orders(b200fem_operator* op, unsigned interior, unsigned surface); /* :1418-1423 */
+int b200fem_operator_set_kernel(b200fem_operator* op, int kernel);
+/* strong Dirichlet marks and values (schemes/dirichletconstraints.hh:435-554) */
+int b200fem_operator_dirichlet(b200fem_operator* op, uint8_t* mask_host, double* values_host);
+int b200fem_operator_timing(b200fem_operator* op, b200fem_timing* out);
+
+/* CgInverseOperator / KrylovInverseOperator<cg> (solver/krylovinverseoperators.hh:118-208 ->
+ * solver/linear/cg.hh:18-117) on the homogeneous linear part.  x holds the initial guess on entry.
+ * *iterations is negative if not converged (cg.hh:116).  history (may be NULL, maxit entries) receives
+ * sqrt(residual) per iteration, the value the reference prints as "Fem::CG it: i : residual r". */
+int b200fem_cg_solve(b200fem_operator* op, const double* b_host, double* x_host, double epsilon, int max_iterations,
+                     int tolerance_criteria, int* iterations, double* history);
+int b200fem_cg_solve_dev(b200fem_operator* op, const double* b_dev, double* x_dev, double epsilon, int max_iterations,
+                         int tolerance_criteria, int* iterations, double* history);
+
+/* BLAS-1 on device dof vectors (function/blockvectors/defaultblockvectors.hh:39-150) and the dot product over
+ * primary dofs followed by the global sum (function/common/scalarproducts.hh:115-127) */
+int b200fem_dot_dev(b200fem_operator* op, const double* x_dev, const double* y_dev, double* result);
+int b200fem_axpy_dev(b200fem_operator* op, double alpha, const double* x_dev, double* y_dev);
+
+/* Multi-GPU: one process per GPU.  `nccl_comm` is an ncclComm_t created by the caller (e.g. from an id broadcast
+ * through torch.distributed); halo exchange replaces DiscreteFunction::communicate
+ * (function/common/discretefunction.hh:825-835, space/common/communicationmanager.hh:130-150): Copy for DG,
+ * Add for Lagrange; dots use ncclAllReduce. */
+int b200fem_ctx_set_nccl(b200fem_ctx* ctx, void* nccl_comm, int rank, int world);
+int b200fem_nccl_unique_id(void* out128);
+int b200fem_nccl_init(b200fem_ctx* ctx, const void* id128, int rank, int world);
+/* exchange the ghost layer of a device dof vector of `space` in place */
+int b200fem_communicate_dev(b200fem_operator* op, double* v_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200FEM_H */

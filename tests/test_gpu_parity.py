@@ -1,0 +1,217 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Tolerance: north_star asks for <= 1e-12 relative (FP64); "relative" is taken against max|w| of the oracle result.
+Dof numbering must be bit-exact.
+"""
+import numpy as np
+import pytest
+
+import dune_fem_b200 as fem
+from dune_fem_b200 import _capi
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+ADV = dict(eps=1e-2, b=(1.0, 0.0, 0.0), dirichlet_mask=0b000011, data=1)     # pydemo/advectiondiffusion.py setup
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def dg_pair(n, lo, hi, order, hier):
+    space = fem.space.dglegendre(fem.structuredGrid(lo, hi, n), order=order, hierarchical=hier)
+    osp = ol.Space(n, lo, hi, ol.DG_LEGENDRE_HIER if hier else ol.DG_LEGENDRE, order)
+    assert space.size == osp.size
+    return space, osp
+
+
+@pytest.mark.parametrize("order,hier", [(1, False), (1, True), (2, False), (2, True), (3, True), (4, False), (5, True)])
+def test_dg_quadrature_kernel_affine_and_linear(order, hier):
+    n = [5, 4, 3] if order <= 3 else [3, 3, 2]
+    space, osp = dg_pair(n, [-1, -1, -1], [1, 0.5, 2.0], order, hier)
+    beta = 20.0 * order ** 2
+    u = np.random.default_rng(order).uniform(-1, 1, space.size)
+    oop = ol.Operator(osp, beta=beta, skeleton=True, boundary=True, **ADV)
+    op = fem.operator.galerkin(space, beta=beta, kernel=_capi.KERNEL_QUADRATURE, **ADV)
+    w = np.empty(space.size)
+    op(u, w)
+    assert rel(w, oop.apply(u)) < TOL
+    op.applyLinear(u, w)
+    assert rel(w, oop.apply(u, linear=True)) < TOL
+    assert rel(op.loadVector(), -oop.apply(np.zeros(space.size))) < TOL
+
+
+@pytest.mark.parametrize("order,hier", [(1, False), (1, True), (2, False), (2, True)])
+@pytest.mark.parametrize("n", [[9, 5, 6], [8, 4, 4], [1, 2, 3]])
+def test_dg_kronecker_kernel(order, hier, n):
+    space, osp = dg_pair(n, [-1, -1, -1], [1, 1.5, 1], order, hier)
+    beta = 20.0 * order ** 2
+    kw = dict(eps=0.3, b=(1.0, -0.5, 0.25), c=0.7, dirichlet_mask=0b011011, data=1)
+    u = np.random.default_rng(7).uniform(-1, 1, space.size)
+    oop = ol.Operator(osp, beta=beta, skeleton=True, boundary=True, **kw)
+    op = fem.operator.galerkin(space, beta=beta, kernel=_capi.KERNEL_KRONECKER, **kw)
+    w = np.empty(space.size)
+    op(u, w)
+    assert rel(w, oop.apply(u)) < TOL
+    op.applyLinear(u, w)
+    assert rel(w, oop.apply(u, linear=True)) < TOL
+    assert op.timing()["kernel"] == _capi.KERNEL_KRONECKER
+
+
+def test_dg_nonlinear_model_uses_quadrature_kernel():
+    space, osp = dg_pair([4, 4, 4], [0, 0, 0], [1, 1, 1], 2, True)
+    kw = dict(eps=0.5, b=(0.3, 0.2, 0.1), c=1.0, gamma=2.0, dirichlet_mask=0b111111, data=2)
+    u = np.random.default_rng(11).uniform(-1, 1, space.size)
+    oop = ol.Operator(osp, beta=80.0, skeleton=True, boundary=True, **kw)
+    op = fem.operator.galerkin(space, beta=80.0, **kw)
+    assert op.nonlinear
+    w = np.empty(space.size)
+    op(u, w)
+    assert rel(w, oop.apply(u)) < TOL
+    assert op.timing()["kernel"] == _capi.KERNEL_QUADRATURE
+    with pytest.raises(_capi.B200FemError):
+        op.setKernel(_capi.KERNEL_KRONECKER)
+        op(u, w)
+
+
+def test_dg_volume_only_and_mass():
+    space, osp = dg_pair([3, 3, 3], [0, 0, 0], [1, 1, 1], 2, False)
+    u = np.random.default_rng(5).uniform(-1, 1, space.size)
+    for kernel in (_capi.KERNEL_QUADRATURE, _capi.KERNEL_KRONECKER):
+        op = fem.operator.galerkin(space, eps=0.0, c=1.0, skeleton=False, boundary=False, kernel=kernel)
+        w = np.empty(space.size)
+        op(u, w)
+        ref = ol.Operator(osp, eps=0.0, c=1.0).apply(u)
+        assert rel(w, ref) < TOL
+        # orthonormal Legendre: the mass operator is detJ * identity
+        np.testing.assert_allclose(w, u / 27.0, rtol=0, atol=1e-14)
+
+
+@pytest.mark.parametrize("dim,order,numbering", [(2, 1, 0), (2, 2, 0), (3, 1, 0), (3, 2, 0), (3, 2, 1), (2, 2, 1)])
+def test_lagrange_dofmap_and_apply(dim, order, numbering):
+    n = [7, 6, 5][:dim]
+    lo, hi = [0.0] * dim, [1.0, 2.0, 1.5][:dim]
+    space = fem.space.lagrange(fem.structuredGrid(lo, hi, n), order=order, numbering=numbering)
+    osp = ol.Space(n, lo, hi, ol.LAGRANGE, order, numbering=numbering)
+    assert space.size == osp.size and space.elements == osp.elements
+    for e in range(space.elements):                              # bit-exact numbering
+        assert (space.mapper(e) == osp.dofmap(e)).all()
+    u = np.random.default_rng(3).uniform(-1, 1, space.size)
+    mask_all = 0b111111 if dim == 3 else 0b1111
+    # Poisson with strong Dirichlet data (DirichletWrapperOperator)
+    kw = dict(eps=1.0, c=0.25, data=2, dirichlet_mask=mask_all, strong_dirichlet=True)
+    op = fem.operator.galerkin(space, **kw)
+    oop = ol.Operator(osp, **kw)
+    w = np.empty(space.size)
+    op(u, w)
+    assert rel(w, oop.apply(u)) < TOL
+    op.applyLinear(u, w)
+    assert rel(w, oop.apply(u, linear=True)) < TOL
+    m1, g1 = op.dirichlet()
+    m2, g2 = oop.dirichlet()
+    assert (m1 == m2).all() and np.abs(g1 - g2).max() < 1e-15
+    # natural boundary terms (Neumann data) + advection, no constraints
+    kw = dict(eps=0.7, b=(1.0, 0.5, -0.25), data=1, dirichlet_mask=0b000011, boundary=True)
+    op = fem.operator.galerkin(space, **kw)
+    op(u, w)
+    assert rel(w, ol.Operator(osp, **kw).apply(u)) < TOL
+
+
+@pytest.mark.parametrize("dim,order,n", [(2, 1, [32, 32]), (2, 2, [12, 10]), (3, 2, [6, 5, 4])])
+def test_cg_iterates_match_reference_recurrence(dim, order, n):
+    lo, hi = [0.0] * dim, [1.0] * dim
+    space = fem.space.lagrange(fem.structuredGrid(lo, hi, n), order=order)
+    osp = ol.Space(n, lo, hi, ol.LAGRANGE, order)
+    mask_all = 0b111111 if dim == 3 else 0b1111
+    kw = dict(eps=1.0, c=0.1, data=1, dirichlet_mask=mask_all, strong_dirichlet=True)
+    op = fem.operator.galerkin(space, **kw)
+    oop = ol.Operator(osp, **kw)
+    b = op.loadVector()
+    assert rel(b, -oop.apply(np.zeros(space.size))) < TOL
+    mask, g = op.dirichlet()
+    x0 = np.where(mask, g, 0.0)
+    # fixed number of iterations: compare iterates' residual norms and x
+    for maxit in (1, 5, 30):
+        inv = fem.solver.CgInverseOperator({"tolerance": 1e-30, "maxiterations": maxit})
+        inv.bind(op)
+        x = x0.copy()
+        it = inv(b, x)
+        it_ref, x_ref, hist_ref = oop.cg(b, x0, 1e-30, maxit)
+        assert it == it_ref == -maxit
+        np.testing.assert_allclose(inv.residuals, hist_ref, rtol=1e-9)
+        assert rel(x, x_ref) < 1e-10
+    inv = fem.solver.CgInverseOperator({"tolerance": 1e-10, "maxiterations": 2000, "errormeasure": "absolute"})
+    inv.bind(op)
+    x = x0.copy()
+    it = inv(b, x)
+    it_ref, x_ref, _ = oop.cg(b, x0, 1e-10, 2000)
+    assert it > 0 and abs(it - it_ref) <= 1
+    assert rel(x, x_ref) < 1e-9
+    for crit in ("relative", "residualreduction"):
+        inv = fem.solver.CgInverseOperator({"tolerance": 1e-6, "maxiterations": 2000, "errormeasure": crit})
+        inv.bind(op)
+        x = x0.copy()
+        it = inv(b, x)
+        it_ref, _, _ = oop.cg(b, x0, 1e-6, 2000, tolcrit={"relative": 1, "residualreduction": 2}[crit])
+        assert abs(it - it_ref) <= 1
+
+
+def test_cg_on_dg_sipg_laplace():
+    space, osp = dg_pair([4, 4, 4], [0, 0, 0], [1, 1, 1], 2, True)
+    kw = dict(eps=1.0, dirichlet_mask=0b111111, data=2)
+    op = fem.operator.galerkin(space, beta=80.0, **kw)
+    oop = ol.Operator(osp, beta=80.0, skeleton=True, boundary=True, **kw)
+    b = op.loadVector()
+    inv = fem.solver.CgInverseOperator({"tolerance": 1e-30, "maxiterations": 20})
+    inv.bind(op)
+    x = np.zeros(space.size)
+    it = inv(b, x)
+    it_ref, x_ref, hist_ref = oop.cg(b, np.zeros(space.size), 1e-30, 20)
+    assert it == it_ref
+    np.testing.assert_allclose(inv.residuals, hist_ref, rtol=1e-9)
+    assert rel(x, x_ref) < 1e-10
+
+
+def test_error_conventions():
+    space, _ = dg_pair([2, 2, 2], [0, 0, 0], [1, 1, 1], 1, False)
+    op = fem.operator.galerkin(space)
+    op.setQuadratureOrders(7, 9)                                    # selects a rule the device kernels do not carry
+    with pytest.raises(_capi.B200FemError) as ei:
+        op(np.zeros(space.size), np.zeros(space.size))
+    assert ei.value.code == _capi.ERR_NOT_IMPLEMENTED
+    with pytest.raises(_capi.B200FemError):
+        fem.space.lagrange(fem.structuredGrid([0, 0], [1, 1], [2, 2]), order=3)
+    inv = fem.solver.CgInverseOperator()
+    with pytest.raises(RuntimeError):
+        inv(np.zeros(3), np.zeros(3))
+
+
+def test_full_size_c2_properties():
+    """BASELINE config 2 at full size (DG Q2, 64^3, 7.08 M dofs): size-independent properties."""
+    n = [64, 64, 64]
+    space = fem.space.dglegendre(fem.structuredGrid([-1, -1, -1], [1, 1, 1], n), order=2, hierarchical=True)
+    assert space.size == 64 ** 3 * 27
+    kw = dict(eps=1e-5, b=(1.0, 0.0, 0.0), beta=80.0, dirichlet_mask=0b000011, data=1)
+    rng = np.random.default_rng(20261017)
+    u, v = rng.uniform(-1, 1, space.size), rng.uniform(-1, 1, space.size)
+    opq = fem.operator.galerkin(space, kernel=_capi.KERNEL_QUADRATURE, **kw)
+    opk = fem.operator.galerkin(space, kernel=_capi.KERNEL_KRONECKER, **kw)
+    wq, wk, wl = np.empty(space.size), np.empty(space.size), np.empty(space.size)
+    opq(u, wq)
+    opk(u, wk)
+    assert rel(wk, wq) < TOL                                       # both device kernels agree
+    # affine structure and linearity of the homogeneous part
+    opk.applyLinear(u, wl)
+    b = opk.loadVector()
+    assert rel(wl - b, wk) < TOL
+    wv, wuv = np.empty(space.size), np.empty(space.size)
+    opk.applyLinear(v, wv)
+    opk.applyLinear(2.0 * u - 3.0 * v, wuv)
+    assert rel(wuv, 2.0 * wl - 3.0 * wv) < TOL
+    # a slab of the full-size result against the oracle: the operator is local, so the first two x-y layers of
+    # elements only depend on the first three layers of u
+    osp = ol.Space([64, 64, 3], [-1, -1, -1], [1, 1, -1 + 3 * 2.0 / 64], ol.DG_LEGENDRE_HIER, 2)
+    ref = ol.Operator(osp, skeleton=True, boundary=True, threads=8, **kw).apply(u[:osp.size])
+    m = 64 * 64 * 2 * 27
+    assert rel(wk[:m], ref[:m]) < TOL
