@@ -1,0 +1,288 @@
+#!/usr/bin/env python
+"""bench.py -- operator-apply throughput (DoF/s, FP64) of the matrix-free Galerkin operator on B200.
+
+Workload (BASELINE.json configs[1], "C2"): advection-diffusion, DG Q2 (dglegendre, hierarchical), 3-D cube
+[-1,1]^3 with 64^3 cells per GPU, SIPG + upwind integrands of pydemo/advectiondiffusion.py, explicit operator
+apply w = L[u] = A u - b (complete affine operator; b = -L[0] precomputed once and streamed by the kernel).
+A "step" is one operator application over one synthetic dof vector (u ~ U(-1,1), PCG64 seed 20261017).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU, torchrun for N>1)
+  python bench.py --impl reference --steps K --warmup W    # the CPU restatement of the reference, all host threads
+
+Prints ONE JSON line (rank 0).  See the task contract for the keys.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+SEED = 20261017
+ORDER = 2
+CELLS = 64
+MODEL = dict(eps=1e-5, b=(1.0, 0.0, 0.0), beta=20.0 * ORDER ** 2, dirichlet_mask=0b000011, data=1)
+ALGORITHMIC_BYTES_PER_DOF = 16.0       # read u once + write w once
+
+
+def proc_grid(n):
+    return {1: [1, 1, 1], 2: [2, 1, 1], 4: [2, 2, 1], 8: [2, 2, 2]}[n]
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock and throttle reasons of one GPU through NVML while the timed region runs"""
+
+    def __init__(self, index, period=0.002):
+        super().__init__(daemon=True)
+        self.index, self.period, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, period, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake": 0x80, "sync_boost": 0x10, "applications_clocks": 0x2}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def result(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_reference_apply(threads, sample_cells, reps):
+    """times the CPU oracle (restatement of the reference's GalerkinOperator::evaluate) -- checker/baseline only"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    n = sample_cells
+    h = 2.0 / CELLS
+    hi = [-1 + n[0] * h, -1 + n[1] * h, -1 + n[2] * h]
+    sp = ol.Space(n, [-1, -1, -1], hi, ol.DG_LEGENDRE_HIER, ORDER)
+    op = ol.Operator(sp, skeleton=True, boundary=True, threads=threads, **MODEL)
+    u = np.random.default_rng(SEED).uniform(-1, 1, sp.size)
+    times = []
+    w = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        w = op.apply(u)
+        times.append(time.perf_counter() - t0)
+    return sp.size, times, w
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    # bounded sample: a 64 x 64 x 16 slab of the 64^3 mesh per step (same elements, quarter of the work)
+    cells = [CELLS, CELLS, 16]
+    ndof, times, _ = cpu_reference_apply(threads, cells, args.warmup + args.steps)
+    timed = times[args.warmup:]
+    total = sum(timed)
+    value = ndof * len(timed) / total
+    line = {
+        "impl": "reference", "metric": "operator-apply DoF/s (FP64)", "value": value, "unit": "DoF/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(timed), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2 advection-diffusion DG Q2 3D 64^3 explicit operator apply (CPU restatement of the reference; "
+                               "DUNE-FEM itself cannot be built in this image)", "sample_cells": cells, "dofs_per_step": ndof},
+        "cpu_baseline": {"value": value, "unit": "DoF/s", "cores": threads, "kind": "port",
+                         "sample": f"{len(timed)} applies of a {cells[0]}x{cells[1]}x{cells[2]} slab of the 64^3 mesh, {threads} threads"},
+        "e2e": {"value": value, "unit": "DoF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "quadrature", "kronecker"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import dune_fem_b200 as fem
+    from dune_fem_b200 import _capi
+    from dune_fem_b200.grid import Context
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    # a dedicated (non-default) stream shared by torch and the library: CUDA events below are recorded on the very
+    # stream the kernels are launched on
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx = Context(device=local_rank, stream=stream.cuda_stream)
+    proc = proc_grid(world)
+    if world > 1:
+        ids = [Context.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.init_nccl(ids[0], rank, world)
+    n_global = [CELLS * p for p in proc]
+    hi = [-1.0 + 2.0 * p for p in proc]                 # every rank keeps a [-1,1]^3-sized box: h is the same at all N
+    grid = fem.structuredGrid([-1.0, -1.0, -1.0], hi, n_global, ctx=ctx, proc=proc if world > 1 else None, rank=rank)
+    space = fem.space.dglegendre(grid, order=ORDER, hierarchical=True)
+    kernel = {"auto": _capi.KERNEL_AUTO, "quadrature": _capi.KERNEL_QUADRATURE, "kronecker": _capi.KERNEL_KRONECKER}[args.kernel]
+    op = fem.operator.galerkin(space, kernel=kernel, **MODEL)
+    ndof_local = CELLS ** 3 * (ORDER + 1) ** 3            # owned dofs per rank
+    ndof_total = ndof_local * world
+
+    # rotating device buffers: 6 (u, w) pairs of 2 x 56.6 MB each = 680 MB >> 126 MB L2
+    npairs = 6
+    rng = np.random.default_rng(SEED + rank)
+    us = [torch.from_numpy(rng.uniform(-1, 1, space.size)).to(dev) for _ in range(npairs)]
+    ws = [torch.empty(space.size, dtype=torch.float64, device=dev) for _ in range(npairs)]
+    if world > 1:
+        for u in us:
+            op.communicate_dev(u.data_ptr())             # consistent ghost copies of the input, as the reference assumes
+
+    def step(i, linear=False):
+        op.apply_dev(us[i % npairs].data_ptr(), ws[i % npairs].data_ptr(), linear)
+
+    def timed(nsteps, linear=False):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(nsteps):
+            step(i, linear)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms = timed(args.steps)
+    sampler.stop_flag = True
+    sampler.join()
+    tinfo = op.timing()
+    ms_linear = timed(args.steps, linear=True)
+
+    value = ndof_total * args.steps / (ms * 1e-3)
+    launches = tinfo["launches_per_apply"] * args.steps
+
+    # end to end through the host-pointer C ABI call (pinned host dof vectors, H2D + kernel + D2H per step)
+    e2e = None
+    uh = torch.from_numpy(rng.uniform(-1, 1, space.size)).pin_memory()
+    wh = torch.empty(space.size, dtype=torch.float64).pin_memory()
+    un, wn = uh.numpy(), wh.numpy()
+    op(un, wn)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        op(un, wn)
+    t1 = time.perf_counter()
+    e2e_t = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e = {"value": ndof_total * args.e2e_steps / float(e2e_t.item()), "unit": "DoF/s", "h2d_bytes_per_step": 8 * space.size,
+           "d2h_bytes_per_step": 8 * space.size, "steps": args.e2e_steps,
+           "api": "b200fem_operator_apply(op, u_host, w_host) with pinned host buffers"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("hbm_gbs")
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    if not peak:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    per_launch_s = ms * 1e-3 / args.steps
+    achieved = ALGORITHMIC_BYTES_PER_DOF * ndof_local / per_launch_s / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
+            "dg_kronecker" if tinfo["kernel"] == _capi.KERNEL_KRONECKER else "dg_quadrature")
+    except Exception:
+        pass
+    kernel_name = {1: "dg_quadrature_kernel<3>", 2: "dg_kronecker_kernel<3>"}.get(tinfo["kernel"], "?")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": kernel_name, "peak_source": peak_src, "algorithmic_bytes_per_dof": ALGORITHMIC_BYTES_PER_DOF,
+                "note": "the affine step also streams the precomputed load vector b (8 B/dof) that the 16 B/dof figure does not count; "
+                        "the homogeneous apply A u moves exactly 16 B/dof, see linear_apply"}
+    lin_s = ms_linear * 1e-3 / args.steps
+    linear_apply = {"value": ndof_total / lin_s, "unit": "DoF/s", "ms_per_step": ms_linear / args.steps,
+                    "achieved_gbs": ALGORITHMIC_BYTES_PER_DOF * ndof_local / lin_s / 1e9,
+                    "frac": ALGORITHMIC_BYTES_PER_DOF * ndof_local / lin_s / 1e9 / peak}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1:
+        threads = os.cpu_count() or 1
+        cells = [CELLS, CELLS, 16]
+        nd, times, _ = cpu_reference_apply(threads, cells, 3)
+        best = min(times[1:])
+        cpu_baseline = {"value": nd / best, "unit": "DoF/s", "cores": threads, "kind": "port",
+                        "sample": f"best of 2 applies of a {cells[0]}x{cells[1]}x{cells[2]} slab of the 64^3 mesh, {threads} threads"}
+
+    line = {
+        "metric": "operator-apply DoF/s (FP64)", "value": value, "unit": "DoF/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2 advection-diffusion DG Q2 (dglegendre hierarchical) 3D 64^3 cells per GPU, explicit operator apply "
+                               "w = L[u] = A u - b (pydemo/advectiondiffusion.py integrands, eps=1e-5)",
+                   "dofs_per_gpu": ndof_local, "process_grid": proc, "halo_exchange": world > 1,
+                   "l2": f"{npairs} rotating (u,w) buffer pairs = {npairs * 2 * 8 * space.size / 1e6:.0f} MB > 126 MB L2",
+                   "kernel": kernel_name},
+        "roofline": roofline, "linear_apply": linear_apply, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
+        "clocks": sampler.result(),
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -14,6 +15,8 @@
 
 #include "../../include/b200fem.h"
 #include "dg_kronecker.cuh"
+#include "dg_kronecker_pipe.cuh"
+#include "dg_kronecker_tma.cuh"
 #include "dg_quadrature.cuh"
 #include "halo.cuh"
 #include "integrands.cuh"
@@ -245,6 +248,33 @@ template <int N, int TX, int TY, int TZ> static int launch_dg_kronecker(b200fem_
   kern<<<(unsigned)(tx * ty * tz), Cfg::kThreads, Cfg::smem_bytes(), op->sp->mesh->ctx->stream>>>(K, b, op->d_perm, u, w, bvec, tx, ty);
   CUDA_OK(cudaGetLastError()); return B200FEM_OK;
 }
+template <int N, bool HIER> static int launch_dg_kronecker_tma(b200fem_operator* op, const double* u, double* w, const double* bvec) {
+  constexpr int TX = 8, TY = 4, TZ = 4;
+  using Cfg = KronTmaCfg<N, TX, TY, TZ>; const BoxDev& b = op->sp->box;
+  KronHost kh = build_kron_tables(op->sp->tab, op->model, b.dim, b.h);
+  KronTabDev<N> K;
+  for (int d = 0; d < 3; ++d) for (int i = 0; i < N * N; ++i) { K.S[d][i] = kh.S[d][i]; K.Dlo[d][i] = kh.Dlo[d][i]; K.Dhi[d][i] = kh.Dhi[d][i]; K.L[d][i] = kh.L[d][i]; K.R[d][i] = kh.R[d][i]; }
+  const int tx = (b.own_hi[0] - b.own_lo[0] + TX - 1) / TX, ty = (b.own_hi[1] - b.own_lo[1] + TY - 1) / TY, tz = (b.own_hi[2] - b.own_lo[2] + TZ - 1) / TZ;
+  auto kern = dg_kronecker_tma_kernel<N, HIER, TX, TY, TZ>;
+  CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes()));
+  kern<<<(unsigned)(tx * ty * tz), Cfg::kThreads, Cfg::smem_bytes(), op->sp->mesh->ctx->stream>>>(K, b, u, w, bvec, tx, ty);
+  CUDA_OK(cudaGetLastError()); return B200FEM_OK;
+}
+template <int N, bool HIER> static int launch_dg_kronecker_pipe(b200fem_operator* op, const double* u, double* w, const double* bvec) {
+  constexpr int TX = 8, TY = 4, TZ = 4;
+  using Cfg = KronPipeCfg<N, TX, TY, TZ>; const BoxDev& b = op->sp->box;
+  KronHost kh = build_kron_tables(op->sp->tab, op->model, b.dim, b.h);
+  KronTabDev<N> K;
+  for (int d = 0; d < 3; ++d) for (int i = 0; i < N * N; ++i) { K.S[d][i] = kh.S[d][i]; K.Dlo[d][i] = kh.Dlo[d][i]; K.Dhi[d][i] = kh.Dhi[d][i]; K.L[d][i] = kh.L[d][i]; K.R[d][i] = kh.R[d][i]; }
+  const int tx = (b.own_hi[0] - b.own_lo[0] + TX - 1) / TX, ty = (b.own_hi[1] - b.own_lo[1] + TY - 1) / TY, tz = (b.own_hi[2] - b.own_lo[2] + TZ - 1) / TZ;
+  const int ntiles = tx * ty * tz;
+  static int sms = 0;
+  if (!sms) CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, op->sp->mesh->ctx->device));
+  auto kern = dg_kronecker_pipe_kernel<N, HIER, TX, TY, TZ>;
+  CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes()));
+  kern<<<(unsigned)std::min(ntiles, sms), Cfg::kThreads, Cfg::smem_bytes(), op->sp->mesh->ctx->stream>>>(K, b, u, w, bvec, tx, ty, ntiles);
+  CUDA_OK(cudaGetLastError()); return B200FEM_OK;
+}
 template <int N> static int launch_lagrange(b200fem_operator* op, const double* u, double* w, bool with_data) {
   const BoxDev& b = op->sp->box; cudaStream_t st = op->sp->mesh->ctx->stream;
   CUDA_OK(cudaMemsetAsync(w, 0, sizeof(double) * (size_t)op->sp->size, st));                 // w.clear() (galerkin.hh:1463)
@@ -294,7 +324,15 @@ static int apply_local(b200fem_operator* op, const double* u, double* w, bool li
     REQUIRE(kron_ok, B200FEM_ERR_INVALID, "Kronecker kernel needs a linear model and order <= 2");
     const double* bvec = nullptr;
     if (!linear && op->model.data) { int rc = ensure_bvec(op); if (rc) return rc; bvec = op->d_bvec; }
-    int rc = N == 2 ? launch_dg_kronecker<2, 8, 8, 4>(op, u, w, bvec) : launch_dg_kronecker<3, 8, 4, 4>(op, u, w, bvec);
+    // v2 (bulk-copy staged) needs 8-byte aligned vectors whose w / b share the 16-byte phase; otherwise v1
+    static const char* variant_env = std::getenv("B200FEM_KRON_VARIANT");      // v1 | tma | pipe (default), for A/B measurements
+    const std::string variant = variant_env ? variant_env : "pipe";
+    const bool phase_ok = !bvec || ((reinterpret_cast<uintptr_t>(bvec) ^ reinterpret_cast<uintptr_t>(w)) & 8) == 0;
+    const bool hier = s->kind == B200FEM_DG_LEGENDRE_HIER;
+    int rc;
+    if (N == 3 && phase_ok && variant == "pipe") rc = hier ? launch_dg_kronecker_pipe<3, true>(op, u, w, bvec) : launch_dg_kronecker_pipe<3, false>(op, u, w, bvec);
+    else if (N == 3 && phase_ok && variant == "tma") rc = hier ? launch_dg_kronecker_tma<3, true>(op, u, w, bvec) : launch_dg_kronecker_tma<3, false>(op, u, w, bvec);
+    else rc = N == 2 ? launch_dg_kronecker<2, 8, 8, 4>(op, u, w, bvec) : launch_dg_kronecker<3, 8, 4, 4>(op, u, w, bvec);
     if (rc) return rc;
   } else {
     int rc = B200FEM_ERR_NOT_IMPLEMENTED;

@@ -48,7 +48,7 @@ template <int N> struct DgQuadCfg {
   static constexpr int kElemDoubles = 2 * N3 + kScratch;
   static constexpr int EB = N == 2 ? 32 : N == 3 ? 16 : N == 4 ? 8 : N == 5 ? 6 : 4;   // elements per CTA
   static constexpr int kThreads = EB * N2;
-  static constexpr size_t smem_bytes() { return sizeof(double) * (size_t)EB * kElemDoubles + sizeof(int) * N3 * 2 + sizeof(long long) * EB; }
+  static constexpr size_t smem_bytes() { return sizeof(double) * (size_t)EB * kElemDoubles + sizeof(int) * N3 * 2 + sizeof(long long) * EB + sizeof(int) * 4 * EB; }
 };
 
 // out[q] = sum_c M[q*N+c] in[c]

@@ -79,7 +79,7 @@ def test_dg_volume_only_and_mass():
     space, osp = dg_pair([3, 3, 3], [0, 0, 0], [1, 1, 1], 2, False)
     u = np.random.default_rng(5).uniform(-1, 1, space.size)
     for kernel in (_capi.KERNEL_QUADRATURE, _capi.KERNEL_KRONECKER):
-        op = fem.operator.galerkin(space, eps=0.0, c=1.0, skeleton=False, boundary=False, kernel=kernel)
+        op = fem.operator.galerkin(space, eps=0.0, c=1.0, beta=0.0, skeleton=False, boundary=False, kernel=kernel)
         w = np.empty(space.size)
         op(u, w)
         ref = ol.Operator(osp, eps=0.0, c=1.0).apply(u)
@@ -112,7 +112,7 @@ def test_lagrange_dofmap_and_apply(dim, order, numbering):
     m2, g2 = oop.dirichlet()
     assert (m1 == m2).all() and np.abs(g1 - g2).max() < 1e-15
     # natural boundary terms (Neumann data) + advection, no constraints
-    kw = dict(eps=0.7, b=(1.0, 0.5, -0.25), data=1, dirichlet_mask=0b000011, boundary=True)
+    kw = dict(eps=0.7, b=(1.0, 0.5, -0.25), beta=20.0, data=1, dirichlet_mask=0b000011, boundary=True)
     op = fem.operator.galerkin(space, **kw)
     op(u, w)
     assert rel(w, ol.Operator(osp, **kw).apply(u)) < TOL
@@ -159,18 +159,32 @@ def test_cg_iterates_match_reference_recurrence(dim, order, n):
 
 def test_cg_on_dg_sipg_laplace():
     space, osp = dg_pair([4, 4, 4], [0, 0, 0], [1, 1, 1], 2, True)
-    kw = dict(eps=1.0, dirichlet_mask=0b111111, data=2)
+    # symmetric positive definite: SIPG interior faces + reaction, Neumann data on the boundary (the weak
+    # Dirichlet form of the pydemo has no symmetry term, CG on it is chaotic)
+    kw = dict(eps=1.0, c=1.0, dirichlet_mask=0, data=2)
     op = fem.operator.galerkin(space, beta=80.0, **kw)
     oop = ol.Operator(osp, beta=80.0, skeleton=True, boundary=True, **kw)
     b = op.loadVector()
-    inv = fem.solver.CgInverseOperator({"tolerance": 1e-30, "maxiterations": 20})
+    # CG on this operator (cond ~ 1e5, oscillating residuals) amplifies rounding differences by ~10x per
+    # iteration, so iterates are compared early and the converged solutions at the end
+    inv = fem.solver.CgInverseOperator({"tolerance": 1e-30, "maxiterations": 8})
     inv.bind(op)
     x = np.zeros(space.size)
     it = inv(b, x)
-    it_ref, x_ref, hist_ref = oop.cg(b, np.zeros(space.size), 1e-30, 20)
-    assert it == it_ref
-    np.testing.assert_allclose(inv.residuals, hist_ref, rtol=1e-9)
-    assert rel(x, x_ref) < 1e-10
+    it_ref, x_ref, hist_ref = oop.cg(b, np.zeros(space.size), 1e-30, 8)
+    assert it == it_ref == -8
+    np.testing.assert_allclose(inv.residuals, hist_ref, rtol=1e-8)
+    assert rel(x, x_ref) < 1e-9
+    inv = fem.solver.CgInverseOperator({"tolerance": 1e-11, "maxiterations": 5000})
+    inv.bind(op)
+    x = np.zeros(space.size)
+    it = inv(b, x)
+    it_ref, x_ref, _ = oop.cg(b, np.zeros(space.size), 1e-11, 5000)
+    assert it > 0 and it_ref > 0 and abs(it - it_ref) <= max(3, it_ref // 20)
+    assert rel(x, x_ref) < 1e-9
+    w = np.empty(space.size)
+    op.applyLinear(x, w)
+    assert np.linalg.norm(w - b) < 2e-11
 
 
 def test_error_conventions():
