@@ -248,7 +248,7 @@ def main():
             "dg_kronecker" if tinfo["kernel"] == _capi.KERNEL_KRONECKER else "dg_quadrature")
     except Exception:
         pass
-    kernel_name = {1: "dg_quadrature_kernel<3>", 2: "dg_kronecker_kernel<3>"}.get(tinfo["kernel"], "?")
+    kernel_name = {1: "dg_quadrature_kernel<3>", 2: "dg_kronecker_tensor_kernel<3> (TMA tensor tiles)"}.get(tinfo["kernel"], "?")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": kernel_name, "peak_source": peak_src, "algorithmic_bytes_per_dof": ALGORITHMIC_BYTES_PER_DOF,
                 "note": "the affine step also streams the precomputed load vector b (8 B/dof) that the 16 B/dof figure does not count; "

@@ -16,6 +16,7 @@
 #include "../../include/b200fem.h"
 #include "dg_kronecker.cuh"
 #include "dg_kronecker_pipe.cuh"
+#include "dg_kronecker_tensor.cuh"
 #include "dg_kronecker_tma.cuh"
 #include "dg_quadrature.cuh"
 #include "halo.cuh"
@@ -260,20 +261,76 @@ template <int N, bool HIER> static int launch_dg_kronecker_tma(b200fem_operator*
   kern<<<(unsigned)(tx * ty * tz), Cfg::kThreads, Cfg::smem_bytes(), op->sp->mesh->ctx->stream>>>(K, b, u, w, bvec, tx, ty);
   CUDA_OK(cudaGetLastError()); return B200FEM_OK;
 }
-template <int N, bool HIER> static int launch_dg_kronecker_pipe(b200fem_operator* op, const double* u, double* w, const double* bvec) {
+// ---- TMA tensor maps (driver entry point resolved at run time: no link-time dependency on libcuda) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode_tiled = nullptr;
+static bool ensure_encode_tiled() {
+  if (g_encode_tiled) return true;
+  void* fn = nullptr; cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return false;
+  g_encode_tiled = (EncodeTiledFn)fn; return true;
+}
+// 3-D tensor of doubles [d2][d1][d0] with byte strides s1, s2 and box b0 x b1 x b2
+static bool make_map3(CUtensorMap* m, const double* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1, uint64_t s2, uint32_t b0, uint32_t b1, uint32_t b2) {
+  const cuuint64_t dims[3] = {d0, d1, d2}; const cuuint64_t strides[2] = {s1, s2};
+  const cuuint32_t boxd[3] = {b0, b1, b2}; const cuuint32_t estr[3] = {1, 1, 1};
+  return g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), dims, strides, boxd, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+template <int N> static bool tensor_path_ok(const b200fem_operator* op, const double* u, const double* w, const double* bvec) {
+  const BoxDev& b = op->sp->box;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return N == 3 && b.n[0] % 2 == 0 && b.own_lo[0] % 2 == 0 && al16(u) && al16(w) && (!bvec || al16(bvec)) && ensure_encode_tiled();
+}
+template <int N, bool HIER, bool SPLIT> static int launch_dg_kronecker_tensor(b200fem_operator* op, const double* u, double* w, const double* bvec) {
+  constexpr int TX = 8, TY = 4, TZ = 4, N3 = N * N * N;
+  using Cfg = KronTensorCfg<N, TX, TY, TZ, SPLIT>; const BoxDev& b = op->sp->box;
+  KronHost kh = build_kron_tables(op->sp->tab, op->model, b.dim, b.h);
+  KronTabDev<N> K;
+  for (int d = 0; d < 3; ++d) for (int i = 0; i < N * N; ++i) { K.S[d][i] = kh.S[d][i]; K.Dlo[d][i] = kh.Dlo[d][i]; K.Dhi[d][i] = kh.Dhi[d][i]; K.L[d][i] = kh.L[d][i]; K.R[d][i] = kh.R[d][i]; }
+  const int on[3] = {b.own_hi[0] - b.own_lo[0], b.own_hi[1] - b.own_lo[1], b.own_hi[2] - b.own_lo[2]};
+  const int tx = (on[0] + TX - 1) / TX, ty = (on[1] + TY - 1) / TY, tz = (on[2] + TZ - 1) / TZ, ntiles = tx * ty * tz;
+  const uint64_t s1 = (uint64_t)b.n[0] * N3 * 8, s2 = s1 * b.n[1];
+  const long long own_off = ((long long)b.own_lo[0] + (long long)b.n[0] * (b.own_lo[1] + (long long)b.n[1] * b.own_lo[2])) * N3;
+  KronTensorMaps M;
+  bool ok = make_map3(&M.u_tile, u, (uint64_t)b.n[0] * N3, b.n[1], b.n[2], s1, s2, TX * N3, TY, TZ) &&
+            make_map3(&M.u_xhalo, u, (uint64_t)b.n[0] * N3, b.n[1], b.n[2], s1, s2, 2 * N3, TY, TZ) &&
+            make_map3(&M.u_yhalo, u, (uint64_t)b.n[0] * N3, b.n[1], b.n[2], s1, s2, TX * N3, 1, TZ) &&
+            make_map3(&M.u_zhalo, u, (uint64_t)b.n[0] * N3, b.n[1], b.n[2], s1, s2, TX * N3, TY, 1) &&
+            make_map3(&M.w_tile, w + own_off, (uint64_t)on[0] * N3, on[1], on[2], s1, s2, TX * N3, TY, TZ) &&
+            make_map3(&M.b_tile, (bvec ? bvec : w) + own_off, (uint64_t)on[0] * N3, on[1], on[2], s1, s2, TX * N3, TY, TZ);
+  REQUIRE(ok, B200FEM_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  static int sms = 0;
+  if (!sms) CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, op->sp->mesh->ctx->device));
+  auto kern = dg_kronecker_tensor_kernel<N, HIER, TX, TY, TZ, SPLIT>;
+  CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes()));
+  kern<<<(unsigned)std::min(ntiles, sms), Cfg::kThreads, Cfg::smem_bytes(), op->sp->mesh->ctx->stream>>>(K, b, M, bvec ? 1 : 0, tx, ty, ntiles);
+  CUDA_OK(cudaGetLastError()); return B200FEM_OK;
+}
+
+static long long* g_dbg = nullptr; static int g_dbg_calls = 0;
+template <int N, bool HIER, bool SPLIT> static int launch_dg_kronecker_pipe(b200fem_operator* op, const double* u, double* w, const double* bvec) {
   constexpr int TX = 8, TY = 4, TZ = 4;
-  using Cfg = KronPipeCfg<N, TX, TY, TZ>; const BoxDev& b = op->sp->box;
+  using Cfg = KronPipeCfg<N, TX, TY, TZ, SPLIT>; const BoxDev& b = op->sp->box;
   KronHost kh = build_kron_tables(op->sp->tab, op->model, b.dim, b.h);
   KronTabDev<N> K;
   for (int d = 0; d < 3; ++d) for (int i = 0; i < N * N; ++i) { K.S[d][i] = kh.S[d][i]; K.Dlo[d][i] = kh.Dlo[d][i]; K.Dhi[d][i] = kh.Dhi[d][i]; K.L[d][i] = kh.L[d][i]; K.R[d][i] = kh.R[d][i]; }
   const int tx = (b.own_hi[0] - b.own_lo[0] + TX - 1) / TX, ty = (b.own_hi[1] - b.own_lo[1] + TY - 1) / TY, tz = (b.own_hi[2] - b.own_lo[2] + TZ - 1) / TZ;
   const int ntiles = tx * ty * tz;
+  if (!g_dbg && std::getenv("B200FEM_DEBUG_TIMELINE")) { cudaMalloc(&g_dbg, 8 * 8 * 32); cudaMemset(g_dbg, 0, 8 * 8 * 32); }
   static int sms = 0;
   if (!sms) CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, op->sp->mesh->ctx->device));
-  auto kern = dg_kronecker_pipe_kernel<N, HIER, TX, TY, TZ>;
+  auto kern = dg_kronecker_pipe_kernel<N, HIER, TX, TY, TZ, SPLIT>;
   CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes()));
-  kern<<<(unsigned)std::min(ntiles, sms), Cfg::kThreads, Cfg::smem_bytes(), op->sp->mesh->ctx->stream>>>(K, b, u, w, bvec, tx, ty, ntiles);
-  CUDA_OK(cudaGetLastError()); return B200FEM_OK;
+  kern<<<(unsigned)std::min(ntiles, sms), Cfg::kThreads, Cfg::smem_bytes(), op->sp->mesh->ctx->stream>>>(K, b, u, w, bvec, tx, ty, ntiles, std::getenv("B200FEM_DEBUG_SKIP") ? 1 : 0, g_dbg);
+  CUDA_OK(cudaGetLastError());
+  if (g_dbg && ++g_dbg_calls == 40) {      // dump the timeline of CTA 0 for one warm call
+    std::vector<long long> h(8 * 32); cudaDeviceSynchronize(); cudaMemcpy(h.data(), g_dbg, h.size() * 8, cudaMemcpyDeviceToHost);
+    long long t0 = h[8 * 1 + 0];
+    for (int it = 0; it < 16; ++it) { std::fprintf(stderr, "it %2d:", it); for (int k = 0; k < 8; ++k) std::fprintf(stderr, " %8lld", h[8 * it + k] ? h[8 * it + k] - t0 : -1); std::fprintf(stderr, "\n"); }
+  }
+  return B200FEM_OK;
 }
 template <int N> static int launch_lagrange(b200fem_operator* op, const double* u, double* w, bool with_data) {
   const BoxDev& b = op->sp->box; cudaStream_t st = op->sp->mesh->ctx->stream;
@@ -325,12 +382,15 @@ static int apply_local(b200fem_operator* op, const double* u, double* w, bool li
     const double* bvec = nullptr;
     if (!linear && op->model.data) { int rc = ensure_bvec(op); if (rc) return rc; bvec = op->d_bvec; }
     // v2 (bulk-copy staged) needs 8-byte aligned vectors whose w / b share the 16-byte phase; otherwise v1
-    static const char* variant_env = std::getenv("B200FEM_KRON_VARIANT");      // v1 | tma | pipe (default), for A/B measurements
-    const std::string variant = variant_env ? variant_env : "pipe";
+    static const char* variant_env = std::getenv("B200FEM_KRON_VARIANT");      // v1 | tma | pipe | split | tensor (default) | tensor3, for A/B measurements
+    const std::string variant = variant_env ? variant_env : "tensor";
     const bool phase_ok = !bvec || ((reinterpret_cast<uintptr_t>(bvec) ^ reinterpret_cast<uintptr_t>(w)) & 8) == 0;
     const bool hier = s->kind == B200FEM_DG_LEGENDRE_HIER;
     int rc;
-    if (N == 3 && phase_ok && variant == "pipe") rc = hier ? launch_dg_kronecker_pipe<3, true>(op, u, w, bvec) : launch_dg_kronecker_pipe<3, false>(op, u, w, bvec);
+    if (variant == "tensor" && tensor_path_ok<3>(op, u, w, bvec) && N == 3) rc = hier ? launch_dg_kronecker_tensor<3, true, false>(op, u, w, bvec) : launch_dg_kronecker_tensor<3, false, false>(op, u, w, bvec);
+    else if (variant == "tensor3" && tensor_path_ok<3>(op, u, w, bvec) && N == 3) rc = hier ? launch_dg_kronecker_tensor<3, true, true>(op, u, w, bvec) : launch_dg_kronecker_tensor<3, false, true>(op, u, w, bvec);
+    else if (N == 3 && phase_ok && (variant == "pipe" || variant == "tensor" || variant == "tensor3")) rc = hier ? launch_dg_kronecker_pipe<3, true, false>(op, u, w, bvec) : launch_dg_kronecker_pipe<3, false, false>(op, u, w, bvec);
+    else if (N == 3 && phase_ok && variant == "split") rc = hier ? launch_dg_kronecker_pipe<3, true, true>(op, u, w, bvec) : launch_dg_kronecker_pipe<3, false, true>(op, u, w, bvec);
     else if (N == 3 && phase_ok && variant == "tma") rc = hier ? launch_dg_kronecker_tma<3, true>(op, u, w, bvec) : launch_dg_kronecker_tma<3, false>(op, u, w, bvec);
     else rc = N == 2 ? launch_dg_kronecker<2, 8, 8, 4>(op, u, w, bvec) : launch_dg_kronecker<3, 8, 4, 4>(op, u, w, bvec);
     if (rc) return rc;

@@ -43,7 +43,7 @@ def test_dg_quadrature_kernel_affine_and_linear(order, hier):
 
 
 @pytest.mark.parametrize("order,hier", [(1, False), (1, True), (2, False), (2, True)])
-@pytest.mark.parametrize("n", [[9, 5, 6], [8, 4, 4], [1, 2, 3]])
+@pytest.mark.parametrize("n", [[9, 5, 6], [8, 4, 4], [1, 2, 3], [10, 7, 5], [18, 4, 9]])
 def test_dg_kronecker_kernel(order, hier, n):
     space, osp = dg_pair(n, [-1, -1, -1], [1, 1.5, 1], order, hier)
     beta = 20.0 * order ** 2
