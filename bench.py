@@ -31,7 +31,7 @@ ALGORITHMIC_BYTES_PER_DOF = 16.0       # read u once + write w o
 
 
 def proc_grid(n):
-    return {1: [1, 1, 1], 2: [2, 1, 1], 4: [2, 2, 1], 8: [2, 2, 2]}[n]
+    return {1: [1, 1, 1], 2: [1, 1, 2], 4: [1, 2, 2], 8: [1, 2, 4]}[n]   # x (the contiguous axis) is never split
 
 
 class ClockSampler(threading.Thread):

@@ -125,6 +125,25 @@ extern "C" int b200fem_mesh_cartesian_distributed(b200fem_ctx* ctx, int dim, con
   return make_mesh(ctx, dim, n, lo, hi, proc, rank, out);
 }
 extern "C" int b200fem_mesh_destroy(b200fem_mesh* m) { delete m; return B200FEM_OK; }
+extern "C" int b200fem_partition_box(int dim, const int32_t* n, const int32_t* proc, int rank, int overlap, int32_t* out) {
+  REQUIRE(n && proc && out && (dim == 2 || dim == 3), B200FEM_ERR_INVALID, "partition_box: bad argument");
+  int p[3] = {1, 1, 1}, g[3] = {1, 1, 1}, world = 1;
+  for (int d = 0; d < dim; ++d) { p[d] = proc[d]; g[d] = n[d]; REQUIRE(p[d] >= 1 && p[d] <= g[d], B200FEM_ERR_INVALID, "partition_box: bad process grid"); world *= p[d]; }
+  REQUIRE(rank >= 0 && rank < world, B200FEM_ERR_INVALID, "partition_box: rank outside process grid");
+  const int pc[3] = {rank % p[0], (rank / p[0]) % p[1], rank / (p[0] * p[1])};
+  for (int d = 0; d < 3; ++d) {
+    const int q = g[d] / p[d], r = g[d] % p[d], c = pc[d];
+    const int olo = c * q + std::min(c, r), ohi = olo + q + (c < r ? 1 : 0);
+    const int glo = (overlap && olo > 0) ? 1 : 0, ghi = (overlap && ohi < g[d]) ? 1 : 0;
+    out[d] = olo - glo; out[3 + d] = (ohi - olo) + glo + ghi; out[6 + d] = glo; out[9 + d] = glo + (ohi - olo);
+  }
+  return B200FEM_OK;
+}
+extern "C" int b200fem_mesh_local_box(b200fem_mesh* m, int overlap, int32_t* out) {
+  REQUIRE(m && out, B200FEM_ERR_INVALID, "mesh_local_box: null argument");
+  const int rank = m->pc[0] + m->proc[0] * (m->pc[1] + m->proc[1] * m->pc[2]);
+  return b200fem_partition_box(m->dim, m->gn, m->proc, rank, overlap, out);
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // AdaptiveLeafIndexSet first-touch numbering of the Lagrange lattice (gridpart/adaptiveleafindexset.hh:884-906)
@@ -434,14 +453,15 @@ static int apply_dev_impl(b200fem_operator* op, const double* u, double* w, bool
   if (op->d_bvec == nullptr && !linear && op->model.data && s->kind != B200FEM_LAGRANGE) { /* built lazily inside apply_local when needed */ }
   CUDA_OK(cudaEventRecord(op->ev0, st));
   int rc = apply_local(op, u, w, linear); if (rc) return rc;
-  if (op->model.strong_dirichlet && op->d_dmask) {
-    dirichlet_sub_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(u, w, op->d_dmask, linear ? nullptr : op->d_dvals, s->size);
-    CUDA_OK(cudaGetLastError()); op->timing.launches_per_apply += 1;
-  }
   if (op->communicate && s->mesh->ctx->world > 1) {
     CUDA_OK(cudaEventRecord(op->evx0, st));
     rc = halo_exchange(op->halo, s->mesh->ctx->nccl, s->mesh->ctx->comm, w, s->kind == B200FEM_LAGRANGE, st); if (rc) return fail(B200FEM_ERR_COMM, "halo exchange failed");
     CUDA_OK(cudaEventRecord(op->evx1, st));
+  }
+  // DirichletWrapperOperator: op_(u,w) (communication included) first, then subConstraints (dirichletwrapper.hh:101-105)
+  if (op->model.strong_dirichlet && op->d_dmask) {
+    dirichlet_sub_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(u, w, op->d_dmask, linear ? nullptr : op->d_dvals, s->size);
+    CUDA_OK(cudaGetLastError()); op->timing.launches_per_apply += 1;
   }
   CUDA_OK(cudaEventRecord(op->ev1, st));
   op->timing.applies += 1;

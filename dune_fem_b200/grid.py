@@ -57,3 +57,14 @@ class GridView:
 
 def structuredGrid(lo, hi, n, ctx=None, proc=None, rank=0):
     return GridView(lo, hi, n, ctx=ctx, proc=proc, rank=rank)
+
+
+def partition_box(n_global, proc, rank, overlap):
+    """host-only: (origin, extents, own_lo, own_hi) of `rank`'s box, see b200fem_partition_box"""
+    dim = len(n_global)
+    n_a = (C.c_int32 * 3)(*(list(n_global) + [1] * (3 - dim)))
+    p_a = (C.c_int32 * 3)(*(list(proc) + [1] * (3 - dim)))
+    out = (C.c_int32 * 12)()
+    capi.check(capi.lib().b200fem_partition_box(dim, n_a, p_a, rank, int(overlap), out))
+    v = list(out)
+    return v[0:3], v[3:6], v[6:9], v[9:12]

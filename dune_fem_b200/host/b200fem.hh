@@ -1,0 +1,167 @@
+// b200fem.hh -- C++ host-side mirror of the reference's operator / solver interface for the GPU hot path.
+//
+// DUNE-FEM is C++ (header templates); its drop-in point for this path is the abstract operator
+//   Dune::Fem::Operator< DomainFunction, RangeFunction >::operator()( u, w )   (dune/fem/operator/common/operator.hh:32-65)
+// implemented by Dune::Fem::GalerkinOperator (dune/fem/schemes/galerkin.hh:1383-1504) and consumed by
+// Dune::Fem::CgInverseOperator / KrylovInverseOperator (dune/fem/solver/krylovinverseoperators.hh:46-281) through
+// bind( op ) and operator()( rhs, x ).  DUNE itself is not available in this image, so this header mirrors those
+// interfaces (same names, argument meaning, error behaviour: exceptions on the C++ side, negative iteration counts
+// for non-converged solves) on top of the C ABI in include/b200fem.h, without any DUNE dependency.  INTEGRATION.md shows
+// the adapter a DUNE-FEM maintainer adds (dune/fem/schemes/b200galerkin.hh) -- it is the same code with DUNE's own
+// DiscreteFunction in place of the one below.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "b200fem.h"
+
+namespace B200Fem {
+
+struct InvalidStateException : std::runtime_error { using std::runtime_error::runtime_error; };   // DUNE_THROW(InvalidStateException, ...)
+struct NotImplemented : std::runtime_error { using std::runtime_error::runtime_error; };          // DUNE_THROW(NotImplemented, ...)
+
+inline void check(int rc) {
+  if (rc == B200FEM_OK) return;
+  const std::string msg = b200fem_last_error();
+  if (rc == B200FEM_ERR_NOT_IMPLEMENTED) throw NotImplemented(msg);
+  throw InvalidStateException(msg);
+}
+
+// MPIManager analogue: device context (misc/mpimanager.hh:352-461)
+class Context {
+ public:
+  explicit Context(int device = 0, void* stream = nullptr) { check(b200fem_ctx_create(device, stream, &h_)); }
+  ~Context() { b200fem_ctx_destroy(h_); }
+  Context(const Context&) = delete;
+  b200fem_ctx* handle() const { return h_; }
+ private:
+  b200fem_ctx* h_ = nullptr;
+};
+
+// GridPart over a Cartesian YaspGrid (gridpart/common/gridpart.hh)
+template <int dim>
+class CartesianGridPart {
+ public:
+  static constexpr int dimension = dim;
+  CartesianGridPart(Context& ctx, const std::array<int, dim>& cells, const std::array<double, dim>& lo, const std::array<double, dim>& hi) {
+    int32_t n[3] = {1, 1, 1}; double l[3] = {0, 0, 0}, h[3] = {1, 1, 1};
+    for (int d = 0; d < dim; ++d) { n[d] = cells[d]; l[d] = lo[d]; h[d] = hi[d]; }
+    check(b200fem_mesh_cartesian(ctx.handle(), dim, n, l, h, &h_));
+  }
+  ~CartesianGridPart() { b200fem_mesh_destroy(h_); }
+  b200fem_mesh* handle() const { return h_; }
+ private:
+  b200fem_mesh* h_ = nullptr;
+};
+
+// DiscreteFunctionSpace: LagrangeDiscreteFunctionSpace / LegendreDiscontinuousGalerkinSpace / Hierarchic...
+template <class GridPart>
+class DiscreteFunctionSpace {
+ public:
+  typedef GridPart GridPartType;
+  DiscreteFunctionSpace(const GridPart& gp, b200fem_space_kind kind, int order, b200fem_numbering numbering = B200FEM_NUMBERING_YASP)
+      : gridPart_(gp), order_(order) {
+    check(b200fem_space_create(gp.handle(), kind, order, numbering, &h_));
+    int64_t s = 0; check(b200fem_space_size(h_, &s)); size_ = (std::size_t)s;
+  }
+  ~DiscreteFunctionSpace() { b200fem_space_destroy(h_); }
+  std::size_t size() const { return size_; }
+  int order() const { return order_; }
+  const GridPart& gridPart() const { return gridPart_; }
+  b200fem_space* handle() const { return h_; }
+ private:
+  const GridPart& gridPart_; int order_; b200fem_space* h_ = nullptr; std::size_t size_ = 0;
+};
+
+// AdaptiveDiscreteFunction: host-owned dof vector in the reference layout (function/adaptivefunction/adaptivefunction.hh:45-203)
+template <class Space>
+class DiscreteFunction {
+ public:
+  typedef Space DiscreteFunctionSpaceType;
+  typedef double RangeFieldType;
+  DiscreteFunction(const std::string& name, const Space& space) : name_(name), space_(space), dofs_(space.size(), 0.0) {}
+  const Space& space() const { return space_; }
+  double* leakPointer() { return dofs_.data(); }                     // adaptivefunction.hh:130-131
+  const double* leakPointer() const { return dofs_.data(); }
+  std::vector<double>& dofVector() { return dofs_; }
+  const std::vector<double>& dofVector() const { return dofs_; }
+  void clear() { dofs_.assign(dofs_.size(), 0.0); }
+  void assign(const DiscreteFunction& o) { dofs_ = o.dofs_; }
+  void axpy(double a, const DiscreteFunction& o) { for (std::size_t i = 0; i < dofs_.size(); ++i) dofs_[i] += a * o.dofs_[i]; }
+  const std::string& name() const { return name_; }
+ private:
+  std::string name_; const Space& space_; std::vector<double> dofs_;
+};
+
+// Dune::Fem::Operator (operator/common/operator.hh:32-65)
+template <class DomainFunction, class RangeFunction = DomainFunction>
+struct Operator {
+  typedef DomainFunction DomainFunctionType;
+  typedef RangeFunction RangeFunctionType;
+  virtual ~Operator() = default;
+  virtual void operator()(const DomainFunctionType& u, RangeFunctionType& w) const = 0;
+  virtual void finalize() {}
+  virtual bool nonlinear() const { return false; }
+};
+
+// Integrands of the advection-diffusion-reaction family (see include/b200fem.h, b200fem_model)
+struct Integrands : b200fem_model {
+  Integrands() : b200fem_model{} { eps = 1.0; }
+};
+
+// Dune::Fem::GalerkinOperator< Integrands, DomainFunction, RangeFunction > (schemes/galerkin.hh:1383-1504), optionally
+// wrapped like DirichletWrapperOperator (schemes/dirichletwrapper.hh:29-165) when integrands.strong_dirichlet is set
+template <class DiscreteFunctionT>
+class GalerkinOperator : public Operator<DiscreteFunctionT, DiscreteFunctionT> {
+ public:
+  typedef typename DiscreteFunctionT::DiscreteFunctionSpaceType DiscreteFunctionSpaceType;
+  GalerkinOperator(const DiscreteFunctionSpaceType& dSpace, const DiscreteFunctionSpaceType& rSpace, const Integrands& integrands)
+      : space_(dSpace), integrands_(integrands) {
+    if (&dSpace != &rSpace) throw NotImplemented("domain and range space must coincide");
+    check(b200fem_operator_create(dSpace.handle(), &integrands_, &h_));
+  }
+  ~GalerkinOperator() override { b200fem_operator_destroy(h_); }
+  void operator()(const DiscreteFunctionT& u, DiscreteFunctionT& w) const override { check(b200fem_operator_apply(h_, u.leakPointer(), w.leakPointer())); }
+  // homogeneous linear part (what the Krylov solvers apply)
+  void applyLinear(const DiscreteFunctionT& u, DiscreteFunctionT& w) const { check(b200fem_operator_apply_linear(h_, u.leakPointer(), w.leakPointer())); }
+  void loadVector(DiscreteFunctionT& b) const { check(b200fem_operator_load_vector(h_, b.leakPointer())); }
+  bool nonlinear() const override { return integrands_.gamma != 0.0; }
+  void setCommunicate(bool communicate) { check(b200fem_operator_set_communicate(h_, communicate)); }                 // galerkin.hh:1409
+  void setQuadratureOrders(unsigned interior, unsigned surface) { check(b200fem_operator_set_quadrature_orders(h_, interior, surface)); }   // :1418-1423
+  const DiscreteFunctionSpaceType& domainSpace() const { return space_; }
+  const DiscreteFunctionSpaceType& rangeSpace() const { return space_; }
+  const Integrands& model() const { return integrands_; }
+  b200fem_operator* handle() const { return h_; }
+ private:
+  const DiscreteFunctionSpaceType& space_; Integrands integrands_; b200fem_operator* h_ = nullptr;
+};
+
+// Dune::Fem::CgInverseOperator = KrylovInverseOperator< DF, SolverParameter::cg > (solver/krylovinverseoperators.hh:46-281)
+struct SolverParameter {                       // solver/parameter.hh:21-295, keys fem.solver.*
+  double tolerance = 1e-8; int errorMeasure = B200FEM_TOL_ABSOLUTE; int maxIterations = 1000; bool verbose = false;
+};
+template <class DiscreteFunctionT>
+class CgInverseOperator {
+ public:
+  typedef GalerkinOperator<DiscreteFunctionT> OperatorType;
+  explicit CgInverseOperator(const SolverParameter& p = SolverParameter()) : parameter_(p) {}
+  void bind(const OperatorType& op) { op_ = &op; }                                    // inverseoperatorinterface.hh:109-113
+  void unbind() { op_ = nullptr; }
+  void operator()(const DiscreteFunctionT& rhs, DiscreteFunctionT& x) const {        // inverseoperatorinterface.hh:81-84
+    if (!op_) throw InvalidStateException("CgInverseOperator: no operator bound");
+    residuals_.assign((std::size_t)std::max(parameter_.maxIterations, 1), 0.0);
+    check(b200fem_cg_solve(op_->handle(), rhs.leakPointer(), x.leakPointer(), parameter_.tolerance, parameter_.maxIterations,
+                           parameter_.errorMeasure, &iterations_, residuals_.data()));
+  }
+  int iterations() const { return iterations_; }                                       // negative: not converged (linear/cg.hh:116)
+  bool converged() const { return iterations_ >= 0; }
+  const std::vector<double>& residuals() const { return residuals_; }
+  SolverParameter& parameter() { return parameter_; }
+ private:
+  SolverParameter parameter_; const OperatorType* op_ = nullptr; mutable int iterations_ = 0; mutable std::vector<double> residuals_;
+};
+
+}  // namespace B200Fem

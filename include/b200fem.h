@@ -88,6 +88,13 @@ int b200fem_mesh_cartesian(b200fem_ctx* ctx, int dim, const int32_t* n, const do
 int b200fem_mesh_cartesian_distributed(b200fem_ctx* ctx, int dim, const int32_t* n_global, const double* lo, const double* hi,
                                        const int32_t* proc, int rank, b200fem_mesh** out);
 int b200fem_mesh_destroy(b200fem_mesh* mesh);
+/* The block partition used by the distributed mesh, without needing a device (host logic only): for `rank` of the
+ * process grid, out[0..2] = global coordinates of local element (0,0,0) (ghost layer included), out[3..5] = local
+ * extents, out[6..8] / out[9..11] = owned range [lo,hi) in local coordinates.  overlap = 1 for DG spaces, 0 for Lagrange.
+ * Cells are dealt in blocks; the first (n % p) ranks along an axis hold one extra cell (YaspGrid's default load
+ * balancer lives in dune-grid and is not restated; the process grid is explicit instead). */
+int b200fem_partition_box(int dim, const int32_t* n_global, const int32_t* proc, int rank, int overlap, int32_t* out12);
+int b200fem_mesh_local_box(b200fem_mesh* mesh, int overlap, int32_t* out12);
 
 /* DiscreteFunctionSpace (space/lagrange/space.hh:129-353, space/discontinuousgalerkin/legendre.hh) */
 int b200fem_space_create(b200fem_mesh* mesh, int kind, int order, int numbering, b200fem_space** out);
