@@ -125,6 +125,7 @@ def main():
     ap.add_argument("--kernel", default="auto", choices=["auto", "quadrature", "kronecker"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--no-cg", action="store_true", help="skip the CG s/iteration measurement (BASELINE configs 1 and 3)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -175,6 +176,8 @@ def main():
     def step(i, linear=False):
         op.apply_dev(us[i % npairs].data_ptr(), ws[i % npairs].data_ptr(), linear)
 
+    host_issue_us = [0.0]
+
     def timed(nsteps, linear=False):
         torch.cuda.synchronize()
         if world > 1:
@@ -182,8 +185,10 @@ def main():
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
+        h0 = time.perf_counter()
         for i in range(nsteps):
             step(i, linear)
+        host_issue_us[0] = 1e6 * (time.perf_counter() - h0) / nsteps
         e1.record(stream)
         torch.cuda.synchronize()
         if world > 1:
@@ -198,10 +203,30 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     ms = timed(args.steps)
+    host_us = host_issue_us[0]
     sampler.stop_flag = True
     sampler.join()
     tinfo = op.timing()
     ms_linear = timed(args.steps, linear=True)
+    # multi-GPU diagnostics: the halo exchange alone and the local kernels alone (same stream, same buffers)
+    diag = None
+    if world > 1:
+        def loop(fn, n):
+            torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for i in range(n):
+                fn(i)
+            b.record(stream)
+            torch.cuda.synchronize()
+            t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return 1e3 * float(t.item()) / n
+        ex_us = loop(lambda i: op.communicate_dev(ws[i % npairs].data_ptr()), 200)
+        op.setCommunicate(False)
+        comp_us = loop(lambda i: step(i), 200)
+        op.setCommunicate(True)
+        diag = {"exchange_only_us": ex_us, "local_kernels_only_us": comp_us}
 
     value = ndof_total * args.steps / (ms * 1e-3)
     launches = tinfo["launches_per_apply"] * args.steps
@@ -225,6 +250,34 @@ def main():
     e2e = {"value": ndof_total * args.e2e_steps / float(e2e_t.item()), "unit": "DoF/s", "h2d_bytes_per_step": 8 * space.size,
            "d2h_bytes_per_step": 8 * space.size, "steps": args.e2e_steps,
            "api": "b200fem_operator_apply(op, u_host, w_host) with pinned host buffers"}
+
+    # CG seconds/iteration (second half of BASELINE's metric): C3 Poisson P2 Lagrange 3D 128^3 and C1 P1 2D 256^2,
+    # 100 fixed iterations of the device-resident CG (tolerance 0 so that no iteration is skipped)
+    cg = None
+    if world == 1 and not args.no_cg:
+        import ctypes as C
+        cg = {}
+        for name, dim, cells, order in (("C3 Poisson P2 Lagrange 3D 128^3", 3, 128, 2), ("C1 Poisson P1 Lagrange 2D 256^2", 2, 256, 1)):
+            g = fem.structuredGrid([0.0] * dim, [1.0] * dim, [cells] * dim, ctx=ctx)
+            sp = fem.space.lagrange(g, order=order)
+            lop = fem.operator.galerkin(sp, eps=1.0, data=2, dirichlet_mask=(1 << (2 * dim)) - 1, strong_dirichlet=True)
+            bt = torch.from_numpy(lop.loadVector()).to(dev)
+            mask, gv = lop.dirichlet()
+            x0 = torch.from_numpy(np.where(mask, gv, 0.0)).to(dev)
+            iters, its = 100, C.c_int()
+            for rep in range(2):
+                xt = x0.clone()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                _capi.check(_capi.lib().b200fem_cg_solve_dev(lop.handle, C.c_void_p(bt.data_ptr()), C.c_void_p(xt.data_ptr()), 0.0, iters,
+                                                             _capi.TOL_ABSOLUTE, C.byref(its), None))
+                e1.record(stream)
+                torch.cuda.synchronize()
+                cg_ms = e0.elapsed_time(e1)
+            cg[name] = {"dofs": sp.size, "iterations": abs(its.value), "s_per_iteration": cg_ms * 1e-3 / iters,
+                        "dofs_per_s": sp.size * iters / (cg_ms * 1e-3), "launches_per_iteration": lop.timing()["launches_per_apply"] + 7}
+            del bt, x0, xt, lop, sp, g
 
     if rank != 0:
         if world > 1:
@@ -276,7 +329,7 @@ def main():
                    "dofs_per_gpu": ndof_local, "process_grid": proc, "halo_exchange": world > 1,
                    "l2": f"{npairs} rotating (u,w) buffer pairs = {npairs * 2 * 8 * space.size / 1e6:.0f} MB > 126 MB L2",
                    "kernel": kernel_name},
-        "roofline": roofline, "linear_apply": linear_apply, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
+        "roofline": roofline, "linear_apply": linear_apply, "cg": cg, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "host_issue_us_per_step": host_us, "exchange_ms_last": tinfo.get("last_exchange_ms"), "multi_gpu_diag": diag,
         "clocks": sampler.result(),
     }
     print(json.dumps(line), flush=True)

@@ -59,7 +59,9 @@ struct b200fem_operator {
   double *d_u = nullptr, *d_w = nullptr;                       // staging for the host-pointer API
   double *d_h = nullptr, *d_r = nullptr, *d_p = nullptr, *d_x = nullptr, *d_b = nullptr, *d_partial = nullptr, *d_sums = nullptr, *d_hist = nullptr;
   CgState* d_cg = nullptr; int hist_cap = 0;
-  HaloPlan halo;
+  bool kron_ready = false; std::vector<unsigned char> kron_tab; struct KronMapCache* map_cache = nullptr;
+  HaloPlan halo; HaloPlanDG halo_dg; HaloPlanP2P halo_p2p; const BoxDev* active_box = nullptr; int reserve_sms = 0;      // active_box: sub-box override for split launches
+  cudaStream_t comm_stream = nullptr; cudaEvent_t ev_bnd = nullptr, ev_comm = nullptr, dbg_ev[2] = {nullptr, nullptr};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evx0 = nullptr, evx1 = nullptr; b200fem_timing timing{};
 };
 
@@ -249,7 +251,7 @@ static bool default_quadrature(const b200fem_operator* op) {
 }
 
 template <int N> static int launch_dg_quadrature(b200fem_operator* op, const double* u, double* w, const double* bvec, bool with_data) {
-  using Cfg = DgQuadCfg<N>; const BoxDev& b = op->sp->box;
+  using Cfg = DgQuadCfg<N>; const BoxDev& b = op->active_box ? *op->active_box : op->sp->box;
   const long long n_owned = (long long)(b.own_hi[0] - b.own_lo[0]) * (b.own_hi[1] - b.own_lo[1]) * (b.own_hi[2] - b.own_lo[2]);
   auto kern = dg_quadrature_kernel<N, AdrIntegrands>;
   CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes()));
@@ -258,7 +260,7 @@ template <int N> static int launch_dg_quadrature(b200fem_operator* op, const dou
   CUDA_OK(cudaGetLastError()); return B200FEM_OK;
 }
 template <int N, int TX, int TY, int TZ> static int launch_dg_kronecker(b200fem_operator* op, const double* u, double* w, const double* bvec) {
-  using Cfg = KronCfg<N, TX, TY, TZ>; const BoxDev& b = op->sp->box;
+  using Cfg = KronCfg<N, TX, TY, TZ>; const BoxDev& b = op->active_box ? *op->active_box : op->sp->box;
   KronHost kh = build_kron_tables(op->sp->tab, op->model, b.dim, b.h);
   KronTabDev<N> K;
   for (int d = 0; d < 3; ++d) for (int i = 0; i < N * N; ++i) { K.S[d][i] = kh.S[d][i]; K.Dlo[d][i] = kh.Dlo[d][i]; K.Dhi[d][i] = kh.Dhi[d][i]; K.L[d][i] = kh.L[d][i]; K.R[d][i] = kh.R[d][i]; }
@@ -270,7 +272,7 @@ template <int N, int TX, int TY, int TZ> static int launch_dg_kronecker(b200fem_
 }
 template <int N, bool HIER> static int launch_dg_kronecker_tma(b200fem_operator* op, const double* u, double* w, const double* bvec) {
   constexpr int TX = 8, TY = 4, TZ = 4;
-  using Cfg = KronTmaCfg<N, TX, TY, TZ>; const BoxDev& b = op->sp->box;
+  using Cfg = KronTmaCfg<N, TX, TY, TZ>; const BoxDev& b = op->active_box ? *op->active_box : op->sp->box;
   KronHost kh = build_kron_tables(op->sp->tab, op->model, b.dim, b.h);
   KronTabDev<N> K;
   for (int d = 0; d < 3; ++d) for (int i = 0; i < N * N; ++i) { K.S[d][i] = kh.S[d][i]; K.Dlo[d][i] = kh.Dlo[d][i]; K.Dhi[d][i] = kh.Dhi[d][i]; K.L[d][i] = kh.L[d][i]; K.R[d][i] = kh.R[d][i]; }
@@ -298,40 +300,63 @@ static bool make_map3(CUtensorMap* m, const double* base, uint64_t d0, uint64_t 
                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 template <int N> static bool tensor_path_ok(const b200fem_operator* op, const double* u, const double* w, const double* bvec) {
-  const BoxDev& b = op->sp->box;
+  const BoxDev& b = op->active_box ? *op->active_box : op->sp->box;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   return N == 3 && b.n[0] % 2 == 0 && b.own_lo[0] % 2 == 0 && al16(u) && al16(w) && (!bvec || al16(bvec)) && ensure_encode_tiled();
 }
+// Host-side cost matters at 40 us per apply: the 1-D operator tables are built once per operator, the kernel attribute
+// is set once per instantiation, and encoded tensor maps are cached per (u, w, b, owned range).
+struct KronMapKey { const void *u, *w, *b; int lo[3], hi[3]; bool operator==(const KronMapKey& o) const { return std::memcmp(this, &o, sizeof(KronMapKey)) == 0; } };
+struct KronMapCache { static constexpr int kSlots = 32; KronMapKey key[kSlots]; KronTensorMaps maps[kSlots]; bool valid[kSlots] = {}; int next = 0; };
 template <int N, bool HIER, bool SPLIT> static int launch_dg_kronecker_tensor(b200fem_operator* op, const double* u, double* w, const double* bvec) {
   constexpr int TX = 8, TY = 4, TZ = 4, N3 = N * N * N;
-  using Cfg = KronTensorCfg<N, TX, TY, TZ, SPLIT>; const BoxDev& b = op->sp->box;
-  KronHost kh = build_kron_tables(op->sp->tab, op->model, b.dim, b.h);
-  KronTabDev<N> K;
-  for (int d = 0; d < 3; ++d) for (int i = 0; i < N * N; ++i) { K.S[d][i] = kh.S[d][i]; K.Dlo[d][i] = kh.Dlo[d][i]; K.Dhi[d][i] = kh.Dhi[d][i]; K.L[d][i] = kh.L[d][i]; K.R[d][i] = kh.R[d][i]; }
+  using Cfg = KronTensorCfg<N, TX, TY, TZ, SPLIT>; const BoxDev& b = op->active_box ? *op->active_box : op->sp->box;
+  if (!op->kron_ready) {
+    KronHost kh = build_kron_tables(op->sp->tab, op->model, b.dim, b.h);
+    op->kron_tab.resize(sizeof(KronTabDev<N>));
+    KronTabDev<N>& K0 = *reinterpret_cast<KronTabDev<N>*>(op->kron_tab.data());
+    for (int d = 0; d < 3; ++d) for (int i = 0; i < N * N; ++i) { K0.S[d][i] = kh.S[d][i]; K0.Dlo[d][i] = kh.Dlo[d][i]; K0.Dhi[d][i] = kh.Dhi[d][i]; K0.L[d][i] = kh.L[d][i]; K0.R[d][i] = kh.R[d][i]; }
+    op->kron_ready = true;
+  }
+  const KronTabDev<N>& K = *reinterpret_cast<const KronTabDev<N>*>(op->kron_tab.data());
   const int on[3] = {b.own_hi[0] - b.own_lo[0], b.own_hi[1] - b.own_lo[1], b.own_hi[2] - b.own_lo[2]};
   const int tx = (on[0] + TX - 1) / TX, ty = (on[1] + TY - 1) / TY, tz = (on[2] + TZ - 1) / TZ, ntiles = tx * ty * tz;
-  const uint64_t s1 = (uint64_t)b.n[0] * N3 * 8, s2 = s1 * b.n[1];
-  const long long own_off = ((long long)b.own_lo[0] + (long long)b.n[0] * (b.own_lo[1] + (long long)b.n[1] * b.own_lo[2])) * N3;
-  KronTensorMaps M;
-  bool ok = make_map3(&M.u_tile, u, (uint64_t)b.n[0] * N3, b.n[1], b.n[2], s1, s2, TX * N3, TY, TZ) &&
-            make_map3(&M.u_xhalo, u, (uint64_t)b.n[0] * N3, b.n[1], b.n[2], s1, s2, 2 * N3, TY, TZ) &&
-            make_map3(&M.u_yhalo, u, (uint64_t)b.n[0] * N3, b.n[1], b.n[2], s1, s2, TX * N3, 1, TZ) &&
-            make_map3(&M.u_zhalo, u, (uint64_t)b.n[0] * N3, b.n[1], b.n[2], s1, s2, TX * N3, TY, 1) &&
-            make_map3(&M.w_tile, w + own_off, (uint64_t)on[0] * N3, on[1], on[2], s1, s2, TX * N3, TY, TZ) &&
-            make_map3(&M.b_tile, (bvec ? bvec : w) + own_off, (uint64_t)on[0] * N3, on[1], on[2], s1, s2, TX * N3, TY, TZ);
-  REQUIRE(ok, B200FEM_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  if (!op->map_cache) op->map_cache = new KronMapCache;
+  KronMapCache& mc = *op->map_cache;
+  KronMapKey key; std::memset(&key, 0, sizeof(key)); key.u = u; key.w = w; key.b = bvec;
+  for (int d = 0; d < 3; ++d) { key.lo[d] = b.own_lo[d]; key.hi[d] = b.own_hi[d]; }
+  int slot = -1;
+  for (int i = 0; i < KronMapCache::kSlots; ++i) if (mc.valid[i] && mc.key[i] == key) { slot = i; break; }
+  if (slot < 0) {
+    slot = mc.next; mc.next = (mc.next + 1) % KronMapCache::kSlots;
+    const uint64_t s1 = (uint64_t)b.n[0] * N3 * 8, s2 = s1 * b.n[1];
+    const long long own_off = ((long long)b.own_lo[0] + (long long)b.n[0] * (b.own_lo[1] + (long long)b.n[1] * b.own_lo[2])) * N3;
+    KronTensorMaps& M = mc.maps[slot];
+    bool ok = make_map3(&M.u_tile, u, (uint64_t)b.n[0] * N3, b.n[1], b.n[2], s1, s2, TX * N3, TY, TZ) &&
+              make_map3(&M.u_xhalo, u, (uint64_t)b.n[0] * N3, b.n[1], b.n[2], s1, s2, 2 * N3, TY, TZ) &&
+              make_map3(&M.u_yhalo, u, (uint64_t)b.n[0] * N3, b.n[1], b.n[2], s1, s2, TX * N3, 1, TZ) &&
+              make_map3(&M.u_zhalo, u, (uint64_t)b.n[0] * N3, b.n[1], b.n[2], s1, s2, TX * N3, TY, 1) &&
+              make_map3(&M.w_tile, w + own_off, (uint64_t)on[0] * N3, on[1], on[2], s1, s2, TX * N3, TY, TZ) &&
+              make_map3(&M.b_tile, (bvec ? bvec : w) + own_off, (uint64_t)on[0] * N3, on[1], on[2], s1, s2, TX * N3, TY, TZ);
+    REQUIRE(ok, B200FEM_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+    mc.key[slot] = key; mc.valid[slot] = true;
+  }
   static int sms = 0;
   if (!sms) CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, op->sp->mesh->ctx->device));
   auto kern = dg_kronecker_tensor_kernel<N, HIER, TX, TY, TZ, SPLIT>;
-  CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes()));
-  kern<<<(unsigned)std::min(ntiles, sms), Cfg::kThreads, Cfg::smem_bytes(), op->sp->mesh->ctx->stream>>>(K, b, M, bvec ? 1 : 0, tx, ty, ntiles);
+  static bool attr_set = false;
+  if (!attr_set) { CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes())); attr_set = true; }
+  // a persistent grid fills every SM for its whole run time; while a halo exchange is in flight a few SMs are left free so
+  // that the exchange kernels are guaranteed to run concurrently
+  const int grid = std::max(1, std::min(ntiles, sms - op->reserve_sms));
+  kern<<<(unsigned)grid, Cfg::kThreads, Cfg::smem_bytes(), op->sp->mesh->ctx->stream>>>(K, b, mc.maps[slot], bvec ? 1 : 0, tx, ty, ntiles);
   CUDA_OK(cudaGetLastError()); return B200FEM_OK;
 }
 
 static long long* g_dbg = nullptr; static int g_dbg_calls = 0;
 template <int N, bool HIER, bool SPLIT> static int launch_dg_kronecker_pipe(b200fem_operator* op, const double* u, double* w, const double* bvec) {
   constexpr int TX = 8, TY = 4, TZ = 4;
-  using Cfg = KronPipeCfg<N, TX, TY, TZ, SPLIT>; const BoxDev& b = op->sp->box;
+  using Cfg = KronPipeCfg<N, TX, TY, TZ, SPLIT>; const BoxDev& b = op->active_box ? *op->active_box : op->sp->box;
   KronHost kh = build_kron_tables(op->sp->tab, op->model, b.dim, b.h);
   KronTabDev<N> K;
   for (int d = 0; d < 3; ++d) for (int i = 0; i < N * N; ++i) { K.S[d][i] = kh.S[d][i]; K.Dlo[d][i] = kh.Dlo[d][i]; K.Dhi[d][i] = kh.Dhi[d][i]; K.L[d][i] = kh.L[d][i]; K.R[d][i] = kh.R[d][i]; }
@@ -352,7 +377,7 @@ template <int N, bool HIER, bool SPLIT> static int launch_dg_kronecker_pipe(b200
   return B200FEM_OK;
 }
 template <int N> static int launch_lagrange(b200fem_operator* op, const double* u, double* w, bool with_data) {
-  const BoxDev& b = op->sp->box; cudaStream_t st = op->sp->mesh->ctx->stream;
+  const BoxDev& b = op->active_box ? *op->active_box : op->sp->box; cudaStream_t st = op->sp->mesh->ctx->stream;
   CUDA_OK(cudaMemsetAsync(w, 0, sizeof(double) * (size_t)op->sp->size, st));                 // w.clear() (galerkin.hh:1463)
   AdrIntegrands I = make_integrands(op, with_data);
   int launches = 1;
@@ -447,16 +472,54 @@ static int ensure_bvec(b200fem_operator* op) {
   op->d_bvec = bv; return B200FEM_OK;
 }
 
+static int exchange(b200fem_operator* op, double* v, cudaStream_t st) {
+  b200fem_space* s = op->sp; b200fem_ctx* c = s->mesh->ctx;
+  int rc = s->kind == B200FEM_LAGRANGE ? halo_exchange(op->halo, c->nccl, c->comm, v, true, st)
+           : op->halo_p2p.built        ? halo_exchange_p2p(op->halo_p2p, v, st)
+                                       : halo_exchange_dg(op->halo_dg, c->nccl, c->comm, v, st);
+  return rc ? fail(B200FEM_ERR_COMM, "halo exchange failed") : B200FEM_OK;
+}
+
+// GalerkinOperator::evaluate + w.communicate() (galerkin.hh:1459-1496).  On several ranks the DG apply is split: the owned
+// layers next to rank interfaces are computed first, their Copy exchange then runs on a second stream while the interior
+// is computed -- the exchange the reference performs serially after the loop is hidden behind the interior elements.
 static int apply_dev_impl(b200fem_operator* op, const double* u, double* w, bool linear) {
   b200fem_space* s = op->sp; cudaStream_t st = s->mesh->ctx->stream;
   CUDA_OK(cudaSetDevice(s->mesh->ctx->device));
-  if (op->d_bvec == nullptr && !linear && op->model.data && s->kind != B200FEM_LAGRANGE) { /* built lazily inside apply_local when needed */ }
   CUDA_OK(cudaEventRecord(op->ev0, st));
-  int rc = apply_local(op, u, w, linear); if (rc) return rc;
-  if (op->communicate && s->mesh->ctx->world > 1) {
-    CUDA_OK(cudaEventRecord(op->evx0, st));
-    rc = halo_exchange(op->halo, s->mesh->ctx->nccl, s->mesh->ctx->comm, w, s->kind == B200FEM_LAGRANGE, st); if (rc) return fail(B200FEM_ERR_COMM, "halo exchange failed");
-    CUDA_OK(cudaEventRecord(op->evx1, st));
+  const bool distributed = op->communicate && s->mesh->ctx->world > 1;
+  int rc;
+  if (distributed && s->kind != B200FEM_LAGRANGE && op->comm_stream) {
+    // boundary sub-boxes: per split axis, one slab at each interface (thickness = one tile layer), carved successively
+    // out of the owned box so that the pieces do not overlap
+    const BoxDev& full = s->box; BoxDev rest = full; std::vector<BoxDev> bnd;
+    const int thick[3] = {8, 4, 4};
+    for (int a = 2; a >= 0; --a) {
+      const bool lo_if = full.own_lo[a] > 0, hi_if = full.own_hi[a] < full.n[a];
+      if (lo_if && rest.own_hi[a] - rest.own_lo[a] > 0) { BoxDev b = rest; b.own_hi[a] = std::min(rest.own_hi[a], rest.own_lo[a] + thick[a]); bnd.push_back(b); rest.own_lo[a] = b.own_hi[a]; }
+      if (hi_if && rest.own_hi[a] - rest.own_lo[a] > 0) { BoxDev b = rest; b.own_lo[a] = std::max(rest.own_lo[a], rest.own_hi[a] - thick[a]); bnd.push_back(b); rest.own_hi[a] = b.own_lo[a]; }
+    }
+    int launches = 0;
+    for (const BoxDev& b : bnd) { op->active_box = &b; rc = apply_local(op, u, w, linear); op->active_box = nullptr; if (rc) return rc; launches += op->timing.launches_per_apply; }
+    CUDA_OK(cudaEventRecord(op->ev_bnd, st));
+    if (op->dbg_ev[0]) CUDA_OK(cudaEventRecord(op->dbg_ev[0], st));
+    CUDA_OK(cudaStreamWaitEvent(op->comm_stream, op->ev_bnd, 0));
+    CUDA_OK(cudaEventRecord(op->evx0, op->comm_stream));
+    rc = exchange(op, w, op->comm_stream); if (rc) return rc;
+    CUDA_OK(cudaEventRecord(op->evx1, op->comm_stream));
+    CUDA_OK(cudaEventRecord(op->ev_comm, op->comm_stream));
+    bool has_rest = true; for (int a = 0; a < 3; ++a) has_rest = has_rest && rest.own_hi[a] > rest.own_lo[a];
+    if (has_rest) { op->active_box = &rest; op->reserve_sms = 8; rc = apply_local(op, u, w, linear); op->active_box = nullptr; op->reserve_sms = 0; if (rc) return rc; launches += op->timing.launches_per_apply; }
+    if (op->dbg_ev[1]) CUDA_OK(cudaEventRecord(op->dbg_ev[1], st));
+    CUDA_OK(cudaStreamWaitEvent(st, op->ev_comm, 0));
+    op->timing.launches_per_apply = launches + 3 * (int)op->halo_dg.nb.size();
+  } else {
+    rc = apply_local(op, u, w, linear); if (rc) return rc;
+    if (distributed) {
+      CUDA_OK(cudaEventRecord(op->evx0, st));
+      rc = exchange(op, w, st); if (rc) return rc;
+      CUDA_OK(cudaEventRecord(op->evx1, st));
+    }
   }
   // DirichletWrapperOperator: op_(u,w) (communication included) first, then subConstraints (dirichletwrapper.hh:101-105)
   if (op->model.strong_dirichlet && op->d_dmask) {
@@ -465,6 +528,12 @@ static int apply_dev_impl(b200fem_operator* op, const double* u, double* w, bool
   }
   CUDA_OK(cudaEventRecord(op->ev1, st));
   op->timing.applies += 1;
+  if (op->dbg_ev[0] && op->timing.applies == 300) {
+    CUDA_OK(cudaEventSynchronize(op->ev1)); float a, b, c, d, e;
+    cudaEventElapsedTime(&a, op->ev0, op->dbg_ev[0]); cudaEventElapsedTime(&b, op->ev0, op->evx0); cudaEventElapsedTime(&c, op->ev0, op->evx1);
+    cudaEventElapsedTime(&d, op->ev0, op->dbg_ev[1]); cudaEventElapsedTime(&e, op->ev0, op->ev1);
+    std::fprintf(stderr, "[b200fem timeline us] boundary done %.1f | exchange start %.1f end %.1f | interior done %.1f | apply done %.1f\n", a * 1e3, b * 1e3, c * 1e3, d * 1e3, e * 1e3);
+  }
   return B200FEM_OK;
 }
 
@@ -511,15 +580,36 @@ extern "C" int b200fem_operator_create(b200fem_space* s, const b200fem_model* mo
   CUDA_OK(cudaEventCreate(&op->ev0)); CUDA_OK(cudaEventCreate(&op->ev1)); CUDA_OK(cudaEventCreate(&op->evx0)); CUDA_OK(cudaEventCreate(&op->evx1));
   if (s->mesh->ctx->world > 1) {
     int rc = halo_plan_build(op->halo, s->mesh->proc, s->mesh->pc, s->box, s->kind == B200FEM_LAGRANGE, s->kind == B200FEM_LAGRANGE ? s->order : 0, s->nb, s->lay, s->size, &op->d_aux);
+    if (!rc && s->kind != B200FEM_LAGRANGE) rc = halo_plan_dg_build(op->halo_dg, s->mesh->proc, s->mesh->pc, s->box, s->nb);
     if (rc) { delete op; return fail(B200FEM_ERR_COMM, "halo plan failed"); }
+    // peer-memory mailboxes (all ranks must take the same decision: it depends only on the environment and on CUDA IPC
+    // working on this box); falls back to NCCL send/recv
+    if (s->kind != B200FEM_LAGRANGE && !std::getenv("B200FEM_NO_P2P")) {
+      b200fem_ctx* c = s->mesh->ctx;
+      if (halo_plan_p2p_build(op->halo_p2p, op->halo_dg, c->nccl, c->comm, c->rank, c->world, s->mesh->proc, s->mesh->pc, s->mesh->gn, s->nb, c->stream) != 0) {
+        halo_plan_p2p_free(op->halo_p2p); cudaGetLastError();
+      }
+      // agree on the outcome: one failing rank switches everybody to NCCL
+      int ok = op->halo_p2p.built ? 1 : 0; int* d_ok = nullptr; CUDA_OK(cudaMalloc(&d_ok, sizeof(int)));
+      CUDA_OK(cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice));
+      if (c->nccl.AllReduce(d_ok, d_ok, 1, /*ncclInt32*/ 2, /*ncclMin*/ 3, c->comm, c->stream) != 0) { delete op; return fail(B200FEM_ERR_COMM, "ncclAllReduce failed"); }
+      CUDA_OK(cudaStreamSynchronize(c->stream)); CUDA_OK(cudaMemcpy(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost)); cudaFree(d_ok);
+      if (!ok) halo_plan_p2p_free(op->halo_p2p);
+    }
+    { int lo_p = 0, hi_p = 0; CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p)); CUDA_OK(cudaStreamCreateWithPriority(&op->comm_stream, cudaStreamNonBlocking, hi_p)); }
+    CUDA_OK(cudaEventCreateWithFlags(&op->ev_bnd, cudaEventDisableTiming)); CUDA_OK(cudaEventCreateWithFlags(&op->ev_comm, cudaEventDisableTiming));
+    if (std::getenv("B200FEM_DEBUG_EVENTS")) { CUDA_OK(cudaEventCreate(&op->dbg_ev[0])); CUDA_OK(cudaEventCreate(&op->dbg_ev[1])); }
   }
   *out = op; return B200FEM_OK;
 }
+static void free_map_cache(b200fem_operator* op) { delete op->map_cache; op->map_cache = nullptr; }
 extern "C" int b200fem_operator_destroy(b200fem_operator* op) {
   if (!op) return B200FEM_OK;
   for (void* p : {(void*)op->d_perm, (void*)op->d_bvec, (void*)op->d_dmask, (void*)op->d_dvals, (void*)op->d_aux, (void*)op->d_u, (void*)op->d_w, (void*)op->d_h, (void*)op->d_r,
                   (void*)op->d_p, (void*)op->d_x, (void*)op->d_b, (void*)op->d_partial, (void*)op->d_sums, (void*)op->d_hist, (void*)op->d_cg}) if (p) cudaFree(p);
-  halo_plan_free(op->halo);
+  halo_plan_p2p_free(op->halo_p2p); halo_plan_free(op->halo); halo_plan_dg_free(op->halo_dg); free_map_cache(op);
+  if (op->comm_stream) cudaStreamDestroy(op->comm_stream);
+  for (cudaEvent_t e : {op->ev_bnd, op->ev_comm}) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : {op->ev0, op->ev1, op->evx0, op->evx1}) if (e) cudaEventDestroy(e);
   delete op; return B200FEM_OK;
 }
@@ -673,6 +763,5 @@ extern "C" int b200fem_nccl_init(b200fem_ctx* c, const void* id128, int rank, in
 extern "C" int b200fem_communicate_dev(b200fem_operator* op, double* v) {
   REQUIRE(op && v, B200FEM_ERR_INVALID, "communicate: null argument");
   b200fem_ctx* c = op->sp->mesh->ctx; if (c->world <= 1) return B200FEM_OK;
-  if (halo_exchange(op->halo, c->nccl, c->comm, v, op->sp->kind == B200FEM_LAGRANGE, c->stream) != 0) return fail(B200FEM_ERR_COMM, "halo exchange failed");
-  return B200FEM_OK;
+  return exchange(op, v, c->stream);
 }

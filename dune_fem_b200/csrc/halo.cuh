@@ -32,6 +32,7 @@ struct NcclApi {
   int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   bool ok() const { return handle != nullptr; }
@@ -47,6 +48,7 @@ struct NcclApi {
     Send = (int (*)(const void*, size_t, int, int, void*, cudaStream_t))sym("ncclSend");
     Recv = (int (*)(void*, size_t, int, int, void*, cudaStream_t))sym("ncclRecv");
     AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))sym("ncclAllReduce");
+    AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))sym("ncclAllGather");
     GroupStart = (int (*)())sym("ncclGroupStart");
     GroupEnd = (int (*)())sym("ncclGroupEnd");
     if (!(GetUniqueId && CommInitRank && CommDestroy && Send && Recv && AllReduce && GroupStart && GroupEnd)) { handle = nullptr; return false; }
@@ -139,6 +141,213 @@ inline int halo_plan_build(HaloPlan& p, const int proc[3], const int pc[3], cons
   if (cudaMalloc(d_aux_out, (size_t)size) != cudaSuccess) return -1;
   cudaMemcpy(*d_aux_out, aux.data(), (size_t)size, cudaMemcpyHostToDevice);
   p.built = true; return 0;
+}
+
+// ---- single-phase exchange for DG spaces: every existing neighbour among the 26 (faces, edges, corners) gets its own
+// message inside ONE ncclGroup, so ghost copies are fully consistent after one round trip (Copy has no ordering issue).
+struct HaloNeighbour { int peer = -1; long long count = 0; long long *d_send_idx = nullptr, *d_recv_idx = nullptr; double *d_send = nullptr, *d_recv = nullptr; };
+struct HaloPlanDG { int block = 1; std::vector<HaloNeighbour> nb; bool built = false; };
+
+inline void halo_plan_dg_free(HaloPlanDG& p) {
+  for (auto& h : p.nb) for (void* q : {(void*)h.d_send_idx, (void*)h.d_recv_idx, (void*)h.d_send, (void*)h.d_recv}) if (q) cudaFree(q);
+  p.nb.clear(); p.built = false;
+}
+inline int halo_plan_dg_build(HaloPlanDG& p, const int proc[3], const int pc[3], const BoxDev& box, int nb) {
+  p.block = nb;
+  for (int dz = -1; dz <= 1; ++dz) for (int dy = -1; dy <= 1; ++dy) for (int dx = -1; dx <= 1; ++dx) {
+    if (!dx && !dy && !dz) continue;
+    const int dir[3] = {dx, dy, dz}; int nc[3]; bool ok = true;
+    for (int a = 0; a < 3; ++a) { nc[a] = pc[a] + dir[a]; if (nc[a] < 0 || nc[a] >= proc[a]) ok = false; }
+    if (!ok) continue;
+    HaloNeighbour h; h.peer = nc[0] + proc[0] * (nc[1] + proc[1] * nc[2]);
+    int slo[3], shi[3], rlo[3], rhi[3];
+    for (int a = 0; a < 3; ++a) {
+      if (dir[a] == 0) { slo[a] = rlo[a] = box.own_lo[a]; shi[a] = rhi[a] = box.own_hi[a]; }
+      else if (dir[a] < 0) { slo[a] = box.own_lo[a]; shi[a] = slo[a] + 1; rlo[a] = box.own_lo[a] - 1; rhi[a] = box.own_lo[a]; }
+      else { shi[a] = box.own_hi[a]; slo[a] = shi[a] - 1; rlo[a] = box.own_hi[a]; rhi[a] = rlo[a] + 1; }
+    }
+    std::vector<long long> send, recv;
+    for (int z = slo[2]; z < shi[2]; ++z) for (int y = slo[1]; y < shi[1]; ++y) for (int x = slo[0]; x < shi[0]; ++x) send.push_back((x + (long long)box.n[0] * (y + (long long)box.n[1] * z)) * nb);
+    for (int z = rlo[2]; z < rhi[2]; ++z) for (int y = rlo[1]; y < rhi[1]; ++y) for (int x = rlo[0]; x < rhi[0]; ++x) recv.push_back((x + (long long)box.n[0] * (y + (long long)box.n[1] * z)) * nb);
+    h.count = (long long)send.size();
+    if (h.count == 0 || send.size() != recv.size()) continue;
+    const size_t ib = sizeof(long long) * send.size(), db = sizeof(double) * send.size() * nb;
+    if (cudaMalloc(&h.d_send_idx, ib) != cudaSuccess || cudaMalloc(&h.d_recv_idx, ib) != cudaSuccess || cudaMalloc(&h.d_send, db) != cudaSuccess || cudaMalloc(&h.d_recv, db) != cudaSuccess) return -1;
+    cudaMemcpy(h.d_send_idx, send.data(), ib, cudaMemcpyHostToDevice); cudaMemcpy(h.d_recv_idx, recv.data(), ib, cudaMemcpyHostToDevice);
+    p.nb.push_back(h);
+  }
+  p.built = true; return 0;
+}
+inline int halo_exchange_dg(HaloPlanDG& p, NcclApi& nccl, void* comm, double* v, cudaStream_t st) {
+  if (!p.built) return -1;
+  if (p.nb.empty()) return 0;
+  for (auto& h : p.nb) { const long long total = h.count * p.block; const int grid = (int)std::min<long long>(592, (total + 255) / 256);
+    halo_pack_kernel<<<grid, 256, 0, st>>>(v, h.d_send_idx, h.count, p.block, h.d_send); }
+  if (nccl.GroupStart() != 0) return -1;
+  for (auto& h : p.nb) {
+    if (nccl.Send(h.d_send, (size_t)(h.count * p.block), 8, h.peer, comm, st) != 0) return -1;
+    if (nccl.Recv(h.d_recv, (size_t)(h.count * p.block), 8, h.peer, comm, st) != 0) return -1;
+  }
+  if (nccl.GroupEnd() != 0) return -1;
+  for (auto& h : p.nb) { const long long total = h.count * p.block; const int grid = (int)std::min<long long>(592, (total + 255) / 256);
+    halo_unpack_kernel<<<grid, 256, 0, st>>>(v, h.d_recv_idx, h.count, p.block, h.d_recv, 0); }
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// ---- peer-memory exchange (all ranks on one NVSwitch box, one process per GPU) ----------------------------------------
+// Every rank owns a mailbox area (plain cudaMalloc, exported with cudaIpcGetMemHandle, handles all-gathered once through
+// NCCL).  Per neighbour the mailbox holds two data buffers, two `ready` sequence flags (written by the neighbour when
+// its message has landed) and one `ack` flag (written by the neighbour when it has consumed my message).  An exchange is
+// two launches on the communication stream and no library call:
+//   send kernel:   wait ack >= seq-2  ->  gather the owned layer and store it DIRECTLY into the neighbour's mailbox over
+//                  NVLink  ->  __threadfence_system  ->  last block publishes ready[seq&1] = seq in the neighbour's memory
+//   recv kernel:   spin on my ready[seq&1] >= seq  ->  scatter the mailbox into the ghost layer  ->  last block
+//                  publishes ack = seq in the neighbour's memory
+struct P2PNeighbourDev {
+  long long count; const long long* send_idx; const long long* recv_idx;
+  double* remote_data[2]; unsigned long long* remote_ready; unsigned long long* remote_ack;     // in the peer's mailbox
+  double* local_data[2]; unsigned long long* local_ready; unsigned long long* local_ack;        // in my mailbox
+  unsigned int* counters;                                                                        // [0] send, [1] recv block counters (local)
+};
+struct HaloPlanP2P {
+  bool built = false; int block = 1; int nnb = 0; unsigned long long seq = 0;
+  P2PNeighbourDev* d_nb = nullptr; void* mailbox = nullptr; unsigned int* d_counters = nullptr; int* d_error = nullptr;
+  std::vector<void*> opened;          // peer mappings to close
+};
+constexpr int kP2PBlocksPerNb = 64;
+constexpr long long kP2PSpinLimit = 4000000000ll;   // ~2 s of SM clocks: a lost peer must not hang the box
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+
+__global__ void __launch_bounds__(256) p2p_send_kernel(const double* __restrict__ v, const P2PNeighbourDev* __restrict__ nbs, int block, unsigned long long seq, int* error) {
+  const P2PNeighbourDev nb = nbs[blockIdx.x / kP2PBlocksPerNb];
+  const int part = blockIdx.x % kP2PBlocksPerNb;
+  if (threadIdx.x == 0 && seq > 2) {                       // the buffer was last used by message seq-2: has it been consumed?
+    const long long t0 = clock64();
+    while (ld_acquire_sys(nb.local_ack) < seq - 2) if (clock64() - t0 > kP2PSpinLimit) { *error = 1; break; }
+  }
+  __syncthreads();
+  double* dst = nb.remote_data[seq & 1];
+  // one warp per element block (no integer division in the copy loop); stores to the peer are contiguous per warp
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (long long e = (long long)part * wpb + warp; e < nb.count; e += (long long)kP2PBlocksPerNb * wpb) {
+    const double* src = v + nb.send_idx[e]; double* d = dst + e * block;
+    for (int j = lane; j < block; j += 32) d[j] = src[j];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();                                // cumulative over the block's stores (ordered by the barrier)
+    if (atomicAdd(&nb.counters[0], 1u) == kP2PBlocksPerNb - 1) { nb.counters[0] = 0; __threadfence_system(); st_release_sys(&nb.remote_ready[seq & 1], seq); }
+  }
+}
+__global__ void __launch_bounds__(256) p2p_recv_kernel(double* __restrict__ v, const P2PNeighbourDev* __restrict__ nbs, int block, unsigned long long seq, int* error) {
+  const P2PNeighbourDev nb = nbs[blockIdx.x / kP2PBlocksPerNb];
+  const int part = blockIdx.x % kP2PBlocksPerNb;
+  if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(&nb.local_ready[seq & 1]) < seq) if (clock64() - t0 > kP2PSpinLimit) { *error = 2; break; }
+  }
+  __syncthreads();
+  const double* src = nb.local_data[seq & 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (long long e = (long long)part * wpb + warp; e < nb.count; e += (long long)kP2PBlocksPerNb * wpb) {
+    const double* sp = src + e * block; double* d = v + nb.recv_idx[e];
+    for (int j = lane; j < block; j += 32) d[j] = sp[j];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(&nb.counters[1], 1u) == kP2PBlocksPerNb - 1) { nb.counters[1] = 0; __threadfence_system(); st_release_sys(nb.remote_ack, seq); }
+  }
+}
+
+inline void halo_plan_p2p_free(HaloPlanP2P& p) {
+  for (void* q : p.opened) cudaIpcCloseMemHandle(q);
+  for (void* q : {(void*)p.d_nb, p.mailbox, (void*)p.d_counters, (void*)p.d_error}) if (q) cudaFree(q);
+  p = HaloPlanP2P();
+}
+
+// mailbox layout of a rank: for each of its neighbours in the fixed 26-direction order: data[2][count*block] doubles,
+// then ready[2] + ack (3 x u64, padded to 32 B).  `counts` = messages sizes (elements) in that order.
+struct MailboxLayout { std::vector<int> dir; std::vector<long long> count; std::vector<size_t> offset; size_t bytes = 0; };
+inline MailboxLayout mailbox_layout(const int proc[3], const int pc[3], const int own_n[3], int nb) {
+  MailboxLayout L; size_t off = 0;
+  for (int dz = -1; dz <= 1; ++dz) for (int dy = -1; dy <= 1; ++dy) for (int dx = -1; dx <= 1; ++dx) {
+    if (!dx && !dy && !dz) continue;
+    const int dir[3] = {dx, dy, dz}; bool ok = true; long long cnt = 1;
+    for (int a = 0; a < 3; ++a) { const int c = pc[a] + dir[a]; if (c < 0 || c >= proc[a]) ok = false; cnt *= dir[a] == 0 ? own_n[a] : 1; }
+    if (!ok || cnt == 0) continue;
+    L.dir.push_back((dx + 1) + 3 * ((dy + 1) + 3 * (dz + 1))); L.count.push_back(cnt); L.offset.push_back(off);
+    off += 2 * (size_t)cnt * nb * sizeof(double) + 32; off = (off + 255) / 256 * 256;
+  }
+  L.bytes = off; return L;
+}
+
+// own extents of rank coordinates c under the block distribution of b200fem_partition_box
+inline void block_extents(const int gn[3], const int proc[3], const int c[3], int out[3]) {
+  for (int a = 0; a < 3; ++a) { const int q = gn[a] / proc[a], r = gn[a] % proc[a]; out[a] = q + (c[a] < r ? 1 : 0); }
+}
+
+inline int halo_plan_p2p_build(HaloPlanP2P& p, HaloPlanDG& dg, NcclApi& nccl, void* comm, int rank, int world, const int proc[3], const int pc[3],
+                               const int gn[3], int nb, cudaStream_t st) {
+  if (!dg.built || !nccl.AllGather) return -1;
+  int own_n[3]; block_extents(gn, proc, pc, own_n);
+  MailboxLayout mine = mailbox_layout(proc, pc, own_n, nb);
+  if (mine.dir.size() != dg.nb.size()) return -1;
+  p.block = nb; p.nnb = (int)dg.nb.size();
+  if (p.nnb == 0) { p.built = true; return 0; }
+  if (cudaMalloc(&p.mailbox, mine.bytes) != cudaSuccess) return -1;
+  cudaMemset(p.mailbox, 0, mine.bytes);
+  cudaMalloc(&p.d_counters, sizeof(unsigned int) * 2 * p.nnb); cudaMemset(p.d_counters, 0, sizeof(unsigned int) * 2 * p.nnb);
+  cudaMalloc(&p.d_error, sizeof(int)); cudaMemset(p.d_error, 0, sizeof(int));
+  // all-gather the IPC handles
+  cudaIpcMemHandle_t h; if (cudaIpcGetMemHandle(&h, p.mailbox) != cudaSuccess) return -1;
+  char *d_h = nullptr, *d_all = nullptr; cudaMalloc(&d_h, sizeof(h)); cudaMalloc(&d_all, sizeof(h) * world);
+  cudaMemcpy(d_h, &h, sizeof(h), cudaMemcpyHostToDevice);
+  if (nccl.AllGather(d_h, d_all, sizeof(h), /*ncclChar*/ 0, comm, st) != 0) return -1;
+  std::vector<cudaIpcMemHandle_t> all(world);
+  cudaStreamSynchronize(st); cudaMemcpy(all.data(), d_all, sizeof(h) * world, cudaMemcpyDeviceToHost); cudaFree(d_h); cudaFree(d_all);
+  std::vector<P2PNeighbourDev> host(p.nnb);
+  std::vector<std::pair<int, void*>> open_cache;
+  for (int i = 0; i < p.nnb; ++i) {
+    HaloNeighbour& hn = dg.nb[i];
+    const int code = mine.dir[i], dx = code % 3 - 1, dy = (code / 3) % 3 - 1, dz = code / 9 - 1;
+    const int pcn[3] = {pc[0] + dx, pc[1] + dy, pc[2] + dz};
+    int own_peer[3]; block_extents(gn, proc, pcn, own_peer);
+    MailboxLayout theirs = mailbox_layout(proc, pcn, own_peer, nb);
+    const int back = (-dx + 1) + 3 * ((-dy + 1) + 3 * (-dz + 1));
+    int j = -1; for (size_t k = 0; k < theirs.dir.size(); ++k) if (theirs.dir[k] == back) j = (int)k;
+    if (j < 0 || theirs.count[j] != hn.count || mine.count[i] != hn.count) return -1;
+    void* peer_base = nullptr;
+    for (auto& oc : open_cache) if (oc.first == hn.peer) peer_base = oc.second;
+    if (!peer_base) {
+      if (cudaIpcOpenMemHandle(&peer_base, all[hn.peer], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return -1; }
+      open_cache.push_back({hn.peer, peer_base}); p.opened.push_back(peer_base);
+    }
+    P2PNeighbourDev& d = host[i];
+    d.count = hn.count; d.send_idx = hn.d_send_idx; d.recv_idx = hn.d_recv_idx;
+    char* rb = (char*)peer_base + theirs.offset[j]; char* lb = (char*)p.mailbox + mine.offset[i];
+    const size_t one = (size_t)hn.count * nb * sizeof(double);
+    d.remote_data[0] = (double*)rb; d.remote_data[1] = (double*)(rb + one);
+    d.remote_ready = (unsigned long long*)(rb + 2 * one); d.remote_ack = d.remote_ready + 2;
+    d.local_data[0] = (double*)lb; d.local_data[1] = (double*)(lb + one);
+    d.local_ready = (unsigned long long*)(lb + 2 * one); d.local_ack = d.local_ready + 2;
+    d.counters = p.d_counters + 2 * i;
+  }
+  cudaMalloc(&p.d_nb, sizeof(P2PNeighbourDev) * p.nnb);
+  cudaMemcpy(p.d_nb, host.data(), sizeof(P2PNeighbourDev) * p.nnb, cudaMemcpyHostToDevice);
+  (void)rank;
+  p.built = cudaGetLastError() == cudaSuccess; return p.built ? 0 : -1;
+}
+inline int halo_exchange_p2p(HaloPlanP2P& p, double* v, cudaStream_t st) {
+  if (!p.built) return -1;
+  if (p.nnb == 0) return 0;
+  const unsigned long long seq = ++p.seq;
+  p2p_send_kernel<<<p.nnb * kP2PBlocksPerNb, 256, 0, st>>>(v, p.d_nb, p.block, seq, p.d_error);
+  p2p_recv_kernel<<<p.nnb * kP2PBlocksPerNb, 256, 0, st>>>(v, p.d_nb, p.block, seq, p.d_error);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
 inline int halo_exchange(HaloPlan& p, NcclApi& nccl, void* comm, double* v, bool add, cudaStream_t st) {
