@@ -60,9 +60,10 @@ struct b200fem_operator {
   double *d_h = nullptr, *d_r = nullptr, *d_p = nullptr, *d_x = nullptr, *d_b = nullptr, *d_partial = nullptr, *d_sums = nullptr, *d_hist = nullptr;
   CgState* d_cg = nullptr; int hist_cap = 0;
   bool kron_ready = false; std::vector<unsigned char> kron_tab; struct KronMapCache* map_cache = nullptr;
-  HaloPlan halo; HaloPlanDG halo_dg; HaloPlanP2P halo_p2p; const BoxDev* active_box = nullptr; int reserve_sms = 0;      // active_box: sub-box override for split launches
+  HaloPlan halo; HaloPlanDG halo_dg; HaloPlanP2P halo_p2p; const BoxDev* active_box = nullptr; int reserve_sms = 0; unsigned long long fused_seq = 0; bool last_launch_tensor = false;      // active_box: sub-box override for split launches
   cudaStream_t comm_stream = nullptr; cudaEvent_t ev_bnd = nullptr, ev_comm = nullptr, dbg_ev[2] = {nullptr, nullptr};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evx0 = nullptr, evx1 = nullptr; b200fem_timing timing{};
+  bool timing_enabled = false;     // event records cost ~1.5 us each on the host: only after b200fem_operator_timing was asked for
 };
 
 extern "C" const char* b200fem_last_error(void) { return g_error.c_str(); }
@@ -349,7 +350,21 @@ template <int N, bool HIER, bool SPLIT> static int launch_dg_kronecker_tensor(b2
   // a persistent grid fills every SM for its whole run time; while a halo exchange is in flight a few SMs are left free so
   // that the exchange kernels are guaranteed to run concurrently
   const int grid = std::max(1, std::min(ntiles, sms - op->reserve_sms));
-  kern<<<(unsigned)grid, Cfg::kThreads, Cfg::smem_bytes(), op->sp->mesh->ctx->stream>>>(K, b, mc.maps[slot], bvec ? 1 : 0, tx, ty, ntiles);
+  KronSendDev snd; std::memset(&snd, 0, sizeof(snd));
+  if (op->fused_seq) {          // this launch also sends the y/z face halos of w (see apply_dev_impl)
+    HaloPlanP2P& hp = op->halo_p2p;
+    for (int i = 0; i < hp.nnb; ++i) {
+      const int c = hp.dir_code[i], dx = c % 3 - 1, dy = (c / 3) % 3 - 1, dz = c / 9 - 1;
+      if (dx != 0 || ((dy != 0) == (dz != 0))) continue;
+      const int d = dy ? (dy < 0 ? 0 : 1) : (dz < 0 ? 2 : 3);
+      snd.enabled[d] = 1; snd.any = 1;
+      snd.remote[d][0] = hp.host_nb[i].remote_data[0]; snd.remote[d][1] = hp.host_nb[i].remote_data[1];
+      snd.remote_ready[d] = hp.host_nb[i].remote_ready; snd.local_ack[d] = hp.host_nb[i].local_ack;
+    }
+    snd.dir_counter = hp.d_cta_counter; snd.seq = op->fused_seq; snd.error = hp.d_error;
+    snd.expected[0] = snd.expected[1] = (unsigned)(tx * tz); snd.expected[2] = snd.expected[3] = (unsigned)(tx * ty);
+  }
+  kern<<<(unsigned)grid, Cfg::kThreads, Cfg::smem_bytes(), op->sp->mesh->ctx->stream>>>(K, b, mc.maps[slot], snd, bvec ? 1 : 0, tx, ty, ntiles);
   CUDA_OK(cudaGetLastError()); return B200FEM_OK;
 }
 
@@ -431,6 +446,7 @@ static int apply_local(b200fem_operator* op, const double* u, double* w, bool li
     const bool phase_ok = !bvec || ((reinterpret_cast<uintptr_t>(bvec) ^ reinterpret_cast<uintptr_t>(w)) & 8) == 0;
     const bool hier = s->kind == B200FEM_DG_LEGENDRE_HIER;
     int rc;
+    op->last_launch_tensor = variant == "tensor" && tensor_path_ok<3>(op, u, w, bvec) && N == 3;
     if (variant == "tensor" && tensor_path_ok<3>(op, u, w, bvec) && N == 3) rc = hier ? launch_dg_kronecker_tensor<3, true, false>(op, u, w, bvec) : launch_dg_kronecker_tensor<3, false, false>(op, u, w, bvec);
     else if (variant == "tensor3" && tensor_path_ok<3>(op, u, w, bvec) && N == 3) rc = hier ? launch_dg_kronecker_tensor<3, true, true>(op, u, w, bvec) : launch_dg_kronecker_tensor<3, false, true>(op, u, w, bvec);
     else if (N == 3 && phase_ok && (variant == "pipe" || variant == "tensor" || variant == "tensor3")) rc = hier ? launch_dg_kronecker_pipe<3, true, false>(op, u, w, bvec) : launch_dg_kronecker_pipe<3, false, false>(op, u, w, bvec);
@@ -485,11 +501,15 @@ static int exchange(b200fem_operator* op, double* v, cudaStream_t st) {
 // is computed -- the exchange the reference performs serially after the loop is hidden behind the interior elements.
 static int apply_dev_impl(b200fem_operator* op, const double* u, double* w, bool linear) {
   b200fem_space* s = op->sp; cudaStream_t st = s->mesh->ctx->stream;
-  CUDA_OK(cudaSetDevice(s->mesh->ctx->device));
-  CUDA_OK(cudaEventRecord(op->ev0, st));
+  if (op->timing_enabled) CUDA_OK(cudaEventRecord(op->ev0, st));
   const bool distributed = op->communicate && s->mesh->ctx->world > 1;
   int rc;
-  if (distributed && s->kind != B200FEM_LAGRANGE && op->comm_stream) {
+  // Measured on 2 x B200 (profiles/r01_multigpu.md): exchange kernels queued on a second stream do not start before the
+  // persistent compute kernel retires, even with SMs left free, so splitting only adds 12 us of small launches; the
+  // peer-memory exchange itself takes 3-4 us.  Default: one compute launch, then the exchange on the same stream.  The
+  // split/overlap schedule stays selectable for experiments.
+  static const bool split_overlap = std::getenv("B200FEM_SPLIT_OVERLAP") != nullptr;
+  if (split_overlap && distributed && s->kind != B200FEM_LAGRANGE && op->comm_stream) {
     // boundary sub-boxes: per split axis, one slab at each interface (thickness = one tile layer), carved successively
     // out of the owned box so that the pieces do not overlap
     const BoxDev& full = s->box; BoxDev rest = full; std::vector<BoxDev> bnd;
@@ -514,11 +534,22 @@ static int apply_dev_impl(b200fem_operator* op, const double* u, double* w, bool
     CUDA_OK(cudaStreamWaitEvent(st, op->ev_comm, 0));
     op->timing.launches_per_apply = launches + 3 * (int)op->halo_dg.nb.size();
   } else {
-    rc = apply_local(op, u, w, linear); if (rc) return rc;
+    // fused send: when the peer-memory mailboxes exist the TMA kernel itself stores boundary rows of w into the
+    // neighbours' mailboxes while it is still computing; afterwards only the receive part runs
+    static const bool no_fused = std::getenv("B200FEM_NO_FUSED_SEND") != nullptr;
+    const bool try_fused = distributed && !no_fused && s->kind != B200FEM_LAGRANGE && op->halo_p2p.built && op->halo_p2p.nnb > 0 &&
+                           s->box.own_lo[0] == 0 && s->box.own_hi[0] == s->box.n[0];
+    op->last_launch_tensor = false;
+    if (try_fused) op->fused_seq = op->halo_p2p.seq + 1;
+    rc = apply_local(op, u, w, linear);
+    const bool fused = try_fused && op->last_launch_tensor;
+    op->fused_seq = 0;
+    if (rc) return rc;
     if (distributed) {
-      CUDA_OK(cudaEventRecord(op->evx0, st));
-      rc = exchange(op, w, st); if (rc) return rc;
-      CUDA_OK(cudaEventRecord(op->evx1, st));
+      if (op->timing_enabled) CUDA_OK(cudaEventRecord(op->evx0, st));
+      if (fused) { const unsigned long long seq = ++op->halo_p2p.seq; if (halo_exchange_p2p_fused_tail(op->halo_p2p, w, seq, st) != 0) return fail(B200FEM_ERR_COMM, "halo exchange failed"); op->timing.launches_per_apply += 1; }
+      else { rc = exchange(op, w, st); if (rc) return rc; }
+      if (op->timing_enabled) CUDA_OK(cudaEventRecord(op->evx1, st));
     }
   }
   // DirichletWrapperOperator: op_(u,w) (communication included) first, then subConstraints (dirichletwrapper.hh:101-105)
@@ -526,7 +557,7 @@ static int apply_dev_impl(b200fem_operator* op, const double* u, double* w, bool
     dirichlet_sub_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(u, w, op->d_dmask, linear ? nullptr : op->d_dvals, s->size);
     CUDA_OK(cudaGetLastError()); op->timing.launches_per_apply += 1;
   }
-  CUDA_OK(cudaEventRecord(op->ev1, st));
+  if (op->timing_enabled) CUDA_OK(cudaEventRecord(op->ev1, st));
   op->timing.applies += 1;
   if (op->dbg_ev[0] && op->timing.applies == 300) {
     CUDA_OK(cudaEventSynchronize(op->ev1)); float a, b, c, d, e;
@@ -598,7 +629,7 @@ extern "C" int b200fem_operator_create(b200fem_space* s, const b200fem_model* mo
     }
     { int lo_p = 0, hi_p = 0; CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p)); CUDA_OK(cudaStreamCreateWithPriority(&op->comm_stream, cudaStreamNonBlocking, hi_p)); }
     CUDA_OK(cudaEventCreateWithFlags(&op->ev_bnd, cudaEventDisableTiming)); CUDA_OK(cudaEventCreateWithFlags(&op->ev_comm, cudaEventDisableTiming));
-    if (std::getenv("B200FEM_DEBUG_EVENTS")) { CUDA_OK(cudaEventCreate(&op->dbg_ev[0])); CUDA_OK(cudaEventCreate(&op->dbg_ev[1])); }
+    if (std::getenv("B200FEM_DEBUG_EVENTS")) { CUDA_OK(cudaEventCreate(&op->dbg_ev[0])); CUDA_OK(cudaEventCreate(&op->dbg_ev[1])); op->timing_enabled = true; }
   }
   *out = op; return B200FEM_OK;
 }
@@ -633,7 +664,10 @@ static int apply_host(b200fem_operator* op, const double* u, double* w, bool lin
 extern "C" int b200fem_operator_apply(b200fem_operator* op, const double* u, double* w) { return apply_host(op, u, w, false); }
 extern "C" int b200fem_operator_apply_linear(b200fem_operator* op, const double* u, double* w) { return apply_host(op, u, w, true); }
 extern "C" int b200fem_operator_apply_dev(b200fem_operator* op, const double* u, double* w, int linear) {
-  REQUIRE(op && u && w, B200FEM_ERR_INVALID, "apply_dev: null argument"); return apply_dev_impl(op, u, w, linear != 0);
+  REQUIRE(op && u && w, B200FEM_ERR_INVALID, "apply_dev: null argument");
+  int cur = -1; cudaGetDevice(&cur);
+  if (cur != op->sp->mesh->ctx->device) CUDA_OK(cudaSetDevice(op->sp->mesh->ctx->device));
+  return apply_dev_impl(op, u, w, linear != 0);
 }
 extern "C" int b200fem_operator_load_vector(b200fem_operator* op, double* b_host) {
   REQUIRE(op && b_host, B200FEM_ERR_INVALID, "load_vector: null argument");
@@ -657,7 +691,8 @@ extern "C" int b200fem_operator_dirichlet(b200fem_operator* op, uint8_t* mask, d
 }
 extern "C" int b200fem_operator_timing(b200fem_operator* op, b200fem_timing* out) {
   REQUIRE(op && out, B200FEM_ERR_INVALID, "null");
-  if (op->timing.applies > 0) {
+  if (!op->timing_enabled) { op->timing_enabled = true; }
+  else if (op->timing.applies > 0) {
     CUDA_OK(cudaEventSynchronize(op->ev1)); float ms = 0; CUDA_OK(cudaEventElapsedTime(&ms, op->ev0, op->ev1)); op->timing.last_apply_ms = ms;
     if (op->communicate && op->sp->mesh->ctx->world > 1) { CUDA_OK(cudaEventElapsedTime(&ms, op->evx0, op->evx1)); op->timing.last_exchange_ms = ms; }
   }

@@ -20,12 +20,22 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include "dg_kronecker_pipe.cuh"
+#include "halo.cuh"
 
 namespace b200fem {
 
 struct KronTensorMaps {
   CUtensorMap u_tile, u_xhalo, u_yhalo, u_zhalo;   // boxes {TX*N3,TY,TZ}, {2*N3,TY,TZ}, {TX*N3,1,TZ}, {TX*N3,TY,1} over the local box
   CUtensorMap b_tile, w_tile;                      // box {TX*N3,TY,TZ} over the owned sub-box
+};
+
+// Fused halo send: the four y/z face directions (index 0 ylo, 1 yhi, 2 zlo, 3 zhi).  remote[d][b] is the neighbour's
+// mailbox buffer b for my message: a dense [rows][on0*N3] array (rows = owned z for y faces, owned y for z faces).
+struct KronSendDev {
+  int any; int enabled[4];
+  double* remote[4][2]; unsigned long long* remote_ready[4]; const unsigned long long* local_ack[4];
+  unsigned int* dir_counter; unsigned int expected[4];     // tiles that contribute to each message
+  unsigned long long seq; int* error;
 };
 
 namespace ptx {
@@ -55,7 +65,8 @@ template <int N, int TX, int TY, int TZ, bool SPLIT> struct KronTensorCfg {
 template <int N, bool HIER, int TX, int TY, int TZ, bool SPLIT>
 __global__ void __launch_bounds__(KronTensorCfg<N, TX, TY, TZ, SPLIT>::kThreads, 1)
 dg_kronecker_tensor_kernel(const __grid_constant__ KronTabDev<N> K, const __grid_constant__ BoxDev box,
-                           const __grid_constant__ KronTensorMaps M, const int has_b, int tiles_x, int tiles_y, int ntiles) {
+                           const __grid_constant__ KronTensorMaps M, const __grid_constant__ KronSendDev SND, const int has_b,
+                           int tiles_x, int tiles_y, int ntiles) {
   using Cfg = KronTensorCfg<N, TX, TY, TZ, SPLIT>;
   constexpr int N3 = Cfg::N3, RX = Cfg::RX;
   constexpr PermTable<N, HIER> P{};
@@ -74,8 +85,12 @@ dg_kronecker_tensor_kernel(const __grid_constant__ KronTabDev<N> K, const __grid
   }
   __syncthreads();
 
+  // tile order: the first and the last tile layer of y and z come first, so that tiles on rank interfaces are computed
+  // (and their halo rows sent) at the very beginning of the kernel
+  const int tiles_z = ntiles / (tiles_x * tiles_y);
+  auto front = [](int i, int n) { return i == 0 ? 0 : (i == 1 ? n - 1 : i - 1); };
   auto tile_origin = [&](int tile, int& x0, int& y0, int& z0) {
-    const int bx = tile % tiles_x, by = (tile / tiles_x) % tiles_y, bz = tile / (tiles_x * tiles_y);
+    const int bx = tile % tiles_x, by = front((tile / tiles_x) % tiles_y, tiles_y), bz = front(tile / (tiles_x * tiles_y), tiles_z);
     x0 = box.own_lo[0] + bx * TX; y0 = box.own_lo[1] + by * TY; z0 = box.own_lo[2] + bz * TZ;
   };
   // stage layout: [A | XL | XH | YL | YH | ZL | ZH | O]
@@ -102,11 +117,64 @@ dg_kronecker_tensor_kernel(const __grid_constant__ KronTabDev<N> K, const __grid
       int x0, y0, z0; tile_origin(tile, x0, y0, z0);
       ptx::tma_load_3d(ptx::smem_addr(stage(s) + oO), &M.b_tile, (x0 - box.own_lo[0]) * N3, y0 - box.own_lo[1], z0 - box.own_lo[2], full_a + 8 * s);
     };
-    auto store_w = [&](int tile, int s) {
+    bool ack_checked = false;
+    auto store_w = [&](int tile, int s) -> int {
       int x0, y0, z0; tile_origin(tile, x0, y0, z0);
       ptx::tma_store_3d(&M.w_tile, (x0 - box.own_lo[0]) * N3, y0 - box.own_lo[1], z0 - box.own_lo[2], ptx::smem_addr(stage(s) + oO));
+      if (SND.any) {
+        // rows of this tile that lie on a rank interface go straight into the neighbour's mailbox (1-D bulk copies over
+        // NVLink; row starts are 16-byte aligned because on0 and TX are even)
+        const int on0 = box.own_hi[0] - box.own_lo[0], xr = x0 - box.own_lo[0];
+        const uint32_t bytes = (uint32_t)(min(TX, box.own_hi[0] - x0)) * N3 * 8;
+        const int buf = (int)(SND.seq & 1);
+        const bool zl = SND.enabled[2] && z0 == box.own_lo[2], zh = SND.enabled[3] && z0 + TZ >= box.own_hi[2];
+        const bool yl = SND.enabled[0] && y0 == box.own_lo[1], yh = SND.enabled[1] && y0 + TY >= box.own_hi[1];
+        if ((zl || zh || yl || yh) && !ack_checked) {              // the mailbox buffer was last used by message seq-2
+          for (int d = 0; d < 4; ++d) if (SND.enabled[d] && SND.seq > 2) {
+            const long long t0 = clock64();
+            while (ld_acquire_sys(SND.local_ack[d]) < SND.seq - 2) if (clock64() - t0 > kP2PSpinLimit) { *SND.error = 3; break; }
+          }
+          ack_checked = true;
+        }
+        const double* O = stage(s) + oO;
+        if (zl || zh) {
+          const int tzl = zl ? 0 : box.own_hi[2] - 1 - z0;
+          for (int which = 0; which < 2; ++which) {
+            if (which == 0 ? !zl : !zh) continue;
+            const int tz_ = which == 0 ? 0 : box.own_hi[2] - 1 - z0; (void)tzl;
+            for (int ty_ = 0; ty_ < TY && y0 + ty_ < box.own_hi[1]; ++ty_)
+              ptx::bulk_s2g(SND.remote[2 + which][buf] + ((long long)(y0 + ty_ - box.own_lo[1]) * on0 + xr) * N3, ptx::smem_addr(O + (tz_ * TY + ty_) * RX), bytes);
+          }
+        }
+        if (yl || yh) {
+          for (int which = 0; which < 2; ++which) {
+            if (which == 0 ? !yl : !yh) continue;
+            const int ty_ = which == 0 ? 0 : box.own_hi[1] - 1 - y0;
+            for (int tz_ = 0; tz_ < TZ && z0 + tz_ < box.own_hi[2]; ++tz_)
+              ptx::bulk_s2g(SND.remote[which][buf] + ((long long)(z0 + tz_ - box.own_lo[2]) * on0 + xr) * N3, ptx::smem_addr(O + (tz_ * TY + ty_) * RX), bytes);
+          }
+        }
+      }
       ptx::bulk_commit();
+      int mask = 0;
+      if (SND.any) {
+        if (SND.enabled[0] && y0 == box.own_lo[1]) mask |= 1;
+        if (SND.enabled[1] && y0 + TY >= box.own_hi[1]) mask |= 2;
+        if (SND.enabled[2] && z0 == box.own_lo[2]) mask |= 4;
+        if (SND.enabled[3] && z0 + TZ >= box.own_hi[2]) mask |= 8;
+      }
+      return mask;
     };
+    // A tile's halo rows may only be counted once they have landed in the neighbour's memory.  Waiting right after the
+    // store would stall the load pipeline for an NVLink round trip, so the accounting is deferred by one tile: by then the
+    // bulk group is (almost always) complete already.  The message is published by whoever completes its last tile.
+    auto publish = [&](int mask) {
+      __threadfence_system();
+      for (int d = 0; d < 4; ++d) if (((mask >> d) & 1) && atomicAdd(&SND.dir_counter[d], 1u) == SND.expected[d] - 1) {
+        SND.dir_counter[d] = 0; __threadfence_system(); st_release_sys(SND.remote_ready[d] + (SND.seq & 1), SND.seq);
+      }
+    };
+    int pending = 0;
     const uint32_t bytes = Cfg::kBytesU + (has_b ? Cfg::kBytesB : 0u);
     for (int it = 0; it < 2; ++it) {                                            // prologue: the first two tiles
       const int tile = blockIdx.x + it * gridDim.x;
@@ -119,7 +187,9 @@ dg_kronecker_tensor_kernel(const __grid_constant__ KronTabDev<N> K, const __grid
       ptx::mbar_wait(done_a + 8 * sp, ((it - 1) >> 1) & 1);
       const int ntile = blockIdx.x + (it + 1) * gridDim.x;
       if (ntile < ntiles) load_u(ntile, sp);                                    // long pole first
-      store_w(ptile, sp);
+      const int mask = store_w(ptile, sp);
+      if (pending) { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); publish(pending); }   // the previous tile's group is complete
+      pending = mask;
       if (ntile < ntiles) {
         ptx::bulk_wait_read();                                                  // tile it-1's output has left the stage: its slot
         if (has_b) load_b(ntile, sp);                                           // may receive the next load-vector tile
@@ -127,6 +197,7 @@ dg_kronecker_tensor_kernel(const __grid_constant__ KronTabDev<N> K, const __grid
       }
     }
     ptx::bulk_wait_all();
+    if (pending) publish(pending);
     return;
   }
 

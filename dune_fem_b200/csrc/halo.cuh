@@ -14,6 +14,8 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "lagrange_quadrature.cuh"
@@ -198,74 +200,99 @@ inline int halo_exchange_dg(HaloPlanDG& p, NcclApi& nccl, void* comm, double* v,
 // Every rank owns a mailbox area (plain cudaMalloc, exported with cudaIpcGetMemHandle, handles all-gathered once through
 // NCCL).  Per neighbour the mailbox holds two data buffers, two `ready` sequence flags (written by the neighbour when
 // its message has landed) and one `ack` flag (written by the neighbour when it has consumed my message).  An exchange is
-// two launches on the communication stream and no library call:
+// ONE launch and no library call (send part, then receive part):
 //   send kernel:   wait ack >= seq-2  ->  gather the owned layer and store it DIRECTLY into the neighbour's mailbox over
 //                  NVLink  ->  __threadfence_system  ->  last block publishes ready[seq&1] = seq in the neighbour's memory
 //   recv kernel:   spin on my ready[seq&1] >= seq  ->  scatter the mailbox into the ghost layer  ->  last block
 //                  publishes ack = seq in the neighbour's memory
 struct P2PNeighbourDev {
-  long long count; const long long* send_idx; const long long* recv_idx;
+  long long total;                                   // doubles per message
+  const unsigned int* send_flat; const unsigned int* recv_flat;   // per double: offset in the dof vector
+  int block_begin, nblocks;                          // this neighbour's slice of the grid
+  int fused;                                         // 1: the compute kernel sends this message and publishes `ready` itself
   double* remote_data[2]; unsigned long long* remote_ready; unsigned long long* remote_ack;     // in the peer's mailbox
   double* local_data[2]; unsigned long long* local_ready; unsigned long long* local_ack;        // in my mailbox
   unsigned int* counters;                                                                        // [0] send, [1] recv block counters (local)
 };
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 struct HaloPlanP2P {
-  bool built = false; int block = 1; int nnb = 0; unsigned long long seq = 0;
+  bool built = false; int block = 1; int nnb = 0; int grid = 0; unsigned long long seq = 0;
   P2PNeighbourDev* d_nb = nullptr; void* mailbox = nullptr; unsigned int* d_counters = nullptr; int* d_error = nullptr;
   std::vector<void*> opened;          // peer mappings to close
+  std::vector<void*> owned;           // flat index arrays
+  std::vector<P2PNeighbourDev> host_nb; std::vector<int> dir_code;   // host copy (+ direction (dx+1)+3(dy+1)+9(dz+1)) for the fused path
+  P2PNeighbourDev* d_nb_fused = nullptr; unsigned int* d_cta_counter = nullptr;
+  unsigned long long* d_ts = nullptr;  // optional timestamps (B200FEM_DEBUG_EVENTS)
 };
-constexpr int kP2PBlocksPerNb = 64;
+constexpr int kP2PThreads = 256;
 constexpr long long kP2PSpinLimit = 4000000000ll;   // ~2 s of SM clocks: a lost peer must not hang the box
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
   unsigned long long v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
 }
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ int p2p_find(const P2PNeighbourDev* nbs, int nnb) {
+  int k = 0; while (k + 1 < nnb && (int)blockIdx.x >= nbs[k + 1].block_begin) ++k; return k;
+}
 
-__global__ void __launch_bounds__(256) p2p_send_kernel(const double* __restrict__ v, const P2PNeighbourDev* __restrict__ nbs, int block, unsigned long long seq, int* error) {
-  const P2PNeighbourDev nb = nbs[blockIdx.x / kP2PBlocksPerNb];
-  const int part = blockIdx.x % kP2PBlocksPerNb;
-  if (threadIdx.x == 0 && seq > 2) {                       // the buffer was last used by message seq-2: has it been consumed?
+// One fused kernel per exchange: every block first sends its slice (kP2PItems independent doubles per thread: index,
+// value and remote store chains overlap), then waits for the neighbour's flag and scatters the same slice of the incoming
+// message.  The send part never waits on this exchange's remote state, so blocks need not be co-resident.
+constexpr int kP2PItems = 8;
+__global__ void __launch_bounds__(kP2PThreads) p2p_exchange_kernel(double* __restrict__ v, const P2PNeighbourDev* __restrict__ nbs, int nnb, unsigned long long seq, int* error, unsigned long long* ts) {
+  const P2PNeighbourDev nb = nbs[p2p_find(nbs, nnb)];
+  if (ts && blockIdx.x == 0 && threadIdx.x == 0) ts[0] = gtimer();
+  if (threadIdx.x == 0 && seq > 2 && !nb.fused) {          // the buffer was last used by message seq-2: has it been consumed?
     const long long t0 = clock64();
     while (ld_acquire_sys(nb.local_ack) < seq - 2) if (clock64() - t0 > kP2PSpinLimit) { *error = 1; break; }
   }
   __syncthreads();
-  double* dst = nb.remote_data[seq & 1];
-  // one warp per element block (no integer division in the copy loop); stores to the peer are contiguous per warp
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  for (long long e = (long long)part * wpb + warp; e < nb.count; e += (long long)kP2PBlocksPerNb * wpb) {
-    const double* src = v + nb.send_idx[e]; double* d = dst + e * block;
-    for (int j = lane; j < block; j += 32) d[j] = src[j];
+  const long long base = (long long)(blockIdx.x - nb.block_begin) * (kP2PThreads * kP2PItems) + threadIdx.x;
+  if (!nb.fused) {
+    double* dst = nb.remote_data[seq & 1];
+    unsigned int idx[kP2PItems]; double val[kP2PItems];
+#pragma unroll
+    for (int k = 0; k < kP2PItems; ++k) { const long long i = base + (long long)k * kP2PThreads; idx[k] = i < nb.total ? nb.send_flat[i] : 0u; }
+#pragma unroll
+    for (int k = 0; k < kP2PItems; ++k) val[k] = v[idx[k]];
+#pragma unroll
+    for (int k = 0; k < kP2PItems; ++k) { const long long i = base + (long long)k * kP2PThreads; if (i < nb.total) dst[i] = val[k]; }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence_system();                                // cumulative over the block's stores (ordered by the barrier)
-    if (atomicAdd(&nb.counters[0], 1u) == kP2PBlocksPerNb - 1) { nb.counters[0] = 0; __threadfence_system(); st_release_sys(&nb.remote_ready[seq & 1], seq); }
-  }
-}
-__global__ void __launch_bounds__(256) p2p_recv_kernel(double* __restrict__ v, const P2PNeighbourDev* __restrict__ nbs, int block, unsigned long long seq, int* error) {
-  const P2PNeighbourDev nb = nbs[blockIdx.x / kP2PBlocksPerNb];
-  const int part = blockIdx.x % kP2PBlocksPerNb;
-  if (threadIdx.x == 0) {
+    if (!nb.fused) {
+      __threadfence_system();                              // cumulative over the block's stores (ordered by the barrier)
+      if (atomicAdd(&nb.counters[0], 1u) == (unsigned)nb.nblocks - 1) { nb.counters[0] = 0; __threadfence_system(); st_release_sys(&nb.remote_ready[seq & 1], seq); if (ts) ts[1] = gtimer(); }
+    }
+    if (ts && blockIdx.x == 0) ts[2] = gtimer();
     const long long t0 = clock64();
     while (ld_acquire_sys(&nb.local_ready[seq & 1]) < seq) if (clock64() - t0 > kP2PSpinLimit) { *error = 2; break; }
+    if (ts && blockIdx.x == 0) ts[3] = gtimer();
   }
   __syncthreads();
-  const double* src = nb.local_data[seq & 1];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  for (long long e = (long long)part * wpb + warp; e < nb.count; e += (long long)kP2PBlocksPerNb * wpb) {
-    const double* sp = src + e * block; double* d = v + nb.recv_idx[e];
-    for (int j = lane; j < block; j += 32) d[j] = sp[j];
+  {
+    const double* src = nb.local_data[seq & 1];
+    unsigned int idx[kP2PItems]; double val[kP2PItems];
+#pragma unroll
+    for (int k = 0; k < kP2PItems; ++k) { const long long i = base + (long long)k * kP2PThreads; idx[k] = i < nb.total ? nb.recv_flat[i] : 0u; val[k] = i < nb.total ? src[i] : 0.0; }
+#pragma unroll
+    for (int k = 0; k < kP2PItems; ++k) { const long long i = base + (long long)k * kP2PThreads; if (i < nb.total) v[idx[k]] = val[k]; }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    if (atomicAdd(&nb.counters[1], 1u) == kP2PBlocksPerNb - 1) { nb.counters[1] = 0; __threadfence_system(); st_release_sys(nb.remote_ack, seq); }
+    if (atomicAdd(&nb.counters[1], 1u) == (unsigned)nb.nblocks - 1) { nb.counters[1] = 0; __threadfence_system(); st_release_sys(nb.remote_ack, seq); if (ts) ts[4] = gtimer(); }
   }
 }
 
 inline void halo_plan_p2p_free(HaloPlanP2P& p) {
+  if (p.d_ts) {
+    unsigned long long h[8]; cudaDeviceSynchronize(); cudaMemcpy(h, p.d_ts, 64, cudaMemcpyDeviceToHost); cudaFree(p.d_ts);
+    std::fprintf(stderr, "[b200fem p2p ns, last exchange] flag published +%lld | recv kernel start +%lld | flag seen +%lld | ack sent +%lld (from send kernel start)\n",
+                 (long long)(h[1] - h[0]), (long long)(h[2] - h[0]), (long long)(h[3] - h[0]), (long long)(h[4] - h[0]));
+  }
   for (void* q : p.opened) cudaIpcCloseMemHandle(q);
-  for (void* q : {(void*)p.d_nb, p.mailbox, (void*)p.d_counters, (void*)p.d_error}) if (q) cudaFree(q);
+  for (void* q : p.owned) cudaFree(q);
+  for (void* q : {(void*)p.d_nb, (void*)p.d_nb_fused, (void*)p.d_cta_counter, p.mailbox, (void*)p.d_counters, (void*)p.d_error}) if (q) cudaFree(q);
   p = HaloPlanP2P();
 }
 
@@ -302,6 +329,7 @@ inline int halo_plan_p2p_build(HaloPlanP2P& p, HaloPlanDG& dg, NcclApi& nccl, vo
   cudaMemset(p.mailbox, 0, mine.bytes);
   cudaMalloc(&p.d_counters, sizeof(unsigned int) * 2 * p.nnb); cudaMemset(p.d_counters, 0, sizeof(unsigned int) * 2 * p.nnb);
   cudaMalloc(&p.d_error, sizeof(int)); cudaMemset(p.d_error, 0, sizeof(int));
+  if (std::getenv("B200FEM_DEBUG_EVENTS")) { cudaMalloc(&p.d_ts, 64); cudaMemset(p.d_ts, 0, 64); }
   // all-gather the IPC handles
   cudaIpcMemHandle_t h; if (cudaIpcGetMemHandle(&h, p.mailbox) != cudaSuccess) return -1;
   char *d_h = nullptr, *d_all = nullptr; cudaMalloc(&d_h, sizeof(h)); cudaMalloc(&d_all, sizeof(h) * world);
@@ -327,7 +355,22 @@ inline int halo_plan_p2p_build(HaloPlanP2P& p, HaloPlanDG& dg, NcclApi& nccl, vo
       open_cache.push_back({hn.peer, peer_base}); p.opened.push_back(peer_base);
     }
     P2PNeighbourDev& d = host[i];
-    d.count = hn.count; d.send_idx = hn.d_send_idx; d.recv_idx = hn.d_recv_idx;
+    {   // flat per-double gather/scatter offsets
+      std::vector<long long> si((size_t)hn.count), ri((size_t)hn.count);
+      cudaMemcpy(si.data(), hn.d_send_idx, sizeof(long long) * hn.count, cudaMemcpyDeviceToHost);
+      cudaMemcpy(ri.data(), hn.d_recv_idx, sizeof(long long) * hn.count, cudaMemcpyDeviceToHost);
+      std::vector<unsigned int> sf((size_t)hn.count * nb), rf((size_t)hn.count * nb);
+      for (long long e = 0; e < hn.count; ++e) for (int j = 0; j < nb; ++j) {
+        if (si[e] + j > 0xffffffffll || ri[e] + j > 0xffffffffll) return -1;
+        sf[(size_t)e * nb + j] = (unsigned int)(si[e] + j); rf[(size_t)e * nb + j] = (unsigned int)(ri[e] + j);
+      }
+      unsigned int *dsf = nullptr, *drf = nullptr;
+      if (cudaMalloc(&dsf, sf.size() * 4) != cudaSuccess || cudaMalloc(&drf, rf.size() * 4) != cudaSuccess) return -1;
+      cudaMemcpy(dsf, sf.data(), sf.size() * 4, cudaMemcpyHostToDevice); cudaMemcpy(drf, rf.data(), rf.size() * 4, cudaMemcpyHostToDevice);
+      p.owned.push_back(dsf); p.owned.push_back(drf);
+      d.total = hn.count * nb; d.send_flat = dsf; d.recv_flat = drf;
+      d.fused = 0; d.block_begin = p.grid; d.nblocks = (int)((d.total + kP2PThreads * kP2PItems - 1) / (kP2PThreads * kP2PItems)); p.grid += d.nblocks;
+    }
     char* rb = (char*)peer_base + theirs.offset[j]; char* lb = (char*)p.mailbox + mine.offset[i];
     const size_t one = (size_t)hn.count * nb * sizeof(double);
     d.remote_data[0] = (double*)rb; d.remote_data[1] = (double*)(rb + one);
@@ -338,15 +381,28 @@ inline int halo_plan_p2p_build(HaloPlanP2P& p, HaloPlanDG& dg, NcclApi& nccl, vo
   }
   cudaMalloc(&p.d_nb, sizeof(P2PNeighbourDev) * p.nnb);
   cudaMemcpy(p.d_nb, host.data(), sizeof(P2PNeighbourDev) * p.nnb, cudaMemcpyHostToDevice);
+  // second table for exchanges whose y/z face messages are sent by the compute kernel itself
+  p.host_nb = host; p.dir_code = mine.dir;
+  std::vector<P2PNeighbourDev> fused = host;
+  for (int i = 0; i < p.nnb; ++i) { const int c = mine.dir[i], dx = c % 3 - 1, dy = (c / 3) % 3 - 1, dz = c / 9 - 1; fused[i].fused = (dx == 0 && ((dy != 0) != (dz != 0))) ? 1 : 0; }
+  cudaMalloc(&p.d_nb_fused, sizeof(P2PNeighbourDev) * p.nnb);
+  cudaMemcpy(p.d_nb_fused, fused.data(), sizeof(P2PNeighbourDev) * p.nnb, cudaMemcpyHostToDevice);
+  cudaMalloc(&p.d_cta_counter, 4 * sizeof(unsigned int)); cudaMemset(p.d_cta_counter, 0, 4 * sizeof(unsigned int));
   (void)rank;
   p.built = cudaGetLastError() == cudaSuccess; return p.built ? 0 : -1;
+}
+// receive side of an exchange whose y/z face messages were sent by the compute kernel (sequence number `seq`); the
+// remaining neighbours (edges, corners, x faces) are sent here
+inline int halo_exchange_p2p_fused_tail(HaloPlanP2P& p, double* v, unsigned long long seq, cudaStream_t st) {
+  if (!p.built || p.nnb == 0) return p.built ? 0 : -1;
+  p2p_exchange_kernel<<<p.grid, kP2PThreads, 0, st>>>(v, p.d_nb_fused, p.nnb, seq, p.d_error, p.d_ts);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 inline int halo_exchange_p2p(HaloPlanP2P& p, double* v, cudaStream_t st) {
   if (!p.built) return -1;
   if (p.nnb == 0) return 0;
   const unsigned long long seq = ++p.seq;
-  p2p_send_kernel<<<p.nnb * kP2PBlocksPerNb, 256, 0, st>>>(v, p.d_nb, p.block, seq, p.d_error);
-  p2p_recv_kernel<<<p.nnb * kP2PBlocksPerNb, 256, 0, st>>>(v, p.d_nb, p.block, seq, p.d_error);
+  p2p_exchange_kernel<<<p.grid, kP2PThreads, 0, st>>>(v, p.d_nb, p.nnb, seq, p.d_error, p.d_ts);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

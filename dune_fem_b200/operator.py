@@ -26,6 +26,7 @@ class GalerkinOperator:
         self.model = m
         self.handle = C.c_void_p()
         capi.check(capi.lib().b200fem_operator_create(space.handle, C.byref(m), C.byref(self.handle)))
+        self._apply_dev = capi.lib().b200fem_operator_apply_dev          # bound once: the call sits in 40 us loops
         if kernel != capi.KERNEL_AUTO:
             self.setKernel(kernel)
 
@@ -37,7 +38,9 @@ class GalerkinOperator:
         capi.check(capi.lib().b200fem_operator_apply_linear(self.handle, capi.ptr(u), capi.ptr(w)))
 
     def apply_dev(self, u_ptr, w_ptr, linear=False):
-        capi.check(capi.lib().b200fem_operator_apply_dev(self.handle, C.c_void_p(u_ptr), C.c_void_p(w_ptr), int(linear)))
+        rc = self._apply_dev(self.handle, u_ptr, w_ptr, 1 if linear else 0)
+        if rc:
+            capi.check(rc)
 
     def loadVector(self):
         bvec = np.empty(self.space.size)
@@ -72,6 +75,12 @@ class GalerkinOperator:
 
     def communicate_dev(self, v_ptr):
         capi.check(capi.lib().b200fem_communicate_dev(self.handle, C.c_void_p(v_ptr)))
+
+    def __del__(self):
+        try:
+            capi.lib().b200fem_operator_destroy(self.handle)
+        except Exception:
+            pass
 
     @property
     def nonlinear(self):
