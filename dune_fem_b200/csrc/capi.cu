@@ -355,14 +355,14 @@ template <int N, bool HIER, bool SPLIT> static int launch_dg_kronecker_tensor(b2
     HaloPlanP2P& hp = op->halo_p2p;
     for (int i = 0; i < hp.nnb; ++i) {
       const int c = hp.dir_code[i], dx = c % 3 - 1, dy = (c / 3) % 3 - 1, dz = c / 9 - 1;
-      if (dx != 0 || ((dy != 0) == (dz != 0))) continue;
-      const int d = dy ? (dy < 0 ? 0 : 1) : (dz < 0 ? 2 : 3);
+      if (dx != 0) continue;
+      const int d = (dy + 1) + 3 * (dz + 1);
       snd.enabled[d] = 1; snd.any = 1;
       snd.remote[d][0] = hp.host_nb[i].remote_data[0]; snd.remote[d][1] = hp.host_nb[i].remote_data[1];
       snd.remote_ready[d] = hp.host_nb[i].remote_ready; snd.local_ack[d] = hp.host_nb[i].local_ack;
+      snd.expected[d] = (unsigned)(tx * (dy == 0 ? ty : 1) * (dz == 0 ? tz : 1));
     }
     snd.dir_counter = hp.d_cta_counter; snd.seq = op->fused_seq; snd.error = hp.d_error;
-    snd.expected[0] = snd.expected[1] = (unsigned)(tx * tz); snd.expected[2] = snd.expected[3] = (unsigned)(tx * ty);
   }
   kern<<<(unsigned)grid, Cfg::kThreads, Cfg::smem_bytes(), op->sp->mesh->ctx->stream>>>(K, b, mc.maps[slot], snd, bvec ? 1 : 0, tx, ty, ntiles);
   CUDA_OK(cudaGetLastError()); return B200FEM_OK;

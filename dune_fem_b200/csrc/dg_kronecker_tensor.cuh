@@ -29,12 +29,13 @@ struct KronTensorMaps {
   CUtensorMap b_tile, w_tile;                      // box {TX*N3,TY,TZ} over the owned sub-box
 };
 
-// Fused halo send: the four y/z face directions (index 0 ylo, 1 yhi, 2 zlo, 3 zhi).  remote[d][b] is the neighbour's
-// mailbox buffer b for my message: a dense [rows][on0*N3] array (rows = owned z for y faces, owned y for z faces).
+// Fused halo send: the eight neighbours in the y-z plane (faces and edges), direction code d = (dy+1) + 3*(dz+1).
+// remote[d][b] is the neighbour's mailbox buffer b for my message: a dense [z-part][y-part][on0*N3] array where a part
+// is the whole owned range for a zero direction component and the single interface layer otherwise.
 struct KronSendDev {
-  int any; int enabled[4];
-  double* remote[4][2]; unsigned long long* remote_ready[4]; const unsigned long long* local_ack[4];
-  unsigned int* dir_counter; unsigned int expected[4];     // tiles that contribute to each message
+  int any; int enabled[9];
+  double* remote[9][2]; unsigned long long* remote_ready[9]; const unsigned long long* local_ack[9];
+  unsigned int* dir_counter; unsigned int expected[9];     // tiles that contribute to each message
   unsigned long long seq; int* error;
 };
 
@@ -121,48 +122,38 @@ dg_kronecker_tensor_kernel(const __grid_constant__ KronTabDev<N> K, const __grid
     auto store_w = [&](int tile, int s) -> int {
       int x0, y0, z0; tile_origin(tile, x0, y0, z0);
       ptx::tma_store_3d(&M.w_tile, (x0 - box.own_lo[0]) * N3, y0 - box.own_lo[1], z0 - box.own_lo[2], ptx::smem_addr(stage(s) + oO));
+      int mask = 0;
       if (SND.any) {
         // rows of this tile that lie on a rank interface go straight into the neighbour's mailbox (1-D bulk copies over
         // NVLink; row starts are 16-byte aligned because on0 and TX are even)
-        const int on0 = box.own_hi[0] - box.own_lo[0], xr = x0 - box.own_lo[0];
+        const int on0 = box.own_hi[0] - box.own_lo[0], on1 = box.own_hi[1] - box.own_lo[1], xr = x0 - box.own_lo[0];
         const uint32_t bytes = (uint32_t)(min(TX, box.own_hi[0] - x0)) * N3 * 8;
         const int buf = (int)(SND.seq & 1);
-        const bool zl = SND.enabled[2] && z0 == box.own_lo[2], zh = SND.enabled[3] && z0 + TZ >= box.own_hi[2];
-        const bool yl = SND.enabled[0] && y0 == box.own_lo[1], yh = SND.enabled[1] && y0 + TY >= box.own_hi[1];
-        if ((zl || zh || yl || yh) && !ack_checked) {              // the mailbox buffer was last used by message seq-2
-          for (int d = 0; d < 4; ++d) if (SND.enabled[d] && SND.seq > 2) {
+        // is this tile at the low / high interface layer of y, z?  (index 0: low, 2: high)
+        const bool aty[3] = {y0 == box.own_lo[1], true, y0 + TY >= box.own_hi[1]};
+        const bool atz[3] = {z0 == box.own_lo[2], true, z0 + TZ >= box.own_hi[2]};
+        for (int d = 0; d < 9; ++d) if (SND.enabled[d] && aty[d % 3] && atz[d / 3]) mask |= 1 << d;
+        if (mask && !ack_checked) {                                  // the mailbox buffer was last used by message seq-2
+          for (int d = 0; d < 9; ++d) if (SND.enabled[d] && SND.seq > 2) {
             const long long t0 = clock64();
             while (ld_acquire_sys(SND.local_ack[d]) < SND.seq - 2) if (clock64() - t0 > kP2PSpinLimit) { *SND.error = 3; break; }
           }
           ack_checked = true;
         }
         const double* O = stage(s) + oO;
-        if (zl || zh) {
-          const int tzl = zl ? 0 : box.own_hi[2] - 1 - z0;
-          for (int which = 0; which < 2; ++which) {
-            if (which == 0 ? !zl : !zh) continue;
-            const int tz_ = which == 0 ? 0 : box.own_hi[2] - 1 - z0; (void)tzl;
-            for (int ty_ = 0; ty_ < TY && y0 + ty_ < box.own_hi[1]; ++ty_)
-              ptx::bulk_s2g(SND.remote[2 + which][buf] + ((long long)(y0 + ty_ - box.own_lo[1]) * on0 + xr) * N3, ptx::smem_addr(O + (tz_ * TY + ty_) * RX), bytes);
-          }
-        }
-        if (yl || yh) {
-          for (int which = 0; which < 2; ++which) {
-            if (which == 0 ? !yl : !yh) continue;
-            const int ty_ = which == 0 ? 0 : box.own_hi[1] - 1 - y0;
-            for (int tz_ = 0; tz_ < TZ && z0 + tz_ < box.own_hi[2]; ++tz_)
-              ptx::bulk_s2g(SND.remote[which][buf] + ((long long)(z0 + tz_ - box.own_lo[2]) * on0 + xr) * N3, ptx::smem_addr(O + (tz_ * TY + ty_) * RX), bytes);
-          }
+        for (int d = 0; d < 9; ++d) if ((mask >> d) & 1) {
+          const int dy = d % 3 - 1, dz = d / 3 - 1;
+          const int ty_lo = dy < 0 ? 0 : dy > 0 ? box.own_hi[1] - 1 - y0 : 0, ty_hi = dy == 0 ? TY : ty_lo + 1;
+          const int tz_lo = dz < 0 ? 0 : dz > 0 ? box.own_hi[2] - 1 - z0 : 0, tz_hi = dz == 0 ? TZ : tz_lo + 1;
+          const int ny = dy == 0 ? on1 : 1;                            // rows per z-part of the message
+          for (int tz_ = tz_lo; tz_ < tz_hi && z0 + tz_ < box.own_hi[2]; ++tz_)
+            for (int ty_ = ty_lo; ty_ < ty_hi && y0 + ty_ < box.own_hi[1]; ++ty_) {
+              const long long zi = dz == 0 ? z0 + tz_ - box.own_lo[2] : 0, yi = dy == 0 ? y0 + ty_ - box.own_lo[1] : 0;
+              ptx::bulk_s2g(SND.remote[d][buf] + ((zi * ny + yi) * on0 + xr) * N3, ptx::smem_addr(O + (tz_ * TY + ty_) * RX), bytes);
+            }
         }
       }
       ptx::bulk_commit();
-      int mask = 0;
-      if (SND.any) {
-        if (SND.enabled[0] && y0 == box.own_lo[1]) mask |= 1;
-        if (SND.enabled[1] && y0 + TY >= box.own_hi[1]) mask |= 2;
-        if (SND.enabled[2] && z0 == box.own_lo[2]) mask |= 4;
-        if (SND.enabled[3] && z0 + TZ >= box.own_hi[2]) mask |= 8;
-      }
       return mask;
     };
     // A tile's halo rows may only be counted once they have landed in the neighbour's memory.  Waiting right after the
@@ -170,7 +161,7 @@ dg_kronecker_tensor_kernel(const __grid_constant__ KronTabDev<N> K, const __grid
     // bulk group is (almost always) complete already.  The message is published by whoever completes its last tile.
     auto publish = [&](int mask) {
       __threadfence_system();
-      for (int d = 0; d < 4; ++d) if (((mask >> d) & 1) && atomicAdd(&SND.dir_counter[d], 1u) == SND.expected[d] - 1) {
+      for (int d = 0; d < 9; ++d) if (((mask >> d) & 1) && atomicAdd(&SND.dir_counter[d], 1u) == SND.expected[d] - 1) {
         SND.dir_counter[d] = 0; __threadfence_system(); st_release_sys(SND.remote_ready[d] + (SND.seq & 1), SND.seq);
       }
     };

@@ -384,10 +384,10 @@ inline int halo_plan_p2p_build(HaloPlanP2P& p, HaloPlanDG& dg, NcclApi& nccl, vo
   // second table for exchanges whose y/z face messages are sent by the compute kernel itself
   p.host_nb = host; p.dir_code = mine.dir;
   std::vector<P2PNeighbourDev> fused = host;
-  for (int i = 0; i < p.nnb; ++i) { const int c = mine.dir[i], dx = c % 3 - 1, dy = (c / 3) % 3 - 1, dz = c / 9 - 1; fused[i].fused = (dx == 0 && ((dy != 0) != (dz != 0))) ? 1 : 0; }
+  for (int i = 0; i < p.nnb; ++i) { const int c = mine.dir[i], dx = c % 3 - 1, dy = (c / 3) % 3 - 1, dz = c / 9 - 1; fused[i].fused = dx == 0 ? 1 : 0; }
   cudaMalloc(&p.d_nb_fused, sizeof(P2PNeighbourDev) * p.nnb);
   cudaMemcpy(p.d_nb_fused, fused.data(), sizeof(P2PNeighbourDev) * p.nnb, cudaMemcpyHostToDevice);
-  cudaMalloc(&p.d_cta_counter, 4 * sizeof(unsigned int)); cudaMemset(p.d_cta_counter, 0, 4 * sizeof(unsigned int));
+  cudaMalloc(&p.d_cta_counter, 9 * sizeof(unsigned int)); cudaMemset(p.d_cta_counter, 0, 9 * sizeof(unsigned int));
   (void)rank;
   p.built = cudaGetLastError() == cudaSuccess; return p.built ? 0 : -1;
 }
