@@ -16,6 +16,7 @@
 #include "../../include/b200fem.h"
 #include "dg_kronecker.cuh"
 #include "dg_kronecker_pipe.cuh"
+#include "dg_kronecker_march.cuh"
 #include "dg_kronecker_tensor.cuh"
 #include "dg_kronecker_tma.cuh"
 #include "dg_quadrature.cuh"
@@ -59,7 +60,7 @@ struct b200fem_operator {
   double *d_u = nullptr, *d_w = nullptr;                       // staging for the host-pointer API
   double *d_h = nullptr, *d_r = nullptr, *d_p = nullptr, *d_x = nullptr, *d_b = nullptr, *d_partial = nullptr, *d_sums = nullptr, *d_hist = nullptr;
   CgState* d_cg = nullptr; int hist_cap = 0;
-  bool kron_ready = false; std::vector<unsigned char> kron_tab; struct KronMapCache* map_cache = nullptr;
+  bool kron_ready = false; std::vector<unsigned char> kron_tab; struct KronMapCache* map_cache = nullptr; struct MarchMapCache* march_cache = nullptr;
   HaloPlan halo; HaloPlanDG halo_dg; HaloPlanP2P halo_p2p; const BoxDev* active_box = nullptr; int reserve_sms = 0; unsigned long long fused_seq = 0; bool last_launch_tensor = false;      // active_box: sub-box override for split launches
   cudaStream_t comm_stream = nullptr; cudaEvent_t ev_bnd = nullptr, ev_comm = nullptr, dbg_ev[2] = {nullptr, nullptr};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evx0 = nullptr, evx1 = nullptr; b200fem_timing timing{};
@@ -368,6 +369,92 @@ template <int N, bool HIER, bool SPLIT> static int launch_dg_kronecker_tensor(b2
   CUDA_OK(cudaGetLastError()); return B200FEM_OK;
 }
 
+// 4-D tensor of doubles [d3][d2][d1][d0] (d0 contiguous) with byte strides s1..s3 and box b0 x b1 x b2 x b3
+static bool make_map4(CUtensorMap* m, const double* base, const uint64_t (&d)[4], const uint64_t (&s)[3], const uint32_t (&bx)[4]) {
+  const cuuint64_t dims[4] = {d[0], d[1], d[2], d[3]}; const cuuint64_t strides[3] = {s[0], s[1], s[2]};
+  const cuuint32_t boxd[4] = {bx[0], bx[1], bx[2], bx[3]}; const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double*>(base), dims, strides, boxd, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+template <int N> static bool march_path_ok(const b200fem_operator* op, const double* u, const double* w, const double* bvec) {
+  const BoxDev& b = op->active_box ? *op->active_box : op->sp->box;
+  return N == 3 && b.dim == 3 && (b.own_hi[0] - b.own_lo[0]) % 2 == 0 && tensor_path_ok<N>(op, u, w, bvec);
+}
+struct MarchMapCache { static constexpr int kSlots = 32; KronMapKey key[kSlots]; KronMarchMaps maps[kSlots]; bool valid[kSlots] = {}; int next = 0; };
+// z-marching Kronecker kernel (dg_kronecker_march.cuh): persistent grid, every CTA gets the same number of plane-tiles
+template <int N, bool HIER> static int launch_dg_kronecker_march(b200fem_operator* op, const double* u, double* w, const double* bvec) {
+  constexpr int TX = 16, TY = 16, N3 = N * N * N;
+  using Cfg = KronMarchCfg<N, TX, TY>; const BoxDev& b = op->active_box ? *op->active_box : op->sp->box;
+  if (!op->kron_ready) {
+    KronHost kh = build_kron_tables(op->sp->tab, op->model, b.dim, b.h);
+    op->kron_tab.resize(sizeof(KronTabDev<N>));
+    KronTabDev<N>& K0 = *reinterpret_cast<KronTabDev<N>*>(op->kron_tab.data());
+    for (int d = 0; d < 3; ++d) for (int i = 0; i < N * N; ++i) { K0.S[d][i] = kh.S[d][i]; K0.Dlo[d][i] = kh.Dlo[d][i]; K0.Dhi[d][i] = kh.Dhi[d][i]; K0.L[d][i] = kh.L[d][i]; K0.R[d][i] = kh.R[d][i]; }
+    op->kron_ready = true;
+  }
+  const KronTabDev<N>& K = *reinterpret_cast<const KronTabDev<N>*>(op->kron_tab.data());
+  const int on[3] = {b.own_hi[0] - b.own_lo[0], b.own_hi[1] - b.own_lo[1], b.own_hi[2] - b.own_lo[2]};
+  const int tx = (on[0] + TX - 1) / TX, ty = (on[1] + TY - 1) / TY, ncols = tx * ty;
+  if (!op->march_cache) op->march_cache = new MarchMapCache;
+  MarchMapCache& mc = *op->march_cache;
+  KronMapKey key; std::memset(&key, 0, sizeof(key)); key.u = u; key.w = w; key.b = bvec;
+  for (int d = 0; d < 3; ++d) { key.lo[d] = b.own_lo[d]; key.hi[d] = b.own_hi[d]; }
+  int slot = -1;
+  for (int i = 0; i < MarchMapCache::kSlots; ++i) if (mc.valid[i] && mc.key[i] == key) { slot = i; break; }
+  if (slot < 0) {
+    slot = mc.next; mc.next = (mc.next + 1) % MarchMapCache::kSlots;
+    const uint64_t sp = 2ull * N3 * 8, s1 = (uint64_t)b.n[0] * N3 * 8, s2 = s1 * b.n[1];
+    const long long own_off = ((long long)b.own_lo[0] + (long long)b.n[0] * (b.own_lo[1] + (long long)b.n[1] * b.own_lo[2])) * N3;
+    KronMarchMaps& M = mc.maps[slot];
+    const uint64_t du[4] = {2ull * N3, (uint64_t)b.n[0] / 2, (uint64_t)b.n[1], (uint64_t)b.n[2]};
+    const uint64_t dw[4] = {2ull * N3, (uint64_t)on[0] / 2, (uint64_t)on[1], (uint64_t)on[2]};
+    const uint64_t st[3] = {sp, s1, s2};
+    const uint32_t bplane[4] = {2u * N3, (TX + 4) / 2, TY + 2, 1}, btile[4] = {2u * N3, TX / 2, TY, 1}, bwarp[4] = {2u * N3, TX / 2, 32 / TX, 1};
+    bool ok = make_map4(&M.u_plane, u, du, st, bplane) && make_map4(&M.u_edge, u, du, st, btile) &&
+              make_map4(&M.w_tile, w + own_off, dw, st, bwarp) && make_map4(&M.b_tile, (bvec ? bvec : w) + own_off, dw, st, bwarp);
+    REQUIRE(ok, B200FEM_ERR_CUDA, "cuTensorMapEncodeTiled (4-D) failed");
+    mc.key[slot] = key; mc.valid[slot] = true;
+  }
+  static int sms = 0;
+  if (!sms) CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, op->sp->mesh->ctx->device));
+  auto kern = bvec ? dg_kronecker_march_kernel<N, HIER, TX, TY, true> : dg_kronecker_march_kernel<N, HIER, TX, TY, false>;
+#ifdef B200FEM_MARCH_EXPERIMENTS
+  { static const char* e = std::getenv("B200FEM_MARCH_EXP"); const int ex = e ? std::atoi(e) : 0;
+    if (ex == 1) kern = dg_kronecker_march_kernel<N, HIER, TX, TY, false, 1>; if (ex == 2) kern = dg_kronecker_march_kernel<N, HIER, TX, TY, false, 2>; if (ex == 3) kern = dg_kronecker_march_kernel<N, HIER, TX, TY, false, 3>;
+    if (ex) CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes())); }
+#endif
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[bvec ? 1 : 0]) { CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes())); attr_set[bvec ? 1 : 0] = true; }
+  const long long total = (long long)ncols * on[2];
+  const int grid = (int)std::max(1ll, std::min(total, (long long)(sms - op->reserve_sms)));
+  static long long* dbg = nullptr; static int dbg_calls = 0, dbg_lin = 0;
+  if (!dbg && std::getenv("B200FEM_DEBUG_TIMELINE")) { cudaMalloc(&dbg, 8 * (256 + 4 * 160)); cudaMemset(dbg, 0, 8 * (256 + 4 * 160)); }
+    // programmatic dependent launch: the CTAs of this launch may be scheduled while the previous kernel of the stream drains;
+  // the kernel itself waits (griddepcontrol.wait) before it touches global memory
+  static const bool no_pdl = std::getenv("B200FEM_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg = {}; cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(Cfg::kThreads); cfg.dynamicSmemBytes = Cfg::smem_bytes(); cfg.stream = op->sp->mesh->ctx->stream;
+  cudaLaunchAttribute attr[1]; attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
+  static const int skew = std::getenv("B200FEM_MARCH_SKEW") ? std::atoi(std::getenv("B200FEM_MARCH_SKEW")) : 0;
+  CUDA_OK(cudaLaunchKernelEx(&cfg, kern, K, b, mc.maps[slot], tx, ncols, skew, dbg));
+  if (dbg && !bvec) ++dbg_lin;
+  if (dbg && (++dbg_calls == 60 || (!bvec && dbg_lin == 60))) { std::fprintf(stderr, "has_b = %d\n", bvec ? 1 : 0);        // dump the step timeline of CTA 0 and CTA 77 for one warm call (cycles since CTA start)
+    std::vector<long long> h(256 + 4 * 160); cudaDeviceSynchronize(); cudaMemcpy(h.data(), dbg, h.size() * 8, cudaMemcpyDeviceToHost);
+    { long long s0 = h[256]; for (int c = 0; c < grid; ++c) s0 = std::min(s0, h[256 + 4 * c]);
+      std::fprintf(stderr, "[march CTAs] start/end ns relative to the first CTA start, steps:");
+      for (int c = 0; c < grid; ++c) std::fprintf(stderr, "%s%d:%lld-%lld/%lld", c % 8 ? "  " : "\n   ", c, h[256 + 4 * c] - s0, h[256 + 4 * c + 1] - s0, h[256 + 4 * c + 2]);
+      long long e1 = 0; for (int c = 0; c < grid; ++c) e1 = std::max(e1, h[256 + 4 * c + 1]);
+      std::fprintf(stderr, "\n[march CTAs] previous kernel's last CTA ended %lld ns before this kernel's first CTA started; this kernel's CTAs span %lld ns\n", s0 - h[256 + 3], e1 - s0); }
+    for (int c = 0; c < 2; ++c) {
+      const long long t0 = h[8 * (16 * c + 14)];
+      std::fprintf(stderr, "[march timeline] CTA %d: end at %lld cycles; per step: begin | u landed | b landed | epilogue done | end   (z, col)\n", c ? 77 : 0, h[8 * (16 * c + 15)] - t0);
+      for (int k = 0; k < 14; ++k) { const long long* r = &h[8 * (16 * c + k)]; if (!r[0]) break;
+        std::fprintf(stderr, "  step %2d: %7lld %7lld %7lld %7lld %7lld   (%lld, %lld)\n", k, r[0] - t0, r[1] - t0, r[2] ? r[2] - t0 : -1, r[3] - t0, r[4] - t0, r[5], r[6]); }
+    }
+  }
+  return B200FEM_OK;
+}
+
 static long long* g_dbg = nullptr; static int g_dbg_calls = 0;
 template <int N, bool HIER, bool SPLIT> static int launch_dg_kronecker_pipe(b200fem_operator* op, const double* u, double* w, const double* bvec) {
   constexpr int TX = 8, TY = 4, TZ = 4;
@@ -441,15 +528,18 @@ static int apply_local(b200fem_operator* op, const double* u, double* w, bool li
     const double* bvec = nullptr;
     if (!linear && op->model.data) { int rc = ensure_bvec(op); if (rc) return rc; bvec = op->d_bvec; }
     // v2 (bulk-copy staged) needs 8-byte aligned vectors whose w / b share the 16-byte phase; otherwise v1
-    static const char* variant_env = std::getenv("B200FEM_KRON_VARIANT");      // v1 | tma | pipe | split | tensor (default) | tensor3, for A/B measurements
+    const char* variant_env = std::getenv("B200FEM_KRON_VARIANT");      // v1 | tma | pipe | split | tensor (default) | tensor3, for A/B measurements
     const std::string variant = variant_env ? variant_env : "tensor";
     const bool phase_ok = !bvec || ((reinterpret_cast<uintptr_t>(bvec) ^ reinterpret_cast<uintptr_t>(w)) & 8) == 0;
     const bool hier = s->kind == B200FEM_DG_LEGENDRE_HIER;
     int rc;
-    op->last_launch_tensor = variant == "tensor" && tensor_path_ok<3>(op, u, w, bvec) && N == 3;
-    if (variant == "tensor" && tensor_path_ok<3>(op, u, w, bvec) && N == 3) rc = hier ? launch_dg_kronecker_tensor<3, true, false>(op, u, w, bvec) : launch_dg_kronecker_tensor<3, false, false>(op, u, w, bvec);
+    const bool use_march = variant == "march" && N == 3 && !op->fused_seq && march_path_ok<3>(op, u, w, bvec);
+    const bool use_tensor = !use_march && (variant == "tensor" || variant == "march") && N == 3 && tensor_path_ok<3>(op, u, w, bvec);
+    op->last_launch_tensor = use_tensor;
+    if (use_march) rc = hier ? launch_dg_kronecker_march<3, true>(op, u, w, bvec) : launch_dg_kronecker_march<3, false>(op, u, w, bvec);
+    else if (use_tensor) rc = hier ? launch_dg_kronecker_tensor<3, true, false>(op, u, w, bvec) : launch_dg_kronecker_tensor<3, false, false>(op, u, w, bvec);
     else if (variant == "tensor3" && tensor_path_ok<3>(op, u, w, bvec) && N == 3) rc = hier ? launch_dg_kronecker_tensor<3, true, true>(op, u, w, bvec) : launch_dg_kronecker_tensor<3, false, true>(op, u, w, bvec);
-    else if (N == 3 && phase_ok && (variant == "pipe" || variant == "tensor" || variant == "tensor3")) rc = hier ? launch_dg_kronecker_pipe<3, true, false>(op, u, w, bvec) : launch_dg_kronecker_pipe<3, false, false>(op, u, w, bvec);
+    else if (N == 3 && phase_ok && (variant == "pipe" || variant == "tensor" || variant == "tensor3" || variant == "march")) rc = hier ? launch_dg_kronecker_pipe<3, true, false>(op, u, w, bvec) : launch_dg_kronecker_pipe<3, false, false>(op, u, w, bvec);
     else if (N == 3 && phase_ok && variant == "split") rc = hier ? launch_dg_kronecker_pipe<3, true, true>(op, u, w, bvec) : launch_dg_kronecker_pipe<3, false, true>(op, u, w, bvec);
     else if (N == 3 && phase_ok && variant == "tma") rc = hier ? launch_dg_kronecker_tma<3, true>(op, u, w, bvec) : launch_dg_kronecker_tma<3, false>(op, u, w, bvec);
     else rc = N == 2 ? launch_dg_kronecker<2, 8, 8, 4>(op, u, w, bvec) : launch_dg_kronecker<3, 8, 4, 4>(op, u, w, bvec);
@@ -633,7 +723,7 @@ extern "C" int b200fem_operator_create(b200fem_space* s, const b200fem_model* mo
   }
   *out = op; return B200FEM_OK;
 }
-static void free_map_cache(b200fem_operator* op) { delete op->map_cache; op->map_cache = nullptr; }
+static void free_map_cache(b200fem_operator* op) { delete op->map_cache; op->map_cache = nullptr; delete op->march_cache; op->march_cache = nullptr; }
 extern "C" int b200fem_operator_destroy(b200fem_operator* op) {
   if (!op) return B200FEM_OK;
   for (void* p : {(void*)op->d_perm, (void*)op->d_bvec, (void*)op->d_dmask, (void*)op->d_dvals, (void*)op->d_aux, (void*)op->d_u, (void*)op->d_w, (void*)op->d_h, (void*)op->d_r,

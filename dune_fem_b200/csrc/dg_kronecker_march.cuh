@@ -1,0 +1,257 @@
+// dg_kronecker_march.cuh -- Kronecker-form DG apply, v5: persistent z-marching with a register pipeline.
+//
+// Same arithmetic as dg_kronecker.cuh:  w_K = sum_d [ S_d u_K + L_d u_{K-e_d} + R_d u_{K+e_d} ] - b_K.
+// What changed against the tile kernel (dg_kronecker_tensor.cuh) is the data movement.  Measured there (profiles/
+// r01_dg_kronecker_tensor.md): all global->SM traffic, L2 hits included, is capped near the DRAM rate, so the 2.5x halo
+// re-read of 8x4x4 tiles -- not DRAM -- bounded the kernel, and 4 consumer warps could not hide shared-load latency.
+//
+//  * A CTA owns a column of TX x TY elements and marches through z.  One thread per element keeps THREE things in
+//    registers: u_K of the current plane and the two partial results w(z-1), w(z).  When plane z arrives,
+//        w(z-1) += R_z u(z)   -> complete, written out;      w(z+1)  = L_z u(z);      w(z) += S u(z) + x/y neighbours
+//    so z-neighbours are never read from shared memory and never re-read from L2: only the two end planes of a run
+//    are loaded twice (as own-only boxes without x/y halo).
+//  * One plane incl. its x/y halo is ONE 4-D TMA box (cp.async.bulk.tensor.4d) over the view [z][y][x/2][2*n^3] of the
+//    dof vector (element pairs make the innermost extent a multiple of 16 bytes); x/y neighbours are at constant
+//    offsets (+-n^3, +-row) inside that box.  Out-of-range parts are zero-filled by the TMA unit = "no neighbour".
+//  * 8 consumer warps (16x16 elements per plane) + 1 producer warp (setmaxnreg moves its registers to the consumers),
+//    2-stage plane ring.  Output is warp-autonomous: every warp has its own staging slab (its two tile rows) that
+//    receives the rows of the load vector b (TMA, per-warp mbarrier), is overwritten with A u - b and leaves through
+//    a TMA store issued by lane 0 -- no CTA-wide barrier and no producer round trip on the output path.
+//  * The plane-tiles (column, z) are split evenly over the persistent grid: every CTA gets the same number of planes.
+//
+// Traffic per dof (C2, 148 CTAs, runs of ~7 planes): u is read 1.7x instead of 2.5x; shared-memory loads per element
+// drop from 7 to 5 element blocks.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "dg_kronecker_tensor.cuh"
+
+namespace b200fem {
+
+struct KronMarchMaps {
+  CUtensorMap u_plane;   // box {2*N3, (TX+4)/2, TY+2, 1} over the local box (owned + ghost)
+  CUtensorMap u_edge;    // box {2*N3, TX/2, TY, 1}       over the local box
+  CUtensorMap b_tile;    // box {2*N3, TX/2, 32/TX, 1}    over the owned sub-box of the load vector: the rows of one warp
+  CUtensorMap w_tile;    // same over the owned sub-box of w
+};
+
+namespace ptx {
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+               ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t src) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+}  // namespace ptx
+
+template <int N, int TX, int TY> struct KronMarchCfg {
+  static constexpr int N3 = N * N * N;
+  static constexpr int kConsumers = TX * TY, kThreads = kConsumers + 128;   // 2 consumer warpgroups + 1 producer warpgroup
+  static constexpr int RS = (TX + 4) * N3;                 // doubles per staged row (x0-2 .. x0+TX+1)
+  static constexpr int RO = TX * N3;                       // doubles per output / edge-plane row
+  static constexpr int kU = ((TY + 2) * RS + 15) / 16 * 16;  // doubles per plane stage, 128-byte multiple
+  static constexpr int kO = TY * RO;
+  static constexpr uint32_t kBytesU = 8u * (TY + 2) * RS, kBytesE = 8u * kO, kBytesB = 8u * kO;
+  static constexpr size_t smem_bytes() { return sizeof(double) * (2 * (size_t)kU + kO + 6 * N * N + 2) + 8 * (4 + kConsumers / 32) + 128; }
+  static_assert(TX % 2 == 0 && (kO * 8) % 128 == 0, "TMA destinations must stay 128-byte aligned");
+};
+
+// Walks the plane steps of one CTA: plane-tiles t in [t0, t1) of the linearised (column, z) index are split into
+// runs (one column, z in [za, zb)); a run is processed as the steps z = za-1 .. zb (the first and the last step only
+// touch the neighbouring plane's own elements).
+struct MarchCursor {
+  int t, t1, nz, col, za, zb, z; bool valid;
+  __device__ __forceinline__ void start_run() {
+    valid = t < t1;
+    if (valid) { col = t / nz; za = t - col * nz; zb = min(nz, za + (t1 - t)); z = za - 1; }
+  }
+  __device__ __forceinline__ void init(int t0_, int t1_, int nz_) { t = t0_; t1 = t1_; nz = nz_; start_run(); }
+  __device__ __forceinline__ void advance() { if (++z > zb) { t += zb - za; start_run(); } }
+  __device__ __forceinline__ bool has_prev() const { return z > za; }          // plane z-1 is owned by this run: it completes now
+  __device__ __forceinline__ bool edge() const { return z == za - 1 || z == zb; }
+};
+
+template <int N, bool HIER, int TX, int TY, bool HAS_B, int EXP = 0>
+__global__ void __launch_bounds__(KronMarchCfg<N, TX, TY>::kThreads, 1)
+dg_kronecker_march_kernel(const __grid_constant__ KronTabDev<N> K, const __grid_constant__ BoxDev box,
+                          const __grid_constant__ KronMarchMaps M, const int tiles_x, const int ncols, const int skew, long long* __restrict__ dbg) {
+  using Cfg = KronMarchCfg<N, TX, TY>;
+  constexpr int N3 = Cfg::N3, RS = Cfg::RS, RO = Cfg::RO, NN = N * N;
+  constexpr int kWarps = Cfg::kConsumers / 32, kRowsPerWarp = 32 / TX, kSlab = kRowsPerWarp * RO;   // doubles per warp slab
+  static_assert(32 % TX == 0 && (kSlab * 8) % 128 == 0, "a warp owns whole tile rows; its slab is a TMA box");
+  constexpr PermTable<N, HIER> P{};
+  extern __shared__ __align__(128) unsigned char smem_dyn[];
+  double* sbase = reinterpret_cast<double*>(smem_dyn + ((128u - (ptx::smem_addr(smem_dyn) & 127u)) & 127u));
+  double* const O = sbase + 2 * (size_t)Cfg::kU;                    // kWarps output slabs
+  double* const Dsm = O + Cfg::kO;                                  // boundary corrections [axis][lo|hi][N*N]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Dsm + 6 * NN + (6 * NN) % 2);
+  const uint32_t ufull = ptx::smem_addr(bars), ufree = ptx::smem_addr(bars + 2), wbar0 = ptx::smem_addr(bars + 4);
+  const int tid = threadIdx.x;
+  if (dbg && tid == 0 && (blockIdx.x == 0 || blockIdx.x == 77)) dbg[((blockIdx.x ? 16 : 0) + 14) * 8] = clock64();
+  auto gtime = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (long long)t; };
+  if (dbg && tid == 0) { dbg[256 + 4 * blockIdx.x] = gtime(); dbg[256 + 4 * blockIdx.x + 3] = *(volatile long long*)&dbg[250]; }
+
+  const int nz = box.own_hi[2] - box.own_lo[2];
+  const long long total = (long long)ncols * nz;
+  const int t0 = (int)(total * blockIdx.x / gridDim.x), t1 = (int)(total * (blockIdx.x + 1) / gridDim.x);
+  auto plane_exists = [&](const MarchCursor& c) { const int lz = box.own_lo[2] + c.z; return lz >= 0 && lz < box.n[2]; };
+  auto issue_u = [&](const MarchCursor& c, int s) {
+    const int x0 = box.own_lo[0] + (c.col % tiles_x) * TX, y0 = box.own_lo[1] + (c.col / tiles_x) * TY, lz = box.own_lo[2] + c.z;
+    const uint32_t dst = ptx::smem_addr(sbase + (size_t)s * Cfg::kU), bar = ufull + 8 * s;
+    if (c.edge()) { ptx::mbar_expect_tx(bar, Cfg::kBytesE); ptx::tma_load_4d(dst, &M.u_edge, 0, x0 / 2, y0, lz, bar); }
+    else          { ptx::mbar_expect_tx(bar, Cfg::kBytesU); ptx::tma_load_4d(dst, &M.u_plane, 0, (x0 - 2) / 2, y0 - 1, lz, bar); }
+  };
+  MarchCursor ld;                                                    // producer thread: next plane to load
+  if (tid == Cfg::kConsumers) {
+    // the producer thread sets the barriers up and gets the first two planes moving before anything else happens
+    ptx::mbar_init(ufull, 1); ptx::mbar_init(ufull + 8, 1);
+    ptx::mbar_init(ufree, Cfg::kConsumers); ptx::mbar_init(ufree + 8, Cfg::kConsumers);
+    for (int w = 0; w < kWarps; ++w) ptx::mbar_init(wbar0 + 8 * w, 1);
+    ptx::fence_barrier_init(); ptx::fence_proxy_async();
+    // programmatic dependent launch: this CTA may have started while the previous kernel of the stream was still draining;
+    // nothing of u / b / w is touched before that kernel has completed (no-op for an ordinary launch)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    ld.init(t0, t1, nz);
+    for (int i = 0; i < 2; ++i) { while (ld.valid && !plane_exists(ld)) ld.advance(); if (ld.valid) { issue_u(ld, i); ld.advance(); } }
+  }
+  if (tid < 3 * NN) { Dsm[(tid / NN) * 2 * NN + tid % NN] = K.Dlo[tid / NN][tid % NN]; Dsm[(tid / NN) * 2 * NN + NN + tid % NN] = K.Dhi[tid / NN][tid % NN]; }
+  __syncthreads();
+  asm volatile("griddepcontrol.launch_dependents;");               // the next kernel may take over SMs as soon as CTAs of this one retire
+  if (tid != Cfg::kConsumers) asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  if (tid >= Cfg::kConsumers) {
+    // ============================== producer: one elected thread streams the u planes ==============================
+    // register reallocation between warpgroups (as in warp-specialised GEMMs): the producer group gives its registers
+    // to the consumers, which need 3 x n^3 doubles each
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    if (tid != Cfg::kConsumers) return;
+    MarchCursor cur; cur.init(t0, t1, nz);
+    auto next_load = [&]() { while (ld.valid && !plane_exists(ld)) ld.advance(); };
+    int ku = 0;
+    for (; cur.valid; cur.advance()) {
+      if (!plane_exists(cur)) continue;
+      next_load(); if (!ld.valid) break;
+      ptx::mbar_wait(ufree + 8 * (ku & 1), (ku >> 1) & 1);           // plane consumed: its stage takes the load after next
+      issue_u(ld, ku & 1); ld.advance(); ++ku;
+    }
+    return;
+  }
+
+  // ============================== consumers: one thread per element of the plane ==============================
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
+  const int tx = tid % TX, ty = tid / TX, warp = tid / 32, lane = tid % 32;
+  double* const slab = O + (size_t)warp * kSlab;                     // this warp's rows of the output tile
+  double* const o = slab + (ty % kRowsPerWarp) * RO + tx * N3;
+  const uint32_t wbar = wbar0 + 8 * warp;
+  const int wrow = warp * kRowsPerWarp;                              // first tile row of this warp
+  const int on1 = box.own_hi[1] - box.own_lo[1];
+  double A[N3], B[N3];                                               // A: plane z-1 (waits for R_z u(z)),  B: plane z
+  int ku = 0, eb = 0, kstep = 0;
+  MarchCursor cur; cur.init(t0, t1, nz);
+  int gcx = 0, gcy = 0;
+  bool rows_owned = false;
+
+  // the warp's own output path: lane 0 loads its rows of the load vector b into the slab and stores the finished rows
+  auto next_epilogue = [&](MarchCursor c) { while (c.valid && !c.has_prev()) c.advance(); return c; };
+  auto issue_b = [&](const MarchCursor& c) {                         // lane 0 only
+    const int y = (c.col / tiles_x) * TY + wrow;
+    if (y < on1) { ptx::mbar_expect_tx(wbar, 8u * kSlab); ptx::tma_load_4d(ptx::smem_addr(slab), &M.b_tile, 0, (c.col % tiles_x) * (TX / 2), y, c.z - 1, wbar); }
+    else ptx::mbar_arrive(wbar);
+  };
+  if (lane == 0) ptx::prefetch_tensormap(&M.w_tile);
+  if (HAS_B && lane == 0) { ptx::prefetch_tensormap(&M.b_tile); const MarchCursor c = next_epilogue(cur); if (c.valid) issue_b(c); }
+
+  // The two warps that share a scheduler (w and w+4) would otherwise run in lock-step: both in their FMA phases (pipe
+  // shared), then both in their latency-bound phases (pipe idle).  A one-time skew of the second group interleaves them.
+  if (warp >= kWarps / 2 && skew > 0) { const long long t_ = clock64(); while (clock64() - t_ < skew) { } }
+  for (; cur.valid; cur.advance()) {
+    if (cur.z == cur.za - 1) {                                       // a new run starts
+      gcx = box.origin[0] + box.own_lo[0] + (cur.col % tiles_x) * TX + tx;
+      gcy = box.origin[1] + box.own_lo[1] + (cur.col / tiles_x) * TY + ty;
+      rows_owned = (cur.col / tiles_x) * TY + wrow < on1;
+#pragma unroll
+      for (int t = 0; t < N3; ++t) { A[t] = 0.0; B[t] = 0.0; }
+    }
+    const bool exists = plane_exists(cur), edge = cur.edge();
+    const bool rec = dbg && tid == 0 && (blockIdx.x == 0 || blockIdx.x == 77) && kstep < 14;
+    long long* const drow = dbg + ((blockIdx.x ? 16 : 0) + kstep) * 8;
+    if (rec) { drow[0] = clock64(); drow[5] = cur.z; drow[6] = cur.col; }
+    const double* st = sbase + (size_t)(ku & 1) * Cfg::kU;
+    const double* own = edge ? st + ty * RO + tx * N3 : st + (ty + 1) * RS + (tx + 2) * N3;
+    double v[N3];
+    if (exists) {
+      ptx::mbar_wait(ufull + 8 * (ku & 1), (ku >> 1) & 1);
+#pragma unroll
+      for (int t = 0; t < N3; ++t) v[t] = own[P.p[t]];
+    } else {
+#pragma unroll
+      for (int t = 0; t < N3; ++t) v[t] = 0.0;
+    }
+    if (rec) drow[1] = clock64();
+    // The order below is a hand-made software pipeline: register-only work (R, S) comes first so that the b rows have time
+    // to land; the latency-bound slab update shares a basic block with the x-neighbour FMAs; the next b load is issued
+    // between the two y-neighbours, when the store has long read the slab.
+    const bool hp = cur.has_prev();
+    if (hp && exists) apply_axis<N, 2>(K.R[2], v, A);                // plane z-1 is complete after R_z u(z)
+    if (!edge) { apply_axis<N, 0>(K.S[0], v, B); apply_axis<N, 1>(K.S[1], v, B); apply_axis<N, 2>(K.S[2], v, B); }
+    if (hp) {
+      if (HAS_B) { ptx::mbar_wait(wbar, eb & 1); ++eb; }              // b rows have landed (and the previous store has read the slab)
+      else { if (lane == 0) ptx::bulk_wait_read(); __syncwarp(); }   // the previous store has read the slab
+    }
+    if (rec) drow[2] = clock64();
+    auto slab_update = [&]() {
+#pragma unroll
+      for (int t = 0; t < N3; ++t) o[P.p[t]] = HAS_B ? A[t] - o[P.p[t]] : A[t];
+    };
+    auto x_neighbours = [&]() {
+      if (EXP == 3) return;
+      if (EXP == 1) { apply_axis<N, 0>(K.L[0], v, B); apply_axis<N, 0>(K.R[0], v, B); return; }
+      apply_axis_smem<N, 0, HIER>(K.L[0], own - N3, B); apply_axis_smem<N, 0, HIER>(K.R[0], own + N3, B); };
+    if (hp && !edge) { if (EXP != 2) slab_update(); x_neighbours(); }
+    else { if (hp && EXP != 2) slab_update(); if (!edge) x_neighbours(); }
+    if (hp && EXP != 2) {
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0 && rows_owned) {
+        ptx::tma_store_4d(&M.w_tile, 0, (cur.col % tiles_x) * (TX / 2), (cur.col / tiles_x) * TY + wrow, cur.z - 1, ptx::smem_addr(slab));
+        ptx::bulk_commit();
+      }
+    }
+    if (rec) drow[3] = clock64();
+    if (!edge) { if (EXP == 1) apply_axis<N, 1>(K.L[1], v, B); else if (EXP != 3) apply_axis_smem<N, 1, HIER>(K.L[1], own - RS, B); }
+    if (HAS_B && lane == 0 && hp) {                                  // the slab takes the b rows of the next output plane
+      MarchCursor c = cur; c.advance(); c = next_epilogue(c);
+      if (c.valid) { ptx::bulk_wait_read(); issue_b(c); }
+    }
+    if (!edge) {
+      if (EXP == 1) apply_axis<N, 1>(K.R[1], v, B); else if (EXP != 3) apply_axis_smem<N, 1, HIER>(K.R[1], own + RS, B);
+      // domain-boundary corrections of the self matrices (tables in shared memory: the choice is per thread)
+      const int gc[3] = {gcx, gcy, box.origin[2] + box.own_lo[2] + cur.z};
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const bool lo = gc[a] == 0, hi = gc[a] == box.gn[a] - 1;
+        if (lo || hi) {
+          double m[NN];
+#pragma unroll
+          for (int i = 0; i < NN; ++i) m[i] = (lo ? Dsm[a * 2 * NN + i] : 0.0) + (hi ? Dsm[a * 2 * NN + NN + i] : 0.0);
+          if (a == 0) apply_axis<N, 0>(m, v, B); else if (a == 1) apply_axis<N, 1>(m, v, B); else apply_axis<N, 2>(m, v, B);
+        }
+      }
+    }
+    if (exists) { ptx::mbar_arrive(ufree + 8 * (ku & 1)); ++ku; }
+    // rotate: plane z now waits for R_{z+1}; plane z+1 starts with L_z u(z)
+#pragma unroll
+    for (int t = 0; t < N3; ++t) { A[t] = B[t]; B[t] = 0.0; }
+    if (exists && cur.z + 1 < cur.zb) apply_axis<N, 2>(K.L[2], v, B);
+    if (rec) drow[4] = clock64();
+    ++kstep;
+  }
+  if (lane == 0) ptx::bulk_wait_all();
+  if (dbg && tid == 0 && (blockIdx.x == 0 || blockIdx.x == 77)) dbg[((blockIdx.x ? 16 : 0) + 15) * 8] = clock64();
+  if (dbg && lane == 0) { atomicMax((unsigned long long*)&dbg[256 + 4 * blockIdx.x + 1], (unsigned long long)gtime()); atomicMax((unsigned long long*)&dbg[250], (unsigned long long)gtime()); if (warp == 0) dbg[256 + 4 * blockIdx.x + 2] = kstep; }
+}
+
+}  // namespace b200fem
