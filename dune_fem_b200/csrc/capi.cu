@@ -23,6 +23,7 @@
 #include "halo.cuh"
 #include "integrands.cuh"
 #include "kron_tables.hpp"
+#include "lagrange_kronecker.cuh"
 #include "lagrange_quadrature.cuh"
 #include "tables.hpp"
 #include "vec_kernels.cuh"
@@ -60,7 +61,7 @@ struct b200fem_operator {
   double *d_u = nullptr, *d_w = nullptr;                       // staging for the host-pointer API
   double *d_h = nullptr, *d_r = nullptr, *d_p = nullptr, *d_x = nullptr, *d_b = nullptr, *d_partial = nullptr, *d_sums = nullptr, *d_hist = nullptr;
   CgState* d_cg = nullptr; int hist_cap = 0;
-  bool kron_ready = false; std::vector<unsigned char> kron_tab; struct KronMapCache* map_cache = nullptr; struct MarchMapCache* march_cache = nullptr;
+  bool kron_ready = false; int kron_chk = -1; double* d_lag_rows = nullptr; LagKronRows lag_rows{}; std::vector<unsigned char> kron_tab; struct KronMapCache* map_cache = nullptr; struct MarchMapCache* march_cache = nullptr;
   HaloPlan halo; HaloPlanDG halo_dg; HaloPlanP2P halo_p2p; const BoxDev* active_box = nullptr; int reserve_sms = 0; unsigned long long fused_seq = 0; bool last_launch_tensor = false;      // active_box: sub-box override for split launches
   cudaStream_t comm_stream = nullptr; cudaEvent_t ev_bnd = nullptr, ev_comm = nullptr, dbg_ev[2] = {nullptr, nullptr};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evx0 = nullptr, evx1 = nullptr; b200fem_timing timing{};
@@ -417,41 +418,32 @@ template <int N, bool HIER> static int launch_dg_kronecker_march(b200fem_operato
   }
   static int sms = 0;
   if (!sms) CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, op->sp->mesh->ctx->device));
-  auto kern = bvec ? dg_kronecker_march_kernel<N, HIER, TX, TY, true> : dg_kronecker_march_kernel<N, HIER, TX, TY, false>;
-#ifdef B200FEM_MARCH_EXPERIMENTS
-  { static const char* e = std::getenv("B200FEM_MARCH_EXP"); const int ex = e ? std::atoi(e) : 0;
-    if (ex == 1) kern = dg_kronecker_march_kernel<N, HIER, TX, TY, false, 1>; if (ex == 2) kern = dg_kronecker_march_kernel<N, HIER, TX, TY, false, 2>; if (ex == 3) kern = dg_kronecker_march_kernel<N, HIER, TX, TY, false, 3>;
-    if (ex) CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes())); }
-#endif
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[bvec ? 1 : 0]) { CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes())); attr_set[bvec ? 1 : 0] = true; }
+  // checkerboard self matrices on the y and z axes (no advection there: even and odd Legendre modes decouple); entries
+  // that are zero up to quadrature rounding (<= 1e-14 of the matrix norm) are not multiplied at all
+  if (op->kron_chk < 0) {
+    bool chk = true;
+    for (int d = 1; d < 3; ++d) {
+      double mx = 0; for (int i = 0; i < N * N; ++i) mx = std::max(mx, std::fabs(K.S[d][i]));
+      for (int i = 0; i < N; ++i) for (int j = 0; j < N; ++j) if (((i + j) & 1) && std::fabs(K.S[d][i * N + j]) > 1e-14 * mx) chk = false;
+    }
+    op->kron_chk = chk && !std::getenv("B200FEM_NO_CHK") ? 1 : 0;
+  }
+  const int variant = (bvec ? 1 : 0) + (op->kron_chk ? 2 : 0);
+  using KernT = void (*)(const KronTabDev<N>, const BoxDev, const KronMarchMaps, const int, const int);
+  const KernT kerns[4] = {dg_kronecker_march_kernel<N, HIER, TX, TY, false, false>, dg_kronecker_march_kernel<N, HIER, TX, TY, true, false>,
+                          dg_kronecker_march_kernel<N, HIER, TX, TY, false, true>, dg_kronecker_march_kernel<N, HIER, TX, TY, true, true>};
+  KernT kern = kerns[variant];
+  static bool attr_set[4] = {false, false, false, false};
+  if (!attr_set[variant]) { CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes())); attr_set[variant] = true; }
   const long long total = (long long)ncols * on[2];
   const int grid = (int)std::max(1ll, std::min(total, (long long)(sms - op->reserve_sms)));
-  static long long* dbg = nullptr; static int dbg_calls = 0, dbg_lin = 0;
-  if (!dbg && std::getenv("B200FEM_DEBUG_TIMELINE")) { cudaMalloc(&dbg, 8 * (256 + 4 * 160)); cudaMemset(dbg, 0, 8 * (256 + 4 * 160)); }
-    // programmatic dependent launch: the CTAs of this launch may be scheduled while the previous kernel of the stream drains;
+  // programmatic dependent launch: the CTAs of this launch may be scheduled while the previous kernel of the stream drains;
   // the kernel itself waits (griddepcontrol.wait) before it touches global memory
   static const bool no_pdl = std::getenv("B200FEM_NO_PDL") != nullptr;
   cudaLaunchConfig_t cfg = {}; cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(Cfg::kThreads); cfg.dynamicSmemBytes = Cfg::smem_bytes(); cfg.stream = op->sp->mesh->ctx->stream;
   cudaLaunchAttribute attr[1]; attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
-  static const int skew = std::getenv("B200FEM_MARCH_SKEW") ? std::atoi(std::getenv("B200FEM_MARCH_SKEW")) : 0;
-  CUDA_OK(cudaLaunchKernelEx(&cfg, kern, K, b, mc.maps[slot], tx, ncols, skew, dbg));
-  if (dbg && !bvec) ++dbg_lin;
-  if (dbg && (++dbg_calls == 60 || (!bvec && dbg_lin == 60))) { std::fprintf(stderr, "has_b = %d\n", bvec ? 1 : 0);        // dump the step timeline of CTA 0 and CTA 77 for one warm call (cycles since CTA start)
-    std::vector<long long> h(256 + 4 * 160); cudaDeviceSynchronize(); cudaMemcpy(h.data(), dbg, h.size() * 8, cudaMemcpyDeviceToHost);
-    { long long s0 = h[256]; for (int c = 0; c < grid; ++c) s0 = std::min(s0, h[256 + 4 * c]);
-      std::fprintf(stderr, "[march CTAs] start/end ns relative to the first CTA start, steps:");
-      for (int c = 0; c < grid; ++c) std::fprintf(stderr, "%s%d:%lld-%lld/%lld", c % 8 ? "  " : "\n   ", c, h[256 + 4 * c] - s0, h[256 + 4 * c + 1] - s0, h[256 + 4 * c + 2]);
-      long long e1 = 0; for (int c = 0; c < grid; ++c) e1 = std::max(e1, h[256 + 4 * c + 1]);
-      std::fprintf(stderr, "\n[march CTAs] previous kernel's last CTA ended %lld ns before this kernel's first CTA started; this kernel's CTAs span %lld ns\n", s0 - h[256 + 3], e1 - s0); }
-    for (int c = 0; c < 2; ++c) {
-      const long long t0 = h[8 * (16 * c + 14)];
-      std::fprintf(stderr, "[march timeline] CTA %d: end at %lld cycles; per step: begin | u landed | b landed | epilogue done | end   (z, col)\n", c ? 77 : 0, h[8 * (16 * c + 15)] - t0);
-      for (int k = 0; k < 14; ++k) { const long long* r = &h[8 * (16 * c + k)]; if (!r[0]) break;
-        std::fprintf(stderr, "  step %2d: %7lld %7lld %7lld %7lld %7lld   (%lld, %lld)\n", k, r[0] - t0, r[1] - t0, r[2] ? r[2] - t0 : -1, r[3] - t0, r[4] - t0, r[5], r[6]); }
-    }
-  }
+  CUDA_OK(cudaLaunchKernelEx(&cfg, kern, K, b, mc.maps[slot], tx, ncols));
   return B200FEM_OK;
 }
 
@@ -506,6 +498,36 @@ template <int N> static int launch_lagrange(b200fem_operator* op, const double* 
   return B200FEM_OK;
 }
 
+// Lagrange Kronecker (sum-factorised lattice stencil) kernel, lagrange_kronecker.cuh
+static int launch_lagrange_kronecker(b200fem_operator* op, const double* u, double* w, const double* bvec) {
+  b200fem_space* s = op->sp; const BoxDev& b = s->box; const int k = s->order, W = 2 * k + 1;
+  if (!op->d_lag_rows) {
+    LagRowsHost rh = build_lagrange_rows(s->tab, op->model, b.dim, k, b.n, b.origin, b.gn, b.h);
+    size_t total = 0; for (int d = 0; d < 3; ++d) total += 2 * rh.M[d].size();
+    std::vector<double> flat; flat.reserve(total); size_t offM[3], offT[3];
+    for (int d = 0; d < 3; ++d) { offM[d] = flat.size(); flat.insert(flat.end(), rh.M[d].begin(), rh.M[d].end()); offT[d] = flat.size(); flat.insert(flat.end(), rh.T[d].begin(), rh.T[d].end()); }
+    CUDA_OK(cudaMalloc(&op->d_lag_rows, sizeof(double) * flat.size()));
+    CUDA_OK(cudaMemcpy(op->d_lag_rows, flat.data(), sizeof(double) * flat.size(), cudaMemcpyHostToDevice));
+    for (int d = 0; d < 3; ++d) { op->lag_rows.M[d] = op->d_lag_rows + offM[d]; op->lag_rows.T[d] = op->d_lag_rows + offT[d]; }
+  }
+  (void)W;
+  const LagrangeLayoutDev& L = s->lay; const bool mapped = L.lattice_map != nullptr;
+  const int TX = 32 - 2 * k, TY = 16 - 2 * k;
+  const int tx = (int)((L.lattice[0] + TX - 1) / TX), ty = (int)((L.lattice[1] + TY - 1) / TY);
+  // z-segments: enough CTAs for 4 resident CTAs per SM, but segments of at least 16 planes (each segment re-reads 2k planes)
+  static int sms = 0;
+  if (!sms) CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->mesh->ctx->device));
+  const int L2 = (int)L.lattice[2];
+  int nseg = std::max(1, std::min((4 * sms + tx * ty - 1) / (tx * ty), (L2 + 15) / 16));
+  const int zseg = (L2 + nseg - 1) / nseg; nseg = (L2 + zseg - 1) / zseg;
+  const unsigned grid = (unsigned)(tx * ty * nseg); cudaStream_t st = s->mesh->ctx->stream;
+  if (k == 1) { if (mapped) lagrange_kronecker_kernel<1, true><<<grid, 512, 0, st>>>(L, op->lag_rows, u, w, bvec, tx, ty, zseg); else lagrange_kronecker_kernel<1, false><<<grid, 512, 0, st>>>(L, op->lag_rows, u, w, bvec, tx, ty, zseg); }
+  else        { if (mapped) lagrange_kronecker_kernel<2, true><<<grid, 512, 0, st>>>(L, op->lag_rows, u, w, bvec, tx, ty, zseg); else lagrange_kronecker_kernel<2, false><<<grid, 512, 0, st>>>(L, op->lag_rows, u, w, bvec, tx, ty, zseg); }
+  CUDA_OK(cudaGetLastError());
+  op->timing.launches_per_apply = 1;
+  return B200FEM_OK;
+}
+
 static int ensure_bvec(b200fem_operator* op);
 
 // one operator application on device vectors, without halo exchange
@@ -515,6 +537,19 @@ static int apply_local(b200fem_operator* op, const double* u, double* w, bool li
   REQUIRE(default_quadrature(op), B200FEM_ERR_NOT_IMPLEMENTED, "only quadrature orders that select the (order+1)-point Gauss rule are implemented on the device");
   if (s->kind == B200FEM_LAGRANGE) {
     REQUIRE(!op->model.has_skeleton, B200FEM_ERR_NOT_IMPLEMENTED, "skeleton integrands on continuous spaces");
+    // linear models: Kronecker form (one launch, every node written once); otherwise the generic quadrature kernel with
+    // colour-ordered scatter
+    const bool lag_kron_ok = op->model.gamma == 0.0;
+    int lk = op->kernel_pref;
+    if (lk == B200FEM_KERNEL_AUTO) lk = lag_kron_ok ? B200FEM_KERNEL_KRONECKER : B200FEM_KERNEL_QUADRATURE;
+    if (lk == B200FEM_KERNEL_KRONECKER) {
+      REQUIRE(lag_kron_ok, B200FEM_ERR_INVALID, "Kronecker kernel needs a linear model");
+      const double* bvec = nullptr;
+      if (!linear && op->model.data) { int rc = ensure_bvec(op); if (rc) return rc; bvec = op->d_bvec; }
+      int rc = launch_lagrange_kronecker(op, u, w, bvec); if (rc) return rc;
+      op->timing.kernel = B200FEM_KERNEL_KRONECKER;
+      return B200FEM_OK;
+    }
     int rc = N == 2 ? launch_lagrange<2>(op, u, w, !linear) : launch_lagrange<3>(op, u, w, !linear);
     if (rc) return rc;
     op->timing.kernel = B200FEM_KERNEL_QUADRATURE;
@@ -528,8 +563,8 @@ static int apply_local(b200fem_operator* op, const double* u, double* w, bool li
     const double* bvec = nullptr;
     if (!linear && op->model.data) { int rc = ensure_bvec(op); if (rc) return rc; bvec = op->d_bvec; }
     // v2 (bulk-copy staged) needs 8-byte aligned vectors whose w / b share the 16-byte phase; otherwise v1
-    const char* variant_env = std::getenv("B200FEM_KRON_VARIANT");      // v1 | tma | pipe | split | tensor (default) | tensor3, for A/B measurements
-    const std::string variant = variant_env ? variant_env : "tensor";
+    const char* variant_env = std::getenv("B200FEM_KRON_VARIANT");      // v1 | tma | pipe | split | tensor | tensor3 | march (default), for A/B measurements
+    const std::string variant = variant_env ? variant_env : "march";
     const bool phase_ok = !bvec || ((reinterpret_cast<uintptr_t>(bvec) ^ reinterpret_cast<uintptr_t>(w)) & 8) == 0;
     const bool hier = s->kind == B200FEM_DG_LEGENDRE_HIER;
     int rc;
@@ -727,7 +762,7 @@ static void free_map_cache(b200fem_operator* op) { delete op->map_cache; op->map
 extern "C" int b200fem_operator_destroy(b200fem_operator* op) {
   if (!op) return B200FEM_OK;
   for (void* p : {(void*)op->d_perm, (void*)op->d_bvec, (void*)op->d_dmask, (void*)op->d_dvals, (void*)op->d_aux, (void*)op->d_u, (void*)op->d_w, (void*)op->d_h, (void*)op->d_r,
-                  (void*)op->d_p, (void*)op->d_x, (void*)op->d_b, (void*)op->d_partial, (void*)op->d_sums, (void*)op->d_hist, (void*)op->d_cg}) if (p) cudaFree(p);
+                  (void*)op->d_p, (void*)op->d_x, (void*)op->d_b, (void*)op->d_partial, (void*)op->d_sums, (void*)op->d_hist, (void*)op->d_cg, (void*)op->d_lag_rows}) if (p) cudaFree(p);
   halo_plan_p2p_free(op->halo_p2p); halo_plan_free(op->halo); halo_plan_dg_free(op->halo_dg); free_map_cache(op);
   if (op->comm_stream) cudaStreamDestroy(op->comm_stream);
   for (cudaEvent_t e : {op->ev_bnd, op->ev_comm}) if (e) cudaEventDestroy(e);

@@ -74,10 +74,56 @@ struct MarchCursor {
   __device__ __forceinline__ bool edge() const { return z == za - 1 || z == zb; }
 };
 
-template <int N, bool HIER, int TX, int TY, bool HAS_B, int EXP = 0>
+// acc += M v along axis AX where M has the checkerboard pattern M[i][j] = 0 for i + j odd (pure-diffusion SIPG axes of
+// the Legendre basis: even and odd polynomials decouple) -- the zero products are not issued
+template <int N, int AX, bool CHK>
+__device__ __forceinline__ void apply_axis_chk(const double* __restrict__ M, const double (&v)[N * N * N], double (&acc)[N * N * N]) {
+  constexpr int st = AX == 0 ? N * N : AX == 1 ? N : 1;
+#pragma unroll
+  for (int t = 0; t < N * N * N; ++t) {
+    const int i = (t / st) % N, base = t - i * st;
+    double s = acc[t];
+#pragma unroll
+    for (int j = 0; j < N; ++j) if (!CHK || ((i + j) & 1) == 0) s = fma(M[i * N + j], v[base + j * st], s);
+    acc[t] = s;
+  }
+}
+
+// One line (N values along axis AX, line index l in [0, N*N)) of acc += M v: the unit of the interleaved schedule below.
+template <int N, int AX> __device__ __forceinline__ constexpr int line_base(int l) { return AX == 0 ? l : AX == 1 ? (l / N) * N * N + (l % N) : l * N; }
+template <int N, int AX, bool CHK>
+__device__ __forceinline__ void unit_reg(const double* __restrict__ M, const double (&v)[N * N * N], double (&acc)[N * N * N], const int l) {
+  constexpr int st = AX == 0 ? N * N : AX == 1 ? N : 1;
+  const int base = line_base<N, AX>(l);
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double a = acc[base + i * st];
+#pragma unroll
+    for (int j = 0; j < N; ++j) if (!CHK || ((i + j) & 1) == 0) a = fma(M[i * N + j], v[base + j * st], a);
+    acc[base + i * st] = a;
+  }
+}
+template <int N, int AX, bool HIER>
+__device__ __forceinline__ void unit_smem(const double* __restrict__ M, const double* __restrict__ src, double (&acc)[N * N * N], const int l) {
+  constexpr PermTable<N, HIER> P{};
+  constexpr int st = AX == 0 ? N * N : AX == 1 ? N : 1;
+  const int base = line_base<N, AX>(l);
+  double line[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) line[j] = src[P.p[base + j * st]];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double a = acc[base + i * st];
+#pragma unroll
+    for (int j = 0; j < N; ++j) a = fma(M[i * N + j], line[j], a);
+    acc[base + i * st] = a;
+  }
+}
+
+template <int N, bool HIER, int TX, int TY, bool HAS_B, bool CHK>
 __global__ void __launch_bounds__(KronMarchCfg<N, TX, TY>::kThreads, 1)
 dg_kronecker_march_kernel(const __grid_constant__ KronTabDev<N> K, const __grid_constant__ BoxDev box,
-                          const __grid_constant__ KronMarchMaps M, const int tiles_x, const int ncols, const int skew, long long* __restrict__ dbg) {
+                          const __grid_constant__ KronMarchMaps M, const int tiles_x, const int ncols) {
   using Cfg = KronMarchCfg<N, TX, TY>;
   constexpr int N3 = Cfg::N3, RS = Cfg::RS, RO = Cfg::RO, NN = N * N;
   constexpr int kWarps = Cfg::kConsumers / 32, kRowsPerWarp = 32 / TX, kSlab = kRowsPerWarp * RO;   // doubles per warp slab
@@ -90,9 +136,6 @@ dg_kronecker_march_kernel(const __grid_constant__ KronTabDev<N> K, const __grid_
   uint64_t* bars = reinterpret_cast<uint64_t*>(Dsm + 6 * NN + (6 * NN) % 2);
   const uint32_t ufull = ptx::smem_addr(bars), ufree = ptx::smem_addr(bars + 2), wbar0 = ptx::smem_addr(bars + 4);
   const int tid = threadIdx.x;
-  if (dbg && tid == 0 && (blockIdx.x == 0 || blockIdx.x == 77)) dbg[((blockIdx.x ? 16 : 0) + 14) * 8] = clock64();
-  auto gtime = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (long long)t; };
-  if (dbg && tid == 0) { dbg[256 + 4 * blockIdx.x] = gtime(); dbg[256 + 4 * blockIdx.x + 3] = *(volatile long long*)&dbg[250]; }
 
   const int nz = box.own_hi[2] - box.own_lo[2];
   const long long total = (long long)ncols * nz;
@@ -145,40 +188,27 @@ dg_kronecker_march_kernel(const __grid_constant__ KronTabDev<N> K, const __grid_
   const int tx = tid % TX, ty = tid / TX, warp = tid / 32, lane = tid % 32;
   double* const slab = O + (size_t)warp * kSlab;                     // this warp's rows of the output tile
   double* const o = slab + (ty % kRowsPerWarp) * RO + tx * N3;
-  const uint32_t wbar = wbar0 + 8 * warp;
+  const uint32_t wbar = wbar0 + 8 * warp, slab_a = ptx::smem_addr(slab);
   const int wrow = warp * kRowsPerWarp;                              // first tile row of this warp
   const int on1 = box.own_hi[1] - box.own_lo[1];
+  const int gz0 = box.origin[2] + box.own_lo[2];
   double A[N3], B[N3];                                               // A: plane z-1 (waits for R_z u(z)),  B: plane z
-  int ku = 0, eb = 0, kstep = 0;
+  int ku = 0, eb = 0;
   MarchCursor cur; cur.init(t0, t1, nz);
-  int gcx = 0, gcy = 0;
-  bool rows_owned = false;
+  int gcx = 0, gcy = 0, cx = 0, cy = 0;                              // global element coordinates; TMA coordinates of the warp's rows
+  bool rows_owned = false, xb = false, yb = false;
+  if (lane == 0) { ptx::prefetch_tensormap(&M.w_tile); if (HAS_B) ptx::prefetch_tensormap(&M.b_tile); }
 
-  // the warp's own output path: lane 0 loads its rows of the load vector b into the slab and stores the finished rows
-  auto next_epilogue = [&](MarchCursor c) { while (c.valid && !c.has_prev()) c.advance(); return c; };
-  auto issue_b = [&](const MarchCursor& c) {                         // lane 0 only
-    const int y = (c.col / tiles_x) * TY + wrow;
-    if (y < on1) { ptx::mbar_expect_tx(wbar, 8u * kSlab); ptx::tma_load_4d(ptx::smem_addr(slab), &M.b_tile, 0, (c.col % tiles_x) * (TX / 2), y, c.z - 1, wbar); }
-    else ptx::mbar_arrive(wbar);
-  };
-  if (lane == 0) ptx::prefetch_tensormap(&M.w_tile);
-  if (HAS_B && lane == 0) { ptx::prefetch_tensormap(&M.b_tile); const MarchCursor c = next_epilogue(cur); if (c.valid) issue_b(c); }
-
-  // The two warps that share a scheduler (w and w+4) would otherwise run in lock-step: both in their FMA phases (pipe
-  // shared), then both in their latency-bound phases (pipe idle).  A one-time skew of the second group interleaves them.
-  if (warp >= kWarps / 2 && skew > 0) { const long long t_ = clock64(); while (clock64() - t_ < skew) { } }
   for (; cur.valid; cur.advance()) {
     if (cur.z == cur.za - 1) {                                       // a new run starts
-      gcx = box.origin[0] + box.own_lo[0] + (cur.col % tiles_x) * TX + tx;
-      gcy = box.origin[1] + box.own_lo[1] + (cur.col / tiles_x) * TY + ty;
-      rows_owned = (cur.col / tiles_x) * TY + wrow < on1;
+      const int bx = cur.col % tiles_x, by = cur.col / tiles_x;
+      gcx = box.origin[0] + box.own_lo[0] + bx * TX + tx; gcy = box.origin[1] + box.own_lo[1] + by * TY + ty;
+      xb = gcx == 0 || gcx == box.gn[0] - 1; yb = gcy == 0 || gcy == box.gn[1] - 1;
+      cx = bx * (TX / 2); cy = by * TY + wrow; rows_owned = cy < on1;
 #pragma unroll
       for (int t = 0; t < N3; ++t) { A[t] = 0.0; B[t] = 0.0; }
     }
-    const bool exists = plane_exists(cur), edge = cur.edge();
-    const bool rec = dbg && tid == 0 && (blockIdx.x == 0 || blockIdx.x == 77) && kstep < 14;
-    long long* const drow = dbg + ((blockIdx.x ? 16 : 0) + kstep) * 8;
-    if (rec) { drow[0] = clock64(); drow[5] = cur.z; drow[6] = cur.col; }
+    const bool exists = plane_exists(cur), edge = cur.edge(), hp = cur.has_prev();
     const double* st = sbase + (size_t)(ku & 1) * Cfg::kU;
     const double* own = edge ? st + ty * RO + tx * N3 : st + (ty + 1) * RS + (tx + 2) * N3;
     double v[N3];
@@ -190,54 +220,53 @@ dg_kronecker_march_kernel(const __grid_constant__ KronTabDev<N> K, const __grid_
 #pragma unroll
       for (int t = 0; t < N3; ++t) v[t] = 0.0;
     }
-    if (rec) drow[1] = clock64();
-    // The order below is a hand-made software pipeline: register-only work (R, S) comes first so that the b rows have time
-    // to land; the latency-bound slab update shares a basic block with the x-neighbour FMAs; the next b load is issued
-    // between the two y-neighbours, when the store has long read the slab.
-    const bool hp = cur.has_prev();
-    if (hp && exists) apply_axis<N, 2>(K.R[2], v, A);                // plane z-1 is complete after R_z u(z)
-    if (!edge) { apply_axis<N, 0>(K.S[0], v, B); apply_axis<N, 1>(K.S[1], v, B); apply_axis<N, 2>(K.S[2], v, B); }
+    // The step is a hand-interleaved stream: every register-only line unit (R, S: FP64 pipe only) is paired with a
+    // neighbour line unit (3 shared loads + 9 FMA), so that shared-memory traffic is spread evenly over the FMA work
+    // instead of being bunched in "neighbour phases" where the load pipe, not the FP64 pipe, would set the pace.
+    if (hp && !edge) {
+#pragma unroll
+      for (int l = 0; l < NN; ++l) { if (exists) unit_reg<N, 2, false>(K.R[2], v, A, l); unit_smem<N, 0, HIER>(K.L[0], own - N3, B, l); }
+    } else {
+      if (hp && exists) apply_axis<N, 2>(K.R[2], v, A);              // plane z-1 is complete after R_z u(z)
+      if (!edge) apply_axis_smem<N, 0, HIER>(K.L[0], own - N3, B);
+    }
     if (hp) {
       if (HAS_B) { ptx::mbar_wait(wbar, eb & 1); ++eb; }              // b rows have landed (and the previous store has read the slab)
       else { if (lane == 0) ptx::bulk_wait_read(); __syncwarp(); }   // the previous store has read the slab
-    }
-    if (rec) drow[2] = clock64();
-    auto slab_update = [&]() {
 #pragma unroll
       for (int t = 0; t < N3; ++t) o[P.p[t]] = HAS_B ? A[t] - o[P.p[t]] : A[t];
-    };
-    auto x_neighbours = [&]() {
-      if (EXP == 3) return;
-      if (EXP == 1) { apply_axis<N, 0>(K.L[0], v, B); apply_axis<N, 0>(K.R[0], v, B); return; }
-      apply_axis_smem<N, 0, HIER>(K.L[0], own - N3, B); apply_axis_smem<N, 0, HIER>(K.R[0], own + N3, B); };
-    if (hp && !edge) { if (EXP != 2) slab_update(); x_neighbours(); }
-    else { if (hp && EXP != 2) slab_update(); if (!edge) x_neighbours(); }
-    if (hp && EXP != 2) {
       ptx::fence_proxy_async();
       __syncwarp();
-      if (lane == 0 && rows_owned) {
-        ptx::tma_store_4d(&M.w_tile, 0, (cur.col % tiles_x) * (TX / 2), (cur.col / tiles_x) * TY + wrow, cur.z - 1, ptx::smem_addr(slab));
-        ptx::bulk_commit();
-      }
-    }
-    if (rec) drow[3] = clock64();
-    if (!edge) { if (EXP == 1) apply_axis<N, 1>(K.L[1], v, B); else if (EXP != 3) apply_axis_smem<N, 1, HIER>(K.L[1], own - RS, B); }
-    if (HAS_B && lane == 0 && hp) {                                  // the slab takes the b rows of the next output plane
-      MarchCursor c = cur; c.advance(); c = next_epilogue(c);
-      if (c.valid) { ptx::bulk_wait_read(); issue_b(c); }
+      if (lane == 0 && rows_owned) { ptx::tma_store_4d(&M.w_tile, 0, cx, cy, cur.z - 1, slab_a); ptx::bulk_commit(); }
     }
     if (!edge) {
-      if (EXP == 1) apply_axis<N, 1>(K.R[1], v, B); else if (EXP != 3) apply_axis_smem<N, 1, HIER>(K.R[1], own + RS, B);
+#pragma unroll
+      for (int l = 0; l < NN; ++l) { unit_reg<N, 0, false>(K.S[0], v, B, l); unit_smem<N, 0, HIER>(K.R[0], own + N3, B, l); }
+#pragma unroll
+      for (int l = 0; l < NN; ++l) { unit_reg<N, 1, CHK>(K.S[1], v, B, l); unit_smem<N, 1, HIER>(K.L[1], own - RS, B, l); }
+    }
+    if (HAS_B && lane == 0 && cur.z >= cur.za && cur.z < cur.zb) {    // plane z completes in the next step: the slab takes its b rows
+      ptx::bulk_wait_read();                                         // (the store issued above has read the slab by now)
+      if (rows_owned) { ptx::mbar_expect_tx(wbar, 8u * kSlab); ptx::tma_load_4d(slab_a, &M.b_tile, 0, cx, cy, cur.z, wbar); }
+      else ptx::mbar_arrive(wbar);
+    }
+    if (!edge) {
+#pragma unroll
+      for (int l = 0; l < NN; ++l) { unit_reg<N, 2, CHK>(K.S[2], v, B, l); unit_smem<N, 1, HIER>(K.R[1], own + RS, B, l); }
       // domain-boundary corrections of the self matrices (tables in shared memory: the choice is per thread)
-      const int gc[3] = {gcx, gcy, box.origin[2] + box.own_lo[2] + cur.z};
+      const int gcz = gz0 + cur.z;
+      const bool zb = gcz == 0 || gcz == box.gn[2] - 1;
+      if (xb | yb | zb) {
+        const int gc[3] = {gcx, gcy, gcz};
 #pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        const bool lo = gc[a] == 0, hi = gc[a] == box.gn[a] - 1;
-        if (lo || hi) {
-          double m[NN];
+        for (int a = 0; a < 3; ++a) {
+          const bool lo = gc[a] == 0, hi = gc[a] == box.gn[a] - 1;
+          if (lo || hi) {
+            double m[NN];
 #pragma unroll
-          for (int i = 0; i < NN; ++i) m[i] = (lo ? Dsm[a * 2 * NN + i] : 0.0) + (hi ? Dsm[a * 2 * NN + NN + i] : 0.0);
-          if (a == 0) apply_axis<N, 0>(m, v, B); else if (a == 1) apply_axis<N, 1>(m, v, B); else apply_axis<N, 2>(m, v, B);
+            for (int i = 0; i < NN; ++i) m[i] = (lo ? Dsm[a * 2 * NN + i] : 0.0) + (hi ? Dsm[a * 2 * NN + NN + i] : 0.0);
+            if (a == 0) apply_axis<N, 0>(m, v, B); else if (a == 1) apply_axis<N, 1>(m, v, B); else apply_axis<N, 2>(m, v, B);
+          }
         }
       }
     }
@@ -246,12 +275,8 @@ dg_kronecker_march_kernel(const __grid_constant__ KronTabDev<N> K, const __grid_
 #pragma unroll
     for (int t = 0; t < N3; ++t) { A[t] = B[t]; B[t] = 0.0; }
     if (exists && cur.z + 1 < cur.zb) apply_axis<N, 2>(K.L[2], v, B);
-    if (rec) drow[4] = clock64();
-    ++kstep;
   }
   if (lane == 0) ptx::bulk_wait_all();
-  if (dbg && tid == 0 && (blockIdx.x == 0 || blockIdx.x == 77)) dbg[((blockIdx.x ? 16 : 0) + 15) * 8] = clock64();
-  if (dbg && lane == 0) { atomicMax((unsigned long long*)&dbg[256 + 4 * blockIdx.x + 1], (unsigned long long)gtime()); atomicMax((unsigned long long*)&dbg[250], (unsigned long long)gtime()); if (warp == 0) dbg[256 + 4 * blockIdx.x + 2] = kstep; }
 }
 
 }  // namespace b200fem

@@ -58,4 +58,41 @@ inline KronHost build_kron_tables(const Tab1D& t, const b200fem_model& m, int di
   return k;
 }
 
+
+// 1-D assembled row tables of the Lagrange Kronecker form (lagrange_kronecker.cuh): for axis d, rows[g*(2k+1) + j] is
+// the entry (g, g-k+j) of  M_d = assembled mass  and  T_d = eps K_d - b_d C_d (+ c M_0 on axis 0) (+ the u-dependent
+// boundary term (eps beta / h_d + hat b) on the end nodes of masked DOMAIN boundaries).  Element matrices are the
+// 1-D quadrature sums of the reference loop (galerkin.hh:332-360) with the tabulation `t` of the space:
+//   Me[i][j] = h sum_q w_q B_qi B_qj,   Ke[i][j] = 1/h sum_q w_q G_qi G_qj,   Ce[i][j] = sum_q w_q G_qi B_qj
+// (i test, j trial; F = eps grad u - b u is tested with grad phi_i).  Axes >= dim get M = [1], T = [0].
+struct LagRowsHost { std::vector<double> M[3], T[3]; int k = 0; long long L[3] = {1, 1, 1}; };
+
+inline LagRowsHost build_lagrange_rows(const Tab1D& t, const b200fem_model& m, int dim, int order, const int* n, const int* origin, const int* gn, const double* h) {
+  LagRowsHost r; const int k = order, W = 2 * k + 1, nb = k + 1; r.k = k;
+  for (int d = 0; d < 3; ++d) {
+    const long long Ld = d < dim ? (long long)k * n[d] + 1 : 1; r.L[d] = Ld;
+    r.M[d].assign((size_t)Ld * W, 0.0); r.T[d].assign((size_t)Ld * W, 0.0);
+    if (d >= dim) { r.M[d][k] = 1.0; continue; }
+    std::vector<double> Me(nb * nb, 0.0), Te(nb * nb, 0.0);
+    for (int q = 0; q < t.m; ++q) for (int i = 0; i < nb; ++i) for (int j = 0; j < nb; ++j) {
+      const double mm = h[d] * t.w[q] * t.B[q * nb + i] * t.B[q * nb + j];
+      Me[i * nb + j] += mm;
+      Te[i * nb + j] += m.eps / h[d] * t.w[q] * t.G[q * nb + i] * t.G[q * nb + j] - m.b[d] * t.w[q] * t.G[q * nb + i] * t.B[q * nb + j];
+      if (d == 0) Te[i * nb + j] += m.c * mm;
+    }
+    for (int e = 0; e < n[d]; ++e) for (int i = 0; i < nb; ++i) for (int j = 0; j < nb; ++j) {
+      const long long g = (long long)k * e + i; const int col = j - i + k;          // column g - k + col = k e + j
+      r.M[d][(size_t)g * W + col] += Me[i * nb + j]; r.T[d][(size_t)g * W + col] += Te[i * nb + j];
+    }
+    if (m.has_boundary) for (int side = 0; side < 2; ++side) {
+      const bool domain_bnd = side == 0 ? origin[d] == 0 : origin[d] + n[d] == gn[d];
+      if (!domain_bnd || !((m.dirichlet_mask >> (2 * d + side)) & 1)) continue;
+      const double bn = m.b[d] * (side ? 1.0 : -1.0), hatb = 0.5 * (bn + std::fabs(bn));
+      const long long g = side ? Ld - 1 : 0;
+      r.T[d][(size_t)g * W + k] += m.eps * m.beta / h[d] + hatb;
+    }
+  }
+  return r;
+}
+
 }  // namespace b200fem
