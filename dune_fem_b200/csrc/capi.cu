@@ -61,7 +61,7 @@ struct b200fem_operator {
   double *d_u = nullptr, *d_w = nullptr;                       // staging for the host-pointer API
   double *d_h = nullptr, *d_r = nullptr, *d_p = nullptr, *d_x = nullptr, *d_b = nullptr, *d_partial = nullptr, *d_sums = nullptr, *d_hist = nullptr;
   CgState* d_cg = nullptr; int hist_cap = 0;
-  bool kron_ready = false; int kron_chk = -1; double* d_lag_rows = nullptr; LagKronRows lag_rows{}; std::vector<unsigned char> kron_tab; struct KronMapCache* map_cache = nullptr; struct MarchMapCache* march_cache = nullptr;
+  bool kron_ready = false; int kron_chk = -1; bool fuse_dirichlet = false, fuse_linear = false, dirichlet_fused = false; double* d_lag_rows = nullptr; LagKronRows lag_rows{}; std::vector<unsigned char> kron_tab; struct KronMapCache* map_cache = nullptr; struct MarchMapCache* march_cache = nullptr;
   HaloPlan halo; HaloPlanDG halo_dg; HaloPlanP2P halo_p2p; const BoxDev* active_box = nullptr; int reserve_sms = 0; unsigned long long fused_seq = 0; bool last_launch_tensor = false;      // active_box: sub-box override for split launches
   cudaStream_t comm_stream = nullptr; cudaEvent_t ev_bnd = nullptr, ev_comm = nullptr, dbg_ev[2] = {nullptr, nullptr};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evx0 = nullptr, evx1 = nullptr; b200fem_timing timing{};
@@ -514,15 +514,25 @@ static int launch_lagrange_kronecker(b200fem_operator* op, const double* u, doub
   const LagrangeLayoutDev& L = s->lay; const bool mapped = L.lattice_map != nullptr;
   const int TX = 32 - 2 * k, TY = 16 - 2 * k;
   const int tx = (int)((L.lattice[0] + TX - 1) / TX), ty = (int)((L.lattice[1] + TY - 1) / TY);
-  // z-segments: enough CTAs for 4 resident CTAs per SM, but segments of at least 16 planes (each segment re-reads 2k planes)
+  // z-segments: every segment re-reads 2k planes and stages its z-rows (<= kMaxSeg planes); the number of segments is chosen
+  // so that the grid fills whole waves of the resident CTA slots (2 CTAs per SM)
   static int sms = 0;
   if (!sms) CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->mesh->ctx->device));
-  const int L2 = (int)L.lattice[2];
-  int nseg = std::max(1, std::min((4 * sms + tx * ty - 1) / (tx * ty), (L2 + 15) / 16));
-  const int zseg = (L2 + nseg - 1) / nseg; nseg = (L2 + zseg - 1) / zseg;
-  const unsigned grid = (unsigned)(tx * ty * nseg); cudaStream_t st = s->mesh->ctx->stream;
-  if (k == 1) { if (mapped) lagrange_kronecker_kernel<1, true><<<grid, 512, 0, st>>>(L, op->lag_rows, u, w, bvec, tx, ty, zseg); else lagrange_kronecker_kernel<1, false><<<grid, 512, 0, st>>>(L, op->lag_rows, u, w, bvec, tx, ty, zseg); }
-  else        { if (mapped) lagrange_kronecker_kernel<2, true><<<grid, 512, 0, st>>>(L, op->lag_rows, u, w, bvec, tx, ty, zseg); else lagrange_kronecker_kernel<2, false><<<grid, 512, 0, st>>>(L, op->lag_rows, u, w, bvec, tx, ty, zseg); }
+  const int L2 = (int)L.lattice[2], slots = 2 * sms, tiles = tx * ty;
+  int best_nseg = 1; double best_cost = 1e300;
+  for (int ns = 1; ns <= 64; ++ns) {
+    const int zs = (L2 + ns - 1) / ns; if (zs > 128) continue;
+    const int nse = (L2 + zs - 1) / zs;
+    const double waves = std::ceil((double)tiles * nse / slots), cost = waves * (zs + 2 * k + 6);
+    if (cost < best_cost) { best_cost = cost; best_nseg = nse; }
+    if (zs <= 4) break;
+  }
+  const int zseg = (L2 + best_nseg - 1) / best_nseg, nseg = (L2 + zseg - 1) / zseg;
+  const unsigned grid = (unsigned)(tiles * nseg); cudaStream_t st = s->mesh->ctx->stream;
+  const unsigned char* dmask = op->fuse_dirichlet ? op->d_dmask : nullptr; const double* dvals = op->fuse_dirichlet && !op->fuse_linear ? op->d_dvals : nullptr;
+  if (k == 1) { if (mapped) lagrange_kronecker_kernel<1, true><<<grid, 512, 0, st>>>(L, op->lag_rows, u, w, bvec, dmask, dvals, tx, ty, zseg); else lagrange_kronecker_kernel<1, false><<<grid, 512, 0, st>>>(L, op->lag_rows, u, w, bvec, dmask, dvals, tx, ty, zseg); }
+  else        { if (mapped) lagrange_kronecker_kernel<2, true><<<grid, 512, 0, st>>>(L, op->lag_rows, u, w, bvec, dmask, dvals, tx, ty, zseg); else lagrange_kronecker_kernel<2, false><<<grid, 512, 0, st>>>(L, op->lag_rows, u, w, bvec, dmask, dvals, tx, ty, zseg); }
+  op->dirichlet_fused = op->fuse_dirichlet;
   CUDA_OK(cudaGetLastError());
   op->timing.launches_per_apply = 1;
   return B200FEM_OK;
@@ -666,7 +676,12 @@ static int apply_dev_impl(b200fem_operator* op, const double* u, double* w, bool
                            s->box.own_lo[0] == 0 && s->box.own_hi[0] == s->box.n[0];
     op->last_launch_tensor = false;
     if (try_fused) op->fused_seq = op->halo_p2p.seq + 1;
+    // single rank: the Dirichlet wrapper can ride along in the store of the Lagrange Kronecker kernel (with several ranks it
+    // has to follow the Add exchange)
+    op->dirichlet_fused = false;
+    op->fuse_dirichlet = !distributed && op->model.strong_dirichlet && op->d_dmask != nullptr; op->fuse_linear = linear;
     rc = apply_local(op, u, w, linear);
+    op->fuse_dirichlet = false;
     const bool fused = try_fused && op->last_launch_tensor;
     op->fused_seq = 0;
     if (rc) return rc;
@@ -678,7 +693,7 @@ static int apply_dev_impl(b200fem_operator* op, const double* u, double* w, bool
     }
   }
   // DirichletWrapperOperator: op_(u,w) (communication included) first, then subConstraints (dirichletwrapper.hh:101-105)
-  if (op->model.strong_dirichlet && op->d_dmask) {
+  if (op->model.strong_dirichlet && op->d_dmask && !op->dirichlet_fused) {
     dirichlet_sub_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(u, w, op->d_dmask, linear ? nullptr : op->d_dvals, s->size);
     CUDA_OK(cudaGetLastError()); op->timing.launches_per_apply += 1;
   }

@@ -34,89 +34,120 @@ struct LagKronRows {
 
 template <int K> struct LagKronCfg {
   static constexpr int W = 2 * K + 1, HX = 32, HY = 16, TX = HX - 2 * K, TY = HY - 2 * K, kThreads = HX * HY;
+  static constexpr int kMaxSeg = 128;                        // planes per z-segment (their z-rows are staged in shared memory)
 };
 
+// dmask / dvals (optional): DirichletWrapperOperator fused into the store, w_d = u_d - g_d on constrained nodes
+// (schemes/dirichletwrapper.hh:101-105); only valid when no halo exchange follows (single rank).
+//
+// Schedule per lattice plane (ONE __syncthreads): the z-pass of plane z+1 writes the other half of the double-buffered
+// (a, b) planes while the y-pass of plane z reads this half; the x-pass exchanges (c, s) between the lanes of a warp with
+// shuffles (a warp is one lattice row), so it needs neither shared memory nor a barrier.
 template <int K, bool MAPPED>
-__global__ void __launch_bounds__(LagKronCfg<K>::kThreads)
+__global__ void __launch_bounds__(LagKronCfg<K>::kThreads, 2)
 lagrange_kronecker_kernel(const __grid_constant__ LagrangeLayoutDev L, const __grid_constant__ LagKronRows R,
                           const double* __restrict__ u, double* __restrict__ w, const double* __restrict__ bvec,
+                          const unsigned char* __restrict__ dmask, const double* __restrict__ dvals,
                           const int tiles_x, const int tiles_y, const int zseg) {
   using Cfg = LagKronCfg<K>;
   constexpr int W = Cfg::W, HX = Cfg::HX, HY = Cfg::HY, TX = Cfg::TX, TY = Cfg::TY;
-  __shared__ double Sa[2][HY][HX], Sb[2][HY][HX], Sc[2][HY][HX], Ss[2][HY][HX];
+  __shared__ double Sa[2][HY][HX], Sb[2][HY][HX];
+  __shared__ double Zr[Cfg::kMaxSeg][2 * W];                  // z-rows of this segment: M then T (uniform per plane)
+  __shared__ double Yr[HY][2 * W];                            // y-rows of this tile (uniform per warp)
+  __shared__ double Xr[HX][2 * W + 1];                        // x-rows of this tile (per lane; odd stride: conflict-free)
 
   const int tid = threadIdx.x, hx = tid % HX, hy = tid / HX;
   const int tile = blockIdx.x % (tiles_x * tiles_y), seg = blockIdx.x / (tiles_x * tiles_y);
   const int L0 = (int)L.lattice[0], L1 = (int)L.lattice[1], L2 = (int)L.lattice[2];
-  const int gx = (tile % tiles_x) * TX - K + hx, gy = (tile / tiles_x) * TY - K + hy;
+  const int gx = (tile % tiles_x) * TX - K + hx, gy0 = (tile / tiles_x) * TY - K, gy = gy0 + hy;
   const bool in_xy = gx >= 0 && gx < L0 && gy >= 0 && gy < L1;
   const int z0 = seg * zseg, z1 = min(L2, z0 + zseg);
 
-  // dof address of lattice node (gx, gy, gz) = base[p] + stride[p] * (gz >> zshift), p = parity class of gz
-  long long base[2] = {0, 0}, stride[2] = {0, 0}; int zshift = 0;
+  for (int i = tid; i < (z1 - z0) * W; i += Cfg::kThreads) {
+    const int p = i / W, j = i % W;
+    Zr[p][j] = R.M[2][(size_t)(z0 + p) * W + j]; Zr[p][W + j] = R.T[2][(size_t)(z0 + p) * W + j];
+  }
+  if (tid < HY * W) {
+    const int r = tid / W, j = tid % W, g = gy0 + r; const bool ok = g >= 0 && g < L1;
+    Yr[r][j] = ok ? R.M[1][(size_t)g * W + j] : 0.0; Yr[r][W + j] = ok ? R.T[1][(size_t)g * W + j] : 0.0;
+  } else if (tid >= 256 && tid < 256 + HX * W) {
+    const int r = (tid - 256) / W, j = (tid - 256) % W, g = gx - hx + r; const bool ok = g >= 0 && g < L0;
+    Xr[r][j] = ok ? R.M[0][(size_t)g * W + j] : 0.0; Xr[r][W + j] = ok ? R.T[0][(size_t)g * W + j] : 0.0;
+  }
+
+  // dof address of lattice node (gx, gy, gz): base_p + stride_p * (gz >> zshift), p = parity class of gz
+  long long base0 = 0, base1 = 0, stride0 = 0, stride1 = 0; int zshift = 0;
   if (!MAPPED && in_xy) {
     if (L.order == 2) {
-      const int sxy = (gx & 1) | ((gy & 1) << 1);
-      for (int p = 0; p < 2; ++p) {
-        const int s = sxy | (p << 2);
-        base[p] = L.group_offset[s] + (gx >> 1) + L.group_dims[s][0] * (long long)(gy >> 1);
-        stride[p] = L.group_dims[s][0] * L.group_dims[s][1];
-      }
+      const int s0 = (gx & 1) | ((gy & 1) << 1), s1 = s0 | 4;
+      base0 = L.group_offset[s0] + (gx >> 1) + L.group_dims[s0][0] * (long long)(gy >> 1); stride0 = L.group_dims[s0][0] * L.group_dims[s0][1];
+      base1 = L.group_offset[s1] + (gx >> 1) + L.group_dims[s1][0] * (long long)(gy >> 1); stride1 = L.group_dims[s1][0] * L.group_dims[s1][1];
       zshift = 1;
     } else {
-      base[0] = base[1] = L.group_offset[0] + gx + L.group_dims[0][0] * (long long)gy;
-      stride[0] = stride[1] = L.group_dims[0][0] * L.group_dims[0][1];
+      base0 = base1 = L.group_offset[0] + gx + L.group_dims[0][0] * (long long)gy;
+      stride0 = stride1 = L.group_dims[0][0] * L.group_dims[0][1];
     }
   }
   auto dof = [&](int gz) -> long long {
     if (MAPPED) return L.lattice_map[gx + (long long)L0 * (gy + (long long)L1 * gz)];
-    const int p = zshift ? (gz & 1) : 0;
-    return base[p] + stride[p] * (long long)(gz >> zshift);
+    return (zshift & gz) ? base1 + stride1 * (long long)(gz >> zshift) : base0 + stride0 * (long long)(gz >> zshift);
   };
   auto load_u = [&](int gz) -> double { return (in_xy && gz >= 0 && gz < L2) ? u[dof(gz)] : 0.0; };
 
-  // y-rows are the same for the whole warp (one warp = one hy)
-  double ym[W], yt[W];
-  const bool y_owned = hy >= K && hy < HY - K && gy < L1;    // (gy >= 0 follows from hy >= K)
-#pragma unroll
-  for (int j = 0; j < W; ++j) { ym[j] = y_owned ? R.M[1][(size_t)gy * W + j] : 0.0; yt[j] = y_owned ? R.T[1][(size_t)gy * W + j] : 0.0; }
+  const bool y_owned = hy >= K && hy < HY - K && gy < L1;    // warp-uniform (gy >= 0 follows from hy >= K)
   const bool x_owned = y_owned && hx >= K && hx < HX - K && gx < L0;
-  double xm[W], xt[W];                                       // x-rows differ per lane
-#pragma unroll
-  for (int j = 0; j < W; ++j) { xm[j] = x_owned ? R.M[0][(size_t)gx * W + j] : 0.0; xt[j] = x_owned ? R.T[0][(size_t)gx * W + j] : 0.0; }
 
-  double uw[W];                                              // u(gx, gy, z-K .. z+K)
+  double uw[W];                                              // u(gx, gy, zc-K .. zc+K), zc = plane of the next z-pass
 #pragma unroll
   for (int j = 1; j < W; ++j) uw[j] = load_u(z0 - K + j - 1);
-  double pre = load_u(z0 + K);                               // one plane of prefetch distance
+  double pre0 = load_u(z0 + K), pre1 = load_u(z0 + K + 1);   // two planes of prefetch distance
+  __syncthreads();                                           // rows staged
 
-  for (int z = z0; z < z1; ++z) {
-    const int buf = (z - z0) & 1;
+  // z-pass of plane zc into buffer nb: shifts the window, keeps the prefetch two planes ahead
+  auto z_pass = [&](int zc, int nb) {
 #pragma unroll
     for (int j = 0; j < W - 1; ++j) uw[j] = uw[j + 1];
-    uw[W - 1] = pre; pre = load_u(z + K + 1);
-    double a = 0, b = 0;
+    uw[W - 1] = pre0; pre0 = pre1; pre1 = load_u(zc + K + 2);
+    const double* zr = Zr[zc - z0];
+    double a0 = 0, a1 = 0, b0 = 0, b1 = 0;
 #pragma unroll
-    for (int j = 0; j < W; ++j) { a = fma(R.M[2][(size_t)z * W + j], uw[j], a); b = fma(R.T[2][(size_t)z * W + j], uw[j], b); }
-    Sa[buf][hy][hx] = a; Sb[buf][hy][hx] = b;
-    __syncthreads();
+    for (int j = 0; j < W; ++j) {
+      if (j & 1) { a1 = fma(zr[j], uw[j], a1); b1 = fma(zr[W + j], uw[j], b1); } else { a0 = fma(zr[j], uw[j], a0); b0 = fma(zr[W + j], uw[j], b0); }
+    }
+    Sa[nb][hy][hx] = a0 + a1; Sb[nb][hy][hx] = b0 + b1;
+  };
+  z_pass(z0, 0);
+  __syncthreads();
+
+  for (int z = z0; z < z1; ++z) {
+    const int cb = (z - z0) & 1;
+    // operands of the store, requested now, used at the end of the step
+    long long g = 0; double bq = 0, dq = 0; bool constrained = false;
+    if (x_owned) {
+      g = dof(z);
+      if (bvec) bq = bvec[g];
+      if (dmask) { constrained = dmask[g] != 0; if (constrained && dvals) dq = dvals[g]; }
+    }
+    const double uc = uw[K];                                 // u(gx, gy, z): the window is centred on z here
+    if (z + 1 < z1) z_pass(z + 1, cb ^ 1);
     if (y_owned) {
-      double c = 0, s = 0;
+      const double* yr = Yr[hy];
+      double c = 0, s0 = 0, s1 = 0;
 #pragma unroll
       for (int j = 0; j < W; ++j) {
-        const double aj = Sa[buf][hy - K + j][hx], bj = Sb[buf][hy - K + j][hx];
-        c = fma(ym[j], aj, c); s = fma(yt[j], aj, s); s = fma(ym[j], bj, s);
+        const double aj = Sa[cb][hy - K + j][hx], bj = Sb[cb][hy - K + j][hx];
+        c = fma(yr[j], aj, c); s0 = fma(yr[W + j], aj, s0); s1 = fma(yr[j], bj, s1);
       }
-      Sc[buf][hy][hx] = c; Ss[buf][hy][hx] = s;
+      const double s = s0 + s1;
+      double r0 = 0, r1 = 0;
+#pragma unroll
+      for (int j = 0; j < W; ++j) {
+        const int src = (hx - K + j) & 31;
+        r0 = fma(Xr[hx][W + j], __shfl_sync(0xffffffffu, c, src), r0); r1 = fma(Xr[hx][j], __shfl_sync(0xffffffffu, s, src), r1);
+      }
+      if (x_owned) w[g] = constrained ? uc - dq : (r0 + r1) - bq;
     }
     __syncthreads();
-    if (x_owned) {
-      double r = 0;
-#pragma unroll
-      for (int j = 0; j < W; ++j) { r = fma(xt[j], Sc[buf][hy][hx - K + j], r); r = fma(xm[j], Ss[buf][hy][hx - K + j], r); }
-      const long long g = dof(z);
-      w[g] = bvec ? r - bvec[g] : r;
-    }
   }
 }
 
