@@ -17,6 +17,7 @@
 #include "dg_kronecker.cuh"
 #include "dg_kronecker_pipe.cuh"
 #include "dg_kronecker_march.cuh"
+#include "dg_kronecker_slab.cuh"
 #include "dg_kronecker_tensor.cuh"
 #include "dg_kronecker_tma.cuh"
 #include "dg_quadrature.cuh"
@@ -447,6 +448,25 @@ template <int N, bool HIER> static int launch_dg_kronecker_march(b200fem_operato
   return B200FEM_OK;
 }
 
+// Kronecker kernel of the higher orders (dg_kronecker_slab.cuh): one CTA per TX x TY x TZ tile, n threads per element
+template <int N, int TX, int TY, int TZ> static int launch_dg_kronecker_slab(b200fem_operator* op, const double* u, double* w, const double* bvec) {
+  using Cfg = KronSlabCfg<N, TX, TY, TZ>; const BoxDev& b = op->active_box ? *op->active_box : op->sp->box;
+  if (!op->kron_ready) {
+    KronHost kh = build_kron_tables(op->sp->tab, op->model, b.dim, b.h);
+    op->kron_tab.resize(sizeof(KronTabDev<N>));
+    KronTabDev<N>& K0 = *reinterpret_cast<KronTabDev<N>*>(op->kron_tab.data());
+    for (int d = 0; d < 3; ++d) for (int i = 0; i < N * N; ++i) { K0.S[d][i] = kh.S[d][i]; K0.Dlo[d][i] = kh.Dlo[d][i]; K0.Dhi[d][i] = kh.Dhi[d][i]; K0.L[d][i] = kh.L[d][i]; K0.R[d][i] = kh.R[d][i]; }
+    op->kron_ready = true;
+  }
+  const KronTabDev<N>& K = *reinterpret_cast<const KronTabDev<N>*>(op->kron_tab.data());
+  const int tx = (b.own_hi[0] - b.own_lo[0] + TX - 1) / TX, ty = (b.own_hi[1] - b.own_lo[1] + TY - 1) / TY, tz = (b.own_hi[2] - b.own_lo[2] + TZ - 1) / TZ;
+  auto kern = dg_kronecker_slab_kernel<N, TX, TY, TZ>;
+  static bool attr_set = false;
+  if (!attr_set) { CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes())); attr_set = true; }
+  kern<<<(unsigned)((long long)tx * ty * tz), Cfg::kThreads, Cfg::smem_bytes(), op->sp->mesh->ctx->stream>>>(K, b, op->d_perm, u, w, bvec, tx, ty);
+  CUDA_OK(cudaGetLastError()); return B200FEM_OK;
+}
+
 static long long* g_dbg = nullptr; static int g_dbg_calls = 0;
 template <int N, bool HIER, bool SPLIT> static int launch_dg_kronecker_pipe(b200fem_operator* op, const double* u, double* w, const double* bvec) {
   constexpr int TX = 8, TY = 4, TZ = 4;
@@ -565,11 +585,11 @@ static int apply_local(b200fem_operator* op, const double* u, double* w, bool li
     op->timing.kernel = B200FEM_KERNEL_QUADRATURE;
     return B200FEM_OK;
   }
-  const bool kron_ok = op->model.gamma == 0.0 && (N == 2 || N == 3);
+  const bool kron_ok = op->model.gamma == 0.0 && N >= 2 && N <= 6;
   int kernel = op->kernel_pref;
   if (kernel == B200FEM_KERNEL_AUTO) kernel = kron_ok ? B200FEM_KERNEL_KRONECKER : B200FEM_KERNEL_QUADRATURE;
   if (kernel == B200FEM_KERNEL_KRONECKER) {
-    REQUIRE(kron_ok, B200FEM_ERR_INVALID, "Kronecker kernel needs a linear model and order <= 2");
+    REQUIRE(kron_ok, B200FEM_ERR_INVALID, "Kronecker kernel needs a linear model");
     const double* bvec = nullptr;
     if (!linear && op->model.data) { int rc = ensure_bvec(op); if (rc) return rc; bvec = op->d_bvec; }
     // v2 (bulk-copy staged) needs 8-byte aligned vectors whose w / b share the 16-byte phase; otherwise v1
@@ -578,6 +598,12 @@ static int apply_local(b200fem_operator* op, const double* u, double* w, bool li
     const bool phase_ok = !bvec || ((reinterpret_cast<uintptr_t>(bvec) ^ reinterpret_cast<uintptr_t>(w)) & 8) == 0;
     const bool hier = s->kind == B200FEM_DG_LEGENDRE_HIER;
     int rc;
+    if (N >= 4) {
+      rc = N == 4 ? launch_dg_kronecker_slab<4, 4, 4, 4>(op, u, w, bvec) : N == 5 ? launch_dg_kronecker_slab<5, 4, 2, 2>(op, u, w, bvec) : launch_dg_kronecker_slab<6, 4, 2, 2>(op, u, w, bvec);
+      if (rc) return rc;
+      op->timing.kernel = kernel; op->timing.launches_per_apply = 1;
+      return B200FEM_OK;
+    }
     const bool use_march = variant == "march" && N == 3 && !op->fused_seq && march_path_ok<3>(op, u, w, bvec);
     const bool use_tensor = !use_march && (variant == "tensor" || variant == "march") && N == 3 && tensor_path_ok<3>(op, u, w, bvec);
     op->last_launch_tensor = use_tensor;

@@ -1,0 +1,209 @@
+// dg_kronecker_slab.cuh -- Kronecker-form DG apply for the higher orders (Q3 .. Q5, n = 4 .. 6 modes per axis).
+//
+// Same arithmetic as dg_kronecker.cuh:  w_K = sum_d [ S_d u_K + L_d u_{K-e_d} + R_d u_{K+e_d} ] - b_K  with n x n
+// matrices acting along one tensor axis (9 n^4 FMA per element).  One thread per element (the Q1/Q2 kernels) is not
+// possible any more -- an element is n^3 = 64 .. 216 doubles -- so an element is shared by n threads and the work is
+// organised around SLABS, the unit that gives n FMAs per shared-memory load (profiles/micro/dmma_bench_b200.txt: the
+// FP64 pipe needs >= 4 FMA per LDS.64 to stay fed; mma.sync.m8n8k4.f64 has the same 37 TFLOP/s peak as DFMA on sm_100a,
+// so padding 6 -> 8 rows and 18 -> 20 columns for the tensor pipe could only lose):
+//
+//   phase A  thread (K, j) owns the slab u_K[m0 = j][.][.]: y- and z-contractions of the element itself happen in
+//            registers (2 n^3 FMA for n^2 loads); the y/z face neighbours are streamed line by line (n loads ->
+//            n^2 FMA).  Result: n^2 accumulators acc[m1][m2] in registers.
+//   phase B  the same thread takes the slab u[.][.][m2 = j] of K and of its two x-neighbours, does the x-contraction
+//            (n loads -> n^2 FMA per line) and writes the partial result into an exchange buffer;
+//   combine  after a barrier the thread reads slab m0 = j of the exchange buffer, adds it to acc and leaves the sum
+//            there; warps then write whole elements to global memory in stored order (coalesced), minus b_K.
+//
+// A CTA owns TX x TY x TZ elements; the tile and its six face halos are staged by 8-byte cp.async (LDGSTS, no
+// register round trip; missing neighbours are zero-filled = "no coupling"), in TENSOR order with a padded layout:
+// slab stride S0 and element stride ES are chosen so that both access patterns -- lanes (K, j) reading slab m0 = j
+// (bank = K ES + j S0) and slab m2 = j (bank = K ES + j) -- hit 16 distinct 8-byte banks per half-warp.  The dof
+// permutation of the hierarchical ordering (legendre.hh:236-250) is folded into the staging addresses, so the compute
+// phases use immediates only.  The exchange buffer aliases the y/z halo slots, which are dead after phase A.  Two CTAs
+// per SM overlap one tile's staging with the other's FMAs.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "dg_kronecker.cuh"
+
+namespace b200fem {
+
+template <int N, int TX, int TY, int TZ> struct KronSlabCfg {
+  static constexpr int N2 = N * N, N3 = N * N * N;
+  static constexpr int slab_stride() {
+    int s = N2;
+    while ((N * (s - 1)) % 16 != 0 && s < N2 + 6) ++s;       // bank(K, j) = N K + S0 j distinct over 16 consecutive lanes
+    return (N * (s - 1)) % 16 == 0 ? s : (N2 | 1);
+  }
+  static constexpr int S0 = slab_stride();
+  static constexpr int elem_stride() { int e = N * S0; while (e % 16 != N % 16) ++e; return e; }
+  static constexpr int ES = elem_stride();
+  static constexpr int NO = TX * TY * TZ, NX = 2 * TY * TZ, NY = 2 * TX * TZ, NZ = 2 * TX * TY, kSlots = NO + NX + NY + NZ;
+  static constexpr int kWork = NO * N, kThreads = (kWork + 31) / 32 * 32, kWarps = kThreads / 32;
+  static constexpr int KS = (N3 + 31) / 32;                  // doubles per lane when a warp moves one element
+  static constexpr size_t smem_bytes() { return sizeof(double) * (size_t)kSlots * ES + sizeof(int) * N3; }
+  static_assert(NY + NZ >= NO, "the exchange buffer aliases the y/z halo slots");
+};
+
+namespace slab {
+__device__ __forceinline__ void cp_async8(uint32_t dst, const double* src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+
+// acc[m1][m2] += sum_k M[i][k] v[..k..] inside one N x N slab; AX = 0 contracts the slow index, AX = 1 the fast one
+template <int N, int AX>
+__device__ __forceinline__ void self(const double* __restrict__ M, const double (&v)[N * N], double (&acc)[N * N]) {
+  constexpr int st = AX == 0 ? N : 1;
+#pragma unroll
+  for (int t = 0; t < N * N; ++t) {
+    const int i = AX == 0 ? t / N : t % N, base = t - i * st;
+    double s = acc[t];
+#pragma unroll
+    for (int k = 0; k < N; ++k) s = fma(M[i * N + k], v[base + k * st], s);
+    acc[t] = s;
+  }
+}
+// the same with the operand streamed from shared memory line by line: src points at the slab, whose slow index has
+// stride SLOW and whose fast index has stride FAST (doubles)
+template <int N, int AX, int SLOW, int FAST>
+__device__ __forceinline__ void streamed(const double* __restrict__ M, const double* __restrict__ src, double (&acc)[N * N]) {
+#pragma unroll
+  for (int l = 0; l < N; ++l) {                              // l = the index that is NOT contracted
+    double line[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) line[k] = AX == 0 ? src[k * SLOW + l * FAST] : src[l * SLOW + k * FAST];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const int t = AX == 0 ? i * N + l : l * N + i;
+      double s = acc[t];
+#pragma unroll
+      for (int k = 0; k < N; ++k) s = fma(M[i * N + k], line[k], s);
+      acc[t] = s;
+    }
+  }
+}
+}  // namespace slab
+
+template <int N, int TX, int TY, int TZ>
+__global__ void __launch_bounds__(KronSlabCfg<N, TX, TY, TZ>::kThreads, 2)
+dg_kronecker_slab_kernel(const __grid_constant__ KronTabDev<N> K, const __grid_constant__ BoxDev box, const int* __restrict__ perm_g,
+                         const double* __restrict__ u, double* __restrict__ w, const double* __restrict__ bvec,
+                         const int tiles_x, const int tiles_y) {
+  using Cfg = KronSlabCfg<N, TX, TY, TZ>;
+  constexpr int N2 = Cfg::N2, N3 = Cfg::N3, S0 = Cfg::S0, ES = Cfg::ES, NO = Cfg::NO, NX = Cfg::NX, NY = Cfg::NY, KS = Cfg::KS;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* const U = reinterpret_cast<double*>(smem_raw);
+  int* const tinv = reinterpret_cast<int*>(U + (size_t)Cfg::kSlots * ES);     // stored index -> tensor index
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int t = tid; t < N3; t += Cfg::kThreads) tinv[perm_g[t]] = t;
+  const int bx = blockIdx.x % tiles_x, by = (blockIdx.x / tiles_x) % tiles_y, bz = blockIdx.x / (tiles_x * tiles_y);
+  const int x0 = box.own_lo[0] + bx * TX, y0 = box.own_lo[1] + by * TY, z0 = box.own_lo[2] + bz * TZ;
+  __syncthreads();
+
+  // shared-memory offset (inside an element) of the doubles this lane moves when its warp stages / stores an element
+  int doff[KS];
+#pragma unroll
+  for (int k = 0; k < KS; ++k) { const int s = lane + 32 * k; const int t = s < N3 ? tinv[s] : 0; doff[k] = (t / N2) * S0 + (t % N2); }
+
+  // ------------------------------ stage the tile and its six face halos ------------------------------
+  for (int sl = warp; sl < Cfg::kSlots; sl += Cfg::kWarps) {
+    int ex, ey, ez;
+    if (sl < NO) { ex = sl % TX; ey = (sl / TX) % TY; ez = sl / (TX * TY); }
+    else if (sl < NO + NX) { int r = sl - NO; const int side = r / (TY * TZ); r -= side * TY * TZ; ex = side ? TX : -1; ey = r % TY; ez = r / TY; }
+    else if (sl < NO + NX + NY) { int r = sl - NO - NX; const int side = r / (TX * TZ); r -= side * TX * TZ; ey = side ? TY : -1; ex = r % TX; ez = r / TX; }
+    else { int r = sl - NO - NX - NY; const int side = r / (TX * TY); r -= side * TX * TY; ez = side ? TZ : -1; ex = r % TX; ey = r / TX; }
+    const int lx = x0 + ex, ly = y0 + ey, lz = z0 + ez;
+    const bool ok = lx >= 0 && lx < box.n[0] && ly >= 0 && ly < box.n[1] && lz >= 0 && lz < box.n[2];
+    const double* src = ok ? u + (lx + (long long)box.n[0] * (ly + (long long)box.n[1] * lz)) * N3 : u;
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(U + (size_t)sl * ES);
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+      const int s = lane + 32 * k;
+      if (s < N3) slab::cp_async8(dst + 8u * doff[k], ok ? src + s : src, ok ? 8 : 0);   // src-size 0: zero fill
+    }
+  }
+  slab::cp_async_wait_all();
+  __syncthreads();
+
+  // ------------------------------ compute: thread (e, j) ------------------------------
+  const bool worker = tid < Cfg::kWork;
+  const int e = worker ? tid / N : 0, j = tid % N;
+  const int tx = e % TX, ty = (e / TX) % TY, tz = e / (TX * TY);
+  const int gx = box.origin[0] + x0 + tx, gy = box.origin[1] + y0 + ty, gz = box.origin[2] + z0 + tz;
+  double* const Xe = U + (size_t)(NO + NX + e) * ES;          // exchange / output slot of this element
+  double acc[N2];
+  if (worker) {
+    // ---- phase A: slab m0 = j, axes y (slow index m1) and z (fast index m2)
+    const double* own = U + (size_t)e * ES + j * S0;
+    {
+      double v[N2];
+#pragma unroll
+      for (int t = 0; t < N2; ++t) { v[t] = own[t]; acc[t] = 0.0; }
+      slab::self<N, 0>(K.S[1], v, acc);
+      slab::self<N, 1>(K.S[2], v, acc);
+      if (gy == 0) slab::self<N, 0>(K.Dlo[1], v, acc);
+      if (gy == box.gn[1] - 1) slab::self<N, 0>(K.Dhi[1], v, acc);
+      if (gz == 0) slab::self<N, 1>(K.Dlo[2], v, acc);
+      if (gz == box.gn[2] - 1) slab::self<N, 1>(K.Dhi[2], v, acc);
+    }
+    const int s_ym = ty > 0 ? e - TX : NO + NX + tz * TX + tx, s_yp = ty < TY - 1 ? e + TX : NO + NX + TX * TZ + tz * TX + tx;
+    const int s_zm = tz > 0 ? e - TX * TY : NO + NX + NY + ty * TX + tx, s_zp = tz < TZ - 1 ? e + TX * TY : NO + NX + NY + TX * TY + ty * TX + tx;
+    slab::streamed<N, 0, N, 1>(K.L[1], U + (size_t)s_ym * ES + j * S0, acc);
+    slab::streamed<N, 0, N, 1>(K.R[1], U + (size_t)s_yp * ES + j * S0, acc);
+    slab::streamed<N, 1, N, 1>(K.L[2], U + (size_t)s_zm * ES + j * S0, acc);
+    slab::streamed<N, 1, N, 1>(K.R[2], U + (size_t)s_zp * ES + j * S0, acc);
+  }
+  __syncthreads();                                            // y/z halo slots are dead from here on: they become the exchange buffer
+  if (worker) {
+    // ---- phase B: slab m2 = j, axis x (slow index m0 with stride S0, fast index m1 with stride N)
+    double pb[N2];
+#pragma unroll
+    for (int t = 0; t < N2; ++t) pb[t] = 0.0;
+    const int s_xm = tx > 0 ? e - 1 : NO + tz * TY + ty, s_xp = tx < TX - 1 ? e + 1 : NO + TY * TZ + tz * TY + ty;
+    const double* own = U + (size_t)e * ES + j;
+    slab::streamed<N, 0, S0, N>(K.S[0], own, pb);
+    if (gx == 0) slab::streamed<N, 0, S0, N>(K.Dlo[0], own, pb);
+    if (gx == box.gn[0] - 1) slab::streamed<N, 0, S0, N>(K.Dhi[0], own, pb);
+    slab::streamed<N, 0, S0, N>(K.L[0], U + (size_t)s_xm * ES + j, pb);
+    slab::streamed<N, 0, S0, N>(K.R[0], U + (size_t)s_xp * ES + j, pb);
+#pragma unroll
+    for (int t = 0; t < N2; ++t) Xe[(t / N) * S0 + (t % N) * N + j] = pb[t];
+  }
+  // the load-vector rows of the elements this warp will store are requested now: their latency hides behind the
+  // barrier and the combine step instead of sitting in front of every store
+  constexpr int ELW = (NO + Cfg::kWarps - 1) / Cfg::kWarps;   // elements per warp in the store loop
+  double breg[ELW][KS];
+  long long gbase[ELW];
+#pragma unroll
+  for (int i = 0; i < ELW; ++i) {
+    const int el = warp + i * Cfg::kWarps;
+    const int lx = x0 + el % TX, ly = y0 + (el / TX) % TY, lz = z0 + el / (TX * TY);
+    const bool owned = el < NO && lx < box.own_hi[0] && ly < box.own_hi[1] && lz < box.own_hi[2];
+    gbase[i] = owned ? (lx + (long long)box.n[0] * (ly + (long long)box.n[1] * lz)) * N3 : -1;
+#pragma unroll
+    for (int k = 0; k < KS; ++k) { const int s = lane + 32 * k; breg[i][k] = (bvec && owned && s < N3) ? bvec[gbase[i] + s] : 0.0; }
+  }
+  __syncthreads();
+  if (worker) {
+#pragma unroll
+    for (int t = 0; t < N2; ++t) { acc[t] += Xe[j * S0 + t]; Xe[j * S0 + t] = acc[t]; }
+  }
+  __syncthreads();
+
+  // ------------------------------ store: one warp per element, stored order, coalesced ------------------------------
+#pragma unroll
+  for (int i = 0; i < ELW; ++i) {
+    if (gbase[i] < 0) continue;
+    const double* X = U + (size_t)(NO + NX + warp + i * Cfg::kWarps) * ES;
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+      const int s = lane + 32 * k;
+      if (s < N3) w[gbase[i] + s] = X[doff[k]] - breg[i][k];
+    }
+  }
+}
+
+}  // namespace b200fem

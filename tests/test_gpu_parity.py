@@ -59,6 +59,24 @@ def test_dg_kronecker_kernel(order, hier, n):
     assert op.timing()["kernel"] == _capi.KERNEL_KRONECKER
 
 
+@pytest.mark.parametrize("order,hier", [(3, False), (3, True), (4, True), (5, False), (5, True)])
+@pytest.mark.parametrize("n", [[9, 5, 6], [4, 4, 4], [1, 2, 3], [5, 3, 2]])
+def test_dg_kronecker_slab_kernel(order, hier, n):
+    """Q3..Q5 (BASELINE configs 4 and 5): the slab Kronecker kernel against the oracle's quadrature loop."""
+    space, osp = dg_pair(n, [-1, -1, -1], [1, 1.5, 1], order, hier)
+    beta = 20.0 * order ** 2
+    kw = dict(eps=0.3, b=(1.0, -0.5, 0.25), c=0.7, dirichlet_mask=0b011011, data=1)
+    u = np.random.default_rng(7).uniform(-1, 1, space.size)
+    oop = ol.Operator(osp, beta=beta, skeleton=True, boundary=True, threads=8, **kw)
+    op = fem.operator.galerkin(space, beta=beta, kernel=_capi.KERNEL_KRONECKER, **kw)
+    w = np.empty(space.size)
+    op(u, w)
+    assert rel(w, oop.apply(u)) < TOL
+    op.applyLinear(u, w)
+    assert rel(w, oop.apply(u, linear=True)) < TOL
+    assert op.timing()["kernel"] == _capi.KERNEL_KRONECKER
+
+
 def test_dg_nonlinear_model_uses_quadrature_kernel():
     space, osp = dg_pair([4, 4, 4], [0, 0, 0], [1, 1, 1], 2, True)
     kw = dict(eps=0.5, b=(0.3, 0.2, 0.1), c=1.0, gamma=2.0, dirichlet_mask=0b111111, data=2)
