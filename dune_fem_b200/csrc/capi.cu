@@ -11,6 +11,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/b200fem.h"
@@ -449,7 +450,7 @@ template <int N, bool HIER> static int launch_dg_kronecker_march(b200fem_operato
 }
 
 // Kronecker kernel of the higher orders (dg_kronecker_slab.cuh): one CTA per TX x TY x TZ tile, n threads per element
-template <int N, int TX, int TY, int TZ> static int launch_dg_kronecker_slab(b200fem_operator* op, const double* u, double* w, const double* bvec) {
+template <int N, int TX, int TY, int TZ, int MINB> static int launch_dg_kronecker_slab(b200fem_operator* op, const double* u, double* w, const double* bvec) {
   using Cfg = KronSlabCfg<N, TX, TY, TZ>; const BoxDev& b = op->active_box ? *op->active_box : op->sp->box;
   if (!op->kron_ready) {
     KronHost kh = build_kron_tables(op->sp->tab, op->model, b.dim, b.h);
@@ -460,7 +461,7 @@ template <int N, int TX, int TY, int TZ> static int launch_dg_kronecker_slab(b20
   }
   const KronTabDev<N>& K = *reinterpret_cast<const KronTabDev<N>*>(op->kron_tab.data());
   const int tx = (b.own_hi[0] - b.own_lo[0] + TX - 1) / TX, ty = (b.own_hi[1] - b.own_lo[1] + TY - 1) / TY, tz = (b.own_hi[2] - b.own_lo[2] + TZ - 1) / TZ;
-  auto kern = dg_kronecker_slab_kernel<N, TX, TY, TZ>;
+  auto kern = dg_kronecker_slab_kernel<N, TX, TY, TZ, MINB>;
   static bool attr_set = false;
   if (!attr_set) { CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes())); attr_set = true; }
   kern<<<(unsigned)((long long)tx * ty * tz), Cfg::kThreads, Cfg::smem_bytes(), op->sp->mesh->ctx->stream>>>(K, b, op->d_perm, u, w, bvec, tx, ty);
@@ -599,7 +600,12 @@ static int apply_local(b200fem_operator* op, const double* u, double* w, bool li
     const bool hier = s->kind == B200FEM_DG_LEGENDRE_HIER;
     int rc;
     if (N >= 4) {
-      rc = N == 4 ? launch_dg_kronecker_slab<4, 4, 4, 4>(op, u, w, bvec) : N == 5 ? launch_dg_kronecker_slab<5, 4, 2, 2>(op, u, w, bvec) : launch_dg_kronecker_slab<6, 4, 2, 2>(op, u, w, bvec);
+      // tile shapes: 4x4x4 (Q3), 4x2x2 (Q4, Q5), two CTAs per SM.  Measured alternatives (4x4x2 with 4 CTAs, 4x4x3 with 3, 2x2x2 with 3
+      // for Q5) were within 2 % or slower: the kernel moves 2.5-3.5 x 8 B/dof of halo'd input through the L2->SM fabric and sits
+      // at ~75 % of that path's throughput (profiles/r01_dg_kronecker_slab_q3.md)
+      if (N == 4) rc = launch_dg_kronecker_slab<4, 4, 4, 4, 2>(op, u, w, bvec);
+      else if (N == 5) rc = launch_dg_kronecker_slab<5, 4, 2, 2, 2>(op, u, w, bvec);
+      else rc = launch_dg_kronecker_slab<6, 4, 2, 2, 2>(op, u, w, bvec);
       if (rc) return rc;
       op->timing.kernel = kernel; op->timing.launches_per_apply = 1;
       return B200FEM_OK;

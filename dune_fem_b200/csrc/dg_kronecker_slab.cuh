@@ -20,8 +20,13 @@
 // slab stride S0 and element stride ES are chosen so that both access patterns -- lanes (K, j) reading slab m0 = j
 // (bank = K ES + j S0) and slab m2 = j (bank = K ES + j) -- hit 16 distinct 8-byte banks per half-warp.  The dof
 // permutation of the hierarchical ordering (legendre.hh:236-250) is folded into the staging addresses, so the compute
-// phases use immediates only.  The exchange buffer aliases the y/z halo slots, which are dead after phase A.  Two CTAs
-// per SM overlap one tile's staging with the other's FMAs.
+// phases use immediates only.  The exchange buffer aliases the y/z halo slots, which are dead after phase A.  Two to four
+// CTAs per SM overlap one tile's staging with the others' FMAs.
+//
+// Tried and dropped (profiles/r01_dg_kronecker_slab_q5.md): a variant with three warp-uniform thread roles per slab (one per
+// axis, 3 n threads per element, n^2 accumulators each).  It triples the warps but 9 warps per CTA put 5 warps on one SM
+// sub-partition, which caps the kernel at 96 registers -> spills, and the three partial results cost two more shared
+// round trips: 54 instead of 99 GDoF/s for Q5.
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -52,17 +57,18 @@ __device__ __forceinline__ void cp_async8(uint32_t dst, const double* src, int s
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 
-// acc[m1][m2] += sum_k M[i][k] v[..k..] inside one N x N slab; AX = 0 contracts the slow index, AX = 1 the fast one
+// acc[m1][m2] += sum_k M[i][k] v[..k..] inside one N x N slab held in registers; AX = 0 contracts the slow index, AX = 1
+// the fast one.  k is the OUTER loop: consecutive FMAs hit different accumulators (no dependent chains back to back).
 template <int N, int AX>
 __device__ __forceinline__ void self(const double* __restrict__ M, const double (&v)[N * N], double (&acc)[N * N]) {
   constexpr int st = AX == 0 ? N : 1;
 #pragma unroll
-  for (int t = 0; t < N * N; ++t) {
-    const int i = AX == 0 ? t / N : t % N, base = t - i * st;
-    double s = acc[t];
+  for (int k = 0; k < N; ++k) {
 #pragma unroll
-    for (int k = 0; k < N; ++k) s = fma(M[i * N + k], v[base + k * st], s);
-    acc[t] = s;
+    for (int t = 0; t < N * N; ++t) {
+      const int i = AX == 0 ? t / N : t % N, base = t - i * st;
+      acc[t] = fma(M[i * N + k], v[base + k * st], acc[t]);
+    }
   }
 }
 // the same with the operand streamed from shared memory line by line: src points at the slab, whose slow index has
@@ -75,19 +81,56 @@ __device__ __forceinline__ void streamed(const double* __restrict__ M, const dou
 #pragma unroll
     for (int k = 0; k < N; ++k) line[k] = AX == 0 ? src[k * SLOW + l * FAST] : src[l * SLOW + k * FAST];
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-      const int t = AX == 0 ? i * N + l : l * N + i;
-      double s = acc[t];
+    for (int k = 0; k < N; ++k) {
 #pragma unroll
-      for (int k = 0; k < N; ++k) s = fma(M[i * N + k], line[k], s);
-      acc[t] = s;
+      for (int i = 0; i < N; ++i) {
+        const int t = AX == 0 ? i * N + l : l * N + i;
+        acc[t] = fma(M[i * N + k], line[k], acc[t]);
+      }
     }
+  }
+}
+
+// Stages the tile and its six face halos.  Slot sl of the CTA is handled by warp sl % kWarps; the decode of a slot (local
+// element coordinates, existence, global offset) is done ONCE per slot by one lane and broadcast by shuffle -- done per
+// warp iteration it was 45 % of all instructions of the first version (profiles/r01_dg_kronecker_slab_q3.md).
+template <class Cfg, int TX, int TY, int TZ>
+__device__ __forceinline__ void stage_tile(const BoxDev& box, const double* __restrict__ u, double* U, const int (&doff)[Cfg::KS],
+                                           const int x0, const int y0, const int z0, const int warp, const int lane) {
+  constexpr int N3 = Cfg::N3, NO = Cfg::NO, NX = Cfg::NX, NY = Cfg::NY, KS = Cfg::KS, SPW = (Cfg::kSlots + Cfg::kWarps - 1) / Cfg::kWarps;
+  static_assert(SPW <= 32, "one lane decodes one slot of its warp");
+  long long my_src = -1;                                     // offset (doubles) of the element in slot warp + lane * kWarps, -1: none
+  {
+    const int sl = warp + lane * Cfg::kWarps;
+    if (sl < Cfg::kSlots) {
+      int ex, ey, ez;
+      if (sl < NO) { ex = sl % TX; ey = (sl / TX) % TY; ez = sl / (TX * TY); }
+      else if (sl < NO + NX) { int r = sl - NO; const int side = r / (TY * TZ); r -= side * TY * TZ; ex = side ? TX : -1; ey = r % TY; ez = r / TY; }
+      else if (sl < NO + NX + NY) { int r = sl - NO - NX; const int side = r / (TX * TZ); r -= side * TX * TZ; ey = side ? TY : -1; ex = r % TX; ez = r / TX; }
+      else { int r = sl - NO - NX - NY; const int side = r / (TX * TY); r -= side * TX * TY; ez = side ? TZ : -1; ex = r % TX; ey = r / TX; }
+      const int lx = x0 + ex, ly = y0 + ey, lz = z0 + ez;
+      if (lx >= 0 && lx < box.n[0] && ly >= 0 && ly < box.n[1] && lz >= 0 && lz < box.n[2])
+        my_src = (lx + (long long)box.n[0] * (ly + (long long)box.n[1] * lz)) * N3;
+    }
+  }
+  const uint32_t ubase = (uint32_t)__cvta_generic_to_shared(U);
+#pragma unroll 1
+  for (int i = 0; i < SPW; ++i) {
+    const int sl = warp + i * Cfg::kWarps;
+    if (sl >= Cfg::kSlots) break;
+    const long long so = __shfl_sync(0xffffffffu, my_src, i);
+    const bool ok = so >= 0;
+    const double* src = u + (ok ? so : 0) + lane;
+    const uint32_t dst = ubase + 8u * (uint32_t)(sl * Cfg::ES);
+#pragma unroll
+    for (int k = 0; k < KS; ++k)
+      if (lane + 32 * k < N3) cp_async8(dst + 8u * doff[k], ok ? src + 32 * k : u, ok ? 8 : 0);   // src-size 0: zero fill
   }
 }
 }  // namespace slab
 
-template <int N, int TX, int TY, int TZ>
-__global__ void __launch_bounds__(KronSlabCfg<N, TX, TY, TZ>::kThreads, 2)
+template <int N, int TX, int TY, int TZ, int MINB>
+__global__ void __launch_bounds__(KronSlabCfg<N, TX, TY, TZ>::kThreads, MINB)
 dg_kronecker_slab_kernel(const __grid_constant__ KronTabDev<N> K, const __grid_constant__ BoxDev box, const int* __restrict__ perm_g,
                          const double* __restrict__ u, double* __restrict__ w, const double* __restrict__ bvec,
                          const int tiles_x, const int tiles_y) {
@@ -108,23 +151,7 @@ dg_kronecker_slab_kernel(const __grid_constant__ KronTabDev<N> K, const __grid_c
 #pragma unroll
   for (int k = 0; k < KS; ++k) { const int s = lane + 32 * k; const int t = s < N3 ? tinv[s] : 0; doff[k] = (t / N2) * S0 + (t % N2); }
 
-  // ------------------------------ stage the tile and its six face halos ------------------------------
-  for (int sl = warp; sl < Cfg::kSlots; sl += Cfg::kWarps) {
-    int ex, ey, ez;
-    if (sl < NO) { ex = sl % TX; ey = (sl / TX) % TY; ez = sl / (TX * TY); }
-    else if (sl < NO + NX) { int r = sl - NO; const int side = r / (TY * TZ); r -= side * TY * TZ; ex = side ? TX : -1; ey = r % TY; ez = r / TY; }
-    else if (sl < NO + NX + NY) { int r = sl - NO - NX; const int side = r / (TX * TZ); r -= side * TX * TZ; ey = side ? TY : -1; ex = r % TX; ez = r / TX; }
-    else { int r = sl - NO - NX - NY; const int side = r / (TX * TY); r -= side * TX * TY; ez = side ? TZ : -1; ex = r % TX; ey = r / TX; }
-    const int lx = x0 + ex, ly = y0 + ey, lz = z0 + ez;
-    const bool ok = lx >= 0 && lx < box.n[0] && ly >= 0 && ly < box.n[1] && lz >= 0 && lz < box.n[2];
-    const double* src = ok ? u + (lx + (long long)box.n[0] * (ly + (long long)box.n[1] * lz)) * N3 : u;
-    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(U + (size_t)sl * ES);
-#pragma unroll
-    for (int k = 0; k < KS; ++k) {
-      const int s = lane + 32 * k;
-      if (s < N3) slab::cp_async8(dst + 8u * doff[k], ok ? src + s : src, ok ? 8 : 0);   // src-size 0: zero fill
-    }
-  }
+  slab::stage_tile<Cfg, TX, TY, TZ>(box, u, U, doff, x0, y0, z0, warp, lane);
   slab::cp_async_wait_all();
   __syncthreads();
 
