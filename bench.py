@@ -91,6 +91,54 @@ def cpu_reference_apply(threads, sample_cells, reps):
     return sp.size, times, w
 
 
+def time_other_configs(fem, _capi, ctx, stream, dev, peak):
+    """Device-resident apply of the other BASELINE configs on one GPU (not bench lines of their own: they explain where
+    the remaining kernels stand).  C4: DG Q5 48^3 SIPG Laplace, C5: DG Q3 133^3 advection-diffusion (150.6 M dofs, one
+    GPU's share of the 8-GPU weak-scaling config), both through the slab Kronecker kernel; C3/C1 Lagrange applies."""
+    import torch
+    out = {}
+
+    def timed(op, size, reps, linear):
+        us = [torch.rand(size, dtype=torch.float64, device=dev) * 2 - 1 for _ in range(3)]
+        ws = [torch.empty(size, dtype=torch.float64, device=dev) for _ in range(3)]
+        for i in range(3):
+            op.apply_dev(us[i % 3].data_ptr(), ws[i % 3].data_ptr(), linear)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(reps):
+            op.apply_dev(us[i % 3].data_ptr(), ws[i % 3].data_ptr(), linear)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        del us, ws
+        return e0.elapsed_time(e1) * 1e-3 / reps
+
+    dg = (("C4 DG Q5 48^3 SIPG Laplace apply", 48, 5, dict(eps=1.0, b=(0.0, 0.0, 0.0), beta=500.0, dirichlet_mask=0b111111, data=2), [0.0] * 3, 20),
+          ("C5 DG Q3 133^3 advection-diffusion apply (one GPU's share)", 133, 3, dict(eps=1e-5, b=(1.0, 0.0, 0.0), beta=180.0, dirichlet_mask=0b000011, data=1), [-1.0] * 3, 10))
+    for name, cells, order, model, lo, reps in dg:
+        grid = fem.structuredGrid(lo, [1.0] * 3, [cells] * 3, ctx=ctx)
+        space = fem.space.dglegendre(grid, order=order, hierarchical=True)
+        op = fem.operator.galerkin(space, **model)
+        t_aff, t_lin = timed(op, space.size, reps, False), timed(op, space.size, reps, True)
+        n = order + 1
+        out[name] = {"dofs": space.size, "kernel": "dg_kronecker_slab_kernel<%d>" % n, "affine_ms": t_aff * 1e3, "dofs_per_s": space.size / t_aff,
+                     "linear_ms": t_lin * 1e3, "linear_dofs_per_s": space.size / t_lin, "frac_hbm_16B": 16 * space.size / t_lin / 1e9 / peak,
+                     "fp64_tflops_kronecker_form": 2 * 9 * n ** 4 * cells ** 3 / t_lin / 1e12, "fp64_peak_tflops_measured": 37.1}
+        del op, space, grid
+        torch.cuda.empty_cache()
+    for name, dim, cells, order in (("C3 Poisson P2 Lagrange 3D 128^3 apply", 3, 128, 2), ("C1 Poisson P1 Lagrange 2D 256^2 apply", 2, 256, 1),
+                                    ("C1 scaled up: P1 Lagrange 2D 4096^2 apply", 2, 4096, 1)):
+        grid = fem.structuredGrid([0.0] * dim, [1.0] * dim, [cells] * dim, ctx=ctx)
+        space = fem.space.lagrange(grid, order=order)
+        op = fem.operator.galerkin(space, eps=1.0, data=2, dirichlet_mask=(1 << (2 * dim)) - 1, strong_dirichlet=True)
+        t_lin = timed(op, space.size, 20, True)
+        out[name] = {"dofs": space.size, "kernel": "lagrange_kronecker_kernel<%d>" % order, "linear_ms": t_lin * 1e3, "linear_dofs_per_s": space.size / t_lin,
+                     "frac_hbm_16B": 16 * space.size / t_lin / 1e9 / peak}
+        del op, space, grid
+        torch.cuda.empty_cache()
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -126,6 +174,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cg", action="store_true", help="skip the CG s/iteration measurement (BASELINE configs 1 and 3)")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the apply timings of BASELINE configs 3, 4, 5")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -281,8 +330,17 @@ def main():
                 torch.cuda.synchronize()
                 cg_ms = e0.elapsed_time(e1)
             cg[name] = {"dofs": sp.size, "iterations": abs(its.value), "s_per_iteration": cg_ms * 1e-3 / iters,
-                        "dofs_per_s": sp.size * iters / (cg_ms * 1e-3), "launches_per_iteration": lop.timing()["launches_per_apply"] + 7}
+                        "dofs_per_s": sp.size * iters / (cg_ms * 1e-3), "launches_per_iteration": lop.timing()["launches_per_apply"] + 3,
+                        "cuda_graph": "16 iterations per graph launch"}
             del bt, x0, xt, lop, sp, g
+
+    other = None
+    if world == 1 and not args.no_other_configs:
+        try:
+            pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs") or 6650.0
+        except Exception:
+            pk = 6650.0
+        other = time_other_configs(fem, _capi, ctx, stream, dev, pk)
 
     if rank != 0:
         if world > 1:
@@ -309,8 +367,11 @@ def main():
     kernel_name = {1: "dg_quadrature_kernel<3>", 2: {"march": "dg_kronecker_march_kernel<3> (z-marching, TMA planes)"}.get(os.environ.get("B200FEM_KRON_VARIANT", "march"), "dg_kronecker_tensor_kernel<3> (TMA tensor tiles)")}.get(tinfo["kernel"], "?")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": kernel_name, "peak_source": peak_src, "algorithmic_bytes_per_dof": ALGORITHMIC_BYTES_PER_DOF,
-                "note": "the affine step also streams the precomputed load vector b (8 B/dof) that the 16 B/dof figure does not count; "
-                        "the homogeneous apply A u moves exactly 16 B/dof, see linear_apply"}
+                "compulsory_bytes_per_dof": 24.0, "achieved_compulsory_gbs": 24.0 * ndof_local / per_launch_s / 1e9,
+                "frac_compulsory": 24.0 * ndof_local / per_launch_s / 1e9 / peak,
+                "note": "the affine step also streams the precomputed load vector b (8 B/dof) that the 16 B/dof figure does not count "
+                        "(compulsory DRAM traffic of w = A u - b is 24 B/dof: frac_compulsory); the homogeneous apply A u moves "
+                        "exactly 16 B/dof, see linear_apply"}
     lin_s = ms_linear * 1e-3 / args.steps
     linear_apply = {"value": ndof_total / lin_s, "unit": "DoF/s", "ms_per_step": ms_linear / args.steps,
                     "achieved_gbs": ALGORITHMIC_BYTES_PER_DOF * ndof_local / lin_s / 1e9,
@@ -334,7 +395,7 @@ def main():
                    "dofs_per_gpu": ndof_local, "process_grid": proc, "halo_exchange": world > 1,
                    "l2": f"{npairs} rotating (u,w) buffer pairs = {npairs * 2 * 8 * space.size / 1e6:.0f} MB > 126 MB L2",
                    "kernel": kernel_name},
-        "roofline": roofline, "linear_apply": linear_apply, "cg": cg, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "host_issue_us_per_step": host_us, "exchange_ms_last": tinfo.get("last_exchange_ms"), "apply_ms_last": tinfo.get("last_apply_ms"), "multi_gpu_diag": diag,
+        "roofline": roofline, "linear_apply": linear_apply, "cg": cg, "other_configs": other, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "host_issue_us_per_step": host_us, "exchange_ms_last": tinfo.get("last_exchange_ms"), "apply_ms_last": tinfo.get("last_apply_ms"), "multi_gpu_diag": diag,
         "clocks": sampler.result(),
     }
     print(json.dumps(line), flush=True)

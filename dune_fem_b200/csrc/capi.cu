@@ -62,7 +62,8 @@ struct b200fem_operator {
   std::vector<uint8_t> h_dmask; std::vector<double> h_dvals;
   double *d_u = nullptr, *d_w = nullptr;                       // staging for the host-pointer API
   double *d_h = nullptr, *d_r = nullptr, *d_p = nullptr, *d_x = nullptr, *d_b = nullptr, *d_partial = nullptr, *d_sums = nullptr, *d_hist = nullptr;
-  CgState* d_cg = nullptr; int hist_cap = 0;
+  CgState* d_cg = nullptr; int hist_cap = 0; unsigned int* d_counter = nullptr;
+  cudaGraphExec_t cg_graph = nullptr; const void* cg_graph_key[3] = {nullptr, nullptr, nullptr}; bool capturing = false;
   bool kron_ready = false; int kron_chk = -1; bool fuse_dirichlet = false, fuse_linear = false, dirichlet_fused = false; double* d_lag_rows = nullptr; LagKronRows lag_rows{}; std::vector<unsigned char> kron_tab; struct KronMapCache* map_cache = nullptr; struct MarchMapCache* march_cache = nullptr;
   HaloPlan halo; HaloPlanDG halo_dg; HaloPlanP2P halo_p2p; const BoxDev* active_box = nullptr; int reserve_sms = 0; unsigned long long fused_seq = 0; bool last_launch_tensor = false;      // active_box: sub-box override for split launches
   cudaStream_t comm_stream = nullptr; cudaEvent_t ev_bnd = nullptr, ev_comm = nullptr, dbg_ev[2] = {nullptr, nullptr};
@@ -668,7 +669,8 @@ static int exchange(b200fem_operator* op, double* v, cudaStream_t st) {
 // is computed -- the exchange the reference performs serially after the loop is hidden behind the interior elements.
 static int apply_dev_impl(b200fem_operator* op, const double* u, double* w, bool linear) {
   b200fem_space* s = op->sp; cudaStream_t st = s->mesh->ctx->stream;
-  if (op->timing_enabled) CUDA_OK(cudaEventRecord(op->ev0, st));
+  const bool timing_events = op->timing_enabled && !op->capturing;
+  if (timing_events) CUDA_OK(cudaEventRecord(op->ev0, st));
   const bool distributed = op->communicate && s->mesh->ctx->world > 1;
   int rc;
   // Measured on 2 x B200 (profiles/r01_multigpu.md): exchange kernels queued on a second stream do not start before the
@@ -718,10 +720,10 @@ static int apply_dev_impl(b200fem_operator* op, const double* u, double* w, bool
     op->fused_seq = 0;
     if (rc) return rc;
     if (distributed) {
-      if (op->timing_enabled) CUDA_OK(cudaEventRecord(op->evx0, st));
+      if (timing_events) CUDA_OK(cudaEventRecord(op->evx0, st));
       if (fused) { const unsigned long long seq = ++op->halo_p2p.seq; if (halo_exchange_p2p_fused_tail(op->halo_p2p, w, seq, st) != 0) return fail(B200FEM_ERR_COMM, "halo exchange failed"); op->timing.launches_per_apply += 1; }
       else { rc = exchange(op, w, st); if (rc) return rc; }
-      if (op->timing_enabled) CUDA_OK(cudaEventRecord(op->evx1, st));
+      if (timing_events) CUDA_OK(cudaEventRecord(op->evx1, st));
     }
   }
   // DirichletWrapperOperator: op_(u,w) (communication included) first, then subConstraints (dirichletwrapper.hh:101-105)
@@ -729,7 +731,7 @@ static int apply_dev_impl(b200fem_operator* op, const double* u, double* w, bool
     dirichlet_sub_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(u, w, op->d_dmask, linear ? nullptr : op->d_dvals, s->size);
     CUDA_OK(cudaGetLastError()); op->timing.launches_per_apply += 1;
   }
-  if (op->timing_enabled) CUDA_OK(cudaEventRecord(op->ev1, st));
+  if (timing_events) CUDA_OK(cudaEventRecord(op->ev1, st));
   op->timing.applies += 1;
   if (op->dbg_ev[0] && op->timing.applies == 300) {
     CUDA_OK(cudaEventSynchronize(op->ev1)); float a, b, c, d, e;
@@ -809,7 +811,8 @@ static void free_map_cache(b200fem_operator* op) { delete op->map_cache; op->map
 extern "C" int b200fem_operator_destroy(b200fem_operator* op) {
   if (!op) return B200FEM_OK;
   for (void* p : {(void*)op->d_perm, (void*)op->d_bvec, (void*)op->d_dmask, (void*)op->d_dvals, (void*)op->d_aux, (void*)op->d_u, (void*)op->d_w, (void*)op->d_h, (void*)op->d_r,
-                  (void*)op->d_p, (void*)op->d_x, (void*)op->d_b, (void*)op->d_partial, (void*)op->d_sums, (void*)op->d_hist, (void*)op->d_cg, (void*)op->d_lag_rows}) if (p) cudaFree(p);
+                  (void*)op->d_p, (void*)op->d_x, (void*)op->d_b, (void*)op->d_partial, (void*)op->d_sums, (void*)op->d_hist, (void*)op->d_cg, (void*)op->d_lag_rows, (void*)op->d_counter}) if (p) cudaFree(p);
+  if (op->cg_graph) cudaGraphExecDestroy(op->cg_graph);
   halo_plan_p2p_free(op->halo_p2p); halo_plan_free(op->halo); halo_plan_dg_free(op->halo_dg); free_map_cache(op);
   if (op->comm_stream) cudaStreamDestroy(op->comm_stream);
   for (cudaEvent_t e : {op->ev_bnd, op->ev_comm}) if (e) cudaEventDestroy(e);
@@ -884,7 +887,7 @@ static int reduce_sums(b200fem_operator* op, int count) {
 static int ensure_cg_buffers(b200fem_operator* op, int maxit) {
   const size_t bytes = sizeof(double) * (size_t)op->sp->size;
   if (!op->d_h) { CUDA_OK(cudaMalloc(&op->d_h, bytes)); CUDA_OK(cudaMalloc(&op->d_r, bytes)); CUDA_OK(cudaMalloc(&op->d_p, bytes)); }
-  if (!op->d_partial) { CUDA_OK(cudaMalloc(&op->d_partial, sizeof(double) * 2 * kRedBlocks)); CUDA_OK(cudaMalloc(&op->d_sums, sizeof(double) * 4)); CUDA_OK(cudaMalloc(&op->d_cg, sizeof(CgState))); }
+  if (!op->d_partial) { CUDA_OK(cudaMalloc(&op->d_partial, sizeof(double) * 2 * kRedBlocks)); CUDA_OK(cudaMalloc(&op->d_sums, sizeof(double) * 4)); CUDA_OK(cudaMalloc(&op->d_cg, sizeof(CgState))); CUDA_OK(cudaMalloc(&op->d_counter, 2 * sizeof(unsigned int))); CUDA_OK(cudaMemset(op->d_counter, 0, 2 * sizeof(unsigned int))); }
   if (maxit > op->hist_cap) { if (op->d_hist) cudaFree(op->d_hist); CUDA_OK(cudaMalloc(&op->d_hist, sizeof(double) * (size_t)std::max(maxit, 1))); op->hist_cap = std::max(maxit, 1); }
   return B200FEM_OK;
 }
@@ -916,18 +919,49 @@ extern "C" int b200fem_cg_solve_dev(b200fem_operator* op, const double* b, doubl
   rc = reduce_sums(op, 2); if (rc) return rc;
   cg_init_final_kernel<<<1, 32, 0, st>>>(op->d_sums, op->d_cg);
   CgState host{}; const int chunk = 16;
-  for (int it = 0; it < maxit;) {
-    const int upto = std::min(maxit, it + chunk);
-    for (; it < upto; ++it) {
-      if (it > 0) cg_update_p_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(op->d_p, op->d_r, n, op->d_cg);
-      rc = apply_dev_impl(op, op->d_p, op->d_h, true); if (rc) return rc;                                     // h = A q
+  // one CG iteration, enqueued on the stream.  Single rank: 4 launches (the last block of a reduction kernel finishes the
+  // reduction and updates the scalars); several ranks: the partial sums go through ncclAllReduce between two kernels.
+  const bool single = c->world == 1;
+  auto enqueue_iteration = [&]() -> int {
+    cg_update_p_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(op->d_p, op->d_r, n, op->d_cg);                      // no-op in iteration 0
+    int e = apply_dev_impl(op, op->d_p, op->d_h, true); if (e) return e;                                        // h = A q
+    if (single) {
+      cg_dot_alpha_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(op->d_p, op->d_h, op->d_aux, n, op->d_partial, op->d_cg, op->d_counter);
+      cg_update_xr_residual_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(x, op->d_r, op->d_p, op->d_h, op->d_aux, n, op->d_partial, op->d_cg, op->d_hist, op->d_counter + 1);
+    } else {
       cg_dot_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(op->d_p, op->d_h, op->d_aux, n, op->d_partial, op->d_cg);
-      rc = reduce_sums(op, 1); if (rc) return rc;
+      e = reduce_sums(op, 1); if (e) return e;
       cg_alpha_kernel<<<1, 32, 0, st>>>(op->d_sums, op->d_cg);
       cg_update_xr_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(x, op->d_r, op->d_p, op->d_h, op->d_aux, n, op->d_partial, op->d_cg);
-      rc = reduce_sums(op, 1); if (rc) return rc;
+      e = reduce_sums(op, 1); if (e) return e;
       cg_residual_kernel<<<1, 32, 0, st>>>(op->d_sums, op->d_cg, op->d_hist);
     }
+    return B200FEM_OK;
+  };
+  // Single rank: a chunk of 16 iterations is captured once into a CUDA graph and replayed (launch-bound sizes such as the
+  // 256^2 P1 grid spend their time in launch gaps otherwise).  Iterations past convergence / max_iterations are no-ops
+  // on the device (every kernel checks the device-resident `done` flag), so whole chunks can always be replayed.
+  static const bool no_graph = std::getenv("B200FEM_NO_CG_GRAPH") != nullptr;
+  const bool use_graph = single && !no_graph && maxit >= chunk;
+  if (use_graph && !(op->cg_graph && op->cg_graph_key[0] == (const void*)x && op->cg_graph_key[1] == (const void*)b && op->cg_graph_key[2] == (const void*)op->d_hist)) {
+    if (op->cg_graph) { cudaGraphExecDestroy(op->cg_graph); op->cg_graph = nullptr; }
+    cudaGraph_t graph = nullptr;
+    CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    op->capturing = true; int e = B200FEM_OK;
+    for (int k = 0; k < chunk && !e; ++k) e = enqueue_iteration();
+    op->capturing = false;
+    cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (e) { if (graph) cudaGraphDestroy(graph); return e; }
+    if (ce != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return fail(B200FEM_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce)); }
+    ce = cudaGraphInstantiate(&op->cg_graph, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) { op->cg_graph = nullptr; return fail(B200FEM_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce)); }
+    op->cg_graph_key[0] = x; op->cg_graph_key[1] = b; op->cg_graph_key[2] = op->d_hist;
+  }
+  for (int it = 0; it < maxit;) {
+    const int upto = std::min(maxit, it + chunk);
+    if (use_graph) { CUDA_OK(cudaGraphLaunch(op->cg_graph, st)); it += chunk; }
+    else for (; it < upto; ++it) { rc = enqueue_iteration(); if (rc) return rc; }
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaMemcpyAsync(&host, op->d_cg, sizeof(CgState), cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st));
     if (host.done) break;

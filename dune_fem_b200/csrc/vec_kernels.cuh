@@ -87,7 +87,7 @@ __global__ void cg_init_final_kernel(const double* __restrict__ sums, CgState* s
 }
 // p <- beta p - r, beta = residual / prevResidual       (cg.hh:72-85, unpreconditioned: q aliases p)
 __global__ void cg_update_p_kernel(double* __restrict__ p, const double* __restrict__ r, long long n, const CgState* st) {
-  if (st->done) return;
+  if (st->done || st->iterations == 0) return;            // the first search direction is p = b - A x (cg_init_kernel)
   const double beta = st->residual / st->prev_residual;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = p[i] * beta - r[i];
 }
@@ -126,6 +126,58 @@ __global__ void cg_residual_kernel(const double* __restrict__ sums, CgState* st,
     if (history) history[st->iterations] = sqrt(sums[0]);
     st->iterations += 1;
     if (!(st->residual > st->tolerance) || st->iterations >= st->max_iterations) st->done = 1;
+  }
+}
+
+// ---- single-rank variants: the block that finishes last also does the second reduction stage and the scalar update, so an
+// iteration is 4 launches (p-update, apply, <p,h>+alpha, x/r-update+residual) instead of 8.  The partials are summed by
+// the same code in the same order as reduce_final_kernel: results are bit-identical to the two-kernel path and
+// independent of which block happens to be last.
+__device__ __forceinline__ bool last_block_done(unsigned int* counter) {
+  __shared__ bool last;
+  if (threadIdx.x == 0) { __threadfence(); last = atomicAdd(counter, 1u) == gridDim.x - 1; }
+  __syncthreads();
+  if (last) __threadfence();
+  return last;
+}
+__device__ __forceinline__ double final_sum(const double* partial) {
+  double s = 0;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) s += __ldcg(partial + i);
+  return block_sum(s);
+}
+__global__ void __launch_bounds__(kRedThreads) cg_dot_alpha_kernel(const double* __restrict__ x, const double* __restrict__ y, const uint8_t* __restrict__ aux,
+                                                                   long long n, double* partial, CgState* st, unsigned int* counter) {
+  if (st->done) return;
+  double s = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    if (!aux || !aux[i]) s = fma(x[i], y[i], s);
+  s = block_sum(s);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+  if (!last_block_done(counter)) return;
+  const double t = final_sum(partial);
+  if (threadIdx.x == 0) { st->qdoth = t; st->alpha = st->residual / t; *counter = 0; }
+}
+__global__ void __launch_bounds__(kRedThreads) cg_update_xr_residual_kernel(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
+                                                                            const double* __restrict__ h, const uint8_t* __restrict__ aux, long long n,
+                                                                            double* partial, CgState* st, double* __restrict__ history, unsigned int* counter) {
+  if (st->done) return;
+  const double alpha = st->alpha;
+  double s = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    x[i] = fma(alpha, p[i], x[i]);
+    const double rv = fma(alpha, h[i], r[i]); r[i] = rv;
+    if (!aux || !aux[i]) s = fma(rv, rv, s);
+  }
+  s = block_sum(s);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+  if (!last_block_done(counter)) return;
+  const double t = final_sum(partial);
+  if (threadIdx.x == 0) {
+    st->prev_residual = st->residual; st->residual = t;
+    if (history) history[st->iterations] = sqrt(t);
+    st->iterations += 1;
+    if (!(st->residual > st->tolerance) || st->iterations >= st->max_iterations) st->done = 1;
+    *counter = 0;
   }
 }
 

@@ -58,6 +58,19 @@ def main():
             err = np.abs(wl - wg[gather]).max() / np.abs(wg).max()      # owned AND ghost copies must match
             worst = max(worst, err)
             assert err < 1e-12, (proc, kernel, err)
+        # ---------------- DG Q3 (slab Kronecker kernel, BASELINE config 5) ----------------
+        space3 = fem.space.dglegendre(grid, order=3, hierarchical=True)
+        osp3 = ol.Space(n, lo, hi, ol.DG_LEGENDRE_HIER, 3)
+        kw3 = dict(eps=0.05, b=(1.0, 0.5, 0.25), beta=180.0, dirichlet_mask=0b000011, data=1)
+        ug3 = np.random.default_rng(8).uniform(-1, 1, osp3.size)
+        wg3 = ol.Operator(osp3, skeleton=True, boundary=True, threads=4, **kw3).apply(ug3)
+        gather3 = (lidx[:, None] * 64 + np.arange(64)[None, :]).ravel()
+        op3 = fem.operator.galerkin(space3, kernel=_capi.KERNEL_KRONECKER, **kw3)
+        wl3 = np.empty(space3.size)
+        op3(np.ascontiguousarray(ug3[gather3]), wl3)
+        err = np.abs(wl3 - wg3[gather3]).max() / np.abs(wg3).max()
+        worst = max(worst, err)
+        assert err < 1e-12, ("q3 slab", proc, err)
         # CG on an SPD DG operator, distributed dots
         kw2 = dict(eps=1.0, c=1.0, beta=80.0, dirichlet_mask=0, data=2)
         op = fem.operator.galerkin(space, **kw2)
