@@ -63,6 +63,7 @@ struct b200fem_operator {
   double *d_u = nullptr, *d_w = nullptr;                       // staging for the host-pointer API
   double *d_h = nullptr, *d_r = nullptr, *d_p = nullptr, *d_x = nullptr, *d_b = nullptr, *d_partial = nullptr, *d_sums = nullptr, *d_hist = nullptr;
   CgState* d_cg = nullptr; int hist_cap = 0; unsigned int* d_counter = nullptr;
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr; cudaEvent_t pipe_ev[2 * 16 + 2] = {};   // host-pointer apply: copy/compute pipeline
   cudaGraphExec_t cg_graph = nullptr; const void* cg_graph_key[3] = {nullptr, nullptr, nullptr}; bool capturing = false;
   bool kron_ready = false; int kron_chk = -1; bool fuse_dirichlet = false, fuse_linear = false, dirichlet_fused = false; double* d_lag_rows = nullptr; LagKronRows lag_rows{}; std::vector<unsigned char> kron_tab; struct KronMapCache* map_cache = nullptr; struct MarchMapCache* march_cache = nullptr;
   HaloPlan halo; HaloPlanDG halo_dg; HaloPlanP2P halo_p2p; const BoxDev* active_box = nullptr; int reserve_sms = 0; unsigned long long fused_seq = 0; bool last_launch_tensor = false;      // active_box: sub-box override for split launches
@@ -815,6 +816,9 @@ extern "C" int b200fem_operator_destroy(b200fem_operator* op) {
   if (op->cg_graph) cudaGraphExecDestroy(op->cg_graph);
   halo_plan_p2p_free(op->halo_p2p); halo_plan_free(op->halo); halo_plan_dg_free(op->halo_dg); free_map_cache(op);
   if (op->comm_stream) cudaStreamDestroy(op->comm_stream);
+  if (op->h2d_stream) cudaStreamDestroy(op->h2d_stream);
+  if (op->d2h_stream) cudaStreamDestroy(op->d2h_stream);
+  for (cudaEvent_t e : op->pipe_ev) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : {op->ev_bnd, op->ev_comm}) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : {op->ev0, op->ev1, op->evx0, op->evx1}) if (e) cudaEventDestroy(e);
   delete op; return B200FEM_OK;
@@ -825,11 +829,45 @@ static int ensure_staging(b200fem_operator* op) {
   if (!op->d_w) CUDA_OK(cudaMalloc(&op->d_w, bytes));
   return B200FEM_OK;
 }
+// Host-pointer apply of a DG space on one rank, pipelined over z-slabs: the element-major dof vector is contiguous per
+// z-plane, so slab c+1 travels host->device while slab c is computed and slab c-1 travels device->host.  PCIe is full
+// duplex: the end-to-end time drops from H2D + kernel + D2H to about max(H2D, D2H).  A slab needs one plane of u beyond
+// each end (face neighbours), so the H2D pieces are shifted by one plane against the compute slabs.
+static int apply_host_pipelined(b200fem_operator* op, const double* u, double* w, bool linear, int nchunks) {
+  b200fem_space* s = op->sp; cudaStream_t st = s->mesh->ctx->stream; const BoxDev& b = s->box;
+  const int nz = b.n[2]; const size_t plane = (size_t)b.n[0] * b.n[1] * s->nb;
+  if (!op->h2d_stream) {
+    CUDA_OK(cudaStreamCreateWithFlags(&op->h2d_stream, cudaStreamNonBlocking)); CUDA_OK(cudaStreamCreateWithFlags(&op->d2h_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t& e : op->pipe_ev) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  if (!linear && op->model.data && op->kernel_pref != B200FEM_KERNEL_QUADRATURE) { int rc = ensure_bvec(op); if (rc) return rc; }
+  cudaEvent_t* ev_h = op->pipe_ev; cudaEvent_t* ev_c = op->pipe_ev + 16; cudaEvent_t ev_start = op->pipe_ev[32], ev_done = op->pipe_ev[33];
+  CUDA_OK(cudaEventRecord(ev_start, st)); CUDA_OK(cudaStreamWaitEvent(op->h2d_stream, ev_start, 0)); CUDA_OK(cudaStreamWaitEvent(op->d2h_stream, ev_start, 0));
+  int launches = 0;
+  for (int c = 0; c < nchunks; ++c) {
+    const int z0 = (int)((long long)nz * c / nchunks), z1 = (int)((long long)nz * (c + 1) / nchunks);
+    const int h0 = c == 0 ? 0 : z0 + 1, h1 = c == nchunks - 1 ? nz : z1 + 1;
+    CUDA_OK(cudaMemcpyAsync(op->d_u + h0 * plane, u + h0 * plane, sizeof(double) * (h1 - h0) * plane, cudaMemcpyHostToDevice, op->h2d_stream));
+    CUDA_OK(cudaEventRecord(ev_h[c], op->h2d_stream)); CUDA_OK(cudaStreamWaitEvent(st, ev_h[c], 0));
+    BoxDev sub = b; sub.own_lo[2] = z0; sub.own_hi[2] = z1;
+    op->active_box = &sub; const int rc = apply_local(op, op->d_u, op->d_w, linear); op->active_box = nullptr; if (rc) return rc;
+    launches += op->timing.launches_per_apply;
+    CUDA_OK(cudaEventRecord(ev_c[c], st)); CUDA_OK(cudaStreamWaitEvent(op->d2h_stream, ev_c[c], 0));
+    CUDA_OK(cudaMemcpyAsync(w + z0 * plane, op->d_w + z0 * plane, sizeof(double) * (z1 - z0) * plane, cudaMemcpyDeviceToHost, op->d2h_stream));
+  }
+  CUDA_OK(cudaEventRecord(ev_done, op->d2h_stream)); CUDA_OK(cudaStreamWaitEvent(st, ev_done, 0));
+  CUDA_OK(cudaStreamSynchronize(st));
+  op->timing.launches_per_apply = launches; op->timing.applies += 1;
+  return B200FEM_OK;
+}
 static int apply_host(b200fem_operator* op, const double* u, double* w, bool linear) {
   REQUIRE(op && u && w, B200FEM_ERR_INVALID, "apply: null argument");
   b200fem_space* s = op->sp; cudaStream_t st = s->mesh->ctx->stream; const size_t bytes = sizeof(double) * (size_t)s->size;
   CUDA_OK(cudaSetDevice(s->mesh->ctx->device));
   int rc = ensure_staging(op); if (rc) return rc;
+  const bool no_pipeline = std::getenv("B200FEM_NO_PIPELINE") != nullptr;     // (read per call: tests toggle it)
+  if (!no_pipeline && s->kind != B200FEM_LAGRANGE && s->mesh->ctx->world == 1 && s->box.dim == 3 && bytes >= (8u << 20) && s->box.n[2] >= 16 && default_quadrature(op))
+    return apply_host_pipelined(op, u, w, linear, std::min(8, s->box.n[2] / 4));
   CUDA_OK(cudaMemcpyAsync(op->d_u, u, bytes, cudaMemcpyHostToDevice, st));
   rc = apply_dev_impl(op, op->d_u, op->d_w, linear); if (rc) return rc;
   CUDA_OK(cudaMemcpyAsync(w, op->d_w, bytes, cudaMemcpyDeviceToHost, st));

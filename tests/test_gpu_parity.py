@@ -247,3 +247,23 @@ def test_full_size_c2_properties():
     ref = ol.Operator(osp, skeleton=True, boundary=True, threads=8, **kw).apply(u[:osp.size])
     m = 64 * 64 * 2 * 27
     assert rel(wk[:m], ref[:m]) < TOL
+
+
+@pytest.mark.parametrize("order,n", [(2, [32, 32, 40]), (3, [24, 24, 33])])
+def test_host_apply_pipeline_matches_single_copy(order, n, monkeypatch):
+    """b200fem_operator_apply overlaps H2D, compute and D2H over z-slabs for DG spaces: same bits as the plain path."""
+    space = fem.space.dglegendre(fem.structuredGrid([-1, -1, -1], [1, 1, 1], n), order=order, hierarchical=True)
+    assert space.size * 8 >= 8 << 20
+    kw = dict(eps=1e-3, b=(1.0, 0.3, -0.2), beta=20.0 * order ** 2, dirichlet_mask=0b000011, data=1)
+    u = np.random.default_rng(99).uniform(-1, 1, space.size)
+    op = fem.operator.galerkin(space, **kw)
+    w_pipe, w_plain = np.empty(space.size), np.empty(space.size)
+    op(u, w_pipe)
+    assert op.timing()["launches_per_apply"] >= 4          # one launch per slab
+    monkeypatch.setenv("B200FEM_NO_PIPELINE", "1")
+    op(u, w_plain)
+    assert np.array_equal(w_pipe, w_plain)
+    op.applyLinear(u, w_plain)
+    monkeypatch.delenv("B200FEM_NO_PIPELINE")
+    op.applyLinear(u, w_pipe)
+    assert np.array_equal(w_pipe, w_plain)
