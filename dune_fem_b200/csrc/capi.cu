@@ -524,6 +524,7 @@ template <int N> static int launch_lagrange(b200fem_operator* op, const double* 
 // Lagrange Kronecker (sum-factorised lattice stencil) kernel, lagrange_kronecker.cuh
 static int launch_lagrange_kronecker(b200fem_operator* op, const double* u, double* w, const double* bvec) {
   b200fem_space* s = op->sp; const BoxDev& b = s->box; const int k = s->order, W = 2 * k + 1;
+  REQUIRE(s->lay.lattice[0] * s->lay.lattice[1] * s->lay.lattice[2] < (1ll << 31) && s->size < (1ll << 31), B200FEM_ERR_NOT_IMPLEMENTED, "lattice kernel: 32-bit dof cursors");
   if (!op->d_lag_rows) {
     LagRowsHost rh = build_lagrange_rows(s->tab, op->model, b.dim, k, b.n, b.origin, b.gn, b.h);
     size_t total = 0; for (int d = 0; d < 3; ++d) total += 2 * rh.M[d].size();
@@ -535,13 +536,15 @@ static int launch_lagrange_kronecker(b200fem_operator* op, const double* u, doub
   }
   (void)W;
   const LagrangeLayoutDev& L = s->lay; const bool mapped = L.lattice_map != nullptr;
-  const int TX = 32 - 2 * k, TY = 16 - 2 * k;
+  static const char* hy_env = std::getenv("B200FEM_LAG_HY");
+  const int HY = hy_env ? std::atoi(hy_env) : 16, ctas_per_sm = HY <= 16 ? 2 : 1;
+  const int TX = 32 - 2 * k, TY = HY - 2 * k;
   const int tx = (int)((L.lattice[0] + TX - 1) / TX), ty = (int)((L.lattice[1] + TY - 1) / TY);
   // z-segments: every segment re-reads 2k planes and stages its z-rows (<= kMaxSeg planes); the number of segments is chosen
-  // so that the grid fills whole waves of the resident CTA slots (2 CTAs per SM)
+  // so that the grid fills whole waves of the resident CTA slots
   static int sms = 0;
   if (!sms) CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->mesh->ctx->device));
-  const int L2 = (int)L.lattice[2], slots = 2 * sms, tiles = tx * ty;
+  const int L2 = (int)L.lattice[2], slots = ctas_per_sm * sms, tiles = tx * ty;
   int best_nseg = 1; double best_cost = 1e300;
   for (int ns = 1; ns <= 64; ++ns) {
     const int zs = (L2 + ns - 1) / ns; if (zs > 128) continue;
@@ -553,8 +556,12 @@ static int launch_lagrange_kronecker(b200fem_operator* op, const double* u, doub
   const int zseg = (L2 + best_nseg - 1) / best_nseg, nseg = (L2 + zseg - 1) / zseg;
   const unsigned grid = (unsigned)(tiles * nseg); cudaStream_t st = s->mesh->ctx->stream;
   const unsigned char* dmask = op->fuse_dirichlet ? op->d_dmask : nullptr; const double* dvals = op->fuse_dirichlet && !op->fuse_linear ? op->d_dvals : nullptr;
-  if (k == 1) { if (mapped) lagrange_kronecker_kernel<1, true><<<grid, 512, 0, st>>>(L, op->lag_rows, u, w, bvec, dmask, dvals, tx, ty, zseg); else lagrange_kronecker_kernel<1, false><<<grid, 512, 0, st>>>(L, op->lag_rows, u, w, bvec, dmask, dvals, tx, ty, zseg); }
-  else        { if (mapped) lagrange_kronecker_kernel<2, true><<<grid, 512, 0, st>>>(L, op->lag_rows, u, w, bvec, dmask, dvals, tx, ty, zseg); else lagrange_kronecker_kernel<2, false><<<grid, 512, 0, st>>>(L, op->lag_rows, u, w, bvec, dmask, dvals, tx, ty, zseg); }
+#define B200FEM_LAGK(KK, MM, HH) lagrange_kronecker_kernel<KK, MM, HH><<<grid, 32 * HH, 0, st>>>(L, op->lag_rows, u, w, bvec, dmask, dvals, tx, ty, zseg)
+#define B200FEM_LAGK_HY(KK, MM) do { if (HY == 24) B200FEM_LAGK(KK, MM, 24); else B200FEM_LAGK(KK, MM, 16); } while (0)
+  if (k == 1) { if (mapped) B200FEM_LAGK_HY(1, true); else B200FEM_LAGK_HY(1, false); }
+  else        { if (mapped) B200FEM_LAGK_HY(2, true); else B200FEM_LAGK_HY(2, false); }
+#undef B200FEM_LAGK_HY
+#undef B200FEM_LAGK
   op->dirichlet_fused = op->fuse_dirichlet;
   CUDA_OK(cudaGetLastError());
   op->timing.launches_per_apply = 1;
