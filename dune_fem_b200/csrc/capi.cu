@@ -57,7 +57,7 @@ struct b200fem_space {
 };
 struct b200fem_operator {
   b200fem_space* sp; b200fem_model model; int kernel_pref = B200FEM_KERNEL_AUTO; bool communicate = true;
-  unsigned q_interior = 0, q_surface = 0;
+  unsigned q_interior = 0, q_surface = 0; bool inverse_mass = false;
   int* d_perm = nullptr; double* d_bvec = nullptr; uint8_t* d_dmask = nullptr; double* d_dvals = nullptr; uint8_t* d_aux = nullptr;
   std::vector<uint8_t> h_dmask; std::vector<double> h_dvals;
   double *d_u = nullptr, *d_w = nullptr;                       // staging for the host-pointer API
@@ -251,6 +251,12 @@ template <int N> static DgTabDev<N> make_tab(const Tab1D& t) {
 }
 static AdrIntegrands make_integrands(const b200fem_operator* op, bool with_data) { AdrIntegrands I; I.m = op->model; I.dim = op->sp->box.dim; I.with_data = with_data; return I; }
 
+// factor applied to every element result: 1, or referenceVolume / volume when the operator acts as MOLGalerkinOperator
+static double mass_scale(const b200fem_operator* op) {
+  if (!op->inverse_mass) return 1.0;
+  const BoxDev& b = op->sp->box; double vol = 1; for (int d = 0; d < b.dim; ++d) vol *= b.h[d];
+  return 1.0 / vol;
+}
 static bool default_quadrature(const b200fem_operator* op) {
   const int k = op->sp->order;
   const int mi = gauss_points_for_order(op->q_interior ? (int)op->q_interior : 2 * k), ms = gauss_points_for_order(op->q_surface ? (int)op->q_surface : 2 * k + 1);
@@ -263,12 +269,12 @@ template <int N> static int launch_dg_quadrature(b200fem_operator* op, const dou
   auto kern = dg_quadrature_kernel<N, AdrIntegrands>;
   CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes()));
   const unsigned grid = (unsigned)((n_owned + Cfg::EB - 1) / Cfg::EB);
-  kern<<<grid, Cfg::kThreads, Cfg::smem_bytes(), op->sp->mesh->ctx->stream>>>(make_tab<N>(op->sp->tab), b, make_integrands(op, with_data), op->d_perm, u, w, bvec, n_owned);
+  kern<<<grid, Cfg::kThreads, Cfg::smem_bytes(), op->sp->mesh->ctx->stream>>>(make_tab<N>(op->sp->tab), b, make_integrands(op, with_data), op->d_perm, u, w, bvec, n_owned, mass_scale(op));
   CUDA_OK(cudaGetLastError()); return B200FEM_OK;
 }
 template <int N, int TX, int TY, int TZ> static int launch_dg_kronecker(b200fem_operator* op, const double* u, double* w, const double* bvec) {
   using Cfg = KronCfg<N, TX, TY, TZ>; const BoxDev& b = op->active_box ? *op->active_box : op->sp->box;
-  KronHost kh = build_kron_tables(op->sp->tab, op->model, b.dim, b.h);
+  KronHost kh = build_kron_tables(op->sp->tab, op->model, b.dim, b.h, mass_scale(op));
   KronTabDev<N> K;
   for (int d = 0; d < 3; ++d) for (int i = 0; i < N * N; ++i) { K.S[d][i] = kh.S[d][i]; K.Dlo[d][i] = kh.Dlo[d][i]; K.Dhi[d][i] = kh.Dhi[d][i]; K.L[d][i] = kh.L[d][i]; K.R[d][i] = kh.R[d][i]; }
   const int tx = (b.own_hi[0] - b.own_lo[0] + TX - 1) / TX, ty = (b.own_hi[1] - b.own_lo[1] + TY - 1) / TY, tz = (b.own_hi[2] - b.own_lo[2] + TZ - 1) / TZ;
@@ -280,7 +286,7 @@ template <int N, int TX, int TY, int TZ> static int launch_dg_kronecker(b200fem_
 template <int N, bool HIER> static int launch_dg_kronecker_tma(b200fem_operator* op, const double* u, double* w, const double* bvec) {
   constexpr int TX = 8, TY = 4, TZ = 4;
   using Cfg = KronTmaCfg<N, TX, TY, TZ>; const BoxDev& b = op->active_box ? *op->active_box : op->sp->box;
-  KronHost kh = build_kron_tables(op->sp->tab, op->model, b.dim, b.h);
+  KronHost kh = build_kron_tables(op->sp->tab, op->model, b.dim, b.h, mass_scale(op));
   KronTabDev<N> K;
   for (int d = 0; d < 3; ++d) for (int i = 0; i < N * N; ++i) { K.S[d][i] = kh.S[d][i]; K.Dlo[d][i] = kh.Dlo[d][i]; K.Dhi[d][i] = kh.Dhi[d][i]; K.L[d][i] = kh.L[d][i]; K.R[d][i] = kh.R[d][i]; }
   const int tx = (b.own_hi[0] - b.own_lo[0] + TX - 1) / TX, ty = (b.own_hi[1] - b.own_lo[1] + TY - 1) / TY, tz = (b.own_hi[2] - b.own_lo[2] + TZ - 1) / TZ;
@@ -319,7 +325,7 @@ template <int N, bool HIER, bool SPLIT> static int launch_dg_kronecker_tensor(b2
   constexpr int TX = 8, TY = 4, TZ = 4, N3 = N * N * N;
   using Cfg = KronTensorCfg<N, TX, TY, TZ, SPLIT>; const BoxDev& b = op->active_box ? *op->active_box : op->sp->box;
   if (!op->kron_ready) {
-    KronHost kh = build_kron_tables(op->sp->tab, op->model, b.dim, b.h);
+    KronHost kh = build_kron_tables(op->sp->tab, op->model, b.dim, b.h, mass_scale(op));
     op->kron_tab.resize(sizeof(KronTabDev<N>));
     KronTabDev<N>& K0 = *reinterpret_cast<KronTabDev<N>*>(op->kron_tab.data());
     for (int d = 0; d < 3; ++d) for (int i = 0; i < N * N; ++i) { K0.S[d][i] = kh.S[d][i]; K0.Dlo[d][i] = kh.Dlo[d][i]; K0.Dhi[d][i] = kh.Dhi[d][i]; K0.L[d][i] = kh.L[d][i]; K0.R[d][i] = kh.R[d][i]; }
@@ -391,7 +397,7 @@ template <int N, bool HIER> static int launch_dg_kronecker_march(b200fem_operato
   constexpr int TX = 16, TY = 16, N3 = N * N * N;
   using Cfg = KronMarchCfg<N, TX, TY>; const BoxDev& b = op->active_box ? *op->active_box : op->sp->box;
   if (!op->kron_ready) {
-    KronHost kh = build_kron_tables(op->sp->tab, op->model, b.dim, b.h);
+    KronHost kh = build_kron_tables(op->sp->tab, op->model, b.dim, b.h, mass_scale(op));
     op->kron_tab.resize(sizeof(KronTabDev<N>));
     KronTabDev<N>& K0 = *reinterpret_cast<KronTabDev<N>*>(op->kron_tab.data());
     for (int d = 0; d < 3; ++d) for (int i = 0; i < N * N; ++i) { K0.S[d][i] = kh.S[d][i]; K0.Dlo[d][i] = kh.Dlo[d][i]; K0.Dhi[d][i] = kh.Dhi[d][i]; K0.L[d][i] = kh.L[d][i]; K0.R[d][i] = kh.R[d][i]; }
@@ -455,7 +461,7 @@ template <int N, bool HIER> static int launch_dg_kronecker_march(b200fem_operato
 template <int N, int TX, int TY, int TZ, int MINB> static int launch_dg_kronecker_slab(b200fem_operator* op, const double* u, double* w, const double* bvec) {
   using Cfg = KronSlabCfg<N, TX, TY, TZ>; const BoxDev& b = op->active_box ? *op->active_box : op->sp->box;
   if (!op->kron_ready) {
-    KronHost kh = build_kron_tables(op->sp->tab, op->model, b.dim, b.h);
+    KronHost kh = build_kron_tables(op->sp->tab, op->model, b.dim, b.h, mass_scale(op));
     op->kron_tab.resize(sizeof(KronTabDev<N>));
     KronTabDev<N>& K0 = *reinterpret_cast<KronTabDev<N>*>(op->kron_tab.data());
     for (int d = 0; d < 3; ++d) for (int i = 0; i < N * N; ++i) { K0.S[d][i] = kh.S[d][i]; K0.Dlo[d][i] = kh.Dlo[d][i]; K0.Dhi[d][i] = kh.Dhi[d][i]; K0.L[d][i] = kh.L[d][i]; K0.R[d][i] = kh.R[d][i]; }
@@ -474,7 +480,7 @@ static long long* g_dbg = nullptr; static int g_dbg_calls = 0;
 template <int N, bool HIER, bool SPLIT> static int launch_dg_kronecker_pipe(b200fem_operator* op, const double* u, double* w, const double* bvec) {
   constexpr int TX = 8, TY = 4, TZ = 4;
   using Cfg = KronPipeCfg<N, TX, TY, TZ, SPLIT>; const BoxDev& b = op->active_box ? *op->active_box : op->sp->box;
-  KronHost kh = build_kron_tables(op->sp->tab, op->model, b.dim, b.h);
+  KronHost kh = build_kron_tables(op->sp->tab, op->model, b.dim, b.h, mass_scale(op));
   KronTabDev<N> K;
   for (int d = 0; d < 3; ++d) for (int i = 0; i < N * N; ++i) { K.S[d][i] = kh.S[d][i]; K.Dlo[d][i] = kh.Dlo[d][i]; K.Dhi[d][i] = kh.Dhi[d][i]; K.L[d][i] = kh.L[d][i]; K.R[d][i] = kh.R[d][i]; }
   const int tx = (b.own_hi[0] - b.own_lo[0] + TX - 1) / TX, ty = (b.own_hi[1] - b.own_lo[1] + TY - 1) / TY, tz = (b.own_hi[2] - b.own_lo[2] + TZ - 1) / TZ;
@@ -904,6 +910,17 @@ extern "C" int b200fem_operator_load_vector(b200fem_operator* op, double* b_host
 extern "C" int b200fem_operator_set_communicate(b200fem_operator* op, int c) { REQUIRE(op, B200FEM_ERR_INVALID, "null"); op->communicate = c != 0; return B200FEM_OK; }
 extern "C" int b200fem_operator_set_quadrature_orders(b200fem_operator* op, unsigned qi, unsigned qs) { REQUIRE(op, B200FEM_ERR_INVALID, "null"); op->q_interior = qi; op->q_surface = qs; return B200FEM_OK; }
 extern "C" int b200fem_operator_set_kernel(b200fem_operator* op, int k) { REQUIRE(op && k >= 0 && k <= 2, B200FEM_ERR_INVALID, "set_kernel: bad kernel id"); op->kernel_pref = k; return B200FEM_OK; }
+extern "C" int b200fem_operator_set_inverse_mass(b200fem_operator* op, int on) {
+  REQUIRE(op, B200FEM_ERR_INVALID, "null");
+  REQUIRE(op->sp->kind != B200FEM_LAGRANGE, B200FEM_ERR_NOT_IMPLEMENTED, "inverse mass (MOLGalerkinOperator): DG spaces only");
+  if (op->inverse_mass == (on != 0)) return B200FEM_OK;
+  op->inverse_mass = on != 0;
+  // the scaled 1-D operators and the scaled load vector are rebuilt on the next apply
+  op->kron_ready = false;
+  if (op->d_bvec) { CUDA_OK(cudaSetDevice(op->sp->mesh->ctx->device)); CUDA_OK(cudaStreamSynchronize(op->sp->mesh->ctx->stream)); CUDA_OK(cudaFree(op->d_bvec)); op->d_bvec = nullptr; }
+  if (op->cg_graph) { cudaGraphExecDestroy(op->cg_graph); op->cg_graph = nullptr; }
+  return B200FEM_OK;
+}
 extern "C" int b200fem_operator_dirichlet(b200fem_operator* op, uint8_t* mask, double* values) {
   REQUIRE(op && mask && values, B200FEM_ERR_INVALID, "null");
   if (op->h_dmask.empty()) { std::fill(mask, mask + op->sp->size, 0); return B200FEM_OK; }

@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(DgQuadCfg<N>::kThreads)
 dg_quadrature_kernel(const __grid_constant__ DgTabDev<N> T, const __grid_constant__ BoxDev box,
                      const __grid_constant__ Integrands I, const int* __restrict__ perm_g,
                      const double* __restrict__ u, double* __restrict__ w, const double* __restrict__ bvec,
-                     long long n_owned) {
+                     long long n_owned, const double out_scale) {
   using Cfg = DgQuadCfg<N>;
   constexpr int N2 = Cfg::N2, N3 = Cfg::N3, EB = Cfg::EB, ELEM = Cfg::kElemDoubles;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -320,7 +320,7 @@ dg_quadrature_kernel(const __grid_constant__ DgTabDev<N> T, const __grid_constan
   for (int idx = tid; idx < EB * N3; idx += blockDim.x) {
     const int s2 = idx / N3, j = idx % N3; const long long e2 = elem_of[s2];
     if (e2 >= 0) {
-      double val = smem[(size_t)s2 * ELEM + N3 + tinv[j]];
+      double val = smem[(size_t)s2 * ELEM + N3 + tinv[j]] * out_scale;      // out_scale: inverse mass of MOLGalerkinOperator (1 otherwise)
       if (bvec) val -= bvec[e2 * N3 + j];
       w[e2 * N3 + j] = val;
     }

@@ -17,7 +17,8 @@ struct KronHost {
   std::vector<double> S[3], Dlo[3], Dhi[3], L[3], R[3];   // n*n each, row = test index, col = trial index
 };
 
-inline KronHost build_kron_tables(const Tab1D& t, const b200fem_model& m, int dim, const double* h) {
+// `scale` multiplies every matrix (inverse mass of MOLGalerkinOperator: 1 / detJ)
+inline KronHost build_kron_tables(const Tab1D& t, const b200fem_model& m, int dim, const double* h, double scale = 1.0) {
   KronHost k; const int n = t.n; k.n = n;
   double detJ = 1; for (int d = 0; d < dim; ++d) detJ *= h[d];
   // 1-D quadrature matrices
@@ -48,11 +49,11 @@ inline KronHost build_kron_tables(const Tab1D& t, const b200fem_model& m, int di
         if ((m.dirichlet_mask >> (2 * d + 1)) & 1) BH = area * (pen + hbp) * p1i * p1j;
         if ((m.dirichlet_mask >> (2 * d)) & 1)     BL = area * (pen + hbm) * p0i * p0j;
       }
-      k.S[d][i * n + j] = vol + HH + LL;
-      k.Dhi[d][i * n + j] = BH - HH;
-      k.Dlo[d][i * n + j] = BL - LL;
-      k.L[d][i * n + j] = Lm;
-      k.R[d][i * n + j] = Rm;
+      k.S[d][i * n + j] = scale * (vol + HH + LL);
+      k.Dhi[d][i * n + j] = scale * (BH - HH);
+      k.Dlo[d][i * n + j] = scale * (BL - LL);
+      k.L[d][i * n + j] = scale * Lm;
+      k.R[d][i * n + j] = scale * Rm;
     }
   }
   return k;

@@ -139,6 +139,16 @@ class GalerkinOperator : public Operator<DiscreteFunctionT, DiscreteFunctionT> {
   const DiscreteFunctionSpaceType& space_; Integrands integrands_; b200fem_operator* h_ = nullptr;
 };
 
+// Dune::Fem::MOLGalerkinOperator (schemes/molgalerkin.hh:37-209): same constructor and interface, applies the inverse local
+// mass matrix after the evaluate (w = M^-1 L[u])
+template <class DiscreteFunctionT>
+class MOLGalerkinOperator : public GalerkinOperator<DiscreteFunctionT> {
+ public:
+  typedef typename DiscreteFunctionT::DiscreteFunctionSpaceType DiscreteFunctionSpaceType;
+  MOLGalerkinOperator(const DiscreteFunctionSpaceType& dSpace, const DiscreteFunctionSpaceType& rSpace, const Integrands& integrands)
+      : GalerkinOperator<DiscreteFunctionT>(dSpace, rSpace, integrands) { check(b200fem_operator_set_inverse_mass(this->handle(), 1)); }
+};
+
 // Dune::Fem::CgInverseOperator = KrylovInverseOperator< DF, SolverParameter::cg > (solver/krylovinverseoperators.hh:46-281)
 struct SolverParameter {                       // solver/parameter.hh:21-295, keys fem.solver.*
   double tolerance = 1e-8; int errorMeasure = B200FEM_TOL_ABSOLUTE; int maxIterations = 1000; bool verbose = false;

@@ -73,6 +73,9 @@ class GalerkinOperator:
         capi.check(capi.lib().b200fem_dot_dev(self.handle, C.c_void_p(x_ptr), C.c_void_p(y_ptr), C.byref(r)))
         return r.value
 
+    def setInverseMass(self, on=True):
+        capi.check(capi.lib().b200fem_operator_set_inverse_mass(self.handle, int(on)))
+
     def communicate_dev(self, v_ptr):
         capi.check(capi.lib().b200fem_communicate_dev(self.handle, C.c_void_p(v_ptr)))
 
@@ -89,3 +92,11 @@ class GalerkinOperator:
 
 def galerkin(space, **kwargs):
     return GalerkinOperator(space, **kwargs)
+
+
+def molGalerkin(space, **kwargs):
+    """dune.fem.operator.molGalerkin (python/dune/fem/operator/__init__.py:203-207): Dune::Fem::MOLGalerkinOperator
+    (schemes/molgalerkin.hh), i.e. w = M^-1 L[u] -- the operator explicit time stepping applies.  DG spaces only."""
+    op = GalerkinOperator(space, **kwargs)
+    op.setInverseMass(True)
+    return op

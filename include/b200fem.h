@@ -121,6 +121,12 @@ int b200fem_operator_load_vector(b200fem_operator* op, double* b_host);
 int b200fem_operator_set_communicate(b200fem_operator* op, int communicate);                    /* galerkin.hh:1409 */
 int b200fem_operator_set_quadrature_orders(b200fem_operator* op, unsigned interior, unsigned surface); /* :1418-1423 */
 int b200fem_operator_set_kernel(b200fem_operator* op, int kernel);
+/* MOLGalerkinOperator (schemes/molgalerkin.hh:100-124, 162-197; python molGalerkin, operator/__init__.py:203-207): apply the
+ * inverse of the local mass matrix after the evaluate, w = M^-1 L[u] -- the form explicit time stepping uses.  For the
+ * orthonormal Legendre bases on affine cells this is the scalar referenceVolume / volume per element
+ * (operator/1order/localmassmatrix.hh:304-311, 421-434), fused into the kernels (scaled 1-D operators and load vector).
+ * DG spaces only (B200FEM_ERR_NOT_IMPLEMENTED otherwise). */
+int b200fem_operator_set_inverse_mass(b200fem_operator* op, int on);
 /* strong Dirichlet marks and values (schemes/dirichletconstraints.hh:435-554) */
 int b200fem_operator_dirichlet(b200fem_operator* op, uint8_t* mask_host, double* values_host);
 int b200fem_operator_timing(b200fem_operator* op, b200fem_timing* out);

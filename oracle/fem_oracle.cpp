@@ -415,6 +415,7 @@ static Range boundaryIntegrand(const Model& m, int dim, int axis, int side, doub
 // ---------------------------------------------------------------------------
 struct Operator {
   const Space& sp; Model model; int threads = 1;
+  bool inverseMass = false;   // MOLGalerkinOperator: applyInverseMass after the evaluate (schemes/molgalerkin.hh:100-124, 162-168)
   std::vector<uint8_t> dirichletDof;      // strong Dirichlet marks (dirichletconstraints.hh:435-554)
   std::vector<double> dirichletValue;     // g at the marked Lagrange nodes
   Operator(const Space& s, const Model& m) : sp(s), model(m) { if (model.strongDirichlet) markDirichlet(); }
@@ -568,6 +569,12 @@ struct Operator {
       });
       for (auto& th : pool) th.join();
     }
+    if (inverseMass) {
+      // LocalMassMatrix::applyInverse on affine cells with an orthonormal DG basis: lf[l] *= referenceVolume / volume
+      // (operator/1order/localmassmatrix.hh:304-311, 421-434); element loop of molgalerkin.hh:108-123
+      const double massVolInv = 1.0 / M.detJ();
+      for (int64_t e = 0; e < M.nelem; ++e) { int c[3]; M.elemCoords(e, c); if (own && !own->contains(c)) continue; for (int l = 0; l < nb; ++l) w[e*nb + l] *= massVolInv; }
+    }
     if (model.strongDirichlet)                                                     // subConstraints: w_d = u_d - g_d
       for (int64_t i = 0; i < sp.size; ++i) if (dirichletDof[(size_t)i]) w[i] = u[i] - dirichletValue[(size_t)i];
   }
@@ -644,6 +651,11 @@ FoOperator* fo_operator_create(FoSpace* s, const double* params, const int* ipar
 }
 void fo_operator_destroy(FoOperator* op) { delete op; }
 void fo_operator_set_threads(FoOperator* op, int t) { op->full->threads = t; op->linear->threads = t; }
+// MOLGalerkinOperator (schemes/molgalerkin.hh): w = M^-1 L[u]; DG spaces only
+int fo_operator_set_inverse_mass(FoOperator* op, int on) {
+  if (op->space->sp->kind == LAGRANGE) return -1;
+  op->full->inverseMass = on != 0; op->linear->inverseMass = on != 0; return 0;
+}
 // L[u] (affine) or its homogeneous part A u (linear != 0)
 void fo_operator_apply(FoOperator* op, const double* u, double* w, int linear) { (linear ? op->linear : op->full)->apply(u, w); }
 // apply restricted to the owned element box [lo,hi); other elements act as ghosts (rank-local apply)

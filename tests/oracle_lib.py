@@ -50,6 +50,8 @@ def lib():
     L.fo_operator_create.argtypes = [C.c_void_p, _dp, _ip]
     L.fo_operator_destroy.argtypes = [C.c_void_p]
     L.fo_operator_set_threads.argtypes = [C.c_void_p, C.c_int]
+    L.fo_operator_set_inverse_mass.argtypes = [C.c_void_p, C.c_int]
+    L.fo_operator_set_inverse_mass.restype = C.c_int
     L.fo_operator_apply.argtypes = [C.c_void_p, _dp, _dp, C.c_int]
     L.fo_operator_apply_box.argtypes = [C.c_void_p, _dp, _dp, C.c_int, _ip, _ip]
     L.fo_dirichlet.argtypes = [C.c_void_p, _bp, _dp]
@@ -125,6 +127,11 @@ class Operator:
         self._h = lib().fo_operator_create(space._h, params, iparams)
         if threads > 1:
             lib().fo_operator_set_threads(self._h, threads)
+
+    def setInverseMass(self, on=True):
+        """MOLGalerkinOperator: w = M^-1 L[u] (schemes/molgalerkin.hh)"""
+        if lib().fo_operator_set_inverse_mass(self._h, int(on)) != 0:
+            raise ValueError("inverse mass: DG spaces only")
 
     def apply(self, u, linear=False):
         w = np.empty(self.space.size)

@@ -267,3 +267,32 @@ def test_host_apply_pipeline_matches_single_copy(order, n, monkeypatch):
     monkeypatch.delenv("B200FEM_NO_PIPELINE")
     op.applyLinear(u, w_pipe)
     assert np.array_equal(w_pipe, w_plain)
+
+
+@pytest.mark.parametrize("order,hier", [(1, True), (2, True), (2, False), (3, True), (5, True)])
+def test_mol_galerkin_inverse_mass(order, hier):
+    """MOLGalerkinOperator (schemes/molgalerkin.hh): w = M^-1 L[u], both device kernels against the oracle."""
+    n = [6, 4, 5] if order <= 3 else [3, 2, 2]
+    space, osp = dg_pair(n, [-1, -1, -1], [1, 0.5, 2.0], order, hier)
+    kw = dict(eps=0.2, b=(1.0, 0.25, -0.5), c=0.3, dirichlet_mask=0b110011, data=1, beta=20.0 * order ** 2)
+    u = np.random.default_rng(17).uniform(-1, 1, space.size)
+    oop = ol.Operator(osp, skeleton=True, boundary=True, **kw)
+    plain = oop.apply(u)
+    oop.setInverseMass(True)
+    ref, ref_lin = oop.apply(u), oop.apply(u, linear=True)
+    detJ = (2.0 / n[0]) * (1.5 / n[1]) * (3.0 / n[2])
+    assert rel(ref, plain / detJ) < 1e-14                    # orthonormal basis on affine cells: a scalar per element
+    w = np.empty(space.size)
+    for kernel in (_capi.KERNEL_QUADRATURE, _capi.KERNEL_KRONECKER):
+        op = fem.operator.molGalerkin(space, kernel=kernel, **kw)
+        op(u, w)
+        assert rel(w, ref) < TOL
+        op.applyLinear(u, w)
+        assert rel(w, ref_lin) < TOL
+        op.setInverseMass(False)                             # back to the plain Galerkin operator (tables and b are rebuilt)
+        op(u, w)
+        assert rel(w, plain) < TOL
+    lsp = fem.space.lagrange(fem.structuredGrid([0, 0, 0], [1, 1, 1], [2, 2, 2]), order=1)
+    with pytest.raises(_capi.B200FemError) as ei:
+        fem.operator.molGalerkin(lsp)
+    assert ei.value.code == _capi.ERR_NOT_IMPLEMENTED

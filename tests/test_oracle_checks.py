@@ -147,3 +147,18 @@ def test_cg_sign_conventions_and_negative_count():
     r = op.apply(x2, linear=True) - b
     assert np.linalg.norm(r) <= 1e-10 * 1.01
     np.testing.assert_allclose(hist2[:3], hist, rtol=1e-14)
+
+
+def test_mol_inverse_mass_is_projection_scaling():
+    """MOLGalerkinOperator (schemes/molgalerkin.hh:100-124): with the mass integrand L[u] = (u, v) the method-of-lines
+    operator M^-1 L is the identity on a DG Legendre space -- the check that pins `referenceVolume / volume`
+    (operator/1order/localmassmatrix.hh:304-311) in the oracle."""
+    n, lo, hi = [3, 4, 2], [-1.0, 0.0, 0.5], [1.0, 3.0, 1.0]
+    sp = ol.Space(n, lo, hi, ol.DG_LEGENDRE_HIER, 2)
+    u = np.random.default_rng(2).uniform(-1, 1, sp.size)
+    op = ol.Operator(sp, eps=0.0, c=1.0)
+    op.setInverseMass(True)
+    np.testing.assert_allclose(op.apply(u), u, rtol=0, atol=1e-13)
+    lsp = ol.Space([2, 2], [0, 0], [1, 1], ol.LAGRANGE, 1)
+    with pytest.raises(ValueError):
+        ol.Operator(lsp).setInverseMass(True)
