@@ -63,6 +63,7 @@ struct b200fem_operator {
   double *d_u = nullptr, *d_w = nullptr;                       // staging for the host-pointer API
   double *d_h = nullptr, *d_r = nullptr, *d_p = nullptr, *d_x = nullptr, *d_b = nullptr, *d_partial = nullptr, *d_sums = nullptr, *d_hist = nullptr;
   CgState* d_cg = nullptr; int hist_cap = 0; unsigned int* d_counter = nullptr;
+  double *d_rstar = nullptr, *d_s = nullptr, *d_tmp = nullptr, *d_partial5 = nullptr, *d_sums5 = nullptr; BicgState* d_bicg = nullptr;   // BiCGStab work vectors
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr; cudaEvent_t pipe_ev[2 * 16 + 2] = {};   // host-pointer apply: copy/compute pipeline
   cudaGraphExec_t cg_graph = nullptr; const void* cg_graph_key[3] = {nullptr, nullptr, nullptr}; bool capturing = false;
   bool kron_ready = false; int kron_chk = -1; bool fuse_dirichlet = false, fuse_linear = false, dirichlet_fused = false; double* d_lag_rows = nullptr; LagKronRows lag_rows{}; std::vector<unsigned char> kron_tab; struct KronMapCache* map_cache = nullptr; struct MarchMapCache* march_cache = nullptr;
@@ -825,7 +826,7 @@ static void free_map_cache(b200fem_operator* op) { delete op->map_cache; op->map
 extern "C" int b200fem_operator_destroy(b200fem_operator* op) {
   if (!op) return B200FEM_OK;
   for (void* p : {(void*)op->d_perm, (void*)op->d_bvec, (void*)op->d_dmask, (void*)op->d_dvals, (void*)op->d_aux, (void*)op->d_u, (void*)op->d_w, (void*)op->d_h, (void*)op->d_r,
-                  (void*)op->d_p, (void*)op->d_x, (void*)op->d_b, (void*)op->d_partial, (void*)op->d_sums, (void*)op->d_hist, (void*)op->d_cg, (void*)op->d_lag_rows, (void*)op->d_counter}) if (p) cudaFree(p);
+                  (void*)op->d_p, (void*)op->d_x, (void*)op->d_b, (void*)op->d_partial, (void*)op->d_sums, (void*)op->d_hist, (void*)op->d_cg, (void*)op->d_lag_rows, (void*)op->d_counter, (void*)op->d_rstar, (void*)op->d_s, (void*)op->d_tmp, (void*)op->d_partial5, (void*)op->d_sums5, (void*)op->d_bicg}) if (p) cudaFree(p);
   if (op->cg_graph) cudaGraphExecDestroy(op->cg_graph);
   halo_plan_p2p_free(op->halo_p2p); halo_plan_free(op->halo); halo_plan_dg_free(op->halo_dg); free_map_cache(op);
   if (op->comm_stream) cudaStreamDestroy(op->comm_stream);
@@ -1041,6 +1042,66 @@ extern "C" int b200fem_cg_solve(b200fem_operator* op, const double* b_host, doub
   if (!op->d_x) { CUDA_OK(cudaMalloc(&op->d_x, bytes)); CUDA_OK(cudaMalloc(&op->d_b, bytes)); }
   CUDA_OK(cudaMemcpyAsync(op->d_x, x_host, bytes, cudaMemcpyHostToDevice, st)); CUDA_OK(cudaMemcpyAsync(op->d_b, b_host, bytes, cudaMemcpyHostToDevice, st));
   int rc = b200fem_cg_solve_dev(op, op->d_b, op->d_x, epsilon, maxit, tolcrit, iterations, history); if (rc) return rc;
+  CUDA_OK(cudaMemcpyAsync(x_host, op->d_x, bytes, cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st));
+  return B200FEM_OK;
+}
+
+// LinearSolver::bicgstab (solver/linear/bicgstab.hh:64-214), unpreconditioned, on the homogeneous linear part of the operator
+extern "C" int b200fem_bicgstab_solve_dev(b200fem_operator* op, const double* b, double* x, double epsilon, int maxit, int tolcrit, int* iterations, double* history) {
+  REQUIRE(op && b && x && iterations, B200FEM_ERR_INVALID, "bicgstab: null argument");
+  REQUIRE(tolcrit >= 0 && tolcrit <= 2, B200FEM_ERR_INVALID, "bicgstab: unknown tolerance criterion");
+  b200fem_space* s = op->sp; b200fem_ctx* c = s->mesh->ctx; cudaStream_t st = c->stream; const long long n = s->size;
+  CUDA_OK(cudaSetDevice(c->device));
+  int rc = ensure_cg_buffers(op, std::max(maxit, 1)); if (rc) return rc;
+  const size_t bytes = sizeof(double) * (size_t)n;
+  if (!op->d_rstar) {
+    CUDA_OK(cudaMalloc(&op->d_rstar, bytes)); CUDA_OK(cudaMalloc(&op->d_s, bytes)); CUDA_OK(cudaMalloc(&op->d_tmp, bytes));
+    CUDA_OK(cudaMalloc(&op->d_partial5, sizeof(double) * 5 * kRedBlocks)); CUDA_OK(cudaMalloc(&op->d_sums5, sizeof(double) * 8)); CUDA_OK(cudaMalloc(&op->d_bicg, sizeof(BicgState)));
+  }
+  double* r = op->d_r; double* p = op->d_p; double* rstar = op->d_rstar; double* sv = op->d_s; double* tmp = op->d_tmp;
+  BicgState init{}; init.epsilon = epsilon; init.max_iterations = maxit; init.tol_criteria = tolcrit;
+  CUDA_OK(cudaMemcpyAsync(op->d_bicg, &init, sizeof(BicgState), cudaMemcpyHostToDevice, st));
+  rc = apply_dev_impl(op, x, r, true); if (rc) return rc;                                                      // r = A x
+  bicg_init_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(r, b, p, rstar, op->d_aux, n, op->d_partial, op->d_partial + kRedBlocks);
+  rc = reduce_sums(op, 2); if (rc) return rc;
+  bicg_init_final_kernel<<<1, 32, 0, st>>>(op->d_sums, op->d_bicg);
+  const bool single = c->world == 1;
+  BicgState host{}; const int chunk = 8; int issued = 0;
+  do {
+    for (int k = 0; k < chunk; ++k, ++issued) {
+      rc = apply_dev_impl(op, p, tmp, true); if (rc) return rc;                                                // tmp = A p
+      if (single) bicg_dot_alpha_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(tmp, rstar, op->d_aux, n, op->d_partial, op->d_bicg, op->d_counter);
+      else {
+        bicg_dot_alpha_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(tmp, rstar, op->d_aux, n, op->d_partial, op->d_bicg, nullptr);
+        rc = reduce_sums(op, 1); if (rc) return rc;
+        bicg_alpha_kernel<<<1, 32, 0, st>>>(op->d_sums, op->d_bicg);
+      }
+      bicg_s_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(sv, r, tmp, n, op->d_bicg);
+      rc = apply_dev_impl(op, sv, r, true); if (rc) return rc;                                                 // r = A s
+      if (single) bicg_dots5_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(r, sv, rstar, op->d_aux, n, op->d_partial5, op->d_bicg, op->d_hist, op->d_counter + 1);
+      else {
+        bicg_dots5_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(r, sv, rstar, op->d_aux, n, op->d_partial5, op->d_bicg, op->d_hist, nullptr);
+        for (int q = 0; q < 5; ++q) reduce_final_kernel<<<1, kRedThreads, 0, st>>>(op->d_partial5 + (size_t)q * kRedBlocks, kRedBlocks, op->d_sums5 + q);
+        if (c->nccl.AllReduce(op->d_sums5, op->d_sums5, 5, /*ncclDouble*/ 8, /*ncclSum*/ 0, c->comm, st) != 0) return fail(B200FEM_ERR_COMM, "ncclAllReduce failed");
+        bicg_scalars_kernel<<<1, 32, 0, st>>>(op->d_sums5, op->d_bicg, op->d_hist);
+      }
+      bicg_update_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(x, r, p, sv, tmp, n, op->d_bicg, op->d_counter);
+    }
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpyAsync(&host, op->d_bicg, sizeof(BicgState), cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st));
+  } while (!host.done);
+  REQUIRE(std::isfinite(host.res), B200FEM_ERR_INVALID, "bicgstab: residual is not finite (breakdown: <tmp,r*> or <r,r> vanished)");
+  if (history && host.iterations > 0) { CUDA_OK(cudaMemcpyAsync(history, op->d_hist, sizeof(double) * host.iterations, cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st)); }
+  *iterations = (host.iterations >= maxit) ? -host.iterations : host.iterations;                               // bicgstab.hh:208-211
+  return B200FEM_OK;
+}
+extern "C" int b200fem_bicgstab_solve(b200fem_operator* op, const double* b_host, double* x_host, double epsilon, int maxit, int tolcrit, int* iterations, double* history) {
+  REQUIRE(op && b_host && x_host && iterations, B200FEM_ERR_INVALID, "bicgstab: null argument");
+  b200fem_space* s = op->sp; cudaStream_t st = s->mesh->ctx->stream; const size_t bytes = sizeof(double) * (size_t)s->size;
+  CUDA_OK(cudaSetDevice(s->mesh->ctx->device));
+  if (!op->d_x) { CUDA_OK(cudaMalloc(&op->d_x, bytes)); CUDA_OK(cudaMalloc(&op->d_b, bytes)); }
+  CUDA_OK(cudaMemcpyAsync(op->d_x, x_host, bytes, cudaMemcpyHostToDevice, st)); CUDA_OK(cudaMemcpyAsync(op->d_b, b_host, bytes, cudaMemcpyHostToDevice, st));
+  int rc = b200fem_bicgstab_solve_dev(op, op->d_b, op->d_x, epsilon, maxit, tolcrit, iterations, history); if (rc) return rc;
   CUDA_OK(cudaMemcpyAsync(x_host, op->d_x, bytes, cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st));
   return B200FEM_OK;
 }

@@ -181,6 +181,92 @@ __global__ void __launch_bounds__(kRedThreads) cg_update_xr_residual_kernel(doub
   }
 }
 
+// ---- BiCGStab (solver/linear/bicgstab.hh:64-214, unpreconditioned; five-fold scalar product of :19-52) ----
+// Scalars live on the device; an iteration is  [tmp = A p] [<tmp,r*> -> alpha] [s = r - alpha tmp] [r = A s]
+// [5 dots -> omega, res, beta, nu, convergence] [x += alpha p + omega s ; r = s - omega r ; p = r + beta (p - omega tmp)].
+struct BicgState {
+  double nu, alpha, omega, beta, res, tolerance, bnorm2;
+  int iterations, done, max_iterations, tol_criteria, x_applied;
+  double epsilon;
+};
+// r = b - r ; p = r ; r* = r ; partial <r,r*> and <b,b>                    (bicgstab.hh:94-122)
+__global__ void __launch_bounds__(kRedThreads) bicg_init_kernel(double* __restrict__ r, const double* __restrict__ b, double* __restrict__ p, double* __restrict__ rstar,
+                                                                const uint8_t* __restrict__ aux, long long n, double* __restrict__ partial, double* __restrict__ partial_b) {
+  double s = 0, sb = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double bv = b[i], rv = -r[i] + bv;
+    r[i] = rv; p[i] = rv; rstar[i] = rv;
+    if (!aux || !aux[i]) { s = fma(rv, rv, s); sb = fma(bv, bv, sb); }
+  }
+  s = block_sum(s); if (threadIdx.x == 0) partial[blockIdx.x] = s;
+  sb = block_sum(sb); if (threadIdx.x == 0) partial_b[blockIdx.x] = sb;
+}
+__global__ void bicg_init_final_kernel(const double* __restrict__ sums, BicgState* st) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    st->nu = sums[0]; st->bnorm2 = sums[1];
+    st->tolerance = st->epsilon * (st->tol_criteria == 1 ? sqrt(sums[1]) : st->tol_criteria == 2 ? sqrt(sums[0]) : 1.0);
+    st->iterations = 0; st->x_applied = 0; st->done = 0;        // the reference tests convergence only after an iteration
+  }
+}
+__device__ __forceinline__ void bicg_scalars(const double* gd, BicgState* st, double* history) {     // bicgstab.hh:166-183
+  const double omega = gd[0] / gd[1];
+  const double res = sqrt(gd[2] - omega * (2.0 * gd[0] - omega * gd[1]));
+  const double nu_new = gd[3] - omega * gd[4];
+  st->beta = nu_new * st->alpha / (omega * st->nu); st->nu = nu_new; st->omega = omega; st->res = res;
+  if (history) history[st->iterations] = res;
+  st->iterations += 1;
+  if (res < st->tolerance || st->iterations >= st->max_iterations || !(res == res)) st->done = 1;
+}
+// partial <tmp, r*>; single rank: the last block computes alpha = nu / <tmp,r*>
+__global__ void __launch_bounds__(kRedThreads) bicg_dot_alpha_kernel(const double* __restrict__ tmp, const double* __restrict__ rstar, const uint8_t* __restrict__ aux,
+                                                                     long long n, double* partial, BicgState* st, unsigned int* counter) {
+  if (st->done) return;
+  double s = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    if (!aux || !aux[i]) s = fma(tmp[i], rstar[i], s);
+  s = block_sum(s);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+  if (!counter || !last_block_done(counter)) return;
+  const double t = final_sum(partial);
+  if (threadIdx.x == 0) { st->alpha = st->nu / t; *counter = 0; }
+}
+__global__ void bicg_alpha_kernel(const double* __restrict__ sums, BicgState* st) { if (threadIdx.x == 0 && blockIdx.x == 0 && !st->done) st->alpha = st->nu / sums[0]; }
+// s = r - alpha tmp                                                        (bicgstab.hh:145-146)
+__global__ void bicg_s_kernel(double* __restrict__ s, const double* __restrict__ r, const double* __restrict__ tmp, long long n, const BicgState* st) {
+  if (st->done) return;
+  const double ma = -st->alpha;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) s[i] = fma(ma, tmp[i], r[i]);
+}
+// the five scalar products r.s, r.r, s.s, s.r*, r.r* in one sweep (scalarProductVecs); partial[k * gridDim.x + block]
+__global__ void __launch_bounds__(kRedThreads) bicg_dots5_kernel(const double* __restrict__ r, const double* __restrict__ s, const double* __restrict__ rstar,
+                                                                 const uint8_t* __restrict__ aux, long long n, double* partial, BicgState* st, double* history, unsigned int* counter) {
+  if (st->done) return;
+  double d[5] = {0, 0, 0, 0, 0};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    if (!aux || !aux[i]) { const double rv = r[i], sv = s[i], qv = rstar[i]; d[0] = fma(rv, sv, d[0]); d[1] = fma(rv, rv, d[1]); d[2] = fma(sv, sv, d[2]); d[3] = fma(sv, qv, d[3]); d[4] = fma(rv, qv, d[4]); }
+#pragma unroll
+  for (int k = 0; k < 5; ++k) { const double t = block_sum(d[k]); if (threadIdx.x == 0) partial[(size_t)k * gridDim.x + blockIdx.x] = t; }
+  if (!counter || !last_block_done(counter)) return;
+  __shared__ double gd[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) { const double t = final_sum(partial + (size_t)k * gridDim.x); if (threadIdx.x == 0) gd[k] = t; }
+  if (threadIdx.x == 0) { bicg_scalars(gd, st, history); *counter = 0; }
+}
+__global__ void bicg_scalars_kernel(const double* __restrict__ sums, BicgState* st, double* history) { if (threadIdx.x == 0 && blockIdx.x == 0 && !st->done) bicg_scalars(sums, st, history); }
+// x += alpha p ; x += omega s ; unless the iteration was the last one: r = s - omega r ; p = r + beta (p - omega tmp)
+// (bicgstab.hh:185-199).  Runs once per executed iteration (x_applied lags the iteration counter by one while pending).
+__global__ void __launch_bounds__(kRedThreads) bicg_update_kernel(double* __restrict__ x, double* __restrict__ r, double* __restrict__ p, const double* __restrict__ s,
+                                                                  const double* __restrict__ tmp, long long n, BicgState* st, unsigned int* counter) {
+  if (st->x_applied == st->iterations) return;
+  const double alpha = st->alpha, omega = st->omega, beta = st->beta; const bool last = st->done != 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double sv = s[i], pv = p[i];
+    x[i] = fma(omega, sv, fma(alpha, pv, x[i]));
+    if (!last) { const double rv = fma(-omega, r[i], sv); r[i] = rv; p[i] = fma(-omega * beta, tmp[i], beta * pv) + rv; }
+  }
+  if (last_block_done(counter) && threadIdx.x == 0) { st->x_applied = st->iterations; *counter = 0; }
+}
+
 // strong Dirichlet rows: w_d = u_d - g_d   (schemes/dirichletwrapper.hh:101-105; Operation::sub)
 __global__ void dirichlet_sub_kernel(const double* __restrict__ u, double* __restrict__ w, const uint8_t* __restrict__ mask,
                                      const double* __restrict__ g, long long n) {

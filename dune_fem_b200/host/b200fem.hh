@@ -153,25 +153,30 @@ class MOLGalerkinOperator : public GalerkinOperator<DiscreteFunctionT> {
 struct SolverParameter {                       // solver/parameter.hh:21-295, keys fem.solver.*
   double tolerance = 1e-8; int errorMeasure = B200FEM_TOL_ABSOLUTE; int maxIterations = 1000; bool verbose = false;
 };
-template <class DiscreteFunctionT>
-class CgInverseOperator {
+// KrylovInverseOperator< DF, method > (solver/krylovinverseoperators.hh:46-288): method cg -> linear/cg.hh, bicgstab -> linear/bicgstab.hh
+enum SolverMethod { cg = 0, bicgstab = 1 };
+template <class DiscreteFunctionT, int method = cg>
+class KrylovInverseOperator {
  public:
   typedef GalerkinOperator<DiscreteFunctionT> OperatorType;
-  explicit CgInverseOperator(const SolverParameter& p = SolverParameter()) : parameter_(p) {}
+  explicit KrylovInverseOperator(const SolverParameter& p = SolverParameter()) : parameter_(p) {}
   void bind(const OperatorType& op) { op_ = &op; }                                    // inverseoperatorinterface.hh:109-113
   void unbind() { op_ = nullptr; }
   void operator()(const DiscreteFunctionT& rhs, DiscreteFunctionT& x) const {        // inverseoperatorinterface.hh:81-84
-    if (!op_) throw InvalidStateException("CgInverseOperator: no operator bound");
+    if (!op_) throw InvalidStateException("KrylovInverseOperator: no operator bound");
     residuals_.assign((std::size_t)std::max(parameter_.maxIterations, 1), 0.0);
-    check(b200fem_cg_solve(op_->handle(), rhs.leakPointer(), x.leakPointer(), parameter_.tolerance, parameter_.maxIterations,
-                           parameter_.errorMeasure, &iterations_, residuals_.data()));
+    auto solve = method == bicgstab ? b200fem_bicgstab_solve : b200fem_cg_solve;
+    check(solve(op_->handle(), rhs.leakPointer(), x.leakPointer(), parameter_.tolerance, parameter_.maxIterations,
+                parameter_.errorMeasure, &iterations_, residuals_.data()));
   }
-  int iterations() const { return iterations_; }                                       // negative: not converged (linear/cg.hh:116)
+  int iterations() const { return iterations_; }                                       // negative: not converged (linear/cg.hh:116, bicgstab.hh:208-211)
   bool converged() const { return iterations_ >= 0; }
   const std::vector<double>& residuals() const { return residuals_; }
   SolverParameter& parameter() { return parameter_; }
  private:
   SolverParameter parameter_; const OperatorType* op_ = nullptr; mutable int iterations_ = 0; mutable std::vector<double> residuals_;
 };
+template <class DiscreteFunctionT> using CgInverseOperator = KrylovInverseOperator<DiscreteFunctionT, cg>;                // krylovinverseoperators.hh:284
+template <class DiscreteFunctionT> using BicgstabInverseOperator = KrylovInverseOperator<DiscreteFunctionT, bicgstab>;    // :288
 
 }  // namespace B200Fem

@@ -11,6 +11,9 @@ _ERRORMEASURE = {"absolute": capi.TOL_ABSOLUTE, "relative": capi.TOL_RELATIVE, "
 
 
 class CgInverseOperator:
+    _solve = "b200fem_cg_solve"          # LinearSolver::cg (solver/linear/cg.hh)
+    _label = "Fem::CG it: {} : residual {}"
+
     def __init__(self, parameters=None):
         p = {"tolerance": 1e-8, "errormeasure": "absolute", "maxiterations": 1000, "verbose": False}
         for k, v in (parameters or {}).items():
@@ -32,14 +35,14 @@ class CgInverseOperator:
         p = self.parameters
         it = C.c_int()
         hist = np.zeros(max(int(p["maxiterations"]), 1))
-        capi.check(capi.lib().b200fem_cg_solve(self._op.handle, capi.ptr(rhs), capi.ptr(x), float(p["tolerance"]),
-                                               int(p["maxiterations"]), _ERRORMEASURE[p["errormeasure"]], C.byref(it),
-                                               capi.ptr(hist)))
+        capi.check(getattr(capi.lib(), self._solve)(self._op.handle, capi.ptr(rhs), capi.ptr(x), float(p["tolerance"]),
+                                                    int(p["maxiterations"]), _ERRORMEASURE[p["errormeasure"]], C.byref(it),
+                                                    capi.ptr(hist)))
         self._iterations = it.value
         self.residuals = hist[:abs(it.value)]
         if p["verbose"]:
             for i, r in enumerate(self.residuals):
-                print(f"Fem::CG it: {i} : residual {r}")                   # solver/linear/cg.hh:110-113
+                print(self._label.format(i, r))                            # solver/linear/cg.hh:110-113, bicgstab.hh:196
         return it.value
 
     @property
@@ -51,4 +54,18 @@ class CgInverseOperator:
         return self._iterations >= 0
 
 
-KrylovInverseOperator = CgInverseOperator
+class BicgstabInverseOperator(CgInverseOperator):
+    """KrylovInverseOperator< DF, SolverParameter::bicgstab > (solver/krylovinverseoperators.hh:288 ->
+    solver/linear/bicgstab.hh:64-214): for non-symmetric operators (advection-diffusion)."""
+    _solve = "b200fem_bicgstab_solve"
+    _label = "Fem::BiCGstab it: {} : {}"
+
+
+def KrylovInverseOperator(parameters=None):
+    """fem.solver.method selects the Krylov method (solver/parameter.hh; krylovinverseoperators.hh:83,126-131)."""
+    method = {k.replace("fem.solver.", ""): v for k, v in (parameters or {}).items()}.get("method", "cg")
+    if method == "cg":
+        return CgInverseOperator(parameters)
+    if method == "bicgstab":
+        return BicgstabInverseOperator(parameters)
+    raise NotImplementedError(f"KrylovInverseOperator: method {method!r} (cg and bicgstab are available)")

@@ -140,6 +140,16 @@ int b200fem_cg_solve(b200fem_operator* op, const double* b_host, double* x_host,
 int b200fem_cg_solve_dev(b200fem_operator* op, const double* b_dev, double* x_dev, double epsilon, int max_iterations,
                          int tolerance_criteria, int* iterations, double* history);
 
+/* KrylovInverseOperator<bicgstab> (solver/krylovinverseoperators.hh:46-281 -> solver/linear/bicgstab.hh:64-214, unpreconditioned)
+ * on the homogeneous linear part -- the Krylov method of pydemo/advectiondiffusion.py (non-symmetric operators).  Same
+ * conventions as the reference: no convergence test before the first iteration; `res` is compared with
+ * epsilon * {1 | sqrt(b.b) | sqrt(r0.r0)}; *iterations is negative when max_iterations was reached (:208-211); history
+ * receives `res` per iteration ("Fem::BiCGstab it: i : res"). */
+int b200fem_bicgstab_solve(b200fem_operator* op, const double* b_host, double* x_host, double epsilon, int max_iterations,
+                           int tolerance_criteria, int* iterations, double* history);
+int b200fem_bicgstab_solve_dev(b200fem_operator* op, const double* b_dev, double* x_dev, double epsilon, int max_iterations,
+                               int tolerance_criteria, int* iterations, double* history);
+
 /* BLAS-1 on device dof vectors (function/blockvectors/defaultblockvectors.hh:39-150) and the dot product over
  * primary dofs followed by the global sum (function/common/scalarproducts.hh:115-127) */
 int b200fem_dot_dev(b200fem_operator* op, const double* x_dev, const double* y_dev, double* result);

@@ -615,6 +615,43 @@ static int cg(const std::function<void(const double*, double*)>& op, int64_t n, 
   return (iterations < maxIterations) ? iterations : -iterations;
 }
 
+// LinearSolver::bicgstab (solver/linear/bicgstab.hh:64-214), unpreconditioned branch (z aliases r), with the fused
+// five-fold scalar product of scalarProductVecs (:19-52).  Note the reference's conventions: no convergence test before
+// the first iteration, `res` (not its square) is compared with tolerance * {1 | sqrt(b.b) | sqrt(r0.r0)}.
+static int bicgstab(const std::function<void(const double*, double*)>& op, int64_t n, double* x, const double* b,
+                    double tolerance, int maxIterations, int tolCrit, double* history) {
+  std::vector<double> r(n), r_star(n), p(n), s(n), tmp(n);
+  double gd[5]; double tol = tolerance;
+  if (tolCrit == 1) tol *= std::sqrt(dot(b, b, n));
+  op(x, r.data());
+  for (int64_t i = 0; i < n; ++i) { r[i] *= -1.0; r[i] += b[i]; }
+  p = r; r_star = r;
+  double nu = dot(r.data(), r_star.data(), n);
+  if (tolCrit == 2) tol *= std::sqrt(nu);
+  int iterations = 0;
+  while (true) {
+    op(p.data(), tmp.data());
+    gd[0] = dot(tmp.data(), r_star.data(), n);
+    const double alpha = nu/gd[0];
+    for (int64_t i = 0; i < n; ++i) { s[i] = r[i]; s[i] += -alpha*tmp[i]; }
+    op(s.data(), r.data());
+    gd[0] = gd[1] = gd[2] = gd[3] = gd[4] = 0.0;
+    for (int64_t i = 0; i < n; ++i) { gd[0] += r[i]*s[i]; gd[1] += r[i]*r[i]; gd[2] += s[i]*s[i]; gd[3] += s[i]*r_star[i]; gd[4] += r[i]*r_star[i]; }
+    const double omega = gd[0]/gd[1];
+    const double res = std::sqrt(gd[2] - omega*(2.0*gd[0] - omega*gd[1]));
+    const double beta = (gd[3] - omega*gd[4])*alpha/(omega*nu);
+    nu = gd[3] - omega*gd[4];
+    for (int64_t i = 0; i < n; ++i) x[i] += alpha*p[i];
+    for (int64_t i = 0; i < n; ++i) x[i] += omega*s[i];
+    if (history) history[iterations] = res;
+    ++iterations;
+    if (res < tol || iterations >= maxIterations) break;
+    for (int64_t i = 0; i < n; ++i) { r[i] *= -omega; r[i] += s[i]; }
+    for (int64_t i = 0; i < n; ++i) { p[i] *= beta; p[i] += -omega*beta*tmp[i]; p[i] += r[i]; }
+  }
+  return (iterations >= maxIterations) ? -iterations : iterations;
+}
+
 }  // namespace oracle
 
 // ===========================================================================
@@ -672,6 +709,10 @@ void fo_dirichlet(FoOperator* op, uint8_t* mask, double* values) {
 int fo_cg(FoOperator* op, const double* b, double* x, double eps, int maxit, int tolCrit, double* history) {
   Operator* A = op->linear.get();
   return cg([A](const double* in, double* out) { A->apply(in, out); }, op->space->sp->size, x, b, eps, maxit, tolCrit, history);
+}
+int fo_bicgstab(FoOperator* op, const double* b, double* x, double eps, int maxit, int tolCrit, double* history) {
+  Operator* A = op->linear.get();
+  return bicgstab([A](const double* in, double* out) { A->apply(in, out); }, op->space->sp->size, x, b, eps, maxit, tolCrit, history);
 }
 double fo_dot(const double* x, const double* y, int64_t n) { return dot(x, y, n); }
 

@@ -296,3 +296,39 @@ def test_mol_galerkin_inverse_mass(order, hier):
     with pytest.raises(_capi.B200FemError) as ei:
         fem.operator.molGalerkin(lsp)
     assert ei.value.code == _capi.ERR_NOT_IMPLEMENTED
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_bicgstab_iterates_match_reference_recurrence(order):
+    """KrylovInverseOperator<bicgstab> (solver/linear/bicgstab.hh) on the non-symmetric advection-diffusion DG operator
+    (the solver pydemo/advectiondiffusion.py uses): iteration counts, residual history and iterates against the oracle."""
+    n = [5, 4, 4] if order < 3 else [3, 3, 2]
+    space, osp = dg_pair(n, [0, 0, 0], [1, 1, 1], order, True)
+    kw = dict(eps=0.1, b=(1.0, 0.5, 0.2), c=1.0, beta=20.0 * order ** 2, dirichlet_mask=0b111111, data=2)
+    op = fem.operator.galerkin(space, **kw)
+    oop = ol.Operator(osp, skeleton=True, boundary=True, **kw)
+    b = op.loadVector()
+    assert rel(b, -oop.apply(np.zeros(space.size))) < TOL
+    x0 = np.zeros(space.size)
+    for maxit in (1, 4, 12):
+        inv = fem.solver.BicgstabInverseOperator({"tolerance": 1e-30, "maxiterations": maxit})
+        inv.bind(op)
+        x = x0.copy()
+        it = inv(b, x)
+        it_ref, x_ref, hist_ref = oop.bicgstab(b, x0, 1e-30, maxit)
+        assert it == it_ref == -maxit
+        np.testing.assert_allclose(inv.residuals, hist_ref, rtol=1e-7)
+        assert rel(x, x_ref) < 1e-8
+    for crit, tc in (("absolute", 0), ("relative", 1), ("residualreduction", 2)):
+        inv = fem.solver.KrylovInverseOperator({"fem.solver.method": "bicgstab", "tolerance": 1e-9, "maxiterations": 2000, "errormeasure": crit})
+        inv.bind(op)
+        x = x0.copy()
+        it = inv(b, x)
+        it_ref, x_ref, _ = oop.bicgstab(b, x0, 1e-9, 2000, tolcrit=tc)
+        # BiCGStab's residuals are erratic on this operator (cond ~ 1e4): rounding differences move the iteration at which
+        # the tolerance is first met by up to ~15 %; the early iterates above are what pins the recurrence
+        assert it > 0 and it_ref > 0 and abs(it - it_ref) <= max(3, it_ref // 4)
+        w = np.empty(space.size)
+        op.applyLinear(x, w)
+        assert np.linalg.norm(w - b) < 1e-6 * max(1.0, np.linalg.norm(b))
+        assert rel(x, x_ref) < 1e-6

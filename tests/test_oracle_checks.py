@@ -162,3 +162,20 @@ def test_mol_inverse_mass_is_projection_scaling():
     lsp = ol.Space([2, 2], [0, 0], [1, 1], ol.LAGRANGE, 1)
     with pytest.raises(ValueError):
         ol.Operator(lsp).setInverseMass(True)
+
+
+def test_bicgstab_oracle_solves_nonsymmetric_system():
+    """LinearSolver::bicgstab restatement (solver/linear/bicgstab.hh:64-214) on the advection-diffusion DG operator:
+    converges, returns the signed iteration count, and its last `res` is the true residual norm."""
+    sp = ol.Space([4, 4, 4], [0, 0, 0], [1, 1, 1], ol.DG_LEGENDRE_HIER, 1)
+    kw = dict(eps=0.1, b=(1.0, 0.5, 0.2), c=1.0, beta=20.0, dirichlet_mask=0b111111, data=2)
+    op = ol.Operator(sp, skeleton=True, boundary=True, **kw)
+    b = -op.apply(np.zeros(sp.size))
+    it, x, hist = op.bicgstab(b, np.zeros(sp.size), 1e-10, 500)
+    assert 0 < it < 500 and hist[-1] < 1e-10
+    assert abs(np.linalg.norm(op.apply(x, linear=True) - b) - hist[-1]) < 1e-12
+    it2, _, hist2 = op.bicgstab(b, np.zeros(sp.size), 1e-30, 7)
+    assert it2 == -7 and np.allclose(hist2, hist[:7], rtol=1e-12)
+    # relative criterion scales the tolerance by sqrt(b.b) (bicgstab.hh:88-92)
+    it3, _, hist3 = op.bicgstab(b, np.zeros(sp.size), 1e-6, 500, tolcrit=1)
+    assert hist3[-1] < 1e-6 * np.linalg.norm(b) <= hist3[-2]
