@@ -60,6 +60,17 @@ __global__ void negate_kernel(double* __restrict__ x, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) x[i] = -x[i];
 }
 
+// The sweeps below move two doubles per thread and iteration (16-byte loads/stores): at 8 bytes per access the grid of
+// 592 x 256 threads keeps too few bytes in flight for HBM3e (update_xr ran at 4.9 TB/s).  Vectors come from cudaMalloc
+// (256-byte aligned); an odd tail element is handled by the last thread.
+__device__ __forceinline__ bool primary2(const uint8_t* __restrict__ aux, long long i2, bool& p0, bool& p1) {
+  if (!aux) { p0 = p1 = true; return true; }
+  const uchar2 m = reinterpret_cast<const uchar2*>(aux)[i2]; p0 = !m.x; p1 = !m.y; return true;
+}
+__device__ __forceinline__ bool vec2_ok(const void* a, const void* b, const void* c, const void* d) {
+  return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) | reinterpret_cast<uintptr_t>(d)) & 15) == 0;
+}
+
 // ---- CG pieces ----
 // r = h - b ; p = b - h ; partial <p,p>          (cg.hh:39-60)
 __global__ void __launch_bounds__(kRedThreads) cg_init_kernel(const double* __restrict__ h, const double* __restrict__ b, double* __restrict__ r,
@@ -89,7 +100,13 @@ __global__ void cg_init_final_kernel(const double* __restrict__ sums, CgState* s
 __global__ void cg_update_p_kernel(double* __restrict__ p, const double* __restrict__ r, long long n, const CgState* st) {
   if (st->done || st->iterations == 0) return;            // the first search direction is p = b - A x (cg_init_kernel)
   const double beta = st->residual / st->prev_residual;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = p[i] * beta - r[i];
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  if (vec2_ok(p, r, p, r)) {
+    double2* p2 = reinterpret_cast<double2*>(p); const double2* r2 = reinterpret_cast<const double2*>(r);
+    for (long long i = tid; i < n / 2; i += nth) { double2 pv = p2[i]; const double2 rv = r2[i]; pv.x = pv.x * beta - rv.x; pv.y = pv.y * beta - rv.y; p2[i] = pv; }
+    if ((n & 1) && tid == 0) p[n - 1] = p[n - 1] * beta - r[n - 1];
+  } else
+    for (long long i = tid; i < n; i += nth) p[i] = p[i] * beta - r[i];
 }
 __global__ void __launch_bounds__(kRedThreads) cg_dot_kernel(const double* __restrict__ x, const double* __restrict__ y, const uint8_t* __restrict__ aux,
                                                              long long n, double* __restrict__ partial, const CgState* st) {
@@ -149,8 +166,18 @@ __global__ void __launch_bounds__(kRedThreads) cg_dot_alpha_kernel(const double*
                                                                    long long n, double* partial, CgState* st, unsigned int* counter) {
   if (st->done) return;
   double s = 0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    if (!aux || !aux[i]) s = fma(x[i], y[i], s);
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  if (vec2_ok(x, y, x, y) && (!aux || (reinterpret_cast<uintptr_t>(aux) & 1) == 0)) {
+    const double2* x2 = reinterpret_cast<const double2*>(x); const double2* y2 = reinterpret_cast<const double2*>(y);
+    for (long long i = tid; i < n / 2; i += nth) {
+      const double2 xv = x2[i], yv = y2[i]; bool p0, p1; primary2(aux, i, p0, p1);
+      if (p0) s = fma(xv.x, yv.x, s);
+      if (p1) s = fma(xv.y, yv.y, s);
+    }
+    if ((n & 1) && tid == 0 && (!aux || !aux[n - 1])) s = fma(x[n - 1], y[n - 1], s);
+  } else
+    for (long long i = tid; i < n; i += nth)
+      if (!aux || !aux[i]) s = fma(x[i], y[i], s);
   s = block_sum(s);
   if (threadIdx.x == 0) partial[blockIdx.x] = s;
   if (!last_block_done(counter)) return;
@@ -163,11 +190,25 @@ __global__ void __launch_bounds__(kRedThreads) cg_update_xr_residual_kernel(doub
   if (st->done) return;
   const double alpha = st->alpha;
   double s = 0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    x[i] = fma(alpha, p[i], x[i]);
-    const double rv = fma(alpha, h[i], r[i]); r[i] = rv;
-    if (!aux || !aux[i]) s = fma(rv, rv, s);
-  }
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  if (vec2_ok(x, r, p, h) && (!aux || (reinterpret_cast<uintptr_t>(aux) & 1) == 0)) {
+    double2* x2 = reinterpret_cast<double2*>(x); double2* r2 = reinterpret_cast<double2*>(r);
+    const double2* p2 = reinterpret_cast<const double2*>(p); const double2* h2 = reinterpret_cast<const double2*>(h);
+    for (long long i = tid; i < n / 2; i += nth) {
+      double2 xv = x2[i], rv = r2[i]; const double2 pv = p2[i], hv = h2[i];
+      xv.x = fma(alpha, pv.x, xv.x); xv.y = fma(alpha, pv.y, xv.y); x2[i] = xv;
+      rv.x = fma(alpha, hv.x, rv.x); rv.y = fma(alpha, hv.y, rv.y); r2[i] = rv;
+      bool p0, p1; primary2(aux, i, p0, p1);
+      if (p0) s = fma(rv.x, rv.x, s);
+      if (p1) s = fma(rv.y, rv.y, s);
+    }
+    if ((n & 1) && tid == 0) { const long long i = n - 1; x[i] = fma(alpha, p[i], x[i]); const double rv = fma(alpha, h[i], r[i]); r[i] = rv; if (!aux || !aux[i]) s = fma(rv, rv, s); }
+  } else
+    for (long long i = tid; i < n; i += nth) {
+      x[i] = fma(alpha, p[i], x[i]);
+      const double rv = fma(alpha, h[i], r[i]); r[i] = rv;
+      if (!aux || !aux[i]) s = fma(rv, rv, s);
+    }
   s = block_sum(s);
   if (threadIdx.x == 0) partial[blockIdx.x] = s;
   if (!last_block_done(counter)) return;
