@@ -65,6 +65,7 @@ struct b200fem_operator {
   CgState* d_cg = nullptr; int hist_cap = 0; unsigned int* d_counter = nullptr;
   double *d_rstar = nullptr, *d_s = nullptr, *d_tmp = nullptr, *d_partial5 = nullptr, *d_sums5 = nullptr; BicgState* d_bicg = nullptr;   // BiCGStab work vectors
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr; cudaEvent_t pipe_ev[2 * 16 + 2] = {};   // host-pointer apply: copy/compute pipeline
+  bool want_dot = false; int dot_parts = 0; double* d_dot_partial = nullptr; int dot_cap = 0;     // <u, A u> fused into the lattice kernel (CG)
   cudaGraphExec_t cg_graph = nullptr; const void* cg_graph_key[3] = {nullptr, nullptr, nullptr}; bool capturing = false;
   bool kron_ready = false; int kron_chk = -1; bool fuse_dirichlet = false, fuse_linear = false, dirichlet_fused = false; double* d_lag_rows = nullptr; LagKronRows lag_rows{}; std::vector<unsigned char> kron_tab; struct KronMapCache* map_cache = nullptr; struct MarchMapCache* march_cache = nullptr;
   HaloPlan halo; HaloPlanDG halo_dg; HaloPlanP2P halo_p2p; const BoxDev* active_box = nullptr; int reserve_sms = 0; unsigned long long fused_seq = 0; bool last_launch_tensor = false;      // active_box: sub-box override for split launches
@@ -563,7 +564,13 @@ static int launch_lagrange_kronecker(b200fem_operator* op, const double* u, doub
   const int zseg = (L2 + best_nseg - 1) / best_nseg, nseg = (L2 + zseg - 1) / zseg;
   const unsigned grid = (unsigned)(tiles * nseg); cudaStream_t st = s->mesh->ctx->stream;
   const unsigned char* dmask = op->fuse_dirichlet ? op->d_dmask : nullptr; const double* dvals = op->fuse_dirichlet && !op->fuse_linear ? op->d_dvals : nullptr;
-#define B200FEM_LAGK(KK, MM, HH) lagrange_kronecker_kernel<KK, MM, HH><<<grid, 32 * HH, 0, st>>>(L, op->lag_rows, u, w, bvec, dmask, dvals, tx, ty, zseg)
+  // fused <u, w> partials (requested by the CG driver on one rank, where every dof is primary and the Dirichlet rows are fused too)
+  double* dotp = nullptr; op->dot_parts = 0;
+  if (op->want_dot && op->fuse_dirichlet == (op->model.strong_dirichlet && op->d_dmask != nullptr) && s->mesh->ctx->world == 1) {
+    if ((int)grid > op->dot_cap) { if (op->capturing) return fail(B200FEM_ERR_INVALID, "dot partial buffer must exist before graph capture"); if (op->d_dot_partial) cudaFree(op->d_dot_partial); CUDA_OK(cudaMalloc(&op->d_dot_partial, sizeof(double) * grid)); op->dot_cap = (int)grid; }
+    dotp = op->d_dot_partial; op->dot_parts = (int)grid;
+  }
+#define B200FEM_LAGK(KK, MM, HH) lagrange_kronecker_kernel<KK, MM, HH><<<grid, 32 * HH, 0, st>>>(L, op->lag_rows, u, w, bvec, dmask, dvals, tx, ty, zseg, dotp)
 #define B200FEM_LAGK_HY(KK, MM) do { if (HY == 24) B200FEM_LAGK(KK, MM, 24); else B200FEM_LAGK(KK, MM, 16); } while (0)
   if (k == 1) { if (mapped) B200FEM_LAGK_HY(1, true); else B200FEM_LAGK_HY(1, false); }
   else        { if (mapped) B200FEM_LAGK_HY(2, true); else B200FEM_LAGK_HY(2, false); }
@@ -826,7 +833,7 @@ static void free_map_cache(b200fem_operator* op) { delete op->map_cache; op->map
 extern "C" int b200fem_operator_destroy(b200fem_operator* op) {
   if (!op) return B200FEM_OK;
   for (void* p : {(void*)op->d_perm, (void*)op->d_bvec, (void*)op->d_dmask, (void*)op->d_dvals, (void*)op->d_aux, (void*)op->d_u, (void*)op->d_w, (void*)op->d_h, (void*)op->d_r,
-                  (void*)op->d_p, (void*)op->d_x, (void*)op->d_b, (void*)op->d_partial, (void*)op->d_sums, (void*)op->d_hist, (void*)op->d_cg, (void*)op->d_lag_rows, (void*)op->d_counter, (void*)op->d_rstar, (void*)op->d_s, (void*)op->d_tmp, (void*)op->d_partial5, (void*)op->d_sums5, (void*)op->d_bicg}) if (p) cudaFree(p);
+                  (void*)op->d_p, (void*)op->d_x, (void*)op->d_b, (void*)op->d_partial, (void*)op->d_sums, (void*)op->d_hist, (void*)op->d_cg, (void*)op->d_lag_rows, (void*)op->d_counter, (void*)op->d_rstar, (void*)op->d_s, (void*)op->d_tmp, (void*)op->d_partial5, (void*)op->d_sums5, (void*)op->d_bicg, (void*)op->d_dot_partial}) if (p) cudaFree(p);
   if (op->cg_graph) cudaGraphExecDestroy(op->cg_graph);
   halo_plan_p2p_free(op->halo_p2p); halo_plan_free(op->halo); halo_plan_dg_free(op->halo_dg); free_map_cache(op);
   if (op->comm_stream) cudaStreamDestroy(op->comm_stream);
@@ -977,7 +984,8 @@ extern "C" int b200fem_cg_solve_dev(b200fem_operator* op, const double* b, doubl
   int rc = ensure_cg_buffers(op, maxit); if (rc) return rc;
   CgState init{}; init.epsilon = epsilon; init.max_iterations = maxit; init.tol_criteria = tolcrit;
   CUDA_OK(cudaMemcpyAsync(op->d_cg, &init, sizeof(CgState), cudaMemcpyHostToDevice, st));
-  rc = apply_dev_impl(op, x, op->d_h, true); if (rc) return rc;                                              // h = A x
+  op->want_dot = c->world == 1;                        // (also allocates the partial buffer of the fused <q,h> before any graph capture)
+  rc = apply_dev_impl(op, x, op->d_h, true); op->want_dot = false; if (rc) return rc;                          // h = A x
   cg_init_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(op->d_h, b, op->d_r, op->d_p, op->d_aux, n, op->d_partial, op->d_partial + kRedBlocks);
   rc = reduce_sums(op, 2); if (rc) return rc;
   cg_init_final_kernel<<<1, 32, 0, st>>>(op->d_sums, op->d_cg);
@@ -987,9 +995,11 @@ extern "C" int b200fem_cg_solve_dev(b200fem_operator* op, const double* b, doubl
   const bool single = c->world == 1;
   auto enqueue_iteration = [&]() -> int {
     cg_update_p_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(op->d_p, op->d_r, n, op->d_cg);                      // no-op in iteration 0
-    int e = apply_dev_impl(op, op->d_p, op->d_h, true); if (e) return e;                                        // h = A q
+    op->want_dot = single; op->dot_parts = 0;
+    int e = apply_dev_impl(op, op->d_p, op->d_h, true); op->want_dot = false; if (e) return e;                  // h = A q (+ <q,h> partials when the kernel can)
     if (single) {
-      cg_dot_alpha_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(op->d_p, op->d_h, op->d_aux, n, op->d_partial, op->d_cg, op->d_counter);
+      if (op->dot_parts > 0) cg_alpha_partials_kernel<<<1, kRedThreads, 0, st>>>(op->d_dot_partial, op->dot_parts, op->d_cg);
+      else cg_dot_alpha_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(op->d_p, op->d_h, op->d_aux, n, op->d_partial, op->d_cg, op->d_counter);
       cg_update_xr_residual_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(x, op->d_r, op->d_p, op->d_h, op->d_aux, n, op->d_partial, op->d_cg, op->d_hist, op->d_counter + 1);
     } else {
       cg_dot_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(op->d_p, op->d_h, op->d_aux, n, op->d_partial, op->d_cg);

@@ -24,6 +24,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include "lagrange_quadrature.cuh"
+#include "vec_kernels.cuh"
 #include <type_traits>
 #include <utility>
 
@@ -57,7 +58,7 @@ __global__ void __launch_bounds__(LagKronCfg<K, HYP>::kThreads, LagKronCfg<K, HY
 lagrange_kronecker_kernel(const __grid_constant__ LagrangeLayoutDev L, const __grid_constant__ LagKronRows R,
                           const double* __restrict__ u, double* __restrict__ w, const double* __restrict__ bvec,
                           const unsigned char* __restrict__ dmask, const double* __restrict__ dvals,
-                          const int tiles_x, const int tiles_y, const int zseg) {
+                          const int tiles_x, const int tiles_y, const int zseg, double* __restrict__ dot_partial) {
   using Cfg = LagKronCfg<K, HYP>;
   constexpr int W = Cfg::W, HX = Cfg::HX, HY = Cfg::HY, TX = Cfg::TX, TY = Cfg::TY;
   __shared__ double Sa[2][HY][HX], Sb[2][HY][HX];
@@ -149,6 +150,7 @@ lagrange_kronecker_kernel(const __grid_constant__ LagrangeLayoutDev L, const __g
   z_pass(std::integral_constant<int, 0>{}, z0, 0);
   __syncthreads();
 
+  double dacc = 0.0;                                         // <u, w> over the nodes this thread stores (CG: <p, A p> without a second sweep)
   auto step = [&](auto rc, int z) {
     constexpr int r = decltype(rc)::value;
     const int cb = (z - z0) & 1;
@@ -177,11 +179,13 @@ lagrange_kronecker_kernel(const __grid_constant__ LagrangeLayoutDev L, const __g
         const int src = (hx - K + j) & 31;
         r0 = fma(Xr[hx][W + j], __shfl_sync(0xffffffffu, c, src), r0); r1 = fma(Xr[hx][j], __shfl_sync(0xffffffffu, s, src), r1);
       }
-      if (x_owned) w[g] = constrained ? uc - dq : (r0 + r1) - bq;
+      if (x_owned) { const double val = constrained ? uc - dq : (r0 + r1) - bq; w[g] = val; dacc = fma(uc, val, dacc); }
     }
     __syncthreads();
   };
   for (int zb = z0; zb < z1; zb += NW) lagk_static_for<NW>([&](auto rc) { const int z = zb + decltype(rc)::value; if (z < z1) step(rc, z); });
+  // optional fused scalar product <u, w>: one partial per CTA, summed in block order by cg_alpha_partials_kernel -- deterministic
+  if (dot_partial) { const double t = block_sum(dacc); if (tid == 0) dot_partial[blockIdx.x] = t; }
 }
 
 }  // namespace b200fem

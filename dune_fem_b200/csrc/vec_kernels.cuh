@@ -184,6 +184,14 @@ __global__ void __launch_bounds__(kRedThreads) cg_dot_alpha_kernel(const double*
   const double t = final_sum(partial);
   if (threadIdx.x == 0) { st->qdoth = t; st->alpha = st->residual / t; *counter = 0; }
 }
+// <q,h> arrives as per-CTA partials of the apply kernel (lagrange_kronecker_kernel's fused scalar product): alpha = residual / <q,h>
+__global__ void __launch_bounds__(kRedThreads) cg_alpha_partials_kernel(const double* __restrict__ partial, int nparts, CgState* st) {
+  if (st->done) return;
+  double s = 0;
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) s += partial[i];
+  s = block_sum(s);
+  if (threadIdx.x == 0) { st->qdoth = s; st->alpha = st->residual / s; }
+}
 __global__ void __launch_bounds__(kRedThreads) cg_update_xr_residual_kernel(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
                                                                             const double* __restrict__ h, const uint8_t* __restrict__ aux, long long n,
                                                                             double* partial, CgState* st, double* __restrict__ history, unsigned int* counter) {
