@@ -727,7 +727,9 @@ static int apply_dev_impl(b200fem_operator* op, const double* u, double* w, bool
   } else {
     // fused send: when the peer-memory mailboxes exist the TMA kernel itself stores boundary rows of w into the
     // neighbours' mailboxes while it is still computing; afterwards only the receive part runs
-    static const bool no_fused = std::getenv("B200FEM_NO_FUSED_SEND") != nullptr;
+    // measured (profiles/r01_multigpu.md): marching kernel + one exchange kernel beats the tensor kernel with fused sends
+    // (53.5 vs 56.0 us at 2 GPUs, 61.2 vs 73.6 us at 4) -- the fused schedule is opt-in
+    static const bool no_fused = std::getenv("B200FEM_FUSED_SEND") == nullptr || std::getenv("B200FEM_NO_FUSED_SEND") != nullptr;
     const bool try_fused = distributed && !no_fused && s->kind != B200FEM_LAGRANGE && op->halo_p2p.built && op->halo_p2p.nnb > 0 &&
                            s->box.own_lo[0] == 0 && s->box.own_hi[0] == s->box.n[0];
     op->last_launch_tensor = false;
