@@ -460,8 +460,8 @@ template <int N, bool HIER> static int launch_dg_kronecker_march(b200fem_operato
 }
 
 // Kronecker kernel of the higher orders (dg_kronecker_slab.cuh): one CTA per TX x TY x TZ tile, n threads per element
-template <int N, int TX, int TY, int TZ, int MINB> static int launch_dg_kronecker_slab(b200fem_operator* op, const double* u, double* w, const double* bvec) {
-  using Cfg = KronSlabCfg<N, TX, TY, TZ>; const BoxDev& b = op->active_box ? *op->active_box : op->sp->box;
+template <int N, int TX, int TY, int TZ, int MINB, int SPLIT> static int launch_dg_kronecker_slab(b200fem_operator* op, const double* u, double* w, const double* bvec) {
+  using Cfg = KronSlabCfg<N, TX, TY, TZ, SPLIT>; const BoxDev& b = op->active_box ? *op->active_box : op->sp->box;
   if (!op->kron_ready) {
     KronHost kh = build_kron_tables(op->sp->tab, op->model, b.dim, b.h, mass_scale(op));
     op->kron_tab.resize(sizeof(KronTabDev<N>));
@@ -471,7 +471,7 @@ template <int N, int TX, int TY, int TZ, int MINB> static int launch_dg_kronecke
   }
   const KronTabDev<N>& K = *reinterpret_cast<const KronTabDev<N>*>(op->kron_tab.data());
   const int tx = (b.own_hi[0] - b.own_lo[0] + TX - 1) / TX, ty = (b.own_hi[1] - b.own_lo[1] + TY - 1) / TY, tz = (b.own_hi[2] - b.own_lo[2] + TZ - 1) / TZ;
-  auto kern = dg_kronecker_slab_kernel<N, TX, TY, TZ, MINB>;
+  auto kern = dg_kronecker_slab_kernel<N, TX, TY, TZ, MINB, SPLIT>;
   static bool attr_set = false;
   if (!attr_set) { CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes())); attr_set = true; }
   kern<<<(unsigned)((long long)tx * ty * tz), Cfg::kThreads, Cfg::smem_bytes(), op->sp->mesh->ctx->stream>>>(K, b, op->d_perm, u, w, bvec, tx, ty);
@@ -626,9 +626,12 @@ static int apply_local(b200fem_operator* op, const double* u, double* w, bool li
       // tile shapes: 4x4x4 (Q3), 4x2x2 (Q4, Q5), two CTAs per SM.  Measured alternatives (4x4x2 with 4 CTAs, 4x4x3 with 3, 2x2x2 with 3
       // for Q5) were within 2 % or slower: the kernel moves 2.5-3.5 x 8 B/dof of halo'd input through the L2->SM fabric and sits
       // at ~75 % of that path's throughput (profiles/r01_dg_kronecker_slab_q3.md)
-      if (N == 4) rc = launch_dg_kronecker_slab<4, 4, 4, 4, 2>(op, u, w, bvec);
-      else if (N == 5) rc = launch_dg_kronecker_slab<5, 4, 2, 2, 2>(op, u, w, bvec);
-      else rc = launch_dg_kronecker_slab<6, 4, 2, 2, 2>(op, u, w, bvec);
+      // one thread per slab.  SPLIT = 2 (two threads per slab, 12 instead of 6 warps per SM for Q5; the kernel template still
+      // carries it) measured 97 vs 101 GDoF/s for Q5 and 99 vs 144 for Q3: the kernel is not short of warps, it waits for its
+      // staging phase -- two CTAs per SM is all the 111 KB tiles allow
+      if (N == 4) rc = launch_dg_kronecker_slab<4, 4, 4, 4, 2, 1>(op, u, w, bvec);
+      else if (N == 5) rc = launch_dg_kronecker_slab<5, 4, 2, 2, 2, 1>(op, u, w, bvec);
+      else rc = launch_dg_kronecker_slab<6, 4, 2, 2, 2, 1>(op, u, w, bvec);
       if (rc) return rc;
       op->timing.kernel = kernel; op->timing.launches_per_apply = 1;
       return B200FEM_OK;
@@ -890,7 +893,11 @@ static int apply_host(b200fem_operator* op, const double* u, double* w, bool lin
   int rc = ensure_staging(op); if (rc) return rc;
   const bool no_pipeline = std::getenv("B200FEM_NO_PIPELINE") != nullptr;     // (read per call: tests toggle it)
   if (!no_pipeline && s->kind != B200FEM_LAGRANGE && s->mesh->ctx->world == 1 && s->box.dim == 3 && bytes >= (8u << 20) && s->box.n[2] >= 16 && default_quadrature(op))
-    return apply_host_pipelined(op, u, w, linear, std::min(8, s->box.n[2] / 4));
+  {
+    static const char* ch = std::getenv("B200FEM_PIPE_CHUNKS");
+    const int want = ch ? std::max(2, std::min(16, std::atoi(ch))) : 8;
+    return apply_host_pipelined(op, u, w, linear, std::min(want, s->box.n[2] / 4));
+  }
   CUDA_OK(cudaMemcpyAsync(op->d_u, u, bytes, cudaMemcpyHostToDevice, st));
   rc = apply_dev_impl(op, op->d_u, op->d_w, linear); if (rc) return rc;
   CUDA_OK(cudaMemcpyAsync(w, op->d_w, bytes, cudaMemcpyDeviceToHost, st));

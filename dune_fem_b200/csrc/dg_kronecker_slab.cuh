@@ -34,8 +34,9 @@
 
 namespace b200fem {
 
-template <int N, int TX, int TY, int TZ> struct KronSlabCfg {
+template <int N, int TX, int TY, int TZ, int SPLIT = 1> struct KronSlabCfg {
   static constexpr int N2 = N * N, N3 = N * N * N;
+  static constexpr int NR = (N + SPLIT - 1) / SPLIT;         // slab rows per thread: SPLIT = 2 shares a slab between two threads
   static constexpr int slab_stride() {
     int s = N2;
     while ((N * (s - 1)) % 16 != 0 && s < N2 + 6) ++s;       // bank(K, j) = N K + S0 j distinct over 16 consecutive lanes
@@ -45,7 +46,7 @@ template <int N, int TX, int TY, int TZ> struct KronSlabCfg {
   static constexpr int elem_stride() { int e = N * S0; while (e % 16 != N % 16) ++e; return e; }
   static constexpr int ES = elem_stride();
   static constexpr int NO = TX * TY * TZ, NX = 2 * TY * TZ, NY = 2 * TX * TZ, NZ = 2 * TX * TY, kSlots = NO + NX + NY + NZ;
-  static constexpr int kWork = NO * N, kThreads = (kWork + 31) / 32 * 32, kWarps = kThreads / 32;
+  static constexpr int kWork = NO * N, kHalf = (kWork + 31) / 32 * 32, kThreads = SPLIT * kHalf, kWarps = kThreads / 32;   // halves are whole warps
   static constexpr int KS = (N3 + 31) / 32;                  // doubles per lane when a warp moves one element
   static constexpr size_t smem_bytes() { return sizeof(double) * (size_t)kSlots * ES + sizeof(int) * N3; }
   static_assert(NY + NZ >= NO, "the exchange buffer aliases the y/z halo slots");
@@ -91,6 +92,69 @@ __device__ __forceinline__ void streamed(const double* __restrict__ M, const dou
   }
 }
 
+
+// ---- row-restricted variants for SPLIT = 2: a thread owns the slab rows [R0, R1) (slow index of its slab); acc is indexed
+// [(row - R0) * N + fast].  Which half a thread takes is warp-uniform, so the matrix indices below stay compile-time
+// constants (constant-bank operands) in both instantiations.
+template <int N, int AX, int R0, int R1, int NA>
+__device__ __forceinline__ void self_rows(const double* __restrict__ M, const double (&v)[N * N], double (&acc)[NA]) {
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+#pragma unroll
+    for (int r = R0; r < R1; ++r) {
+#pragma unroll
+      for (int f = 0; f < N; ++f)
+        acc[(r - R0) * N + f] = AX == 0 ? fma(M[r * N + k], v[k * N + f], acc[(r - R0) * N + f]) : fma(M[f * N + k], v[r * N + k], acc[(r - R0) * N + f]);
+    }
+  }
+}
+// contraction over the SLOW index of the streamed slab, output rows restricted to [R0, R1): lines run along the slow index
+template <int N, int R0, int R1, int SLOW, int FAST, int NA>
+__device__ __forceinline__ void streamed_slow_rows(const double* __restrict__ M, const double* __restrict__ src, double (&acc)[NA]) {
+#pragma unroll
+  for (int f = 0; f < N; ++f) {
+    double line[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) line[k] = src[k * SLOW + f * FAST];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+#pragma unroll
+      for (int r = R0; r < R1; ++r) acc[(r - R0) * N + f] = fma(M[r * N + k], line[k], acc[(r - R0) * N + f]);
+    }
+  }
+}
+// contraction over the FAST index, rows [R0, R1) only: lines run along the fast index of those rows
+template <int N, int R0, int R1, int SLOW, int FAST, int NA>
+__device__ __forceinline__ void streamed_fast_rows(const double* __restrict__ M, const double* __restrict__ src, double (&acc)[NA]) {
+#pragma unroll
+  for (int r = R0; r < R1; ++r) {
+    double line[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) line[k] = src[r * SLOW + k * FAST];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+#pragma unroll
+      for (int f = 0; f < N; ++f) acc[(r - R0) * N + f] = fma(M[f * N + k], line[k], acc[(r - R0) * N + f]);
+    }
+  }
+}
+// x-contraction of phase B for the slab m2 = j: slow index m0 (contracted, stride S0), fast index m1 restricted to [R0, R1);
+// pb is indexed [m0 * (R1 - R0) + (m1 - R0)]
+template <int N, int R0, int R1, int S0, int NA>
+__device__ __forceinline__ void streamed_x_rows(const double* __restrict__ M, const double* __restrict__ src, double (&pb)[NA]) {
+#pragma unroll
+  for (int r = R0; r < R1; ++r) {
+    double line[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) line[k] = src[k * S0 + r * N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) pb[i * (R1 - R0) + (r - R0)] = fma(M[i * N + k], line[k], pb[i * (R1 - R0) + (r - R0)]);
+    }
+  }
+}
+
 // Stages the tile and its six face halos.  Slot sl of the CTA is handled by warp sl % kWarps; the decode of a slot (local
 // element coordinates, existence, global offset) is done ONCE per slot by one lane and broadcast by shuffle -- done per
 // warp iteration it was 45 % of all instructions of the first version (profiles/r01_dg_kronecker_slab_q3.md).
@@ -120,22 +184,83 @@ __device__ __forceinline__ void stage_tile(const BoxDev& box, const double* __re
     if (sl >= Cfg::kSlots) break;
     const long long so = __shfl_sync(0xffffffffu, my_src, i);
     const bool ok = so >= 0;
-    const double* src = u + (ok ? so : 0) + lane;
+    const double* src = u + (ok ? so : 0) + lane;            // (a missing element reads nothing: src-size 0 zero-fills; the address only has to be valid)
+    const int bytes = ok ? 8 : 0;
     const uint32_t dst = ubase + 8u * (uint32_t)(sl * Cfg::ES);
 #pragma unroll
     for (int k = 0; k < KS; ++k)
-      if (lane + 32 * k < N3) cp_async8(dst + 8u * doff[k], ok ? src + 32 * k : u, ok ? 8 : 0);   // src-size 0: zero fill
+      if (lane + 32 * k < N3) cp_async8(dst + 8u * doff[k], src + 32 * k, bytes);
   }
 }
 }  // namespace slab
 
-template <int N, int TX, int TY, int TZ, int MINB>
-__global__ void __launch_bounds__(KronSlabCfg<N, TX, TY, TZ>::kThreads, MINB)
+// phase A of thread (e, j) for the slab rows [R0, R1): slab m0 = j, axes y (slow index m1) and z (fast index m2)
+template <int N, int TX, int TY, int TZ, int R0, int R1, class Cfg, int NA>
+__device__ __forceinline__ void slab_phase_a(const KronTabDev<N>& K, const BoxDev& box, const double* __restrict__ U, const int e, const int j,
+                                             const int tx, const int ty, const int tz, const int gy, const int gz, double (&acc)[NA]) {
+  constexpr int N2 = Cfg::N2, S0 = Cfg::S0, ES = Cfg::ES, NO = Cfg::NO, NX = Cfg::NX, NY = Cfg::NY;
+  const double* own = U + (size_t)e * ES + j * S0;
+  {
+    double v[N2];
+#pragma unroll
+    for (int t = 0; t < N2; ++t) v[t] = own[t];
+#pragma unroll
+    for (int t = 0; t < NA; ++t) acc[t] = 0.0;
+    slab::self_rows<N, 0, R0, R1>(K.S[1], v, acc);
+    slab::self_rows<N, 1, R0, R1>(K.S[2], v, acc);
+    if (gy == 0) slab::self_rows<N, 0, R0, R1>(K.Dlo[1], v, acc);
+    if (gy == box.gn[1] - 1) slab::self_rows<N, 0, R0, R1>(K.Dhi[1], v, acc);
+    if (gz == 0) slab::self_rows<N, 1, R0, R1>(K.Dlo[2], v, acc);
+    if (gz == box.gn[2] - 1) slab::self_rows<N, 1, R0, R1>(K.Dhi[2], v, acc);
+  }
+  const int s_ym = ty > 0 ? e - TX : NO + NX + tz * TX + tx, s_yp = ty < TY - 1 ? e + TX : NO + NX + TX * TZ + tz * TX + tx;
+  const int s_zm = tz > 0 ? e - TX * TY : NO + NX + NY + ty * TX + tx, s_zp = tz < TZ - 1 ? e + TX * TY : NO + NX + NY + TX * TY + ty * TX + tx;
+  slab::streamed_slow_rows<N, R0, R1, N, 1>(K.L[1], U + (size_t)s_ym * ES + j * S0, acc);
+  slab::streamed_slow_rows<N, R0, R1, N, 1>(K.R[1], U + (size_t)s_yp * ES + j * S0, acc);
+  slab::streamed_fast_rows<N, R0, R1, N, 1>(K.L[2], U + (size_t)s_zm * ES + j * S0, acc);
+  slab::streamed_fast_rows<N, R0, R1, N, 1>(K.R[2], U + (size_t)s_zp * ES + j * S0, acc);
+}
+// phase B: slab m2 = j, axis x, the fast index m1 restricted to [R0, R1); the partial result goes to the exchange slot
+template <int N, int TX, int TY, int TZ, int R0, int R1, class Cfg>
+__device__ __forceinline__ void slab_phase_b(const KronTabDev<N>& K, const BoxDev& box, double* __restrict__ U, const int e, const int j,
+                                             const int tx, const int ty, const int tz, const int gx) {
+  constexpr int S0 = Cfg::S0, ES = Cfg::ES, NO = Cfg::NO, NX = Cfg::NX, NRR = R1 - R0;
+  if (NRR <= 0) return;
+  double pb[N * (NRR > 0 ? NRR : 1)];
+#pragma unroll
+  for (int t = 0; t < N * NRR; ++t) pb[t] = 0.0;
+  const int s_xm = tx > 0 ? e - 1 : NO + tz * TY + ty, s_xp = tx < TX - 1 ? e + 1 : NO + TY * TZ + tz * TY + ty;
+  const double* own = U + (size_t)e * ES + j;
+  slab::streamed_x_rows<N, R0, R1, S0>(K.S[0], own, pb);
+  if (gx == 0) slab::streamed_x_rows<N, R0, R1, S0>(K.Dlo[0], own, pb);
+  if (gx == box.gn[0] - 1) slab::streamed_x_rows<N, R0, R1, S0>(K.Dhi[0], own, pb);
+  slab::streamed_x_rows<N, R0, R1, S0>(K.L[0], U + (size_t)s_xm * ES + j, pb);
+  slab::streamed_x_rows<N, R0, R1, S0>(K.R[0], U + (size_t)s_xp * ES + j, pb);
+  double* Xe = U + (size_t)(NO + NX + e) * ES;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+#pragma unroll
+    for (int r = R0; r < R1; ++r) Xe[i * S0 + r * N + j] = pb[i * NRR + (r - R0)];
+  }
+}
+// combine: rows [R0, R1) of slab m0 = j of the exchange slot += acc, the sum stays there for the store loop
+template <int N, int R0, int R1, class Cfg, int NA>
+__device__ __forceinline__ void slab_combine(double* __restrict__ U, const int e, const int j, const double (&acc)[NA]) {
+  double* X = U + (size_t)(Cfg::NO + Cfg::NX + e) * Cfg::ES + j * Cfg::S0;
+#pragma unroll
+  for (int r = R0; r < R1; ++r) {
+#pragma unroll
+    for (int f = 0; f < N; ++f) X[r * N + f] += acc[(r - R0) * N + f];
+  }
+}
+
+template <int N, int TX, int TY, int TZ, int MINB, int SPLIT>
+__global__ void __launch_bounds__(KronSlabCfg<N, TX, TY, TZ, SPLIT>::kThreads, MINB)
 dg_kronecker_slab_kernel(const __grid_constant__ KronTabDev<N> K, const __grid_constant__ BoxDev box, const int* __restrict__ perm_g,
                          const double* __restrict__ u, double* __restrict__ w, const double* __restrict__ bvec,
                          const int tiles_x, const int tiles_y) {
-  using Cfg = KronSlabCfg<N, TX, TY, TZ>;
-  constexpr int N2 = Cfg::N2, N3 = Cfg::N3, S0 = Cfg::S0, ES = Cfg::ES, NO = Cfg::NO, NX = Cfg::NX, NY = Cfg::NY, KS = Cfg::KS;
+  using Cfg = KronSlabCfg<N, TX, TY, TZ, SPLIT>;
+  constexpr int N2 = Cfg::N2, N3 = Cfg::N3, S0 = Cfg::S0, ES = Cfg::ES, NO = Cfg::NO, NX = Cfg::NX, KS = Cfg::KS, NR = Cfg::NR;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* const U = reinterpret_cast<double*>(smem_raw);
   int* const tinv = reinterpret_cast<int*>(U + (size_t)Cfg::kSlots * ES);     // stored index -> tensor index
@@ -155,49 +280,23 @@ dg_kronecker_slab_kernel(const __grid_constant__ KronTabDev<N> K, const __grid_c
   slab::cp_async_wait_all();
   __syncthreads();
 
-  // ------------------------------ compute: thread (e, j) ------------------------------
-  const bool worker = tid < Cfg::kWork;
-  const int e = worker ? tid / N : 0, j = tid % N;
+  // ------------------------------ compute: thread (e, j[, half]) ------------------------------
+  // SPLIT = 2: the two halves of a slab (rows [0, NR) and [NR, N)) belong to different WARPS (half = warp-uniform), so both
+  // instantiations keep compile-time matrix indices and consecutive lanes still are consecutive (e, j): no bank conflicts
+  const int half = SPLIT == 1 ? 0 : tid / Cfg::kHalf, idx = tid - half * Cfg::kHalf;
+  const bool worker = idx < Cfg::kWork;
+  const int e = worker ? idx / N : 0, j = idx % N;
   const int tx = e % TX, ty = (e / TX) % TY, tz = e / (TX * TY);
   const int gx = box.origin[0] + x0 + tx, gy = box.origin[1] + y0 + ty, gz = box.origin[2] + z0 + tz;
-  double* const Xe = U + (size_t)(NO + NX + e) * ES;          // exchange / output slot of this element
-  double acc[N2];
+  double acc[NR * N];
   if (worker) {
-    // ---- phase A: slab m0 = j, axes y (slow index m1) and z (fast index m2)
-    const double* own = U + (size_t)e * ES + j * S0;
-    {
-      double v[N2];
-#pragma unroll
-      for (int t = 0; t < N2; ++t) { v[t] = own[t]; acc[t] = 0.0; }
-      slab::self<N, 0>(K.S[1], v, acc);
-      slab::self<N, 1>(K.S[2], v, acc);
-      if (gy == 0) slab::self<N, 0>(K.Dlo[1], v, acc);
-      if (gy == box.gn[1] - 1) slab::self<N, 0>(K.Dhi[1], v, acc);
-      if (gz == 0) slab::self<N, 1>(K.Dlo[2], v, acc);
-      if (gz == box.gn[2] - 1) slab::self<N, 1>(K.Dhi[2], v, acc);
-    }
-    const int s_ym = ty > 0 ? e - TX : NO + NX + tz * TX + tx, s_yp = ty < TY - 1 ? e + TX : NO + NX + TX * TZ + tz * TX + tx;
-    const int s_zm = tz > 0 ? e - TX * TY : NO + NX + NY + ty * TX + tx, s_zp = tz < TZ - 1 ? e + TX * TY : NO + NX + NY + TX * TY + ty * TX + tx;
-    slab::streamed<N, 0, N, 1>(K.L[1], U + (size_t)s_ym * ES + j * S0, acc);
-    slab::streamed<N, 0, N, 1>(K.R[1], U + (size_t)s_yp * ES + j * S0, acc);
-    slab::streamed<N, 1, N, 1>(K.L[2], U + (size_t)s_zm * ES + j * S0, acc);
-    slab::streamed<N, 1, N, 1>(K.R[2], U + (size_t)s_zp * ES + j * S0, acc);
+    if (half == 0) slab_phase_a<N, TX, TY, TZ, 0, NR, Cfg>(K, box, U, e, j, tx, ty, tz, gy, gz, acc);
+    else slab_phase_a<N, TX, TY, TZ, (SPLIT == 1 ? N : NR), N, Cfg>(K, box, U, e, j, tx, ty, tz, gy, gz, acc);
   }
   __syncthreads();                                            // y/z halo slots are dead from here on: they become the exchange buffer
   if (worker) {
-    // ---- phase B: slab m2 = j, axis x (slow index m0 with stride S0, fast index m1 with stride N)
-    double pb[N2];
-#pragma unroll
-    for (int t = 0; t < N2; ++t) pb[t] = 0.0;
-    const int s_xm = tx > 0 ? e - 1 : NO + tz * TY + ty, s_xp = tx < TX - 1 ? e + 1 : NO + TY * TZ + tz * TY + ty;
-    const double* own = U + (size_t)e * ES + j;
-    slab::streamed<N, 0, S0, N>(K.S[0], own, pb);
-    if (gx == 0) slab::streamed<N, 0, S0, N>(K.Dlo[0], own, pb);
-    if (gx == box.gn[0] - 1) slab::streamed<N, 0, S0, N>(K.Dhi[0], own, pb);
-    slab::streamed<N, 0, S0, N>(K.L[0], U + (size_t)s_xm * ES + j, pb);
-    slab::streamed<N, 0, S0, N>(K.R[0], U + (size_t)s_xp * ES + j, pb);
-#pragma unroll
-    for (int t = 0; t < N2; ++t) Xe[(t / N) * S0 + (t % N) * N + j] = pb[t];
+    if (half == 0) slab_phase_b<N, TX, TY, TZ, 0, NR, Cfg>(K, box, U, e, j, tx, ty, tz, gx);
+    else slab_phase_b<N, TX, TY, TZ, (SPLIT == 1 ? N : NR), N, Cfg>(K, box, U, e, j, tx, ty, tz, gx);
   }
   // the load-vector rows of the elements this warp will store are requested now: their latency hides behind the
   // barrier and the combine step instead of sitting in front of every store
@@ -215,8 +314,8 @@ dg_kronecker_slab_kernel(const __grid_constant__ KronTabDev<N> K, const __grid_c
   }
   __syncthreads();
   if (worker) {
-#pragma unroll
-    for (int t = 0; t < N2; ++t) { acc[t] += Xe[j * S0 + t]; Xe[j * S0 + t] = acc[t]; }
+    if (half == 0) slab_combine<N, 0, NR, Cfg>(U, e, j, acc);
+    else slab_combine<N, (SPLIT == 1 ? N : NR), N, Cfg>(U, e, j, acc);
   }
   __syncthreads();
 
