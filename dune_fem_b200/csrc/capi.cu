@@ -474,8 +474,23 @@ template <int N, int TX, int TY, int TZ, int MINB, int SPLIT> static int launch_
   auto kern = dg_kronecker_slab_kernel<N, TX, TY, TZ, MINB, SPLIT>;
   static bool attr_set = false;
   if (!attr_set) { CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes())); attr_set = true; }
-  kern<<<(unsigned)((long long)tx * ty * tz), Cfg::kThreads, Cfg::smem_bytes(), op->sp->mesh->ctx->stream>>>(K, b, op->d_perm, u, w, bvec, tx, ty);
-  CUDA_OK(cudaGetLastError()); return B200FEM_OK;
+  static int sms = 0;
+  if (!sms) CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, op->sp->mesh->ctx->device));
+  const long long ntiles = (long long)tx * ty * tz;
+  REQUIRE(ntiles < (1ll << 31), B200FEM_ERR_NOT_IMPLEMENTED, "slab kernel: too many tiles");
+  static const char* pw = std::getenv("B200FEM_SLAB_WAVES");     // CTAs per resident slot (0: one CTA per tile, the non-persistent schedule)
+  const int waves = pw ? std::atoi(pw) : 1;
+  const long long grid = waves > 0 ? std::min<long long>(ntiles, (long long)waves * MINB * sms) : ntiles;
+  static long long* d_tl = nullptr; static int tl_calls = 0;
+  if (!d_tl && std::getenv("B200FEM_SLAB_TIMELINE")) { CUDA_OK(cudaMalloc(&d_tl, 64)); CUDA_OK(cudaMemset(d_tl, 0, 64)); }
+  kern<<<(unsigned)grid, Cfg::kThreads, Cfg::smem_bytes(), op->sp->mesh->ctx->stream>>>(K, b, op->d_perm, u, w, bvec, tx, ty, (int)ntiles, d_tl);
+  CUDA_OK(cudaGetLastError());
+  if (d_tl && ++tl_calls == 12) {
+    long long h[8]; cudaDeviceSynchronize(); cudaMemcpy(h, d_tl, 64, cudaMemcpyDeviceToHost);
+    std::fprintf(stderr, "[b200fem slab timeline, clocks] staging issued %lld | data landed %lld | phase A %lld | phase B %lld | b rows + barrier + combine %lld | store %lld\n",
+                 h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5]);
+  }
+  return B200FEM_OK;
 }
 
 static long long* g_dbg = nullptr; static int g_dbg_calls = 0;

@@ -258,7 +258,7 @@ template <int N, int TX, int TY, int TZ, int MINB, int SPLIT>
 __global__ void __launch_bounds__(KronSlabCfg<N, TX, TY, TZ, SPLIT>::kThreads, MINB)
 dg_kronecker_slab_kernel(const __grid_constant__ KronTabDev<N> K, const __grid_constant__ BoxDev box, const int* __restrict__ perm_g,
                          const double* __restrict__ u, double* __restrict__ w, const double* __restrict__ bvec,
-                         const int tiles_x, const int tiles_y) {
+                         const int tiles_x, const int tiles_y, const int ntiles, long long* __restrict__ timeline) {
   using Cfg = KronSlabCfg<N, TX, TY, TZ, SPLIT>;
   constexpr int N2 = Cfg::N2, N3 = Cfg::N3, S0 = Cfg::S0, ES = Cfg::ES, NO = Cfg::NO, NX = Cfg::NX, KS = Cfg::KS, NR = Cfg::NR;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -267,8 +267,6 @@ dg_kronecker_slab_kernel(const __grid_constant__ KronTabDev<N> K, const __grid_c
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   for (int t = tid; t < N3; t += Cfg::kThreads) tinv[perm_g[t]] = t;
-  const int bx = blockIdx.x % tiles_x, by = (blockIdx.x / tiles_x) % tiles_y, bz = blockIdx.x / (tiles_x * tiles_y);
-  const int x0 = box.own_lo[0] + bx * TX, y0 = box.own_lo[1] + by * TY, z0 = box.own_lo[2] + bz * TZ;
   __syncthreads();
 
   // shared-memory offset (inside an element) of the doubles this lane moves when its warp stages / stores an element
@@ -276,9 +274,21 @@ dg_kronecker_slab_kernel(const __grid_constant__ KronTabDev<N> K, const __grid_c
 #pragma unroll
   for (int k = 0; k < KS; ++k) { const int s = lane + 32 * k; const int t = s < N3 ? tinv[s] : 0; doff[k] = (t / N2) * S0 + (t % N2); }
 
+  // persistent over tiles: the per-CTA prologue above and the CTA launch are paid once per resident slot, not once per tile
+  // (a CTA's lifetime was ~10 us per tile of which only ~3 us were FMAs)
+#pragma unroll 1
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  const int bx = tile % tiles_x, by = (tile / tiles_x) % tiles_y, bz = tile / (tiles_x * tiles_y);
+  const int x0 = box.own_lo[0] + bx * TX, y0 = box.own_lo[1] + by * TY, z0 = box.own_lo[2] + bz * TZ;
+
+  // optional timeline of one CTA (B200FEM_SLAB_TIMELINE): clock64 stamps of the phases of its second tile
+  const bool stamp = timeline != nullptr && blockIdx.x == 77 && tile == blockIdx.x + (int)gridDim.x && tid == 0;
+  if (stamp) timeline[0] = clock64();
   slab::stage_tile<Cfg, TX, TY, TZ>(box, u, U, doff, x0, y0, z0, warp, lane);
+  if (stamp) timeline[1] = clock64();
   slab::cp_async_wait_all();
   __syncthreads();
+  if (stamp) timeline[2] = clock64();
 
   // ------------------------------ compute: thread (e, j[, half]) ------------------------------
   // SPLIT = 2: the two halves of a slab (rows [0, NR) and [NR, N)) belong to different WARPS (half = warp-uniform), so both
@@ -294,6 +304,7 @@ dg_kronecker_slab_kernel(const __grid_constant__ KronTabDev<N> K, const __grid_c
     else slab_phase_a<N, TX, TY, TZ, (SPLIT == 1 ? N : NR), N, Cfg>(K, box, U, e, j, tx, ty, tz, gy, gz, acc);
   }
   __syncthreads();                                            // y/z halo slots are dead from here on: they become the exchange buffer
+  if (stamp) timeline[3] = clock64();
   if (worker) {
     if (half == 0) slab_phase_b<N, TX, TY, TZ, 0, NR, Cfg>(K, box, U, e, j, tx, ty, tz, gx);
     else slab_phase_b<N, TX, TY, TZ, (SPLIT == 1 ? N : NR), N, Cfg>(K, box, U, e, j, tx, ty, tz, gx);
@@ -312,6 +323,7 @@ dg_kronecker_slab_kernel(const __grid_constant__ KronTabDev<N> K, const __grid_c
 #pragma unroll
     for (int k = 0; k < KS; ++k) { const int s = lane + 32 * k; breg[i][k] = (bvec && owned && s < N3) ? bvec[gbase[i] + s] : 0.0; }
   }
+  if (stamp) timeline[4] = clock64();
   __syncthreads();
   if (worker) {
     if (half == 0) slab_combine<N, 0, NR, Cfg>(U, e, j, acc);
@@ -319,6 +331,7 @@ dg_kronecker_slab_kernel(const __grid_constant__ KronTabDev<N> K, const __grid_c
   }
   __syncthreads();
 
+  if (stamp) timeline[5] = clock64();
   // ------------------------------ store: one warp per element, stored order, coalesced ------------------------------
 #pragma unroll
   for (int i = 0; i < ELW; ++i) {
@@ -329,6 +342,9 @@ dg_kronecker_slab_kernel(const __grid_constant__ KronTabDev<N> K, const __grid_c
       const int s = lane + 32 * k;
       if (s < N3) w[gbase[i] + s] = X[doff[k]] - breg[i][k];
     }
+  }
+  __syncthreads();                                            // the exchange slots have been read: the next tile may be staged
+  if (stamp) timeline[6] = clock64();
   }
 }
 
