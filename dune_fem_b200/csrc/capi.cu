@@ -63,6 +63,7 @@ struct b200fem_operator {
   double *d_u = nullptr, *d_w = nullptr;                       // staging for the host-pointer API
   double *d_h = nullptr, *d_r = nullptr, *d_p = nullptr, *d_x = nullptr, *d_b = nullptr, *d_partial = nullptr, *d_sums = nullptr, *d_hist = nullptr;
   CgState* d_cg = nullptr; int hist_cap = 0; unsigned int* d_counter = nullptr;
+  std::vector<double*> gmres_v; double* d_gm_partial = nullptr; double* d_gm_sums = nullptr; int gm_cap = 0;   // GMRES basis and reduction scratch
   double *d_rstar = nullptr, *d_s = nullptr, *d_tmp = nullptr, *d_partial5 = nullptr, *d_sums5 = nullptr; BicgState* d_bicg = nullptr;   // BiCGStab work vectors
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr; cudaEvent_t pipe_ev[2 * 16 + 2] = {};   // host-pointer apply: copy/compute pipeline
   bool want_dot = false; int dot_parts = 0; double* d_dot_partial = nullptr; int dot_cap = 0;     // <u, A u> fused into the lattice kernel (CG)
@@ -855,6 +856,9 @@ extern "C" int b200fem_operator_destroy(b200fem_operator* op) {
   for (void* p : {(void*)op->d_perm, (void*)op->d_bvec, (void*)op->d_dmask, (void*)op->d_dvals, (void*)op->d_aux, (void*)op->d_u, (void*)op->d_w, (void*)op->d_h, (void*)op->d_r,
                   (void*)op->d_p, (void*)op->d_x, (void*)op->d_b, (void*)op->d_partial, (void*)op->d_sums, (void*)op->d_hist, (void*)op->d_cg, (void*)op->d_lag_rows, (void*)op->d_counter, (void*)op->d_rstar, (void*)op->d_s, (void*)op->d_tmp, (void*)op->d_partial5, (void*)op->d_sums5, (void*)op->d_bicg, (void*)op->d_dot_partial}) if (p) cudaFree(p);
   if (op->cg_graph) cudaGraphExecDestroy(op->cg_graph);
+  for (double* q : op->gmres_v) if (q) cudaFree(q);
+  if (op->d_gm_partial) cudaFree(op->d_gm_partial);
+  if (op->d_gm_sums) cudaFree(op->d_gm_sums);
   halo_plan_p2p_free(op->halo_p2p); halo_plan_free(op->halo); halo_plan_dg_free(op->halo_dg); free_map_cache(op);
   if (op->comm_stream) cudaStreamDestroy(op->comm_stream);
   if (op->h2d_stream) cudaStreamDestroy(op->h2d_stream);
@@ -1076,6 +1080,109 @@ extern "C" int b200fem_cg_solve(b200fem_operator* op, const double* b_host, doub
   if (!op->d_x) { CUDA_OK(cudaMalloc(&op->d_x, bytes)); CUDA_OK(cudaMalloc(&op->d_b, bytes)); }
   CUDA_OK(cudaMemcpyAsync(op->d_x, x_host, bytes, cudaMemcpyHostToDevice, st)); CUDA_OK(cudaMemcpyAsync(op->d_b, b_host, bytes, cudaMemcpyHostToDevice, st));
   int rc = b200fem_cg_solve_dev(op, op->d_b, op->d_x, epsilon, maxit, tolcrit, iterations, history); if (rc) return rc;
+  CUDA_OK(cudaMemcpyAsync(x_host, op->d_x, bytes, cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st));
+  return B200FEM_OK;
+}
+
+// LinearSolver::gmres (solver/linear/gmres.hh:117-301), unpreconditioned, on the homogeneous linear part of the operator
+extern "C" int b200fem_gmres_solve_dev(b200fem_operator* op, const double* b, double* u, int m, double epsilon, int maxit, int tolcrit, int* iterations, double* history) {
+  REQUIRE(op && b && u && iterations, B200FEM_ERR_INVALID, "gmres: null argument");
+  REQUIRE(tolcrit >= 0 && tolcrit <= 2, B200FEM_ERR_INVALID, "gmres: unknown tolerance criterion");
+  REQUIRE(m >= 1 && m <= 200, B200FEM_ERR_INVALID, "gmres: restart must be in [1, 200]");
+  b200fem_space* s = op->sp; b200fem_ctx* c = s->mesh->ctx; cudaStream_t st = c->stream; const long long n = s->size;
+  CUDA_OK(cudaSetDevice(c->device));
+  const size_t bytes = sizeof(double) * (size_t)n;
+  while ((int)op->gmres_v.size() < m + 1) { double* q = nullptr; CUDA_OK(cudaMalloc(&q, bytes)); op->gmres_v.push_back(q); }
+  if (op->gm_cap < m + 2) {
+    if (op->d_gm_partial) cudaFree(op->d_gm_partial); if (op->d_gm_sums) cudaFree(op->d_gm_sums);
+    CUDA_OK(cudaMalloc(&op->d_gm_partial, sizeof(double) * (size_t)(m + 2) * kRedBlocks)); CUDA_OK(cudaMalloc(&op->d_gm_sums, sizeof(double) * (size_t)(m + 2)));
+    op->gm_cap = m + 2;
+  }
+  std::vector<double*>& v = op->gmres_v;
+  // device scalar products of `count` (vector, v_l) pairs -> d_gm_sums[offset ..], globally reduced
+  auto reduce = [&](int offset, int count) -> int {
+    for (int q = 0; q < count; ++q) reduce_final_kernel<<<1, kRedThreads, 0, st>>>(op->d_gm_partial + (size_t)(offset + q) * kRedBlocks, kRedBlocks, op->d_gm_sums + offset + q);
+    CUDA_OK(cudaGetLastError());
+    if (c->world > 1 && c->nccl.AllReduce(op->d_gm_sums + offset, op->d_gm_sums + offset, (size_t)count, /*ncclDouble*/ 8, /*ncclSum*/ 0, c->comm, st) != 0) return fail(B200FEM_ERR_COMM, "ncclAllReduce failed");
+    return B200FEM_OK;
+  };
+  auto norm2 = [&](const double* x, double* out) -> int {            // <x,x> over primary dofs, on the host
+    dot_partial_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(x, x, op->d_aux, n, op->d_gm_partial);
+    int e = reduce(0, 1); if (e) return e;
+    CUDA_OK(cudaMemcpyAsync(out, op->d_gm_sums, sizeof(double), cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st));
+    return B200FEM_OK;
+  };
+  std::vector<double> H((size_t)(m + 1) * m, 0.0), g(m + 1, 0.0), sn(m, 0.0), cs(m, 0.0), y(m + 1, 0.0), gd(m + 2, 0.0);
+  auto Hm = [&](int i, int j) -> double& { return H[(size_t)i * m + j]; };
+  auto rotate = [](double& x, double& yy, double cc, double ss) { const double _x = x, _y = yy; x = cc * _x + ss * _y; yy = cc * _y - ss * _x; };
+  double tol = epsilon, t = 0;
+  int rc;
+  if (tolcrit == B200FEM_TOL_RELATIVE) { rc = norm2(b, &t); if (rc) return rc; tol *= std::sqrt(t); }
+  int it = 0;
+  while (true) {
+    rc = apply_dev_impl(op, u, v[0], true); if (rc) return rc;                                                  // v0 = A u - b
+    axpy_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(-1.0, b, v[0], n);
+    rc = norm2(v[0], &t); if (rc) return rc;
+    const double res = std::sqrt(t);
+    REQUIRE(std::isfinite(res), B200FEM_ERR_INVALID, "gmres: residual is not finite");
+    if (tolcrit == B200FEM_TOL_RESIDUAL_REDUCTION && it == 0) tol *= res;
+    if (res <= tol * (1 + 1e-15)) break;
+    g[0] = -res; for (int i = 1; i <= m; ++i) g[i] = 0.0;
+    scale_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(v[0], 1.0 / res, n);
+    for (int j = 0; j < m; ++j) {
+      double* vjp = v[j + 1];
+      rc = apply_dev_impl(op, v[j], vjp, true); if (rc) return rc;
+      // classical Gram-Schmidt: all j+1 scalar products of vjp in one (chunked) sweep, then the axpys, then the norm -- the
+      // coefficients never leave the device; ONE device->host copy per iteration brings H(0..j, j) and H(j+1, j)^2
+      for (int l0 = 0; l0 <= j; l0 += kGemvChunk) {
+        GmresVecs V; const int cnt = std::min(kGemvChunk, j + 1 - l0); for (int q = 0; q < kGemvChunk; ++q) V.v[q] = v[std::min(l0 + q, j)];
+        gmres_gemv_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(vjp, V, cnt, op->d_aux, n, op->d_gm_partial + (size_t)(1 + l0) * kRedBlocks);
+      }
+      rc = reduce(1, j + 1); if (rc) return rc;
+      for (int l0 = 0; l0 <= j; l0 += kGemvChunk) {
+        GmresVecs V; const int cnt = std::min(kGemvChunk, j + 1 - l0); for (int q = 0; q < kGemvChunk; ++q) V.v[q] = v[std::min(l0 + q, j)];
+        gmres_axpys_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(vjp, V, cnt, op->d_gm_sums + 1 + l0, -1.0, n);
+      }
+      dot_partial_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(vjp, vjp, op->d_aux, n, op->d_gm_partial);
+      rc = reduce(0, 1); if (rc) return rc;
+      CUDA_OK(cudaMemcpyAsync(gd.data(), op->d_gm_sums, sizeof(double) * (size_t)(j + 2), cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st));
+      for (int i = 0; i <= j; ++i) Hm(i, j) = gd[1 + i];
+      Hm(j + 1, j) = std::sqrt(gd[0]);
+      scale_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(vjp, 1.0 / Hm(j + 1, j), n);
+      for (int i = 0; i < j; ++i) rotate(Hm(i + 1, j), Hm(i, j), cs[i], sn[i]);                                 // Givens rotations, gmres.hh:227-239
+      const double hjj = Hm(j, j), hjpj = Hm(j + 1, j), nrm = std::sqrt(hjj * hjj + hjpj * hjpj);
+      cs[j] = hjj / nrm; sn[j] = -hjpj / nrm;
+      rotate(Hm(j + 1, j), Hm(j, j), cs[j], sn[j]);
+      rotate(g[j + 1], g[j], cs[j], sn[j]);
+      REQUIRE(std::isfinite(g[j + 1]), B200FEM_ERR_INVALID, "gmres: breakdown (non-finite Hessenberg entry)");
+      if (history && it < std::max(maxit, 1)) history[it] = std::fabs(g[j + 1]);
+      ++it;
+      if (std::fabs(g[j + 1]) < tol || it >= maxit) break;
+    }
+    int last = it % m; if (last == 0) last = m;
+    for (int i = last - 1; i >= 0; --i) {                                                                       // back substitution, :255-260
+      double d = 0; for (int k = 0; k < last - (i + 1); ++k) d += Hm(i, i + 1 + k) * y[i + 1 + k];
+      y[i] = (g[i] - d) / Hm(i, i);
+    }
+    CUDA_OK(cudaMemcpyAsync(op->d_gm_sums, y.data(), sizeof(double) * (size_t)last, cudaMemcpyHostToDevice, st));
+    for (int l0 = 0; l0 < last; l0 += kGemvChunk) {                                                             // u += (v_0 .. v_last-1) y
+      GmresVecs V; const int cnt = std::min(kGemvChunk, last - l0); for (int q = 0; q < kGemvChunk; ++q) V.v[q] = v[std::min(l0 + q, last - 1)];
+      gmres_axpys_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(u, V, cnt, op->d_gm_sums + l0, 1.0, n);
+    }
+    CUDA_OK(cudaStreamSynchronize(st));          // y is a host vector that is rewritten in the next cycle
+    if (std::fabs(g[last]) < tol || it >= maxit) break;
+  }
+  CUDA_OK(cudaGetLastError());
+  *iterations = (it < maxit) ? it : -it;
+  return B200FEM_OK;
+}
+extern "C" int b200fem_gmres_solve(b200fem_operator* op, const double* b_host, double* x_host, int restart, double epsilon, int maxit, int tolcrit, int* iterations, double* history) {
+  REQUIRE(op && b_host && x_host && iterations, B200FEM_ERR_INVALID, "gmres: null argument");
+  b200fem_space* s = op->sp; cudaStream_t st = s->mesh->ctx->stream; const size_t bytes = sizeof(double) * (size_t)s->size;
+  CUDA_OK(cudaSetDevice(s->mesh->ctx->device));
+  if (!op->d_x) { CUDA_OK(cudaMalloc(&op->d_x, bytes)); CUDA_OK(cudaMalloc(&op->d_b, bytes)); }
+  CUDA_OK(cudaMemcpyAsync(op->d_x, x_host, bytes, cudaMemcpyHostToDevice, st)); CUDA_OK(cudaMemcpyAsync(op->d_b, b_host, bytes, cudaMemcpyHostToDevice, st));
+  int rc = b200fem_gmres_solve_dev(op, op->d_b, op->d_x, restart, epsilon, maxit, tolcrit, iterations, history); if (rc) return rc;
   CUDA_OK(cudaMemcpyAsync(x_host, op->d_x, bytes, cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st));
   return B200FEM_OK;
 }

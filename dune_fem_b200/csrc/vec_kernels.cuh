@@ -316,6 +316,43 @@ __global__ void __launch_bounds__(kRedThreads) bicg_update_kernel(double* __rest
   if (last_block_done(counter) && threadIdx.x == 0) { st->x_applied = st->iterations; *counter = 0; }
 }
 
+// ---- GMRES (solver/linear/gmres.hh:117-301) vector work; the (m+1) x m Hessenberg matrix, the Givens rotations and the
+// back substitution are O(m^2) scalars and stay on the host like in the reference ----
+constexpr int kGemvChunk = 8;
+struct GmresVecs { const double* v[kGemvChunk]; };
+// y[l] = <vjp, v_l> over primary dofs for up to kGemvChunk basis vectors in ONE sweep over vjp (gemv, gmres.hh:64-92);
+// partial[l * gridDim.x + block]
+__global__ void __launch_bounds__(kRedThreads) gmres_gemv_kernel(const double* __restrict__ vjp, const GmresVecs V, int count, const uint8_t* __restrict__ aux,
+                                                                 long long n, double* __restrict__ partial) {
+  double d[kGemvChunk];
+#pragma unroll
+  for (int l = 0; l < kGemvChunk; ++l) d[l] = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (aux && aux[i]) continue;
+    const double x = vjp[i];
+#pragma unroll
+    for (int l = 0; l < kGemvChunk; ++l) if (l < count) d[l] = fma(x, V.v[l][i], d[l]);
+  }
+#pragma unroll
+  for (int l = 0; l < kGemvChunk; ++l) { const double t = block_sum(d[l]); if (threadIdx.x == 0 && l < count) partial[(size_t)l * gridDim.x + blockIdx.x] = t; }
+}
+// y += sign * sum_l coef[l] v_l for up to kGemvChunk vectors, coefficients read from device memory, applied in order
+// (vjp.axpy(-global_dot[l], v[l]) for l = 0..j, gmres.hh:214-217; u.axpy(y[i], v[i]), :289-292)
+__global__ void gmres_axpys_kernel(double* __restrict__ y, const GmresVecs V, int count, const double* __restrict__ coef, double sign, long long n) {
+  double c[kGemvChunk];
+#pragma unroll
+  for (int l = 0; l < kGemvChunk; ++l) c[l] = l < count ? sign * coef[l] : 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double s = y[i];
+#pragma unroll
+    for (int l = 0; l < kGemvChunk; ++l) if (l < count) s = fma(c[l], V.v[l][i], s);
+    y[i] = s;
+  }
+}
+__global__ void scale_kernel(double* __restrict__ x, double a, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) x[i] *= a;
+}
+
 // strong Dirichlet rows: w_d = u_d - g_d   (schemes/dirichletwrapper.hh:101-105; Operation::sub)
 __global__ void dirichlet_sub_kernel(const double* __restrict__ u, double* __restrict__ w, const uint8_t* __restrict__ mask,
                                      const double* __restrict__ g, long long n) {

@@ -152,9 +152,10 @@ class MOLGalerkinOperator : public GalerkinOperator<DiscreteFunctionT> {
 // Dune::Fem::CgInverseOperator = KrylovInverseOperator< DF, SolverParameter::cg > (solver/krylovinverseoperators.hh:46-281)
 struct SolverParameter {                       // solver/parameter.hh:21-295, keys fem.solver.*
   double tolerance = 1e-8; int errorMeasure = B200FEM_TOL_ABSOLUTE; int maxIterations = 1000; bool verbose = false;
+  int gmresRestart = 20;                        // fem.solver.gmres.restart (parameter.hh:197-201)
 };
 // KrylovInverseOperator< DF, method > (solver/krylovinverseoperators.hh:46-288): method cg -> linear/cg.hh, bicgstab -> linear/bicgstab.hh
-enum SolverMethod { cg = 0, bicgstab = 1 };
+enum SolverMethod { cg = 0, bicgstab = 1, gmres = 2 };
 template <class DiscreteFunctionT, int method = cg>
 class KrylovInverseOperator {
  public:
@@ -165,9 +166,14 @@ class KrylovInverseOperator {
   void operator()(const DiscreteFunctionT& rhs, DiscreteFunctionT& x) const {        // inverseoperatorinterface.hh:81-84
     if (!op_) throw InvalidStateException("KrylovInverseOperator: no operator bound");
     residuals_.assign((std::size_t)std::max(parameter_.maxIterations, 1), 0.0);
-    auto solve = method == bicgstab ? b200fem_bicgstab_solve : b200fem_cg_solve;
-    check(solve(op_->handle(), rhs.leakPointer(), x.leakPointer(), parameter_.tolerance, parameter_.maxIterations,
-                parameter_.errorMeasure, &iterations_, residuals_.data()));
+    if (method == gmres)
+      check(b200fem_gmres_solve(op_->handle(), rhs.leakPointer(), x.leakPointer(), parameter_.gmresRestart, parameter_.tolerance,
+                                parameter_.maxIterations, parameter_.errorMeasure, &iterations_, residuals_.data()));
+    else {
+      auto solve = method == bicgstab ? b200fem_bicgstab_solve : b200fem_cg_solve;
+      check(solve(op_->handle(), rhs.leakPointer(), x.leakPointer(), parameter_.tolerance, parameter_.maxIterations,
+                  parameter_.errorMeasure, &iterations_, residuals_.data()));
+    }
   }
   int iterations() const { return iterations_; }                                       // negative: not converged (linear/cg.hh:116, bicgstab.hh:208-211)
   bool converged() const { return iterations_ >= 0; }
@@ -178,5 +184,6 @@ class KrylovInverseOperator {
 };
 template <class DiscreteFunctionT> using CgInverseOperator = KrylovInverseOperator<DiscreteFunctionT, cg>;                // krylovinverseoperators.hh:284
 template <class DiscreteFunctionT> using BicgstabInverseOperator = KrylovInverseOperator<DiscreteFunctionT, bicgstab>;    // :288
+template <class DiscreteFunctionT> using GmresInverseOperator = KrylovInverseOperator<DiscreteFunctionT, gmres>;          // :295
 
 }  // namespace B200Fem

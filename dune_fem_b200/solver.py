@@ -61,6 +61,28 @@ class BicgstabInverseOperator(CgInverseOperator):
     _label = "Fem::BiCGstab it: {} : {}"
 
 
+class GmresInverseOperator(CgInverseOperator):
+    """KrylovInverseOperator< DF, SolverParameter::gmres > (solver/krylovinverseoperators.hh:295 ->
+    solver/linear/gmres.hh:117-301): restarted GMRES, "gmres.restart" (default 20, solver/parameter.hh:197-201)."""
+    _label = "Fem::GMRES it: {} : {}"
+
+    def __call__(self, rhs, x):
+        if self._op is None:
+            raise RuntimeError("GmresInverseOperator: no operator bound")
+        p = self.parameters
+        it = C.c_int()
+        hist = np.zeros(max(int(p["maxiterations"]), 1))
+        capi.check(capi.lib().b200fem_gmres_solve(self._op.handle, capi.ptr(rhs), capi.ptr(x), int(p.get("gmres.restart", 20)),
+                                                  float(p["tolerance"]), int(p["maxiterations"]), _ERRORMEASURE[p["errormeasure"]],
+                                                  C.byref(it), capi.ptr(hist)))
+        self._iterations = it.value
+        self.residuals = hist[:abs(it.value)]
+        if p["verbose"]:
+            for i, r in enumerate(self.residuals):
+                print(self._label.format(i, r))
+        return it.value
+
+
 def KrylovInverseOperator(parameters=None):
     """fem.solver.method selects the Krylov method (solver/parameter.hh; krylovinverseoperators.hh:83,126-131)."""
     method = {k.replace("fem.solver.", ""): v for k, v in (parameters or {}).items()}.get("method", "cg")
@@ -68,4 +90,6 @@ def KrylovInverseOperator(parameters=None):
         return CgInverseOperator(parameters)
     if method == "bicgstab":
         return BicgstabInverseOperator(parameters)
-    raise NotImplementedError(f"KrylovInverseOperator: method {method!r} (cg and bicgstab are available)")
+    if method == "gmres":
+        return GmresInverseOperator(parameters)
+    raise NotImplementedError(f"KrylovInverseOperator: method {method!r} (cg, bicgstab and gmres are available)")

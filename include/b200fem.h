@@ -150,6 +150,16 @@ int b200fem_bicgstab_solve(b200fem_operator* op, const double* b_host, double* x
 int b200fem_bicgstab_solve_dev(b200fem_operator* op, const double* b_dev, double* x_dev, double epsilon, int max_iterations,
                                int tolerance_criteria, int* iterations, double* history);
 
+/* KrylovInverseOperator<gmres> (solver/krylovinverseoperators.hh:142-160 -> solver/linear/gmres.hh:117-301, unpreconditioned):
+ * restarted GMRES(restart) ("fem.solver.gmres.restart", default 20, solver/parameter.hh:197-201) with the reference's classical
+ * Gram-Schmidt sweep and Givens rotations; the basis vectors and all vector work stay on the device, the (restart+1) x restart
+ * Hessenberg system on the host.  history receives |g[j+1]| per iteration ("Fem::GMRES it: i : ...").  *iterations is negative when
+ * max_iterations was reached. */
+int b200fem_gmres_solve(b200fem_operator* op, const double* b_host, double* x_host, int restart, double epsilon, int max_iterations,
+                        int tolerance_criteria, int* iterations, double* history);
+int b200fem_gmres_solve_dev(b200fem_operator* op, const double* b_dev, double* x_dev, int restart, double epsilon, int max_iterations,
+                            int tolerance_criteria, int* iterations, double* history);
+
 /* BLAS-1 on device dof vectors (function/blockvectors/defaultblockvectors.hh:39-150) and the dot product over
  * primary dofs followed by the global sum (function/common/scalarproducts.hh:115-127) */
 int b200fem_dot_dev(b200fem_operator* op, const double* x_dev, const double* y_dev, double* result);

@@ -652,6 +652,57 @@ static int bicgstab(const std::function<void(const double*, double*)>& op, int64
   return (iterations >= maxIterations) ? -iterations : iterations;
 }
 
+// LinearSolver::gmres (solver/linear/gmres.hh:117-301; Saad & Schultz 1986), unpreconditioned: restarted GMRES(m) with
+// classical Gram-Schmidt (all j+1 scalar products in one sweep, gemv :64-92) and Givens rotations.  Conventions of the
+// reference: v0 = A u - b (so g[0] = -res), convergence test on |g[j+1]| < tolerance * {1 | sqrt(b.b) | res_0}, the outer
+// loop stops when res <= tolerance (1 + 1e-15); returns iterations, negative when maxIterations was reached.
+static int gmres(const std::function<void(const double*, double*)>& op, int64_t n, double* u, const double* b, int m,
+                 double tolerance, int maxIterations, int tolCrit, double* history) {
+  std::vector<std::vector<double>> v(m + 1, std::vector<double>(n));
+  std::vector<double> H((size_t)(m + 1)*m, 0.0), g(m + 1, 0.0), sn(m, 0.0), cs(m, 0.0), y(m + 1, 0.0), gd(m + 1, 0.0);
+  auto Hm = [&](int i, int j) -> double& { return H[(size_t)i*m + j]; };
+  auto rotate = [](double& x, double& yy, double c, double s) { const double _x = x, _y = yy; x = c*_x + s*_y; yy = c*_y - s*_x; };
+  double tol = tolerance;
+  if (tolCrit == 1) tol *= std::sqrt(dot(b, b, n));
+  int iterations = 0;
+  while (true) {
+    op(u, v[0].data());
+    for (int64_t i = 0; i < n; ++i) v[0][i] -= b[i];
+    const double res = std::sqrt(dot(v[0].data(), v[0].data(), n));
+    if (tolCrit == 2 && iterations == 0) tol *= res;
+    if (res <= tol*(1 + 1e-15)) break;
+    g[0] = -res; for (int i = 1; i <= m; ++i) g[i] = 0.0;
+    for (int64_t i = 0; i < n; ++i) v[0][i] *= (1.0/res);
+    for (int j = 0; j < m; ++j) {
+      std::vector<double>& vjp = v[j + 1];
+      op(v[j].data(), vjp.data());
+      for (int l = 0; l <= j; ++l) gd[l] = 0.0;
+      for (int64_t i = 0; i < n; ++i) for (int l = 0; l <= j; ++l) gd[l] += vjp[i]*v[l][i];
+      for (int i = 0; i <= j; ++i) Hm(i, j) = gd[i];
+      for (int l = 0; l <= j; ++l) for (int64_t i = 0; i < n; ++i) vjp[i] += -gd[l]*v[l][i];
+      Hm(j + 1, j) = std::sqrt(dot(vjp.data(), vjp.data(), n));
+      { const double sc = 1.0/Hm(j + 1, j); for (int64_t i = 0; i < n; ++i) vjp[i] *= sc; }
+      for (int i = 0; i < j; ++i) rotate(Hm(i + 1, j), Hm(i, j), cs[i], sn[i]);
+      const double hjj = Hm(j, j), hjpj = Hm(j + 1, j), norm = std::sqrt(hjj*hjj + hjpj*hjpj);
+      cs[j] = hjj/norm; sn[j] = -hjpj/norm;
+      rotate(Hm(j + 1, j), Hm(j, j), cs[j], sn[j]);
+      rotate(g[j + 1], g[j], cs[j], sn[j]);
+      if (history) history[iterations] = std::abs(g[j + 1]);
+      ++iterations;
+      if (std::abs(g[j + 1]) < tol || iterations >= maxIterations) break;
+    }
+    int last = iterations % m; if (last == 0) last = m;
+    for (int i = last - 1; i >= 0; --i) {
+      double d = 0; for (int k = 0; k < last - (i + 1); ++k) d += Hm(i, i + 1 + k)*y[i + 1 + k];
+      y[i] = (g[i] - d)/Hm(i, i);
+    }
+    for (int i = 0; i < last; ++i) for (int64_t q = 0; q < n; ++q) u[q] += y[i]*v[i][q];
+    if (std::abs(g[last]) < tol) break;
+    if (iterations >= maxIterations) break;   // (the reference keeps restarting here with a one-step Krylov space until the outer test passes; bounded instead)
+  }
+  return (iterations < maxIterations) ? iterations : -iterations;
+}
+
 }  // namespace oracle
 
 // ===========================================================================
@@ -713,6 +764,10 @@ int fo_cg(FoOperator* op, const double* b, double* x, double eps, int maxit, int
 int fo_bicgstab(FoOperator* op, const double* b, double* x, double eps, int maxit, int tolCrit, double* history) {
   Operator* A = op->linear.get();
   return bicgstab([A](const double* in, double* out) { A->apply(in, out); }, op->space->sp->size, x, b, eps, maxit, tolCrit, history);
+}
+int fo_gmres(FoOperator* op, const double* b, double* x, int restart, double eps, int maxit, int tolCrit, double* history) {
+  Operator* A = op->linear.get();
+  return gmres([A](const double* in, double* out) { A->apply(in, out); }, op->space->sp->size, x, b, restart, eps, maxit, tolCrit, history);
 }
 double fo_dot(const double* x, const double* y, int64_t n) { return dot(x, y, n); }
 

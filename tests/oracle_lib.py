@@ -57,6 +57,8 @@ def lib():
     L.fo_dirichlet.argtypes = [C.c_void_p, _bp, _dp]
     L.fo_cg.restype = C.c_int
     L.fo_cg.argtypes = [C.c_void_p, _dp, _dp, C.c_double, C.c_int, C.c_int, C.c_void_p]
+    L.fo_gmres.restype = C.c_int
+    L.fo_gmres.argtypes = [C.c_void_p, _dp, _dp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_void_p]
     L.fo_bicgstab.restype = C.c_int
     L.fo_bicgstab.argtypes = [C.c_void_p, _dp, _dp, C.c_double, C.c_int, C.c_int, C.c_void_p]
     L.fo_dot.restype = C.c_double
@@ -158,6 +160,13 @@ class Operator:
         hist = np.zeros(max(maxit, 1))
         it = lib().fo_cg(self._h, np.ascontiguousarray(b, dtype=np.float64), x, eps, maxit, tolcrit,
                          hist.ctypes.data_as(C.c_void_p))
+        return it, x, hist[:abs(it)]
+
+    def gmres(self, b, x0, eps, maxit, tolcrit=0, restart=20):
+        x = np.array(x0, dtype=np.float64, copy=True)
+        hist = np.zeros(max(maxit, 1))
+        it = lib().fo_gmres(self._h, np.ascontiguousarray(b, dtype=np.float64), x, restart, eps, maxit, tolcrit,
+                            hist.ctypes.data_as(C.c_void_p))
         return it, x, hist[:abs(it)]
 
     def bicgstab(self, b, x0, eps, maxit, tolcrit=0):

@@ -332,3 +332,37 @@ def test_bicgstab_iterates_match_reference_recurrence(order):
         op.applyLinear(x, w)
         assert np.linalg.norm(w - b) < 1e-6 * max(1.0, np.linalg.norm(b))
         assert rel(x, x_ref) < 1e-6
+
+
+@pytest.mark.parametrize("order,restart", [(1, 5), (2, 20), (3, 11)])
+def test_gmres_iterates_match_reference_recurrence(order, restart):
+    """KrylovInverseOperator<gmres> (solver/linear/gmres.hh): |g[j+1]| history, iteration counts (restarts included) and
+    iterates against the oracle restatement on the non-symmetric advection-diffusion DG operator."""
+    n = [5, 4, 4] if order < 3 else [3, 3, 2]
+    space, osp = dg_pair(n, [0, 0, 0], [1, 1, 1], order, True)
+    kw = dict(eps=0.1, b=(1.0, 0.5, 0.2), c=1.0, beta=20.0 * order ** 2, dirichlet_mask=0b111111, data=2)
+    op = fem.operator.galerkin(space, **kw)
+    oop = ol.Operator(osp, skeleton=True, boundary=True, **kw)
+    b = op.loadVector()
+    x0 = np.zeros(space.size)
+    for maxit in (1, restart - 1, 2 * restart + 3):
+        inv = fem.solver.GmresInverseOperator({"tolerance": 1e-30, "maxiterations": maxit, "gmres.restart": restart})
+        inv.bind(op)
+        x = x0.copy()
+        it = inv(b, x)
+        it_ref, x_ref, hist_ref = oop.gmres(b, x0, 1e-30, maxit, restart=restart)
+        assert it == it_ref == -maxit
+        np.testing.assert_allclose(inv.residuals, hist_ref, rtol=1e-7)
+        assert rel(x, x_ref) < 1e-8
+    for crit, tc in (("absolute", 0), ("relative", 1), ("residualreduction", 2)):
+        inv = fem.solver.KrylovInverseOperator({"fem.solver.method": "gmres", "tolerance": 1e-9, "maxiterations": 3000, "errormeasure": crit,
+                                                "gmres.restart": restart})
+        inv.bind(op)
+        x = x0.copy()
+        it = inv(b, x)
+        it_ref, x_ref, _ = oop.gmres(b, x0, 1e-9, 3000, tolcrit=tc, restart=restart)
+        assert it > 0 and it_ref > 0 and abs(it - it_ref) <= max(2, it_ref // 20)
+        assert rel(x, x_ref) < 1e-6
+        w = np.empty(space.size)
+        op.applyLinear(x, w)
+        assert np.linalg.norm(w - b) < 1e-6 * max(1.0, np.linalg.norm(b))

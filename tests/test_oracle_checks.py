@@ -179,3 +179,18 @@ def test_bicgstab_oracle_solves_nonsymmetric_system():
     # relative criterion scales the tolerance by sqrt(b.b) (bicgstab.hh:88-92)
     it3, _, hist3 = op.bicgstab(b, np.zeros(sp.size), 1e-6, 500, tolcrit=1)
     assert hist3[-1] < 1e-6 * np.linalg.norm(b) <= hist3[-2]
+
+
+def test_gmres_oracle_solves_nonsymmetric_system():
+    """LinearSolver::gmres restatement (solver/linear/gmres.hh:117-301): the last |g[j+1]| is the true residual norm, a
+    full-length Krylov space converges faster than restarted cycles, maxIterations yields a negative count."""
+    sp = ol.Space([4, 4, 4], [0, 0, 0], [1, 1, 1], ol.DG_LEGENDRE_HIER, 1)
+    kw = dict(eps=0.1, b=(1.0, 0.5, 0.2), c=1.0, beta=20.0, dirichlet_mask=0b111111, data=2)
+    op = ol.Operator(sp, skeleton=True, boundary=True, **kw)
+    b = -op.apply(np.zeros(sp.size))
+    it20, x, hist = op.gmres(b, np.zeros(sp.size), 1e-10, 1000, restart=20)
+    assert it20 > 0 and abs(np.linalg.norm(op.apply(x, linear=True) - b) - hist[-1]) < 1e-12
+    it5, _, _ = op.gmres(b, np.zeros(sp.size), 1e-10, 1000, restart=5)
+    assert it5 > it20
+    it, _, h7 = op.gmres(b, np.zeros(sp.size), 1e-30, 7, restart=5)
+    assert it == -7 and np.all(np.diff(h7[:5]) <= 0)           # GMRES residuals decrease monotonically inside a cycle
