@@ -18,7 +18,7 @@ SYMBOLS = [
     "b200fem_space_size", "b200fem_space_local_size", "b200fem_space_elements", "b200fem_space_dofmap",
     "b200fem_operator_create", "b200fem_operator_destroy", "b200fem_operator_apply", "b200fem_operator_apply_linear",
     "b200fem_operator_apply_dev", "b200fem_operator_load_vector", "b200fem_operator_set_communicate",
-    "b200fem_operator_set_quadrature_orders", "b200fem_operator_set_kernel", "b200fem_operator_set_inverse_mass", "b200fem_operator_dirichlet",
+    "b200fem_operator_set_quadrature_orders", "b200fem_operator_set_kernel", "b200fem_operator_set_inverse_mass", "b200fem_operator_linearize", "b200fem_operator_linearize_dev", "b200fem_operator_dirichlet",
     "b200fem_operator_timing", "b200fem_cg_solve", "b200fem_cg_solve_dev", "b200fem_bicgstab_solve", "b200fem_bicgstab_solve_dev", "b200fem_gmres_solve", "b200fem_gmres_solve_dev", "b200fem_dot_dev", "b200fem_axpy_dev",
     "b200fem_ctx_set_nccl", "b200fem_nccl_unique_id", "b200fem_nccl_init", "b200fem_communicate_dev",
 ]
@@ -78,7 +78,8 @@ def lib():
         "b200fem_operator_apply": [vp, vp, vp], "b200fem_operator_apply_linear": [vp, vp, vp],
         "b200fem_operator_apply_dev": [vp, vp, vp, C.c_int], "b200fem_operator_load_vector": [vp, vp],
         "b200fem_operator_set_communicate": [vp, C.c_int], "b200fem_operator_set_quadrature_orders": [vp, C.c_uint, C.c_uint],
-        "b200fem_operator_set_kernel": [vp, C.c_int], "b200fem_operator_set_inverse_mass": [vp, C.c_int], "b200fem_operator_dirichlet": [vp, vp, vp],
+        "b200fem_operator_set_kernel": [vp, C.c_int], "b200fem_operator_set_inverse_mass": [vp, C.c_int],
+        "b200fem_operator_linearize": [vp, vp, dbl], "b200fem_operator_linearize_dev": [vp, vp, dbl], "b200fem_operator_dirichlet": [vp, vp, vp],
         "b200fem_operator_timing": [vp, P(Timing)],
         "b200fem_cg_solve": [vp, vp, vp, dbl, C.c_int, C.c_int, P(C.c_int), vp],
         "b200fem_cg_solve_dev": [vp, vp, vp, dbl, C.c_int, C.c_int, P(C.c_int), vp],

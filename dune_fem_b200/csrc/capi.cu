@@ -63,6 +63,7 @@ struct b200fem_operator {
   double *d_u = nullptr, *d_w = nullptr;                       // staging for the host-pointer API
   double *d_h = nullptr, *d_r = nullptr, *d_p = nullptr, *d_x = nullptr, *d_b = nullptr, *d_partial = nullptr, *d_sums = nullptr, *d_hist = nullptr;
   CgState* d_cg = nullptr; int hist_cap = 0; unsigned int* d_counter = nullptr;
+  bool jac_mode = false; double *d_jac_u = nullptr, *d_jac_opu = nullptr, *d_jac_b = nullptr; FdState* d_fd = nullptr;   // AutomaticDifferenceLinearOperator
   std::vector<double*> gmres_v; double* d_gm_partial = nullptr; double* d_gm_sums = nullptr; int gm_cap = 0;   // GMRES basis and reduction scratch
   double *d_rstar = nullptr, *d_s = nullptr, *d_tmp = nullptr, *d_partial5 = nullptr, *d_sums5 = nullptr; BicgState* d_bicg = nullptr;   // BiCGStab work vectors
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr; cudaEvent_t pipe_ev[2 * 16 + 2] = {};   // host-pointer apply: copy/compute pipeline
@@ -708,7 +709,27 @@ static int exchange(b200fem_operator* op, double* v, cudaStream_t st) {
 // GalerkinOperator::evaluate + w.communicate() (galerkin.hh:1459-1496).  On several ranks the DG apply is split: the owned
 // layers next to rank interfaces are computed first, their Copy exchange then runs on a second stream while the interior
 // is computed -- the exchange the reference performs serially after the loop is hidden behind the interior elements.
+static int reduce_sums(b200fem_operator* op, int count);
+static int ensure_cg_buffers(b200fem_operator* op, int maxit);
+static int apply_dev_impl(b200fem_operator* op, const double* u, double* w, bool linear);
+// AutomaticDifferenceLinearOperator::operator() (automaticdifferenceoperator.hh:124-149), everything on the device and on the
+// operator's stream (no host round trip: the difference quotient can sit inside a captured CG graph)
+static int apply_fd_jacobian(b200fem_operator* op, const double* arg, double* dest) {
+  b200fem_space* s = op->sp; cudaStream_t st = s->mesh->ctx->stream; const long long n = s->size;
+  int rc = ensure_cg_buffers(op, 1); if (rc) return rc;
+  dot_partial_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(arg, arg, op->d_aux, n, op->d_partial + kRedBlocks);          // arg.normSquaredDofs()
+  reduce_final_kernel<<<1, kRedThreads, 0, st>>>(op->d_partial + kRedBlocks, kRedBlocks, op->d_sums + 3);
+  b200fem_ctx* c = s->mesh->ctx;
+  if (c->world > 1 && c->nccl.AllReduce(op->d_sums + 3, op->d_sums + 3, 1, /*ncclDouble*/ 8, /*ncclSum*/ 0, c->comm, st) != 0) return fail(B200FEM_ERR_COMM, "ncclAllReduce failed");
+  fd_eps_kernel<<<1, 32, 0, st>>>(op->d_sums + 3, op->d_fd);
+  fd_perturb_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(op->d_jac_b, op->d_jac_u, arg, n, op->d_fd);
+  const bool want_dot = op->want_dot; op->want_dot = false;   // (a fused <u, w> of the perturbed apply is not <arg, J arg>)
+  op->jac_mode = false; rc = apply_dev_impl(op, op->d_jac_b, dest, false); op->jac_mode = true; op->want_dot = want_dot; op->dot_parts = 0; if (rc) return rc;   // (*op_)(b_, dest)
+  fd_quotient_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(dest, op->d_jac_opu, n, op->d_fd);
+  CUDA_OK(cudaGetLastError()); return B200FEM_OK;
+}
 static int apply_dev_impl(b200fem_operator* op, const double* u, double* w, bool linear) {
+  if (linear && op->jac_mode) return apply_fd_jacobian(op, u, w);
   b200fem_space* s = op->sp; cudaStream_t st = s->mesh->ctx->stream;
   const bool timing_events = op->timing_enabled && !op->capturing;
   if (timing_events) CUDA_OK(cudaEventRecord(op->ev0, st));
@@ -857,6 +878,7 @@ extern "C" int b200fem_operator_destroy(b200fem_operator* op) {
                   (void*)op->d_p, (void*)op->d_x, (void*)op->d_b, (void*)op->d_partial, (void*)op->d_sums, (void*)op->d_hist, (void*)op->d_cg, (void*)op->d_lag_rows, (void*)op->d_counter, (void*)op->d_rstar, (void*)op->d_s, (void*)op->d_tmp, (void*)op->d_partial5, (void*)op->d_sums5, (void*)op->d_bicg, (void*)op->d_dot_partial}) if (p) cudaFree(p);
   if (op->cg_graph) cudaGraphExecDestroy(op->cg_graph);
   for (double* q : op->gmres_v) if (q) cudaFree(q);
+  for (void* q : {(void*)op->d_jac_u, (void*)op->d_jac_opu, (void*)op->d_jac_b, (void*)op->d_fd}) if (q) cudaFree(q);
   if (op->d_gm_partial) cudaFree(op->d_gm_partial);
   if (op->d_gm_sums) cudaFree(op->d_gm_sums);
   halo_plan_p2p_free(op->halo_p2p); halo_plan_free(op->halo); halo_plan_dg_free(op->halo_dg); free_map_cache(op);
@@ -911,7 +933,7 @@ static int apply_host(b200fem_operator* op, const double* u, double* w, bool lin
   CUDA_OK(cudaSetDevice(s->mesh->ctx->device));
   int rc = ensure_staging(op); if (rc) return rc;
   const bool no_pipeline = std::getenv("B200FEM_NO_PIPELINE") != nullptr;     // (read per call: tests toggle it)
-  if (!no_pipeline && s->kind != B200FEM_LAGRANGE && s->mesh->ctx->world == 1 && s->box.dim == 3 && bytes >= (8u << 20) && s->box.n[2] >= 16 && default_quadrature(op))
+  if (!no_pipeline && !(linear && op->jac_mode) && s->kind != B200FEM_LAGRANGE && s->mesh->ctx->world == 1 && s->box.dim == 3 && bytes >= (8u << 20) && s->box.n[2] >= 16 && default_quadrature(op))
   {
     static const char* ch = std::getenv("B200FEM_PIPE_CHUNKS");
     const int want = ch ? std::max(2, std::min(16, std::atoi(ch))) : 8;
@@ -956,6 +978,33 @@ extern "C" int b200fem_operator_set_inverse_mass(b200fem_operator* op, int on) {
   if (op->d_bvec) { CUDA_OK(cudaSetDevice(op->sp->mesh->ctx->device)); CUDA_OK(cudaStreamSynchronize(op->sp->mesh->ctx->stream)); CUDA_OK(cudaFree(op->d_bvec)); op->d_bvec = nullptr; }
   if (op->cg_graph) { cudaGraphExecDestroy(op->cg_graph); op->cg_graph = nullptr; }
   return B200FEM_OK;
+}
+extern "C" int b200fem_operator_linearize_dev(b200fem_operator* op, const double* u, double eps) {
+  REQUIRE(op, B200FEM_ERR_INVALID, "linearize: null operator");
+  b200fem_space* s = op->sp; b200fem_ctx* c = s->mesh->ctx; cudaStream_t st = c->stream; const long long n = s->size; const size_t bytes = sizeof(double) * (size_t)n;
+  CUDA_OK(cudaSetDevice(c->device));
+  if (op->cg_graph) { cudaGraphExecDestroy(op->cg_graph); op->cg_graph = nullptr; }        // the captured iteration applied another operator
+  if (!u) { op->jac_mode = false; return B200FEM_OK; }
+  int rc = ensure_cg_buffers(op, 1); if (rc) return rc;
+  if (!op->d_jac_u) { CUDA_OK(cudaMalloc(&op->d_jac_u, bytes)); CUDA_OK(cudaMalloc(&op->d_jac_opu, bytes)); CUDA_OK(cudaMalloc(&op->d_jac_b, bytes)); CUDA_OK(cudaMalloc(&op->d_fd, sizeof(FdState))); }
+  // jOp.set(u, op, eps) (automaticdifferenceoperator.hh:152-166): u_, op_u_ = op(u), norm_u_ = sqrt(u.u) when eps is dynamic
+  if (u != op->d_jac_u) CUDA_OK(cudaMemcpyAsync(op->d_jac_u, u, bytes, cudaMemcpyDeviceToDevice, st));
+  op->jac_mode = false;
+  rc = apply_dev_impl(op, op->d_jac_u, op->d_jac_opu, false); if (rc) return rc;
+  FdState h{}; h.eps_given = eps; h.norm_u = 0; h.eps = eps;
+  if (eps <= 0) { double uu = 0; rc = b200fem_dot_dev(op, op->d_jac_u, op->d_jac_u, &uu); if (rc) return rc; h.norm_u = std::sqrt(uu); }
+  CUDA_OK(cudaMemcpyAsync(op->d_fd, &h, sizeof(FdState), cudaMemcpyHostToDevice, st)); CUDA_OK(cudaStreamSynchronize(st));
+  op->jac_mode = true;
+  return B200FEM_OK;
+}
+extern "C" int b200fem_operator_linearize(b200fem_operator* op, const double* u_host, double eps) {
+  REQUIRE(op, B200FEM_ERR_INVALID, "linearize: null operator");
+  if (!u_host) return b200fem_operator_linearize_dev(op, nullptr, eps);
+  b200fem_space* s = op->sp; cudaStream_t st = s->mesh->ctx->stream; const size_t bytes = sizeof(double) * (size_t)s->size;
+  CUDA_OK(cudaSetDevice(s->mesh->ctx->device));
+  if (!op->d_jac_u) { CUDA_OK(cudaMalloc(&op->d_jac_u, bytes)); CUDA_OK(cudaMalloc(&op->d_jac_opu, bytes)); CUDA_OK(cudaMalloc(&op->d_jac_b, bytes)); CUDA_OK(cudaMalloc(&op->d_fd, sizeof(FdState))); }
+  CUDA_OK(cudaMemcpyAsync(op->d_jac_u, u_host, bytes, cudaMemcpyHostToDevice, st));
+  return b200fem_operator_linearize_dev(op, op->d_jac_u, eps);
 }
 extern "C" int b200fem_operator_dirichlet(b200fem_operator* op, uint8_t* mask, double* values) {
   REQUIRE(op && mask && values, B200FEM_ERR_INVALID, "null");

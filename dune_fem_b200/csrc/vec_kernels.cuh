@@ -353,6 +353,26 @@ __global__ void scale_kernel(double* __restrict__ x, double a, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) x[i] *= a;
 }
 
+// ---- AutomaticDifferenceLinearOperator (operator/common/automaticdifferenceoperator.hh:124-149): dest = (L[u + eps arg] - L[u]) / eps ----
+struct FdState { double eps_given, norm_u, eps; };
+// eps = eps_given > 0 ? eps_given : sqrt((1 + |u|) macheps / |arg|^2)   (|arg|^2 = sums[0], globally reduced)
+__global__ void fd_eps_kernel(const double* __restrict__ sums, FdState* st) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const double me = 2.220446049250313e-16;
+    st->eps = st->eps_given > 0 ? st->eps_given : (sums[0] > me ? sqrt((1.0 + st->norm_u) * me / sums[0]) : sqrt(me));
+  }
+}
+// b = u + eps arg
+__global__ void fd_perturb_kernel(double* __restrict__ b, const double* __restrict__ u, const double* __restrict__ arg, long long n, const FdState* st) {
+  const double eps = st->eps;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) b[i] = fma(eps, arg[i], u[i]);
+}
+// dest = (dest - op_u) * (1 / eps)
+__global__ void fd_quotient_kernel(double* __restrict__ dest, const double* __restrict__ op_u, long long n, const FdState* st) {
+  const double inv = 1.0 / st->eps;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dest[i] = (dest[i] - op_u[i]) * inv;
+}
+
 // strong Dirichlet rows: w_d = u_d - g_d   (schemes/dirichletwrapper.hh:101-105; Operation::sub)
 __global__ void dirichlet_sub_kernel(const double* __restrict__ u, double* __restrict__ w, const uint8_t* __restrict__ mask,
                                      const double* __restrict__ g, long long n) {

@@ -129,6 +129,9 @@ class GalerkinOperator : public Operator<DiscreteFunctionT, DiscreteFunctionT> {
   void applyLinear(const DiscreteFunctionT& u, DiscreteFunctionT& w) const { check(b200fem_operator_apply_linear(h_, u.leakPointer(), w.leakPointer())); }
   void loadVector(DiscreteFunctionT& b) const { check(b200fem_operator_load_vector(h_, b.leakPointer())); }
   bool nonlinear() const override { return integrands_.gamma != 0.0; }
+  // AutomaticDifferenceOperator::jacobian: linearise at u; applyLinear and the Krylov solvers then act on J(u) (automaticdifferenceoperator.hh:108-166)
+  void linearize(const DiscreteFunctionT& u, double eps = 0.0) { check(b200fem_operator_linearize(h_, u.leakPointer(), eps)); }
+  void dropLinearization() { check(b200fem_operator_linearize(h_, nullptr, 0.0)); }
   void setCommunicate(bool communicate) { check(b200fem_operator_set_communicate(h_, communicate)); }                 // galerkin.hh:1409
   void setQuadratureOrders(unsigned interior, unsigned surface) { check(b200fem_operator_set_quadrature_orders(h_, interior, surface)); }   // :1418-1423
   const DiscreteFunctionSpaceType& domainSpace() const { return space_; }

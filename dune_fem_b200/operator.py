@@ -76,6 +76,12 @@ class GalerkinOperator:
     def setInverseMass(self, on=True):
         capi.check(capi.lib().b200fem_operator_set_inverse_mass(self.handle, int(on)))
 
+    # --- AutomaticDifferenceOperator::jacobian(u, jOp) (operator/common/automaticdifferenceoperator.hh:108-111) ---
+    def linearize(self, u=None, eps=0.0):
+        """jOp.set(u, op, eps): afterwards applyLinear and the Krylov solvers act on the difference-quotient Jacobian
+        J(u) v = (L[u + eps v] - L[u]) / eps (dynamic eps when eps <= 0); linearize(None) drops the linearisation."""
+        capi.check(capi.lib().b200fem_operator_linearize(self.handle, capi.ptr(u) if u is not None else None, float(eps)))
+
     def communicate_dev(self, v_ptr):
         capi.check(capi.lib().b200fem_communicate_dev(self.handle, C.c_void_p(v_ptr)))
 

@@ -127,6 +127,14 @@ int b200fem_operator_set_kernel(b200fem_operator* op, int kernel);
  * (operator/1order/localmassmatrix.hh:304-311, 421-434), fused into the kernels (scaled 1-D operators and load vector).
  * DG spaces only (B200FEM_ERR_NOT_IMPLEMENTED otherwise). */
 int b200fem_operator_set_inverse_mass(b200fem_operator* op, int on);
+/* AutomaticDifferenceOperator::jacobian / AutomaticDifferenceLinearOperator (operator/common/automaticdifferenceoperator.hh:58-166):
+ * Jacobian-free linearisation J(u) v = (L[u + eps v] - L[u]) / eps with the reference's dynamic eps = sqrt((1 + |u|) macheps / |v|^2)
+ * when eps <= 0 ("fem.differenceoperator.eps").  linearize(u) is jOp.set(u, op, eps): it stores u and L[u] on the device; while a
+ * linearisation is set, apply_linear / apply_dev(linear != 0) and the Krylov solvers act on J(u) instead of on the homogeneous
+ * linear part, i.e. a Newton step is  linearize(u);  solve J(u) delta = -L[u];  u += delta.  u_host == NULL drops the
+ * linearisation.  Works for every model, including the non-linear ones (gamma != 0) that have no Kronecker form. */
+int b200fem_operator_linearize(b200fem_operator* op, const double* u_host, double eps);
+int b200fem_operator_linearize_dev(b200fem_operator* op, const double* u_dev, double eps);
 /* strong Dirichlet marks and values (schemes/dirichletconstraints.hh:435-554) */
 int b200fem_operator_dirichlet(b200fem_operator* op, uint8_t* mask_host, double* values_host);
 int b200fem_operator_timing(b200fem_operator* op, b200fem_timing* out);

@@ -42,6 +42,7 @@
 #include <cassert>
 #include <chrono>
 #include <cmath>
+#include <limits>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -711,7 +712,11 @@ static int gmres(const std::function<void(const double*, double*)>& op, int64_t 
 using namespace oracle;
 
 struct FoSpace { std::unique_ptr<Space> sp; };
-struct FoOperator { FoSpace* space; std::unique_ptr<Operator> full, linear; };
+struct FoOperator {
+  FoSpace* space; std::unique_ptr<Operator> full, linear;
+  // AutomaticDifferenceLinearOperator state (operator/common/automaticdifferenceoperator.hh:58-92, set: :152-166)
+  std::vector<double> jac_u, jac_op_u; double jac_eps = 0, jac_norm_u = 0; bool jac_set = false;
+};
 
 extern "C" {
 
@@ -764,6 +769,34 @@ int fo_cg(FoOperator* op, const double* b, double* x, double eps, int maxit, int
 int fo_bicgstab(FoOperator* op, const double* b, double* x, double eps, int maxit, int tolCrit, double* history) {
   Operator* A = op->linear.get();
   return bicgstab([A](const double* in, double* out) { A->apply(in, out); }, op->space->sp->size, x, b, eps, maxit, tolCrit, history);
+}
+// AutomaticDifferenceLinearOperator::set (automaticdifferenceoperator.hh:152-166)
+void fo_operator_linearize(FoOperator* op, const double* u, double eps) {
+  const int64_t n = op->space->sp->size;
+  op->jac_u.assign(u, u + n); op->jac_op_u.resize(n);
+  op->full->apply(u, op->jac_op_u.data());
+  op->jac_eps = eps; op->jac_set = true;
+  if (eps <= 0) op->jac_norm_u = std::sqrt(dot(u, u, n));
+}
+// AutomaticDifferenceLinearOperator::operator() (automaticdifferenceoperator.hh:124-149): dest = (L[u + eps arg] - L[u]) / eps,
+// eps = sqrt((1 + |u|) macheps / |arg|^2) when no eps was given
+double fo_operator_apply_jacobian(FoOperator* op, const double* arg, double* dest) {
+  const int64_t n = op->space->sp->size;
+  double eps = op->jac_eps;
+  if (eps <= 0) {
+    const double me = std::numeric_limits<double>::epsilon(), np2 = dot(arg, arg, n);
+    eps = np2 > me ? std::sqrt((1.0 + op->jac_norm_u)*me/np2) : std::sqrt(me);
+  }
+  std::vector<double> b(op->jac_u);
+  for (int64_t i = 0; i < n; ++i) b[i] += eps*arg[i];
+  op->full->apply(b.data(), dest);
+  for (int64_t i = 0; i < n; ++i) dest[i] -= op->jac_op_u[i];
+  for (int64_t i = 0; i < n; ++i) dest[i] *= 1.0/eps;
+  return eps;
+}
+// Krylov solvers on the difference-quotient Jacobian (Newton step: J(u) delta = -L[u])
+int fo_gmres_jacobian(FoOperator* op, const double* b, double* x, int restart, double eps, int maxit, int tolCrit, double* history) {
+  return gmres([op](const double* in, double* out) { fo_operator_apply_jacobian(op, in, out); }, op->space->sp->size, x, b, restart, eps, maxit, tolCrit, history);
 }
 int fo_gmres(FoOperator* op, const double* b, double* x, int restart, double eps, int maxit, int tolCrit, double* history) {
   Operator* A = op->linear.get();

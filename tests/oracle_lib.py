@@ -57,6 +57,11 @@ def lib():
     L.fo_dirichlet.argtypes = [C.c_void_p, _bp, _dp]
     L.fo_cg.restype = C.c_int
     L.fo_cg.argtypes = [C.c_void_p, _dp, _dp, C.c_double, C.c_int, C.c_int, C.c_void_p]
+    L.fo_operator_linearize.argtypes = [C.c_void_p, _dp, C.c_double]
+    L.fo_operator_apply_jacobian.argtypes = [C.c_void_p, _dp, _dp]
+    L.fo_operator_apply_jacobian.restype = C.c_double
+    L.fo_gmres_jacobian.restype = C.c_int
+    L.fo_gmres_jacobian.argtypes = [C.c_void_p, _dp, _dp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_void_p]
     L.fo_gmres.restype = C.c_int
     L.fo_gmres.argtypes = [C.c_void_p, _dp, _dp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_void_p]
     L.fo_bicgstab.restype = C.c_int
@@ -160,6 +165,22 @@ class Operator:
         hist = np.zeros(max(maxit, 1))
         it = lib().fo_cg(self._h, np.ascontiguousarray(b, dtype=np.float64), x, eps, maxit, tolcrit,
                          hist.ctypes.data_as(C.c_void_p))
+        return it, x, hist[:abs(it)]
+
+    def linearize(self, u, eps=0.0):
+        """AutomaticDifferenceLinearOperator::set(u, op, eps) (operator/common/automaticdifferenceoperator.hh:152-166)"""
+        lib().fo_operator_linearize(self._h, np.ascontiguousarray(u, dtype=np.float64), float(eps))
+
+    def applyJacobian(self, v):
+        w = np.empty(self.space.size)
+        eps = lib().fo_operator_apply_jacobian(self._h, np.ascontiguousarray(v, dtype=np.float64), w)
+        return w, eps
+
+    def gmres_jacobian(self, b, x0, eps, maxit, tolcrit=0, restart=20):
+        x = np.array(x0, dtype=np.float64, copy=True)
+        hist = np.zeros(max(maxit, 1))
+        it = lib().fo_gmres_jacobian(self._h, np.ascontiguousarray(b, dtype=np.float64), x, restart, eps, maxit, tolcrit,
+                                     hist.ctypes.data_as(C.c_void_p))
         return it, x, hist[:abs(it)]
 
     def gmres(self, b, x0, eps, maxit, tolcrit=0, restart=20):

@@ -366,3 +366,56 @@ def test_gmres_iterates_match_reference_recurrence(order, restart):
         w = np.empty(space.size)
         op.applyLinear(x, w)
         assert np.linalg.norm(w - b) < 1e-6 * max(1.0, np.linalg.norm(b))
+
+
+def test_difference_quotient_jacobian_and_newton_krylov():
+    """AutomaticDifferenceLinearOperator (operator/common/automaticdifferenceoperator.hh:124-166) on the NON-LINEAR model
+    (gamma u^3, quadrature kernel): J(u) v against the oracle for a fixed and for the dynamic eps, then Newton-GMRES."""
+    space, osp = dg_pair([3, 3, 3], [0, 0, 0], [1, 1, 1], 1, True)
+    kw = dict(eps=0.5, b=(0.3, 0.2, 0.1), c=1.0, gamma=2.0, beta=20.0, dirichlet_mask=0b111111, data=2)
+    op = fem.operator.galerkin(space, **kw)
+    oop = ol.Operator(osp, skeleton=True, boundary=True, **kw)
+    rng = np.random.default_rng(23)
+    u, v = rng.uniform(-1, 1, space.size), rng.uniform(-1, 1, space.size)
+    w = np.empty(space.size)
+    # fixed eps: both sides do the same arithmetic, rounding differences are amplified by 1/eps only
+    op.linearize(u, eps=1e-4)
+    oop.linearize(u, eps=1e-4)
+    op.applyLinear(v, w)
+    ref, _ = oop.applyJacobian(v)
+    assert rel(w, ref) < 1e-9
+    # dynamic eps = sqrt((1 + |u|) macheps / |v|^2) ~ 1e-8: the quotient itself carries ~1e-8 of rounding noise
+    op.linearize(u)
+    oop.linearize(u)
+    op.applyLinear(v, w)
+    ref, eps = oop.applyJacobian(v)
+    assert 1e-9 < eps < 1e-7 and rel(w, ref) < 1e-5
+    # the true directional derivative: (eps grad v, grad phi) ... + 3 gamma u^2 v -- check against a centred difference of the oracle
+    h = 1e-5
+    central = (oop.apply(u + h * v) - oop.apply(u - h * v)) / (2 * h)
+    assert rel(w, central) < 1e-5
+    op.linearize(None)
+    op.applyLinear(v, w)
+    assert rel(w, oop.apply(v, linear=True)) < TOL                 # back to the homogeneous part L[v] - L[0]
+    # Newton-Krylov: J(u) delta = -L[u] with GMRES on the device, quadratic convergence as in the oracle
+    x, xo = np.zeros(space.size), np.zeros(space.size)
+    norms = []
+    for _ in range(6):
+        op(x, w)
+        norms.append(np.linalg.norm(w))
+        if norms[-1] < 1e-7:          # the quotient's rounding noise (~1e-8) is the floor of a Jacobian-free Newton method
+            break
+        op.linearize(x)
+        # (the quotient carries ~1e-8 of rounding noise: the linear solves are asked for a residual REDUCTION, an absolute
+        # tolerance below the noise floor would make restarted GMRES spin)
+        inv = fem.solver.GmresInverseOperator({"tolerance": 1e-7, "maxiterations": 400, "gmres.restart": 30, "errormeasure": "residualreduction"})
+        inv.bind(op)
+        d = np.zeros(space.size)
+        assert inv(-w, d) > 0
+        x += d
+        r = oop.apply(xo)
+        oop.linearize(xo)
+        _, do, _ = oop.gmres_jacobian(-r, np.zeros(space.size), 1e-7, 400, tolcrit=2, restart=30)
+        xo += do
+    assert len(norms) == 4 and norms[-1] < 1e-7 and norms[2] < 1e-2 * norms[1] and norms[3] < 1e-3 * norms[2]
+    assert rel(x, xo) < 1e-7

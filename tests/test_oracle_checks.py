@@ -194,3 +194,29 @@ def test_gmres_oracle_solves_nonsymmetric_system():
     assert it5 > it20
     it, _, h7 = op.gmres(b, np.zeros(sp.size), 1e-30, 7, restart=5)
     assert it == -7 and np.all(np.diff(h7[:5]) <= 0)           # GMRES residuals decrease monotonically inside a cycle
+
+
+def test_difference_quotient_jacobian_oracle():
+    """AutomaticDifferenceLinearOperator restatement: for a LINEAR operator the quotient reproduces A v (up to the rounding
+    noise 1/eps amplifies), and Newton-GMRES on the cubic reaction model converges quadratically."""
+    sp = ol.Space([3, 3, 3], [0, 0, 0], [1, 1, 1], ol.DG_LEGENDRE_HIER, 1)
+    lin = ol.Operator(sp, skeleton=True, boundary=True, eps=0.5, b=(0.3, 0.2, 0.1), c=1.0, beta=20.0, dirichlet_mask=0b111111, data=2)
+    rng = np.random.default_rng(1)
+    u, v = rng.uniform(-1, 1, sp.size), rng.uniform(-1, 1, sp.size)
+    lin.linearize(u)
+    w, eps = lin.applyJacobian(v)
+    av = lin.apply(v, linear=True)
+    assert np.abs(w - av).max() < 1e-6 * np.abs(av).max()
+    assert abs(eps - math.sqrt((1 + np.linalg.norm(u)) * np.finfo(float).eps / np.dot(v, v))) < 1e-20
+    op = ol.Operator(sp, skeleton=True, boundary=True, eps=0.5, b=(0.3, 0.2, 0.1), c=1.0, gamma=2.0, beta=20.0, dirichlet_mask=0b111111, data=2)
+    x, norms = np.zeros(sp.size), []
+    for _ in range(6):
+        r = op.apply(x)
+        norms.append(np.linalg.norm(r))
+        if norms[-1] < 1e-7:          # the quotient's rounding noise (~1e-8) is the floor of a Jacobian-free Newton method
+            break
+        op.linearize(x)
+        it, d, _ = op.gmres_jacobian(-r, np.zeros(sp.size), 1e-7, 400, tolcrit=2, restart=30)
+        assert it > 0
+        x += d
+    assert len(norms) == 4 and norms[-1] < 1e-7 and norms[2] < 1e-2 * norms[1] and norms[3] < 1e-3 * norms[2]
