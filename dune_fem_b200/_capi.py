@@ -19,7 +19,7 @@ SYMBOLS = [
     "b200fem_operator_create", "b200fem_operator_destroy", "b200fem_operator_apply", "b200fem_operator_apply_linear",
     "b200fem_operator_apply_dev", "b200fem_operator_load_vector", "b200fem_operator_set_communicate",
     "b200fem_operator_set_quadrature_orders", "b200fem_operator_set_kernel", "b200fem_operator_set_inverse_mass", "b200fem_operator_linearize", "b200fem_operator_linearize_dev", "b200fem_operator_dirichlet",
-    "b200fem_operator_timing", "b200fem_cg_solve", "b200fem_cg_solve_dev", "b200fem_bicgstab_solve", "b200fem_bicgstab_solve_dev", "b200fem_gmres_solve", "b200fem_gmres_solve_dev", "b200fem_dot_dev", "b200fem_axpy_dev",
+    "b200fem_operator_timing", "b200fem_cg_solve", "b200fem_cg_solve_dev", "b200fem_bicgstab_solve", "b200fem_bicgstab_solve_dev", "b200fem_gmres_solve", "b200fem_gmres_solve_dev", "b200fem_operator_diagonal", "b200fem_pcg_solve", "b200fem_pcg_solve_dev", "b200fem_dot_dev", "b200fem_axpy_dev",
     "b200fem_ctx_set_nccl", "b200fem_nccl_unique_id", "b200fem_nccl_init", "b200fem_communicate_dev",
 ]
 
@@ -85,6 +85,9 @@ def lib():
         "b200fem_cg_solve_dev": [vp, vp, vp, dbl, C.c_int, C.c_int, P(C.c_int), vp],
         "b200fem_bicgstab_solve": [vp, vp, vp, dbl, C.c_int, C.c_int, P(C.c_int), vp],
         "b200fem_bicgstab_solve_dev": [vp, vp, vp, dbl, C.c_int, C.c_int, P(C.c_int), vp],
+        "b200fem_operator_diagonal": [vp, vp],
+        "b200fem_pcg_solve": [vp, vp, vp, dbl, C.c_int, C.c_int, P(C.c_int), vp],
+        "b200fem_pcg_solve_dev": [vp, vp, vp, dbl, C.c_int, C.c_int, P(C.c_int), vp],
         "b200fem_gmres_solve": [vp, vp, vp, C.c_int, dbl, C.c_int, C.c_int, P(C.c_int), vp],
         "b200fem_gmres_solve_dev": [vp, vp, vp, C.c_int, dbl, C.c_int, C.c_int, P(C.c_int), vp],
         "b200fem_dot_dev": [vp, vp, vp, P(dbl)], "b200fem_axpy_dev": [vp, dbl, vp, vp],

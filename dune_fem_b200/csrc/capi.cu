@@ -64,6 +64,7 @@ struct b200fem_operator {
   double *d_h = nullptr, *d_r = nullptr, *d_p = nullptr, *d_x = nullptr, *d_b = nullptr, *d_partial = nullptr, *d_sums = nullptr, *d_hist = nullptr;
   CgState* d_cg = nullptr; int hist_cap = 0; unsigned int* d_counter = nullptr;
   bool jac_mode = false; double *d_jac_u = nullptr, *d_jac_opu = nullptr, *d_jac_b = nullptr; FdState* d_fd = nullptr;   // AutomaticDifferenceLinearOperator
+  double* d_dinv = nullptr; double *d_pq = nullptr, *d_ps = nullptr; bool dinv_mass = false;   // Jacobi preconditioner: 1 / diag(A) (+ the inverse-mass state it was built for), PCG work vectors
   std::vector<double*> gmres_v; double* d_gm_partial = nullptr; double* d_gm_sums = nullptr; int gm_cap = 0;   // GMRES basis and reduction scratch
   double *d_rstar = nullptr, *d_s = nullptr, *d_tmp = nullptr, *d_partial5 = nullptr, *d_sums5 = nullptr; BicgState* d_bicg = nullptr;   // BiCGStab work vectors
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr; cudaEvent_t pipe_ev[2 * 16 + 2] = {};   // host-pointer apply: copy/compute pipeline
@@ -878,6 +879,7 @@ extern "C" int b200fem_operator_destroy(b200fem_operator* op) {
                   (void*)op->d_p, (void*)op->d_x, (void*)op->d_b, (void*)op->d_partial, (void*)op->d_sums, (void*)op->d_hist, (void*)op->d_cg, (void*)op->d_lag_rows, (void*)op->d_counter, (void*)op->d_rstar, (void*)op->d_s, (void*)op->d_tmp, (void*)op->d_partial5, (void*)op->d_sums5, (void*)op->d_bicg, (void*)op->d_dot_partial}) if (p) cudaFree(p);
   if (op->cg_graph) cudaGraphExecDestroy(op->cg_graph);
   for (double* q : op->gmres_v) if (q) cudaFree(q);
+  for (void* q : {(void*)op->d_dinv, (void*)op->d_pq, (void*)op->d_ps}) if (q) cudaFree(q);
   for (void* q : {(void*)op->d_jac_u, (void*)op->d_jac_opu, (void*)op->d_jac_b, (void*)op->d_fd}) if (q) cudaFree(q);
   if (op->d_gm_partial) cudaFree(op->d_gm_partial);
   if (op->d_gm_sums) cudaFree(op->d_gm_sums);
@@ -1129,6 +1131,115 @@ extern "C" int b200fem_cg_solve(b200fem_operator* op, const double* b_host, doub
   if (!op->d_x) { CUDA_OK(cudaMalloc(&op->d_x, bytes)); CUDA_OK(cudaMalloc(&op->d_b, bytes)); }
   CUDA_OK(cudaMemcpyAsync(op->d_x, x_host, bytes, cudaMemcpyHostToDevice, st)); CUDA_OK(cudaMemcpyAsync(op->d_b, b_host, bytes, cudaMemcpyHostToDevice, st));
   int rc = b200fem_cg_solve_dev(op, op->d_b, op->d_x, epsilon, maxit, tolcrit, iterations, history); if (rc) return rc;
+  CUDA_OK(cudaMemcpyAsync(x_host, op->d_x, bytes, cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st));
+  return B200FEM_OK;
+}
+
+// diag(A) of the Kronecker form, on the host (setup cost O(N), once per operator)
+static int host_diagonal(b200fem_operator* op, std::vector<double>& diag, bool dirichlet_rows = true) {
+  b200fem_space* s = op->sp; const BoxDev& b = s->box;
+  REQUIRE(op->model.gamma == 0.0 && default_quadrature(op), B200FEM_ERR_NOT_IMPLEMENTED, "diagonal: needs a linear model with the default quadrature (Kronecker form)");
+  diag.assign((size_t)s->size, 0.0);
+  if (s->kind == B200FEM_LAGRANGE) {
+    REQUIRE(!op->model.has_skeleton, B200FEM_ERR_NOT_IMPLEMENTED, "skeleton integrands on continuous spaces");
+    const int k = s->order;
+    LagRowsHost rh = build_lagrange_rows(s->tab, op->model, b.dim, k, b.n, b.origin, b.gn, b.h);
+    const int W = 2 * k + 1;
+    LagrangeLayoutDev L = s->lay; L.lattice_map = s->lattice_map.empty() ? nullptr : s->lattice_map.data();
+    for (long long g2 = 0; g2 < L.lattice[2]; ++g2) for (long long g1 = 0; g1 < L.lattice[1]; ++g1) for (long long g0 = 0; g0 < L.lattice[0]; ++g0) {
+      const double m0 = rh.M[0][(size_t)g0 * W + k], m1 = rh.M[1][(size_t)g1 * W + k], m2 = rh.M[2][(size_t)g2 * W + k];
+      const double t0 = rh.T[0][(size_t)g0 * W + k], t1 = rh.T[1][(size_t)g1 * W + k], t2 = rh.T[2][(size_t)g2 * W + k];
+      const long long dof = lagrange_dof(L, g0, g1, g2);
+      diag[(size_t)dof] = t0 * m1 * m2 + m0 * t1 * m2 + m0 * m1 * t2;
+      if (dirichlet_rows && !op->h_dmask.empty() && op->h_dmask[(size_t)dof]) diag[(size_t)dof] = 1.0;      // DirichletWrapperOperator: identity rows
+    }
+    return B200FEM_OK;
+  }
+  const int N = s->n1, nb = s->nb;
+  KronHost kh = build_kron_tables(s->tab, op->model, b.dim, b.h, mass_scale(op));
+  for (long long e2 = 0; e2 < b.n[2]; ++e2) for (long long e1 = 0; e1 < b.n[1]; ++e1) for (long long e0 = 0; e0 < b.n[0]; ++e0) {
+    const long long ec[3] = {e0, e1, e2}; const long long e = e0 + b.n[0] * (e1 + b.n[1] * e2);
+    for (int t = 0; t < nb; ++t) {
+      const int idx[3] = {t / (N * N), (t / N) % N, t % N}; double v = 0;
+      for (int d = 0; d < 3; ++d) {
+        const int ii = idx[d] * N + idx[d]; const long long g = b.origin[d] + ec[d];
+        v += kh.S[d][ii] + (g == 0 ? kh.Dlo[d][ii] : 0.0) + (g == b.gn[d] - 1 ? kh.Dhi[d][ii] : 0.0);
+      }
+      diag[(size_t)(e * nb + s->perm[t])] = v;
+    }
+  }
+  return B200FEM_OK;
+}
+extern "C" int b200fem_operator_diagonal(b200fem_operator* op, double* diag_host) {
+  REQUIRE(op && diag_host, B200FEM_ERR_INVALID, "diagonal: null argument");
+  std::vector<double> d; int rc = host_diagonal(op, d); if (rc) return rc;
+  std::copy(d.begin(), d.end(), diag_host); return B200FEM_OK;
+}
+// LinearSolver::cg, preconditioned branch (solver/linear/cg.hh:52-56, 72-107) with the Jacobi preconditioner
+extern "C" int b200fem_pcg_solve_dev(b200fem_operator* op, const double* b, double* x, double epsilon, int maxit, int tolcrit, int* iterations, double* history) {
+  REQUIRE(op && b && x && iterations, B200FEM_ERR_INVALID, "pcg: null argument");
+  REQUIRE(tolcrit >= 0 && tolcrit <= 2, B200FEM_ERR_INVALID, "pcg: unknown tolerance criterion");
+  REQUIRE(!op->jac_mode, B200FEM_ERR_NOT_IMPLEMENTED, "pcg: no diagonal for a difference-quotient linearisation");
+  b200fem_space* s = op->sp; b200fem_ctx* c = s->mesh->ctx; cudaStream_t st = c->stream; const long long n = s->size; const size_t bytes = sizeof(double) * (size_t)n;
+  CUDA_OK(cudaSetDevice(c->device));
+  int rc = ensure_cg_buffers(op, maxit); if (rc) return rc;
+  if (!op->d_dinv || op->dinv_mass != op->inverse_mass) {
+    // several ranks, continuous space: interface nodes hold partial sums (like the apply), completed by the Add exchange before
+    // the Dirichlet rows are set to one
+    const bool shared_nodes = c->world > 1 && s->kind == B200FEM_LAGRANGE;
+    std::vector<double> d; rc = host_diagonal(op, d, !shared_nodes); if (rc) return rc;
+    if (!op->d_dinv) { CUDA_OK(cudaMalloc(&op->d_dinv, bytes)); CUDA_OK(cudaMalloc(&op->d_pq, bytes)); CUDA_OK(cudaMalloc(&op->d_ps, bytes)); }
+    CUDA_OK(cudaMemcpyAsync(op->d_dinv, d.data(), bytes, cudaMemcpyHostToDevice, st));
+    if (shared_nodes) {
+      rc = exchange(op, op->d_dinv, st); if (rc) return rc;
+      if (op->d_dmask) set_masked_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(op->d_dinv, op->d_dmask, 1.0, n);
+    }
+    invert_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(op->d_dinv, n);
+    CUDA_OK(cudaStreamSynchronize(st)); op->dinv_mass = op->inverse_mass;
+  }
+  double* p = op->d_p; double* q = op->d_pq; double* sv = op->d_ps; double* h = op->d_h;
+  CgState init{}; init.epsilon = epsilon; init.max_iterations = maxit; init.tol_criteria = tolcrit;
+  CUDA_OK(cudaMemcpyAsync(op->d_cg, &init, sizeof(CgState), cudaMemcpyHostToDevice, st));
+  rc = apply_dev_impl(op, x, h, true); if (rc) return rc;                                                       // h = A x
+  pcg_init_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(h, b, op->d_dinv, p, q, sv, op->d_aux, n, op->d_partial, op->d_partial + kRedBlocks);
+  rc = reduce_sums(op, 2); if (rc) return rc;
+  cg_init_final_kernel<<<1, 32, 0, st>>>(op->d_sums, op->d_cg);
+  const bool single = c->world == 1;
+  CgState host{}; const int chunk = 16;
+  for (int it = 0; it < maxit;) {
+    const int upto = std::min(maxit, it + chunk);
+    for (; it < upto; ++it) {
+      pcg_update_q_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(q, sv, n, op->d_cg);
+      rc = apply_dev_impl(op, q, h, true); if (rc) return rc;                                                   // h = A q
+      if (single) {
+        cg_dot_alpha_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(q, h, op->d_aux, n, op->d_partial, op->d_cg, op->d_counter);
+        pcg_update_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(x, p, sv, q, h, op->d_dinv, op->d_aux, n, op->d_partial, op->d_cg, op->d_hist, op->d_counter + 1);
+      } else {
+        cg_dot_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(q, h, op->d_aux, n, op->d_partial, op->d_cg);
+        rc = reduce_sums(op, 1); if (rc) return rc;
+        cg_alpha_kernel<<<1, 32, 0, st>>>(op->d_sums, op->d_cg);
+        pcg_update_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(x, p, sv, q, h, op->d_dinv, op->d_aux, n, op->d_partial, op->d_cg, nullptr, nullptr);
+        rc = reduce_sums(op, 1); if (rc) return rc;
+        cg_residual_kernel<<<1, 32, 0, st>>>(op->d_sums, op->d_cg, op->d_hist);
+      }
+    }
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpyAsync(&host, op->d_cg, sizeof(CgState), cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st));
+    if (host.done) break;
+  }
+  if (maxit <= 0) { CUDA_OK(cudaMemcpyAsync(&host, op->d_cg, sizeof(CgState), cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st)); }
+  REQUIRE(std::isfinite(host.residual), B200FEM_ERR_INVALID, "pcg: residual is not finite");
+  if (history && host.iterations > 0) { CUDA_OK(cudaMemcpyAsync(history, op->d_hist, sizeof(double) * host.iterations, cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st)); }
+  *iterations = (host.iterations < maxit) ? host.iterations : -host.iterations;
+  return B200FEM_OK;
+}
+extern "C" int b200fem_pcg_solve(b200fem_operator* op, const double* b_host, double* x_host, double epsilon, int maxit, int tolcrit, int* iterations, double* history) {
+  REQUIRE(op && b_host && x_host && iterations, B200FEM_ERR_INVALID, "pcg: null argument");
+  b200fem_space* s = op->sp; cudaStream_t st = s->mesh->ctx->stream; const size_t bytes = sizeof(double) * (size_t)s->size;
+  CUDA_OK(cudaSetDevice(s->mesh->ctx->device));
+  if (!op->d_x) { CUDA_OK(cudaMalloc(&op->d_x, bytes)); CUDA_OK(cudaMalloc(&op->d_b, bytes)); }
+  CUDA_OK(cudaMemcpyAsync(op->d_x, x_host, bytes, cudaMemcpyHostToDevice, st)); CUDA_OK(cudaMemcpyAsync(op->d_b, b_host, bytes, cudaMemcpyHostToDevice, st));
+  int rc = b200fem_pcg_solve_dev(op, op->d_b, op->d_x, epsilon, maxit, tolcrit, iterations, history); if (rc) return rc;
   CUDA_OK(cudaMemcpyAsync(x_host, op->d_x, bytes, cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st));
   return B200FEM_OK;
 }

@@ -373,6 +373,58 @@ __global__ void fd_quotient_kernel(double* __restrict__ dest, const double* __re
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dest[i] = (dest[i] - op_u[i]) * inv;
 }
 
+// ---- Jacobi-preconditioned CG: the preconditioned branch of LinearSolver::cg (cg.hh:52-56, 72-107) with B = diag(A)^-1 ----
+// after h = A x:  p = b - h ; q = s = B p ; partial <p,q> and <b,b>
+__global__ void __launch_bounds__(kRedThreads) pcg_init_kernel(const double* __restrict__ h, const double* __restrict__ b, const double* __restrict__ dinv,
+                                                               double* __restrict__ p, double* __restrict__ q, double* __restrict__ s_, const uint8_t* __restrict__ aux,
+                                                               long long n, double* __restrict__ partial, double* __restrict__ partial_b) {
+  double s = 0, sb = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double bv = b[i], pv = bv - h[i], qv = dinv[i] * pv;
+    p[i] = pv; q[i] = qv; s_[i] = qv;
+    if (!aux || !aux[i]) { s = fma(pv, qv, s); sb = fma(bv, bv, sb); }
+  }
+  s = block_sum(s); if (threadIdx.x == 0) partial[blockIdx.x] = s;
+  sb = block_sum(sb); if (threadIdx.x == 0) partial_b[blockIdx.x] = sb;
+}
+// q <- beta q + s   (cg.hh:76-80)
+__global__ void pcg_update_q_kernel(double* __restrict__ q, const double* __restrict__ s_, long long n, const CgState* st) {
+  if (st->done || st->iterations == 0) return;
+  const double beta = st->residual / st->prev_residual;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) q[i] = q[i] * beta + s_[i];
+}
+// x += alpha q ; p -= alpha h ; s = B p ; partial <p,s>   (cg.hh:92-101); the last block closes the iteration
+__global__ void __launch_bounds__(kRedThreads) pcg_update_kernel(double* __restrict__ x, double* __restrict__ p, double* __restrict__ s_, const double* __restrict__ q,
+                                                                 const double* __restrict__ h, const double* __restrict__ dinv, const uint8_t* __restrict__ aux, long long n,
+                                                                 double* partial, CgState* st, double* __restrict__ history, unsigned int* counter) {
+  if (st->done) return;
+  const double alpha = st->alpha;
+  double s = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    x[i] = fma(alpha, q[i], x[i]);
+    const double pv = fma(-alpha, h[i], p[i]), sv = dinv[i] * pv;
+    p[i] = pv; s_[i] = sv;
+    if (!aux || !aux[i]) s = fma(pv, sv, s);
+  }
+  s = block_sum(s);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+  if (!counter || !last_block_done(counter)) return;
+  const double t = final_sum(partial);
+  if (threadIdx.x == 0) {
+    st->prev_residual = st->residual; st->residual = t;
+    if (history) history[st->iterations] = sqrt(t);
+    st->iterations += 1;
+    if (!(st->residual > st->tolerance) || st->iterations >= st->max_iterations) st->done = 1;
+    *counter = 0;
+  }
+}
+__global__ void set_masked_kernel(double* __restrict__ d, const uint8_t* __restrict__ mask, double value, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) if (mask[i]) d[i] = value;
+}
+__global__ void invert_kernel(double* __restrict__ d, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) d[i] = 1.0 / d[i];
+}
+
 // strong Dirichlet rows: w_d = u_d - g_d   (schemes/dirichletwrapper.hh:101-105; Operation::sub)
 __global__ void dirichlet_sub_kernel(const double* __restrict__ u, double* __restrict__ w, const uint8_t* __restrict__ mask,
                                      const double* __restrict__ g, long long n) {

@@ -73,6 +73,12 @@ class GalerkinOperator:
         capi.check(capi.lib().b200fem_dot_dev(self.handle, C.c_void_p(x_ptr), C.c_void_p(y_ptr), C.byref(r)))
         return r.value
 
+    def diagonal(self):
+        """diag(A) of the homogeneous linear part (what DiagonalPreconditioner needs, solver/diagonalpreconditioner.hh)"""
+        d = np.empty(self.space.size)
+        capi.check(capi.lib().b200fem_operator_diagonal(self.handle, capi.ptr(d)))
+        return d
+
     def setInverseMass(self, on=True):
         capi.check(capi.lib().b200fem_operator_set_inverse_mass(self.handle, int(on)))
 

@@ -54,6 +54,13 @@ class CgInverseOperator:
         return self._iterations >= 0
 
 
+class JacobiCgInverseOperator(CgInverseOperator):
+    """CG with "fem.solver.preconditioning.method: jacobi": the preconditioned branch of LinearSolver::cg
+    (solver/linear/cg.hh:52-56, 72-107) with B = diag(A)^-1 built matrix-free (the reference's DiagonalPreconditioner needs an
+    assembled operator, solver/diagonalpreconditioner.hh:37-57)."""
+    _solve = "b200fem_pcg_solve"
+
+
 class BicgstabInverseOperator(CgInverseOperator):
     """KrylovInverseOperator< DF, SolverParameter::bicgstab > (solver/krylovinverseoperators.hh:288 ->
     solver/linear/bicgstab.hh:64-214): for non-symmetric operators (advection-diffusion)."""
@@ -86,8 +93,9 @@ class GmresInverseOperator(CgInverseOperator):
 def KrylovInverseOperator(parameters=None):
     """fem.solver.method selects the Krylov method (solver/parameter.hh; krylovinverseoperators.hh:83,126-131)."""
     method = {k.replace("fem.solver.", ""): v for k, v in (parameters or {}).items()}.get("method", "cg")
+    precon = {k.replace("fem.solver.", ""): v for k, v in (parameters or {}).items()}.get("preconditioning.method", "none")
     if method == "cg":
-        return CgInverseOperator(parameters)
+        return JacobiCgInverseOperator(parameters) if precon == "jacobi" else CgInverseOperator(parameters)
     if method == "bicgstab":
         return BicgstabInverseOperator(parameters)
     if method == "gmres":

@@ -148,6 +148,18 @@ int b200fem_cg_solve(b200fem_operator* op, const double* b_host, double* x_host,
 int b200fem_cg_solve_dev(b200fem_operator* op, const double* b_dev, double* x_dev, double epsilon, int max_iterations,
                          int tolerance_criteria, int* iterations, double* history);
 
+/* Diagonal of the homogeneous linear part A (what DiagonalPreconditioner extracts from an ASSEMBLED operator,
+ * solver/diagonalpreconditioner.hh:104-141; the reference throws NotImplemented for matrix-free operators, :37-57).  Available
+ * when the operator has a Kronecker form (linear model, default quadrature): the diagonal is then a sum of products of 1-D
+ * diagonal entries and costs O(N).  Strong-Dirichlet rows hold 1. */
+int b200fem_operator_diagonal(b200fem_operator* op, double* diag_host);
+/* CG with the Jacobi preconditioner B = diag(A)^-1: the preconditioned branch of LinearSolver::cg (solver/linear/cg.hh:52-56,
+ * 72-107; residual = <r, B r>).  history receives sqrt(<r, B r>) per iteration. */
+int b200fem_pcg_solve(b200fem_operator* op, const double* b_host, double* x_host, double epsilon, int max_iterations,
+                      int tolerance_criteria, int* iterations, double* history);
+int b200fem_pcg_solve_dev(b200fem_operator* op, const double* b_dev, double* x_dev, double epsilon, int max_iterations,
+                          int tolerance_criteria, int* iterations, double* history);
+
 /* KrylovInverseOperator<bicgstab> (solver/krylovinverseoperators.hh:46-281 -> solver/linear/bicgstab.hh:64-214, unpreconditioned)
  * on the homogeneous linear part -- the Krylov method of pydemo/advectiondiffusion.py (non-symmetric operators).  Same
  * conventions as the reference: no convergence test before the first iteration; `res` is compared with

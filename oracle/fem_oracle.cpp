@@ -616,6 +616,30 @@ static int cg(const std::function<void(const double*, double*)>& op, int64_t n, 
   return (iterations < maxIterations) ? iterations : -iterations;
 }
 
+// LinearSolver::cg, preconditioned branch (solver/linear/cg.hh:52-56, 72-107): q = B p, s = B r_k, residual = <r_k, B r_k>;
+// B = diag(A)^-1 (DiagonalPreconditioner, solver/diagonalpreconditioner.hh:104-141, here for the matrix-free operator)
+static int pcgDiagonal(const std::function<void(const double*, double*)>& op, const double* dinv, int64_t n, double* x, const double* b,
+                       double epsilon, int maxIterations, int tolCrit, double* history) {
+  std::vector<double> h(n), p(n), s(n), q(n);
+  op(x, h.data());
+  for (int64_t i = 0; i < n; ++i) { p[i] = b[i]; p[i] -= h[i]; }
+  for (int64_t i = 0; i < n; ++i) { q[i] = dinv[i]*p[i]; s[i] = q[i]; }
+  double prevResidual = 0, residual = dot(p.data(), q.data(), n);
+  const double tolerance = epsilon*epsilon*(tolCrit == 1 ? dot(b, b, n) : tolCrit == 2 ? residual : 1.0);
+  int iterations = 0;
+  for (iterations = 0; residual > tolerance && iterations < maxIterations; ++iterations) {
+    if (iterations > 0) { const double beta = residual/prevResidual; for (int64_t i = 0; i < n; ++i) { q[i] *= beta; q[i] += s[i]; } }
+    op(q.data(), h.data());
+    const double qdoth = dot(q.data(), h.data(), n), alpha = residual/qdoth;
+    for (int64_t i = 0; i < n; ++i) x[i] += alpha*q[i];
+    for (int64_t i = 0; i < n; ++i) p[i] += -alpha*h[i];
+    for (int64_t i = 0; i < n; ++i) s[i] = dinv[i]*p[i];
+    prevResidual = residual; residual = dot(p.data(), s.data(), n);
+    if (history) history[iterations] = std::sqrt(residual);
+  }
+  return (iterations < maxIterations) ? iterations : -iterations;
+}
+
 // LinearSolver::bicgstab (solver/linear/bicgstab.hh:64-214), unpreconditioned branch (z aliases r), with the fused
 // five-fold scalar product of scalarProductVecs (:19-52).  Note the reference's conventions: no convergence test before
 // the first iteration, `res` (not its square) is compared with tolerance * {1 | sqrt(b.b) | sqrt(r0.r0)}.
@@ -765,6 +789,17 @@ void fo_dirichlet(FoOperator* op, uint8_t* mask, double* values) {
 int fo_cg(FoOperator* op, const double* b, double* x, double eps, int maxit, int tolCrit, double* history) {
   Operator* A = op->linear.get();
   return cg([A](const double* in, double* out) { A->apply(in, out); }, op->space->sp->size, x, b, eps, maxit, tolCrit, history);
+}
+// diagonal of the homogeneous linear part by probing with unit vectors (independent of any factorisation: O(N^2), tests only)
+void fo_operator_diagonal(FoOperator* op, double* diag) {
+  Operator* A = op->linear.get(); const int64_t n = op->space->sp->size;
+  std::vector<double> e(n, 0.0), w(n);
+  for (int64_t i = 0; i < n; ++i) { e[i] = 1.0; A->apply(e.data(), w.data()); diag[i] = w[i]; e[i] = 0.0; }
+}
+int fo_pcg_diagonal(FoOperator* op, const double* diag, const double* b, double* x, double eps, int maxit, int tolCrit, double* history) {
+  Operator* A = op->linear.get(); const int64_t n = op->space->sp->size;
+  std::vector<double> dinv(n); for (int64_t i = 0; i < n; ++i) dinv[i] = 1.0/diag[i];
+  return pcgDiagonal([A](const double* in, double* out) { A->apply(in, out); }, dinv.data(), n, x, b, eps, maxit, tolCrit, history);
 }
 int fo_bicgstab(FoOperator* op, const double* b, double* x, double eps, int maxit, int tolCrit, double* history) {
   Operator* A = op->linear.get();

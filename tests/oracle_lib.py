@@ -62,6 +62,9 @@ def lib():
     L.fo_operator_apply_jacobian.restype = C.c_double
     L.fo_gmres_jacobian.restype = C.c_int
     L.fo_gmres_jacobian.argtypes = [C.c_void_p, _dp, _dp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_void_p]
+    L.fo_operator_diagonal.argtypes = [C.c_void_p, _dp]
+    L.fo_pcg_diagonal.restype = C.c_int
+    L.fo_pcg_diagonal.argtypes = [C.c_void_p, _dp, _dp, _dp, C.c_double, C.c_int, C.c_int, C.c_void_p]
     L.fo_gmres.restype = C.c_int
     L.fo_gmres.argtypes = [C.c_void_p, _dp, _dp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_void_p]
     L.fo_bicgstab.restype = C.c_int
@@ -165,6 +168,18 @@ class Operator:
         hist = np.zeros(max(maxit, 1))
         it = lib().fo_cg(self._h, np.ascontiguousarray(b, dtype=np.float64), x, eps, maxit, tolcrit,
                          hist.ctypes.data_as(C.c_void_p))
+        return it, x, hist[:abs(it)]
+
+    def diagonal(self):
+        d = np.empty(self.space.size)
+        lib().fo_operator_diagonal(self._h, d)
+        return d
+
+    def pcg(self, diag, b, x0, eps, maxit, tolcrit=0):
+        x = np.array(x0, dtype=np.float64, copy=True)
+        hist = np.zeros(max(maxit, 1))
+        it = lib().fo_pcg_diagonal(self._h, np.ascontiguousarray(diag, dtype=np.float64), np.ascontiguousarray(b, dtype=np.float64), x, eps, maxit,
+                                   tolcrit, hist.ctypes.data_as(C.c_void_p))
         return it, x, hist[:abs(it)]
 
     def linearize(self, u, eps=0.0):

@@ -419,3 +419,53 @@ def test_difference_quotient_jacobian_and_newton_krylov():
         xo += do
     assert len(norms) == 4 and norms[-1] < 1e-7 and norms[2] < 1e-2 * norms[1] and norms[3] < 1e-3 * norms[2]
     assert rel(x, xo) < 1e-7
+
+
+@pytest.mark.parametrize("case", ["lagrange2", "lagrange1_2d", "dg2", "dg3_mol"])
+def test_matrix_free_diagonal_and_jacobi_cg(case):
+    """diag(A) from the 1-D factors against the oracle's unit-vector probing, and Jacobi-preconditioned CG (preconditioned
+    branch of solver/linear/cg.hh) against the oracle restatement."""
+    if case.startswith("lagrange"):
+        dim, order, n = (3, 2, [4, 3, 3]) if case == "lagrange2" else (2, 1, [12, 9])
+        lo, hi = [0.0] * dim, [1.0, 1.5, 0.75][:dim]
+        space = fem.space.lagrange(fem.structuredGrid(lo, hi, n), order=order)
+        osp = ol.Space(n, lo, hi, ol.LAGRANGE, order)
+        kw = dict(eps=1.0, c=0.1, data=1, dirichlet_mask=(1 << (2 * dim)) - 1, strong_dirichlet=True)
+        op, oop = fem.operator.galerkin(space, **kw), ol.Operator(osp, **kw)
+    else:
+        order = 2 if case == "dg2" else 3
+        space, osp = dg_pair([3, 3, 2], [0, 0, 0], [1, 1, 1], order, True)
+        kw = dict(eps=1.0, c=1.0, beta=20.0 * order ** 2, dirichlet_mask=0, data=2)          # SPD: SIPG + reaction, Neumann data
+        op, oop = fem.operator.galerkin(space, **kw), ol.Operator(osp, skeleton=True, boundary=True, **kw)
+        if case == "dg3_mol":
+            op.setInverseMass(True)
+            oop.setInverseMass(True)
+    d, d_ref = op.diagonal(), oop.diagonal()
+    assert rel(d, d_ref) < TOL
+    if case == "dg3_mol":
+        return                       # M^-1 A is not symmetric in the Euclidean inner product: no CG on it
+    b = op.loadVector()
+    mask, g = oop.dirichlet()
+    x0 = np.where(mask, g, 0.0)
+    for maxit in (1, 6):
+        inv = fem.solver.JacobiCgInverseOperator({"tolerance": 1e-30, "maxiterations": maxit})
+        inv.bind(op)
+        x = x0.copy()
+        it = inv(b, x)
+        it_ref, x_ref, hist_ref = oop.pcg(d_ref, b, x0, 1e-30, maxit)
+        assert it == it_ref == -maxit
+        np.testing.assert_allclose(inv.residuals, hist_ref, rtol=1e-8)
+        assert rel(x, x_ref) < 1e-9
+    inv = fem.solver.KrylovInverseOperator({"fem.solver.method": "cg", "fem.solver.preconditioning.method": "jacobi", "tolerance": 1e-10,
+                                            "maxiterations": 3000})
+    inv.bind(op)
+    x = x0.copy()
+    it = inv(b, x)
+    it_ref, x_ref, _ = oop.pcg(d_ref, b, x0, 1e-10, 3000)
+    plain = fem.solver.CgInverseOperator({"tolerance": 1e-10, "maxiterations": 3000})
+    plain.bind(op)
+    xp = x0.copy()
+    it_plain = plain(b, xp)
+    assert it > 0 and abs(it - it_ref) <= max(2, it_ref // 10) and rel(x, x_ref) < 1e-8 and rel(x, xp) < 1e-7
+    if case == "lagrange2":
+        assert it < it_plain             # Jacobi helps on the Q2 Lagrange Laplacian (vertex / edge / face / cell nodes scale differently)
