@@ -84,6 +84,27 @@ def main():
         assert it == it_ref
         np.testing.assert_allclose(inv.residuals, hist_ref, rtol=1e-8)
         assert np.abs(xl - x_ref[gather]).max() / np.abs(x_ref).max() < 1e-9
+        # BiCGStab and GMRES on the non-symmetric advection-diffusion operator, MOL scaling (distributed dots via ncclAllReduce)
+        kw4 = dict(eps=0.1, b=(1.0, 0.5, 0.2), c=1.0, beta=80.0, dirichlet_mask=0b111111, data=2)
+        opn = fem.operator.galerkin(space, **kw4)
+        oopn = ol.Operator(osp, skeleton=True, boundary=True, **kw4)
+        bgn = -oopn.apply(np.zeros(osp.size))
+        for name, solver, ref in (("bicgstab", fem.solver.BicgstabInverseOperator({"tolerance": 1e-30, "maxiterations": 6}), oopn.bicgstab(bgn, np.zeros(osp.size), 1e-30, 6)),
+                                  ("gmres", fem.solver.GmresInverseOperator({"tolerance": 1e-30, "maxiterations": 9, "gmres.restart": 4}), oopn.gmres(bgn, np.zeros(osp.size), 1e-30, 9, restart=4))):
+            solver.bind(opn)
+            xl = np.zeros(space.size)
+            it = solver(np.ascontiguousarray(bgn[gather]), xl)
+            assert it == ref[0], (name, it, ref[0])
+            np.testing.assert_allclose(solver.residuals, ref[2], rtol=1e-7)
+            assert np.abs(xl - ref[1][gather]).max() / np.abs(ref[1]).max() < 1e-8, name
+        opn.setInverseMass(True)
+        oopn.setInverseMass(True)
+        wl = np.empty(space.size)
+        opn(ul, wl)
+        wm = oopn.apply(ug)
+        err = np.abs(wl - wm[gather]).max() / np.abs(wm).max()
+        worst = max(worst, err)
+        assert err < 1e-12, ("mol", proc, err)
         # ---------------- Lagrange P2 (Add on shared dofs) ----------------
         origin, ext, olo, ohi = partition_box(n, proc, rank, overlap=0)
         lspace = fem.space.lagrange(grid, order=2)
@@ -116,6 +137,16 @@ def main():
         xl = np.ascontiguousarray(x0g[l2g])
         it = inv(np.ascontiguousarray(blg[l2g]), xl)
         it_ref, x_ref, hist_ref = loop_.cg(blg, x0g, 1e-30, 10)
+        assert it == it_ref
+        np.testing.assert_allclose(inv.residuals, hist_ref, rtol=1e-8)
+        assert np.abs(xl - x_ref[l2g]).max() / np.abs(x_ref).max() < 1e-9
+        # matrix-free diagonal (partial sums on interface nodes, completed by the Add exchange) and Jacobi-preconditioned CG
+        dg_ref = loop_.diagonal()
+        inv = fem.solver.JacobiCgInverseOperator({"tolerance": 1e-30, "maxiterations": 7})
+        inv.bind(lop)
+        xl = np.ascontiguousarray(x0g[l2g])
+        it = inv(np.ascontiguousarray(blg[l2g]), xl)
+        it_ref, x_ref, hist_ref = loop_.pcg(dg_ref, blg, x0g, 1e-30, 7)
         assert it == it_ref
         np.testing.assert_allclose(inv.residuals, hist_ref, rtol=1e-8)
         assert np.abs(xl - x_ref[l2g]).max() / np.abs(x_ref).max() < 1e-9
