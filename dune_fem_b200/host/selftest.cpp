@@ -41,6 +41,29 @@ int main() {
     double res = 0; for (std::size_t i = 0; i < p2.size(); ++i) res += (r.dofVector()[i] - rhs.dofVector()[i]) * (r.dofVector()[i] - rhs.dofVector()[i]);
     std::printf("CG: %d iterations, |Ax-b| = %.3e\n", cg.iterations(), std::sqrt(res));
     if (!(cg.converged() && std::sqrt(res) < 2e-10)) return 1;
+
+    // (3) method of lines: MOLGalerkinOperator = M^-1 L; for the orthonormal Legendre basis on this uniform grid M^-1 = 1 / detJ
+    MOLGalerkinOperator<DiscreteFunctionType> mol(dg, dg, adv);
+    DiscreteFunctionType wm("wm", dg);
+    mol(u, wm);
+    const double detJ = 1.0 / (8.0 * 8.0 * 8.0);
+    double merr = 0;
+    for (std::size_t i = 0; i < dg.size(); ++i) merr = std::fmax(merr, std::fabs(wm.dofVector()[i] * detJ - w.dofVector()[i]));
+    std::printf("MOL: max |detJ M^-1 L[u] - L[u]| / max|L[u]| = %.3e\n", merr / scale);
+    if (!(merr <= 1e-12 * scale)) return 1;
+
+    // (4) non-symmetric system through KrylovInverseOperator<bicgstab> and <gmres>
+    Integrands ad = adv; ad.eps = 0.1; ad.b[1] = 0.5; ad.c = 1.0; ad.dirichlet_mask = 63; ad.data = 2;
+    GalerkinOperator<DiscreteFunctionType> adop(dg, dg, ad);
+    DiscreteFunctionType rb("rb", dg), xb("xb", dg), xg("xg", dg), rr("rr", dg);
+    adop.loadVector(rb);
+    SolverParameter kp; kp.tolerance = 1e-8; kp.maxIterations = 5000; kp.gmresRestart = 50;
+    BicgstabInverseOperator<DiscreteFunctionType> bicg(kp); bicg.bind(adop); bicg(rb, xb);
+    GmresInverseOperator<DiscreteFunctionType> gm(kp); gm.bind(adop); gm(rb, xg);
+    double dmax = 0, xmax = 0;
+    for (std::size_t i = 0; i < dg.size(); ++i) { dmax = std::fmax(dmax, std::fabs(xb.dofVector()[i] - xg.dofVector()[i])); xmax = std::fmax(xmax, std::fabs(xg.dofVector()[i])); }
+    std::printf("BiCGStab: %d iterations, GMRES(50): %d iterations, max |x_bicgstab - x_gmres| / max|x| = %.3e\n", bicg.iterations(), gm.iterations(), dmax / xmax);
+    if (!(bicg.converged() && gm.converged() && dmax <= 1e-6 * xmax)) return 1;
     std::printf("host selftest OK\n");
     return 0;
   } catch (const InvalidStateException& e) {
