@@ -469,3 +469,40 @@ def test_matrix_free_diagonal_and_jacobi_cg(case):
     assert it > 0 and abs(it - it_ref) <= max(2, it_ref // 10) and rel(x, x_ref) < 1e-8 and rel(x, xp) < 1e-7
     if case == "lagrange2":
         assert it < it_plain             # Jacobi helps on the Q2 Lagrange Laplacian (vertex / edge / face / cell nodes scale differently)
+
+
+@pytest.mark.parametrize("order,cells,model", [
+    (5, 48, dict(eps=1.0, b=(0.0, 0.0, 0.0), beta=500.0, dirichlet_mask=0b111111, data=2)),      # BASELINE config 4 at full size (23.9 M dofs)
+    (3, 64, dict(eps=1e-5, b=(1.0, 0.0, 0.0), beta=180.0, dirichlet_mask=0b000011, data=1)),     # config 5's kernel at 16.8 M dofs
+])
+def test_full_size_high_order_properties(order, cells, model):
+    """Size-independent properties of the slab Kronecker kernel at benchmark sizes: it agrees with the independent
+    quadrature kernel, L[u] = A u - b, A is linear, and a corner block matches the CPU oracle."""
+    n = [cells] * 3
+    space = fem.space.dglegendre(fem.structuredGrid([0, 0, 0], [1, 1, 1], n), order=order, hierarchical=True)
+    nb = (order + 1) ** 3
+    assert space.size == cells ** 3 * nb
+    rng = np.random.default_rng(20261017)
+    u, v = rng.uniform(-1, 1, space.size), rng.uniform(-1, 1, space.size)
+    opq = fem.operator.galerkin(space, kernel=_capi.KERNEL_QUADRATURE, **model)
+    opk = fem.operator.galerkin(space, kernel=_capi.KERNEL_KRONECKER, **model)
+    wq, wk, wl, wv, wuv = (np.empty(space.size) for _ in range(5))
+    opq(u, wq)
+    opk(u, wk)
+    assert rel(wk, wq) < TOL
+    opk.applyLinear(u, wl)
+    assert rel(wl - opk.loadVector(), wk) < TOL
+    opk.applyLinear(v, wv)
+    opk.applyLinear(2.0 * u - 3.0 * v, wuv)
+    assert rel(wuv, 2.0 * wl - 3.0 * wv) < TOL
+    # the operator is local: the first x-y layer of elements depends on the first two layers of u only
+    m = 6 if order == 5 else 12                       # a m x m x 2 corner of the mesh on the oracle
+    h = 1.0 / cells
+    osp = ol.Space([m, m, 2], [0, 0, 0], [m * h, m * h, 2 * h], ol.DG_LEGENDRE_HIER, order)
+    idx = np.array([(x + cells * (y + cells * z)) for z in range(2) for y in range(m) for x in range(m)], dtype=np.int64)
+    gather = (idx[:, None] * nb + np.arange(nb)[None, :]).ravel()
+    ref = ol.Operator(osp, skeleton=True, boundary=True, threads=8, **model).apply(u[gather])
+    # compare the elements that are interior to the corner block in x and y and lie in the first layer
+    keep = np.array([(x + m * (y + m * 0)) for y in range(m - 1) for x in range(m - 1)], dtype=np.int64)
+    sel = (keep[:, None] * nb + np.arange(nb)[None, :]).ravel()
+    assert np.abs(wk[gather][sel] - ref[sel]).max() / np.abs(ref[sel]).max() < TOL
