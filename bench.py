@@ -338,8 +338,8 @@ def main():
                 torch.cuda.synchronize()
                 cg_ms = e0.elapsed_time(e1)
             cg[name] = {"dofs": sp.size, "iterations": abs(its.value), "s_per_iteration": cg_ms * 1e-3 / iters,
-                        "dofs_per_s": sp.size * iters / (cg_ms * 1e-3), "launches_per_iteration": lop.timing()["launches_per_apply"] + 3,
-                        "cuda_graph": "16 iterations per graph launch"}
+                        "dofs_per_s": sp.size * iters / (cg_ms * 1e-3), "schedule": ("one cooperative kernel launch per 16 iterations (grid-wide barriers, cg_coop2d.cuh)" if dim == 2 else
+                                     "CUDA graph of 16 iterations, %d launches per iteration" % (lop.timing()["launches_per_apply"] + 3))}
             del bt, x0, xt, lop, sp, g
 
     other = None

@@ -29,6 +29,7 @@
 #include "lagrange_quadrature.cuh"
 #include "tables.hpp"
 #include "vec_kernels.cuh"
+#include "cg_coop2d.cuh"
 
 using namespace b200fem;
 
@@ -1094,7 +1095,8 @@ extern "C" int b200fem_cg_solve_dev(b200fem_operator* op, const double* b, doubl
   // 256^2 P1 grid spend their time in launch gaps otherwise).  Iterations past convergence / max_iterations are no-ops
   // on the device (every kernel checks the device-resident `done` flag), so whole chunks can always be replayed.
   static const bool no_graph = std::getenv("B200FEM_NO_CG_GRAPH") != nullptr;
-  const bool use_graph = single && !no_graph && maxit >= chunk;
+  bool use_graph = single && !no_graph && maxit >= chunk;
+  if (std::getenv("B200FEM_NO_COOP_CG") == nullptr && single && !op->jac_mode && s->kind == B200FEM_LAGRANGE && s->box.dim == 2 && op->model.gamma == 0.0 && n <= (1 << 20)) use_graph = false;   // cooperative path below
   if (use_graph && !(op->cg_graph && op->cg_graph_key[0] == (const void*)x && op->cg_graph_key[1] == (const void*)b && op->cg_graph_key[2] == (const void*)op->d_hist)) {
     if (op->cg_graph) { cudaGraphExecDestroy(op->cg_graph); op->cg_graph = nullptr; }
     cudaGraph_t graph = nullptr;
@@ -1110,9 +1112,32 @@ extern "C" int b200fem_cg_solve_dev(b200fem_operator* op, const double* b, doubl
     if (ce != cudaSuccess) { op->cg_graph = nullptr; return fail(B200FEM_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce)); }
     op->cg_graph_key[0] = x; op->cg_graph_key[1] = b; op->cg_graph_key[2] = op->d_hist;
   }
+  // Launch-bound sizes on a 2-D Lagrange lattice (BASELINE config 1): a chunk of iterations is ONE cooperative launch with
+  // grid-wide barriers instead of kernel boundaries (cg_coop2d.cuh).  B200FEM_NO_COOP_CG disables it.
+  static const bool no_coop = std::getenv("B200FEM_NO_COOP_CG") != nullptr;
+  int coop_grid = 0;
+  const bool use_coop = single && !no_coop && !op->jac_mode && s->kind == B200FEM_LAGRANGE && s->box.dim == 2 && op->model.gamma == 0.0 && !op->model.has_skeleton &&
+                        default_quadrature(op) && n <= (1 << 20) && op->d_lag_rows != nullptr && (!op->model.strong_dirichlet || op->d_dmask);
+  if (use_coop) {
+    int per_sm = 0, sms = 0, coop_ok = 0;
+    CUDA_OK(cudaDeviceGetAttribute(&coop_ok, cudaDevAttrCooperativeLaunch, c->device));
+    CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    if (s->order == 1) CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_coop2d_kernel<1>, kCoopThreads, 0));
+    else CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_coop2d_kernel<2>, kCoopThreads, 0));
+    const long long nodes = s->lay.lattice[0] * s->lay.lattice[1];
+    coop_grid = coop_ok ? (int)std::min<long long>(std::min<long long>((long long)per_sm * sms, kRedBlocks), (nodes + kCoopThreads - 1) / kCoopThreads) : 0;
+  }
   for (int it = 0; it < maxit;) {
     const int upto = std::min(maxit, it + chunk);
-    if (use_graph) { CUDA_OK(cudaGraphLaunch(op->cg_graph, st)); it += chunk; }
+    if (coop_grid > 0) {
+      int iters = chunk; const unsigned char* dm = op->model.strong_dirichlet ? op->d_dmask : nullptr; double* xx = x;
+      void* args[] = {(void*)&s->lay, (void*)&op->lag_rows, (void*)&xx, (void*)&op->d_r, (void*)&op->d_p, (void*)&op->d_h, (void*)&dm, (void*)&op->d_partial,
+                      (void*)&op->d_cg, (void*)&op->d_hist, (void*)&iters};
+      if (s->order == 1) CUDA_OK(cudaLaunchCooperativeKernel((const void*)cg_coop2d_kernel<1>, dim3((unsigned)coop_grid), dim3(kCoopThreads), args, 0, st));
+      else CUDA_OK(cudaLaunchCooperativeKernel((const void*)cg_coop2d_kernel<2>, dim3((unsigned)coop_grid), dim3(kCoopThreads), args, 0, st));
+      it += chunk;
+    }
+    else if (use_graph) { CUDA_OK(cudaGraphLaunch(op->cg_graph, st)); it += chunk; }
     else for (; it < upto; ++it) { rc = enqueue_iteration(); if (rc) return rc; }
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaMemcpyAsync(&host, op->d_cg, sizeof(CgState), cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st));
