@@ -728,6 +728,44 @@ static int gmres(const std::function<void(const double*, double*)>& op, int64_t 
   return (iterations < maxIterations) ? iterations : -iterations;
 }
 
+template <int N>
+static void kronApplyT(const int* n3, const int* tensorOfStored, const double* mats, double c2, const double* u, double* w,
+                       const double* bvec, int threads) {
+  constexpr int nb = N*N*N, nn = N*N;
+  const int nx = n3[0], ny = n3[1], nz = n3[2];
+  auto M = [&](int d, int which) { return mats + ((size_t)d*5 + which)*nn; };
+  auto work = [&](int z0, int z1) {
+    double own[nb], v[nb], acc[nb], m[nn];
+    // acc[.. i ..] += sum_j A[i][j] src[.. j ..] along tensor axis D (tensor index (m0*N + m1)*N + m2)
+    auto ax0 = [&](const double* A, const double* src) { for (int i = 0; i < N; ++i) for (int j = 0; j < N; ++j) { const double a = A[i*N + j]; for (int r = 0; r < nn; ++r) acc[i*nn + r] += a*src[j*nn + r]; } };
+    auto ax1 = [&](const double* A, const double* src) { for (int p = 0; p < N; ++p) for (int i = 0; i < N; ++i) for (int j = 0; j < N; ++j) { const double a = A[i*N + j]; for (int r = 0; r < N; ++r) acc[p*nn + i*N + r] += a*src[p*nn + j*N + r]; } };
+    auto ax2 = [&](const double* A, const double* src) { for (int p = 0; p < nn; ++p) for (int i = 0; i < N; ++i) { double s = acc[p*N + i]; for (int j = 0; j < N; ++j) s += A[i*N + j]*src[p*N + j]; acc[p*N + i] = s; } };
+    auto axis = [&](int d, const double* A, const double* src) { if (d == 0) ax0(A, src); else if (d == 1) ax1(A, src); else ax2(A, src); };
+    auto gather = [&](int64_t e, double* dst) { const double* ue = u + e*nb; for (int l = 0; l < nb; ++l) dst[tensorOfStored[l]] = ue[l]; };
+    for (int z = z0; z < z1; ++z) for (int y = 0; y < ny; ++y) for (int x = 0; x < nx; ++x) {
+      const int ec[3] = {x, y, z}, ext[3] = {nx, ny, nz}; const int64_t e = x + (int64_t)nx*(y + (int64_t)ny*z);
+      const int64_t step[3] = {1, nx, (int64_t)nx*ny};
+      gather(e, own);
+      for (int t = 0; t < nb; ++t) acc[t] = -c2*own[t];
+      for (int d = 0; d < 3; ++d) {
+        const bool lo = ec[d] == 0, hi = ec[d] == ext[d]-1;
+        const double* S = M(d, 0);
+        if (lo || hi) { for (int q = 0; q < nn; ++q) m[q] = S[q] + (lo ? M(d, 3)[q] : 0.0) + (hi ? M(d, 4)[q] : 0.0); S = m; }
+        axis(d, S, own);
+        if (!lo) { gather(e - step[d], v); axis(d, M(d, 1), v); }
+        if (!hi) { gather(e + step[d], v); axis(d, M(d, 2), v); }
+      }
+      double* we = w + e*nb;
+      if (bvec) { const double* be = bvec + e*nb; for (int l = 0; l < nb; ++l) we[l] = acc[tensorOfStored[l]] - be[l]; }
+      else for (int l = 0; l < nb; ++l) we[l] = acc[tensorOfStored[l]];
+    }
+  };
+  const int T = std::max(1, std::min(threads, nz));
+  if (T == 1) { work(0, nz); return; }
+  std::vector<std::thread> pool;
+  for (int t = 0; t < T; ++t) pool.emplace_back(work, (int)((int64_t)nz*t/T), (int)((int64_t)nz*(t + 1)/T));
+  for (auto& th : pool) th.join();
+}
 }  // namespace oracle
 
 // ===========================================================================
@@ -830,6 +868,26 @@ double fo_operator_apply_jacobian(FoOperator* op, const double* arg, double* des
   return eps;
 }
 // Krylov solvers on the difference-quotient Jacobian (Newton step: J(u) delta = -L[u])
+// ---------------------------------------------------------------------------------------------------------------
+// Kronecker-form CPU apply: the fair CPU comparator of BASELINE.md section 3.1 ("sum-factorised, to be fair to the CPU").
+// For linear constant-coefficient integrands on a uniform box the operator of Operator::apply factorises as
+//     w_K = sum_d [ (S_d + [K at low bnd] Dlo_d + [K at high bnd] Dhi_d) u_K + L_d u_{K-e_d} + R_d u_{K+e_d} ] - c2 u_K - b_K
+// with n x n matrices acting along tensor axis d.  The matrices are NOT derived here: tests/oracle_lib.py obtains them by
+// probing Operator::apply (the literal restatement of the reference loop) on a 3x3x3 mesh, so this routine is pinned to the
+// dense loop and checks the factorisation claim the GPU Kronecker kernels rest on.  mats = [axis][S, L, R, Dlo, Dhi][n*n];
+// tensorOfStored[stored local index] = (m0*n + m1)*n + m2.
+void fo_kron_apply(const int* n3, int n, const int* tensorOfStored, const double* mats, double c2, const double* u, double* w,
+                   const double* bvec, int threads) {
+  switch (n) {
+    case 2: kronApplyT<2>(n3, tensorOfStored, mats, c2, u, w, bvec, threads); break;
+    case 3: kronApplyT<3>(n3, tensorOfStored, mats, c2, u, w, bvec, threads); break;
+    case 4: kronApplyT<4>(n3, tensorOfStored, mats, c2, u, w, bvec, threads); break;
+    case 5: kronApplyT<5>(n3, tensorOfStored, mats, c2, u, w, bvec, threads); break;
+    case 6: kronApplyT<6>(n3, tensorOfStored, mats, c2, u, w, bvec, threads); break;
+    default: std::abort();
+  }
+}
+
 int fo_gmres_jacobian(FoOperator* op, const double* b, double* x, int restart, double eps, int maxit, int tolCrit, double* history) {
   return gmres([op](const double* in, double* out) { fo_operator_apply_jacobian(op, in, out); }, op->space->sp->size, x, b, restart, eps, maxit, tolCrit, history);
 }

@@ -65,6 +65,8 @@ def lib():
     L.fo_operator_diagonal.argtypes = [C.c_void_p, _dp]
     L.fo_pcg_diagonal.restype = C.c_int
     L.fo_pcg_diagonal.argtypes = [C.c_void_p, _dp, _dp, _dp, C.c_double, C.c_int, C.c_int, C.c_void_p]
+    L.fo_kron_apply.argtypes = [_ip, C.c_int, _ip, _dp, C.c_double, _dp, _dp, C.c_void_p, C.c_int]
+    L.fo_kron_apply.restype = None
     L.fo_gmres.restype = C.c_int
     L.fo_gmres.argtypes = [C.c_void_p, _dp, _dp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_void_p]
     L.fo_bicgstab.restype = C.c_int
@@ -235,3 +237,63 @@ def quadrature(dim, order):
     w = np.empty(n)
     lib().fo_quadrature(dim, order, x.ctypes.data_as(C.c_void_p), w.ctypes.data_as(C.c_void_p))
     return x, w
+
+
+class KroneckerCpu:
+    """Kronecker-form CPU apply of a linear, constant-coefficient DG operator on a uniform box (fem_oracle.cpp: fo_kron_apply).
+    The 1-D matrices are obtained by PROBING the dense oracle operator on a 3x3x3 mesh of the same cell size: unit vectors whose
+    tensor mode varies along one axis only, read back on the same modes of the centre / boundary elements."""
+
+    def __init__(self, n, lo, hi, kind, order, threads=1, **model):
+        assert kind in (DG_LEGENDRE, DG_LEGENDRE_HIER) and len(n) == 3
+        self.n, self.N, self.threads = list(n), order + 1, threads
+        N, nb = self.N, (order + 1) ** 3
+        h = [(hi[d] - lo[d]) / n[d] for d in range(3)]
+        self.space = Space(n, lo, hi, kind, order)
+        probe = Space([3, 3, 3], lo, [lo[d] + 3 * h[d] for d in range(3)], kind, order)
+        op = Operator(probe, skeleton=True, boundary=True, **dict(model, data=0))
+        mi = np.zeros(3 * nb, dtype=np.int32)
+        lib().fo_space_multiindex(probe._h, mi)
+        mi = mi.reshape(nb, 3)
+        self.tensor_of_stored = np.ascontiguousarray((mi[:, 0] * N + mi[:, 1]) * N + mi[:, 2], dtype=np.int32)
+        stored_of = {tuple(m): l for l, m in enumerate(mi.tolist())}
+
+        def mode(d, j):                     # stored local index of the tensor mode that is j along axis d and 0 elsewhere
+            m = [0, 0, 0]
+            m[d] = j
+            return stored_of[tuple(m)]
+
+        def elem(c):
+            return c[0] + 3 * (c[1] + 3 * c[2])
+
+        def block(d, src, dst):             # response matrix [i][j] of element dst (modes along d) to unit vectors in element src
+            A = np.zeros((N, N))
+            for j in range(N):
+                e = np.zeros(probe.size)
+                e[elem(src) * nb + mode(d, j)] = 1.0
+                w = op.apply(e, linear=True)
+                for i in range(N):
+                    A[i, j] = w[elem(dst) * nb + mode(d, i)]
+            return A
+
+        mats = np.zeros((3, 5, N, N))
+        for d in range(3):
+            c, lo_e, hi_e = [1, 1, 1], [1, 1, 1], [1, 1, 1]
+            lo_e[d], hi_e[d] = 0, 2
+            S = block(d, c, c)
+            mats[d, 0] = S
+            mats[d, 1] = block(d, lo_e, c)                     # L_d: u_{K-e_d} -> w_K
+            mats[d, 2] = block(d, hi_e, c)                     # R_d
+            mats[d, 3] = block(d, lo_e, lo_e) - S              # Dlo_d
+            mats[d, 4] = block(d, hi_e, hi_e) - S              # Dhi_d
+        # every S above carries the (0,0) entries of the two other axes on its diagonal: S_d(probed) = S_d + (C - c_d) I, C = sum_d c_d,
+        # so  sum_d S_d(probed) = sum_d S_d + 2 C I  and  C = S(probed)[0][0] for any axis
+        self.c2 = 2.0 * mats[0, 0, 0, 0]
+        self.mats = np.ascontiguousarray(mats)
+
+    def apply(self, u, bvec=None, out=None):
+        w = np.empty(self.space.size) if out is None else out
+        n3 = np.array(self.n, dtype=np.int32)
+        bp = None if bvec is None else np.ascontiguousarray(bvec, dtype=np.float64).ctypes.data_as(C.c_void_p)
+        lib().fo_kron_apply(n3, self.N, self.tensor_of_stored, self.mats.ravel(), self.c2, np.ascontiguousarray(u, dtype=np.float64), w, bp, self.threads)
+        return w
