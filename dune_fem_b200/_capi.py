@@ -18,15 +18,15 @@ SYMBOLS = [
     "b200fem_space_size", "b200fem_space_local_size", "b200fem_space_elements", "b200fem_space_dofmap",
     "b200fem_operator_create", "b200fem_operator_destroy", "b200fem_operator_apply", "b200fem_operator_apply_linear",
     "b200fem_operator_apply_dev", "b200fem_operator_load_vector", "b200fem_operator_set_communicate",
-    "b200fem_operator_set_quadrature_orders", "b200fem_operator_set_kernel", "b200fem_operator_set_inverse_mass", "b200fem_operator_linearize", "b200fem_operator_linearize_dev", "b200fem_operator_dirichlet",
+    "b200fem_operator_set_quadrature_orders", "b200fem_operator_set_kernel", "b200fem_operator_set_host_pipeline", "b200fem_operator_set_inverse_mass", "b200fem_operator_linearize", "b200fem_operator_linearize_dev", "b200fem_operator_dirichlet",
     "b200fem_operator_timing", "b200fem_cg_solve", "b200fem_cg_solve_dev", "b200fem_bicgstab_solve", "b200fem_bicgstab_solve_dev", "b200fem_gmres_solve", "b200fem_gmres_solve_dev", "b200fem_operator_diagonal", "b200fem_pcg_solve", "b200fem_pcg_solve_dev", "b200fem_dot_dev", "b200fem_axpy_dev",
-    "b200fem_ctx_set_nccl", "b200fem_nccl_unique_id", "b200fem_nccl_init", "b200fem_communicate_dev",
+    "b200fem_ctx_set_nccl", "b200fem_nccl_unique_id", "b200fem_nccl_init", "b200fem_ctx_transport", "b200fem_communicate_dev",
 ]
 
 OK, ERR_INVALID, ERR_NOT_IMPLEMENTED, ERR_CUDA, ERR_COMM = 0, -1, -2, -3, -4
 LAGRANGE, DG_LEGENDRE, DG_LEGENDRE_HIER = 0, 1, 2
 NUMBERING_YASP, NUMBERING_ADAPTIVE_LEAF = 0, 1
-KERNEL_AUTO, KERNEL_QUADRATURE, KERNEL_KRONECKER = 0, 1, 2
+KERNEL_AUTO, KERNEL_QUADRATURE, KERNEL_KRONECKER, KERNEL_KRONECKER_TILE = 0, 1, 2, 3
 TOL_ABSOLUTE, TOL_RELATIVE, TOL_RESIDUAL_REDUCTION = 0, 1, 2
 
 
@@ -79,6 +79,7 @@ def lib():
         "b200fem_operator_apply_dev": [vp, vp, vp, C.c_int], "b200fem_operator_load_vector": [vp, vp],
         "b200fem_operator_set_communicate": [vp, C.c_int], "b200fem_operator_set_quadrature_orders": [vp, C.c_uint, C.c_uint],
         "b200fem_operator_set_kernel": [vp, C.c_int], "b200fem_operator_set_inverse_mass": [vp, C.c_int],
+        "b200fem_operator_set_host_pipeline": [vp, C.c_int], "b200fem_ctx_transport": [vp, P(C.c_int)],
         "b200fem_operator_linearize": [vp, vp, dbl], "b200fem_operator_linearize_dev": [vp, vp, dbl], "b200fem_operator_dirichlet": [vp, vp, vp],
         "b200fem_operator_timing": [vp, P(Timing)],
         "b200fem_cg_solve": [vp, vp, vp, dbl, C.c_int, C.c_int, P(C.c_int), vp],
@@ -107,7 +108,10 @@ def check(code):
         raise B200FemError(code, lib().b200fem_last_error().decode())
 
 
-def ptr(a):
-    """numpy array -> void* (must be C-contiguous)"""
-    assert a.flags["C_CONTIGUOUS"]
+def ptr(a, dtype=np.float64):
+    """numpy array -> void*.  The C ABI reads raw memory: the array must be C-contiguous and of the expected dtype (dof
+    vectors float64, masks uint8) -- anything else would be silently reinterpreted."""
+    if not isinstance(a, np.ndarray) or a.dtype != dtype or not a.flags["C_CONTIGUOUS"]:
+        raise TypeError(f"expected a C-contiguous numpy array of dtype {np.dtype(dtype).name}, got "
+                        f"{type(a).__name__}{'' if not isinstance(a, np.ndarray) else ' of dtype ' + a.dtype.name}")
     return a.ctypes.data_as(C.c_void_p)

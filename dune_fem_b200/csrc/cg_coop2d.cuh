@@ -14,7 +14,7 @@
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include "lagrange_kronecker.cuh"
-#include "vec_kernels.cuh"
+#include "vec_types.hpp"
 
 namespace b200fem {
 

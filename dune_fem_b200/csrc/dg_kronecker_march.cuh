@@ -25,7 +25,8 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
-#include "dg_kronecker_tensor.cuh"
+#include "comm.cuh"
+#include "kron_common.cuh"
 
 namespace b200fem {
 
@@ -36,16 +37,6 @@ struct KronMarchMaps {
   CUtensorMap w_tile;    // same over the owned sub-box of w
 };
 
-namespace ptx {
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
-  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-               ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t src) {
-  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-}  // namespace ptx
 
 template <int N, int TX, int TY> struct KronMarchCfg {
   static constexpr int N3 = N * N * N;
@@ -55,7 +46,7 @@ template <int N, int TX, int TY> struct KronMarchCfg {
   static constexpr int kU = ((TY + 2) * RS + 15) / 16 * 16;  // doubles per plane stage, 128-byte multiple
   static constexpr int kO = TY * RO;
   static constexpr uint32_t kBytesU = 8u * (TY + 2) * RS, kBytesE = 8u * kO, kBytesB = 8u * kO;
-  static constexpr size_t smem_bytes() { return sizeof(double) * (2 * (size_t)kU + kO + 6 * N * N + 2) + 8 * (4 + kConsumers / 32) + 128; }
+  static constexpr size_t smem_bytes() { return sizeof(double) * (2 * (size_t)kU + kO + 6 * N * N + 2) + 8 * (4 + kConsumers / 32) + 64 + 128; }
   static_assert(TX % 2 == 0 && (kO * 8) % 128 == 0, "TMA destinations must stay 128-byte aligned");
 };
 
@@ -123,7 +114,7 @@ __device__ __forceinline__ void unit_smem(const double* __restrict__ M, const do
 template <int N, bool HIER, int TX, int TY, bool HAS_B, bool CHK>
 __global__ void __launch_bounds__(KronMarchCfg<N, TX, TY>::kThreads, 1)
 dg_kronecker_march_kernel(const __grid_constant__ KronTabDev<N> K, const __grid_constant__ BoxDev box,
-                          const __grid_constant__ KronMarchMaps M, const int tiles_x, const int ncols) {
+                          const __grid_constant__ KronMarchMaps M, const __grid_constant__ MarchCommDev C, const int tiles_x, const int ncols) {
   using Cfg = KronMarchCfg<N, TX, TY>;
   constexpr int N3 = Cfg::N3, RS = Cfg::RS, RO = Cfg::RO, NN = N * N;
   constexpr int kWarps = Cfg::kConsumers / 32, kRowsPerWarp = 32 / TX, kSlab = kRowsPerWarp * RO;   // doubles per warp slab
@@ -135,7 +126,9 @@ dg_kronecker_march_kernel(const __grid_constant__ KronTabDev<N> K, const __grid_
   double* const Dsm = O + Cfg::kO;                                  // boundary corrections [axis][lo|hi][N*N]
   uint64_t* bars = reinterpret_cast<uint64_t*>(Dsm + 6 * NN + (6 * NN) % 2);
   const uint32_t ufull = ptx::smem_addr(bars), ufree = ptx::smem_addr(bars + 2), wbar0 = ptx::smem_addr(bars + 4);
+  unsigned int* const s_cnt = reinterpret_cast<unsigned int*>(bars + 4 + kWarps);   // [9] row segments this CTA has sent per direction
   const int tid = threadIdx.x;
+  if (tid < 16) s_cnt[tid] = 0u;
 
   const int nz = box.own_hi[2] - box.own_lo[2];
   const long long total = (long long)ncols * nz;
@@ -198,6 +191,35 @@ dg_kronecker_march_kernel(const __grid_constant__ KronTabDev<N> K, const __grid_
   int gcx = 0, gcy = 0, cx = 0, cy = 0;                              // global element coordinates; TMA coordinates of the warp's rows
   bool rows_owned = false, xb = false, yb = false;
   if (lane == 0) { ptx::prefetch_tensormap(&M.w_tile); if (HAS_B) ptx::prefetch_tensormap(&M.b_tile); }
+  // fused Copy exchange of w (several ranks, comm.cuh): sequence number of this exchange (device-resident, so that the
+  // launch can sit inside a captured graph); read after griddepcontrol.wait, i.e. after the previous exchange has retired
+  const unsigned long long seq = C.any ? *C.seq + 1 : 0ull;
+  const int on0 = box.own_hi[0] - box.own_lo[0];
+  // lane 0: the rows of the completed plane zc (owned coordinates) that lie on a rank interface go straight from the
+  // warp's slab into the neighbours' mailboxes (1-D bulk copies over NVLink; 16-byte aligned because on0 and TX are even)
+  auto send_rows = [&](const int zc, const int col) {
+    const int xoff = (col % tiles_x) * TX;
+    const uint32_t bytes = (uint32_t)min(TX, on0 - xoff) * N3 * 8u;
+    const bool zlo = zc == 0, zhi = zc == nz - 1;
+#pragma unroll
+    for (int r = 0; r < kRowsPerWarp; ++r) {
+      const int yc = cy + r;
+      if (yc >= on1) break;
+      const bool ylo = yc == 0, yhi = yc == on1 - 1;
+      if (!(ylo | yhi | zlo | zhi)) continue;
+      for (int dzc = 0; dzc < 3; ++dzc) {
+        if ((dzc == 0 && !zlo) || (dzc == 2 && !zhi)) continue;
+        for (int dyc = 0; dyc < 3; ++dyc) {
+          if ((dyc == 0 && !ylo) || (dyc == 2 && !yhi) || (dyc == 1 && dzc == 1)) continue;
+          const int d = dyc + 3 * dzc;
+          if (!C.enabled[d]) continue;
+          const long long zi = dzc == 1 ? zc : 0, yi = dyc == 1 ? yc : 0, ny = dyc == 1 ? on1 : 1;
+          ptx::bulk_s2g(C.remote[d][seq & 1] + ((zi * ny + yi) * on0 + xoff) * N3, slab_a + (uint32_t)(r * RO) * 8u, bytes);
+          atomicAdd(&s_cnt[d], 1u);
+        }
+      }
+    }
+  };
 
   for (; cur.valid; cur.advance()) {
     if (cur.z == cur.za - 1) {                                       // a new run starts
@@ -237,7 +259,7 @@ dg_kronecker_march_kernel(const __grid_constant__ KronTabDev<N> K, const __grid_
       for (int t = 0; t < N3; ++t) o[P.p[t]] = HAS_B ? A[t] - o[P.p[t]] : A[t];
       ptx::fence_proxy_async();
       __syncwarp();
-      if (lane == 0 && rows_owned) { ptx::tma_store_4d(&M.w_tile, 0, cx, cy, cur.z - 1, slab_a); ptx::bulk_commit(); }
+      if (lane == 0 && rows_owned) { ptx::tma_store_4d(&M.w_tile, 0, cx, cy, cur.z - 1, slab_a); if (C.any) send_rows(cur.z - 1, cur.col); ptx::bulk_commit(); }
     }
     if (!edge) {
 #pragma unroll
@@ -277,6 +299,57 @@ dg_kronecker_march_kernel(const __grid_constant__ KronTabDev<N> K, const __grid_
     if (exists && cur.z + 1 < cur.zb) apply_axis<N, 2>(K.L[2], v, B);
   }
   if (lane == 0) ptx::bulk_wait_all();
+  if (!C.any) return;
+
+  // ============================== fused Copy exchange: publish, receive, retire ==============================
+  // (1) all bulk stores of this warp (local and remote) have completed; order them before the flags at system scope
+  if (lane == 0) __threadfence_system();
+  asm volatile("bar.sync 1, %0;" ::"n"(Cfg::kConsumers) : "memory");
+  if (tid == 0) {
+    for (int d = 0; d < 9; ++d) {
+      const unsigned int c = s_cnt[d];
+      if (!c) continue;
+      __threadfence();
+      if (atomicAdd(&C.counters[d], c) + c == C.expected[d]) {        // the message is complete: publish its sequence number
+        C.counters[d] = 0; __threadfence_system(); st_release_sys(C.remote_ready[d] + (seq & 1), seq);
+      }
+    }
+  }
+  // (2) receive: the row segments of the incoming messages are dealt to all consumer warps of the (fully resident)
+  // grid; a warp waits for the flag of a message the first time it needs it.  Peers publish from their own compute
+  // kernels, which never wait for anything of this exchange: no cycle.
+  {
+    const int on2 = nz, n0 = box.n[0], n1 = box.n[1];
+    const long long gwarp = (long long)blockIdx.x * kWarps + warp, nwarps = (long long)gridDim.x * kWarps;
+    long long first[10]; first[0] = 0;
+#pragma unroll
+    for (int d = 0; d < 9; ++d) first[d + 1] = first[d] + (C.enabled[d] ? (long long)tiles_x * (d % 3 == 1 ? on1 : 1) * (d / 3 == 1 ? on2 : 1) : 0);
+    unsigned int seen = 0;
+    for (long long it = gwarp; it < first[9]; it += nwarps) {
+      int d = 0;
+#pragma unroll
+      for (int k = 1; k < 9; ++k) if (it >= first[k]) d = k;
+      const int dyc = d % 3, dzc = d / 3, ny = dyc == 1 ? on1 : 1;
+      const long long q = it - first[d]; const int seg = (int)(q % tiles_x); const long long row = q / tiles_x;
+      const int yi = (int)(row % ny), zi = (int)(row / ny);
+      if (!((seen >> d) & 1u)) {
+        int ok = 1;
+        if (lane == 0) ok = wait_flag_ge(C.local_ready[d] + (seq & 1), seq, C.err, kCommTimeoutFused) ? 1 : 0;
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        if (!ok) break;
+        seen |= 1u << d;
+      }
+      const int gy = dyc == 1 ? box.own_lo[1] + yi : (dyc == 0 ? box.own_lo[1] - 1 : box.own_hi[1]);
+      const int gz = dzc == 1 ? box.own_lo[2] + zi : (dzc == 0 ? box.own_lo[2] - 1 : box.own_hi[2]);
+      const int xoff = seg * TX, cnt2 = min(TX, on0 - xoff) * N3 / 2;                 // double2 items of this segment
+      const double2* src = reinterpret_cast<const double2*>(C.local[d][seq & 1] + (row * on0 + xoff) * N3);
+      double2* dst = reinterpret_cast<double2*>(C.w + (((long long)gz * n1 + gy) * n0 + box.own_lo[0] + xoff) * N3);
+      for (int i = lane; i < cnt2; i += 32) dst[i] = __ldcg(src + i);
+    }
+  }
+  // (3) the CTA that finishes last advances the sequence number (the next exchange on this stream reads it)
+  asm volatile("bar.sync 1, %0;" ::"n"(Cfg::kConsumers) : "memory");
+  if (tid == 0) { __threadfence(); if (atomicAdd(&C.counters[9], 1u) == gridDim.x - 1) { C.counters[9] = 0; *C.seq = seq; } }
 }
 
 }  // namespace b200fem

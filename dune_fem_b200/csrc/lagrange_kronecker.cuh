@@ -24,7 +24,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include "lagrange_quadrature.cuh"
-#include "vec_kernels.cuh"
+#include "vec_types.hpp"
 #include <type_traits>
 #include <utility>
 
@@ -36,11 +36,6 @@ template <int N, class F> __device__ __forceinline__ void lagk_static_for(F&& f)
 #ifndef LAGK_PF
 #define LAGK_PF 1      // prefetch distance in planes: 1 needs no spills at 64 registers and measured fastest (284 vs 306 us at 3, C3)
 #endif
-struct LagKronRows {
-  const double* M[3];      // [L_d][2k+1]: row g holds the coefficients of columns g-k .. g+k
-  const double* T[3];
-};
-
 template <int K, int HYP = 16> struct LagKronCfg {
   static constexpr int W = 2 * K + 1, HX = 32, HY = HYP, TX = HX - 2 * K, TY = HY - 2 * K, kThreads = HX * HY;
   static constexpr int kCtasPerSm = HYP <= 16 ? 2 : 1;

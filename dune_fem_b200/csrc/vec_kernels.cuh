@@ -8,35 +8,10 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include "comm.cuh"
+#include "vec_types.hpp"
 
 namespace b200fem {
-
-constexpr int kRedBlocks = 592;     // 4 per SM on 148 SMs
-constexpr int kRedThreads = 256;
-
-// device-resident CG state
-struct CgState {
-  double residual, prev_residual, qdoth, alpha, beta, tolerance, bnorm2;
-  int iterations, done, max_iterations, tol_criteria;
-  double epsilon;
-};
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-__device__ __forceinline__ double block_sum(double v) {
-  __shared__ double part[32];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  v = warp_sum(v);
-  __syncthreads();
-  if (lane == 0) part[wid] = v;
-  __syncthreads();
-  v = (threadIdx.x < (blockDim.x >> 5)) ? part[threadIdx.x] : 0.0;
-  if (wid == 0) v = warp_sum(v);
-  return v;    // valid in thread 0
-}
 
 // partial[b] = sum over this block's grid-stride range of x*y restricted to primary dofs (mask may be null)
 __global__ void __launch_bounds__(kRedThreads) dot_partial_kernel(const double* __restrict__ x, const double* __restrict__ y,
@@ -162,8 +137,35 @@ __device__ __forceinline__ double final_sum(const double* partial) {
   for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) s += __ldcg(partial + i);
   return block_sum(s);
 }
+// Several ranks: the block that has finished the local reduction also performs the global sum over peer memory (comm.cuh:
+// every rank stores its value into every rank's table and adds the table in rank order), so an iteration keeps its 4
+// launches and contains no library call -- it can be captured into a CUDA graph on every rank.  A.world <= 1: no-op.
+// To be called by all threads of the block; t (in/out) is meaningful in thread 0.
+__device__ __forceinline__ double global_sum1(const PeerScalarsDev& A, double t) {
+  if (A.world <= 1) return t;
+  __shared__ double sh_gs[kArMax];
+  if (threadIdx.x == 0) sh_gs[0] = t;
+  __syncthreads();
+  peer_allreduce_block(A, sh_gs, 1);
+  return sh_gs[0];
+}
+// second stage of `count` (<= kArMax) two-stage reductions + global sum: out[k] = sum over ranks of sum(partial[k * nparts ..])
+__global__ void __launch_bounds__(kRedThreads) reduce_final_allreduce_kernel(const double* __restrict__ partial, int nparts, int count, double* __restrict__ out,
+                                                                             const __grid_constant__ PeerScalarsDev A) {
+  __shared__ double sh[kArMax];
+  for (int k = 0; k < count; ++k) {
+    double s = 0;
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) s += partial[(size_t)k * nparts + i];
+    s = block_sum(s);
+    if (threadIdx.x == 0) sh[k] = s;
+  }
+  __syncthreads();
+  if (A.world > 1) peer_allreduce_block(A, sh, count);
+  if ((int)threadIdx.x < count) out[threadIdx.x] = sh[threadIdx.x];
+}
 __global__ void __launch_bounds__(kRedThreads) cg_dot_alpha_kernel(const double* __restrict__ x, const double* __restrict__ y, const uint8_t* __restrict__ aux,
-                                                                   long long n, double* partial, CgState* st, unsigned int* counter) {
+                                                                   long long n, double* partial, CgState* st, unsigned int* counter,
+                                                                   const __grid_constant__ PeerScalarsDev A) {
   if (st->done) return;
   double s = 0;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(kRedThreads) cg_dot_alpha_kernel(const double*
   s = block_sum(s);
   if (threadIdx.x == 0) partial[blockIdx.x] = s;
   if (!last_block_done(counter)) return;
-  const double t = final_sum(partial);
+  const double t = global_sum1(A, final_sum(partial));
   if (threadIdx.x == 0) { st->qdoth = t; st->alpha = st->residual / t; *counter = 0; }
 }
 // <q,h> arrives as per-CTA partials of the apply kernel (lagrange_kronecker_kernel's fused scalar product): alpha = residual / <q,h>
@@ -194,7 +196,8 @@ __global__ void __launch_bounds__(kRedThreads) cg_alpha_partials_kernel(const do
 }
 __global__ void __launch_bounds__(kRedThreads) cg_update_xr_residual_kernel(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
                                                                             const double* __restrict__ h, const uint8_t* __restrict__ aux, long long n,
-                                                                            double* partial, CgState* st, double* __restrict__ history, unsigned int* counter) {
+                                                                            double* partial, CgState* st, double* __restrict__ history, unsigned int* counter,
+                                                                            const __grid_constant__ PeerScalarsDev A) {
   if (st->done) return;
   const double alpha = st->alpha;
   double s = 0;
@@ -220,7 +223,7 @@ __global__ void __launch_bounds__(kRedThreads) cg_update_xr_residual_kernel(doub
   s = block_sum(s);
   if (threadIdx.x == 0) partial[blockIdx.x] = s;
   if (!last_block_done(counter)) return;
-  const double t = final_sum(partial);
+  const double t = global_sum1(A, final_sum(partial));
   if (threadIdx.x == 0) {
     st->prev_residual = st->residual; st->residual = t;
     if (history) history[st->iterations] = sqrt(t);
@@ -233,11 +236,6 @@ __global__ void __launch_bounds__(kRedThreads) cg_update_xr_residual_kernel(doub
 // ---- BiCGStab (solver/linear/bicgstab.hh:64-214, unpreconditioned; five-fold scalar product of :19-52) ----
 // Scalars live on the device; an iteration is  [tmp = A p] [<tmp,r*> -> alpha] [s = r - alpha tmp] [r = A s]
 // [5 dots -> omega, res, beta, nu, convergence] [x += alpha p + omega s ; r = s - omega r ; p = r + beta (p - omega tmp)].
-struct BicgState {
-  double nu, alpha, omega, beta, res, tolerance, bnorm2;
-  int iterations, done, max_iterations, tol_criteria, x_applied;
-  double epsilon;
-};
 // r = b - r ; p = r ; r* = r ; partial <r,r*> and <b,b>                    (bicgstab.hh:94-122)
 __global__ void __launch_bounds__(kRedThreads) bicg_init_kernel(double* __restrict__ r, const double* __restrict__ b, double* __restrict__ p, double* __restrict__ rstar,
                                                                 const uint8_t* __restrict__ aux, long long n, double* __restrict__ partial, double* __restrict__ partial_b) {
@@ -268,7 +266,8 @@ __device__ __forceinline__ void bicg_scalars(const double* gd, BicgState* st, do
 }
 // partial <tmp, r*>; single rank: the last block computes alpha = nu / <tmp,r*>
 __global__ void __launch_bounds__(kRedThreads) bicg_dot_alpha_kernel(const double* __restrict__ tmp, const double* __restrict__ rstar, const uint8_t* __restrict__ aux,
-                                                                     long long n, double* partial, BicgState* st, unsigned int* counter) {
+                                                                     long long n, double* partial, BicgState* st, unsigned int* counter,
+                                                                     const __grid_constant__ PeerScalarsDev A) {
   if (st->done) return;
   double s = 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -276,7 +275,7 @@ __global__ void __launch_bounds__(kRedThreads) bicg_dot_alpha_kernel(const doubl
   s = block_sum(s);
   if (threadIdx.x == 0) partial[blockIdx.x] = s;
   if (!counter || !last_block_done(counter)) return;
-  const double t = final_sum(partial);
+  const double t = global_sum1(A, final_sum(partial));
   if (threadIdx.x == 0) { st->alpha = st->nu / t; *counter = 0; }
 }
 __global__ void bicg_alpha_kernel(const double* __restrict__ sums, BicgState* st) { if (threadIdx.x == 0 && blockIdx.x == 0 && !st->done) st->alpha = st->nu / sums[0]; }
@@ -288,7 +287,8 @@ __global__ void bicg_s_kernel(double* __restrict__ s, const double* __restrict__
 }
 // the five scalar products r.s, r.r, s.s, s.r*, r.r* in one sweep (scalarProductVecs); partial[k * gridDim.x + block]
 __global__ void __launch_bounds__(kRedThreads) bicg_dots5_kernel(const double* __restrict__ r, const double* __restrict__ s, const double* __restrict__ rstar,
-                                                                 const uint8_t* __restrict__ aux, long long n, double* partial, BicgState* st, double* history, unsigned int* counter) {
+                                                                 const uint8_t* __restrict__ aux, long long n, double* partial, BicgState* st, double* history, unsigned int* counter,
+                                                                 const __grid_constant__ PeerScalarsDev A) {
   if (st->done) return;
   double d[5] = {0, 0, 0, 0, 0};
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -296,9 +296,11 @@ __global__ void __launch_bounds__(kRedThreads) bicg_dots5_kernel(const double* _
 #pragma unroll
   for (int k = 0; k < 5; ++k) { const double t = block_sum(d[k]); if (threadIdx.x == 0) partial[(size_t)k * gridDim.x + blockIdx.x] = t; }
   if (!counter || !last_block_done(counter)) return;
-  __shared__ double gd[5];
+  __shared__ double gd[kArMax];
 #pragma unroll
   for (int k = 0; k < 5; ++k) { const double t = final_sum(partial + (size_t)k * gridDim.x); if (threadIdx.x == 0) gd[k] = t; }
+  __syncthreads();
+  if (A.world > 1) peer_allreduce_block(A, gd, 5);
   if (threadIdx.x == 0) { bicg_scalars(gd, st, history); *counter = 0; }
 }
 __global__ void bicg_scalars_kernel(const double* __restrict__ sums, BicgState* st, double* history) { if (threadIdx.x == 0 && blockIdx.x == 0 && !st->done) bicg_scalars(sums, st, history); }
@@ -318,8 +320,6 @@ __global__ void __launch_bounds__(kRedThreads) bicg_update_kernel(double* __rest
 
 // ---- GMRES (solver/linear/gmres.hh:117-301) vector work; the (m+1) x m Hessenberg matrix, the Givens rotations and the
 // back substitution are O(m^2) scalars and stay on the host like in the reference ----
-constexpr int kGemvChunk = 8;
-struct GmresVecs { const double* v[kGemvChunk]; };
 // y[l] = <vjp, v_l> over primary dofs for up to kGemvChunk basis vectors in ONE sweep over vjp (gemv, gmres.hh:64-92);
 // partial[l * gridDim.x + block]
 __global__ void __launch_bounds__(kRedThreads) gmres_gemv_kernel(const double* __restrict__ vjp, const GmresVecs V, int count, const uint8_t* __restrict__ aux,
@@ -354,7 +354,6 @@ __global__ void scale_kernel(double* __restrict__ x, double a, long long n) {
 }
 
 // ---- AutomaticDifferenceLinearOperator (operator/common/automaticdifferenceoperator.hh:124-149): dest = (L[u + eps arg] - L[u]) / eps ----
-struct FdState { double eps_given, norm_u, eps; };
 // eps = eps_given > 0 ? eps_given : sqrt((1 + |u|) macheps / |arg|^2)   (|arg|^2 = sums[0], globally reduced)
 __global__ void fd_eps_kernel(const double* __restrict__ sums, FdState* st) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -396,7 +395,8 @@ __global__ void pcg_update_q_kernel(double* __restrict__ q, const double* __rest
 // x += alpha q ; p -= alpha h ; s = B p ; partial <p,s>   (cg.hh:92-101); the last block closes the iteration
 __global__ void __launch_bounds__(kRedThreads) pcg_update_kernel(double* __restrict__ x, double* __restrict__ p, double* __restrict__ s_, const double* __restrict__ q,
                                                                  const double* __restrict__ h, const double* __restrict__ dinv, const uint8_t* __restrict__ aux, long long n,
-                                                                 double* partial, CgState* st, double* __restrict__ history, unsigned int* counter) {
+                                                                 double* partial, CgState* st, double* __restrict__ history, unsigned int* counter,
+                                                                 const __grid_constant__ PeerScalarsDev A) {
   if (st->done) return;
   const double alpha = st->alpha;
   double s = 0;
@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(kRedThreads) pcg_update_kernel(double* __restr
   s = block_sum(s);
   if (threadIdx.x == 0) partial[blockIdx.x] = s;
   if (!counter || !last_block_done(counter)) return;
-  const double t = final_sum(partial);
+  const double t = global_sum1(A, final_sum(partial));
   if (threadIdx.x == 0) {
     st->prev_residual = st->residual; st->residual = t;
     if (history) history[st->iterations] = sqrt(t);

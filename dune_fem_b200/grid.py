@@ -25,6 +25,20 @@ class Context:
     def synchronize(self):
         capi.check(capi.lib().b200fem_ctx_synchronize(self.handle))
 
+    def close(self):
+        """destroys the context (stream, communicator, peer mappings); every grid / space / operator made from it must
+        have been closed or dropped before"""
+        if self.handle:
+            capi.lib().b200fem_ctx_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    @property
+    def peer_memory(self):
+        """True when halo exchange and scalar sums use peer-mapped mailboxes over NVLink, False for the NCCL transport"""
+        v = C.c_int()
+        capi.check(capi.lib().b200fem_ctx_transport(self.handle, C.byref(v)))
+        return bool(v.value)
+
     def init_nccl(self, unique_id: bytes, rank: int, world: int):
         buf = C.create_string_buffer(unique_id, 128)
         capi.check(capi.lib().b200fem_nccl_init(self.handle, buf, rank, world))
@@ -53,6 +67,17 @@ class GridView:
             capi.check(capi.lib().b200fem_mesh_cartesian_distributed(self.ctx.handle, self.dim, n_a, lo_a, hi_a, p_a, rank,
                                                                      C.byref(self.handle)))
         self.proc, self.rank = proc, rank
+
+    def close(self):
+        if self.handle:
+            capi.lib().b200fem_mesh_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):       # (spaces keep their grid view alive through self.gridView, grid views their context)
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def structuredGrid(lo, hi, n, ctx=None, proc=None, rank=0):

@@ -56,10 +56,14 @@ class GalerkinOperator:
     def setKernel(self, kernel):
         capi.check(capi.lib().b200fem_operator_set_kernel(self.handle, kernel))
 
+    def setHostPipeline(self, chunks):
+        """z-slabs of the H2D / compute / D2H pipeline of __call__ on DG spaces (0: one copy each way)"""
+        capi.check(capi.lib().b200fem_operator_set_host_pipeline(self.handle, int(chunks)))
+
     def dirichlet(self):
         mask = np.zeros(self.space.size, dtype=np.uint8)
         vals = np.zeros(self.space.size)
-        capi.check(capi.lib().b200fem_operator_dirichlet(self.handle, capi.ptr(mask), capi.ptr(vals)))
+        capi.check(capi.lib().b200fem_operator_dirichlet(self.handle, capi.ptr(mask, np.uint8), capi.ptr(vals)))
         return mask, vals
 
     def timing(self):
@@ -91,9 +95,14 @@ class GalerkinOperator:
     def communicate_dev(self, v_ptr):
         capi.check(capi.lib().b200fem_communicate_dev(self.handle, C.c_void_p(v_ptr)))
 
+    def close(self):
+        if self.handle:
+            capi.lib().b200fem_operator_destroy(self.handle)
+            self.handle = C.c_void_p()
+
     def __del__(self):
         try:
-            capi.lib().b200fem_operator_destroy(self.handle)
+            self.close()
         except Exception:
             pass
 

@@ -20,6 +20,17 @@ class DiscreteFunctionSpace:
         capi.check(capi.lib().b200fem_space_local_size(self.handle, C.byref(nb)))
         self.localBlockSize = nb.value
 
+    def close(self):
+        if self.handle:
+            capi.lib().b200fem_space_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):       # (operators keep their space alive through self.space)
+        try:
+            self.close()
+        except Exception:
+            pass
+
     def mapper(self, element):
         """blockMapper().map(entity) -- global dof indices of an element"""
         out = np.empty(self.localBlockSize, dtype=np.int64)

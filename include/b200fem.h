@@ -40,7 +40,9 @@ enum b200fem_numbering { B200FEM_NUMBERING_YASP = 0, B200FEM_NUMBERING_ADAPTIVE_
 enum b200fem_kernel {
   B200FEM_KERNEL_AUTO = 0,       /* fastest kernel that is valid for the model                              */
   B200FEM_KERNEL_QUADRATURE = 1, /* generic: gather, basis evaluation at quadrature points, integrand, axpy */
-  B200FEM_KERNEL_KRONECKER = 2   /* linear constant-coefficient models on uniform boxes: 1-D operator form  */
+  B200FEM_KERNEL_KRONECKER = 2,  /* linear constant-coefficient models on uniform boxes: 1-D operator form  */
+  B200FEM_KERNEL_KRONECKER_TILE = 3 /* same form through the plain tile kernel (DG Q1/Q2; the fallback of the TMA marching
+                                       kernel, selectable for A/B checks)                                        */
 };
 /* solver/parameter.hh:21-295 "fem.solver.errormeasure" */
 enum b200fem_tolerance { B200FEM_TOL_ABSOLUTE = 0, B200FEM_TOL_RELATIVE = 1, B200FEM_TOL_RESIDUAL_REDUCTION = 2 };
@@ -121,6 +123,8 @@ int b200fem_operator_load_vector(b200fem_operator* op, double* b_host);
 int b200fem_operator_set_communicate(b200fem_operator* op, int communicate);                    /* galerkin.hh:1409 */
 int b200fem_operator_set_quadrature_orders(b200fem_operator* op, unsigned interior, unsigned surface); /* :1418-1423 */
 int b200fem_operator_set_kernel(b200fem_operator* op, int kernel);
+/* host-pointer apply of DG spaces: number of z-slabs of the H2D / compute / D2H pipeline (default 8; 0 or 1: one copy each way) */
+int b200fem_operator_set_host_pipeline(b200fem_operator* op, int chunks);
 /* MOLGalerkinOperator (schemes/molgalerkin.hh:100-124, 162-197; python molGalerkin, operator/__init__.py:203-207): apply the
  * inverse of the local mass matrix after the evaluate, w = M^-1 L[u] -- the form explicit time stepping uses.  For the
  * orthonormal Legendre bases on affine cells this is the scalar referenceVolume / volume per element
@@ -188,10 +192,17 @@ int b200fem_axpy_dev(b200fem_operator* op, double alpha, const double* x_dev, do
 /* Multi-GPU: one process per GPU.  `nccl_comm` is an ncclComm_t created by the caller (e.g. from an id broadcast
  * through torch.distributed); halo exchange replaces DiscreteFunction::communicate
  * (function/common/discretefunction.hh:825-835, space/common/communicationmanager.hh:130-150): Copy for DG,
- * Add for Lagrange; dots use ncclAllReduce. */
+ * Add for Lagrange.  Default transport: peer-mapped mailboxes written directly over NVLink by the kernels (the DG marching
+ * kernel sends and receives inside the apply kernel itself; scalar products are summed inside the reduction kernels), so that
+ * Krylov iterations contain no library call and are replayed as CUDA graphs on every rank; ncclSend/Recv + ncclAllReduce when
+ * peer mappings are unavailable (or B200FEM_NO_P2P is set when the communicator is attached).  A peer that does not arrive
+ * within 20 s makes the next entry point return B200FEM_ERR_COMM instead of hanging. */
 int b200fem_ctx_set_nccl(b200fem_ctx* ctx, void* nccl_comm, int rank, int world);
 int b200fem_nccl_unique_id(void* out128);
 int b200fem_nccl_init(b200fem_ctx* ctx, const void* id128, int rank, int world);
+/* *peer_memory = 1 when halo exchange and scalar sums run over peer-mapped mailboxes (cudaIpc, NVLink), 0 when they use
+ * ncclSend/ncclRecv/ncclAllReduce (the choice is collective: all ranks agree) */
+int b200fem_ctx_transport(b200fem_ctx* ctx, int* peer_memory);
 /* exchange the ghost layer of a device dof vector of `space` in place */
 int b200fem_communicate_dev(b200fem_operator* op, double* v_dev);
 

@@ -1,13 +1,11 @@
 """GPU parity of the z-marching Kronecker DG kernel (dg_kronecker_march.cuh) through the C ABI.
 
 Oracle comparisons on meshes the CPU restatement finishes in seconds; on a larger mesh the marching kernel is compared
-with the tile kernel (dg_kronecker_tensor.cuh), which is itself pinned to the oracle in test_gpu_parity.py.
+with the plain tile kernel (dg_kronecker.cuh, B200FEM_KERNEL_KRONECKER_TILE), which is itself pinned to the oracle in test_gpu_parity.py.
 Tolerance 1e-12 relative to max|w| (north_star).  Mesh sizes cover: partial tiles in x and y (tile = 16 x 16 elements),
 a single plane, runs that cross column boundaries, one-element extents, both local dof orderings, and both the dense and
 the checkerboard (no advection along y, z) self-matrix code paths.
 """
-import os
-
 import numpy as np
 import pytest
 
@@ -25,19 +23,12 @@ def rel(a, b):
 
 
 def run(space, variant, u, **kw):
-    old = os.environ.get("B200FEM_KRON_VARIANT")
-    os.environ["B200FEM_KRON_VARIANT"] = variant
-    try:
-        op = fem.operator.galerkin(space, beta=80.0, kernel=_capi.KERNEL_KRONECKER, **kw)
-        w, wl = np.full(space.size, np.nan), np.full(space.size, np.nan)
-        op(u, w)
-        op.applyLinear(u, wl)
-        return w, wl
-    finally:
-        if old is None:
-            del os.environ["B200FEM_KRON_VARIANT"]
-        else:
-            os.environ["B200FEM_KRON_VARIANT"] = old
+    kernel = {"march": _capi.KERNEL_KRONECKER, "tile": _capi.KERNEL_KRONECKER_TILE}[variant]
+    op = fem.operator.galerkin(space, beta=80.0, kernel=kernel, **kw)
+    w, wl = np.full(space.size, np.nan), np.full(space.size, np.nan)
+    op(u, w)
+    op.applyLinear(u, wl)
+    return w, wl
 
 
 @pytest.mark.parametrize("bvel", [(1.0, -0.5, 0.25), (1.0, 0.0, 0.0)])
@@ -61,5 +52,5 @@ def test_march_kernel_against_tile_kernel_large(bvel):
     kw = dict(eps=1e-5, b=bvel, dirichlet_mask=0b000011, data=1)
     u = np.random.default_rng(11).uniform(-1, 1, space.size)
     wm, wlm = run(space, "march", u, **kw)
-    wt, wlt = run(space, "tensor", u, **kw)
+    wt, wlt = run(space, "tile", u, **kw)
     assert rel(wm, wt) < TOL and rel(wlm, wlt) < TOL

@@ -250,7 +250,7 @@ def test_full_size_c2_properties():
 
 
 @pytest.mark.parametrize("order,n", [(2, [32, 32, 40]), (3, [24, 24, 33])])
-def test_host_apply_pipeline_matches_single_copy(order, n, monkeypatch):
+def test_host_apply_pipeline_matches_single_copy(order, n):
     """b200fem_operator_apply overlaps H2D, compute and D2H over z-slabs for DG spaces: same bits as the plain path."""
     space = fem.space.dglegendre(fem.structuredGrid([-1, -1, -1], [1, 1, 1], n), order=order, hierarchical=True)
     assert space.size * 8 >= 8 << 20
@@ -260,11 +260,11 @@ def test_host_apply_pipeline_matches_single_copy(order, n, monkeypatch):
     w_pipe, w_plain = np.empty(space.size), np.empty(space.size)
     op(u, w_pipe)
     assert op.timing()["launches_per_apply"] >= 4          # one launch per slab
-    monkeypatch.setenv("B200FEM_NO_PIPELINE", "1")
+    op.setHostPipeline(0)
     op(u, w_plain)
     assert np.array_equal(w_pipe, w_plain)
     op.applyLinear(u, w_plain)
-    monkeypatch.delenv("B200FEM_NO_PIPELINE")
+    op.setHostPipeline(8)
     op.applyLinear(u, w_pipe)
     assert np.array_equal(w_pipe, w_plain)
 
