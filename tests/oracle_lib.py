@@ -27,7 +27,10 @@ def lib():
         return _LIB
     so = os.path.join(_ORACLE_DIR, "libfem_oracle.so")
     src = os.path.join(_ORACLE_DIR, "fem_oracle.cpp")
-    if not os.path.exists(so) or (os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(so)):
+    native = os.environ.get("B200FEM_ORACLE_SO")      # bench.py's CPU legs: the same source built -march=native on the timed host
+    if native and os.path.exists(native) and os.path.getmtime(native) >= os.path.getmtime(src):
+        so = native
+    elif not os.path.exists(so) or (os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(so)):
         subprocess.check_call(["make", "-C", _ORACLE_DIR, "-s"])
     L = C.CDLL(so)
     L.fo_space_create.restype = C.c_void_p
