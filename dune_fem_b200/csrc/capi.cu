@@ -41,14 +41,20 @@ extern "C" int b200fem_ctx_create(int device, void* stream, b200fem_ctx** out) {
   CUDA_OK(cudaHostGetDevicePointer((void**)&c->d_comm_error, c->h_comm_error, 0));
   *out = c; return B200FEM_OK;
 }
-extern "C" int b200fem_ctx_destroy(b200fem_ctx* c) {
-  if (!c) return B200FEM_OK;
+static void ctx_delete(b200fem_ctx* c) {
   cudaSetDevice(c->device);
   if (c->scalars.ok) peer_scalars_free(c->scalars);
   if (c->own_comm && c->comm && c->nccl.ok()) c->nccl.CommDestroy(c->comm);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   if (c->h_comm_error) cudaFreeHost(c->h_comm_error);
-  delete c; return B200FEM_OK;
+  delete c;
+}
+static void ctx_unref(b200fem_ctx* c) { if (--c->refs <= 0 && c->released) ctx_delete(c); }
+extern "C" int b200fem_ctx_destroy(b200fem_ctx* c) {
+  if (!c || c->released) return B200FEM_OK;
+  c->released = true;
+  if (c->refs <= 0) ctx_delete(c);
+  return B200FEM_OK;
 }
 extern "C" int b200fem_ctx_synchronize(b200fem_ctx* c) { REQUIRE(c, B200FEM_ERR_INVALID, "null ctx"); CUDA_OK(cudaSetDevice(c->device)); CUDA_OK(cudaStreamSynchronize(c->stream)); return check_comm_error(c); }
 extern "C" int b200fem_malloc(b200fem_ctx* c, int64_t bytes, void** dev) { REQUIRE(c && dev, B200FEM_ERR_INVALID, "malloc: null"); CUDA_OK(cudaSetDevice(c->device)); CUDA_OK(cudaMalloc(dev, (size_t)bytes)); return B200FEM_OK; }
@@ -82,6 +88,7 @@ static int make_mesh(b200fem_ctx* ctx, int dim, const int32_t* n, const double* 
     b.own_lo[d] = glo; b.own_hi[d] = glo + (m->ohi[d] - m->olo[d]);
     b.gn[d] = m->gn[d]; b.lo[d] = m->lo[d]; b.h[d] = m->h[d];
   }
+  ctx->refs += 1;
   *out = m; return B200FEM_OK;
 }
 extern "C" int b200fem_mesh_cartesian(b200fem_ctx* ctx, int dim, const int32_t* n, const double* lo, const double* hi, b200fem_mesh** out) {
@@ -91,7 +98,13 @@ extern "C" int b200fem_mesh_cartesian_distributed(b200fem_ctx* ctx, int dim, con
   REQUIRE(proc, B200FEM_ERR_INVALID, "mesh: proc is null");
   return make_mesh(ctx, dim, n, lo, hi, proc, rank, out);
 }
-extern "C" int b200fem_mesh_destroy(b200fem_mesh* m) { delete m; return B200FEM_OK; }
+static void mesh_unref(b200fem_mesh* m) { if (--m->refs <= 0 && m->released) { ctx_unref(m->ctx); delete m; } }
+extern "C" int b200fem_mesh_destroy(b200fem_mesh* m) {
+  if (!m || m->released) return B200FEM_OK;
+  m->released = true;
+  if (m->refs <= 0) { ctx_unref(m->ctx); delete m; }
+  return B200FEM_OK;
+}
 extern "C" int b200fem_partition_box(int dim, const int32_t* n, const int32_t* proc, int rank, int overlap, int32_t* out) {
   REQUIRE(n && proc && out && (dim == 2 || dim == 3), B200FEM_ERR_INVALID, "partition_box: bad argument");
   int p[3] = {1, 1, 1}, g[3] = {1, 1, 1}, world = 1;
@@ -180,10 +193,18 @@ extern "C" int b200fem_space_create(b200fem_mesh* mesh, int kind, int order, int
       s->tab = tabulate_1d(Basis::Legendre, order, gauss_points_for_order(2 * order));
       s->perm = legendre_local_permutation(dim, order, kind == B200FEM_DG_LEGENDRE_HIER);
     }
+    mesh->refs += 1;
     *out = s.release(); return B200FEM_OK;
   } catch (const std::exception& ex) { return fail(B200FEM_ERR_INVALID, ex.what()); }
 }
-extern "C" int b200fem_space_destroy(b200fem_space* s) { if (s && s->d_lattice_map) cudaFree(s->d_lattice_map); delete s; return B200FEM_OK; }
+static void space_delete(b200fem_space* s) { if (s->d_lattice_map) { cudaSetDevice(s->mesh->ctx->device); cudaFree(s->d_lattice_map); } mesh_unref(s->mesh); delete s; }
+static void space_unref(b200fem_space* s) { if (--s->refs <= 0 && s->released) space_delete(s); }
+extern "C" int b200fem_space_destroy(b200fem_space* s) {
+  if (!s || s->released) return B200FEM_OK;
+  s->released = true;
+  if (s->refs <= 0) space_delete(s);
+  return B200FEM_OK;
+}
 extern "C" int b200fem_space_size(b200fem_space* s, int64_t* size) { REQUIRE(s && size, B200FEM_ERR_INVALID, "null"); *size = s->size; return B200FEM_OK; }
 extern "C" int b200fem_space_local_size(b200fem_space* s, int32_t* nb) { REQUIRE(s && nb, B200FEM_ERR_INVALID, "null"); *nb = s->nb; return B200FEM_OK; }
 extern "C" int b200fem_space_elements(b200fem_space* s, int64_t* n) { REQUIRE(s && n, B200FEM_ERR_INVALID, "null"); *n = s->elements; return B200FEM_OK; }
@@ -232,7 +253,7 @@ extern "C" int b200fem_operator_create(b200fem_space* s, const b200fem_model* mo
   REQUIRE(!(model->strong_dirichlet && s->kind != B200FEM_LAGRANGE), B200FEM_ERR_INVALID, "strong Dirichlet constraints need a Lagrange space");
   b200fem_ctx* c = s->mesh->ctx;
   CUDA_OK(cudaSetDevice(c->device));
-  auto* op = new b200fem_operator; op->sp = s; op->model = *model;
+  auto* op = new b200fem_operator; op->sp = s; op->model = *model; s->refs += 1;
   if (s->kind != B200FEM_LAGRANGE) {
     CUDA_OK(cudaMalloc(&op->d_perm, sizeof(int) * s->perm.size()));
     CUDA_OK(cudaMemcpy(op->d_perm, s->perm.data(), sizeof(int) * s->perm.size(), cudaMemcpyHostToDevice));
@@ -288,6 +309,7 @@ extern "C" int b200fem_operator_destroy(b200fem_operator* op) {
   if (op->d2h_stream) cudaStreamDestroy(op->d2h_stream);
   for (cudaEvent_t e : op->pipe_ev) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : {op->ev0, op->ev1, op->evx0, op->evx1}) if (e) cudaEventDestroy(e);
+  space_unref(op->sp);
   delete op; return B200FEM_OK;
 }
 extern "C" int b200fem_operator_apply(b200fem_operator* op, const double* u, double* w) { return apply_host(op, u, w, false); }

@@ -39,18 +39,22 @@ struct b200fem_ctx {
   b200fem::PeerScalars scalars;                 // peer-memory all-reduce of scalars (dot products), built with the communicator
   int* h_comm_error = nullptr; int* d_comm_error = nullptr;   // mapped host word: kernels report communication time-outs here
   std::set<const void*> attr_set;               // kernels whose dynamic shared memory limit has been raised ON THIS DEVICE
+  int refs = 0; bool released = false;          // handles are reference counted: a parent destroyed before its children (garbage
+                                                // collectors finalise in any order) lives on until the last child is gone
 };
 struct b200fem_mesh {
   b200fem_ctx* ctx; int dim; int gn[3]; double lo[3], hi[3], h[3];
   int proc[3], pc[3];                    // process grid and this rank's coordinates
   b200fem::BoxDev box;                   // local box incl. ghost layers (ghost layers only used by DG spaces)
   int olo[3], ohi[3];                    // owned range in global element coordinates
+  int refs = 0; bool released = false;
 };
 struct b200fem_space {
   b200fem_mesh* mesh; int kind, order, numbering, n1, nb; long long size, elements;
   b200fem::BoxDev box;                   // DG: mesh box with ghosts; Lagrange: owned elements only
   b200fem::Tab1D tab; std::vector<int> perm;
   b200fem::LagrangeLayoutDev lay; long long* d_lattice_map = nullptr; std::vector<long long> lattice_map;
+  int refs = 0; bool released = false;
 };
 struct MarchMapCache;
 struct b200fem_operator {
