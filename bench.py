@@ -305,8 +305,6 @@ def main():
     for i in range(npairs):
         step(i, linear=True)
     ms_linear, _ = timed_loop(lambda i: step(i, True), args.steps)
-    tinfo = op.timing()            # (also switches the per-apply timing events on: keep it after the timed loops)
-    launches = tinfo["launches_per_apply"] * args.steps
 
     # multi-GPU diagnostics: the halo exchange alone and the local kernels alone (same stream, same buffers)
     diag = None
@@ -322,6 +320,8 @@ def main():
         diag = {"exchange_only_us": 1e3 * ex_ms / 200, "local_kernels_only_us": 1e3 * comp_ms / 200,
                 "transport": "peer memory (fused into the marching kernel)" if ctx.peer_memory else "nccl send/recv"}
 
+    tinfo = op.timing()            # (switches the per-apply timing events on, which serialises launches: only after ALL timed loops)
+    launches = tinfo["launches_per_apply"] * args.steps
     value = ndof_total * args.steps / (ms * 1e-3)
     per_launch_s = ms * 1e-3 / args.steps
     kernel_name = {1: "dg_quadrature_kernel<3>", 2: "dg_kronecker_march_kernel<3>"}.get(tinfo["kernel"], "?")

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libb200fem.so")
 SYMBOLS = [
     "b200fem_last_error", "b200fem_version", "b200fem_ctx_create", "b200fem_ctx_destroy", "b200fem_ctx_synchronize",
     "b200fem_malloc", "b200fem_free", "b200fem_memcpy_h2d", "b200fem_memcpy_d2h", "b200fem_mesh_cartesian",
-    "b200fem_mesh_cartesian_distributed", "b200fem_mesh_destroy", "b200fem_partition_box", "b200fem_mesh_local_box", "b200fem_space_create", "b200fem_space_destroy",
+    "b200fem_mesh_cartesian_distributed", "b200fem_mesh_destroy", "b200fem_partition_box", "b200fem_mesh_local_box", "b200fem_march_schedule", "b200fem_space_create", "b200fem_space_destroy",
     "b200fem_space_size", "b200fem_space_local_size", "b200fem_space_elements", "b200fem_space_dofmap",
     "b200fem_operator_create", "b200fem_operator_destroy", "b200fem_operator_apply", "b200fem_operator_apply_linear",
     "b200fem_operator_apply_dev", "b200fem_operator_load_vector", "b200fem_operator_set_communicate",
@@ -71,6 +71,7 @@ def lib():
         "b200fem_mesh_destroy": [vp],
         "b200fem_partition_box": [C.c_int, P(i32), P(i32), C.c_int, C.c_int, P(i32)],
         "b200fem_mesh_local_box": [vp, C.c_int, P(i32)],
+        "b200fem_march_schedule": [P(i32), C.c_int, C.c_int, P(i32), i32, P(i32), P(i32)],
         "b200fem_space_create": [vp, C.c_int, C.c_int, C.c_int, P(vp)], "b200fem_space_destroy": [vp],
         "b200fem_space_size": [vp, P(i64)], "b200fem_space_local_size": [vp, P(i32)], "b200fem_space_elements": [vp, P(i64)],
         "b200fem_space_dofmap": [vp, i64, P(i64)],

@@ -287,6 +287,15 @@ static void block_extents(const int gn[3], const int proc[3], const int c[3], in
 }
 
 void halo_plan_p2p_free(HaloPlanP2P& p) {
+  if (p.d_march_ts) {      // diagnostics (B200FEM_MARCH_TS): tail phases of the last fused exchange, ns after the end of CTA 0's main loop
+    std::vector<unsigned long long> h(16 + 4 * 160); cudaDeviceSynchronize(); cudaMemcpy(h.data(), p.d_march_ts, h.size() * 8, cudaMemcpyDeviceToHost); cudaFree(p.d_march_ts);
+    std::fprintf(stderr, "[b200fem march tail, ns] CTA 0: stores complete +%lld | sends accounted +%lld | first flag seen +%lld | receive done +%lld | start -> loop end %lld | previous tail end -> this start %lld\n",
+                 (long long)(h[1] - h[0]), (long long)(h[2] - h[0]), (long long)(h[5] - h[0]), (long long)(h[6] - h[0]), (long long)(h[0] - h[8]), (long long)(h[8] - h[9]));
+    unsigned long long s0 = ~0ull, s1 = 0, e0 = ~0ull, e1 = 0, p1 = 0, t1 = 0; int n = 0;
+    for (int b = 0; b < 160; ++b) { const unsigned long long st = h[16 + 4 * b], en = h[16 + 4 * b + 1], pe = h[16 + 4 * b + 2], te = h[16 + 4 * b + 3]; if (!st) continue; ++n; s0 = std::min(s0, st); s1 = std::max(s1, st); e0 = std::min(e0, en); e1 = std::max(e1, en); p1 = std::max(p1, pe); t1 = std::max(t1, te); }
+    std::fprintf(stderr, "[b200fem march tail, ns] %d CTAs: starts spread %lld | loop ends spread %lld | first start -> last loop end %lld | last loop end -> last tail end %lld | previous launch's last TAIL end -> first start %lld\n",
+                 n, (long long)(s1 - s0), (long long)(e1 - e0), (long long)(e1 - s0), (long long)(t1 - e1), (long long)(s0 - p1));
+  }
   for (void* q : p.owned) cudaFree(q);
   for (void* q : {(void*)p.d_nb, (void*)p.d_counters, (void*)p.d_seq, (void*)p.d_done, (void*)p.d_march_counters}) if (q) cudaFree(q);
   peer_region_free(p.region);
@@ -347,7 +356,7 @@ int halo_plan_p2p_build(HaloPlanP2P& p, HaloPlanDG& dg, NcclApi& nccl, void* com
   {
     MarchCommDev& m = p.march; std::memset(&m, 0, sizeof(m));
     bool plane_only = proc[0] == 1;
-    cudaMalloc(&p.d_march_counters, sizeof(unsigned int) * 10); cudaMemset(p.d_march_counters, 0, sizeof(unsigned int) * 10);
+    cudaMalloc(&p.d_march_counters, sizeof(unsigned int) * 12); cudaMemset(p.d_march_counters, 0, sizeof(unsigned int) * 12);
     const int on[3] = {box.own_hi[0] - box.own_lo[0], box.own_hi[1] - box.own_lo[1], box.own_hi[2] - box.own_lo[2]};
     const unsigned tiles_x = (unsigned)((on[0] + 15) / 16);
     for (int i = 0; i < p.nnb; ++i) {
@@ -359,7 +368,8 @@ int halo_plan_p2p_build(HaloPlanP2P& p, HaloPlanDG& dg, NcclApi& nccl, void* com
       m.local[d9][0] = host[(size_t)i].local_data[0]; m.local[d9][1] = host[(size_t)i].local_data[1]; m.local_ready[d9] = host[(size_t)i].local_ready;
       m.expected[d9] = tiles_x * (unsigned)(dy == 0 ? on[1] : 1) * (unsigned)(dz == 0 ? on[2] : 1);
     }
-    m.counters = p.d_march_counters; m.seq = p.d_seq; m.err = d_err; m.w = nullptr;
+    m.counters = p.d_march_counters; m.seq = p.d_seq; m.err = d_err; m.w = nullptr; m.ts = nullptr;
+    if (std::getenv("B200FEM_MARCH_TS")) { cudaMalloc(&p.d_march_ts, (16 + 4 * 160) * sizeof(unsigned long long)); cudaMemset(p.d_march_ts, 0, (16 + 4 * 160) * sizeof(unsigned long long)); m.ts = p.d_march_ts; }
     p.march_ok = plane_only && m.any;
   }
   p.built = cudaGetLastError() == cudaSuccess; return p.built ? 0 : -1;

@@ -192,10 +192,11 @@ struct MarchCommDev {
   double* remote[9][2]; unsigned long long* remote_ready[9];
   const double* local[9][2]; const unsigned long long* local_ready[9];
   unsigned int expected[9];                          // row segments (one per tile row and plane) that make up message d
-  unsigned int* counters;                            // [0..8] segments stored so far, [9] CTAs that finished receiving
+  unsigned int* counters;                            // [0..8] segments stored so far, [9] CTAs that finished receiving, [10] receive items handed out
   unsigned long long* seq;                           // device-resident sequence number, shared with the stand-alone kernels
   int* err;
   double* w;                                         // output vector (the receive part fills its ghost layers)
+  unsigned long long* ts;                            // optional: globaltimer stamps of the tail phases of CTA 0 (diagnostics), else null
 };
 struct HaloPlanP2P {
   bool built = false; int block = 1; int nnb = 0; int grid = 0;
@@ -203,7 +204,7 @@ struct HaloPlanP2P {
   P2PNeighbourDev* d_nb = nullptr; unsigned int* d_counters = nullptr; unsigned long long* d_seq = nullptr; unsigned int* d_done = nullptr;
   std::vector<void*> owned;                          // flat index arrays
   std::vector<P2PNeighbourDev> host_nb; std::vector<int> dir_code;   // host copy, direction code (dx+1) + 3 (dy+1) + 9 (dz+1)
-  bool march_ok = false; MarchCommDev march{}; unsigned int* d_march_counters = nullptr;
+  bool march_ok = false; MarchCommDev march{}; unsigned int* d_march_counters = nullptr; unsigned long long* d_march_ts = nullptr;
 };
 int halo_plan_p2p_build(HaloPlanP2P& p, HaloPlanDG& dg, NcclApi& nccl, void* comm, int rank, int world, const int proc[3], const int pc[3],
                         const int gn[3], const BoxDev& box, int nb, int* d_err, cudaStream_t st);

@@ -27,6 +27,7 @@
 #include <cstdint>
 #include "comm.cuh"
 #include "kron_common.cuh"
+#include "march_schedule.hpp"
 
 namespace b200fem {
 
@@ -46,21 +47,24 @@ template <int N, int TX, int TY> struct KronMarchCfg {
   static constexpr int kU = ((TY + 2) * RS + 15) / 16 * 16;  // doubles per plane stage, 128-byte multiple
   static constexpr int kO = TY * RO;
   static constexpr uint32_t kBytesU = 8u * (TY + 2) * RS, kBytesE = 8u * kO, kBytesB = 8u * kO;
-  static constexpr size_t smem_bytes() { return sizeof(double) * (2 * (size_t)kU + kO + 6 * N * N + 2) + 8 * (4 + kConsumers / 32) + 64 + 128; }
+  static constexpr size_t smem_bytes() { return sizeof(double) * (2 * (size_t)kU + kO + 6 * N * N + 2) + 8 * (4 + kConsumers / 32) + 4 * 9 * (kConsumers / 32) + 32 + 128; }
   static_assert(TX % 2 == 0 && (kO * 8) % 128 == 0, "TMA destinations must stay 128-byte aligned");
 };
 
-// Walks the plane steps of one CTA: plane-tiles t in [t0, t1) of the linearised (column, z) index are split into
-// runs (one column, z in [za, zb)); a run is processed as the steps z = za-1 .. zb (the first and the last step only
-// touch the neighbouring plane's own elements).
+// The work of a launch is a list of RUNS (one column of TX x TY elements, planes z in [za, zb)), built on the host
+// (launch_march.cu: march_schedule) and handed to the CTAs as contiguous slices run_begin[b] .. run_begin[b+1]: a run is
+// processed as the steps z = za-1 .. zb (the first and the last step only touch the neighbouring plane's own elements).
+// The list balances the CTAs with a cost model (planes, run overheads, boundary columns) and, on several ranks, puts the
+// single-plane runs of the rank-interface planes FIRST (flush = 1: their rows are on their way to the neighbours' mailboxes,
+// and their sequence number published, while the rest of the box is still being computed).
 struct MarchCursor {
-  int t, t1, nz, col, za, zb, z; bool valid;
+  const MarchRun* runs; int i, iend, col, za, zb, z, flush; bool valid;
   __device__ __forceinline__ void start_run() {
-    valid = t < t1;
-    if (valid) { col = t / nz; za = t - col * nz; zb = min(nz, za + (t1 - t)); z = za - 1; }
+    valid = i < iend;
+    if (valid) { const int4 r = __ldg(reinterpret_cast<const int4*>(runs + i)); col = r.x; za = r.y; zb = r.z; flush = r.w; z = za - 1; }
   }
-  __device__ __forceinline__ void init(int t0_, int t1_, int nz_) { t = t0_; t1 = t1_; nz = nz_; start_run(); }
-  __device__ __forceinline__ void advance() { if (++z > zb) { t += zb - za; start_run(); } }
+  __device__ __forceinline__ void init(const MarchRun* r, int b, int e) { runs = r; i = b; iend = e; start_run(); }
+  __device__ __forceinline__ void advance() { if (++z > zb) { ++i; start_run(); } }
   __device__ __forceinline__ bool has_prev() const { return z > za; }          // plane z-1 is owned by this run: it completes now
   __device__ __forceinline__ bool edge() const { return z == za - 1 || z == zb; }
 };
@@ -114,7 +118,8 @@ __device__ __forceinline__ void unit_smem(const double* __restrict__ M, const do
 template <int N, bool HIER, int TX, int TY, bool HAS_B, bool CHK>
 __global__ void __launch_bounds__(KronMarchCfg<N, TX, TY>::kThreads, 1)
 dg_kronecker_march_kernel(const __grid_constant__ KronTabDev<N> K, const __grid_constant__ BoxDev box,
-                          const __grid_constant__ KronMarchMaps M, const __grid_constant__ MarchCommDev C, const int tiles_x, const int ncols) {
+                          const __grid_constant__ KronMarchMaps M, const __grid_constant__ MarchCommDev C,
+                          const MarchRun* __restrict__ runs, const int* __restrict__ run_begin, const int tiles_x) {
   using Cfg = KronMarchCfg<N, TX, TY>;
   constexpr int N3 = Cfg::N3, RS = Cfg::RS, RO = Cfg::RO, NN = N * N;
   constexpr int kWarps = Cfg::kConsumers / 32, kRowsPerWarp = 32 / TX, kSlab = kRowsPerWarp * RO;   // doubles per warp slab
@@ -126,13 +131,13 @@ dg_kronecker_march_kernel(const __grid_constant__ KronTabDev<N> K, const __grid_
   double* const Dsm = O + Cfg::kO;                                  // boundary corrections [axis][lo|hi][N*N]
   uint64_t* bars = reinterpret_cast<uint64_t*>(Dsm + 6 * NN + (6 * NN) % 2);
   const uint32_t ufull = ptx::smem_addr(bars), ufree = ptx::smem_addr(bars + 2), wbar0 = ptx::smem_addr(bars + 4);
-  unsigned int* const s_cnt = reinterpret_cast<unsigned int*>(bars + 4 + kWarps);   // [9] row segments this CTA has sent per direction
+  unsigned int* const s_cnt = reinterpret_cast<unsigned int*>(bars + 4 + kWarps);   // [warp][9] row segments sent per direction, not yet accounted
   const int tid = threadIdx.x;
-  if (tid < 16) s_cnt[tid] = 0u;
+  if (tid < 9 * kWarps) s_cnt[tid] = 0u;
 
   const int nz = box.own_hi[2] - box.own_lo[2];
-  const long long total = (long long)ncols * nz;
-  const int t0 = (int)(total * blockIdx.x / gridDim.x), t1 = (int)(total * (blockIdx.x + 1) / gridDim.x);
+  const int t0 = __ldg(run_begin + blockIdx.x), t1 = __ldg(run_begin + blockIdx.x + 1);       // this CTA's slice of the run list (static:
+                                                                                               // read before the dependency wait)
   auto plane_exists = [&](const MarchCursor& c) { const int lz = box.own_lo[2] + c.z; return lz >= 0 && lz < box.n[2]; };
   auto issue_u = [&](const MarchCursor& c, int s) {
     const int x0 = box.own_lo[0] + (c.col % tiles_x) * TX, y0 = box.own_lo[1] + (c.col / tiles_x) * TY, lz = box.own_lo[2] + c.z;
@@ -149,8 +154,8 @@ dg_kronecker_march_kernel(const __grid_constant__ KronTabDev<N> K, const __grid_
     ptx::fence_barrier_init(); ptx::fence_proxy_async();
     // programmatic dependent launch: this CTA may have started while the previous kernel of the stream was still draining;
     // nothing of u / b / w is touched before that kernel has completed (no-op for an ordinary launch)
+    ld.init(runs, t0, t1);                                            // (the run list is static: fetched before the wait)
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    ld.init(t0, t1, nz);
     for (int i = 0; i < 2; ++i) { while (ld.valid && !plane_exists(ld)) ld.advance(); if (ld.valid) { issue_u(ld, i); ld.advance(); } }
   }
   if (tid < 3 * NN) { Dsm[(tid / NN) * 2 * NN + tid % NN] = K.Dlo[tid / NN][tid % NN]; Dsm[(tid / NN) * 2 * NN + NN + tid % NN] = K.Dhi[tid / NN][tid % NN]; }
@@ -164,7 +169,7 @@ dg_kronecker_march_kernel(const __grid_constant__ KronTabDev<N> K, const __grid_
     // to the consumers, which need 3 x n^3 doubles each
     asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
     if (tid != Cfg::kConsumers) return;
-    MarchCursor cur; cur.init(t0, t1, nz);
+    MarchCursor cur; cur.init(runs, t0, t1);
     auto next_load = [&]() { while (ld.valid && !plane_exists(ld)) ld.advance(); };
     int ku = 0;
     for (; cur.valid; cur.advance()) {
@@ -187,16 +192,20 @@ dg_kronecker_march_kernel(const __grid_constant__ KronTabDev<N> K, const __grid_
   const int gz0 = box.origin[2] + box.own_lo[2];
   double A[N3], B[N3];                                               // A: plane z-1 (waits for R_z u(z)),  B: plane z
   int ku = 0, eb = 0;
-  MarchCursor cur; cur.init(t0, t1, nz);
+  MarchCursor cur; cur.init(runs, t0, t1);
   int gcx = 0, gcy = 0, cx = 0, cy = 0;                              // global element coordinates; TMA coordinates of the warp's rows
   bool rows_owned = false, xb = false, yb = false;
   if (lane == 0) { ptx::prefetch_tensormap(&M.w_tile); if (HAS_B) ptx::prefetch_tensormap(&M.b_tile); }
   // fused Copy exchange of w (several ranks, comm.cuh): sequence number of this exchange (device-resident, so that the
   // launch can sit inside a captured graph); read after griddepcontrol.wait, i.e. after the previous exchange has retired
   const unsigned long long seq = C.any ? *C.seq + 1 : 0ull;
+  const bool stamp = C.ts != nullptr && blockIdx.x == 0 && tid == 0;
+  if (stamp) { C.ts[9] = C.ts[7]; C.ts[10] = C.ts[0]; C.ts[8] = gtimer_ns(); }     // (previous launch: end of tail, end of main loop)
+  if (C.ts != nullptr && tid == 0) { C.ts[16 + 4 * blockIdx.x + 2] = C.ts[16 + 4 * blockIdx.x + 3]; C.ts[16 + 4 * blockIdx.x] = gtimer_ns(); }   // per CTA: start, loop end, previous tail end, tail end
   const int on0 = box.own_hi[0] - box.own_lo[0];
   // lane 0: the rows of the completed plane zc (owned coordinates) that lie on a rank interface go straight from the
   // warp's slab into the neighbours' mailboxes (1-D bulk copies over NVLink; 16-byte aligned because on0 and TX are even)
+  int zflush = 0, commits = 0;                                       // (lane 0) steps until the z-interface rows are accounted; store groups committed since
   auto send_rows = [&](const int zc, const int col) {
     const int xoff = (col % tiles_x) * TX;
     const uint32_t bytes = (uint32_t)min(TX, on0 - xoff) * N3 * 8u;
@@ -214,14 +223,36 @@ dg_kronecker_march_kernel(const __grid_constant__ KronTabDev<N> K, const __grid_
           const int d = dyc + 3 * dzc;
           if (!C.enabled[d]) continue;
           const long long zi = dzc == 1 ? zc : 0, yi = dyc == 1 ? yc : 0, ny = dyc == 1 ? on1 : 1;
-          ptx::bulk_s2g(C.remote[d][seq & 1] + ((zi * ny + yi) * on0 + xoff) * N3, slab_a + (uint32_t)(r * RO) * 8u, bytes);
-          atomicAdd(&s_cnt[d], 1u);
+          double* const mbox = C.remote[d][seq & 1];
+          ptx::bulk_s2g(mbox + ((zi * ny + yi) * on0 + xoff) * N3, slab_a + (uint32_t)(r * RO) * 8u, bytes);
+          s_cnt[9 * warp + d] += 1u;
+          if (dzc != 1) zflush = 2;                                  // a z-interface plane is on its way: account it two steps from now
         }
       }
     }
   };
 
+  // lane 0: accounts the row segments this warp has sent so far.  All its bulk stores are complete (wait_group), a gpu-scope
+  // fence orders them before the counter update; whoever completes a message publishes its sequence number with ONE
+  // system-scope release, which is cumulative over everything ordered before it.
+  auto flush_sends = [&](const bool all) {
+    if (all) ptx::bulk_wait_all(); else asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");   // (all but the newest store group)
+    bool any = false;
+    for (int d = 0; d < 9; ++d) any = any || s_cnt[9 * warp + d] != 0u;
+    if (!any) return;
+    __threadfence();
+    for (int d = 0; d < 9; ++d) {
+      const unsigned int c = s_cnt[9 * warp + d];
+      if (!c) continue;
+      s_cnt[9 * warp + d] = 0u;
+      if (atomicAdd(&C.counters[d], c) + c == C.expected[d]) { C.counters[d] = 0; __threadfence(); st_release_sys(C.remote_ready[d] + (seq & 1), seq); }
+    }
+  };
   for (; cur.valid; cur.advance()) {
+    // rows of a z-interface plane were sent two steps ago: by now their bulk stores have (almost always) completed, so the
+    // accounting -- and, for whoever completes the message, the publication of its sequence number -- costs no round trip.
+    // The peers thus hold the interface planes, which the schedule puts first, long before they finish their own box.
+    if (lane == 0 && zflush && --zflush == 0) { flush_sends(commits == 0); }
     if (cur.z == cur.za - 1) {                                       // a new run starts
       const int bx = cur.col % tiles_x, by = cur.col / tiles_x;
       gcx = box.origin[0] + box.own_lo[0] + bx * TX + tx; gcy = box.origin[1] + box.own_lo[1] + by * TY + ty;
@@ -259,7 +290,7 @@ dg_kronecker_march_kernel(const __grid_constant__ KronTabDev<N> K, const __grid_
       for (int t = 0; t < N3; ++t) o[P.p[t]] = HAS_B ? A[t] - o[P.p[t]] : A[t];
       ptx::fence_proxy_async();
       __syncwarp();
-      if (lane == 0 && rows_owned) { ptx::tma_store_4d(&M.w_tile, 0, cx, cy, cur.z - 1, slab_a); if (C.any) send_rows(cur.z - 1, cur.col); ptx::bulk_commit(); }
+      if (lane == 0 && rows_owned) { ptx::tma_store_4d(&M.w_tile, 0, cx, cy, cur.z - 1, slab_a); if (C.any) { commits += 1; send_rows(cur.z - 1, cur.col); if (zflush == 2) commits = 0; } ptx::bulk_commit(); }
     }
     if (!edge) {
 #pragma unroll
@@ -298,45 +329,50 @@ dg_kronecker_march_kernel(const __grid_constant__ KronTabDev<N> K, const __grid_
     for (int t = 0; t < N3; ++t) { A[t] = B[t]; B[t] = 0.0; }
     if (exists && cur.z + 1 < cur.zb) apply_axis<N, 2>(K.L[2], v, B);
   }
+  if (stamp) C.ts[0] = gtimer_ns();
+  if (C.ts != nullptr && tid == 0) C.ts[16 + 4 * blockIdx.x + 1] = gtimer_ns();
   if (lane == 0) ptx::bulk_wait_all();
-  if (!C.any) return;
+  if (stamp) C.ts[1] = gtimer_ns();
+  if (!C.any) { if (stamp) C.ts[7] = gtimer_ns(); if (C.ts != nullptr && tid == 0) C.ts[16 + 4 * blockIdx.x + 3] = gtimer_ns(); return; }
 
   // ============================== fused Copy exchange: publish, receive, retire ==============================
-  // (1) all bulk stores of this warp (local and remote) have completed; order them before the flags at system scope
-  if (lane == 0) __threadfence_system();
-  asm volatile("bar.sync 1, %0;" ::"n"(Cfg::kConsumers) : "memory");
-  if (tid == 0) {
-    for (int d = 0; d < 9; ++d) {
-      const unsigned int c = s_cnt[d];
-      if (!c) continue;
-      __threadfence();
-      if (atomicAdd(&C.counters[d], c) + c == C.expected[d]) {        // the message is complete: publish its sequence number
-        C.counters[d] = 0; __threadfence_system(); st_release_sys(C.remote_ready[d] + (seq & 1), seq);
-      }
-    }
-  }
+  // (1) the rest of this warp's row segments (no CTA-wide barrier: warps account on their own)
+  if (lane == 0) flush_sends(true);
+  if (stamp) C.ts[2] = gtimer_ns();
+  if (stamp) C.ts[3] = gtimer_ns();
+  if (stamp) C.ts[4] = gtimer_ns();
   // (2) receive: the row segments of the incoming messages are dealt to all consumer warps of the (fully resident)
   // grid; a warp waits for the flag of a message the first time it needs it.  Peers publish from their own compute
   // kernels, which never wait for anything of this exchange: no cycle.
   {
+    constexpr int kSplit = 4;                                          // a row segment is copied out of the mailbox by kSplit warps
     const int on2 = nz, n0 = box.n[0], n1 = box.n[1];
     const long long gwarp = (long long)blockIdx.x * kWarps + warp, nwarps = (long long)gridDim.x * kWarps;
     long long first[10]; first[0] = 0;
 #pragma unroll
-    for (int d = 0; d < 9; ++d) first[d + 1] = first[d] + (C.enabled[d] ? (long long)tiles_x * (d % 3 == 1 ? on1 : 1) * (d / 3 == 1 ? on2 : 1) : 0);
+    for (int d = 0; d < 9; ++d) first[d + 1] = first[d] + (C.enabled[d] ? (long long)kSplit * tiles_x * (d % 3 == 1 ? on1 : 1) * (d / 3 == 1 ? on2 : 1) : 0);
     unsigned int seen = 0;
-    for (long long it = gwarp; it < first[9]; it += nwarps) {
+    (void)gwarp; (void)nwarps;
+    // items are handed out dynamically: CTAs that finish early (the schedule lets those with rank-interface rows finish first)
+    // do the receiving, the CTAs on the critical path find nothing left
+    while (true) {
+      long long it = 0;
+      if (lane == 0) it = (long long)atomicAdd(&C.counters[10], 1u);
+      it = __shfl_sync(0xffffffffu, it, 0);
+      if (it >= first[9]) break;
       int d = 0;
 #pragma unroll
       for (int k = 1; k < 9; ++k) if (it >= first[k]) d = k;
       const int dyc = d % 3, dzc = d / 3, ny = dyc == 1 ? on1 : 1;
-      const long long q = it - first[d]; const int seg = (int)(q % tiles_x); const long long row = q / tiles_x;
+      const long long q0 = it - first[d]; const int part = (int)(q0 % kSplit); const long long q = q0 / kSplit;
+      const int seg = (int)(q % tiles_x); const long long row = q / tiles_x;
       const int yi = (int)(row % ny), zi = (int)(row / ny);
       if (!((seen >> d) & 1u)) {
         int ok = 1;
         if (lane == 0) ok = wait_flag_ge(C.local_ready[d] + (seq & 1), seq, C.err, kCommTimeoutFused) ? 1 : 0;
         ok = __shfl_sync(0xffffffffu, ok, 0);
         if (!ok) break;
+        if (stamp && !seen) C.ts[5] = gtimer_ns();
         seen |= 1u << d;
       }
       const int gy = dyc == 1 ? box.own_lo[1] + yi : (dyc == 0 ? box.own_lo[1] - 1 : box.own_hi[1]);
@@ -344,12 +380,16 @@ dg_kronecker_march_kernel(const __grid_constant__ KronTabDev<N> K, const __grid_
       const int xoff = seg * TX, cnt2 = min(TX, on0 - xoff) * N3 / 2;                 // double2 items of this segment
       const double2* src = reinterpret_cast<const double2*>(C.local[d][seq & 1] + (row * on0 + xoff) * N3);
       double2* dst = reinterpret_cast<double2*>(C.w + (((long long)gz * n1 + gy) * n0 + box.own_lo[0] + xoff) * N3);
-      for (int i = lane; i < cnt2; i += 32) dst[i] = __ldcg(src + i);
+      const int per = (cnt2 + kSplit - 1) / kSplit, i1 = min(cnt2, (part + 1) * per);
+      for (int i = part * per + lane; i < i1; i += 32) dst[i] = __ldcg(src + i);
     }
   }
   // (3) the CTA that finishes last advances the sequence number (the next exchange on this stream reads it)
+  if (stamp) C.ts[6] = gtimer_ns();
   asm volatile("bar.sync 1, %0;" ::"n"(Cfg::kConsumers) : "memory");
-  if (tid == 0) { __threadfence(); if (atomicAdd(&C.counters[9], 1u) == gridDim.x - 1) { C.counters[9] = 0; *C.seq = seq; } }
+  if (stamp) C.ts[7] = gtimer_ns();
+  if (C.ts != nullptr && tid == 0) C.ts[16 + 4 * blockIdx.x + 3] = gtimer_ns();
+  if (tid == 0) { __threadfence(); if (atomicAdd(&C.counters[9], 1u) == gridDim.x - 1) { C.counters[9] = 0; C.counters[10] = 0; *C.seq = seq; } }
 }
 
 }  // namespace b200fem

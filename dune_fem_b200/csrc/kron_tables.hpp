@@ -96,4 +96,40 @@ inline LagRowsHost build_lagrange_rows(const Tab1D& t, const b200fem_model& m, i
   return r;
 }
 
+
+// The same operators in the two-row-type form of lagrange_lattice.cuh: an assembled row depends only on the node type (element
+// vertex: contributions of the element to the left, local node k, and to the right, local node 0; element-interior node,
+// k = 2: one element) -- except on the first / last lattice plane of the local box, where one element contribution is missing.
+// Nodes outside the box read as zero, so those rows are the interior row plus a correction of the diagonal entry:
+//   lo: -Xe[k][k] (no left element),  hi: -Xe[0][0] (no right element),  T additionally + the boundary term on masked DOMAIN sides.
+// Offsets -k..k sit in slots 0..2k.  Axes >= dim: M = identity (centre 1), T = 0.
+struct LagStencilHost { int k = 0; double M[3][2][5] = {}, T[3][2][5] = {}, Mlo[3] = {}, Mhi[3] = {}, Tlo[3] = {}, Thi[3] = {}; };
+
+inline LagStencilHost build_lagrange_stencil(const Tab1D& t, const b200fem_model& m, int dim, int order, const int* n, const int* origin, const int* gn, const double* h) {
+  LagStencilHost r; const int k = order, nb = k + 1; r.k = k;
+  for (int d = 0; d < 3; ++d) {
+    if (d >= dim) { r.M[d][0][k] = 1.0; r.M[d][1][k] = 1.0; continue; }
+    std::vector<double> Me(nb * nb, 0.0), Te(nb * nb, 0.0);
+    for (int q = 0; q < t.m; ++q) for (int i = 0; i < nb; ++i) for (int j = 0; j < nb; ++j) {
+      const double mm = h[d] * t.w[q] * t.B[q * nb + i] * t.B[q * nb + j];
+      Me[i * nb + j] += mm;
+      Te[i * nb + j] += m.eps / h[d] * t.w[q] * t.G[q * nb + i] * t.G[q * nb + j] - m.b[d] * t.w[q] * t.G[q * nb + i] * t.B[q * nb + j];
+      if (d == 0) Te[i * nb + j] += m.c * mm;
+    }
+    for (int j = 0; j < nb; ++j) {               // vertex row: left element (test node k) on offsets -k..0, right element (test node 0) on 0..k
+      r.M[d][0][j] += Me[k * nb + j]; r.T[d][0][j] += Te[k * nb + j];
+      r.M[d][0][k + j] += Me[0 * nb + j]; r.T[d][0][k + j] += Te[0 * nb + j];
+    }
+    if (k == 2) for (int j = 0; j < nb; ++j) { r.M[d][1][1 + j] = Me[1 * nb + j]; r.T[d][1][1 + j] = Te[1 * nb + j]; }   // interior node: offsets -1..1
+    r.Mlo[d] = -Me[k * nb + k]; r.Mhi[d] = -Me[0]; r.Tlo[d] = -Te[k * nb + k]; r.Thi[d] = -Te[0];
+    if (m.has_boundary) for (int side = 0; side < 2; ++side) {
+      const bool domain_bnd = side == 0 ? origin[d] == 0 : origin[d] + n[d] == gn[d];
+      if (!domain_bnd || !((m.dirichlet_mask >> (2 * d + side)) & 1)) continue;
+      const double bn = m.b[d] * (side ? 1.0 : -1.0), hatb = 0.5 * (bn + std::fabs(bn));
+      (side ? r.Thi[d] : r.Tlo[d]) += m.eps * m.beta / h[d] + hatb;
+    }
+  }
+  return r;
+}
+
 }  // namespace b200fem

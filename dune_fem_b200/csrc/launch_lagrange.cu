@@ -9,6 +9,7 @@
 #include "internal.hpp"
 #include "kron_tables.hpp"
 #include "lagrange_kronecker.cuh"
+#include "lagrange_lattice.cuh"
 #include "lagrange_quadrature.cuh"
 
 using namespace b200fem;
@@ -67,17 +68,15 @@ static int ensure_lag_rows(b200fem_operator* op) {
   return B200FEM_OK;
 }
 
-// Lagrange Kronecker (sum-factorised lattice stencil) kernel
-int launch_lagrange_kronecker(b200fem_operator* op, const double* u, double* w, const double* bvec) {
+// first-generation lattice kernel (one node per thread, per-row coefficient tables): kept selectable through
+// B200FEM_KERNEL_KRONECKER_TILE for A/B checks of the second generation
+static int launch_lagrange_kronecker_v1(b200fem_operator* op, const double* u, double* w, const double* bvec) {
   b200fem_space* s = op->sp; const int k = s->order; b200fem_ctx* ctx = s->mesh->ctx;
-  REQUIRE(s->lay.lattice[0] * s->lay.lattice[1] * s->lay.lattice[2] < (1ll << 31) && s->size < (1ll << 31), B200FEM_ERR_NOT_IMPLEMENTED, "lattice kernel: 32-bit dof cursors");
   int rc = ensure_lag_rows(op); if (rc) return rc;
   const LagrangeLayoutDev& L = s->lay; const bool mapped = L.lattice_map != nullptr;
   constexpr int HY = 16, ctas_per_sm = 2;
   const int TX = 32 - 2 * k, TY = HY - 2 * k;
   const int tx = (int)((L.lattice[0] + TX - 1) / TX), ty = (int)((L.lattice[1] + TY - 1) / TY);
-  // z-segments: every segment re-reads 2k planes and stages its z-rows (<= kMaxSeg planes); the number of segments is chosen
-  // so that the grid fills whole waves of the resident CTA slots
   const int L2 = (int)L.lattice[2], slots = ctas_per_sm * ctx->sms, tiles = tx * ty;
   int best_nseg = 1; double best_cost = 1e300;
   for (int ns = 1; ns <= 64; ++ns) {
@@ -90,7 +89,6 @@ int launch_lagrange_kronecker(b200fem_operator* op, const double* u, double* w, 
   const int zseg = (L2 + best_nseg - 1) / best_nseg, nseg = (L2 + zseg - 1) / zseg;
   const unsigned grid = (unsigned)(tiles * nseg); cudaStream_t st = ctx->stream;
   const unsigned char* dmask = op->fuse_dirichlet ? op->d_dmask : nullptr; const double* dvals = op->fuse_dirichlet && !op->fuse_linear ? op->d_dvals : nullptr;
-  // fused <u, w> partials (requested by the CG driver on one rank, where every dof is primary and the Dirichlet rows are fused too)
   double* dotp = nullptr; op->dot_parts = 0;
   if (op->want_dot && op->fuse_dirichlet == (op->model.strong_dirichlet && op->d_dmask != nullptr) && ctx->world == 1) {
     if ((int)grid > op->dot_cap) { if (op->capturing) return fail(B200FEM_ERR_INVALID, "dot partial buffer must exist before graph capture"); if (op->d_dot_partial) cudaFree(op->d_dot_partial); CUDA_OK(cudaMalloc(&op->d_dot_partial, sizeof(double) * grid)); op->dot_cap = (int)grid; }
@@ -104,6 +102,65 @@ int launch_lagrange_kronecker(b200fem_operator* op, const double* u, double* w, 
   CUDA_OK(cudaGetLastError());
   op->timing.launches_per_apply = 1;
   return B200FEM_OK;
+}
+
+// second-generation lattice kernel (lagrange_lattice.cuh): four nodes per thread, two row types in the constant bank
+template <int K, int LX, bool MAPPED>
+static int launch_lattice(b200fem_operator* op, const LagStencilDev<K>& S, const double* u, double* w, const double* bvec, const double* dvals) {
+  using Cfg = LagLatCfg<K, LX>;
+  b200fem_space* s = op->sp; b200fem_ctx* ctx = s->mesh->ctx; const LagrangeLayoutDev& L = s->lay;
+  const int tx = (int)((L.lattice[0] + Cfg::TXO - 1) / Cfg::TXO), ty = (int)((L.lattice[1] + Cfg::TYO - 1) / Cfg::TYO), tiles = tx * ty;
+  // z-segments: every segment re-reads 2k planes; the number of segments is chosen so that the grid fills whole waves of the
+  // resident CTA slots (one CTA per SM)
+  const int L2 = (int)L.lattice[2], slots = ctx->sms;
+  int best_nseg = 1; double best_cost = 1e300;
+  for (int ns = 1; ns <= 64 && ns <= L2; ++ns) {
+    const int zs = (L2 + ns - 1) / ns, nse = (L2 + zs - 1) / zs;
+    const double waves = std::ceil((double)tiles * nse / slots), cost = waves * (zs + 2 * K + 4);
+    if (cost < best_cost) { best_cost = cost; best_nseg = nse; }
+  }
+  const int zseg = (L2 + best_nseg - 1) / best_nseg, nseg = (L2 + zseg - 1) / zseg;
+  const unsigned grid = (unsigned)(tiles * nseg);
+  double* dotp = nullptr; op->dot_parts = 0;
+  if (op->want_dot && op->fuse_dirichlet == (op->model.strong_dirichlet && op->d_dmask != nullptr) && ctx->world == 1) {
+    if ((int)grid > op->dot_cap) { if (op->capturing) return fail(B200FEM_ERR_INVALID, "dot partial buffer must exist before graph capture"); if (op->d_dot_partial) cudaFree(op->d_dot_partial); CUDA_OK(cudaMalloc(&op->d_dot_partial, sizeof(double) * grid)); op->dot_cap = (int)grid; }
+    dotp = op->d_dot_partial; op->dot_parts = (int)grid;
+  }
+  auto kern = lagrange_lattice_kernel<K, LX, MAPPED>;
+  int rc = ensure_smem_attr(ctx, (const void*)kern, Cfg::smem_bytes()); if (rc) return rc;
+  kern<<<grid, Cfg::kThreads, Cfg::smem_bytes(), ctx->stream>>>(L, S, u, w, bvec, dvals, tx, ty, zseg, dotp);
+  CUDA_OK(cudaGetLastError());
+  return B200FEM_OK;
+}
+template <int K> static int launch_lattice_k(b200fem_operator* op, const double* u, double* w, const double* bvec) {
+  b200fem_space* s = op->sp; const BoxDev& b = s->box; const LagrangeLayoutDev& L = s->lay;
+  const LagStencilHost h = build_lagrange_stencil(s->tab, op->model, b.dim, K, b.n, b.origin, b.gn, b.h);
+  LagStencilDev<K> S; std::memset(&S, 0, sizeof(S));
+  for (int d = 0; d < 3; ++d) {
+    for (int ty = 0; ty < 2; ++ty) for (int t = 0; t < 2 * K + 1; ++t) { S.M[d][ty][t] = h.M[d][ty][t]; S.T[d][ty][t] = h.T[d][ty][t]; }
+    S.Mlo[d] = h.Mlo[d]; S.Mhi[d] = h.Mhi[d]; S.Tlo[d] = h.Tlo[d]; S.Thi[d] = h.Thi[d];
+    S.glo[d] = d < b.dim ? K * b.origin[d] : 0; S.gend[d] = d < b.dim ? K * b.gn[d] : 0;
+  }
+  S.dirichlet_bits = op->fuse_dirichlet ? (op->model.dirichlet_mask & ((1 << (2 * b.dim)) - 1)) : 0;
+  S.affine = op->fuse_dirichlet && !op->fuse_linear ? 1 : 0;
+  const double* dvals = S.affine ? op->d_dvals : nullptr;
+  const bool mapped = L.lattice_map != nullptr;
+  // tile width: 4 LX nodes per row, 512 / LX rows; the width with the fewest node-planes (padding of the last tiles included)
+  auto cost = [&](int lx) { const long long nx = 4 * lx, hy = 512 / lx, txo = nx - 2 * K, tyo = hy - 2 * K; return ((L.lattice[0] + txo - 1) / txo) * ((L.lattice[1] + tyo - 1) / tyo) * nx * hy; };
+  const bool wide = cost(32) < cost(16);
+  int rc;
+  if (wide) rc = mapped ? launch_lattice<K, 32, true>(op, S, u, w, bvec, dvals) : launch_lattice<K, 32, false>(op, S, u, w, bvec, dvals);
+  else      rc = mapped ? launch_lattice<K, 16, true>(op, S, u, w, bvec, dvals) : launch_lattice<K, 16, false>(op, S, u, w, bvec, dvals);
+  if (rc) return rc;
+  op->dirichlet_fused = op->fuse_dirichlet;
+  op->timing.launches_per_apply = 1;
+  return B200FEM_OK;
+}
+int launch_lagrange_kronecker(b200fem_operator* op, const double* u, double* w, const double* bvec) {
+  b200fem_space* s = op->sp;
+  REQUIRE(s->lay.lattice[0] * s->lay.lattice[1] * s->lay.lattice[2] < (1ll << 31) && s->size < (1ll << 31), B200FEM_ERR_NOT_IMPLEMENTED, "lattice kernel: 32-bit dof cursors");
+  if (op->kernel_pref == B200FEM_KERNEL_KRONECKER_TILE) return launch_lagrange_kronecker_v1(op, u, w, bvec);
+  return s->order == 1 ? launch_lattice_k<1>(op, u, w, bvec) : launch_lattice_k<2>(op, u, w, bvec);
 }
 
 // Launch-bound sizes on a 2-D Lagrange lattice (BASELINE config 1): a chunk of CG iterations is ONE cooperative launch with

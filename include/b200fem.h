@@ -97,6 +97,12 @@ int b200fem_mesh_destroy(b200fem_mesh* mesh);
  * balancer lives in dune-grid and is not restated; the process grid is explicit instead). */
 int b200fem_partition_box(int dim, const int32_t* n_global, const int32_t* proc, int rank, int overlap, int32_t* out12);
 int b200fem_mesh_local_box(b200fem_mesh* mesh, int overlap, int32_t* out12);
+/* Host logic, no device needed: the static work schedule of the z-marching DG Q2 kernel for an owned box of on[0..2] elements on
+ * `grid` CTAs.  flags: bit 0 / 1 = a rank interface below / above in z (their planes become single-plane runs that go first and are
+ * flushed to the neighbour at once), bits 2..5 = the box touches the domain boundary at x-low, x-high, y-low, y-high, bits 6 / 7 = a rank interface
+ * below / above in y (cost model).
+ * runs_out (may be NULL; cap = runs that fit) receives (column, za, zb, flush) per run, begin_out[0..grid] the slice of each CTA. */
+int b200fem_march_schedule(const int32_t* on, int grid, int flags, int32_t* runs_out, int32_t cap, int32_t* begin_out, int32_t* nruns_out);
 
 /* DiscreteFunctionSpace (space/lagrange/space.hh:129-353, space/discontinuousgalerkin/legendre.hh) */
 int b200fem_space_create(b200fem_mesh* mesh, int kind, int order, int numbering, b200fem_space** out);

@@ -22,4 +22,4 @@ for f in ("bench_short", "bench_long"):
     except Exception as ex:
         print(f, "unreadable:", ex)
 PY
-tail -3 gpurun_out/bench_short.err gpurun_out/bench_long.err
+tail -n 3 gpurun_out/bench_short.err; tail -n 3 gpurun_out/bench_long.err
