@@ -25,7 +25,7 @@
 //    global box: dirichletconstraints.hh:435-554 in closed form) -- no mask bytes travel with u.
 //
 // Kernel: a CTA owns a tile of lattice columns and marches through z.
-//   z-pass  every thread keeps the 2k+1 z-neighbours of its four columns in a register ring (unrolled ring-fold, no moves):
+//   z-pass  every thread keeps the 2k+1 z-neighbours of its four columns in registers (a window shifted once per plane):
 //           a = M_z u,  b = T_z u                                   (no shared memory, u is read once per column)
 //   y-pass  c = M_y a,  s = T_y a + M_y b     neighbours' (a, b) out of shared memory, 16-byte accesses
 //   x-pass  w = T_x c + M_x s                 neighbours' (c, s) by warp shuffles
@@ -55,23 +55,22 @@ template <int K> struct LagStencilDev {
   int affine;                              // 1: constrained rows store u - g (g from dvals), 0: they store u (homogeneous part)
 };
 
-template <int K, int LX> struct LagLatCfg {
-  static constexpr int W = 2 * K + 1, R = 4, kWarps = 16, kThreads = 32 * kWarps;
+template <int K, int LX, int WARPS = 16> struct LagLatCfg {
+  static constexpr int W = 2 * K + 1, R = 4, kWarps = WARPS, kThreads = 32 * kWarps, kCtasPerSm = 16 / WARPS;
   static constexpr int RPW = 32 / LX;                        // tile rows per warp
   static constexpr int HY = kWarps * RPW, NX = R * LX;       // tile extents incl. halo (rows, nodes per row)
   static constexpr int TXO = NX - 2 * K, TYO = HY - 2 * K;   // nodes a tile produces
-  static constexpr int PF = 1, NW = W + PF;                  // prefetch distance in planes, ring slots
   static constexpr size_t smem_bytes() { return sizeof(double) * 2 * (size_t)HY * 2 * NX; }
   static_assert(32 % LX == 0 && TXO % 2 == 0 && TYO % 2 == 0, "tiles start on even lattice coordinates: node types are fixed per register slot / warp");
 };
 
-template <int K, int LX, bool MAPPED>
-__global__ void __launch_bounds__(LagLatCfg<K, LX>::kThreads, 1)
+template <int K, int LX, bool MAPPED, int WARPS>
+__global__ void __launch_bounds__(LagLatCfg<K, LX, WARPS>::kThreads, LagLatCfg<K, LX, WARPS>::kCtasPerSm)
 lagrange_lattice_kernel(const __grid_constant__ LagrangeLayoutDev L, const __grid_constant__ LagStencilDev<K> S,
                         const double* __restrict__ u, double* __restrict__ w, const double* __restrict__ bvec, const double* __restrict__ dvals,
                         const int tiles_x, const int tiles_y, const int zseg, double* __restrict__ dot_partial) {
-  using Cfg = LagLatCfg<K, LX>;
-  constexpr int W = Cfg::W, R = Cfg::R, HY = Cfg::HY, NX = Cfg::NX, NW = Cfg::NW;
+  using Cfg = LagLatCfg<K, LX, WARPS>;
+  constexpr int W = Cfg::W, R = Cfg::R, HY = Cfg::HY, NX = Cfg::NX;
   extern __shared__ __align__(16) unsigned char lat_smem[];
   double* const AB = reinterpret_cast<double*>(lat_smem);      // [buffer][row][field][NX]
   auto plane_ptr = [&](int buf, int row, int field) { return AB + (((size_t)buf * HY + row) * 2 + field) * NX; };
@@ -106,43 +105,54 @@ lagrange_lattice_kernel(const __grid_constant__ LagrangeLayoutDev L, const __gri
 
   // dof addresses.  Closed-form YaspGrid numbering: 8 parity classes (k = 2), each a dense array; the thread's nodes 0, 2 (even x)
   // are neighbours in one class, nodes 1, 3 (odd x) in another: dof = base[class] + stride[class] * (gz >> 1) (+1 for the second
-  // node).  k = 1: one class, four consecutive dofs.  Adaptive-leaf numbering: lattice -> dof table.
-  int baseE[2] = {0, 0}, baseO[2] = {0, 0}, strE[2] = {0, 0}, strO[2] = {0, 0};
-  if (!MAPPED) {
-    if (K == 2) {
-      const int xe = gx0 >> 1;                                          // (gx0 is even; arithmetic shift keeps -1 for the left halo pair)
-#pragma unroll
-      for (int pz = 0; pz < 2; ++pz) {
-        const int s0 = ((gy & 1) << 1) | (pz << 2), s1 = s0 | 1;
-        baseE[pz] = (int)(L.group_offset[s0] + xe + L.group_dims[s0][0] * (long long)(gy >> 1)); strE[pz] = (int)(L.group_dims[s0][0] * L.group_dims[s0][1]);
-        baseO[pz] = (int)(L.group_offset[s1] + xe + L.group_dims[s1][0] * (long long)(gy >> 1)); strO[pz] = (int)(L.group_dims[s1][0] * L.group_dims[s1][1]);
-      }
+  // node).  k = 1: one class, four consecutive dofs.  Adaptive-leaf numbering: lattice -> dof table.  Addresses are not
+  // recomputed per plane: the load stream and the store stream each keep a CURSOR for the plane they touch next and one for the
+  // plane after it (the other z-parity class); a cursor is advanced by its class stride after use and the two swap roles.
+  struct LatCursor { int e, o, se, so; };
+  auto make_cursor = [&](const int gz) -> LatCursor {
+    LatCursor c;
+    if (MAPPED) { c.e = gx0 + L0 * (gy + L1 * gz); c.o = 0; c.se = 2 * L0 * L1; c.so = 0; }
+    else if (K == 2) {
+      const int xe = gx0 >> 1, pz = gz & 1;                             // (gx0 is even; arithmetic shifts keep the halo consistent)
+      const int s0 = ((gy & 1) << 1) | (pz << 2), s1 = s0 | 1;
+      c.se = (int)(L.group_dims[s0][0] * L.group_dims[s0][1]); c.so = (int)(L.group_dims[s1][0] * L.group_dims[s1][1]);
+      c.e = (int)(L.group_offset[s0] + xe + L.group_dims[s0][0] * (long long)(gy >> 1)) + c.se * (gz >> 1);
+      c.o = (int)(L.group_offset[s1] + xe + L.group_dims[s1][0] * (long long)(gy >> 1)) + c.so * (gz >> 1);
     } else {
-      baseE[0] = baseE[1] = (int)(L.group_offset[0] + gx0 + L.group_dims[0][0] * (long long)gy);
-      strE[0] = strE[1] = (int)(L.group_dims[0][0] * L.group_dims[0][1]);
+      const int st = (int)(L.group_dims[0][0] * L.group_dims[0][1]);
+      c.e = (int)(L.group_offset[0] + gx0 + L.group_dims[0][0] * (long long)gy) + st * gz; c.o = 0; c.se = 2 * st; c.so = 0;
     }
-  }
-  // dof of node j on lattice plane gz (only meaningful where the node exists)
-  auto dof_of = [&](const int j, const int gz) -> int {
-    if (MAPPED) return (int)L.lattice_map[(gx0 + j) + (long long)L0 * (gy + (long long)L1 * gz)];
-    if (K == 2) { const int pz = gz & 1, h = gz >> 1; return (j & 1) ? baseO[pz] + strO[pz] * h + (j >> 1) : baseE[pz] + strE[pz] * h + (j >> 1); }
-    return baseE[0] + strE[0] * gz + j;
+    return c;
   };
+  auto node_dof = [&](const LatCursor& c, const int j) -> int {
+    if (MAPPED) return (int)L.lattice_map[c.e + j];
+    return K == 2 ? ((j & 1) ? c.o : c.e) + (j >> 1) : c.e + j;
+  };
+  auto advance = [&](LatCursor& a, LatCursor& b) { a.e += a.se; a.o += a.so; const LatCursor t = a; a = b; b = t; };
+  LatCursor ld_a = make_cursor(z0 - K), ld_b = make_cursor(z0 - K + 1);   // load stream: planes z0-K, z0-K+1, ...
+  LatCursor st_a = make_cursor(z0), st_b = make_cursor(z0 + 1);           // store stream: planes z0, z0+1, ...
 
-  // Register RING of z-neighbours: slot (p - (z0 - K)) mod NW holds u(., ., p) for the W planes of the current window and the
-  // plane that is prefetched ahead.  The march is unrolled NW-fold so that every slot index is a compile-time constant.
-  double ring[R][NW];
-  auto load_plane = [&](auto slot_c, const int gz) {
-    constexpr int slot = decltype(slot_c)::value;
+  // z-neighbours of the thread's four columns in registers: win[j][t] = u(., ., z - K + t), t = 0 .. 2K, for the plane z whose
+  // z-pass comes next, plus the plane after the window, which is loaded one whole plane step ahead of its use (nxt).  The window
+  // is shifted by register moves once per plane (the march loop is NOT unrolled: the first generation's ring-fold unrolling
+  // made 190 KB of code; the moves are 8 per node against ~70 other instructions).
+  double win[R][W], nxt[R];
+  auto load_plane = [&](const int gz, double (&dst)[R]) {          // (planes are requested in ascending order, one per call)
     const bool zok = (unsigned)gz < (unsigned)L2;
 #pragma unroll
-    for (int j = 0; j < R; ++j) ring[j][slot] = (zok && ((xin >> j) & 1u)) ? u[dof_of(j, gz)] : 0.0;
+    for (int j = 0; j < R; ++j) dst[j] = (zok && ((xin >> j) & 1u)) ? u[node_dof(ld_a, j)] : 0.0;
+    advance(ld_a, ld_b);
   };
-  lat_static_for<NW>([&](auto i) { load_plane(i, z0 - K + decltype(i)::value); });
+#pragma unroll
+  for (int t = 0; t < W; ++t) {
+    double tmp[R]; load_plane(z0 - K + t, tmp);
+#pragma unroll
+    for (int j = 0; j < R; ++j) win[j][t] = tmp[j];
+  }
+  load_plane(z0 + K + 1, nxt);
 
-  // z-pass of plane zc (ring phase r = (zc - z0) mod NW) into buffer nb; afterwards slot r is dead and takes plane zc - K + NW
-  auto z_pass = [&](auto rc, const int zc, const int nb) {
-    constexpr int r = decltype(rc)::value;
+  // z-pass of plane zc (the window is centred on it) into buffer nb
+  auto z_pass = [&](const int zc, const int nb) {
     double a[R], b[R];
     const int tz = K == 2 ? (zc & 1) : 0;
 #pragma unroll
@@ -152,35 +162,34 @@ lagrange_lattice_kernel(const __grid_constant__ LagrangeLayoutDev L, const __gri
       for (int t = 1; t < W - 1; ++t) {
         const double cm = S.M[2][1][t], ct = S.T[2][1][t];
 #pragma unroll
-        for (int j = 0; j < R; ++j) { const double v = ring[j][(r + t) % NW]; a[j] = fma(cm, v, a[j]); b[j] = fma(ct, v, b[j]); }
+        for (int j = 0; j < R; ++j) { a[j] = fma(cm, win[j][t], a[j]); b[j] = fma(ct, win[j][t], b[j]); }
       }
     } else {
 #pragma unroll
       for (int t = 0; t < W; ++t) {
         const double cm = S.M[2][0][t], ct = S.T[2][0][t];
 #pragma unroll
-        for (int j = 0; j < R; ++j) { const double v = ring[j][(r + t) % NW]; a[j] = fma(cm, v, a[j]); b[j] = fma(ct, v, b[j]); }
+        for (int j = 0; j < R; ++j) { a[j] = fma(cm, win[j][t], a[j]); b[j] = fma(ct, win[j][t], b[j]); }
       }
     }
     if (zc == 0 || zc == L2 - 1) {                                       // first / last plane of the box: diagonal corrections
       const double cm = (zc == 0 ? S.Mlo[2] : 0.0) + (zc == L2 - 1 ? S.Mhi[2] : 0.0), ct = (zc == 0 ? S.Tlo[2] : 0.0) + (zc == L2 - 1 ? S.Thi[2] : 0.0);
 #pragma unroll
-      for (int j = 0; j < R; ++j) { const double v = ring[j][(r + K) % NW]; a[j] = fma(cm, v, a[j]); b[j] = fma(ct, v, b[j]); }
+      for (int j = 0; j < R; ++j) { a[j] = fma(cm, win[j][K], a[j]); b[j] = fma(ct, win[j][K], b[j]); }
     }
     double* pa = plane_ptr(nb, row, 0) + R * lx; double* pb = plane_ptr(nb, row, 1) + R * lx;
     *reinterpret_cast<double2*>(pa) = make_double2(a[0], a[1]); *reinterpret_cast<double2*>(pa + 2) = make_double2(a[2], a[3]);
     *reinterpret_cast<double2*>(pb) = make_double2(b[0], b[1]); *reinterpret_cast<double2*>(pb + 2) = make_double2(b[2], b[3]);
-    load_plane(rc, zc - K + NW);
   };
-  z_pass(std::integral_constant<int, 0>{}, z0, 0);
+  z_pass(z0, 0);
   __syncthreads();
 
   const bool y_owned = row >= K && row < HY - K && gy < L1;              // (gy >= 0 follows from row >= K)
   const unsigned ymask = __ballot_sync(0xffffffffu, y_owned);            // lanes that take part in the x-pass shuffles (whole tile rows)
   const bool ylo = gy == 0, yhi = gy == L1 - 1;
   double dacc = 0.0;                                                     // <u, w> over the nodes this thread stores (CG: <p, A p> without a second sweep)
-  auto step = [&](auto rc, const int z) {
-    constexpr int r = decltype(rc)::value;
+#pragma unroll 1
+  for (int z = z0; z < z1; ++z) {
     const int cb = (z - z0) & 1;
     // operands of the store, requested now, used at the end of the step
     double uc[R], bq[R], dq[R]; int g[R];                                 // (dof indices fit 32 bits: checked by the launcher)
@@ -188,15 +197,25 @@ lagrange_lattice_kernel(const __grid_constant__ LagrangeLayoutDev L, const __gri
     const bool zdir = (gzg == 0 && (db & 16)) || (gzg == S.gend[2] && (db & 32));
     const unsigned cons = zdir ? 0xfu : xdir;                            // constrained nodes of this thread on this plane
 #pragma unroll
-    for (int j = 0; j < R; ++j) {
-      uc[j] = ring[j][(r + K) % NW]; bq[j] = 0.0; dq[j] = 0.0; g[j] = 0;
-      if ((xout >> j) & 1u) {
-        g[j] = dof_of(j, z);
-        if (bvec) bq[j] = bvec[g[j]];
-        if (((cons >> j) & 1u) && S.affine) dq[j] = dvals[g[j]];
-      }
+    for (int j = 0; j < R; ++j) {                                        // (straight-line, predicated: no divergent blocks)
+      const bool out = (xout >> j) & 1u;
+      uc[j] = win[j][K]; g[j] = out ? node_dof(st_a, j) : 0;
+      bq[j] = (out && bvec != nullptr) ? bvec[g[j]] : 0.0;
+      dq[j] = (out && ((cons >> j) & 1u) && S.affine) ? dvals[g[j]] : 0.0;
     }
-    if (z + 1 < z1) z_pass(std::integral_constant<int, (r + 1) % NW>{}, z + 1, cb ^ 1);
+    advance(st_a, st_b);
+    if (z + 1 < z1) {
+      // shift the window to plane z+1 (the plane that enters was requested a whole step ago), request the plane after it,
+      // and do the z-pass of plane z+1 into the other buffer
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+#pragma unroll
+        for (int t = 0; t < W - 1; ++t) win[j][t] = win[j][t + 1];
+        win[j][W - 1] = nxt[j];
+      }
+      load_plane(z + K + 2, nxt);
+      z_pass(z + 1, cb ^ 1);
+    }
     if (y_owned) {
       // ---- y-pass: own row from shared memory too (the registers of the z-pass are long gone), neighbours by 16-byte loads
       double c[R], s[R];
@@ -240,15 +259,13 @@ lagrange_lattice_kernel(const __grid_constant__ LagrangeLayoutDev L, const __gri
           r0 = fma((gx == 0 ? S.Tlo[0] : 0.0) + (gx == L0 - 1 ? S.Thi[0] : 0.0), c[j], r0);
           r1 = fma((gx == 0 ? S.Mlo[0] : 0.0) + (gx == L0 - 1 ? S.Mhi[0] : 0.0), s[j], r1);
         }
-        if ((xout >> j) & 1u) {
-          const double val = ((cons >> j) & 1u) ? uc[j] - dq[j] : (r0 + r1) - bq[j];
-          w[g[j]] = val; dacc = fma(uc[j], val, dacc);
-        }
+        const double val = ((cons >> j) & 1u) ? uc[j] - dq[j] : (r0 + r1) - bq[j];
+        if ((xout >> j) & 1u) w[g[j]] = val;
+        dacc = fma(((xout >> j) & 1u) ? uc[j] : 0.0, val, dacc);
       }
     }
     __syncthreads();
-  };
-  for (int zb = z0; zb < z1; zb += NW) lat_static_for<NW>([&](auto rc) { const int z = zb + decltype(rc)::value; if (z < z1) step(rc, z); });
+  }
   // optional fused scalar product <u, w>: one partial per CTA, summed in block order by cg_alpha_partials_kernel -- deterministic
   if (dot_partial) { const double t = block_sum(dacc); if (tid == 0) dot_partial[blockIdx.x] = t; }
 }

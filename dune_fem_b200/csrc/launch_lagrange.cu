@@ -3,6 +3,7 @@
 // cooperative CG kernel for launch-bound 2-D problems (cg_coop2d.cuh)
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "cg_coop2d.cuh"
 #include "integrands.cuh"
@@ -105,14 +106,14 @@ static int launch_lagrange_kronecker_v1(b200fem_operator* op, const double* u, d
 }
 
 // second-generation lattice kernel (lagrange_lattice.cuh): four nodes per thread, two row types in the constant bank
-template <int K, int LX, bool MAPPED>
+template <int K, int LX, bool MAPPED, int WARPS = 16>
 static int launch_lattice(b200fem_operator* op, const LagStencilDev<K>& S, const double* u, double* w, const double* bvec, const double* dvals) {
-  using Cfg = LagLatCfg<K, LX>;
+  using Cfg = LagLatCfg<K, LX, WARPS>;
   b200fem_space* s = op->sp; b200fem_ctx* ctx = s->mesh->ctx; const LagrangeLayoutDev& L = s->lay;
   const int tx = (int)((L.lattice[0] + Cfg::TXO - 1) / Cfg::TXO), ty = (int)((L.lattice[1] + Cfg::TYO - 1) / Cfg::TYO), tiles = tx * ty;
   // z-segments: every segment re-reads 2k planes; the number of segments is chosen so that the grid fills whole waves of the
   // resident CTA slots (one CTA per SM)
-  const int L2 = (int)L.lattice[2], slots = ctx->sms;
+  const int L2 = (int)L.lattice[2], slots = ctx->sms * Cfg::kCtasPerSm;
   int best_nseg = 1; double best_cost = 1e300;
   for (int ns = 1; ns <= 64 && ns <= L2; ++ns) {
     const int zs = (L2 + ns - 1) / ns, nse = (L2 + zs - 1) / zs;
@@ -126,7 +127,7 @@ static int launch_lattice(b200fem_operator* op, const LagStencilDev<K>& S, const
     if ((int)grid > op->dot_cap) { if (op->capturing) return fail(B200FEM_ERR_INVALID, "dot partial buffer must exist before graph capture"); if (op->d_dot_partial) cudaFree(op->d_dot_partial); CUDA_OK(cudaMalloc(&op->d_dot_partial, sizeof(double) * grid)); op->dot_cap = (int)grid; }
     dotp = op->d_dot_partial; op->dot_parts = (int)grid;
   }
-  auto kern = lagrange_lattice_kernel<K, LX, MAPPED>;
+  auto kern = lagrange_lattice_kernel<K, LX, MAPPED, WARPS>;
   int rc = ensure_smem_attr(ctx, (const void*)kern, Cfg::smem_bytes()); if (rc) return rc;
   kern<<<grid, Cfg::kThreads, Cfg::smem_bytes(), ctx->stream>>>(L, S, u, w, bvec, dvals, tx, ty, zseg, dotp);
   CUDA_OK(cudaGetLastError());
@@ -145,12 +146,10 @@ template <int K> static int launch_lattice_k(b200fem_operator* op, const double*
   S.affine = op->fuse_dirichlet && !op->fuse_linear ? 1 : 0;
   const double* dvals = S.affine ? op->d_dvals : nullptr;
   const bool mapped = L.lattice_map != nullptr;
-  // tile width: 4 LX nodes per row, 512 / LX rows; the width with the fewest node-planes (padding of the last tiles included)
-  auto cost = [&](int lx) { const long long nx = 4 * lx, hy = 512 / lx, txo = nx - 2 * K, tyo = hy - 2 * K; return ((L.lattice[0] + txo - 1) / txo) * ((L.lattice[1] + tyo - 1) / tyo) * nx * hy; };
-  const bool wide = cost(32) < cost(16);
-  int rc;
-  if (wide) rc = mapped ? launch_lattice<K, 32, true>(op, S, u, w, bvec, dvals) : launch_lattice<K, 32, false>(op, S, u, w, bvec, dvals);
-  else      rc = mapped ? launch_lattice<K, 16, true>(op, S, u, w, bvec, dvals) : launch_lattice<K, 16, false>(op, S, u, w, bvec, dvals);
+  // tile: 64 nodes wide (16 lanes x 4 nodes), 16 rows (8 warps x 2 rows), two CTAs per SM.  Measured on P2 128^3 (profiles/
+  // r02_lagrange_lattice.md): 259 us against 295 us for 16-warp CTAs with 32 rows -- the smaller CTAs run out of phase (one
+  // CTA's shared-memory phase under the other's FMA phase), which outweighs their larger halo share
+  int rc = mapped ? launch_lattice<K, 16, true, 8>(op, S, u, w, bvec, dvals) : launch_lattice<K, 16, false, 8>(op, S, u, w, bvec, dvals);
   if (rc) return rc;
   op->dirichlet_fused = op->fuse_dirichlet;
   op->timing.launches_per_apply = 1;
