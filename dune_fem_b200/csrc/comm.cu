@@ -293,6 +293,7 @@ void halo_plan_p2p_free(HaloPlanP2P& p) {
                  (long long)(h[1] - h[0]), (long long)(h[2] - h[0]), (long long)(h[5] - h[0]), (long long)(h[6] - h[0]), (long long)(h[0] - h[8]), (long long)(h[8] - h[9]));
     unsigned long long s0 = ~0ull, s1 = 0, e0 = ~0ull, e1 = 0, p1 = 0, t1 = 0; int n = 0;
     for (int b = 0; b < 160; ++b) { const unsigned long long st = h[16 + 4 * b], en = h[16 + 4 * b + 1], pe = h[16 + 4 * b + 2], te = h[16 + 4 * b + 3]; if (!st) continue; ++n; s0 = std::min(s0, st); s1 = std::max(s1, st); e0 = std::min(e0, en); e1 = std::max(e1, en); p1 = std::max(p1, pe); t1 = std::max(t1, te); }
+    if (std::getenv("B200FEM_MARCH_TS_DUMP")) for (int b = 0; b < 160; ++b) { const unsigned long long st = h[16 + 4 * b], en = h[16 + 4 * b + 1], te = h[16 + 4 * b + 3]; if (st) std::fprintf(stderr, "rank %d cta %d start %lld loop %lld tail %lld\n", p.region.rank, b, (long long)(st - s0), (long long)(en - st), (long long)(te - en)); }
     std::fprintf(stderr, "[b200fem march tail, ns] %d CTAs: starts spread %lld | loop ends spread %lld | first start -> last loop end %lld | last loop end -> last tail end %lld | previous launch's last TAIL end -> first start %lld\n",
                  n, (long long)(s1 - s0), (long long)(e1 - e0), (long long)(e1 - s0), (long long)(t1 - e1), (long long)(s0 - p1));
   }
@@ -356,7 +357,7 @@ int halo_plan_p2p_build(HaloPlanP2P& p, HaloPlanDG& dg, NcclApi& nccl, void* com
   {
     MarchCommDev& m = p.march; std::memset(&m, 0, sizeof(m));
     bool plane_only = proc[0] == 1;
-    cudaMalloc(&p.d_march_counters, sizeof(unsigned int) * 12); cudaMemset(p.d_march_counters, 0, sizeof(unsigned int) * 12);
+    cudaMalloc(&p.d_march_counters, sizeof(unsigned int) * 20); cudaMemset(p.d_march_counters, 0, sizeof(unsigned int) * 20);
     const int on[3] = {box.own_hi[0] - box.own_lo[0], box.own_hi[1] - box.own_lo[1], box.own_hi[2] - box.own_lo[2]};
     const unsigned tiles_x = (unsigned)((on[0] + 15) / 16);
     for (int i = 0; i < p.nnb; ++i) {

@@ -192,7 +192,7 @@ struct MarchCommDev {
   double* remote[9][2]; unsigned long long* remote_ready[9];
   const double* local[9][2]; const unsigned long long* local_ready[9];
   unsigned int expected[9];                          // row segments (one per tile row and plane) that make up message d
-  unsigned int* counters;                            // [0..8] segments stored so far, [9] CTAs that finished receiving, [10] receive items handed out
+  unsigned int* counters;                            // [0..8] segments stored so far, [9] CTAs that finished receiving, [10+d] receive items of message d handed out
   unsigned long long* seq;                           // device-resident sequence number, shared with the stand-alone kernels
   int* err;
   double* w;                                         // output vector (the receive part fills its ghost layers)

@@ -245,7 +245,9 @@ dg_kronecker_march_kernel(const __grid_constant__ KronTabDev<N> K, const __grid_
       const unsigned int c = s_cnt[9 * warp + d];
       if (!c) continue;
       s_cnt[9 * warp + d] = 0u;
-      if (atomicAdd(&C.counters[d], c) + c == C.expected[d]) { C.counters[d] = 0; __threadfence(); st_release_sys(C.remote_ready[d] + (seq & 1), seq); }
+      if (atomicAdd(&C.counters[d], c) + c == C.expected[d]) {
+        C.counters[d] = 0; __threadfence(); st_release_sys(C.remote_ready[d] + (seq & 1), seq);
+      }
     }
   };
   for (; cur.valid; cur.advance()) {
@@ -345,43 +347,49 @@ dg_kronecker_march_kernel(const __grid_constant__ KronTabDev<N> K, const __grid_
   // grid; a warp waits for the flag of a message the first time it needs it.  Peers publish from their own compute
   // kernels, which never wait for anything of this exchange: no cycle.
   {
-    constexpr int kSplit = 4;                                          // a row segment is copied out of the mailbox by kSplit warps
+    constexpr int kSplit = 1;                                          // an item is one row segment (TX elements), all its loads in flight at once
     const int on2 = nz, n0 = box.n[0], n1 = box.n[1];
-    const long long gwarp = (long long)blockIdx.x * kWarps + warp, nwarps = (long long)gridDim.x * kWarps;
-    long long first[10]; first[0] = 0;
-#pragma unroll
-    for (int d = 0; d < 9; ++d) first[d + 1] = first[d] + (C.enabled[d] ? (long long)kSplit * tiles_x * (d % 3 == 1 ? on1 : 1) * (d / 3 == 1 ? on2 : 1) : 0);
-    unsigned int seen = 0;
-    (void)gwarp; (void)nwarps;
-    // items are handed out dynamically: CTAs that finish early (the schedule lets those with rank-interface rows finish first)
-    // do the receiving, the CTAs on the critical path find nothing left
-    while (true) {
-      long long it = 0;
-      if (lane == 0) it = (long long)atomicAdd(&C.counters[10], 1u);
-      it = __shfl_sync(0xffffffffu, it, 0);
-      if (it >= first[9]) break;
-      int d = 0;
-#pragma unroll
-      for (int k = 1; k < 9; ++k) if (it >= first[k]) d = k;
-      const int dyc = d % 3, dzc = d / 3, ny = dyc == 1 ? on1 : 1;
-      const long long q0 = it - first[d]; const int part = (int)(q0 % kSplit); const long long q = q0 / kSplit;
-      const int seg = (int)(q % tiles_x); const long long row = q / tiles_x;
-      const int yi = (int)(row % ny), zi = (int)(row / ny);
-      if (!((seen >> d) & 1u)) {
-        int ok = 1;
-        if (lane == 0) ok = wait_flag_ge(C.local_ready[d] + (seq & 1), seq, C.err, kCommTimeoutFused) ? 1 : 0;
+    // Items (quarter row segments) are handed out dynamically, per message: CTAs that finish early (the schedule lets those
+    // with rank-interface rows finish first) do the receiving, the CTAs on the critical path find nothing left.  First pass:
+    // only messages whose sequence number has already arrived (the z-interface planes, published early in the peers' kernels);
+    // second pass: wait for the rest.  Peers publish from their own compute kernels, which never wait for anything of this
+    // exchange: no cycle.
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int d = 0; d < 9; ++d) {
+        if (!C.enabled[d]) continue;
+        const int dyc = d % 3, dzc = d / 3, ny = dyc == 1 ? on1 : 1;
+        const long long nitems = (long long)kSplit * tiles_x * ny * (dzc == 1 ? on2 : 1);
+        int ok = 0;
+        if (lane == 0) {
+          if (*reinterpret_cast<volatile unsigned int*>(&C.counters[10 + d]) >= nitems) ok = 2;          // nothing left of this message
+          else if (pass == 0) ok = ld_acquire_sys(C.local_ready[d] + (seq & 1)) >= seq ? 1 : 0;
+          else ok = wait_flag_ge(C.local_ready[d] + (seq & 1), seq, C.err, kCommTimeoutFused) ? 1 : 2;
+        }
         ok = __shfl_sync(0xffffffffu, ok, 0);
-        if (!ok) break;
-        if (stamp && !seen) C.ts[5] = gtimer_ns();
-        seen |= 1u << d;
+        if (ok != 1) continue;
+        if (stamp && C.ts[5] < C.ts[8]) C.ts[5] = gtimer_ns();
+        while (true) {
+          long long it = 0;
+          if (lane == 0) it = (long long)atomicAdd(&C.counters[10 + d], 1u);
+          it = __shfl_sync(0xffffffffu, it, 0);
+          if (it >= nitems) break;
+          const int part = (int)(it % kSplit); const long long q = it / kSplit;
+          const int seg = (int)(q % tiles_x); const long long row = q / tiles_x;
+          const int yi = (int)(row % ny), zi = (int)(row / ny);
+          const int gy = dyc == 1 ? box.own_lo[1] + yi : (dyc == 0 ? box.own_lo[1] - 1 : box.own_hi[1]);
+          const int gz = dzc == 1 ? box.own_lo[2] + zi : (dzc == 0 ? box.own_lo[2] - 1 : box.own_hi[2]);
+          const int xoff = seg * TX, cnt2 = min(TX, on0 - xoff) * N3 / 2;                 // double2 items of this segment
+          const double2* src = reinterpret_cast<const double2*>(C.local[d][seq & 1] + (row * on0 + xoff) * N3);
+          double2* dst = reinterpret_cast<double2*>(C.w + (((long long)gz * n1 + gy) * n0 + box.own_lo[0] + xoff) * N3);
+          (void)part;
+          constexpr int kPer = (TX * N3 / 2 + 31) / 32;                                    // double2 per lane
+          double2 v[kPer];
+#pragma unroll
+          for (int k = 0; k < kPer; ++k) { const int i = lane + 32 * k; v[k] = i < cnt2 ? __ldcg(src + i) : make_double2(0.0, 0.0); }
+#pragma unroll
+          for (int k = 0; k < kPer; ++k) { const int i = lane + 32 * k; if (i < cnt2) dst[i] = v[k]; }
+        }
       }
-      const int gy = dyc == 1 ? box.own_lo[1] + yi : (dyc == 0 ? box.own_lo[1] - 1 : box.own_hi[1]);
-      const int gz = dzc == 1 ? box.own_lo[2] + zi : (dzc == 0 ? box.own_lo[2] - 1 : box.own_hi[2]);
-      const int xoff = seg * TX, cnt2 = min(TX, on0 - xoff) * N3 / 2;                 // double2 items of this segment
-      const double2* src = reinterpret_cast<const double2*>(C.local[d][seq & 1] + (row * on0 + xoff) * N3);
-      double2* dst = reinterpret_cast<double2*>(C.w + (((long long)gz * n1 + gy) * n0 + box.own_lo[0] + xoff) * N3);
-      const int per = (cnt2 + kSplit - 1) / kSplit, i1 = min(cnt2, (part + 1) * per);
-      for (int i = part * per + lane; i < i1; i += 32) dst[i] = __ldcg(src + i);
     }
   }
   // (3) the CTA that finishes last advances the sequence number (the next exchange on this stream reads it)
@@ -389,7 +397,7 @@ dg_kronecker_march_kernel(const __grid_constant__ KronTabDev<N> K, const __grid_
   asm volatile("bar.sync 1, %0;" ::"n"(Cfg::kConsumers) : "memory");
   if (stamp) C.ts[7] = gtimer_ns();
   if (C.ts != nullptr && tid == 0) C.ts[16 + 4 * blockIdx.x + 3] = gtimer_ns();
-  if (tid == 0) { __threadfence(); if (atomicAdd(&C.counters[9], 1u) == gridDim.x - 1) { C.counters[9] = 0; C.counters[10] = 0; *C.seq = seq; } }
+  if (tid == 0) { __threadfence(); if (atomicAdd(&C.counters[9], 1u) == gridDim.x - 1) { C.counters[9] = 0; for (int d = 0; d < 9; ++d) C.counters[10 + d] = 0; *C.seq = seq; } }
 }
 
 }  // namespace b200fem

@@ -23,7 +23,7 @@ inline void march_schedule(const MarchScheduleKey& k, int tx, int ty, std::vecto
   auto plane_cost = [&](int col) { const int bx = col % tx, by = col / tx; double c = 1.0;
     if ((bx == 0 && k.gx_lo) || (bx == tx - 1 && k.gx_hi)) c += 0.10;
     if ((by == 0 && k.gy_lo) || (by == ty - 1 && k.gy_hi)) c += 0.03;
-    if ((by == 0 && k.ify_lo) || (by == ty - 1 && k.ify_hi)) c += 0.20;     // rows for a y-neighbour: these CTAs are to finish early
+    if ((by == 0 && k.ify_lo) || (by == ty - 1 && k.ify_hi)) c += 0.35;     // rows for a y-neighbour: these CTAs are to finish early
     return c; };
   constexpr double kRun = 0.8, kFlush = 1.0;
   std::vector<std::vector<MarchRun>> mine((size_t)grid);
