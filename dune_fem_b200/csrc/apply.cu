@@ -40,22 +40,27 @@ int apply_local(b200fem_operator* op, const double* u, double* w, bool linear) {
     op->timing.kernel = B200FEM_KERNEL_QUADRATURE;
     return B200FEM_OK;
   }
-  REQUIRE(default_quadrature(op), B200FEM_ERR_NOT_IMPLEMENTED, "only quadrature orders that select the (order+1)-point Gauss rule are implemented on the device");
-  const bool kron_ok = op->model.gamma == 0.0 && N >= 2 && N <= 6 && s->box.dim == 3;
+  // The Kronecker form rests on the default rules (the (k+1)-point Gauss rules integrate the 1-D mass matrices of the
+  // orthonormal basis exactly); other quadrature orders (setQuadratureOrders) go through the generic quadrature kernel
+  const bool kron_ok = op->model.gamma == 0.0 && N >= 2 && N <= 6 && s->box.dim == 3 && default_quadrature(op);
   int kernel = op->kernel_pref;
   if (kernel == B200FEM_KERNEL_AUTO) kernel = kron_ok ? B200FEM_KERNEL_KRONECKER : B200FEM_KERNEL_QUADRATURE;
   int rc;
+  // the data terms (sources, boundary values) do not depend on u: L[u] = N(u) - l with l = -L[0] evaluated once
+  // (python/dune/fem/operator/__init__.py:347-350), so every apply runs the homogeneous integrands and subtracts the stored
+  // load vector instead of evaluating the analytic data at every quadrature point again
+  const double* bvec = nullptr;
+  if (!linear && op->model.data && !op->in_bvec) { rc = ensure_bvec(op); if (rc) return rc; bvec = op->d_bvec; }
   if (kernel == B200FEM_KERNEL_KRONECKER || kernel == B200FEM_KERNEL_KRONECKER_TILE) {
-    REQUIRE(kron_ok, B200FEM_ERR_INVALID, "Kronecker kernel needs a linear model");
-    const double* bvec = nullptr;
-    if (!linear && op->model.data) { rc = ensure_bvec(op); if (rc) return rc; bvec = op->d_bvec; }
+    REQUIRE(op->model.gamma == 0.0, B200FEM_ERR_INVALID, "Kronecker kernel needs a linear model");
+    REQUIRE(kron_ok, B200FEM_ERR_NOT_IMPLEMENTED, "Kronecker kernel: 3-D DG spaces of order 1..5 with the default quadrature orders");
     // marching kernel for Q2, slab kernel for Q3..Q5, tile kernel for Q1 and for Q2 boxes / vectors the TMA views cannot take
     if (N >= 4) rc = launch_dg_slab(op, u, w, bvec);
     else if (kernel == B200FEM_KERNEL_KRONECKER && dg_march_ok(op, u, w, bvec)) rc = launch_dg_march(op, u, w, bvec, op->want_exchange);
     else rc = launch_dg_kronecker_v1(op, u, w, bvec);
     kernel = B200FEM_KERNEL_KRONECKER;
   } else {
-    rc = launch_dg_quadrature_any(op, u, w, !linear);
+    rc = launch_dg_quadrature_any(op, u, w, bvec, op->in_bvec);
   }
   if (rc) return rc;
   op->timing.kernel = kernel;
@@ -72,9 +77,9 @@ int ensure_bvec(b200fem_operator* op) {
   CUDA_OK(cudaMemsetAsync(zero_u, 0, bytes, st)); CUDA_OK(cudaMemsetAsync(bv, 0, bytes, st));
   const int saved = op->kernel_pref; const bool want = op->want_exchange; const BoxDev* ab = op->active_box;
   op->kernel_pref = B200FEM_KERNEL_QUADRATURE; op->want_exchange = false; op->active_box = nullptr;
-  const bool fd = op->fuse_dirichlet; op->fuse_dirichlet = false;
+  const bool fd = op->fuse_dirichlet; op->fuse_dirichlet = false; op->in_bvec = true;
   int rc = apply_local(op, zero_u, bv, /*linear=*/false);
-  op->kernel_pref = saved; op->want_exchange = want; op->active_box = ab; op->fuse_dirichlet = fd;
+  op->kernel_pref = saved; op->want_exchange = want; op->active_box = ab; op->fuse_dirichlet = fd; op->in_bvec = false;
   if (rc) { cudaFree(zero_u); cudaFree(bv); return rc; }
   rc = negate_dev(bv, s->size, st);
   if (rc) { cudaFree(zero_u); cudaFree(bv); return rc; }

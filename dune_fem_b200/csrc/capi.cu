@@ -86,7 +86,7 @@ static int make_mesh(b200fem_ctx* ctx, int dim, const int32_t* n, const double* 
     const int glo = m->olo[d] > 0 ? 1 : 0, ghi = m->ohi[d] < m->gn[d] ? 1 : 0;      // overlap 1 where a neighbour rank exists
     b.origin[d] = m->olo[d] - glo; b.n[d] = (m->ohi[d] - m->olo[d]) + glo + ghi;
     b.own_lo[d] = glo; b.own_hi[d] = glo + (m->ohi[d] - m->olo[d]);
-    b.gn[d] = m->gn[d]; b.lo[d] = m->lo[d]; b.h[d] = m->h[d];
+    b.gn[d] = m->gn[d]; b.lo[d] = m->lo[d]; b.h[d] = m->h[d]; b.ih[d] = 1.0 / m->h[d];
   }
   ctx->refs += 1;
   *out = m; return B200FEM_OK;
@@ -340,7 +340,11 @@ extern "C" int b200fem_operator_load_vector(b200fem_operator* op, double* b_host
 extern "C" int b200fem_operator_set_communicate(b200fem_operator* op, int c) { REQUIRE(op, B200FEM_ERR_INVALID, "null"); if (op->communicate != (c != 0)) { op->communicate = c != 0; invalidate_cached_state(op); } return B200FEM_OK; }
 extern "C" int b200fem_operator_set_quadrature_orders(b200fem_operator* op, unsigned qi, unsigned qs) {
   REQUIRE(op, B200FEM_ERR_INVALID, "null");
-  if (op->q_interior != qi || op->q_surface != qs) { op->q_interior = qi; op->q_surface = qs; invalidate_cached_state(op); }
+  if (op->q_interior != qi || op->q_surface != qs) {
+    op->q_interior = qi; op->q_surface = qs; invalidate_cached_state(op);
+    // the load vector was integrated with the old rules
+    if (op->d_bvec) { CUDA_OK(cudaSetDevice(op->sp->mesh->ctx->device)); CUDA_OK(cudaStreamSynchronize(op->sp->mesh->ctx->stream)); CUDA_OK(cudaFree(op->d_bvec)); op->d_bvec = nullptr; }
+  }
   return B200FEM_OK;
 }
 extern "C" int b200fem_operator_set_kernel(b200fem_operator* op, int k) {

@@ -78,6 +78,7 @@ struct b200fem_operator {
   double* d_lag_rows = nullptr; b200fem::LagKronRows lag_rows{}; std::vector<unsigned char> kron_tab; MarchMapCache* march_cache = nullptr;
   b200fem::HaloPlan halo; b200fem::HaloPlanDG halo_dg; b200fem::HaloPlanP2P halo_p2p; b200fem::HaloPlanAddP2P halo_add;
   const b200fem::BoxDev* active_box = nullptr;   // sub-box override (host-pointer pipeline)
+  bool in_bvec = false;                         // the load vector is being computed (data terms on, no recursion into ensure_bvec)
   bool want_exchange = false;                   // apply_dev_impl -> launcher: the Copy exchange of w is due after this apply
   bool exchange_fused = false;                  // launcher -> apply_dev_impl: the kernel did the exchange itself
   int host_pipeline_chunks = 8;                 // host-pointer apply of DG spaces: z-slabs of the copy/compute pipeline (< 2: off)
@@ -106,7 +107,7 @@ int launch_dg_march(b200fem_operator* op, const double* u, double* w, const doub
 bool dg_march_ok(const b200fem_operator* op, const double* u, const double* w, const double* bvec);
 int launch_dg_slab(b200fem_operator* op, const double* u, double* w, const double* bvec);                        // Q3..Q5
 int launch_dg_kronecker_v1(b200fem_operator* op, const double* u, double* w, const double* bvec);                // Q1, Q2 fallback
-int launch_dg_quadrature_any(b200fem_operator* op, const double* u, double* w, bool with_data);                 // Q1..Q5 generic
+int launch_dg_quadrature_any(b200fem_operator* op, const double* u, double* w, const double* bvec, bool with_data);   // Q1..Q5 generic
 int launch_lagrange_quadrature(b200fem_operator* op, const double* u, double* w, bool with_data);
 int launch_lagrange_kronecker(b200fem_operator* op, const double* u, double* w, const double* bvec);
 void free_march_cache(b200fem_operator* op);

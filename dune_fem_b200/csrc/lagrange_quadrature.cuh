@@ -16,6 +16,14 @@
 
 namespace b200fem {
 
+// 1-D tables of the (k+1)-point rule for the register-only 2-D kernel
+template <int N>
+struct DgTabDev {
+  double B[N * N], G[N * N];     // B[q*N+i] = phi_i(x_q), G = phi_i'(x_q)   (volume and face rules coincide)
+  double x[N], w[N];             // Gauss points / weights on [0,1]
+  double phi[2][N], dphi[2][N];  // traces at 0 and 1
+};
+
 struct LagrangeLayoutDev {
   int order;                        // 1 or 2
   long long group_offset[8];        // per "shift" bit set (directions the sub-entity extends in)
@@ -33,20 +41,20 @@ __host__ __device__ inline long long lagrange_dof(const LagrangeLayoutDev& L, co
 
 // ------------------------------------------------------------------ 3-D: N*N threads per element, shared-memory tensors
 template <int N, class Integrands>
-__global__ void __launch_bounds__(DgQuadCfg<N>::kThreads)
-lagrange3d_quadrature_kernel(const __grid_constant__ DgTabDev<N> T, const __grid_constant__ BoxDev box,
+__global__ void __launch_bounds__(DgQuadCfg<N, N, N>::kThreads)
+lagrange3d_quadrature_kernel(const __grid_constant__ QuadTabDev<N, N, N> T, const __grid_constant__ BoxDev box,
                              const __grid_constant__ Integrands I, const __grid_constant__ LagrangeLayoutDev L,
                              const double* __restrict__ u, double* __restrict__ w,
                              int c0, int c1, int c2, int m0, int m1, long long n_colour) {
-  using Cfg = DgQuadCfg<N>;
-  constexpr int N2 = Cfg::N2, N3 = Cfg::N3, EB = Cfg::EB, ELEM = Cfg::kElemDoubles;
+  using Cfg = DgQuadCfg<N, N, N>;
+  constexpr int N2 = N * N, N3 = N * N * N, EB = Cfg::EB, ELEM = Cfg::kElemDoubles, LN = Cfg::LN;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* smem = reinterpret_cast<double*>(smem_raw);
   int* ecs = reinterpret_cast<int*>(smem + (size_t)EB * ELEM);       // 4 ints per slot: coords + active flag
 
-  const int tid = threadIdx.x, es = tid / N2, lt = tid % N2;
+  const int tid = threadIdx.x, es = tid / Cfg::T2, lt = tid % Cfg::T2;
   const long long oe = (long long)blockIdx.x * EB + es;
-  const bool active = oe < n_colour;
+  const bool active = es < EB && oe < n_colour;
   int lc[3] = {0, 0, 0};
   if (active) {
     lc[0] = box.own_lo[0] + 2 * (int)(oe % m0) + c0;
@@ -54,25 +62,25 @@ lagrange3d_quadrature_kernel(const __grid_constant__ DgTabDev<N> T, const __grid
     lc[2] = box.own_lo[2] + 2 * (int)(oe / ((long long)m0 * m1)) + c2;
   }
   const long long e = lc[0] + (long long)box.n[0] * (lc[1] + (long long)box.n[1] * lc[2]);
-  if (lt == 0) { ecs[4 * es] = lc[0]; ecs[4 * es + 1] = lc[1]; ecs[4 * es + 2] = lc[2]; ecs[4 * es + 3] = active; }
+  if (lt == 0 && es < EB) { ecs[4 * es] = lc[0]; ecs[4 * es + 1] = lc[1]; ecs[4 * es + 2] = lc[2]; ecs[4 * es + 3] = active; }
   __syncthreads();
   const int k = N - 1;
   for (int idx = tid; idx < EB * N3; idx += blockDim.x) {            // gather (getLocalDofs)
     const int s2 = idx / N3, t = idx % N3;
     if (ecs[4 * s2 + 3]) {
       const int i0 = t / N2, i1 = (t / N) % N, i2 = t % N;
-      smem[(size_t)s2 * ELEM + t] = u[lagrange_dof(L, (long long)k * ecs[4 * s2] + i0, (long long)k * ecs[4 * s2 + 1] + i1, (long long)k * ecs[4 * s2 + 2] + i2)];
+      smem[(size_t)s2 * ELEM + (i0 * N + i1) * LN + i2] = u[lagrange_dof(L, (long long)k * ecs[4 * s2] + i0, (long long)k * ecs[4 * s2 + 1] + i1, (long long)k * ecs[4 * s2 + 2] + i2)];
     }
   }
   __syncthreads();
-  double* U = smem + (size_t)es * ELEM;
-  element_integrals<N, Integrands>(T, box, I, nullptr, u, active, lc, e, lt, U, U + N3, U + 2 * N3);
+  double* U = smem + (size_t)(es < EB ? es : 0) * ELEM;
+  element_integrals<N, N, N, Integrands>(T, box, I, nullptr, u, active, lc, e, lt, U, U + Cfg::kU, U + 2 * Cfg::kU);
   for (int idx = tid; idx < EB * N3; idx += blockDim.x) {            // coloured scatter-add (addLocalDofs)
     const int s2 = idx / N3, t = idx % N3;
     if (ecs[4 * s2 + 3]) {
       const int i0 = t / N2, i1 = (t / N) % N, i2 = t % N;
       const long long g = lagrange_dof(L, (long long)k * ecs[4 * s2] + i0, (long long)k * ecs[4 * s2 + 1] + i1, (long long)k * ecs[4 * s2 + 2] + i2);
-      w[g] += smem[(size_t)s2 * ELEM + N3 + t];
+      w[g] += smem[(size_t)s2 * ELEM + Cfg::kU + (i0 * N + i1) * LN + i2];
     }
   }
 }
@@ -160,7 +168,7 @@ lagrange2d_quadrature_kernel(const __grid_constant__ DgTabDev<N> T, const __grid
         pv.du[d] = dn / hh[d]; pv.du[a] = dt / hh[a];
         double xq[3] = {0, 0, 0};
         xq[d] = box.lo[d] + hh[d] * (gc + s); xq[a] = box.lo[a] + hh[a] * ((box.origin[a] + lc[a]) + T.x[q]);
-        PointRange r = I.boundary(d, s, hh[d], xq, pv);
+        PointRange r = I.boundary(d, s, 1.0 / hh[d], xq, pv);
         const double wq = T.w[q] * area;
 #pragma unroll
         for (int ia = 0; ia < N; ++ia) {

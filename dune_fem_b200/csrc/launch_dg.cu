@@ -1,43 +1,24 @@
 // launch_dg.cu -- host side of the generic DG quadrature kernel (dg_quadrature.cuh) and of the tile Kronecker kernel
 // (dg_kronecker.cuh: Q1, and Q2 boxes the marching kernel cannot take)
 #include "dg_kronecker.cuh"
-#include "dg_quadrature.cuh"
-#include "integrands.cuh"
-#include "internal.hpp"
+#include "launch_dgq.hpp"
 #include "kron_tables.hpp"
 
 using namespace b200fem;
 
 namespace b200fem {
 
-template <int N> static DgTabDev<N> make_tab(const Tab1D& t) {
-  DgTabDev<N> T;
-  for (int i = 0; i < N * N; ++i) { T.B[i] = t.B[i]; T.G[i] = t.G[i]; }
-  for (int i = 0; i < N; ++i) { T.x[i] = t.x[i]; T.w[i] = t.w[i]; T.phi[0][i] = t.phi0[i]; T.phi[1][i] = t.phi1[i]; T.dphi[0][i] = t.dphi0[i]; T.dphi[1][i] = t.dphi1[i]; }
-  return T;
-}
-
-template <int N> static int launch_dg_quadrature(b200fem_operator* op, const double* u, double* w, bool with_data) {
-  using Cfg = DgQuadCfg<N>; const BoxDev& b = op->active_box ? *op->active_box : op->sp->box;
-  b200fem_ctx* ctx = op->sp->mesh->ctx;
-  const long long n_owned = (long long)(b.own_hi[0] - b.own_lo[0]) * (b.own_hi[1] - b.own_lo[1]) * (b.own_hi[2] - b.own_lo[2]);
-  auto kern = dg_quadrature_kernel<N, AdrIntegrands>;
-  int rc = ensure_smem_attr(ctx, (const void*)kern, Cfg::smem_bytes()); if (rc) return rc;
-  AdrIntegrands I; I.m = op->model; I.dim = b.dim; I.with_data = with_data;
-  const unsigned grid = (unsigned)((n_owned + Cfg::EB - 1) / Cfg::EB);
-  kern<<<grid, Cfg::kThreads, Cfg::smem_bytes(), ctx->stream>>>(make_tab<N>(op->sp->tab), b, I, op->d_perm, u, w, nullptr, n_owned, mass_scale(op));
-  CUDA_OK(cudaGetLastError());
-  op->timing.launches_per_apply = 1;
-  return B200FEM_OK;
-}
-int launch_dg_quadrature_any(b200fem_operator* op, const double* u, double* w, bool with_data) {
-  switch (op->sp->n1) {
-    case 2: return launch_dg_quadrature<2>(op, u, w, with_data);
-    case 3: return launch_dg_quadrature<3>(op, u, w, with_data);
-    case 4: return launch_dg_quadrature<4>(op, u, w, with_data);
-    case 5: return launch_dg_quadrature<5>(op, u, w, with_data);
-    case 6: return launch_dg_quadrature<6>(op, u, w, with_data);
-  }
+// generic quadrature kernel: the Gauss rules follow the operator's quadrature orders (galerkin.hh:131-132, 1418-1423; rule =
+// smallest Gauss rule of at least the requested order, femquadratures_inline.hh:59-70)
+int launch_dg_quadrature_any(b200fem_operator* op, const double* u, double* w, const double* bvec, bool with_data) {
+  const int k = op->sp->order, N = op->sp->n1;
+  int mi, ms;
+  try { mi = gauss_points_for_order(op->q_interior ? (int)op->q_interior : 2 * k); ms = gauss_points_for_order(op->q_surface ? (int)op->q_surface : 2 * k + 1); }
+  catch (const std::exception& ex) { return fail(B200FEM_ERR_NOT_IMPLEMENTED, ex.what()); }
+  // a rule with fewer points than basis functions per axis is under-integration the reference would perform as asked
+  if (N <= 3) return launch_dg_quadrature_n23(op, u, w, bvec, with_data, mi, ms);
+  if (N == 4) return launch_dg_quadrature_n4(op, u, w, bvec, with_data, mi, ms);
+  if (N <= 6) return launch_dg_quadrature_n56(op, u, w, bvec, with_data, mi, ms);
   return fail(B200FEM_ERR_NOT_IMPLEMENTED, "DG order > 5");
 }
 

@@ -23,6 +23,12 @@ template <int N> static DgTabDev<N> make_tab(const Tab1D& t) {
   for (int i = 0; i < N; ++i) { T.x[i] = t.x[i]; T.w[i] = t.w[i]; T.phi[0][i] = t.phi0[i]; T.phi[1][i] = t.phi1[i]; T.dphi[0][i] = t.dphi0[i]; T.dphi[1][i] = t.dphi1[i]; }
   return T;
 }
+template <int N> static QuadTabDev<N, N, N> make_quad_tab3(const Tab1D& t) {
+  QuadTabDev<N, N, N> T;
+  for (int i = 0; i < N * N; ++i) { T.Bi[i] = T.Bs[i] = t.B[i]; T.Gi[i] = T.Gs[i] = t.G[i]; }
+  for (int i = 0; i < N; ++i) { T.xi[i] = T.xs[i] = t.x[i]; T.wi[i] = T.ws[i] = t.w[i]; T.phi[0][i] = t.phi0[i]; T.phi[1][i] = t.phi1[i]; T.dphi[0][i] = t.dphi0[i]; T.dphi[1][i] = t.dphi1[i]; }
+  return T;
+}
 
 // generic element integrals, 2^dim colours = 2^dim launches with plain read-modify-write (deterministic)
 template <int N> static int launch_lagrange(b200fem_operator* op, const double* u, double* w, bool with_data) {
@@ -31,13 +37,13 @@ template <int N> static int launch_lagrange(b200fem_operator* op, const double* 
   AdrIntegrands I; I.m = op->model; I.dim = b.dim; I.with_data = with_data;
   int launches = 1;
   if (b.dim == 3) {
-    using Cfg = DgQuadCfg<N>; auto kern = lagrange3d_quadrature_kernel<N, AdrIntegrands>;
+    using Cfg = DgQuadCfg<N, N, N>; auto kern = lagrange3d_quadrature_kernel<N, AdrIntegrands>;
     int rc = ensure_smem_attr(ctx, (const void*)kern, Cfg::smem_bytes()); if (rc) return rc;
     for (int c = 0; c < 8; ++c) {
       const int c0 = c & 1, c1 = (c >> 1) & 1, c2 = c >> 2;
       const int m0 = (b.n[0] - c0 + 1) / 2, m1 = (b.n[1] - c1 + 1) / 2, m2 = (b.n[2] - c2 + 1) / 2;
       const long long nc = (long long)m0 * m1 * m2; if (nc <= 0) continue;
-      kern<<<(unsigned)((nc + Cfg::EB - 1) / Cfg::EB), Cfg::kThreads, Cfg::smem_bytes(), st>>>(make_tab<N>(op->sp->tab), b, I, op->sp->lay, u, w, c0, c1, c2, m0, m1, nc);
+      kern<<<(unsigned)((nc + Cfg::EB - 1) / Cfg::EB), Cfg::kThreads, Cfg::smem_bytes(), st>>>(make_quad_tab3<N>(op->sp->tab), b, I, op->sp->lay, u, w, c0, c1, c2, m0, m1, nc);
       ++launches;
     }
   } else {

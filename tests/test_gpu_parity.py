@@ -42,6 +42,36 @@ def test_dg_quadrature_kernel_affine_and_linear(order, hier):
     assert rel(op.loadVector(), -oop.apply(np.zeros(space.size))) < TOL
 
 
+@pytest.mark.parametrize("order,qi,qs", [(1, 4, 3), (1, 5, 5), (2, 4, 7), (2, 6, 5), (2, 6, 6), (2, 8, 9), (3, 8, 8), (3, 10, 10), (4, 10, 11), (5, 12, 12)])
+def test_dg_quadrature_orders_are_honoured(order, qi, qs):
+    """setQuadratureOrders (galerkin.hh:1418-1423): the Gauss rules follow the requested orders, here on the non-linear
+    model (u^3 makes the rule visible in the result), kernel left on AUTO."""
+    n = [4, 3, 3] if order <= 3 else [3, 2, 2]
+    space, _ = dg_pair(n, [-1, -1, -1], [1, 0.5, 2.0], order, True)
+    osp = ol.Space(n, [-1, -1, -1], [1, 0.5, 2.0], ol.DG_LEGENDRE_HIER, order, interior_order=qi, surface_order=qs)
+    kw = dict(eps=0.05, b=(1.0, -0.5, 0.25), c=0.3, gamma=0.7, beta=20.0 * order ** 2, dirichlet_mask=0b010011, data=1)
+    u = np.random.default_rng(100 * order + qi).uniform(-1, 1, space.size)
+    oop = ol.Operator(osp, skeleton=True, boundary=True, **kw)
+    op = fem.operator.galerkin(space, **kw)
+    op.setQuadratureOrders(qi, qs)
+    w = np.empty(space.size)
+    op(u, w)
+    ref = oop.apply(u)
+    assert rel(w, ref) < TOL
+    osp_default = ol.Space(n, [-1, -1, -1], [1, 0.5, 2.0], ol.DG_LEGENDRE_HIER, order)
+    assert rel(ol.Operator(osp_default, skeleton=True, boundary=True, **kw).apply(u), ref) > 1e-9   # the rule matters here
+    kw["gamma"] = 0.0                                               # linear model: the Kronecker kernels must step aside
+    oop = ol.Operator(osp, skeleton=True, boundary=True, **kw)
+    op = fem.operator.galerkin(space, **kw)
+    op.setQuadratureOrders(qi, qs)
+    op(u, w)
+    assert rel(w, oop.apply(u)) < TOL
+    assert rel(op.loadVector(), -oop.apply(np.zeros(space.size))) < TOL
+    op.setQuadratureOrders(0, 0)                                    # back to the defaults: cached load vector is rebuilt
+    op(u, w)
+    assert rel(w, ol.Operator(osp_default, skeleton=True, boundary=True, **kw).apply(u)) < TOL
+
+
 @pytest.mark.parametrize("order,hier", [(1, False), (1, True), (2, False), (2, True)])
 @pytest.mark.parametrize("n", [[9, 5, 6], [8, 4, 4], [1, 2, 3], [10, 7, 5], [18, 4, 9]])
 def test_dg_kronecker_kernel(order, hier, n):
