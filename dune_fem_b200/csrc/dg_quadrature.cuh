@@ -57,13 +57,22 @@ template <int N, int MI, int MS> struct DgQuadCfg {
   static constexpr int kVol = 2 * N * N * LM + 3 * N * MI * LM;                // T1a, T1b; T2a, T2b, T2c
   static constexpr int kRegA = quad_max(24 * N * LN, 18 * N * LS);             // face coefficients C, later X
   static constexpr int kRegB = quad_max(36 * N * LS, 12 * N * LN);             // E, later R
-  static constexpr int kScratch = quad_max(kVol, kRegA + kRegB);
+  // stored-order dofs of the six face neighbours, fetched (coalesced) with the element's own dofs at kernel start and read by
+  // the trace stage F0; they sit behind the volume scratch and the C region, inside or behind E (not yet in use at F0)
+  static constexpr int kNb = quad_max(kVol, kRegA);
+  static constexpr int kScratch = quad_max(kRegA + kRegB, kNb + 6 * N * N * N);
   static constexpr int kElemDoubles = quad_odd(2 * kU + kScratch);
-  // elements per CTA: about 128 threads (whole warps as far as possible), at most ~72 KB of shared memory
-  static constexpr int eb_fit() { int eb = 1; while ((eb + 1) * T2 <= 128 && (size_t)(eb + 1) * kElemDoubles * 8 <= 72 * 1024) ++eb; return eb; }
+  // Elements per CTA and the thread map.  The element slot is the FAST index of the thread id (slot = tid % EB, lane in the
+  // element = tid / EB): neighbouring lanes of a warp do the same job on different elements, so every shared-memory access of
+  // a (half-)warp is "same offset, element stride" -- conflict-free whatever the access pattern, because the element stride
+  // is odd (kElemDoubles); and the job loops (trip count depends on the lane in the element) do not diverge inside a warp.
+  // EB = 16 fills a half-warp; smaller powers of two where 16 elements do not fit ~100 KB / 640 threads.
+  static constexpr int eb_fit() { int eb = 16; while (eb > 1 && (eb * T2 > 640 || (size_t)eb * kElemDoubles * 8 > 100 * 1024)) eb /= 2; return eb; }
   static constexpr int EB = eb_fit();
   static constexpr int kThreads = (EB * T2 + 31) / 32 * 32;
-  static constexpr size_t smem_bytes() { return sizeof(double) * (size_t)EB * kElemDoubles + sizeof(int) * N * N * N * 2 + sizeof(long long) * EB + sizeof(int) * 4 * EB + 64; }
+  __device__ static int slot(int tid) { return tid % EB; }
+  __device__ static int lane(int tid) { return tid / EB; }     // >= T2 for the padding threads of the last warp
+  static constexpr size_t smem_bytes() { return sizeof(double) * (size_t)EB * kElemDoubles + sizeof(int) * N * N * N * 2 + sizeof(long long) * EB + sizeof(int) * 4 * EB; }
 };
 
 template <int N> __device__ __forceinline__ void quad_zero(double (&a)[N]) {
@@ -169,7 +178,6 @@ __device__ __forceinline__ void element_integrals(const QuadTabDev<N, MI, MS>& T
   // E[f][k][e] after the first tangential sweep; later X[f][x] overlays C and R[f][field] overlays E.
   double* const Cc = S; double* const Ee = S + Cfg::kRegA;
   constexpr int kC = N * LN, kE = N * LS;
-  const long long estep1 = box.n[0], estep2 = (long long)box.n[0] * box.n[1];
   // F0: trace coefficients of u_K and of the neighbour on each face; thread = (ia, ib); one unrolled block per axis
   if (active && la < N && lb < N) {
 #pragma unroll
@@ -190,8 +198,7 @@ __device__ __forceinline__ void element_integrals(const QuadTabDev<N, MI, MS>& T
         double nv = 0, nd = 0;
         const int cn = lc[d] + (s ? 1 : -1);
         if (I.m.has_skeleton && cn >= 0 && cn < box.n[d]) {
-          const long long step = d == 0 ? 1 : d == 1 ? estep1 : estep2;
-          const double* un = u + (e + (s ? step : -step)) * N3;
+          const double* un = S + Cfg::kNb + f * N3;     // staged by the kernel prologue (stored order)
 #pragma unroll
           for (int c = 0; c < N; ++c) {
             const int t = tbase + c * stt[d];
@@ -330,11 +337,12 @@ dg_quadrature_kernel(const __grid_constant__ QuadTabDev<N, MI, MS> T, const __gr
   long long* elem_of = reinterpret_cast<long long*>(smem + (size_t)EB * ELEM);   // local element index per slot
   int* perm = reinterpret_cast<int*>(elem_of + EB);                               // tensor index -> stored index
   int* tinv = perm + N3;                                                          // stored index -> tensor index (padded offset)
+  int* ecs = tinv + N3;                                                           // element coordinates per slot (4 ints)
 
-  const int tid = threadIdx.x, es = tid / Cfg::T2, lt = tid % Cfg::T2;
+  const int tid = threadIdx.x, es = Cfg::slot(tid), lt = Cfg::lane(tid);
   const int on0 = box.own_hi[0] - box.own_lo[0], on1 = box.own_hi[1] - box.own_lo[1];
   const long long oe = (long long)blockIdx.x * EB + es;
-  const bool active = es < EB && oe < n_owned;
+  const bool active = lt < Cfg::T2 && oe < n_owned;
   int lc[3] = {0, 0, 0};
   if (active) {
     lc[0] = box.own_lo[0] + (int)(oe % on0);
@@ -342,18 +350,48 @@ dg_quadrature_kernel(const __grid_constant__ QuadTabDev<N, MI, MS> T, const __gr
     lc[2] = box.own_lo[2] + (int)(oe / ((long long)on0 * on1));
   }
   const long long e = lc[0] + (long long)box.n[0] * (lc[1] + (long long)box.n[1] * lc[2]);
-  if (lt == 0 && es < EB) elem_of[es] = active ? e : -1;
+  if (lt == 0) { elem_of[es] = active ? e : -1; ecs[4 * es] = lc[0]; ecs[4 * es + 1] = lc[1]; ecs[4 * es + 2] = lc[2]; }
   for (int i = tid; i < N3; i += blockDim.x) { const int p = perm_g[i]; perm[i] = p; tinv[p] = (i / N2 * N + (i / N) % N) * LN + i % N; }
   __syncthreads();
 
-  // ---- gather (coalesced over the CTA's elements), stored order -> tensor order (padded lines) ----
-  for (int idx = tid; idx < EB * N3; idx += blockDim.x) {
-    const int s2 = idx / N3, j = idx % N3; const long long e2 = elem_of[s2];
-    if (e2 >= 0) smem[(size_t)s2 * ELEM + tinv[j]] = u[e2 * N3 + j];
+  // ---- gather: the elements' own dofs (stored order -> tensor order, padded lines) and, for skeleton terms, the stored-order
+  //      dofs of their six face neighbours.  Coalesced: consecutive slots are consecutive elements, and so are their
+  //      neighbours across one face.  All loads of a thread are issued before the first store (one latency, not seven). ----
+  {
+    constexpr int KI = (EB * N3 + Cfg::kThreads - 1) / Cfg::kThreads;
+    const long long estep1 = box.n[0], estep2 = (long long)box.n[0] * box.n[1];
+    const bool skel = I.m.has_skeleton;
+    double own[KI], nbv[KI][6]; bool have[KI][6]; int base[KI], jj[KI];
+#pragma unroll
+    for (int k = 0; k < KI; ++k) {
+      const int idx = tid + k * Cfg::kThreads, s2 = idx / N3, j = idx % N3;
+      const long long e2 = idx < EB * N3 ? elem_of[s2] : -1;
+      base[k] = e2 >= 0 ? s2 * ELEM : -1; jj[k] = j;
+      if (e2 >= 0) own[k] = u[e2 * N3 + j];
+#pragma unroll
+      for (int f = 0; f < 6; ++f) {
+        const int d = f >> 1;
+        have[k][f] = false;
+        if (skel && e2 >= 0) {
+          const int cn = ecs[4 * s2 + d] + ((f & 1) ? 1 : -1);
+          const long long step = d == 0 ? 1 : d == 1 ? estep1 : estep2;
+          if (cn >= 0 && cn < box.n[d]) { have[k][f] = true; nbv[k][f] = u[(e2 + ((f & 1) ? step : -step)) * N3 + j]; }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < KI; ++k) {
+      if (base[k] >= 0) {
+        smem[base[k] + tinv[jj[k]]] = own[k];
+#pragma unroll
+        for (int f = 0; f < 6; ++f)
+          if (have[k][f]) smem[base[k] + 2 * Cfg::kU + Cfg::kNb + f * N3 + jj[k]] = nbv[k][f];
+      }
+    }
   }
   __syncthreads();
 
-  double* U = smem + (size_t)(es < EB ? es : 0) * ELEM;
+  double* U = smem + (size_t)es * ELEM;
   element_integrals<N, MI, MS, Integrands>(T, box, I, perm, u, active, lc, e, lt, U, U + Cfg::kU, U + 2 * Cfg::kU);
 
   // ---- write w_K once (tensor order -> stored order), optionally w = A u - b ----

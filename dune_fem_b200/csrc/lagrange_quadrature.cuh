@@ -52,9 +52,9 @@ lagrange3d_quadrature_kernel(const __grid_constant__ QuadTabDev<N, N, N> T, cons
   double* smem = reinterpret_cast<double*>(smem_raw);
   int* ecs = reinterpret_cast<int*>(smem + (size_t)EB * ELEM);       // 4 ints per slot: coords + active flag
 
-  const int tid = threadIdx.x, es = tid / Cfg::T2, lt = tid % Cfg::T2;
+  const int tid = threadIdx.x, es = Cfg::slot(tid), lt = Cfg::lane(tid);
   const long long oe = (long long)blockIdx.x * EB + es;
-  const bool active = es < EB && oe < n_colour;
+  const bool active = lt < Cfg::T2 && oe < n_colour;
   int lc[3] = {0, 0, 0};
   if (active) {
     lc[0] = box.own_lo[0] + 2 * (int)(oe % m0) + c0;
@@ -62,7 +62,7 @@ lagrange3d_quadrature_kernel(const __grid_constant__ QuadTabDev<N, N, N> T, cons
     lc[2] = box.own_lo[2] + 2 * (int)(oe / ((long long)m0 * m1)) + c2;
   }
   const long long e = lc[0] + (long long)box.n[0] * (lc[1] + (long long)box.n[1] * lc[2]);
-  if (lt == 0 && es < EB) { ecs[4 * es] = lc[0]; ecs[4 * es + 1] = lc[1]; ecs[4 * es + 2] = lc[2]; ecs[4 * es + 3] = active; }
+  if (lt == 0) { ecs[4 * es] = lc[0]; ecs[4 * es + 1] = lc[1]; ecs[4 * es + 2] = lc[2]; ecs[4 * es + 3] = active; }
   __syncthreads();
   const int k = N - 1;
   for (int idx = tid; idx < EB * N3; idx += blockDim.x) {            // gather (getLocalDofs)
@@ -73,7 +73,7 @@ lagrange3d_quadrature_kernel(const __grid_constant__ QuadTabDev<N, N, N> T, cons
     }
   }
   __syncthreads();
-  double* U = smem + (size_t)(es < EB ? es : 0) * ELEM;
+  double* U = smem + (size_t)es * ELEM;
   element_integrals<N, N, N, Integrands>(T, box, I, nullptr, u, active, lc, e, lt, U, U + Cfg::kU, U + 2 * Cfg::kU);
   for (int idx = tid; idx < EB * N3; idx += blockDim.x) {            // coloured scatter-add (addLocalDofs)
     const int s2 = idx / N3, t = idx % N3;
