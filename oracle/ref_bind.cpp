@@ -1,0 +1,161 @@
+// oracle/ref_bind.cpp -- TEST INFRASTRUCTURE.  C bindings around the pieces of the reference that compile from their own
+// source files, where they lie under /root/reference (nothing is copied into this repository):
+//
+//   dune/fem/solver/linear/cg.hh, bicgstab.hh, gmres.hh        the Krylov loops (templates on operator / discrete function)
+//   dune/fem/quadrature/gausspoints{,_implementation}.hh       the 1-D Gauss tables
+//   dune/fem/space/shapefunctionset/legendrepolynomials.{hh,cc} the Legendre coefficient table and its Horner evaluation
+//   dune/fem/space/shapefunctionset/orthonormal/orthonormalbase_{1,2,3}d.hh   the orthonormal P_k bases behind `dgonb`
+//
+// Built by oracle/Makefile (target `ref`) into oracle/_ref/libdunefem_ref.so with `-I oracle/ref_shim -I /root/reference`;
+// the shim directory only supplies stand-ins for headers of dune-common that are absent from this image (see the files
+// there).  The element loop of schemes/galerkin.hh needs dune-grid/-geometry and cannot be compiled here.
+//
+// tests/test_reference_pieces.py uses this library to pin the oracle's restatements (fo_cg, fo_bicgstab, fo_gmres,
+// fo_quadrature, fo_legendre, the dgonb shape functions) against the reference code itself.  Only tests/ may load it.
+#include <algorithm>
+#include <cassert>
+#include <cmath>
+#include <complex>   // std::real(double): dune-common pulls it in for the reference (cg.hh:64)
+#include <iostream>
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+#include <iomanip>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include <dune/fem/solver/linear/cg.hh>
+#include <dune/fem/solver/linear/bicgstab.hh>
+#include <dune/fem/solver/linear/gmres.hh>
+#include <dune/fem/quadrature/gausspoints.hh>
+#include <dune/fem/space/shapefunctionset/legendrepolynomials.hh>
+#include <dune/fem/space/shapefunctionset/orthonormal/orthonormalbase_1d.hh>
+#include <dune/fem/space/shapefunctionset/orthonormal/orthonormalbase_2d.hh>
+#include <dune/fem/space/shapefunctionset/orthonormal/orthonormalbase_3d.hh>
+
+namespace {
+
+// The slice of the DiscreteFunction interface the reference loops use (function/common/discretefunction.hh,
+// blockvectors/defaultblockvectors.hh:39-150, scalarproducts.hh:115-127), over a plain array on one rank.
+struct Comm { template <class T> void sum(T*, int) const {} };
+struct GridPart { Comm c; const Comm& comm() const { return c; } };
+struct Space {
+  GridPart gp; std::vector<std::size_t> aux;   // sorted auxiliary dofs, terminated by the vector size (auxiliarydofs.hh)
+  const GridPart& gridPart() const { return gp; }
+  const std::vector<std::size_t>& auxiliaryDofs() const { return aux; }
+};
+
+struct Vec {
+  typedef double RangeFieldType;
+  const Space* sp; std::vector<double> d;
+  Vec(const Space& s, std::size_t n) : sp(&s), d(n, 0.0) {}
+  const Space& space() const { return *sp; }
+  std::vector<double>& dofVector() { return d; }
+  const std::vector<double>& dofVector() const { return d; }
+  void clear() { std::fill(d.begin(), d.end(), 0.0); }
+  void assign(const Vec& o) { d = o.d; }
+  Vec& operator+=(const Vec& o) { for (std::size_t i = 0; i < d.size(); ++i) d[i] += o.d[i]; return *this; }
+  Vec& operator-=(const Vec& o) { for (std::size_t i = 0; i < d.size(); ++i) d[i] -= o.d[i]; return *this; }
+  Vec& operator*=(double s) { for (std::size_t i = 0; i < d.size(); ++i) d[i] *= s; return *this; }
+  void axpy(double s, const Vec& o) { for (std::size_t i = 0; i < d.size(); ++i) d[i] += s * o.d[i]; }
+  double scalarProductDofs(const Vec& o) const {
+    double scp = 0;
+    Dune::Fem::forEachPrimaryDof(sp->aux, [&](std::size_t i) { scp += d[i] * o.d[i]; });
+    return scp;
+  }
+  double normSquaredDofs() const { return scalarProductDofs(*this); }
+};
+
+typedef void (*ApplyFn)(const double* u, double* w, void* ctx);
+struct Op {
+  ApplyFn fn; void* ctx;
+  void operator()(const Vec& u, Vec& w) const { fn(u.d.data(), w.d.data(), ctx); }
+};
+
+Space makeSpace(std::int64_t n, const std::int64_t* aux, std::int64_t naux) {
+  Space s; for (std::int64_t i = 0; i < naux; ++i) s.aux.push_back(std::size_t(aux[i])); s.aux.push_back(std::size_t(n)); return s;
+}
+
+// the loops report residuals only through their verbose stream: parse it back (17 significant digits round-trip a double)
+int parseHistory(const std::string& log, const char* key, double* hist, int maxHist) {
+  std::istringstream in(log); std::string line; int k = 0;
+  while (std::getline(in, line)) {
+    if (line.find(key) == std::string::npos) continue;
+    std::string tail = line.substr(line.rfind(':') + 1);            // " residual 1.2e-3" (cg.hh:110) or " 1.2e-3"
+    const std::size_t r = tail.find("residual"); if (r != std::string::npos) tail = tail.substr(r + 8);
+    if (hist && k < maxHist) hist[k] = std::stod(tail);
+    ++k;
+  }
+  return k;
+}
+
+}  // namespace
+
+extern "C" {
+
+// LinearSolver::cg (dune/fem/solver/linear/cg.hh:18-117); precon may be NULL
+int ref_cg(ApplyFn apply, void* ctx, ApplyFn precon, void* pctx, std::int64_t n, const std::int64_t* aux, std::int64_t naux,
+           double* x, const double* b, double eps, int maxit, int crit, double* hist, int maxHist, int* nHist) {
+  Space sp = makeSpace(n, aux, naux);
+  Vec X(sp, n), B(sp, n); std::memcpy(X.d.data(), x, n * 8); std::memcpy(B.d.data(), b, n * 8);
+  std::vector<Vec> tmp(precon ? 5 : 3, Vec(sp, n));
+  Op op{apply, ctx}, pre{precon, pctx};
+  std::ostringstream os; os << std::setprecision(17);
+  const int it = Dune::Fem::LinearSolver::cg(op, precon ? &pre : (Op*)nullptr, tmp, X, B, eps, maxit, crit, &os);
+  const int k = parseHistory(os.str(), "Fem::CG it:", hist, maxHist); if (nHist) *nHist = k;
+  std::memcpy(x, X.d.data(), n * 8);
+  return it;
+}
+
+// LinearSolver::bicgstab (dune/fem/solver/linear/bicgstab.hh:63-214)
+int ref_bicgstab(ApplyFn apply, void* ctx, std::int64_t n, const std::int64_t* aux, std::int64_t naux,
+                 double* x, const double* b, double tol, int maxit, int crit, double* hist, int maxHist, int* nHist) {
+  Space sp = makeSpace(n, aux, naux);
+  Vec X(sp, n), B(sp, n); std::memcpy(X.d.data(), x, n * 8); std::memcpy(B.d.data(), b, n * 8);
+  std::vector<Vec> tmp(5, Vec(sp, n));
+  Op op{apply, ctx};
+  std::ostringstream os; os << std::setprecision(17);
+  const int it = Dune::Fem::LinearSolver::bicgstab(op, (Op*)nullptr, tmp, X, B, tol, maxit, crit, &os);
+  const int k = parseHistory(os.str(), "Fem::BiCGstab it:", hist, maxHist); if (nHist) *nHist = k;
+  std::memcpy(x, X.d.data(), n * 8);
+  return it;
+}
+
+// LinearSolver::gmres (dune/fem/solver/linear/gmres.hh:116-301)
+int ref_gmres(ApplyFn apply, void* ctx, std::int64_t n, const std::int64_t* aux, std::int64_t naux,
+              double* x, const double* b, int restart, double tol, int maxit, int crit, double* hist, int maxHist, int* nHist) {
+  Space sp = makeSpace(n, aux, naux);
+  Vec X(sp, n), B(sp, n); std::memcpy(X.d.data(), x, n * 8); std::memcpy(B.d.data(), b, n * 8);
+  std::vector<Vec> v(restart + 1, Vec(sp, n));
+  Op op{apply, ctx};
+  std::ostringstream os; os << std::setprecision(17);
+  const int it = Dune::Fem::LinearSolver::gmres(op, (Op*)nullptr, v, X, B, restart, tol, maxit, crit, &os);
+  const int k = parseHistory(os.str(), "Fem::GMRES it:", hist, maxHist); if (nHist) *nHist = k;
+  std::memcpy(x, X.d.data(), n * 8);
+  return it;
+}
+
+// GaussPts (dune/fem/quadrature/gausspoints_implementation.hh): m-point rule on [0,1]
+int ref_gauss_maxp() { return Dune::Fem::GaussPts::MAXP; }
+int ref_gauss_rule(int m, double* x, double* w) {
+  static const Dune::Fem::GaussPts g;
+  for (int i = 0; i < m; ++i) { x[i] = g.point(m, i); w[i] = g.weight(m, i); }
+  return g.order(m);
+}
+
+// LegendrePolynomials (shapefunctionset/legendrepolynomials.hh:15-62, table in legendrepolynomials.cc)
+int ref_legendre_max_order() { return Dune::Fem::LegendrePolynomials::maxOrder; }
+double ref_legendre(int num, double x, int deriv) {
+  typedef Dune::Fem::LegendrePolynomials L;
+  return deriv == 0 ? L::evaluate(num, x) : deriv == 1 ? L::jacobian(num, x) : L::hessian(num, x);
+}
+
+// OrthonormalBase_{1,2,3}D on the cube (line / quadrilateral / hexahedron): value and gradient of shape function i
+double ref_onb_cube(int dim, int i, const double* x, double* grad) {
+  if (dim == 1) { typedef Dune::Fem::OrthonormalBase_1D<double, double> B; if (grad) B::grad_line(i, x, grad); return B::eval_line(i, x); }
+  if (dim == 2) { typedef Dune::Fem::OrthonormalBase_2D<double, double> B; if (grad) B::grad_quadrilateral_2d(i, x, grad); return B::eval_quadrilateral_2d(i, x); }
+  typedef Dune::Fem::OrthonormalBase_3D<double, double> B; if (grad) B::grad_hexahedron_3d(i, x, grad); return B::eval_hexahedron_3d(i, x);
+}
+
+}  // extern "C"

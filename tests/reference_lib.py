@@ -1,0 +1,112 @@
+"""ctypes binding of oracle/_ref/libdunefem_ref.so: the pieces of the reference (DUNE-FEM) that compile from their own source
+files where they lie under /root/reference (oracle/ref_bind.cpp, oracle/Makefile target `ref`).  Test infrastructure only.
+
+The library is built in the development container (where /root/reference exists) and travels to the GPU box as a built file;
+`available()` is False where neither the library nor the reference tree is present."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ORACLE_DIR = os.path.join(os.path.dirname(_HERE), "oracle")
+_SO = os.path.join(_ORACLE_DIR, "_ref", "libdunefem_ref.so")
+REFERENCE = os.environ.get("B200FEM_REFERENCE", "/root/reference")
+_LIB = None
+
+APPLY_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p)
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_lp = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+
+
+def available():
+    return os.path.exists(_SO) or os.path.isdir(os.path.join(REFERENCE, "dune", "fem"))
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    src = os.path.join(_ORACLE_DIR, "ref_bind.cpp")
+    if os.path.isdir(os.path.join(REFERENCE, "dune", "fem")) and (not os.path.exists(_SO) or os.path.getmtime(src) > os.path.getmtime(_SO)):
+        subprocess.check_call(["make", "-C", _ORACLE_DIR, "-s", "ref", f"REFERENCE={REFERENCE}"])
+    L = C.CDLL(_SO)
+    L.ref_cg.restype = C.c_int
+    L.ref_cg.argtypes = [APPLY_FN, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, _lp, C.c_int64, _dp, _dp, C.c_double, C.c_int, C.c_int,
+                         _dp, C.c_int, C.POINTER(C.c_int)]
+    L.ref_bicgstab.restype = C.c_int
+    L.ref_bicgstab.argtypes = [APPLY_FN, C.c_void_p, C.c_int64, _lp, C.c_int64, _dp, _dp, C.c_double, C.c_int, C.c_int, _dp, C.c_int, C.POINTER(C.c_int)]
+    L.ref_gmres.restype = C.c_int
+    L.ref_gmres.argtypes = [APPLY_FN, C.c_void_p, C.c_int64, _lp, C.c_int64, _dp, _dp, C.c_int, C.c_double, C.c_int, C.c_int, _dp, C.c_int, C.POINTER(C.c_int)]
+    L.ref_gauss_maxp.restype = C.c_int
+    L.ref_gauss_rule.restype = C.c_int
+    L.ref_gauss_rule.argtypes = [C.c_int, _dp, _dp]
+    L.ref_legendre_max_order.restype = C.c_int
+    L.ref_legendre.restype = C.c_double
+    L.ref_legendre.argtypes = [C.c_int, C.c_double, C.c_int]
+    L.ref_onb_cube.restype = C.c_double
+    L.ref_onb_cube.argtypes = [C.c_int, C.c_int, _dp, C.c_void_p]
+    _LIB = L
+    return L
+
+
+def _wrap(apply, n):
+    def cb(pu, pw, _ctx):
+        u = np.ctypeslib.as_array(pu, shape=(n,))
+        w = np.ctypeslib.as_array(pw, shape=(n,))
+        w[:] = apply(u)
+    return APPLY_FN(cb)
+
+
+def _aux(aux):
+    return np.ascontiguousarray([] if aux is None else aux, dtype=np.int64)
+
+
+def cg(apply, b, x0, eps, maxit, tolcrit=0, precon=None, aux=None):
+    """Dune::Fem::LinearSolver::cg on python callables (apply: u -> A u; precon: r -> B r or None)."""
+    n = len(b)
+    x = np.array(x0, dtype=np.float64, copy=True)
+    hist, nh = np.zeros(max(maxit, 1)), C.c_int(0)
+    f = _wrap(apply, n)
+    p = _wrap(precon, n) if precon is not None else None
+    a = _aux(aux)
+    it = lib().ref_cg(f, None, C.cast(p, C.c_void_p) if p is not None else None, None, n, a, len(a), x, np.ascontiguousarray(b, dtype=np.float64),
+                      eps, maxit, tolcrit, hist, len(hist), C.byref(nh))
+    return it, x, hist[:nh.value]
+
+
+def bicgstab(apply, b, x0, tol, maxit, tolcrit=0, aux=None):
+    n = len(b)
+    x = np.array(x0, dtype=np.float64, copy=True)
+    hist, nh = np.zeros(max(maxit, 1)), C.c_int(0)
+    a = _aux(aux)
+    it = lib().ref_bicgstab(_wrap(apply, n), None, n, a, len(a), x, np.ascontiguousarray(b, dtype=np.float64), tol, maxit, tolcrit, hist, len(hist), C.byref(nh))
+    return it, x, hist[:nh.value]
+
+
+def gmres(apply, b, x0, tol, maxit, tolcrit=0, restart=20, aux=None):
+    n = len(b)
+    x = np.array(x0, dtype=np.float64, copy=True)
+    hist, nh = np.zeros(max(maxit, 1) + restart), C.c_int(0)
+    a = _aux(aux)
+    it = lib().ref_gmres(_wrap(apply, n), None, n, a, len(a), x, np.ascontiguousarray(b, dtype=np.float64), restart, tol, maxit, tolcrit, hist, len(hist), C.byref(nh))
+    return it, x, hist[:nh.value]
+
+
+def gauss_rule(m):
+    x, w = np.empty(m), np.empty(m)
+    order = lib().ref_gauss_rule(m, x, w)
+    return x, w, order
+
+
+def legendre(num, x, deriv=0):
+    return lib().ref_legendre(num, float(x), deriv)
+
+
+def onb_cube(dim, i, x, grad=False):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    if not grad:
+        return lib().ref_onb_cube(dim, i, x, None)
+    g = np.zeros(3)
+    v = lib().ref_onb_cube(dim, i, x, g.ctypes.data_as(C.c_void_p))
+    return v, g[:dim]

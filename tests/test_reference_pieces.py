@@ -1,0 +1,121 @@
+"""Pins the oracle's restatements against the reference ITSELF where the reference compiles from its own source files
+(oracle/_ref/libdunefem_ref.so, built by `make -C oracle ref` from /root/reference): the Krylov loops of
+dune/fem/solver/linear/{cg,bicgstab,gmres}.hh run on the oracle's operators, the Gauss tables, the Legendre polynomials and
+the orthonormal cube bases.  CPU only; skipped where neither the built library nor the reference tree exists."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import reference_lib as rl
+
+pytestmark = pytest.mark.skipif(not rl.available(), reason="oracle/_ref not built and /root/reference absent")
+
+
+def _poisson(dim, order, n):
+    sp = ol.Space(n, [0.0] * dim, [1.0] * dim, ol.LAGRANGE, order)
+    op = ol.Operator(sp, eps=1.0, c=0.5, data=2, dirichlet_mask=(1 << (2 * dim)) - 1, strong_dirichlet=True)
+    mask, _ = op.dirichlet()
+    b = np.random.default_rng(11).uniform(-1, 1, sp.size) * (1 - mask)     # many CG iterations, unlike the smooth data term
+    return sp, op, b
+
+
+@pytest.mark.parametrize("dim,order,n", [(2, 1, [24, 24]), (2, 2, [10, 9]), (3, 2, [5, 4, 3])])
+@pytest.mark.parametrize("tolcrit", [0, 1, 2])
+def test_cg_restatement_is_the_reference_loop(dim, order, n, tolcrit):
+    sp, op, b = _poisson(dim, order, n)
+    A = lambda u: op.apply(u, linear=True)
+    x0 = np.zeros(sp.size)
+    it_r, x_r, h_r = rl.cg(A, b, x0, 1e-9, 60, tolcrit)
+    it_o, x_o, h_o = op.cg(b, x0, 1e-9, 60, tolcrit)
+    assert it_r == it_o and len(h_r) == abs(it_o)
+    np.testing.assert_array_equal(h_o, h_r)          # same operations in the same order: bit-identical
+    np.testing.assert_array_equal(x_o, x_r)
+    # not converged: negative iteration count (cg.hh:116)
+    it_r, _, _ = rl.cg(A, b, x0, 1e-14, 5, tolcrit)
+    it_o, _, _ = op.cg(b, x0, 1e-14, 5, tolcrit)
+    assert it_r == it_o == -5
+
+
+def test_preconditioned_cg_restatement_is_the_reference_loop():
+    sp, op, b = _poisson(3, 2, [4, 4, 3])
+    A = lambda u: op.apply(u, linear=True)
+    d = op.diagonal()
+    x0 = np.zeros(sp.size)
+    it_r, x_r, h_r = rl.cg(A, b, x0, 1e-10, 80, 0, precon=lambda r: r / d)
+    it_o, x_o, h_o = op.pcg(d, b, x0, 1e-10, 80, 0)
+    assert it_r == it_o
+    np.testing.assert_allclose(h_o, h_r, rtol=1e-12)   # the oracle multiplies by 1/d, the callback divides
+    np.testing.assert_allclose(x_o, x_r, rtol=1e-11, atol=1e-14)
+
+
+def _advdiff(order, n=(4, 3, 3), eps=1e-2):
+    sp = ol.Space(list(n), [-1.0] * 3, [1.0] * 3, ol.DG_LEGENDRE_HIER, order)
+    op = ol.Operator(sp, eps=eps, b=(1.0, 0.3, 0.0), beta=20.0 * order * order, dirichlet_mask=0b000011, data=1, skeleton=True, boundary=True)
+    return sp, op, -op.apply(np.zeros(sp.size)) + np.random.default_rng(12).uniform(-1, 1, sp.size)
+
+
+@pytest.mark.parametrize("order", [1, 2])
+@pytest.mark.parametrize("tolcrit", [0, 1, 2])
+def test_bicgstab_restatement_is_the_reference_loop(order, tolcrit):
+    sp, op, b = _advdiff(order, eps=1.0)
+    A = lambda u: op.apply(u, linear=True)
+    x0 = np.zeros(sp.size)
+    # a fixed number of steps: same recurrence, same scalars (BiCGStab amplifies rounding differences -- FMA contraction in
+    # the vector updates -- too quickly for a comparison of whole convergence histories)
+    it_r, x_r, h_r = rl.bicgstab(A, b, x0, 1e-12, 12, tolcrit)
+    it_o, x_o, h_o = op.bicgstab(b, x0, 1e-12, 12, tolcrit)
+    assert it_r == it_o == -12
+    # the reference reports `res` only for iterations that continue (bicgstab.hh:186-189): its log is one entry shorter
+    assert len(h_r) == 11 and len(h_o) == 12
+    np.testing.assert_allclose(h_o[:11], h_r, rtol=1e-9)
+    np.testing.assert_allclose(h_o[:4], h_r[:4], rtol=1e-13)
+    np.testing.assert_allclose(x_o, x_r, rtol=0, atol=1e-9 * np.abs(x_r).max())
+    # run to convergence: positive counts, same solution
+    it_r, x_r, _ = rl.bicgstab(A, b, x0, 1e-8, 2000, tolcrit)
+    it_o, x_o, _ = op.bicgstab(b, x0, 1e-8, 2000, tolcrit)
+    assert it_r > 0 and it_o > 0
+    np.testing.assert_allclose(x_o, x_r, rtol=0, atol=1e-5 * np.abs(x_r).max())
+
+
+@pytest.mark.parametrize("order,restart", [(1, 5), (2, 20)])
+@pytest.mark.parametrize("tolcrit", [0, 1, 2])
+def test_gmres_restatement_is_the_reference_loop(order, restart, tolcrit):
+    sp, op, b = _advdiff(order)
+    A = lambda u: op.apply(u, linear=True)
+    x0 = np.zeros(sp.size)
+    it_r, x_r, h_r = rl.gmres(A, b, x0, 1e-7, 600, tolcrit, restart)
+    it_o, x_o, h_o = op.gmres(b, x0, 1e-7, 600, tolcrit, restart)
+    assert it_r == it_o and it_r > 0 and len(h_r) == len(h_o)
+    np.testing.assert_allclose(h_o, h_r, rtol=1e-9)
+    np.testing.assert_allclose(h_o[:10], h_r[:10], rtol=1e-13)
+    np.testing.assert_allclose(x_o, x_r, rtol=1e-9, atol=1e-12)
+    # Known deviation, on purpose: when maxIterations is hit inside a restart cycle the reference keeps restarting with
+    # one-step Krylov spaces and finally tests a stale g[last] (gmres.hh:246-289) -- it returns -(maxIterations + 1) after one
+    # more apply; the oracle and the device solver stop at -maxIterations with the iterate of that moment.
+    it_r, _, _ = rl.gmres(A, b, x0, 1e-14, 7, tolcrit, restart)
+    it_o, _, _ = op.gmres(b, x0, 1e-14, 7, tolcrit, restart)
+    assert it_o == -7 and it_r in (-7, -8)
+
+
+def test_gauss_rules_are_the_reference_tables():
+    lib = rl.lib()
+    assert lib.ref_gauss_maxp() == 10
+    for m in range(1, 11):
+        x, w, order = rl.gauss_rule(m)
+        assert order == 2 * m - 1
+        xo, wo = ol.quadrature(1, order)
+        assert len(wo) == m
+        np.testing.assert_array_equal(xo[:, 0], x)
+        np.testing.assert_array_equal(wo, w)
+        # the order selection of femquadratures_inline.hh:59-70: smallest rule with order >= requested
+        xo2, _ = ol.quadrature(1, max(order - 1, 0))
+        assert len(xo2) == m
+
+
+def test_legendre_polynomials_are_the_reference_evaluation():
+    assert rl.lib().ref_legendre_max_order() == 11
+    xs = np.random.default_rng(5).uniform(0, 1, 40).tolist() + [0.0, 0.5, 1.0]
+    for num in range(11):
+        for x in xs:
+            for deriv in (0, 1):
+                assert ol.lib().fo_legendre(num, x, deriv) == rl.legendre(num, x, deriv), (num, x, deriv)
