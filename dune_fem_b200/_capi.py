@@ -24,7 +24,7 @@ SYMBOLS = [
 ]
 
 OK, ERR_INVALID, ERR_NOT_IMPLEMENTED, ERR_CUDA, ERR_COMM = 0, -1, -2, -3, -4
-LAGRANGE, DG_LEGENDRE, DG_LEGENDRE_HIER = 0, 1, 2
+LAGRANGE, DG_LEGENDRE, DG_LEGENDRE_HIER, DG_ONB = 0, 1, 2, 3
 NUMBERING_YASP, NUMBERING_ADAPTIVE_LEAF = 0, 1
 KERNEL_AUTO, KERNEL_QUADRATURE, KERNEL_KRONECKER, KERNEL_KRONECKER_TILE = 0, 1, 2, 3
 TOL_ABSOLUTE, TOL_RELATIVE, TOL_RESIDUAL_REDUCTION = 0, 1, 2

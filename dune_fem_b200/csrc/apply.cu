@@ -42,7 +42,7 @@ int apply_local(b200fem_operator* op, const double* u, double* w, bool linear) {
   }
   // The Kronecker form rests on the default rules (the (k+1)-point Gauss rules integrate the 1-D mass matrices of the
   // orthonormal basis exactly); other quadrature orders (setQuadratureOrders) go through the generic quadrature kernel
-  const bool kron_ok = op->model.gamma == 0.0 && N >= 2 && N <= 6 && s->box.dim == 3 && default_quadrature(op);
+  const bool kron_ok = op->model.gamma == 0.0 && N >= 2 && N <= 6 && s->tensor_full && default_quadrature(op);
   int kernel = op->kernel_pref;
   if (kernel == B200FEM_KERNEL_AUTO) kernel = kron_ok ? B200FEM_KERNEL_KRONECKER : B200FEM_KERNEL_QUADRATURE;
   int rc;
@@ -53,7 +53,7 @@ int apply_local(b200fem_operator* op, const double* u, double* w, bool linear) {
   if (!linear && op->model.data && !op->in_bvec) { rc = ensure_bvec(op); if (rc) return rc; bvec = op->d_bvec; }
   if (kernel == B200FEM_KERNEL_KRONECKER || kernel == B200FEM_KERNEL_KRONECKER_TILE) {
     REQUIRE(op->model.gamma == 0.0, B200FEM_ERR_INVALID, "Kronecker kernel needs a linear model");
-    REQUIRE(kron_ok, B200FEM_ERR_NOT_IMPLEMENTED, "Kronecker kernel: 3-D DG spaces of order 1..5 with the default quadrature orders");
+    REQUIRE(kron_ok, B200FEM_ERR_NOT_IMPLEMENTED, "Kronecker kernel: 3-D Q_k Legendre spaces of order 1..5 with the default quadrature orders (2-D and dgonb spaces run through the quadrature kernel)");
     // marching kernel for Q2, slab kernel for Q3..Q5, tile kernel for Q1 and for Q2 boxes / vectors the TMA views cannot take
     if (N >= 4) rc = launch_dg_slab(op, u, w, bvec);
     else if (kernel == B200FEM_KERNEL_KRONECKER && dg_march_ok(op, u, w, bvec)) rc = launch_dg_march(op, u, w, bvec, op->want_exchange);

@@ -156,7 +156,7 @@ static void build_adaptive_leaf_map(b200fem_space* s) {
 
 extern "C" int b200fem_space_create(b200fem_mesh* mesh, int kind, int order, int numbering, b200fem_space** out) {
   REQUIRE(mesh && out, B200FEM_ERR_INVALID, "space_create: null argument");
-  REQUIRE(kind >= 0 && kind <= 2, B200FEM_ERR_INVALID, "space_create: unknown space kind");
+  REQUIRE(kind >= 0 && kind <= 3, B200FEM_ERR_INVALID, "space_create: unknown space kind");
   try {
     auto s = std::unique_ptr<b200fem_space>(new b200fem_space);
     s->mesh = mesh; s->kind = kind; s->order = order; s->numbering = numbering; s->n1 = order + 1;
@@ -186,12 +186,13 @@ extern "C" int b200fem_space_create(b200fem_mesh* mesh, int kind, int order, int
         L.lattice_map = s->d_lattice_map;
       }
     } else {
-      REQUIRE(order >= 1 && order <= 5, B200FEM_ERR_NOT_IMPLEMENTED, "DG Legendre spaces: orders 1..5");
-      REQUIRE(dim == 3, B200FEM_ERR_NOT_IMPLEMENTED, "DG Legendre spaces: 3-D boxes only");
+      REQUIRE(order >= 1 && order <= (kind == B200FEM_DG_ONB ? 4 : 5), B200FEM_ERR_NOT_IMPLEMENTED, "DG spaces: Legendre orders 1..5, dgonb orders 1..4");
       const BoxDev& b = s->box;
+      // the kernels work on the full tensor basis of the (3-D) cube; the space is a sub-basis of it (tables.hpp: dg_tensor_map)
+      s->perm = dg_tensor_map(dim, order, kind, &s->nb);
+      s->tensor_full = dim == 3 && s->nb == s->n1 * s->n1 * s->n1;
       s->elements = (long long)b.n[0] * b.n[1] * b.n[2]; s->size = s->elements * s->nb;
       s->tab = tabulate_1d(Basis::Legendre, order, gauss_points_for_order(2 * order));
-      s->perm = legendre_local_permutation(dim, order, kind == B200FEM_DG_LEGENDRE_HIER);
     }
     mesh->refs += 1;
     *out = s.release(); return B200FEM_OK;

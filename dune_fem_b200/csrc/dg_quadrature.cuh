@@ -202,7 +202,8 @@ __device__ __forceinline__ void element_integrals(const QuadTabDev<N, MI, MS>& T
 #pragma unroll
           for (int c = 0; c < N; ++c) {
             const int t = tbase + c * stt[d];
-            const double uv = un[perm ? perm[t] : t];
+            const int ps = perm ? perm[t] : t;                 // -1: the space holds no such function (sub-bases, see below)
+            const double uv = ps >= 0 ? un[ps] : 0.0;
             nv = fma(T.phi[1 - s][c], uv, nv); nd = fma(T.dphi[1 - s][c], uv, nd);
           }
         }
@@ -274,7 +275,7 @@ __device__ __forceinline__ void element_integrals(const QuadTabDev<N, MI, MS>& T
             if (own_inside) { I.skeleton(d, s ? 1.0 : -1.0, ihe, own, nb, rin, rout); r = rin; }
             else            { I.skeleton(d, s ? -1.0 : 1.0, ihe, nb, own, rin, rout); r = rout; }
           }
-        } else if (I.m.has_boundary) {
+        } else if (I.m.has_boundary && d < box.dim) {         // (a 2-D mesh is one layer of cells: its x2-faces are no boundary)
           r = I.boundary(d, s, ihe, xq, own);
         }
         const double wq = T.ws[qa] * T.ws[qb] * area;
@@ -327,7 +328,7 @@ __device__ __forceinline__ void element_integrals(const QuadTabDev<N, MI, MS>& T
 template <int N, int MI, int MS, class Integrands>
 __global__ void __launch_bounds__(DgQuadCfg<N, MI, MS>::kThreads)
 dg_quadrature_kernel(const __grid_constant__ QuadTabDev<N, MI, MS> T, const __grid_constant__ BoxDev box,
-                     const __grid_constant__ Integrands I, const int* __restrict__ perm_g,
+                     const __grid_constant__ Integrands I, const int* __restrict__ perm_g, const int nbs,
                      const double* __restrict__ u, double* __restrict__ w, const double* __restrict__ bvec,
                      long long n_owned, const double out_scale) {
   using Cfg = DgQuadCfg<N, MI, MS>;
@@ -351,7 +352,12 @@ dg_quadrature_kernel(const __grid_constant__ QuadTabDev<N, MI, MS> T, const __gr
   }
   const long long e = lc[0] + (long long)box.n[0] * (lc[1] + (long long)box.n[1] * lc[2]);
   if (lt == 0) { elem_of[es] = active ? e : -1; ecs[4 * es] = lc[0]; ecs[4 * es + 1] = lc[1]; ecs[4 * es + 2] = lc[2]; }
-  for (int i = tid; i < N3; i += blockDim.x) { const int p = perm_g[i]; perm[i] = p; tinv[p] = (i / N2 * N + (i / N) % N) * LN + i % N; }
+  // The space may be a SUB-BASIS of the full tensor basis the kernel works on: nbs <= N^3 stored dofs per element, perm_g[t] = -1
+  // for tensor functions it does not hold (2-D Q_k: functions constant in x2; dgonb P_k: total degree <= k).  Their coefficients
+  // are zero on input and their residuals are dropped on output -- the Galerkin operator of the sub-space, exactly.
+  for (int i = tid; i < N3; i += blockDim.x) { const int p = perm_g[i]; perm[i] = p; if (p >= 0) tinv[p] = (i / N2 * N + (i / N) % N) * LN + i % N; }
+  if (nbs < N3)
+    for (int idx = tid; idx < EB * Cfg::kU; idx += blockDim.x) smem[(size_t)(idx / Cfg::kU) * ELEM + idx % Cfg::kU] = 0.0;
   __syncthreads();
 
   // ---- gather: the elements' own dofs (stored order -> tensor order, padded lines) and, for skeleton terms, the stored-order
@@ -364,10 +370,10 @@ dg_quadrature_kernel(const __grid_constant__ QuadTabDev<N, MI, MS> T, const __gr
     double own[KI], nbv[KI][6]; bool have[KI][6]; int base[KI], jj[KI];
 #pragma unroll
     for (int k = 0; k < KI; ++k) {
-      const int idx = tid + k * Cfg::kThreads, s2 = idx / N3, j = idx % N3;
-      const long long e2 = idx < EB * N3 ? elem_of[s2] : -1;
+      const int idx = tid + k * Cfg::kThreads, s2 = idx / nbs, j = idx % nbs;
+      const long long e2 = idx < EB * nbs ? elem_of[s2] : -1;
       base[k] = e2 >= 0 ? s2 * ELEM : -1; jj[k] = j;
-      if (e2 >= 0) own[k] = u[e2 * N3 + j];
+      if (e2 >= 0) own[k] = u[e2 * nbs + j];
 #pragma unroll
       for (int f = 0; f < 6; ++f) {
         const int d = f >> 1;
@@ -375,7 +381,7 @@ dg_quadrature_kernel(const __grid_constant__ QuadTabDev<N, MI, MS> T, const __gr
         if (skel && e2 >= 0) {
           const int cn = ecs[4 * s2 + d] + ((f & 1) ? 1 : -1);
           const long long step = d == 0 ? 1 : d == 1 ? estep1 : estep2;
-          if (cn >= 0 && cn < box.n[d]) { have[k][f] = true; nbv[k][f] = u[(e2 + ((f & 1) ? step : -step)) * N3 + j]; }
+          if (cn >= 0 && cn < box.n[d]) { have[k][f] = true; nbv[k][f] = u[(e2 + ((f & 1) ? step : -step)) * nbs + j]; }
         }
       }
     }
@@ -395,12 +401,12 @@ dg_quadrature_kernel(const __grid_constant__ QuadTabDev<N, MI, MS> T, const __gr
   element_integrals<N, MI, MS, Integrands>(T, box, I, perm, u, active, lc, e, lt, U, U + Cfg::kU, U + 2 * Cfg::kU);
 
   // ---- write w_K once (tensor order -> stored order), optionally w = A u - b ----
-  for (int idx = tid; idx < EB * N3; idx += blockDim.x) {
-    const int s2 = idx / N3, j = idx % N3; const long long e2 = elem_of[s2];
+  for (int idx = tid; idx < EB * nbs; idx += blockDim.x) {
+    const int s2 = idx / nbs, j = idx % nbs; const long long e2 = elem_of[s2];
     if (e2 >= 0) {
       double val = smem[(size_t)s2 * ELEM + Cfg::kU + tinv[j]] * out_scale;      // out_scale: inverse mass of MOLGalerkinOperator (1 otherwise)
-      if (bvec) val -= bvec[e2 * N3 + j];
-      w[e2 * N3 + j] = val;
+      if (bvec) val -= bvec[e2 * nbs + j];
+      w[e2 * nbs + j] = val;
     }
   }
 }

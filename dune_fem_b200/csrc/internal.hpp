@@ -52,7 +52,8 @@ struct b200fem_mesh {
 struct b200fem_space {
   b200fem_mesh* mesh; int kind, order, numbering, n1, nb; long long size, elements;
   b200fem::BoxDev box;                   // DG: mesh box with ghosts; Lagrange: owned elements only
-  b200fem::Tab1D tab; std::vector<int> perm;
+  b200fem::Tab1D tab; std::vector<int> perm;   // DG: tensor index -> stored local index over the full n1^3 tensor basis (-1: not in the space)
+  bool tensor_full = false;              // DG: the space is the whole 3-D tensor basis (the Kronecker kernels apply)
   b200fem::LagrangeLayoutDev lay; long long* d_lattice_map = nullptr; std::vector<long long> lattice_map;
   int refs = 0; bool released = false;
 };

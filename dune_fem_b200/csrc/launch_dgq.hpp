@@ -28,12 +28,12 @@ template <int N, int MI, int MS> inline int launch_dg_quadrature(b200fem_operato
     auto kern = dg_quadrature_kernel<N, MI, MS, AdrIntegrands>;
     int rc = ensure_smem_attr(ctx, (const void*)kern, Cfg::smem_bytes()); if (rc) return rc;
     AdrIntegrands I; I.m = op->model; I.dim = b.dim; I.with_data = true;
-    kern<<<grid, Cfg::kThreads, Cfg::smem_bytes(), ctx->stream>>>(tab, b, I, op->d_perm, u, w, bvec, n_owned, mass_scale(op));
+    kern<<<grid, Cfg::kThreads, Cfg::smem_bytes(), ctx->stream>>>(tab, b, I, op->d_perm, op->sp->nb, u, w, bvec, n_owned, mass_scale(op));
   } else {
     auto kern = dg_quadrature_kernel<N, MI, MS, AdrIntegrandsHom>;
     int rc = ensure_smem_attr(ctx, (const void*)kern, Cfg::smem_bytes()); if (rc) return rc;
     AdrIntegrandsHom I; I.m = op->model; I.dim = b.dim; I.with_data = false;
-    kern<<<grid, Cfg::kThreads, Cfg::smem_bytes(), ctx->stream>>>(tab, b, I, op->d_perm, u, w, bvec, n_owned, mass_scale(op));
+    kern<<<grid, Cfg::kThreads, Cfg::smem_bytes(), ctx->stream>>>(tab, b, I, op->d_perm, op->sp->nb, u, w, bvec, n_owned, mass_scale(op));
   }
   CUDA_OK(cudaGetLastError());
   op->timing.launches_per_apply = 1;

@@ -133,4 +133,39 @@ inline std::vector<int> legendre_local_permutation(int dim, int order, bool hier
   return perm;
 }
 
+// Number of local dofs of a DG space and the map tensor index -> stored local index over the FULL 3-D tensor basis
+// (t = (m0*n + m1)*n + m2, n = order+1), -1 where the space holds no such function.  The device kernels work on the full
+// tensor-product Legendre basis of the cube; the spaces are sub-bases of it:
+//   Q_k Legendre in 3-D: all n^3 functions (legendre.hh:169-194, hierarchical sort :236-250)
+//   Q_k Legendre in 2-D: the functions that are constant in x2 (m2 = 0); the mesh is one layer of unit-height cells
+//   `dgonb` P_k (orthonormal.hh:55-60, orthonormal/orthonormalbase_{2,3}d.hh): total degree <= k, graded by degree, the
+//   exponent of x0 descending first -- on cubes these ARE products of the orthonormal 1-D Legendre polynomials
+inline std::vector<int> dg_tensor_map(int dim, int order, int kind /* 1 lexicographic, 2 hierarchical, 3 dgonb */, int* nb_out) {
+  const int n = order + 1;
+  std::vector<std::array<int, 3>> stored;
+  if (kind == 3) {
+    for (int p = 0; p <= order; ++p)
+      for (int a = p; a >= 0; --a)
+        for (int b = p - a; b >= 0; --b) {
+          if (dim == 2) { if (a + b == p) stored.push_back({a, b, 0}); }
+          else stored.push_back({a, b, p - a - b});
+        }
+  } else {
+    int nb = 1; for (int d = 0; d < dim; ++d) nb *= n;
+    stored.resize(nb);
+    for (int t = 0; t < nb; ++t) { int z = t; std::array<int, 3> a = {0, 0, 0}; for (int d = dim - 1; d >= 0; --d) { a[d] = z % n; z /= n; } stored[t] = a; }
+    if (kind == 2) {
+      auto key = [&](const std::array<int, 3>& a) { return *std::max_element(a.begin(), a.begin() + dim); };
+      std::stable_sort(stored.begin(), stored.end(), [&](const std::array<int, 3>& a, const std::array<int, 3>& b) {
+        if (key(a) != key(b)) return key(a) < key(b);
+        return std::lexicographical_compare(a.begin(), a.begin() + dim, b.begin(), b.begin() + dim);
+      });
+    }
+  }
+  std::vector<int> map((size_t)n * n * n, -1);
+  for (size_t l = 0; l < stored.size(); ++l) map[(size_t)(stored[l][0] * n + stored[l][1]) * n + stored[l][2]] = (int)l;
+  if (nb_out) *nb_out = (int)stored.size();
+  return map;
+}
+
 }  // namespace b200fem

@@ -1,4 +1,4 @@
-"""Discrete function spaces.  Mirrors dune.fem.space.lagrange / dglegendre (python/dune/fem/space/_spaces.py:106,183-229)."""
+"""Discrete function spaces.  Mirrors dune.fem.space.lagrange / dglegendre / dgonb (python/dune/fem/space/_spaces.py:106,183-229)."""
 import ctypes as C
 
 import numpy as np
@@ -50,3 +50,8 @@ def lagrange(gridView, order=1, numbering=capi.NUMBERING_YASP):
 
 def dglegendre(gridView, order=1, hierarchical=True):
     return DiscreteFunctionSpace(gridView, capi.DG_LEGENDRE_HIER if hierarchical else capi.DG_LEGENDRE, order)
+
+
+def dgonb(gridView, order=1):
+    """orthonormal P_k on cubes -- the space pydemo/advectiondiffusion.py:9 imports (shapefunctionset/orthonormal.hh:55-60)"""
+    return DiscreteFunctionSpace(gridView, capi.DG_ONB, order)

@@ -31,8 +31,10 @@ enum b200fem_status {
   B200FEM_ERR_COMM = -4            /* NCCL / peer access                         */
 };
 
-/* space kinds: python/dune/fem/space/_spaces.py:106 (lagrange), :183-229 (dglegendre, hierarchical flag) */
-enum b200fem_space_kind { B200FEM_LAGRANGE = 0, B200FEM_DG_LEGENDRE = 1, B200FEM_DG_LEGENDRE_HIER = 2 };
+/* space kinds: python/dune/fem/space/_spaces.py:106 (lagrange), :183-229 (dglegendre, hierarchical flag), `dgonb`
+ * (orthonormal P_k, space/shapefunctionset/orthonormal.hh:55-60 -- what pydemo/advectiondiffusion.py:9 imports).  The DG
+ * spaces exist on 2-D and 3-D boxes; Q_k Legendre orders 1..5, dgonb orders 1..4 (PMAX3D of orthonormalbase_3d.hh). */
+enum b200fem_space_kind { B200FEM_LAGRANGE = 0, B200FEM_DG_LEGENDRE = 1, B200FEM_DG_LEGENDRE_HIER = 2, B200FEM_DG_ONB = 3 };
 /* sub-entity numbering of Lagrange dofs: YaspGrid leaf index set or AdaptiveLeafIndexSet first-touch order
  * (gridpart/adaptiveleafindexset.hh:884-906) */
 enum b200fem_numbering { B200FEM_NUMBERING_YASP = 0, B200FEM_NUMBERING_ADAPTIVE_LEAF = 1 };

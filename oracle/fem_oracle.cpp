@@ -167,7 +167,7 @@ struct Mesh {
 // ---------------------------------------------------------------------------
 // Shape function sets on the reference cube
 // ---------------------------------------------------------------------------
-enum SpaceKind { LAGRANGE = 0, DG_LEGENDRE = 1, DG_LEGENDRE_HIER = 2 };
+enum SpaceKind { LAGRANGE = 0, DG_LEGENDRE = 1, DG_LEGENDRE_HIER = 2, DG_ONB = 3 };
 enum Numbering { NUMBERING_YASP = 0, NUMBERING_ADAPTIVE_LEAF = 1 };
 
 struct ShapeFunctionSet {
@@ -175,6 +175,24 @@ struct ShapeFunctionSet {
   std::vector<std::array<int,3>> multiIndex;   // per shape function
   ShapeFunctionSet(int dim_, int order_, int kind_) : dim(dim_), order(order_), kind(kind_) {
     int n1 = order + 1; nb = 1; for (int d = 0; d < dim; ++d) nb *= n1;
+    if (kind == DG_ONB) {
+      // `dgonb`: orthonormal P_k on the cube (space/shapefunctionset/orthonormal.hh:55-60; the functions themselves are the
+      // expanded polynomials of orthonormal/orthonormalbase_{1,2,3}d.hh, eval_line / eval_quadrilateral_2d / eval_hexahedron_3d).
+      // On the cube they are products of the orthonormal 1-D Legendre polynomials of total degree <= k, graded by total
+      // degree; inside a degree the exponent of x0 descends first, then that of x1 (checked against the reference's own
+      // functions in tests/test_reference_pieces.py).
+      multiIndex.clear();
+      for (int p = 0; p <= order; ++p)
+        for (int a = p; a >= 0; --a) {
+          if (dim == 1) { if (a == p) multiIndex.push_back({a, 0, 0}); continue; }
+          for (int b = p - a; b >= 0; --b) {
+            if (dim == 2) { if (a + b == p) multiIndex.push_back({a, b, 0}); continue; }
+            multiIndex.push_back({a, b, p - a - b});
+          }
+        }
+      nb = (int)multiIndex.size();
+      return;
+    }
     multiIndex.resize(nb);
     if (kind == LAGRANGE) {
       // lexicographic lattice numbering, coordinate 0 fastest (lagrange/genericlagrangepoints.hh:862-876)

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ORACLE_DIR = os.path.join(os.path.dirname(_HERE), "oracle")
 _LIB = None
 
-LAGRANGE, DG_LEGENDRE, DG_LEGENDRE_HIER = 0, 1, 2
+LAGRANGE, DG_LEGENDRE, DG_LEGENDRE_HIER, DG_ONB = 0, 1, 2, 3
 NUMBERING_YASP, NUMBERING_ADAPTIVE_LEAF = 0, 1
 
 _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")

@@ -119,3 +119,22 @@ def test_legendre_polynomials_are_the_reference_evaluation():
         for x in xs:
             for deriv in (0, 1):
                 assert ol.lib().fo_legendre(num, x, deriv) == rl.legendre(num, x, deriv), (num, x, deriv)
+
+
+@pytest.mark.parametrize("dim,max_order", [(2, 4), (3, 4)])
+def test_dgonb_shape_functions_are_the_reference_functions(dim, max_order):
+    """The oracle's `dgonb` space (products of orthonormal Legendre polynomials of total degree <= k, graded ordering) against
+    the reference's expanded polynomials eval_/grad_quadrilateral_2d, eval_/grad_hexahedron_3d (orthonormalbase_{2,3}d.hh).
+    Tolerance: the reference evaluates monomial expansions with coefficients up to 1e3 -- rounding only."""
+    rng = np.random.default_rng(7)
+    for order in range(1, max_order + 1):
+        sp = ol.Space([2] * dim, [0.0] * dim, [1.0] * dim, ol.DG_ONB, order)
+        assert sp.local_size == (order + 1) * (order + 2) // 2 if dim == 2 else sp.local_size == (order + 1) * (order + 2) * (order + 3) // 6
+        for _ in range(25):
+            x = np.zeros(3)
+            x[:dim] = rng.uniform(0, 1, dim)
+            phi, dphi = sp.shape(x[:dim])
+            for i in range(sp.local_size):
+                v, g = rl.onb_cube(dim, i, x, grad=True)
+                assert abs(v - phi[i]) < 1e-12 * max(1.0, abs(v))
+                assert np.abs(g - dphi[i, :dim]).max() < 1e-11 * max(1.0, np.abs(g).max())
