@@ -298,10 +298,21 @@ def main():
     for i in range(npairs):
         step(i, linear=False)
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if os.environ.get("B200FEM_BENCH_STEPTIMES"):      # diagnostic: one event pair per step (not a bench value)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+        barrier()
+        evs[0].record(stream)
+        for i in range(args.steps):
+            step(i, False)
+            evs[i + 1].record(stream)
+        barrier()
+        sys.stderr.write("step times (us): " + " ".join(f"{1e3 * evs[i].elapsed_time(evs[i + 1]):.1f}" for i in range(args.steps)) + "\n")
+    if not os.environ.get("B200FEM_BENCH_NOSAMPLER"):
+        sampler.start()
     ms, host_us = timed_loop(lambda i: step(i, False), args.steps)
     sampler.stop_flag = True
-    sampler.join()
+    if sampler.is_alive():
+        sampler.join()
     for i in range(npairs):
         step(i, linear=True)
     ms_linear, _ = timed_loop(lambda i: step(i, True), args.steps)

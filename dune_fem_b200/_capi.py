@@ -95,6 +95,8 @@ def lib():
         "b200fem_dot_dev": [vp, vp, vp, P(dbl)], "b200fem_axpy_dev": [vp, dbl, vp, vp],
         "b200fem_ctx_set_nccl": [vp, vp, C.c_int, C.c_int], "b200fem_nccl_unique_id": [vp],
         "b200fem_nccl_init": [vp, vp, C.c_int, C.c_int], "b200fem_communicate_dev": [vp, vp],
+        "b200fem_operator_create_jit": [vp, C.c_char_p, vp, C.c_int, C.c_int, C.c_int, P(vp)],
+        "b200fem_operator_set_constants": [vp, vp, C.c_int], "b200fem_jit_compile_check": [C.c_char_p, C.c_int, C.c_char_p, C.c_int],
     }
     for name, argtypes in sig.items():
         fn = getattr(L, name)

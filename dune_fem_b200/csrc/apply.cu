@@ -20,6 +20,7 @@ int check_comm_error(b200fem_ctx* c) {
 int apply_local(b200fem_operator* op, const double* u, double* w, bool linear) {
   b200fem_space* s = op->sp; const int N = s->n1;
   op->exchange_fused = false;
+  if (op->jit) return apply_jit(op, u, w, linear);       // run-time compiled integrands: always the generic quadrature kernel
   if (s->kind == B200FEM_LAGRANGE) {
     REQUIRE(!op->model.has_skeleton, B200FEM_ERR_NOT_IMPLEMENTED, "skeleton integrands on continuous spaces");
     REQUIRE(default_quadrature(op), B200FEM_ERR_NOT_IMPLEMENTED, "Lagrange spaces: only quadrature orders that select the (order+1)-point Gauss rule");

@@ -23,8 +23,10 @@
 // and a gradient indexed by a run-time axis, 93 double divisions per thread, 370 KB of code): no run-time indexed
 // register arrays, reciprocal cell sizes, the six faces share one code path whose axis enters through selects.
 #pragma once
+#ifndef __CUDACC_RTC__       // (also compiled at run time by NVRTC for user-supplied integrands, jit.cu: no host headers there)
 #include <cuda_runtime.h>
 #include <cstdint>
+#endif
 #include "integrands.cuh"
 
 namespace b200fem {
@@ -47,8 +49,8 @@ struct QuadTabDev {
   double phi[2][N], dphi[2][N];
 };
 
-constexpr int quad_odd(int x) { return x | 1; }
-constexpr int quad_max(int a, int b) { return a > b ? a : b; }
+__host__ __device__ constexpr int quad_odd(int x) { return x | 1; }
+__host__ __device__ constexpr int quad_max(int a, int b) { return a > b ? a : b; }
 
 template <int N, int MI, int MS> struct DgQuadCfg {
   static constexpr int P = quad_max(N, quad_max(MI, MS)), T2 = P * P;          // threads per element
@@ -67,12 +69,12 @@ template <int N, int MI, int MS> struct DgQuadCfg {
   // a (half-)warp is "same offset, element stride" -- conflict-free whatever the access pattern, because the element stride
   // is odd (kElemDoubles); and the job loops (trip count depends on the lane in the element) do not diverge inside a warp.
   // EB = 16 fills a half-warp; smaller powers of two where 16 elements do not fit ~100 KB / 640 threads.
-  static constexpr int eb_fit() { int eb = 16; while (eb > 1 && (eb * T2 > 640 || (size_t)eb * kElemDoubles * 8 > 100 * 1024)) eb /= 2; return eb; }
+  __host__ __device__ static constexpr int eb_fit() { int eb = 16; while (eb > 1 && (eb * T2 > 640 || (size_t)eb * kElemDoubles * 8 > 100 * 1024)) eb /= 2; return eb; }
   static constexpr int EB = eb_fit();
   static constexpr int kThreads = (EB * T2 + 31) / 32 * 32;
   __device__ static int slot(int tid) { return tid % EB; }
   __device__ static int lane(int tid) { return tid / EB; }     // >= T2 for the padding threads of the last warp
-  static constexpr size_t smem_bytes() { return sizeof(double) * (size_t)EB * kElemDoubles + sizeof(int) * N * N * N * 2 + sizeof(long long) * EB + sizeof(int) * 4 * EB; }
+  __host__ __device__ static constexpr size_t smem_bytes() { return sizeof(double) * (size_t)EB * kElemDoubles + sizeof(int) * N * N * N * 2 + sizeof(long long) * EB + sizeof(int) * 4 * EB; }
 };
 
 template <int N> __device__ __forceinline__ void quad_zero(double (&a)[N]) {
@@ -272,8 +274,8 @@ __device__ __forceinline__ void element_integrals(const QuadTabDev<N, MI, MS>& T
         if (nb_exists) {
           if (I.m.has_skeleton) {
             PointRange rin, rout;
-            if (own_inside) { I.skeleton(d, s ? 1.0 : -1.0, ihe, own, nb, rin, rout); r = rin; }
-            else            { I.skeleton(d, s ? -1.0 : 1.0, ihe, nb, own, rin, rout); r = rout; }
+            if (own_inside) { I.skeleton(xq, d, s ? 1.0 : -1.0, ihe, own, nb, rin, rout); r = rin; }
+            else            { I.skeleton(xq, d, s ? -1.0 : 1.0, ihe, nb, own, rin, rout); r = rout; }
           }
         } else if (I.m.has_boundary && d < box.dim) {         // (a 2-D mesh is one layer of cells: its x2-faces are no boundary)
           r = I.boundary(d, s, ihe, xq, own);

@@ -9,7 +9,9 @@
 // data elsewhere) extended by a reaction term c u + gamma u^3.  The generic quadrature kernel is templated on
 // this struct, so another integrand family is another struct with the same three members.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
+#endif
 #include "../../include/b200fem.h"
 
 namespace b200fem {
@@ -62,7 +64,8 @@ struct AdrIntegrandsT {
   // unit outer normal of the inside element = sign * e_axis; ihe = 1 / he, he = avg(CellVolume)/FacetArea (the caller
   // passes the reciprocal: one division per face instead of one per quadrature point)
   // (the axis may be a run-time value: it selects components, it never indexes a register array)
-  __device__ void skeleton(int axis, double sign, double ihe, const PointValue& in, const PointValue& out,
+  // (x: the face point -- unused by this constant-coefficient family, part of the interface for generic integrands)
+  __device__ void skeleton(const double* x, int axis, double sign, double ihe, const PointValue& in, const PointValue& out,
                            PointRange& rin, PointRange& rout) const {
     const double jump = in.u - out.u;
     const double in_dn = axis == 0 ? in.du[0] : axis == 1 ? in.du[1] : in.du[2], out_dn = axis == 0 ? out.du[0] : axis == 1 ? out.du[1] : out.du[2];

@@ -8,6 +8,7 @@
 //   launch_lagrange.cu  Lagrange lattice kernel, generic quadrature kernels with colour-ordered scatter
 //   solvers.cu          CG / Jacobi-CG / BiCGStab / GMRES drivers, BLAS-1
 //   comm.cu             halo plans, peer-memory mailboxes, NCCL fallback, scalar all-reduce
+//   jit.cu              run-time compiled (NVRTC) integrands in the generic quadrature kernel
 // No CPU compute fallback exists anywhere: every compute entry point needs a CUDA device.
 #pragma once
 #include <cuda.h>
@@ -58,6 +59,7 @@ struct b200fem_space {
   int refs = 0; bool released = false;
 };
 struct MarchMapCache;
+namespace b200fem { struct JitState; }
 struct b200fem_operator {
   b200fem_space* sp; b200fem_model model; int kernel_pref = B200FEM_KERNEL_AUTO; bool communicate = true;
   unsigned q_interior = 0, q_surface = 0; bool inverse_mass = false;
@@ -79,6 +81,7 @@ struct b200fem_operator {
   double* d_lag_rows = nullptr; b200fem::LagKronRows lag_rows{}; std::vector<unsigned char> kron_tab; MarchMapCache* march_cache = nullptr;
   b200fem::HaloPlan halo; b200fem::HaloPlanDG halo_dg; b200fem::HaloPlanP2P halo_p2p; b200fem::HaloPlanAddP2P halo_add;
   const b200fem::BoxDev* active_box = nullptr;   // sub-box override (host-pointer pipeline)
+  b200fem::JitState* jit = nullptr;             // run-time compiled integrands (jit.cu); null: the built-in ADR family
   bool in_bvec = false;                         // the load vector is being computed (data terms on, no recursion into ensure_bvec)
   bool want_exchange = false;                   // apply_dev_impl -> launcher: the Copy exchange of w is due after this apply
   bool exchange_fused = false;                  // launcher -> apply_dev_impl: the kernel did the exchange itself
@@ -112,6 +115,10 @@ int launch_dg_quadrature_any(b200fem_operator* op, const double* u, double* w, c
 int launch_lagrange_quadrature(b200fem_operator* op, const double* u, double* w, bool with_data);
 int launch_lagrange_kronecker(b200fem_operator* op, const double* u, double* w, const double* bvec);
 void free_march_cache(b200fem_operator* op);
+
+// ---- jit.cu ----
+int apply_jit(b200fem_operator* op, const double* u, double* w, bool linear);   // w = L[u] or L[u] - L[0] with compiled integrands
+void jit_free(b200fem_operator* op);
 
 // ---- apply.cu ----
 int apply_local(b200fem_operator* op, const double* u, double* w, bool linear);

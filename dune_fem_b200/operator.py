@@ -111,6 +111,30 @@ class GalerkinOperator:
         return self.model.gamma != 0.0
 
 
+class JitGalerkinOperator(GalerkinOperator):
+    """GalerkinOperator< Integrands > for user-supplied integrands: the reference generates the Integrands class from UFL and
+    compiles the operator for it (python/dune/fem/operator/__init__.py:148-181, models/integrands/model.py); here `source` is
+    CUDA C++ defining interior / skeleton / boundary (include/b200fem.h: b200fem_operator_create_jit), compiled by NVRTC into the
+    generic quadrature kernel.  `constants` play the role of dune.ufl.Constant coefficients (setConstants: no recompilation)."""
+
+    def __init__(self, space, source, constants=(), skeleton=True, boundary=True):
+        self.space = space
+        self.model = None
+        c = np.ascontiguousarray(constants, dtype=np.float64)
+        self.handle = C.c_void_p()
+        capi.check(capi.lib().b200fem_operator_create_jit(space.handle, source.encode(), capi.ptr(c) if len(c) else None, len(c),
+                                                          int(skeleton), int(boundary), C.byref(self.handle)))
+        self._apply_dev = capi.lib().b200fem_operator_apply_dev
+
+    def setConstants(self, constants):
+        c = np.ascontiguousarray(constants, dtype=np.float64)
+        capi.check(capi.lib().b200fem_operator_set_constants(self.handle, capi.ptr(c) if len(c) else None, len(c)))
+
+
+def galerkinJit(space, source, constants=(), skeleton=True, boundary=True):
+    return JitGalerkinOperator(space, source, constants, skeleton, boundary)
+
+
 def galerkin(space, **kwargs):
     return GalerkinOperator(space, **kwargs)
 

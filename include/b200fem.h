@@ -12,7 +12,12 @@
 #ifndef B200FEM_H
 #define B200FEM_H
 
+#ifdef __CUDACC_RTC__   /* the device headers of the library are also compiled at run time (NVRTC has no host headers) */
+typedef signed char int8_t; typedef unsigned char uint8_t; typedef int int32_t; typedef unsigned int uint32_t;
+typedef long long int64_t; typedef unsigned long long uint64_t;
+#else
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -71,6 +76,7 @@ typedef struct b200fem_timing {
   int32_t launches_per_apply;
 } b200fem_timing;
 
+#ifndef __CUDACC_RTC__   /* (the run-time compiled device code only needs the types above) */
 const char* b200fem_last_error(void);
 int b200fem_version(void);
 
@@ -147,6 +153,33 @@ int b200fem_operator_set_inverse_mass(b200fem_operator* op, int on);
  * linearisation.  Works for every model, including the non-linear ones (gamma != 0) that have no Kronecker form. */
 int b200fem_operator_linearize(b200fem_operator* op, const double* u_host, double eps);
 int b200fem_operator_linearize_dev(b200fem_operator* op, const double* u_dev, double eps);
+/* Generic integrands (schemes/integrands.hh:152-375).  The reference JIT-compiles a C++ Integrands class generated from the UFL
+ * form (python/dune/models/integrands/model.py:10-106, python/dune/ufl/codegen.py) into its GalerkinOperator; this entry point
+ * does the same for the device: `source` is CUDA C++ that defines the three integrand functions below, and it is compiled at
+ * run time (NVRTC, sm_100a) INTO the generic quadrature kernel (dg_quadrature.cuh) -- one specialised kernel per operator,
+ * exactly like the reference's one specialised operator class per form.  DG spaces (all kinds), scalar range.
+ *
+ *   struct PointValue { double u; double du[3]; };   // DomainValueType  = (u, grad u) at the quadrature point
+ *   struct PointRange { double s; double F[3]; };    // RangeValueType: tested as  s * phi + F . grad phi
+ *   __device__ void interior(const double* x, const PointValue& u, PointRange& r, const double* c, int dim);
+ *   __device__ void skeleton(const double* x, int axis, double sign, double ihe, const PointValue& in, const PointValue& out,
+ *                            PointRange& rin, PointRange& rout, const double* c, int dim);
+ *   __device__ void boundary(const double* x, int axis, int side, double ihbnd, const PointValue& u, PointRange& r,
+ *                            const double* c, int dim);
+ *
+ * x: physical coordinates of the point; c: the `nconstants` (<= 32) values passed here (the reference's dune.ufl.Constant
+ * coefficients; b200fem_operator_set_constants changes them without recompiling); sign * e_axis is the unit outer normal of
+ * `in` (of the element, for boundary(): sign = side ? +1 : -1); ihe = 1 / he with he = avg(CellVolume) / FacetArea,
+ * ihbnd = FacetArea / CellVolume.  r / rin / rout arrive zeroed.  The functions evaluate the WHOLE integrand, data terms
+ * included: apply = L[u]; apply_linear = L[u] - L[0] (meaningful for integrands that are affine in u; non-linear ones are
+ * solved through b200fem_operator_linearize).  Compile errors: B200FEM_ERR_INVALID with the NVRTC log as the message. */
+int b200fem_operator_create_jit(b200fem_space* space, const char* source, const double* constants, int nconstants,
+                                int has_skeleton, int has_boundary, b200fem_operator** out);
+int b200fem_operator_set_constants(b200fem_operator* op, const double* constants, int nconstants);
+/* Compiles `source` for a Q_order / dgonb space with the default quadrature orders without touching a device (NVRTC only):
+ * 0 when it compiles; the log (NUL-terminated, truncated to log_len) is returned either way.  Host logic, testable on CPU. */
+int b200fem_jit_compile_check(const char* source, int order, char* log, int log_len);
+
 /* strong Dirichlet marks and values (schemes/dirichletconstraints.hh:435-554) */
 int b200fem_operator_dirichlet(b200fem_operator* op, uint8_t* mask_host, double* values_host);
 int b200fem_operator_timing(b200fem_operator* op, b200fem_timing* out);
@@ -213,6 +246,7 @@ int b200fem_nccl_init(b200fem_ctx* ctx, const void* id128, int rank, int world);
 int b200fem_ctx_transport(b200fem_ctx* ctx, int* peer_memory);
 /* exchange the ghost layer of a device dof vector of `space` in place */
 int b200fem_communicate_dev(b200fem_operator* op, double* v_dev);
+#endif /* __CUDACC_RTC__ */
 
 #ifdef __cplusplus
 }

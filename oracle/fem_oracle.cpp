@@ -376,13 +376,22 @@ struct Space {
 //   0: g = f = 0 (homogeneous linear part), 1: g = sin(x0 x1) (pydemo), 2: g = prod sin(pi x_k)
 // f = -eps lap g + b.grad g + c g + gamma g^3 so that g solves the PDE.
 // ---------------------------------------------------------------------------
+struct UserIntegrands;
 struct Model {
+  const UserIntegrands* user = nullptr;   // non-null: callbacks instead of the built-in ADR family
   double eps = 1, b[3] = {0,0,0}, c = 0, gamma = 0, beta = 0;
   int dirichletMask = 0;      // bit (2*axis+side): boundary side carries (weak or strong) Dirichlet data
   int data = 0; int hasSkeleton = 0, hasBoundary = 0, strongDirichlet = 0;
 };
 struct Value { double u; double du[3]; };
 struct Range { double s; double F[3]; };
+// User-supplied integrands (the reference's generated Integrands class, schemes/integrands.hh:152-375): three callbacks with the
+// interface of include/b200fem.h (b200fem_operator_create_jit) -- the tests compile the SAME source text for the host and hand
+// the functions in here.  They evaluate the whole integrand (data terms included).
+typedef void (*UserInterior)(const double* x, const Value* u, Range* r, const double* c, int dim);
+typedef void (*UserSkeleton)(const double* x, int axis, double sign, double ihe, const Value* in, const Value* out, Range* rin, Range* rout, const double* c, int dim);
+typedef void (*UserBoundary)(const double* x, int axis, int side, double ihbnd, const Value* u, Range* r, const double* c, int dim);
+struct UserIntegrands { UserInterior interior = nullptr; UserSkeleton skeleton = nullptr; UserBoundary boundary = nullptr; double c[32] = {}; };
 
 static void dataFunction(int data, int dim, const double* x, double& g, double dg[3], double& lap) {
   g = 0; lap = 0; dg[0] = dg[1] = dg[2] = 0;
@@ -399,6 +408,7 @@ static void dataFunction(int data, int dim, const double* x, double& g, double d
 }
 
 static Range interiorIntegrand(const Model& m, int dim, const double* x, const Value& v) {
+  if (m.user) { Range r; r.s = 0; r.F[0] = r.F[1] = r.F[2] = 0; m.user->interior(x, &v, &r, m.user->c, dim); return r; }
   Range r; double g, dg[3], lap; double f = 0;
   if (m.data) { dataFunction(m.data, dim, x, g, dg, lap); f = -m.eps*lap + m.c*g + m.gamma*g*g*g; for (int d = 0; d < dim; ++d) f += m.b[d]*dg[d]; }
   r.s = m.c*v.u + m.gamma*v.u*v.u*v.u - f;
@@ -406,7 +416,12 @@ static Range interiorIntegrand(const Model& m, int dim, const double* x, const V
   return r;
 }
 // normal = sign * e_axis (outer normal of the inside element)
-static void skeletonIntegrand(const Model& m, int axis, double sign, double he, const Value& in, const Value& out, Range& rIn, Range& rOut) {
+static void skeletonIntegrand(const Model& m, int dim, const double* x, int axis, double sign, double he, const Value& in, const Value& out, Range& rIn, Range& rOut) {
+  if (m.user) {
+    rIn.s = rOut.s = 0; for (int d = 0; d < 3; ++d) rIn.F[d] = rOut.F[d] = 0.0;
+    if (m.user->skeleton) m.user->skeleton(x, axis, sign, 1.0/he, &in, &out, &rIn, &rOut, m.user->c, dim);
+    return;
+  }
   const double jumpU = in.u - out.u;
   const double avgGradN = 0.5*(in.du[axis] + out.du[axis])*sign;
   const double bn = m.b[axis]*sign;
@@ -418,6 +433,7 @@ static void skeletonIntegrand(const Model& m, int axis, double sign, double he, 
 }
 static Range boundaryIntegrand(const Model& m, int dim, int axis, int side, double hbnd, const double* x, const Value& v) {
   Range r; r.s = 0; r.F[0] = r.F[1] = r.F[2] = 0;
+  if (m.user) { if (m.user->boundary) m.user->boundary(x, axis, side, 1.0/hbnd, &v, &r, m.user->c, dim); return r; }
   const double sign = side ? 1.0 : -1.0;
   double g = 0, dg[3] = {0,0,0}, lap = 0;
   if (m.data) dataFunction(m.data, dim, x, g, dg, lap);
@@ -509,14 +525,16 @@ struct Operator {
     }
   }
   // two-sided (wOut != nullptr) and one-sided skeleton integral (galerkin.hh:475-537)
-  void addSkeletonIntegral(int f, Scratch& S, bool twoSided) const {
+  void addSkeletonIntegral(int64_t e, int f, Scratch& S, bool twoSided) const {
     const Mesh& M = sp.mesh; const int axis = f/2, side = f%2; const Tabulation& tIn = sp.face[f]; const Tabulation& tOut = sp.face[f^1];
+    int ec[3]; M.elemCoords(e, ec);
     const double area = M.faceArea(axis), he = M.detJ()/area;   // avg(CellVolume)/FacetArea on a uniform mesh
     evaluateQuadrature(tIn, S.uIn.data(), S.vIn.data());
     evaluateQuadrature(tOut, S.uOut.data(), S.vOut.data());
     for (int q = 0; q < tIn.nop; ++q) {
       const double weight = tIn.w[q]*area;
-      Range rIn, rOut; skeletonIntegrand(model, axis, side ? 1.0 : -1.0, he, S.vIn[q], S.vOut[q], rIn, rOut);
+      double x[3]; for (int d = 0; d < 3; ++d) x[d] = M.lo[d] + M.h[d]*(ec[d] + tIn.x[3*q+d]);
+      Range rIn, rOut; skeletonIntegrand(model, M.dim, x, axis, side ? 1.0 : -1.0, he, S.vIn[q], S.vOut[q], rIn, rOut);
       rIn.s *= weight; rOut.s *= weight; for (int d = 0; d < 3; ++d) { rIn.F[d] *= weight; rOut.F[d] *= weight; }
       axpyPoint(tIn, q, rIn, S.wIn.data());
       if (twoSided) axpyPoint(tOut, q, rOut, S.wOut.data());
@@ -550,11 +568,11 @@ struct Operator {
             const int64_t o = M.elemIndex(nc);
             if (own && !own->contains(nc)) {                                      // ghost neighbour: one-sided
               sp.dofMap(o, S.gOut.data()); for (int i = 0; i < nb; ++i) S.uOut[i] = u[S.gOut[i]];
-              addSkeletonIntegral(f, S, false);
+              addSkeletonIntegral(e, f, S, false);
             } else if (e < o) {                                                   // face owned by the lower index
               sp.dofMap(o, S.gOut.data()); for (int i = 0; i < nb; ++i) S.uOut[i] = u[S.gOut[i]];
               std::fill(S.wOut.begin(), S.wOut.end(), 0.0);
-              addSkeletonIntegral(f, S, true);
+              addSkeletonIntegral(e, f, S, true);
               addLocalDofs(o, S.gOut.data(), S.wOut.data());
             }
           } else if (model.hasBoundary) addBoundaryIntegral(e, f, S);
@@ -793,7 +811,7 @@ using namespace oracle;
 
 struct FoSpace { std::unique_ptr<Space> sp; };
 struct FoOperator {
-  FoSpace* space; std::unique_ptr<Operator> full, linear;
+  FoSpace* space; std::unique_ptr<Operator> full, linear; std::unique_ptr<UserIntegrands> user;
   // AutomaticDifferenceLinearOperator state (operator/common/automaticdifferenceoperator.hh:58-92, set: :152-166)
   std::vector<double> jac_u, jac_op_u; double jac_eps = 0, jac_norm_u = 0; bool jac_set = false;
 };
@@ -822,6 +840,14 @@ FoOperator* fo_operator_create(FoSpace* s, const double* params, const int* ipar
   Model lin = m; lin.data = 0; op->linear.reset(new Operator(*s->sp, lin));   // homogeneous part: g = f = 0
   return op;
 }
+// GalerkinOperator over user-supplied integrands (callbacks); apply(linear) is then L[u] - L[0]
+FoOperator* fo_operator_create_user(FoSpace* s, UserInterior fi, UserSkeleton fs, UserBoundary fb, const double* c, int nc) {
+  FoOperator* op = new FoOperator; op->space = s; op->user.reset(new UserIntegrands);
+  op->user->interior = fi; op->user->skeleton = fs; op->user->boundary = fb; for (int i = 0; i < nc && i < 32; ++i) op->user->c[i] = c[i];
+  Model m; m.user = op->user.get(); m.hasSkeleton = fs != nullptr; m.hasBoundary = fb != nullptr;
+  op->full.reset(new Operator(*s->sp, m)); op->linear.reset(new Operator(*s->sp, m));
+  return op;
+}
 void fo_operator_destroy(FoOperator* op) { delete op; }
 void fo_operator_set_threads(FoOperator* op, int t) { op->full->threads = t; op->linear->threads = t; }
 // MOLGalerkinOperator (schemes/molgalerkin.hh): w = M^-1 L[u]; DG spaces only
@@ -830,7 +856,14 @@ int fo_operator_set_inverse_mass(FoOperator* op, int on) {
   op->full->inverseMass = on != 0; op->linear->inverseMass = on != 0; return 0;
 }
 // L[u] (affine) or its homogeneous part A u (linear != 0)
-void fo_operator_apply(FoOperator* op, const double* u, double* w, int linear) { (linear ? op->linear : op->full)->apply(u, w); }
+void fo_operator_apply(FoOperator* op, const double* u, double* w, int linear) {
+  (linear ? op->linear : op->full)->apply(u, w);
+  if (linear && op->user) {                       // callbacks carry their data terms: A u = L[u] - L[0]
+    const int64_t n = op->space->sp->size; std::vector<double> zero((size_t)n, 0.0), l0((size_t)n);
+    op->full->apply(zero.data(), l0.data());
+    for (int64_t i = 0; i < n; ++i) w[i] -= l0[i];
+  }
+}
 // apply restricted to the owned element box [lo,hi); other elements act as ghosts (rank-local apply)
 void fo_operator_apply_box(FoOperator* op, const double* u, double* w, int linear, const int* lo, const int* hi) {
   Operator::Box b; for (int d = 0; d < 3; ++d) { b.lo[d] = lo[d]; b.hi[d] = hi[d]; }

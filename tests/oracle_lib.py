@@ -52,6 +52,8 @@ def lib():
     L.fo_operator_create.restype = C.c_void_p
     L.fo_operator_create.argtypes = [C.c_void_p, _dp, _ip]
     L.fo_operator_destroy.argtypes = [C.c_void_p]
+    L.fo_operator_create_user.restype = C.c_void_p
+    L.fo_operator_create_user.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _dp, C.c_int]
     L.fo_operator_set_threads.argtypes = [C.c_void_p, C.c_int]
     L.fo_operator_set_inverse_mass.argtypes = [C.c_void_p, C.c_int]
     L.fo_operator_set_inverse_mass.restype = C.c_int
@@ -232,6 +234,40 @@ class Operator:
             lib().fo_operator_destroy(self._h)
         except Exception:
             pass
+
+
+class UserOperator(Operator):
+    """GalerkinOperator over user-supplied integrands: `source` is the text handed to b200fem_operator_create_jit, compiled here
+    for the HOST (g++, __device__ defined away) into three callbacks the oracle integrates."""
+    _PRELUDE = ("#include <cmath>\nusing namespace std;\n#define __device__\n#define __forceinline__ inline\n"
+                "struct PointValue { double u; double du[3]; };\nstruct PointRange { double s; double F[3]; };\nnamespace user {\n")
+    _EPILOGUE = ("\n}\nextern \"C\" {\n"
+                 "void u_interior(const double* x, const PointValue* u, PointRange* r, const double* c, int dim) { user::interior(x, *u, *r, c, dim); }\n"
+                 "#ifdef HAS_SKELETON\nvoid u_skeleton(const double* x, int axis, double sign, double ihe, const PointValue* in, const PointValue* out, PointRange* rin, PointRange* rout, const double* c, int dim) { user::skeleton(x, axis, sign, ihe, *in, *out, *rin, *rout, c, dim); }\n#endif\n"
+                 "#ifdef HAS_BOUNDARY\nvoid u_boundary(const double* x, int axis, int side, double ihbnd, const PointValue* u, PointRange* r, const double* c, int dim) { user::boundary(x, axis, side, ihbnd, *u, *r, c, dim); }\n#endif\n}\n")
+
+    def __init__(self, space, source, constants=(), skeleton=True, boundary=True, threads=1):
+        import hashlib
+        import tempfile
+        self.space = space
+        text = self._PRELUDE + source + self._EPILOGUE
+        tag = hashlib.sha1((text + str(skeleton) + str(boundary)).encode()).hexdigest()[:16]
+        d = os.path.join(tempfile.gettempdir(), "b200fem_oracle_user")
+        os.makedirs(d, exist_ok=True)
+        so = os.path.join(d, f"user_{tag}.so")
+        if not os.path.exists(so):
+            src = os.path.join(d, f"user_{tag}.cpp")
+            with open(src, "w") as f:
+                f.write(text)
+            flags = (["-DHAS_SKELETON"] if skeleton else []) + (["-DHAS_BOUNDARY"] if boundary else [])
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src] + flags)
+        self._user = C.CDLL(so)
+        fn = lambda name, on: C.cast(getattr(self._user, name), C.c_void_p) if on else None
+        c = np.zeros(32)
+        c[:len(constants)] = constants
+        self._h = lib().fo_operator_create_user(space._h, fn("u_interior", True), fn("u_skeleton", skeleton), fn("u_boundary", boundary), c, 32)
+        if threads > 1:
+            lib().fo_operator_set_threads(self._h, threads)
 
 
 def quadrature(dim, order):

@@ -1,0 +1,84 @@
+"""GPU parity of run-time compiled integrands (b200fem_operator_create_jit): a variable-coefficient, non-linear
+advection-diffusion-reaction form that the built-in family cannot express, compiled by NVRTC into the generic quadrature
+kernel -- against the CPU oracle integrating the SAME source text compiled for the host.  Tolerance 1e-12 of max|w|."""
+import os
+
+import numpy as np
+import pytest
+
+import dune_fem_b200 as fem
+from dune_fem_b200 import _capi
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+HERE = os.path.dirname(os.path.abspath(__file__))
+SOURCE = open(os.path.join(HERE, "integrands", "adr_variable.cuh")).read()
+CONST = [0.05, 1.0, -0.5, 0.25, 80.0, 0.3, 0.7]       # k0, b0, b1, b2, penalty, c0, c1 (cubic reaction)
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def spaces(kind, dim, order, n):
+    lo, hi = [-1.0] * dim, [1.0, 0.5, 2.0][:dim]
+    g = fem.structuredGrid(lo, hi, n)
+    if kind == "onb":
+        return fem.space.dgonb(g, order=order), ol.Space(n, lo, hi, ol.DG_ONB, order)
+    return fem.space.dglegendre(g, order=order, hierarchical=True), ol.Space(n, lo, hi, ol.DG_LEGENDRE_HIER, order)
+
+
+@pytest.mark.parametrize("kind,dim,order,n", [("hier", 3, 1, [5, 4, 3]), ("hier", 3, 2, [5, 4, 3]), ("hier", 3, 3, [3, 3, 2]), ("hier", 3, 4, [3, 2, 2]),
+                                              ("hier", 2, 2, [7, 5]), ("onb", 2, 2, [7, 5]), ("onb", 3, 2, [4, 3, 3])])
+def test_compiled_integrands_match_the_oracle(kind, dim, order, n):
+    space, osp = spaces(kind, dim, order, n)
+    const = list(CONST)
+    const[4] = 20.0 * order ** 2
+    op = fem.operator.galerkinJit(space, SOURCE, const)
+    oop = ol.UserOperator(osp, SOURCE, const)
+    u = np.random.default_rng(order + 10 * dim).uniform(-1, 1, space.size)
+    w = np.empty(space.size)
+    op(u, w)
+    assert rel(w, oop.apply(u)) < TOL
+    assert op.timing()["kernel"] == _capi.KERNEL_QUADRATURE
+    # b = -L[0] and the difference L[u] - L[0]
+    assert rel(op.loadVector(), -oop.apply(np.zeros(space.size))) < TOL
+    op.applyLinear(u, w)
+    assert rel(w, oop.apply(u, linear=True)) < 1e-11
+    # constants change without recompilation (dune.ufl.Constant)
+    const[0], const[6] = 0.2, 0.0
+    op.setConstants(const)
+    oop2 = ol.UserOperator(osp, SOURCE, const)
+    op(u, w)
+    assert rel(w, oop2.apply(u)) < TOL
+    # non-default quadrature orders select another compiled kernel
+    if order <= 3 and kind == "hier":
+        op.setQuadratureOrders(2 * order + 2, 2 * order + 2)
+        osp_q = ol.Space(n, [-1.0] * dim, [1.0, 0.5, 2.0][:dim], ol.DG_LEGENDRE_HIER, order, interior_order=2 * order + 2, surface_order=2 * order + 2)
+        op(u, w)
+        assert rel(w, ol.UserOperator(osp_q, SOURCE, const).apply(u)) < TOL
+
+
+def test_compiled_linear_integrands_are_solved_with_gmres():
+    """linear variable-coefficient problem (cubic term off): GMRES on A u = L[u] - L[0] converges to the root of L"""
+    space, osp = spaces("hier", 2, 2, [8, 8])
+    const = list(CONST)
+    const[0], const[4], const[6] = 0.5, 80.0, 0.0
+    op = fem.operator.galerkinJit(space, SOURCE, const)
+    inv = fem.solver.GmresInverseOperator({"tolerance": 1e-11, "maxiterations": 4000, "gmres.restart": 50})
+    inv.bind(op)
+    x = np.zeros(space.size)
+    b = op.loadVector()
+    inv(b, x)
+    assert inv.iterations > 0
+    r = ol.UserOperator(osp, SOURCE, const).apply(x)
+    assert np.abs(r).max() < 1e-8 * np.abs(b).max()
+
+
+def test_compile_error_raises_with_the_log():
+    space, _ = spaces("hier", 3, 1, [2, 2, 2])
+    op = fem.operator.galerkinJit(space, SOURCE + "\n__device__ void broken() { undefined_symbol(); }\n", CONST)
+    with pytest.raises(_capi.B200FemError) as ei:
+        op(np.zeros(space.size), np.empty(space.size))
+    assert "undefined_symbol" in str(ei.value)
