@@ -27,6 +27,12 @@ extern "C" const char* b200fem_last_error(void) { return g_error.c_str(); }
 extern "C" int b200fem_version(void) { return 200; }
 
 // ---------------------------------------------------------------------------------------------------------------
+extern "C" int b200fem_device_count(int* count) {
+  REQUIRE(count, B200FEM_ERR_INVALID, "device_count: null argument");
+  int n = 0; const cudaError_t e = cudaGetDeviceCount(&n); *count = e == cudaSuccess ? n : 0;
+  if (e != cudaSuccess || n == 0) return fail(B200FEM_ERR_CUDA, "no CUDA device available: this library has no CPU fallback");
+  return B200FEM_OK;
+}
 extern "C" int b200fem_ctx_create(int device, void* stream, b200fem_ctx** out) {
   REQUIRE(out, B200FEM_ERR_INVALID, "ctx_create: out is null");
   int count = 0; cudaError_t e = cudaGetDeviceCount(&count);

@@ -81,6 +81,7 @@ const char* b200fem_last_error(void);
 int b200fem_version(void);
 
 /* MPIManager / device selection (misc/mpimanager.hh:352-461).  `stream` may be NULL (own stream) or a cudaStream_t. */
+int b200fem_device_count(int* count);     /* visible CUDA devices (0 and B200FEM_ERR_CUDA when there is none) */
 int b200fem_ctx_create(int device, void* stream, b200fem_ctx** out);
 int b200fem_ctx_destroy(b200fem_ctx* ctx);
 int b200fem_ctx_synchronize(b200fem_ctx* ctx);

@@ -28,3 +28,49 @@ def test_host_mirror_apply_and_cg_on_gpu():
     r = _run()
     assert r.returncode == 0, r.stdout + r.stderr
     assert "host selftest OK" in r.stdout
+
+
+# ---- the reference-side binding dune/fem/schemes/b200galerkin.hh, compiled against stand-in DUNE headers (tests/dune_stub) ----
+EXE2 = os.path.join(ROOT, "dune_fem_b200", "lib", "dune_binding_selftest")
+
+
+def _run2():
+    if not os.path.exists(EXE2):
+        import __graft_entry__
+        __graft_entry__.build()
+    return subprocess.run([EXE2], capture_output=True, text=True, timeout=300)
+
+
+def test_dune_binding_compiles_and_reports_missing_device_as_dune_exception():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    r = _run2()
+    assert r.returncode == 1 and "InvalidStateException" in r.stdout and "no CPU fallback" in r.stdout
+
+
+@pytest.mark.gpu
+def test_dune_binding_apply_and_gmres_match_the_oracle():
+    """B200GalerkinOperator< GeneratedIntegrands, DF > on a dgonb P2 space over an 8x8 mesh, used through Dune::Fem::Operator, and
+    B200KrylovInverseOperator (GMRES): the apply and the solution against the oracle integrating the same source."""
+    import re
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    r = _run2()
+    assert r.returncode == 0, r.stdout + r.stderr
+    src = open(os.path.join(ROOT, "tests", "dune_binding_selftest.cpp")).read()
+    body = "".join(eval(m) for m in re.findall(r'^\s*(?:return\s+)?("(?:[^"\\]|\\.)*")\s*;?\s*$', src[src.index("b200Source"):src.index("int main")], flags=re.M))
+    sp = ol.Space([8, 8], [-1.0, -1.0], [1.0, 1.0], ol.DG_ONB, 2)
+    op = ol.UserOperator(sp, body, [0.5, 0.3, 80.0])
+    u = np.sin(0.37 * np.arange(sp.size))
+    out = dict(line.split(" ", 1) for line in r.stdout.strip().splitlines())
+    ref = float(np.sum(op.apply(u) ** 2))
+    assert abs(float(out["apply_norm2"]) - ref) < 1e-11 * ref
+    # the solution: oracle GMRES on the same system
+    b = -op.apply(np.zeros(sp.size))
+    it, x, _ = op.gmres(b, np.zeros(sp.size), 1e-11, 3000, 0, 40)
+    assert it > 0
+    for i in range(6):
+        assert abs(float(out[f"x{i}"]) - x[i]) < 1e-7 * np.abs(x).max()
