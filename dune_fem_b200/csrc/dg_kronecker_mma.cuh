@@ -33,8 +33,9 @@ struct KronMmaCfg {
   static constexpr int kLand = PX * PY * N3;              // TMA landing buffer: the plane in stored order, dense
   static constexpr int kOut = TX * TY * N3;
   static constexpr int kPlane = (PY * RS * ES + 15) / 16 * 16;   // doubles (128-byte multiple)
-  // [landing | out | b tile | plane | perm, poff | 2 mbarriers]
-  static constexpr size_t smem_bytes() { return sizeof(double) * (size_t)(kLand + 2 * kOut + kPlane) + sizeof(int) * 2 * N3 + 16 + 128; }
+  static constexpr int kQ = ((TY - 1) * RS + TX) * ES;           // finished plane in the fragment layout (owned elements only)
+  // [landing | out | b tile | plane | q | 2 mbarriers]
+  static constexpr size_t smem_bytes() { return sizeof(double) * (size_t)(kLand + 2 * kOut + kPlane + kQ) + 16 + 128; }
   // offset of (a, b, c = 0 | 2) inside an element: 16-byte chunks, chunk = (c >> 1) * 16 + ((a * 4 + b) ^ ((a >> 1) << 1))
   __host__ __device__ static constexpr int eoff(int a, int b, int chalf) { return 2 * (chalf * 16 + ((a * 4 + b) ^ ((a >> 1) << 1))); }
 };
@@ -42,6 +43,12 @@ struct KronMmaCfg {
 // tensor maps of one launch: u over the local box [z][y][x][64] (box 64 x 10 x 10 x 1, out-of-bounds = zero = missing neighbour),
 // w and b over the OWNED sub-box (box 64 x 8 x 8 x 1: stores are clipped to the owned range by the TMA unit)
 struct KronMmaMaps { CUtensorMap u_plane, w_tile, b_tile; };
+// The stored (hierarchical) dof order is a permutation of the tensor order the fragments use.  Both re-layout passes (landing buffer
+// -> fragment layout, finished plane -> stored order) move one 8-byte word per lane between a dense element (bank = dof % 16) and
+// the swizzled element (bank = offset % 16): `dof[i]` assigns dofs to lanes such that every half-warp touches 16 different banks on
+// BOTH sides (the 64 (source bank, destination bank) pairs form a 4-regular bipartite multigraph; it splits into four perfect
+// matchings, one per half-warp of the two passes -- computed on the host).  off[i] = offset of dof[i] inside a swizzled element.
+struct KronMmaOrder { int dof[64], off[64]; };
 
 __device__ __forceinline__ void dmma884(double (&d)[2], const double a, const double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
@@ -50,7 +57,7 @@ __device__ __forceinline__ void dmma884(double (&d)[2], const double a, const do
 template <bool HAS_B>
 __global__ void __launch_bounds__(KronMmaCfg::kThreads, 1)
 dg_kronecker_mma_kernel(const __grid_constant__ KronTabDev<4> K, const __grid_constant__ BoxDev box, const __grid_constant__ KronMmaMaps M,
-                        const int* __restrict__ perm_g, const int tx, const int ty) {
+                        const __grid_constant__ KronMmaOrder O, const int tx, const int ty, long long* __restrict__ dbg) {
   using Cfg = KronMmaCfg;
   constexpr int N = 4, N3 = 64, ES = Cfg::ES, RS = Cfg::RS;
   extern __shared__ unsigned char mma_smem_raw[];
@@ -61,16 +68,12 @@ dg_kronecker_mma_kernel(const __grid_constant__ KronTabDev<4> K, const __grid_co
   double* const OUT = LND + Cfg::kLand;                              // finished plane: [oy][ox][stored order], leaves by TMA store
   double* const BT = OUT + Cfg::kOut;                                // load-vector tile of the plane that leaves next
   double* const P = BT + Cfg::kOut;                                  // plane z of u: [ey'][ex' (RS)][swizzled tensor order (ES)]
-  int* const perm = reinterpret_cast<int*>(P + Cfg::kPlane);         // tensor index -> stored index
-  int* const poff = perm + N3;                                       // stored index -> offset inside a P element
-  const uint32_t bar_l = ptx::smem_addr(poff + N3), bar_b = bar_l + 8;
+  double* const Q = P + Cfg::kPlane;                                 // finished plane, fragment layout: [oy][ox (RS)][swizzled (ES)]
+  const uint32_t bar_l = ptx::smem_addr(Q + Cfg::kQ), bar_b = bar_l + 8;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-  for (int i = tid; i < N3; i += Cfg::kThreads) {
-    const int p = perm_g[i]; perm[i] = p;
-    const int a = i >> 4, b = (i >> 2) & 3, c = i & 3;
-    poff[p] = Cfg::eoff(a, b, c >> 1) + (c & 1);
-  }
+  // the two dofs this lane moves in the re-layout passes (see KronMmaOrder)
+  const int rl_j0 = O.dof[lane], rl_j1 = O.dof[32 + lane], rl_o0 = O.off[lane], rl_o1 = O.off[32 + lane];
 
   // ---- operator fragments (constant over the kernel) ----
   // x-axis, A operand: row g = (ex, a), column t = a'  of  [L S R 0; 0 L S R]  for the four source elements s = 0 .. 3
@@ -93,14 +96,9 @@ dg_kronecker_mma_kernel(const __grid_constant__ KronTabDev<4> K, const __grid_co
   const long long s1 = total * (blockIdx.x + 1) / gridDim.x;
   if (tid == 0) { ptx::mbar_init(bar_l, 1); ptx::mbar_init(bar_b, 1); ptx::fence_barrier_init(); ptx::prefetch_tensormap(&M.u_plane); ptx::prefetch_tensormap(&M.w_tile); if (HAS_B) ptx::prefetch_tensormap(&M.b_tile); }
   unsigned n_l = 0, n_b = 0;                       // completed waits on the two barriers (their phase parities)
+  long long tph[6] = {0, 0, 0, 0, 0, 0}, tlast = clock64();   // diagnostics (dbg != nullptr): cycles per phase seen by one thread
+  auto stamp = [&](int i) { if (dbg) { const long long now = clock64(); tph[i] += now - tlast; tlast = now; } };
   __syncthreads();
-  // per-thread constants of the staging pass and of the output pass (the lane's dofs are the same in every patch and plane)
-  const int st_o0 = poff[2 * (tid & 31)], st_o1 = poff[2 * (tid & 31) + 1];
-  int pm[2][4];
-#pragma unroll
-  for (int r = 0; r < 2; ++r)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) pm[r][c] = perm[(g & 3) * 16 + ((2 * t + r) & 3) * 4 + c];
 
   while (s0 < s1) {
     const int col = (int)(s0 / on2), za = (int)(s0 % on2), zb = (int)min((long long)on2, za + (s1 - s0));
@@ -122,21 +120,25 @@ dg_kronecker_mma_kernel(const __grid_constant__ KronTabDev<4> K, const __grid_co
     for (int zl = zfirst; zl <= zlast; ++zl) {
       // ---- plane zl (with its x/y halo; elements outside the local box arrive as zeros = missing neighbours) has landed in stored
       //      order: re-lay it into the swizzled tensor order the fragment loads want ----
+      stamp(5);
       ptx::mbar_wait(bar_l, n_l & 1u); ++n_l;
+      stamp(0);
       {
-        // item idx = tid + 256 k: element pe = (tid >> 5) + 8 k of the plane, dof pair j = 2 (tid & 31) -- the same pair for every k
-        constexpr int kItems = (Cfg::PX * Cfg::PY * (N3 / 2) + Cfg::kThreads - 1) / Cfg::kThreads;
-        double2 v[kItems];
+        // warp w re-lays the elements pe = w, w + 8, ...: two 8-byte words per lane and element, conflict-free on both sides
+        constexpr int kItems = (Cfg::PX * Cfg::PY + Cfg::kWarps - 1) / Cfg::kWarps;
+        double v0[kItems], v1[kItems];
 #pragma unroll
-        for (int k = 0; k < kItems; ++k) if (tid + k * Cfg::kThreads < Cfg::PX * Cfg::PY * (N3 / 2)) v[k] = *reinterpret_cast<const double2*>(LND + 2 * (tid + k * Cfg::kThreads));
+        for (int k = 0; k < kItems; ++k) { const int pe = warp + Cfg::kWarps * k; if (pe < Cfg::PX * Cfg::PY) { v0[k] = LND[pe * N3 + rl_j0]; v1[k] = LND[pe * N3 + rl_j1]; } }
 #pragma unroll
         for (int k = 0; k < kItems; ++k) {
-          const int pe = (tid >> 5) + 8 * k, ey = pe / Cfg::PX, ex = pe - ey * Cfg::PX;
-          if (tid + k * Cfg::kThreads < Cfg::PX * Cfg::PY * (N3 / 2)) { double* const pel = P + (ey * RS + ex) * ES; pel[st_o0] = v[k].x; pel[st_o1] = v[k].y; }
+          const int pe = warp + Cfg::kWarps * k, ey = pe / Cfg::PX, ex = pe - ey * Cfg::PX;
+          if (pe < Cfg::PX * Cfg::PY) { double* const pel = P + (ey * RS + ex) * ES; pel[rl_o0] = v0[k]; pel[rl_o1] = v1[k]; }
         }
       }
+      stamp(1);
       if (tid == 0) ptx::bulk_wait_read();            // the previous plane's TMA store has read OUT
       __syncthreads();
+      stamp(2);
       if (tid == 0 && zl < zlast) {                   // next plane of u, under this plane's arithmetic
         ptx::fence_proxy_async();
         ptx::mbar_expect_tx(bar_l, 8u * Cfg::kLand); ptx::tma_load_4d(ptx::smem_addr(LND), &M.u_plane, 0, x0 - 1, y0 - 1, zl + 1, bar_l);
@@ -237,18 +239,15 @@ dg_kronecker_mma_kernel(const __grid_constant__ KronTabDev<4> K, const __grid_co
             }
           }
         }
-        // ---- plane zl-1 is complete: into the staging buffer in stored order (minus the load vector); rotate the accumulators ----
+        // ---- plane zl-1 is complete: into Q in the fragment layout (16-byte stores, conflict-free); rotate the accumulators ----
         {
-          const bool out_plane = zl - 1 >= box.own_lo[2] + za;
-          if (HAS_B && q == 0 && out_plane) ptx::mbar_wait(bar_b, n_b & 1u);
-          const int ox = 2 * pxi + (g >> 2);
-          if (out_plane) {
+          if (zl - 1 >= box.own_lo[2] + za) {
+            double* const qel = Q + ((2 * pyi + (t >> 1)) * RS + 2 * pxi + (g >> 2)) * ES;
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
-              const int colr = 2 * t + r, oy = 2 * pyi + (colr >> 2);
-              const int eb = (oy * Cfg::TX + ox) * N3;
-#pragma unroll
-              for (int c = 0; c < 4; ++c) { const int o = eb + pm[r][c]; OUT[o] = HAS_B ? accm[q][c][r] - BT[o] : accm[q][c][r]; }
+              const int o = Cfg::eoff(g & 3, 2 * (t & 1) + r, 0);
+              *reinterpret_cast<double2*>(qel + o) = make_double2(accm[q][0][r], accm[q][1][r]);
+              *reinterpret_cast<double2*>(qel + o + 32) = make_double2(accm[q][2][r], accm[q][3][r]);
             }
           }
 #pragma unroll
@@ -257,9 +256,24 @@ dg_kronecker_mma_kernel(const __grid_constant__ KronTabDev<4> K, const __grid_co
             for (int r = 0; r < 2; ++r) { accm[q][c][r] = acc0[q][c][r]; acc0[q][c][r] = accp[q][c][r]; accp[q][c][r] = 0.0; }
         }
       }
+      stamp(3);
       const bool out_plane = zl - 1 >= box.own_lo[2] + za;
-      if (out_plane) { if (HAS_B) ++n_b; ptx::fence_proxy_async(); }        // generic writes of OUT -> visible to the TMA store
       __syncthreads();
+      // ---- fragment layout -> stored order (dense, what the TMA store wants), minus the load vector ----
+      if (out_plane) {
+        if (HAS_B) { ptx::mbar_wait(bar_b, n_b & 1u); ++n_b; }
+#pragma unroll
+        for (int k = 0; k < Cfg::TX * Cfg::TY / Cfg::kWarps; ++k) {
+          const int eo = warp + Cfg::kWarps * k, oy = eo >> 3, ox = eo & 7;
+          const double* const qel = Q + (oy * RS + ox) * ES;
+          double a0 = qel[rl_o0], a1 = qel[rl_o1];
+          if (HAS_B) { a0 -= BT[eo * N3 + rl_j0]; a1 -= BT[eo * N3 + rl_j1]; }
+          OUT[eo * N3 + rl_j0] = a0; OUT[eo * N3 + rl_j1] = a1;
+        }
+        ptx::fence_proxy_async();                     // generic writes of OUT -> visible to the TMA store
+      }
+      __syncthreads();
+      stamp(4);
       // ---- plane zl-1 leaves by one TMA store (clipped to the owned range); its successor's load-vector tile is requested ----
       if (tid == 0 && out_plane) {
         const int zo = zl - 1 - box.own_lo[2];
@@ -271,6 +285,7 @@ dg_kronecker_mma_kernel(const __grid_constant__ KronTabDev<4> K, const __grid_co
     __syncthreads();
   }
   if (tid == 0) ptx::bulk_wait_all();
+  if (dbg && blockIdx.x == 1 && (tid == 0 || tid == 255)) { for (int i = 0; i < 6; ++i) dbg[(tid ? 8 : 0) + i] = tph[i]; dbg[(tid ? 8 : 0) + 6] = n_l; }
   (void)on0; (void)on1;
 }
 

@@ -1,6 +1,9 @@
 // launch_slab.cu -- host side of the slab Kronecker DG kernel for Q3..Q5 (dg_kronecker_slab.cuh)
 #include <algorithm>
 
+#include <cstdio>
+#include <functional>
+#include <vector>
 #include <cstdlib>
 
 #include "dg_kronecker_mma.cuh"
@@ -46,6 +49,36 @@ static bool ensure_encode_tiled_q3() {
   g_encode_tiled_q3 = (EncodeTiledQ3Fn)fn; return true;
 }
 
+// KronMmaOrder (dg_kronecker_mma.cuh): split the 64 dofs of an element into four groups of 16 such that inside a group all source banks
+// (dof % 16) and all destination banks (swizzled offset % 16) are different -- four perfect matchings of a 4-regular bipartite
+// multigraph on 16 + 16 banks, found by augmenting paths
+static KronMmaOrder make_mma_order(const std::vector<int>& perm) {
+  int off_of[64];                                      // stored dof -> offset inside a swizzled element
+  for (int i = 0; i < 64; ++i) { const int a = i >> 4, b = (i >> 2) & 3, c = i & 3; off_of[perm[(size_t)i]] = KronMmaCfg::eoff(a, b, c >> 1) + (c & 1); }
+  std::vector<int> left(64); for (int j = 0; j < 64; ++j) left[(size_t)j] = j;        // remaining edges (dofs)
+  KronMmaOrder O;
+  for (int m = 0; m < 4; ++m) {
+    int match_r[16]; std::fill(match_r, match_r + 16, -1);                               // destination bank -> edge
+    for (int l = 0; l < 16; ++l) {
+      bool seen[16] = {};
+      std::function<bool(int)> aug = [&](int lb) {
+        for (int e : left) {
+          if (e % 16 != lb) continue;
+          const int rb = off_of[e] % 16; if (seen[rb]) continue; seen[rb] = true;
+          if (match_r[rb] < 0 || aug(match_r[rb] % 16)) { match_r[rb] = e; return true; }
+        }
+        return false;
+      };
+      aug(l);
+    }
+    for (int r = 0; r < 16; ++r) {
+      const int e = match_r[r]; O.dof[m * 16 + r] = e; O.off[m * 16 + r] = off_of[e];
+      left.erase(std::find(left.begin(), left.end(), e));
+    }
+  }
+  return O;
+}
+
 // Q3 on the FP64 tensor cores (dg_kronecker_mma.cuh): persistent CTAs, one per SM, each marching through its share of the
 // (8 x 8 column, z) plane steps
 static int launch_mma_q3(b200fem_operator* op, const double* u, double* w, const double* bvec) {
@@ -78,8 +111,15 @@ static int launch_mma_q3(b200fem_operator* op, const double* u, double* w, const
   auto kern = bvec ? dg_kronecker_mma_kernel<true> : dg_kronecker_mma_kernel<false>;
   int rc = ensure_smem_attr(ctx, (const void*)kern, Cfg::smem_bytes()); if (rc) return rc;
   const unsigned grid = (unsigned)std::max(1ll, std::min<long long>(steps, ctx->sms));
-  kern<<<grid, Cfg::kThreads, Cfg::smem_bytes(), ctx->stream>>>(K, b, M, op->d_perm, tx, ty);
+  static long long* d_dbg = nullptr; static const bool want_dbg = std::getenv("B200FEM_MMA_TIMELINE") != nullptr;   // diagnostics only
+  if (want_dbg && !d_dbg) { CUDA_OK(cudaMalloc(&d_dbg, 16 * sizeof(long long))); CUDA_OK(cudaMemset(d_dbg, 0, 16 * sizeof(long long))); }
+  kern<<<grid, Cfg::kThreads, Cfg::smem_bytes(), ctx->stream>>>(K, b, M, make_mma_order(op->sp->perm), tx, ty, want_dbg ? d_dbg : nullptr);
   CUDA_OK(cudaGetLastError());
+  if (want_dbg) {
+    long long h[16]; CUDA_OK(cudaStreamSynchronize(ctx->stream)); CUDA_OK(cudaMemcpy(h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int w2 = 0; w2 < 2; ++w2) { const long long* t = h + 8 * w2; const double n = (double)std::max(1ll, t[6]);
+      std::fprintf(stderr, "[mma timeline, CTA 1 thread %d, clocks per plane step over %lld steps] wait u %.0f | stage %.0f | sync %.0f | compute+out %.0f | sync %.0f | store/issue %.0f\n", w2 ? 255 : 0, t[6], t[0] / n, t[1] / n, t[2] / n, t[3] / n, t[4] / n, t[5] / n); }
+  }
   op->timing.launches_per_apply = 1;
   return B200FEM_OK;
 }
