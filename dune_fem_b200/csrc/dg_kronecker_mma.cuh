@@ -26,22 +26,26 @@
 
 namespace b200fem {
 
-struct KronMmaCfg {
-  static constexpr int N = 4, N3 = 64, TX = 8, TY = 8, kThreads = 256, kWarps = 8;
+// TY_ rows of elements per column tile, two 2 x 2 patches per warp: TY_ = 8 -> 8 warps, one CTA per SM; TY_ = 4 -> 4 warps, TWO CTAs
+// per SM that run out of phase (one CTA's shared-memory-bound re-layout passes under the other's tensor-core phase)
+template <int TY_> struct KronMmaCfgT {
+  static constexpr int N = 4, N3 = 64, TX = 8, TY = TY_, kWarps = TX * TY_ / 8, kThreads = 32 * kWarps, kCtasPerSm = 8 / kWarps;
   static constexpr int PX = TX + 2, PY = TY + 2;          // plane incl. halo
   static constexpr int ES = 66, RS = 11;                  // element stride (doubles), row stride (elements): see the header
   static constexpr int kLand = PX * PY * N3;              // TMA landing buffer: the plane in stored order, dense
   static constexpr int kOut = TX * TY * N3;
   static constexpr int kPlane = (PY * RS * ES + 15) / 16 * 16;   // doubles (128-byte multiple)
   static constexpr int kQ = ((TY - 1) * RS + TX) * ES;           // finished plane in the fragment layout (owned elements only)
-  // [landing | out | b tile | plane | q | 2 mbarriers]
-  static constexpr size_t smem_bytes() { return sizeof(double) * (size_t)(kLand + 2 * kOut + kPlane + kQ) + 16 + 128; }
+  // [landing | out (the load-vector tile lands here first) | plane | q | 2 mbarriers]
+  static constexpr size_t smem_bytes() { return sizeof(double) * (size_t)(kLand + kOut + kPlane + kQ) + 16 + 128; }
   // offset of (a, b, c = 0 | 2) inside an element: 16-byte chunks, chunk = (c >> 1) * 16 + ((a * 4 + b) ^ ((a >> 1) << 1))
   __host__ __device__ static constexpr int eoff(int a, int b, int chalf) { return 2 * (chalf * 16 + ((a * 4 + b) ^ ((a >> 1) << 1))); }
 };
 
 // tensor maps of one launch: u over the local box [z][y][x][64] (box 64 x 10 x 10 x 1, out-of-bounds = zero = missing neighbour),
 // w and b over the OWNED sub-box (box 64 x 8 x 8 x 1: stores are clipped to the owned range by the TMA unit)
+using KronMmaCfg = KronMmaCfgT<4>;
+
 struct KronMmaMaps { CUtensorMap u_plane, w_tile, b_tile; };
 // The stored (hierarchical) dof order is a permutation of the tensor order the fragments use.  Both re-layout passes (landing buffer
 // -> fragment layout, finished plane -> stored order) move one 8-byte word per lane between a dense element (bank = dof % 16) and
@@ -54,20 +58,20 @@ __device__ __forceinline__ void dmma884(double (&d)[2], const double a, const do
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
 }
 
-template <bool HAS_B>
-__global__ void __launch_bounds__(KronMmaCfg::kThreads, 1)
+template <bool HAS_B, int TY_>
+__global__ void __launch_bounds__(KronMmaCfgT<TY_>::kThreads, KronMmaCfgT<TY_>::kCtasPerSm)
 dg_kronecker_mma_kernel(const __grid_constant__ KronTabDev<4> K, const __grid_constant__ BoxDev box, const __grid_constant__ KronMmaMaps M,
                         const __grid_constant__ KronMmaOrder O, const int tx, const int ty, long long* __restrict__ dbg) {
-  using Cfg = KronMmaCfg;
+  using Cfg = KronMmaCfgT<TY_>;
   constexpr int N = 4, N3 = 64, ES = Cfg::ES, RS = Cfg::RS;
   extern __shared__ unsigned char mma_smem_raw[];
   // TMA wants 128-byte alignment.  (An offset added to the shared symbol keeps the accesses LDS / STS; a round trip of the pointer
   // through an integer would turn every one of them into a generic LD / ST.)
   unsigned char* const mma_smem = mma_smem_raw + ((128u - (ptx::smem_addr(mma_smem_raw) & 127u)) & 127u);
   double* const LND = reinterpret_cast<double*>(mma_smem);          // landing buffer of the TMA load: plane in stored order
-  double* const OUT = LND + Cfg::kLand;                              // finished plane: [oy][ox][stored order], leaves by TMA store
-  double* const BT = OUT + Cfg::kOut;                                // load-vector tile of the plane that leaves next
-  double* const P = BT + Cfg::kOut;                                  // plane z of u: [ey'][ex' (RS)][swizzled tensor order (ES)]
+  double* const OUT = LND + Cfg::kLand;                              // finished plane: [oy][ox][stored order], leaves by TMA store;
+                                                                     // the load-vector tile of that plane is loaded into it beforehand
+  double* const P = OUT + Cfg::kOut;                                 // plane z of u: [ey'][ex' (RS)][swizzled tensor order (ES)]
   double* const Q = P + Cfg::kPlane;                                 // finished plane, fragment layout: [oy][ox (RS)][swizzled (ES)]
   const uint32_t bar_l = ptx::smem_addr(Q + Cfg::kQ), bar_b = bar_l + 8;
 
@@ -115,7 +119,7 @@ dg_kronecker_mma_kernel(const __grid_constant__ KronTabDev<4> K, const __grid_co
     const int ox0 = x0 - box.own_lo[0], oy0 = y0 - box.own_lo[1];          // tile origin in the owned sub-box (w / b tensor maps)
     if (tid == 0) {
       ptx::mbar_expect_tx(bar_l, 8u * Cfg::kLand); ptx::tma_load_4d(ptx::smem_addr(LND), &M.u_plane, 0, x0 - 1, y0 - 1, zfirst, bar_l);
-      if (HAS_B) { ptx::mbar_expect_tx(bar_b, 8u * Cfg::kOut); ptx::tma_load_4d(ptx::smem_addr(BT), &M.b_tile, 0, ox0, oy0, za, bar_b); }
+      if (HAS_B) { ptx::mbar_expect_tx(bar_b, 8u * Cfg::kOut); ptx::tma_load_4d(ptx::smem_addr(OUT), &M.b_tile, 0, ox0, oy0, za, bar_b); }
     }
     for (int zl = zfirst; zl <= zlast; ++zl) {
       // ---- plane zl (with its x/y halo; elements outside the local box arrive as zeros = missing neighbours) has landed in stored
@@ -267,7 +271,7 @@ dg_kronecker_mma_kernel(const __grid_constant__ KronTabDev<4> K, const __grid_co
           const int eo = warp + Cfg::kWarps * k, oy = eo >> 3, ox = eo & 7;
           const double* const qel = Q + (oy * RS + ox) * ES;
           double a0 = qel[rl_o0], a1 = qel[rl_o1];
-          if (HAS_B) { a0 -= BT[eo * N3 + rl_j0]; a1 -= BT[eo * N3 + rl_j1]; }
+          if (HAS_B) { a0 -= OUT[eo * N3 + rl_j0]; a1 -= OUT[eo * N3 + rl_j1]; }
           OUT[eo * N3 + rl_j0] = a0; OUT[eo * N3 + rl_j1] = a1;
         }
         ptx::fence_proxy_async();                     // generic writes of OUT -> visible to the TMA store
@@ -278,14 +282,17 @@ dg_kronecker_mma_kernel(const __grid_constant__ KronTabDev<4> K, const __grid_co
       if (tid == 0 && out_plane) {
         const int zo = zl - 1 - box.own_lo[2];
         ptx::tma_store_4d(&M.w_tile, 0, ox0, oy0, zo, ptx::smem_addr(OUT)); ptx::bulk_commit();
-        if (HAS_B && zl < zlast) { ptx::mbar_expect_tx(bar_b, 8u * Cfg::kOut); ptx::tma_load_4d(ptx::smem_addr(BT), &M.b_tile, 0, ox0, oy0, zo + 1, bar_b); }
+        if (HAS_B && zl < zlast) {                    // the next plane's load-vector tile, into OUT once the store has read it
+          ptx::bulk_wait_read();
+          ptx::mbar_expect_tx(bar_b, 8u * Cfg::kOut); ptx::tma_load_4d(ptx::smem_addr(OUT), &M.b_tile, 0, ox0, oy0, zo + 1, bar_b);
+        }
       }
     }
     if (tid == 0) ptx::bulk_wait_read();
     __syncthreads();
   }
   if (tid == 0) ptx::bulk_wait_all();
-  if (dbg && blockIdx.x == 1 && (tid == 0 || tid == 255)) { for (int i = 0; i < 6; ++i) dbg[(tid ? 8 : 0) + i] = tph[i]; dbg[(tid ? 8 : 0) + 6] = n_l; }
+  if (dbg && blockIdx.x == 1 && (tid == 0 || tid == Cfg::kThreads - 1)) { for (int i = 0; i < 6; ++i) dbg[(tid ? 8 : 0) + i] = tph[i]; dbg[(tid ? 8 : 0) + 6] = n_l; }
   (void)on0; (void)on1;
 }
 

@@ -108,9 +108,9 @@ static int launch_mma_q3(b200fem_operator* op, const double* u, double* w, const
     };
     REQUIRE(enc(&M.u_plane, u, du, bu) && enc(&M.w_tile, w + own_off, dw, bw) && enc(&M.b_tile, (bvec ? bvec : w) + own_off, dw, bw), B200FEM_ERR_CUDA, "cuTensorMapEncodeTiled failed (Q3 tensor-core kernel)");
   }
-  auto kern = bvec ? dg_kronecker_mma_kernel<true> : dg_kronecker_mma_kernel<false>;
+  auto kern = bvec ? dg_kronecker_mma_kernel<true, Cfg::TY> : dg_kronecker_mma_kernel<false, Cfg::TY>;
   int rc = ensure_smem_attr(ctx, (const void*)kern, Cfg::smem_bytes()); if (rc) return rc;
-  const unsigned grid = (unsigned)std::max(1ll, std::min<long long>(steps, ctx->sms));
+  const unsigned grid = (unsigned)std::max(1ll, std::min<long long>(steps, (long long)ctx->sms * Cfg::kCtasPerSm));
   static long long* d_dbg = nullptr; static const bool want_dbg = std::getenv("B200FEM_MMA_TIMELINE") != nullptr;   // diagnostics only
   if (want_dbg && !d_dbg) { CUDA_OK(cudaMalloc(&d_dbg, 16 * sizeof(long long))); CUDA_OK(cudaMemset(d_dbg, 0, 16 * sizeof(long long))); }
   kern<<<grid, Cfg::kThreads, Cfg::smem_bytes(), ctx->stream>>>(K, b, M, make_mma_order(op->sp->perm), tx, ty, want_dbg ? d_dbg : nullptr);
