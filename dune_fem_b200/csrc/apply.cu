@@ -43,7 +43,7 @@ int apply_local(b200fem_operator* op, const double* u, double* w, bool linear) {
   }
   // The Kronecker form rests on the default rules (the (k+1)-point Gauss rules integrate the 1-D mass matrices of the
   // orthonormal basis exactly); other quadrature orders (setQuadratureOrders) go through the generic quadrature kernel
-  const bool kron_ok = op->model.gamma == 0.0 && N >= 2 && N <= 6 && s->tensor_full && default_quadrature(op);
+  const bool kron_ok = op->model.gamma == 0.0 && N >= 2 && N <= 6 && s->tensor_full && s->box.periodic == 0 && default_quadrature(op);
   int kernel = op->kernel_pref;
   if (kernel == B200FEM_KERNEL_AUTO) kernel = kron_ok ? B200FEM_KERNEL_KRONECKER : B200FEM_KERNEL_QUADRATURE;
   int rc;

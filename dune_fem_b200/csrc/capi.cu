@@ -84,7 +84,7 @@ static int make_mesh(b200fem_ctx* ctx, int dim, const int32_t* n, const double* 
   }
   if (rank < 0 || rank >= world) { delete m; return fail(B200FEM_ERR_INVALID, "mesh: rank outside process grid"); }
   m->pc[0] = rank % m->proc[0]; m->pc[1] = (rank / m->proc[0]) % m->proc[1]; m->pc[2] = rank / (m->proc[0] * m->proc[1]);
-  BoxDev& b = m->box; b.dim = dim;
+  BoxDev& b = m->box; b.dim = dim; b.periodic = 0;
   for (int d = 0; d < 3; ++d) {
     // block distribution: the first (gn % proc) ranks along an axis get one extra cell
     const int q = m->gn[d] / m->proc[d], r = m->gn[d] % m->proc[d], c = m->pc[d];
@@ -96,6 +96,13 @@ static int make_mesh(b200fem_ctx* ctx, int dim, const int32_t* n, const double* 
   }
   ctx->refs += 1;
   *out = m; return B200FEM_OK;
+}
+extern "C" int b200fem_mesh_set_periodic(b200fem_mesh* m, int mask) {
+  REQUIRE(m && mask >= 0 && mask < (1 << m->dim), B200FEM_ERR_INVALID, "mesh_set_periodic: bad argument");
+  REQUIRE(m->refs == 0, B200FEM_ERR_INVALID, "mesh_set_periodic: spaces already exist on this mesh");
+  REQUIRE(mask == 0 || m->proc[0] * m->proc[1] * m->proc[2] == 1, B200FEM_ERR_NOT_IMPLEMENTED, "periodic grids: one rank");
+  for (int d = 0; d < m->dim; ++d) REQUIRE(!((mask >> d) & 1) || m->gn[d] >= 2, B200FEM_ERR_INVALID, "periodic axis needs at least two cells");
+  m->box.periodic = mask; return B200FEM_OK;
 }
 extern "C" int b200fem_mesh_cartesian(b200fem_ctx* ctx, int dim, const int32_t* n, const double* lo, const double* hi, b200fem_mesh** out) {
   return make_mesh(ctx, dim, n, lo, hi, nullptr, 0, out);
@@ -170,6 +177,7 @@ extern "C" int b200fem_space_create(b200fem_mesh* mesh, int kind, int order, int
     s->box = mesh->box;
     if (kind == B200FEM_LAGRANGE) {
       REQUIRE(order == 1 || order == 2, B200FEM_ERR_NOT_IMPLEMENTED, "Lagrange spaces: order 1 and 2 only");
+      REQUIRE(mesh->box.periodic == 0, B200FEM_ERR_NOT_IMPLEMENTED, "Lagrange spaces on periodic grids (dof identification across the boundary)");
       BoxDev& b = s->box;      // continuous spaces need no ghost elements: the local box is the owned box
       for (int d = 0; d < 3; ++d) { b.origin[d] = mesh->olo[d]; b.n[d] = mesh->ohi[d] - mesh->olo[d]; b.own_lo[d] = 0; b.own_hi[d] = b.n[d]; }
       LagrangeLayoutDev& L = s->lay; L.order = order; L.lattice_map = nullptr;

@@ -39,6 +39,8 @@ struct BoxDev {
   int origin[3];            // global element coordinates of local element (0,0,0)
   int gn[3];                // global extents
   double lo[3], h[3], ih[3];   // ih = 1 / h (filled by the host: no division in the kernels)
+  int periodic;             // bit d: periodic along axis d -- the faces on those sides have the element of the far side as neighbour
+                            // (single rank; only the generic quadrature kernel wraps)
 };
 
 // 1-D tables: N basis functions tabulated at the MI-point interior rule and at the MS-point surface rule, traces at 0 / 1
@@ -199,7 +201,7 @@ __device__ __forceinline__ void element_integrals(const QuadTabDev<N, MI, MS>& T
         Cc[((f * 2 + 0) * 2 + 0) * kC + la * LN + lb] = tv; Cc[((f * 2 + 0) * 2 + 1) * kC + la * LN + lb] = td;
         double nv = 0, nd = 0;
         const int cn = lc[d] + (s ? 1 : -1);
-        if (I.m.has_skeleton && cn >= 0 && cn < box.n[d]) {
+        if (I.m.has_skeleton && ((cn >= 0 && cn < box.n[d]) || ((box.periodic >> d) & 1))) {
           const double* un = S + Cfg::kNb + f * N3;     // staged by the kernel prologue (stored order)
 #pragma unroll
           for (int c = 0; c < N; ++c) {
@@ -248,12 +250,16 @@ __device__ __forceinline__ void element_integrals(const QuadTabDev<N, MI, MS>& T
       const double area = detJ * ihd, ihe = ihd;          // faceArea; 1 / he with he = avg(CellVolume)/FacetArea = h_d on a uniform box
       const int lcd = d == 0 ? lc[0] : d == 1 ? lc[1] : lc[2], nd_ = d == 0 ? box.n[0] : d == 1 ? box.n[1] : box.n[2];
       const int olo = d == 0 ? box.own_lo[0] : d == 1 ? box.own_lo[1] : box.own_lo[2], ohi = d == 0 ? box.own_hi[0] : d == 1 ? box.own_hi[1] : box.own_hi[2];
-      const int cn = lcd + (s ? 1 : -1);
-      const bool nb_exists = cn >= 0 && cn < nd_, nb_owned = cn >= olo && cn < ohi;
+      int cn = lcd + (s ? 1 : -1);
+      bool nb_exists = cn >= 0 && cn < nd_;
+      if (!nb_exists && ((box.periodic >> d) & 1)) { cn = cn < 0 ? nd_ - 1 : 0; nb_exists = true; }     // periodic: the far side's element (galerkin.hh:859-861)
+      const bool nb_owned = cn >= olo && cn < ohi;
       // inside = lower element index, or the owned element next to a ghost (one-sided from the owned side, galerkin.hh:866-878)
-      const bool own_inside = !nb_owned || s == 1;        // (the neighbour across the high side has the larger index)
-      // physical coordinates: the normal coordinate is fixed, (a, b) follow the face points
-      const double xd = (d == 0 ? box.lo[0] + box.h[0] * (box.origin[0] + lc[0] + s) : d == 1 ? box.lo[1] + box.h[1] * (box.origin[1] + lc[1] + s) : box.lo[2] + box.h[2] * (box.origin[2] + lc[2] + s));
+      const bool own_inside = !nb_owned || cn > lcd;      // (without wrap-around: the neighbour across the high side)
+      // physical coordinates: the normal coordinate is fixed, (a, b) follow the face points.  The point is the INSIDE element's
+      // (on a periodic face the two sides differ by the domain length)
+      const int cface = own_inside ? lcd + s : cn + (s ? 0 : 1);
+      const double xd = (d == 0 ? box.lo[0] + box.h[0] * (box.origin[0] + cface) : d == 1 ? box.lo[1] + box.h[1] * (box.origin[1] + cface) : box.lo[2] + box.h[2] * (box.origin[2] + cface));
       const double xb_ = d == 2 ? box.lo[1] + box.h[1] * ((box.origin[1] + lc[1]) + T.xs[qb]) : box.lo[2] + box.h[2] * ((box.origin[2] + lc[2]) + T.xs[qb]);
       double R0[MS], Ra[MS], Rb[MS], Rn[MS];
 #pragma unroll
@@ -381,9 +387,10 @@ dg_quadrature_kernel(const __grid_constant__ QuadTabDev<N, MI, MS> T, const __gr
         const int d = f >> 1;
         have[k][f] = false;
         if (skel && e2 >= 0) {
-          const int cn = ecs[4 * s2 + d] + ((f & 1) ? 1 : -1);
+          const int c0 = ecs[4 * s2 + d]; int cn = c0 + ((f & 1) ? 1 : -1);
           const long long step = d == 0 ? 1 : d == 1 ? estep1 : estep2;
-          if (cn >= 0 && cn < box.n[d]) { have[k][f] = true; nbv[k][f] = u[(e2 + ((f & 1) ? step : -step)) * nbs + j]; }
+          if ((cn < 0 || cn >= box.n[d]) && ((box.periodic >> d) & 1)) cn = cn < 0 ? box.n[d] - 1 : 0;
+          if (cn >= 0 && cn < box.n[d]) { have[k][f] = true; nbv[k][f] = u[(e2 + (long long)(cn - c0) * step) * nbs + j]; }
         }
       }
     }

@@ -52,7 +52,7 @@ class Context:
 
 
 class GridView:
-    def __init__(self, lo, hi, n, ctx=None, proc=None, rank=0):
+    def __init__(self, lo, hi, n, ctx=None, proc=None, rank=0, periodic=None):
         self.ctx = ctx or Context.default()
         self.dim = len(n)
         self.n, self.lo, self.hi = list(n), list(lo), list(hi)
@@ -67,6 +67,10 @@ class GridView:
             capi.check(capi.lib().b200fem_mesh_cartesian_distributed(self.ctx.handle, self.dim, n_a, lo_a, hi_a, p_a, rank,
                                                                      C.byref(self.handle)))
         self.proc, self.rank = proc, rank
+        self.periodic = 0
+        if periodic is not None and any(periodic):       # dune.grid.structuredGrid(..., periodic=[...]) -> YaspGrid's periodic bitset
+            self.periodic = sum(1 << d for d, on in enumerate(periodic) if on)
+            capi.check(capi.lib().b200fem_mesh_set_periodic(self.handle, self.periodic))
 
     def close(self):
         if self.handle:
@@ -80,8 +84,8 @@ class GridView:
             pass
 
 
-def structuredGrid(lo, hi, n, ctx=None, proc=None, rank=0):
-    return GridView(lo, hi, n, ctx=ctx, proc=proc, rank=rank)
+def structuredGrid(lo, hi, n, ctx=None, proc=None, rank=0, periodic=None):
+    return GridView(lo, hi, n, ctx=ctx, proc=proc, rank=rank, periodic=periodic)
 
 
 def partition_box(n_global, proc, rank, overlap):

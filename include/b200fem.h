@@ -98,6 +98,10 @@ int b200fem_memcpy_d2h(b200fem_ctx* ctx, void* host, const void* dev, int64_t by
 int b200fem_mesh_cartesian(b200fem_ctx* ctx, int dim, const int32_t* n, const double* lo, const double* hi, b200fem_mesh** out);
 int b200fem_mesh_cartesian_distributed(b200fem_ctx* ctx, int dim, const int32_t* n_global, const double* lo, const double* hi,
                                        const int32_t* proc, int rank, b200fem_mesh** out);
+/* Periodic grid (YaspGrid's `periodic` bitset): bit d set = the faces on the two sides of axis d are interior faces whose
+ * neighbour is the element on the far side; the operator treats them as skeleton faces first, as the reference does
+ * (schemes/galerkin.hh:859-861).  DG spaces on one rank, evaluated by the generic quadrature kernel (Kronecker kernels step aside). */
+int b200fem_mesh_set_periodic(b200fem_mesh* mesh, int mask);
 int b200fem_mesh_destroy(b200fem_mesh* mesh);
 /* The block partition used by the distributed mesh, without needing a device (host logic only): for `rank` of the
  * process grid, out[0..2] = global coordinates of local element (0,0,0) (ghost layer included), out[3..5] = local

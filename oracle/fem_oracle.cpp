@@ -157,6 +157,7 @@ static double legendreJacobian(int num, double x) {
 struct Mesh {
   int dim = 2; int n[3] = {1,1,1}; double lo[3] = {0,0,0}, hi[3] = {1,1,1}, h[3] = {1,1,1};
   int64_t nelem = 1;
+  int periodic = 0;          // bit d: the grid is periodic along axis d (YaspGrid's periodic bitset): the faces on those sides have neighbours
   void finish() { nelem = 1; for (int d = 0; d < 3; ++d) { if (d >= dim) { n[d] = 1; lo[d] = 0; hi[d] = 1; } h[d] = (hi[d]-lo[d])/n[d]; nelem *= n[d]; } }
   void elemCoords(int64_t e, int c[3]) const { c[0] = (int)(e % n[0]); e /= n[0]; c[1] = (int)(e % n[1]); c[2] = (int)(e / n[1]); }
   int64_t elemIndex(const int c[3]) const { return c[0] + (int64_t)n[0]*(c[1] + (int64_t)n[1]*c[2]); }
@@ -562,7 +563,9 @@ struct Operator {
       if (model.hasSkeleton || (model.hasBoundary && bndElem)) {
         for (int f = 0; f < 2*M.dim; ++f) {
           const int axis = f/2, side = f%2; int nc[3] = {ec[0], ec[1], ec[2]}; nc[axis] += side ? 1 : -1;
-          const bool neighbor = nc[axis] >= 0 && nc[axis] < M.n[axis];
+          bool neighbor = nc[axis] >= 0 && nc[axis] < M.n[axis];
+          // periodic boundaries: neighbor() and boundary() are both true and the neighbour is treated first (galerkin.hh:859-861)
+          if (!neighbor && ((M.periodic >> axis) & 1)) { nc[axis] = (nc[axis] + M.n[axis]) % M.n[axis]; neighbor = true; }
           if (neighbor) {
             if (!model.hasSkeleton) continue;
             const int64_t o = M.elemIndex(nc);
@@ -823,6 +826,7 @@ FoSpace* fo_space_create(int dim, const int* n, const double* lo, const double* 
   FoSpace* s = new FoSpace; s->sp.reset(new Space(m, kind, order, numbering, interiorOrder, surfaceOrder)); return s;
 }
 void fo_space_destroy(FoSpace* s) { delete s; }
+void fo_space_set_periodic(FoSpace* s, int mask) { s->sp->mesh.periodic = mask; }
 int64_t fo_space_size(FoSpace* s) { return s->sp->size; }
 int fo_space_local_size(FoSpace* s) { return s->sp->nb; }
 int64_t fo_space_elements(FoSpace* s) { return s->sp->mesh.nelem; }

@@ -36,6 +36,7 @@ def lib():
     L.fo_space_create.restype = C.c_void_p
     L.fo_space_create.argtypes = [C.c_int, _ip, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     L.fo_space_destroy.argtypes = [C.c_void_p]
+    L.fo_space_set_periodic.argtypes = [C.c_void_p, C.c_int]
     L.fo_space_size.restype = C.c_int64
     L.fo_space_size.argtypes = [C.c_void_p]
     L.fo_space_local_size.restype = C.c_int
@@ -100,6 +101,10 @@ class Space:
         self.size = lib().fo_space_size(self._h)
         self.local_size = lib().fo_space_local_size(self._h)
         self.elements = lib().fo_space_elements(self._h)
+
+    def set_periodic(self, mask):
+        """bit d: periodic along axis d (DG spaces)"""
+        lib().fo_space_set_periodic(self._h, mask)
 
     def dofmap(self, e):
         out = np.empty(self.local_size, dtype=np.int64)

@@ -205,6 +205,30 @@ def test_cg_iterates_match_reference_recurrence(dim, order, n):
         assert abs(it - it_ref) <= 1
 
 
+@pytest.mark.parametrize("dim,order,n", [(2, 1, [256, 256]), (3, 2, [24, 24, 24])])
+def test_cg_first_50_iterates_at_contract_tolerance(dim, order, n):
+    """the first 50 iterates' residual norms and x to 1e-12 relative -- on BASELINE config 1 at full size (P1 256^2:
+    the cooperative CG kernel) and on a P2 3-D lattice (the lattice kernel + CUDA-graph schedule), rough right-hand side so that
+    all 50 iterations are genuine.  Measured drift against the oracle's sequential summation: 4e-14 / 7e-14."""
+    lo, hi = [0.0] * dim, [1.0] * dim
+    space = fem.space.lagrange(fem.structuredGrid(lo, hi, n), order=order)
+    osp = ol.Space(n, lo, hi, ol.LAGRANGE, order)
+    kw = dict(eps=1.0, data=2, dirichlet_mask=(1 << (2 * dim)) - 1, strong_dirichlet=True)
+    op = fem.operator.galerkin(space, **kw)
+    oop = ol.Operator(osp, threads=8, **kw)
+    mask, _ = op.dirichlet()
+    b = np.random.default_rng(5).uniform(-1, 1, space.size) * (1 - mask)
+    x0 = np.zeros(space.size)
+    inv = fem.solver.CgInverseOperator({"tolerance": 1e-30, "maxiterations": 50})
+    inv.bind(op)
+    x = x0.copy()
+    it = inv(b, x)
+    it_ref, x_ref, hist_ref = oop.cg(b, x0, 1e-30, 50)
+    assert it == it_ref == -50
+    np.testing.assert_allclose(inv.residuals, hist_ref, rtol=1e-12)
+    assert rel(x, x_ref) < 1e-12
+
+
 def test_cg_on_dg_sipg_laplace():
     space, osp = dg_pair([4, 4, 4], [0, 0, 0], [1, 1, 1], 2, True)
     # symmetric positive definite: SIPG interior faces + reaction, Neumann data on the boundary (the weak

@@ -99,3 +99,45 @@ def test_pydemo_advection_diffusion_2d_eoc_on_the_device(kind):
         assert np.abs(r).max() < 1e-9 * np.abs(op.loadVector()).max()
     eoc = [math.log(errs[i + 1] / errs[i]) / math.log(0.5) for i in range(2)]
     assert eoc[-1] > order + 1 - 0.1, (errs, eoc)
+
+
+@pytest.mark.parametrize("kind,dim,order,periodic", [("hier", 3, 2, (1, 0, 1)), ("lex", 3, 1, (1, 1, 1)), ("onb", 2, 2, (0, 1)), ("hier", 2, 3, (1, 1)), ("hier", 3, 3, (0, 1, 0))])
+def test_periodic_grids(kind, dim, order, periodic):
+    """Periodic sides are skeleton faces whose neighbour is the element on the far side (galerkin.hh:859-861); incl. the case of two
+    cells along an axis, where both faces of an element meet the same neighbour."""
+    n = ([5, 2] if dim == 2 else [4, 2, 3])
+    lo, hi = [-1.0] * dim, [1.0, 0.5, 2.0][:dim]
+    g = fem.structuredGrid(lo, hi, n, periodic=periodic)
+    if kind == "onb":
+        space, osp = fem.space.dgonb(g, order=order), ol.Space(n, lo, hi, ol.DG_ONB, order)
+    else:
+        space, osp = fem.space.dglegendre(g, order=order, hierarchical=kind == "hier"), ol.Space(n, lo, hi, ol.DG_LEGENDRE_HIER if kind == "hier" else ol.DG_LEGENDRE, order)
+    osp.set_periodic(g.periodic)
+    kw = dict(eps=0.05, b=(1.0, -0.5, 0.25)[:dim], c=0.3, beta=20.0 * order ** 2, dirichlet_mask=0b11 if not periodic[0] else 0, data=1)
+    u = np.random.default_rng(order).uniform(-1, 1, space.size)
+    oop = ol.Operator(osp, skeleton=True, boundary=True, **kw)
+    ref = oop.apply(u)
+    osp_np = ol.Space(n, lo, hi, osp.kind, order)
+    assert rel(ol.Operator(osp_np, skeleton=True, boundary=True, **kw).apply(u), ref) > 1e-3     # the wrap-around matters
+    op = fem.operator.galerkin(space, **kw)
+    w = np.empty(space.size)
+    op(u, w)
+    assert rel(w, ref) < TOL
+    assert op.timing()["kernel"] == _capi.KERNEL_QUADRATURE       # the Kronecker kernels do not wrap: AUTO steps aside
+    op.applyLinear(u, w)
+    assert rel(w, oop.apply(u, linear=True)) < TOL
+
+
+def test_periodic_with_compiled_x_dependent_integrands():
+    """on a periodic face the integrand sees the INSIDE element's point (the two sides differ by the domain length)"""
+    import os
+    src = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "integrands", "adr_variable.cuh")).read()
+    n, lo, hi = [4, 3, 2], [-1.0] * 3, [1.0, 0.5, 2.0]
+    g = fem.structuredGrid(lo, hi, n, periodic=(1, 1, 0))
+    space, osp = fem.space.dglegendre(g, order=2), ol.Space(n, lo, hi, ol.DG_LEGENDRE_HIER, 2)
+    osp.set_periodic(g.periodic)
+    const = [0.05, 1.0, -0.5, 0.25, 80.0, 0.3, 0.7]
+    u = np.random.default_rng(1).uniform(-1, 1, space.size)
+    w = np.empty(space.size)
+    fem.operator.galerkinJit(space, src, const)(u, w)
+    assert rel(w, ol.UserOperator(osp, src, const).apply(u)) < TOL
