@@ -95,9 +95,14 @@ dg_kronecker_mma_kernel(const __grid_constant__ KronTabDev<4> K, const __grid_co
   const double dlo_y = K.Dlo[1][(g & 3) * N + t], dhi_y = K.Dhi[1][(g & 3) * N + t];
 
   const int on0 = box.own_hi[0] - box.own_lo[0], on1 = box.own_hi[1] - box.own_lo[1], on2 = box.own_hi[2] - box.own_lo[2];
-  const long long total = (long long)tx * ty * on2;
-  long long s0 = total * blockIdx.x / gridDim.x;
-  const long long s1 = total * (blockIdx.x + 1) / gridDim.x;
+  // Work split.  Enough columns for every CTA: whole columns, dealt round-robin -- the CTAs of a wave then march through z in
+  // lockstep over NEIGHBOURING columns, so the x/y halo rows two of them share are read from DRAM once and hit the L2 the second
+  // time.  Fewer columns than CTAs: the (column, z) plane steps are split evenly and a column is shared by several CTAs.
+  const int ncols = tx * ty;
+  const bool whole_columns = ncols >= (int)gridDim.x;
+  const long long total = whole_columns ? (long long)((ncols - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * on2 : (long long)ncols * on2;
+  long long s0 = whole_columns ? 0 : total * blockIdx.x / gridDim.x;
+  const long long s1 = whole_columns ? total : total * (blockIdx.x + 1) / gridDim.x;
   if (tid == 0) { ptx::mbar_init(bar_l, 1); ptx::mbar_init(bar_b, 1); ptx::fence_barrier_init(); ptx::prefetch_tensormap(&M.u_plane); ptx::prefetch_tensormap(&M.w_tile); if (HAS_B) ptx::prefetch_tensormap(&M.b_tile); }
   unsigned n_l = 0, n_b = 0;                       // completed waits on the two barriers (their phase parities)
   long long tph[6] = {0, 0, 0, 0, 0, 0}, tlast = clock64();   // diagnostics (dbg != nullptr): cycles per phase seen by one thread
@@ -105,7 +110,8 @@ dg_kronecker_mma_kernel(const __grid_constant__ KronTabDev<4> K, const __grid_co
   __syncthreads();
 
   while (s0 < s1) {
-    const int col = (int)(s0 / on2), za = (int)(s0 % on2), zb = (int)min((long long)on2, za + (s1 - s0));
+    const int col = whole_columns ? (int)blockIdx.x + (int)(s0 / on2) * (int)gridDim.x : (int)(s0 / on2);
+    const int za = (int)(s0 % on2), zb = (int)min((long long)on2, za + (s1 - s0));
     s0 += zb - za;
     const int x0 = box.own_lo[0] + (col % tx) * Cfg::TX, y0 = box.own_lo[1] + (col / tx) * Cfg::TY;   // local coordinates of the column's first element
     // accumulators of the planes z-1 (m), z (0), z+1 (p) for the two patches of this warp: [patch][c][2]
