@@ -465,7 +465,7 @@ def main():
             W = 2 * order + 1
             fl = sp.size * 2.0 * (5 * W if dim == 3 else 3 * W)        # z: 2W, y: 3W (2W in 2-D... counted as 3W upper bound), x: 2W FMA per node
             other[name] = {"dofs": sp.size, "linear_ms": t_lin * 1e3, "linear_dofs_per_s": sp.size / t_lin,
-                           "roofline": roofline_block("lagrange_kronecker_kernel<%d>" % order, sp.size, t_lin, peak, peak_src, traffic, fl, "lattice stencil: 2 * (7 W) flop per node in 3-D (W = 2k+1), 2 * 3 W in 2-D")}
+                           "roofline": roofline_block("lagrange_lattice_kernel<%d>" % order, sp.size, t_lin, peak, peak_src, traffic, fl, "lattice stencil: 2 * (7 W) flop per node in 3-D (W = 2k+1), 2 * 3 W in 2-D")}
             del o, sp, g
             torch.cuda.empty_cache()
 
