@@ -70,6 +70,31 @@ def check_dg_apply(ctx, rank, proc, n, order, kernels, kw, seed):
     return worst, (grid, space, osp, gather)
 
 
+def check_dg_onb_and_compiled_integrands(ctx, rank, proc, n):
+    """round 2: the `dgonb` P_2 space (10 dofs per element: halo blocks of another size) and run-time compiled integrands on a
+    distributed mesh, both through the generic quadrature kernel followed by the Copy exchange"""
+    lo, hi = [-1.0, -1.0, -1.0], [1.0, 1.0, 1.0]
+    grid = fem.structuredGrid(lo, hi, n, ctx=ctx, proc=proc, rank=rank)
+    worst = 0.0
+    space, osp = fem.space.dgonb(grid, order=2), ol.Space(n, lo, hi, ol.DG_ONB, 2)
+    kw = dict(eps=0.05, b=(1.0, 0.5, 0.25), beta=80.0, dirichlet_mask=0b000011, data=1)
+    ug = np.random.default_rng(21).uniform(-1, 1, osp.size)
+    gather = dg_gather(n, proc, rank, 10)
+    wl = np.full(space.size, np.nan)
+    fem.operator.galerkin(space, **kw)(np.ascontiguousarray(ug[gather]), wl)
+    worst = max(worst, rel(wl, ol.Operator(osp, skeleton=True, boundary=True, threads=4, **kw).apply(ug)[gather]))
+    src = open(os.path.join(ROOT, "tests", "integrands", "adr_variable.cuh")).read()
+    const = [0.05, 1.0, -0.5, 0.25, 80.0, 0.3, 0.7]
+    space, osp = fem.space.dglegendre(grid, order=2), ol.Space(n, lo, hi, ol.DG_LEGENDRE_HIER, 2)
+    ug = np.random.default_rng(22).uniform(-1, 1, osp.size)
+    gather = dg_gather(n, proc, rank, 27)
+    wl = np.full(space.size, np.nan)
+    fem.operator.galerkinJit(space, src, const)(np.ascontiguousarray(ug[gather]), wl)
+    worst = max(worst, rel(wl, ol.UserOperator(osp, src, const).apply(ug)[gather]))
+    assert worst < TOL, ("dgonb / compiled integrands", proc, worst)
+    return worst
+
+
 def check_dg_solvers(ctx, rank, proc, n):
     lo, hi = [-1.0, -1.0, -1.0], [1.0, 1.0, 1.0]
     grid = fem.structuredGrid(lo, hi, n, ctx=ctx, proc=proc, rank=rank)
@@ -192,7 +217,7 @@ def parity_block(ctx, rank, world):
     kw = dict(eps=0.05, b=(1.0, 0.5, 0.25), beta=80.0, dirichlet_mask=0b000011, data=1)
     cases["dg_q2_apply_march_fused_exchange"], _ = check_dg_apply(ctx, rank, dg_proc, [16, 8, 16], 2, (_capi.KERNEL_KRONECKER,), kw, 5)
     cases["dg_q2_apply_quadrature"], _ = check_dg_apply(ctx, rank, dg_proc, [8, 6, 8], 2, (_capi.KERNEL_QUADRATURE,), kw, 5)
-    cases["dg_q3_apply_slab"], _ = check_dg_apply(ctx, rank, dg_proc, [8, 6, 8], 3, (_capi.KERNEL_KRONECKER,), dict(kw, beta=180.0), 8)
+    cases["dg_q3_apply_tensor_core"], _ = check_dg_apply(ctx, rank, dg_proc, [8, 6, 8], 3, (_capi.KERNEL_KRONECKER,), dict(kw, beta=180.0), 8)
     cases["lagrange_p2_apply"], cases["lagrange_p2_cg10_x"] = check_lagrange(ctx, rank, lag_proc, [8, 6, 8], 2, cg_iters=10, jacobi=False)
     return {"max_rel_err": max(cases.values()), "cases": cases, "tolerance": "apply 1e-12 of max|w|; CG x 1e-10, residual history 1e-9, iteration counts equal",
             "transport": "peer memory" if ctx.peer_memory else "nccl"}
@@ -218,9 +243,11 @@ def main():
         # partial tiles in x / y, several columns per CTA row, odd plane counts
         w, _ = check_dg_apply(ctx, rank, proc, [34, 20, 14], 2, (_capi.KERNEL_KRONECKER,), kw, 15)
         worst = max(worst, w)
-        w, _ = check_dg_apply(ctx, rank, proc, [8, 6, 8], 3, (_capi.KERNEL_KRONECKER,), dict(kw, beta=180.0), 8)   # slab kernel (BASELINE config 5)
+        w, _ = check_dg_apply(ctx, rank, proc, [8, 6, 8], 3, (_capi.KERNEL_KRONECKER,), dict(kw, beta=180.0), 8)   # Q3 tensor-core kernel on boxes with ghost layers (BASELINE config 5)
         worst = max(worst, w)
         worst = max(worst, check_dg_solvers(ctx, rank, proc, [8, 6, 8]))
+        if proc is procs[0]:
+            worst = max(worst, check_dg_onb_and_compiled_integrands(ctx, rank, proc, [8, 6, 8]))
         w, _ = check_lagrange(ctx, rank, proc, [8, 6, 8], 2)
         worst = max(worst, w)
         w, _ = check_lagrange(ctx, rank, proc, [8, 6, 8], 1)
