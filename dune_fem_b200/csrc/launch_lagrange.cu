@@ -155,11 +155,9 @@ template <int K> static int launch_lattice_k(b200fem_operator* op, const double*
   // tile: 64 nodes wide (16 lanes x 4 nodes), 16 rows (8 warps x 2 rows), two CTAs per SM.  Measured on P2 128^3 (profiles/
   // r02_lagrange_lattice.md): 259 us against 295 us for 16-warp CTAs with 32 rows -- the smaller CTAs run out of phase (one
   // CTA's shared-memory phase under the other's FMA phase), which outweighs their larger halo share
-  static const int tile_variant = std::getenv("B200FEM_LAT_TILE") ? std::atoi(std::getenv("B200FEM_LAT_TILE")) : 0;     // A/B switch (read once)
-  int rc;
-  if (tile_variant == 1) rc = mapped ? launch_lattice<K, 8, true, 8>(op, S, u, w, bvec, dvals) : launch_lattice<K, 8, false, 8>(op, S, u, w, bvec, dvals);          // 32 x 32 tiles
-  else if (tile_variant == 2) rc = mapped ? launch_lattice<K, 8, true, 16>(op, S, u, w, bvec, dvals) : launch_lattice<K, 8, false, 16>(op, S, u, w, bvec, dvals);   // 32 x 64 tiles
-  else rc = mapped ? launch_lattice<K, 16, true, 8>(op, S, u, w, bvec, dvals) : launch_lattice<K, 16, false, 8>(op, S, u, w, bvec, dvals);
+  // (round 2, measured: 32 x 32 tiles (LX = 8) 273 us, 32 x 64 tiles (LX = 8, 16 warps) 300 us -- better tile efficiency on paper,
+  // slower in fact)
+  int rc = mapped ? launch_lattice<K, 16, true, 8>(op, S, u, w, bvec, dvals) : launch_lattice<K, 16, false, 8>(op, S, u, w, bvec, dvals);
   if (rc) return rc;
   op->dirichlet_fused = op->fuse_dirichlet;
   op->timing.launches_per_apply = 1;
