@@ -177,9 +177,12 @@ lagrange_lattice_kernel(const __grid_constant__ LagrangeLayoutDev L, const __gri
 #pragma unroll
       for (int j = 0; j < R; ++j) { a[j] = fma(cm, win[j][K], a[j]); b[j] = fma(ct, win[j][K], b[j]); }
     }
-    double* pa = plane_ptr(nb, row, 0) + R * lx; double* pb = plane_ptr(nb, row, 1) + R * lx;
-    *reinterpret_cast<double2*>(pa) = make_double2(a[0], a[1]); *reinterpret_cast<double2*>(pa + 2) = make_double2(a[2], a[3]);
-    *reinterpret_cast<double2*>(pb) = make_double2(b[0], b[1]); *reinterpret_cast<double2*>(pb + 2) = make_double2(b[2], b[3]);
+    // A row of a plane is stored as two halves: the lanes' node pairs (0, 1) side by side, then their pairs (2, 3).  16-byte
+    // accesses of neighbouring lanes are then 16 bytes apart (a lane's four nodes in one 32-byte piece put every other lane of a
+    // quarter-warp on the same banks: half of the y-pass wavefronts were conflicts, profiles/r02_lattice.md)
+    double* pa = plane_ptr(nb, row, 0) + 2 * lx; double* pb = plane_ptr(nb, row, 1) + 2 * lx;
+    *reinterpret_cast<double2*>(pa) = make_double2(a[0], a[1]); *reinterpret_cast<double2*>(pa + NX / 2) = make_double2(a[2], a[3]);
+    *reinterpret_cast<double2*>(pb) = make_double2(b[0], b[1]); *reinterpret_cast<double2*>(pb + NX / 2) = make_double2(b[2], b[3]);
   };
   z_pass(z0, 0);
   __syncthreads();
@@ -222,8 +225,8 @@ lagrange_lattice_kernel(const __grid_constant__ LagrangeLayoutDev L, const __gri
 #pragma unroll
       for (int j = 0; j < R; ++j) { c[j] = 0.0; s[j] = 0.0; }
       auto y_term = [&](const int t, const double cm, const double ct) {
-        const double2 a01 = *reinterpret_cast<const double2*>(plane_ptr(cb, row - K + t, 0) + R * lx), a23 = *reinterpret_cast<const double2*>(plane_ptr(cb, row - K + t, 0) + R * lx + 2);
-        const double2 b01 = *reinterpret_cast<const double2*>(plane_ptr(cb, row - K + t, 1) + R * lx), b23 = *reinterpret_cast<const double2*>(plane_ptr(cb, row - K + t, 1) + R * lx + 2);
+        const double2 a01 = *reinterpret_cast<const double2*>(plane_ptr(cb, row - K + t, 0) + 2 * lx), a23 = *reinterpret_cast<const double2*>(plane_ptr(cb, row - K + t, 0) + 2 * lx + NX / 2);
+        const double2 b01 = *reinterpret_cast<const double2*>(plane_ptr(cb, row - K + t, 1) + 2 * lx), b23 = *reinterpret_cast<const double2*>(plane_ptr(cb, row - K + t, 1) + 2 * lx + NX / 2);
         const double av[R] = {a01.x, a01.y, a23.x, a23.y}, bv[R] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
         for (int j = 0; j < R; ++j) { c[j] = fma(cm, av[j], c[j]); s[j] = fma(ct, av[j], s[j]); s[j] = fma(cm, bv[j], s[j]); }
