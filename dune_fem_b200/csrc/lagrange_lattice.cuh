@@ -64,7 +64,9 @@ template <int K, int LX, int WARPS = 16> struct LagLatCfg {
   static_assert(32 % LX == 0 && TXO % 2 == 0 && TYO % 2 == 0, "tiles start on even lattice coordinates: node types are fixed per register slot / warp");
 };
 
-template <int K, int LX, bool MAPPED, int WARPS>
+// DATA = false: neither a load vector nor Dirichlet values are streamed (the homogeneous apply A u of the Krylov loops): their
+// eight operand registers are compiled out, which is what keeps this instantiation free of spills at the 128-register cap
+template <int K, int LX, bool MAPPED, int WARPS, bool DATA>
 __global__ void __launch_bounds__(LagLatCfg<K, LX, WARPS>::kThreads, LagLatCfg<K, LX, WARPS>::kCtasPerSm)
 lagrange_lattice_kernel(const __grid_constant__ LagrangeLayoutDev L, const __grid_constant__ LagStencilDev<K> S,
                         const double* __restrict__ u, double* __restrict__ w, const double* __restrict__ bvec, const double* __restrict__ dvals,
@@ -203,8 +205,10 @@ lagrange_lattice_kernel(const __grid_constant__ LagrangeLayoutDev L, const __gri
     for (int j = 0; j < R; ++j) {                                        // (straight-line, predicated: no divergent blocks)
       const bool out = (xout >> j) & 1u;
       uc[j] = win[j][K]; g[j] = out ? node_dof(st_a, j) : 0;
-      bq[j] = (out && bvec != nullptr) ? bvec[g[j]] : 0.0;
-      dq[j] = (out && ((cons >> j) & 1u) && S.affine) ? dvals[g[j]] : 0.0;
+      if (DATA) {
+        bq[j] = (out && bvec != nullptr) ? bvec[g[j]] : 0.0;
+        dq[j] = (out && ((cons >> j) & 1u) && S.affine) ? dvals[g[j]] : 0.0;
+      } else { bq[j] = 0.0; dq[j] = 0.0; }
     }
     advance(st_a, st_b);
     if (z + 1 < z1) {

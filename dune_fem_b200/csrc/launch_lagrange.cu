@@ -133,7 +133,7 @@ static int launch_lattice(b200fem_operator* op, const LagStencilDev<K>& S, const
     if ((int)grid > op->dot_cap) { if (op->capturing) return fail(B200FEM_ERR_INVALID, "dot partial buffer must exist before graph capture"); if (op->d_dot_partial) cudaFree(op->d_dot_partial); CUDA_OK(cudaMalloc(&op->d_dot_partial, sizeof(double) * grid)); op->dot_cap = (int)grid; }
     dotp = op->d_dot_partial; op->dot_parts = (int)grid;
   }
-  auto kern = lagrange_lattice_kernel<K, LX, MAPPED, WARPS>;
+  auto kern = (bvec != nullptr || dvals != nullptr) ? lagrange_lattice_kernel<K, LX, MAPPED, WARPS, true> : lagrange_lattice_kernel<K, LX, MAPPED, WARPS, false>;
   int rc = ensure_smem_attr(ctx, (const void*)kern, Cfg::smem_bytes()); if (rc) return rc;
   kern<<<grid, Cfg::kThreads, Cfg::smem_bytes(), ctx->stream>>>(L, S, u, w, bvec, dvals, tx, ty, zseg, dotp);
   CUDA_OK(cudaGetLastError());
