@@ -102,7 +102,8 @@ template <int Q, int N> __device__ __forceinline__ void quad_mvt_add(const doubl
 // (it synchronises); `lt` is the thread's index inside its element group (P x P threads), `lc` the element's local
 // coordinates, `e` its local index, u the global vector (only read for skeleton neighbours of DG spaces), perm the
 // tensor -> stored permutation of the neighbours' dofs (null: identity).
-template <int N, int MI, int MS, class Integrands>
+// GEN = true: sub-basis spaces and periodic grids (run-time dof count, wrap-around neighbours); GEN = false compiles both out
+template <int N, int MI, int MS, class Integrands, bool GEN = false>
 __device__ __forceinline__ void element_integrals(const QuadTabDev<N, MI, MS>& T, const BoxDev& box, const Integrands& I, const int* perm,
                                                   const double* __restrict__ u, const bool active, const int (&lc)[3],
                                                   const long long e, const int lt, double* U, double* W, double* S) {
@@ -201,7 +202,7 @@ __device__ __forceinline__ void element_integrals(const QuadTabDev<N, MI, MS>& T
         Cc[((f * 2 + 0) * 2 + 0) * kC + la * LN + lb] = tv; Cc[((f * 2 + 0) * 2 + 1) * kC + la * LN + lb] = td;
         double nv = 0, nd = 0;
         const int cn = lc[d] + (s ? 1 : -1);
-        if (I.m.has_skeleton && ((cn >= 0 && cn < box.n[d]) || ((box.periodic >> d) & 1))) {
+        if (I.m.has_skeleton && ((cn >= 0 && cn < box.n[d]) || (GEN && ((box.periodic >> d) & 1)))) {
           const double* un = S + Cfg::kNb + f * N3;     // staged by the kernel prologue (stored order)
 #pragma unroll
           for (int c = 0; c < N; ++c) {
@@ -252,7 +253,7 @@ __device__ __forceinline__ void element_integrals(const QuadTabDev<N, MI, MS>& T
       const int olo = d == 0 ? box.own_lo[0] : d == 1 ? box.own_lo[1] : box.own_lo[2], ohi = d == 0 ? box.own_hi[0] : d == 1 ? box.own_hi[1] : box.own_hi[2];
       int cn = lcd + (s ? 1 : -1);
       bool nb_exists = cn >= 0 && cn < nd_;
-      if (!nb_exists && ((box.periodic >> d) & 1)) { cn = cn < 0 ? nd_ - 1 : 0; nb_exists = true; }     // periodic: the far side's element (galerkin.hh:859-861)
+      if (GEN && !nb_exists && ((box.periodic >> d) & 1)) { cn = cn < 0 ? nd_ - 1 : 0; nb_exists = true; }     // periodic: the far side's element (galerkin.hh:859-861)
       const bool nb_owned = cn >= olo && cn < ohi;
       // inside = lower element index, or the owned element next to a ghost (one-sided from the owned side, galerkin.hh:866-878)
       const bool own_inside = !nb_owned || cn > lcd;      // (without wrap-around: the neighbour across the high side)
@@ -333,14 +334,15 @@ __device__ __forceinline__ void element_integrals(const QuadTabDev<N, MI, MS>& T
   }
 }
 
-template <int N, int MI, int MS, class Integrands>
+template <int N, int MI, int MS, class Integrands, bool GEN>
 __global__ void __launch_bounds__(DgQuadCfg<N, MI, MS>::kThreads)
 dg_quadrature_kernel(const __grid_constant__ QuadTabDev<N, MI, MS> T, const __grid_constant__ BoxDev box,
-                     const __grid_constant__ Integrands I, const int* __restrict__ perm_g, const int nbs,
+                     const __grid_constant__ Integrands I, const int* __restrict__ perm_g, const int nbs_arg,
                      const double* __restrict__ u, double* __restrict__ w, const double* __restrict__ bvec,
                      long long n_owned, const double out_scale) {
   using Cfg = DgQuadCfg<N, MI, MS>;
   constexpr int N2 = N * N, N3 = N * N * N, EB = Cfg::EB, ELEM = Cfg::kElemDoubles, LN = Cfg::LN;
+  const int nbs = GEN ? nbs_arg : N3;          // (a compile-time constant in the common case: the index divisions below fold)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* smem = reinterpret_cast<double*>(smem_raw);
   long long* elem_of = reinterpret_cast<long long*>(smem + (size_t)EB * ELEM);   // local element index per slot
@@ -389,7 +391,7 @@ dg_quadrature_kernel(const __grid_constant__ QuadTabDev<N, MI, MS> T, const __gr
         if (skel && e2 >= 0) {
           const int c0 = ecs[4 * s2 + d]; int cn = c0 + ((f & 1) ? 1 : -1);
           const long long step = d == 0 ? 1 : d == 1 ? estep1 : estep2;
-          if ((cn < 0 || cn >= box.n[d]) && ((box.periodic >> d) & 1)) cn = cn < 0 ? box.n[d] - 1 : 0;
+          if (GEN && (cn < 0 || cn >= box.n[d]) && ((box.periodic >> d) & 1)) cn = cn < 0 ? box.n[d] - 1 : 0;
           if (cn >= 0 && cn < box.n[d]) { have[k][f] = true; nbv[k][f] = u[(e2 + (long long)(cn - c0) * step) * nbs + j]; }
         }
       }
@@ -407,7 +409,7 @@ dg_quadrature_kernel(const __grid_constant__ QuadTabDev<N, MI, MS> T, const __gr
   __syncthreads();
 
   double* U = smem + (size_t)es * ELEM;
-  element_integrals<N, MI, MS, Integrands>(T, box, I, perm, u, active, lc, e, lt, U, U + Cfg::kU, U + 2 * Cfg::kU);
+  element_integrals<N, MI, MS, Integrands, GEN>(T, box, I, perm, u, active, lc, e, lt, U, U + Cfg::kU, U + 2 * Cfg::kU);
 
   // ---- write w_K once (tensor order -> stored order), optionally w = A u - b ----
   for (int idx = tid; idx < EB * nbs; idx += blockDim.x) {

@@ -87,7 +87,7 @@ std::string program_text(const std::string& user, bool skel, bool bnd, int N, in
   t += "  }\n  __device__ PointRange boundary(int axis, int side, double ihbnd, const double* x, const PointValue& v) const { PointRange r; r.s = 0; r.F[0] = r.F[1] = r.F[2] = 0;\n";
   if (bnd) t += "    user::boundary(x, axis, side, ihbnd, v, r, c, dim);\n";
   t += "    return r; }\n};\n}  // namespace b200fem\n";
-  *name_expr = "b200fem::dg_quadrature_kernel<" + std::to_string(N) + ", " + std::to_string(MI) + ", " + std::to_string(MS) + ", b200fem::JitIntegrands>";
+  *name_expr = "b200fem::dg_quadrature_kernel<" + std::to_string(N) + ", " + std::to_string(MI) + ", " + std::to_string(MS) + ", b200fem::JitIntegrands, true>";
   return t;
 }
 

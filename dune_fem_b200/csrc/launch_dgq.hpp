@@ -24,17 +24,19 @@ template <int N, int MI, int MS> inline int launch_dg_quadrature(b200fem_operato
   const long long n_owned = (long long)(b.own_hi[0] - b.own_lo[0]) * (b.own_hi[1] - b.own_lo[1]) * (b.own_hi[2] - b.own_lo[2]);
   const unsigned grid = (unsigned)((n_owned + Cfg::EB - 1) / Cfg::EB);
   const auto tab = make_quad_tab<N, MI, MS>(true, N - 1);
-  if (with_data) {   // load-vector pass (once per operator): the instantiation that carries the analytic data
-    auto kern = dg_quadrature_kernel<N, MI, MS, AdrIntegrands>;
+  const bool gen = !op->sp->tensor_full || b.periodic != 0;      // sub-basis space or periodic grid: the general instantiation
+  auto launch = [&](auto kern, auto I) -> int {
     int rc = ensure_smem_attr(ctx, (const void*)kern, Cfg::smem_bytes()); if (rc) return rc;
-    AdrIntegrands I; I.m = op->model; I.dim = b.dim; I.with_data = true;
+    I.m = op->model; I.dim = b.dim; I.with_data = with_data;
     kern<<<grid, Cfg::kThreads, Cfg::smem_bytes(), ctx->stream>>>(tab, b, I, op->d_perm, op->sp->nb, u, w, bvec, n_owned, mass_scale(op));
-  } else {
-    auto kern = dg_quadrature_kernel<N, MI, MS, AdrIntegrandsHom>;
-    int rc = ensure_smem_attr(ctx, (const void*)kern, Cfg::smem_bytes()); if (rc) return rc;
-    AdrIntegrandsHom I; I.m = op->model; I.dim = b.dim; I.with_data = false;
-    kern<<<grid, Cfg::kThreads, Cfg::smem_bytes(), ctx->stream>>>(tab, b, I, op->d_perm, op->sp->nb, u, w, bvec, n_owned, mass_scale(op));
-  }
+    return B200FEM_OK;
+  };
+  int rc;
+  // the load-vector pass (once per operator) is the instantiation that carries the analytic data; it always takes the general kernel
+  if (with_data) rc = launch(dg_quadrature_kernel<N, MI, MS, AdrIntegrands, true>, AdrIntegrands{});
+  else if (gen) rc = launch(dg_quadrature_kernel<N, MI, MS, AdrIntegrandsHom, true>, AdrIntegrandsHom{});
+  else rc = launch(dg_quadrature_kernel<N, MI, MS, AdrIntegrandsHom, false>, AdrIntegrandsHom{});
+  if (rc) return rc;
   CUDA_OK(cudaGetLastError());
   op->timing.launches_per_apply = 1;
   return B200FEM_OK;
