@@ -310,7 +310,7 @@ extern "C" int b200fem_operator_destroy(b200fem_operator* op) {
   b200fem_ctx* c = op->sp->mesh->ctx;
   cudaSetDevice(c->device); cudaStreamSynchronize(c->stream);
   for (void* p : {(void*)op->d_perm, (void*)op->d_bvec, (void*)op->d_dmask, (void*)op->d_dvals, (void*)op->d_aux, (void*)op->d_u, (void*)op->d_w, (void*)op->d_h, (void*)op->d_r,
-                  (void*)op->d_p, (void*)op->d_x, (void*)op->d_b, (void*)op->d_partial, (void*)op->d_sums, (void*)op->d_hist, (void*)op->d_cg, (void*)op->d_lag_rows, (void*)op->d_counter, (void*)op->d_rstar, (void*)op->d_s, (void*)op->d_tmp, (void*)op->d_partial5, (void*)op->d_sums5, (void*)op->d_bicg, (void*)op->d_dot_partial}) if (p) cudaFree(p);
+                  (void*)op->d_p, (void*)op->d_x, (void*)op->d_b, (void*)op->d_partial, (void*)op->d_sums, (void*)op->d_hist, (void*)op->d_cg, (void*)op->d_lag_rows, (void*)op->d_counter, (void*)op->d_rstar, (void*)op->d_s, (void*)op->d_tmp, (void*)op->d_partial5, (void*)op->d_sums5, (void*)op->d_bicg, (void*)op->d_dot_partial, (void*)op->d_nw_res, (void*)op->d_nw_dw, (void*)op->d_nw_w, (void*)op->d_nw_u}) if (p) cudaFree(p);
   jit_free(op);
   if (op->cg_graph) cudaGraphExecDestroy(op->cg_graph);
   for (double* q : op->gmres_v) if (q) cudaFree(q);

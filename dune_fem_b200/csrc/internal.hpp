@@ -9,6 +9,7 @@
 //   solvers.cu          CG / Jacobi-CG / BiCGStab / GMRES drivers, BLAS-1
 //   comm.cu             halo plans, peer-memory mailboxes, NCCL fallback, scalar all-reduce
 //   jit.cu              run-time compiled (NVRTC) integrands in the generic quadrature kernel
+//   newton.cu           NewtonInverseOperator over linearize + Krylov solve
 // No CPU compute fallback exists anywhere: every compute entry point needs a CUDA device.
 #pragma once
 #include <cuda.h>
@@ -81,6 +82,7 @@ struct b200fem_operator {
   double* d_lag_rows = nullptr; b200fem::LagKronRows lag_rows{}; std::vector<unsigned char> kron_tab; MarchMapCache* march_cache = nullptr;
   b200fem::HaloPlan halo; b200fem::HaloPlanDG halo_dg; b200fem::HaloPlanP2P halo_p2p; b200fem::HaloPlanAddP2P halo_add;
   const b200fem::BoxDev* active_box = nullptr;   // sub-box override (host-pointer pipeline)
+  double *d_nw_res = nullptr, *d_nw_dw = nullptr, *d_nw_w = nullptr, *d_nw_u = nullptr;   // NewtonInverseOperator work vectors (newton.cu)
   b200fem::JitState* jit = nullptr;             // run-time compiled integrands (jit.cu); null: the built-in ADR family
   bool in_bvec = false;                         // the load vector is being computed (data terms on, no recursion into ensure_bvec)
   bool want_exchange = false;                   // apply_dev_impl -> launcher: the Copy exchange of w is due after this apply

@@ -101,3 +101,47 @@ def KrylovInverseOperator(parameters=None):
     if method == "gmres":
         return GmresInverseOperator(parameters)
     raise NotImplementedError(f"KrylovInverseOperator: method {method!r} (cg, bicgstab and gmres are available)")
+
+
+class NewtonInverseOperator:
+    """Dune::Fem::NewtonInverseOperator (solver/newtoninverseoperator.hh:423-803): bind(op); __call__(u, w) solves L[w] = u from the
+    initial guess in w (u = None: L[w] = 0).  Parameters as fem.solver.nonlinear.*: tolerance (1e-6), maxiterations, linesearch.method
+    ("none" | "simple"), linear.{method, tolerance, errormeasure, maxiterations, gmres.restart}.  The Jacobian is the difference
+    quotient of AutomaticDifferenceLinearOperator; the whole iteration runs on the device (b200fem_newton_solve)."""
+    _METHODS = {"cg": 0, "bicgstab": 1, "gmres": 2}
+    FAILURES = {0: "Success", 1: "InvalidResidual", 4: "LineSearchFailed", 5: "TooManyIterations", 6: "TooManyLinearIterations", 7: "LinearSolverFailed"}
+
+    def __init__(self, parameters=None):
+        p = {"tolerance": 1e-6, "maxiterations": 2 ** 31 - 1, "linesearch.method": "none", "verbose": False,
+             "linear.method": "gmres", "linear.tolerance": 1e-8, "linear.errormeasure": "absolute", "linear.maxiterations": 1000, "linear.gmres.restart": 20}
+        for k, v in (parameters or {}).items():
+            p[k.replace("fem.solver.", "").replace("nonlinear.", "")] = v
+        self.parameters = p
+        self._op = None
+        self.iterations = self.linearIterations = 0
+        self.residual = float("nan")
+        self.failure = 0
+
+    def bind(self, op):
+        self._op = op
+
+    def unbind(self):
+        self._op = None
+
+    def __call__(self, u, w):
+        if self._op is None:
+            raise RuntimeError("NewtonInverseOperator: no operator bound")
+        p = self.parameters
+        it, lit, fail, res = C.c_int(), C.c_int(), C.c_int(), C.c_double()
+        capi.check(capi.lib().b200fem_newton_solve(self._op.handle, None if u is None else capi.ptr(u), capi.ptr(w), float(p["tolerance"]), int(min(p["maxiterations"], 2 ** 31 - 1)),
+                                                   self._METHODS[p["linear.method"]], float(p["linear.tolerance"]), int(p["linear.maxiterations"]),
+                                                   _ERRORMEASURE[p["linear.errormeasure"]], int(p["linear.gmres.restart"]), int(p["linesearch.method"] == "simple"),
+                                                   C.byref(it), C.byref(lit), C.byref(res), C.byref(fail)))
+        self.iterations, self.linearIterations, self.residual, self.failure = it.value, lit.value, res.value, fail.value
+        if p["verbose"]:
+            print(f"Newton iterations: {it.value}, linear iterations: {lit.value}, |residual| = {res.value} ({self.FAILURES.get(fail.value, fail.value)})")
+        return it.value
+
+    @property
+    def converged(self):
+        return self.failure == 0

@@ -230,6 +230,20 @@ int b200fem_gmres_solve(b200fem_operator* op, const double* b_host, double* x_ho
 int b200fem_gmres_solve_dev(b200fem_operator* op, const double* b_dev, double* x_dev, int restart, double epsilon, int max_iterations,
                             int tolerance_criteria, int* iterations, double* history);
 
+/* NewtonInverseOperator (solver/newtoninverseoperator.hh:690-803) -- the caller directly above the Krylov loop (FemScheme::solve):
+ * solves L[w] = u (u == NULL: L[w] = 0) from the initial guess in w.  Jacobian = the difference quotient of
+ * AutomaticDifferenceLinearOperator (b200fem_operator_linearize), linear solves by cg (0) / bicgstab (1) / gmres (2) with
+ * "fem.solver.nonlinear.linear.*" tolerance, criterion and iteration budget (the budget is shared by all Newton steps, :745-757),
+ * "fem.solver.nonlinear.{tolerance, maxiterations}", line search "none" (0) or "simple" (1, :588-629).  Linear operators take one step
+ * (:761, 791-792).  *failure receives NewtonFailure (:389-400: 0 Success, 1 InvalidResidual, 4 LineSearchFailed, 5 TooManyIterations,
+ * 6 TooManyLinearIterations, 7 LinearSolverFailed); *residual_norm = |L[w] - u| of the last iterate.  Everything runs on the device. */
+int b200fem_newton_solve(b200fem_operator* op, const double* u_host, double* w_host, double tolerance, int max_iterations, int linear_method,
+                         double linear_tolerance, int linear_max_iterations, int linear_tolerance_criteria, int gmres_restart, int line_search,
+                         int* iterations, int* linear_iterations, double* residual_norm, int* failure);
+int b200fem_newton_solve_dev(b200fem_operator* op, const double* u_dev, double* w_dev, double tolerance, int max_iterations, int linear_method,
+                             double linear_tolerance, int linear_max_iterations, int linear_tolerance_criteria, int gmres_restart, int line_search,
+                             int* iterations, int* linear_iterations, double* residual_norm, int* failure);
+
 /* BLAS-1 on device dof vectors (function/blockvectors/defaultblockvectors.hh:39-150) and the dot product over
  * primary dofs followed by the global sum (function/common/scalarproducts.hh:115-127) */
 int b200fem_dot_dev(b200fem_operator* op, const double* x_dev, const double* y_dev, double* result);

@@ -82,3 +82,58 @@ def test_compile_error_raises_with_the_log():
     with pytest.raises(_capi.B200FemError) as ei:
         op(np.zeros(space.size), np.empty(space.size))
     assert "undefined_symbol" in str(ei.value)
+
+
+def _oracle_newton(oop, w0, tol, maxit, lin_tol, lin_maxit, restart):
+    """NewtonInverseOperator::operator() (newtoninverseoperator.hh:690-803) restated on the oracle's pieces (u = 0, no line search)"""
+    w = w0.copy()
+    res = oop.apply(w)
+    delta = np.sqrt(res @ res)
+    it = lit = 0
+    while True:
+        oop.linearize(w)
+        if lin_maxit - lit <= 0:
+            break
+        li, dw, _ = oop.gmres_jacobian(res, np.zeros_like(w), lin_tol, lin_maxit - lit, 0, restart)
+        if li < 0:
+            lit = li
+            break
+        lit += li
+        w -= dw
+        res = oop.apply(w)
+        delta = np.sqrt(res @ res)
+        it += 1
+        if delta < tol or it >= maxit or lit >= lin_maxit:
+            break
+    return it, lit, delta, w
+
+
+@pytest.mark.parametrize("builtin", [True, False])
+def test_newton_inverse_operator(builtin):
+    """the non-linear reaction-diffusion problem solved in ONE call: same Newton iterates as the restatement on the oracle (iteration
+    counts, final residual and solution), built-in model and run-time compiled integrands"""
+    n, lo, hi = [4, 4, 3], [-1.0] * 3, [1.0] * 3
+    space, osp = spaces("hier", 3, 2, n)
+    space = fem.space.dglegendre(fem.structuredGrid(lo, hi, n), order=2)
+    osp = ol.Space(n, lo, hi, ol.DG_LEGENDRE_HIER, 2)
+    if builtin:
+        kw = dict(eps=0.5, b=(1.0, 0.0, 0.0), c=1.0, gamma=2.0, beta=80.0, dirichlet_mask=0b000011, data=1)
+        op, oop = fem.operator.galerkin(space, **kw), ol.Operator(osp, skeleton=True, boundary=True, **kw)
+    else:
+        const = [0.5, 1.0, -0.5, 0.25, 80.0, 1.0, 2.0]
+        op, oop = fem.operator.galerkinJit(space, SOURCE, const), ol.UserOperator(osp, SOURCE, const)
+    newton = fem.solver.NewtonInverseOperator({"tolerance": 1e-9, "linear.method": "gmres", "linear.tolerance": 1e-11, "linear.maxiterations": 4000, "linear.gmres.restart": 30})
+    newton.bind(op)
+    w = np.zeros(space.size)
+    newton(None, w)
+    it, lit, delta, w_ref = _oracle_newton(oop, np.zeros(space.size), 1e-9, 2 ** 31 - 1, 1e-11, 4000, 30)
+    assert newton.converged and newton.iterations == it and 2 <= it <= 12
+    assert abs(newton.linearIterations - lit) <= max(3, lit // 50)
+    assert newton.residual < 1e-9 and np.abs(oop.apply(w)).max() < 1e-8
+    assert rel(w, w_ref) < 1e-8
+    # a linear iteration budget that is too small: NewtonFailure::LinearSolverFailed (the Krylov solver reports a negative count)
+    newton = fem.solver.NewtonInverseOperator({"tolerance": 1e-9, "linear.tolerance": 1e-13, "linear.maxiterations": 5, "linear.gmres.restart": 5})
+    newton.bind(op)
+    w = np.zeros(space.size)
+    newton(None, w)
+    assert not newton.converged and newton.failure in (6, 7)
