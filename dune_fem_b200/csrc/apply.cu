@@ -171,7 +171,7 @@ int apply_host(b200fem_operator* op, const double* u, double* w, bool linear) {
   b200fem_space* s = op->sp; b200fem_ctx* c = s->mesh->ctx; cudaStream_t st = c->stream; const size_t bytes = sizeof(double) * (size_t)s->size;
   CUDA_OK(cudaSetDevice(c->device));
   int rc = ensure_staging(op); if (rc) return rc;
-  if (op->host_pipeline_chunks >= 2 && !(linear && op->jac_mode) && s->kind != B200FEM_LAGRANGE && c->world == 1 && s->box.dim == 3 && bytes >= (8u << 20) && s->box.n[2] >= 16 &&
+  if (op->host_pipeline_chunks >= 2 && !(linear && op->jac_mode) && s->kind != B200FEM_LAGRANGE && s->dim_range == 1 && c->world == 1 && s->box.dim == 3 && bytes >= (8u << 20) && s->box.n[2] >= 16 &&
       default_quadrature(op))
     return apply_host_pipelined(op, u, w, linear, std::min(std::min(op->host_pipeline_chunks, 16), s->box.n[2] / 4));
   CUDA_OK(cudaMemcpyAsync(op->d_u, u, bytes, cudaMemcpyHostToDevice, st));

@@ -167,6 +167,15 @@ static void build_adaptive_leaf_map(b200fem_space* s) {
   }
 }
 
+extern "C" int b200fem_space_create_vector(b200fem_mesh* mesh, int kind, int order, int numbering, int dim_range, b200fem_space** out) {
+  REQUIRE(dim_range >= 1 && dim_range <= 4, B200FEM_ERR_NOT_IMPLEMENTED, "space_create_vector: dimRange 1..4");
+  REQUIRE(dim_range == 1 || (mesh && mesh->ctx->world == 1), B200FEM_ERR_NOT_IMPLEMENTED, "vector-valued spaces on distributed meshes");
+  REQUIRE(dim_range == 1 || order <= 3, B200FEM_ERR_NOT_IMPLEMENTED, "vector-valued spaces: orders 1..3");
+  int rc = b200fem_space_create(mesh, kind, order, numbering, out); if (rc) return rc;
+  (*out)->dim_range = dim_range; (*out)->size *= dim_range;        // space.size() = blockMapper().size() * localBlockSize
+  return B200FEM_OK;
+}
+extern "C" int b200fem_space_dim_range(b200fem_space* s, int32_t* dim_range) { REQUIRE(s && dim_range, B200FEM_ERR_INVALID, "null"); *dim_range = s->dim_range; return B200FEM_OK; }
 extern "C" int b200fem_space_create(b200fem_mesh* mesh, int kind, int order, int numbering, b200fem_space** out) {
   REQUIRE(mesh && out, B200FEM_ERR_INVALID, "space_create: null argument");
   REQUIRE(kind >= 0 && kind <= 3, B200FEM_ERR_INVALID, "space_create: unknown space kind");
@@ -265,6 +274,10 @@ static void mark_dirichlet(b200fem_operator* op) {
 
 extern "C" int b200fem_operator_create(b200fem_space* s, const b200fem_model* model, b200fem_operator** out) {
   REQUIRE(s && model && out, B200FEM_ERR_INVALID, "operator_create: null argument");
+  REQUIRE(s->dim_range == 1, B200FEM_ERR_NOT_IMPLEMENTED, "the built-in advection-diffusion-reaction integrands are scalar: vector-valued spaces take run-time compiled integrands (b200fem_operator_create_jit)");
+  return b200fem::operator_create_impl(s, model, out);
+}
+int b200fem::operator_create_impl(b200fem_space* s, const b200fem_model* model, b200fem_operator** out) {
   REQUIRE(!(model->strong_dirichlet && s->kind != B200FEM_LAGRANGE), B200FEM_ERR_INVALID, "strong Dirichlet constraints need a Lagrange space");
   b200fem_ctx* c = s->mesh->ctx;
   CUDA_OK(cudaSetDevice(c->device));

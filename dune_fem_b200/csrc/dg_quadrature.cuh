@@ -98,15 +98,45 @@ template <int Q, int N> __device__ __forceinline__ void quad_mvt_add(const doubl
     for (int q = 0; q < Q; ++q) s = fma(M[q * N + c], in[q], s); out[c] = s; }
 }
 
+// ---- vector-valued spaces (dimRange R > 1; DofVector blocks of R components, function/blockvectors/defaultblockvectors.hh:284-294,
+// vectorial basis phi_i e_c with local index i * R + c, space/shapefunctionset/vectorial.hh:508-526).  The sum-factorised sweeps act on one component at a
+// time, so the R components of an element occupy R neighbouring element SLOTS (= neighbouring lanes of a warp) and run the scalar
+// code unchanged; only the integrand needs all components of (u, grad u) at a point: the lanes collect them with shuffles,
+// every lane evaluates the integrand and keeps its own component of the result. ----
+template <int R> struct PointValueV { double u[R]; double du[R][3]; };   // DomainValueType of a range-R space
+template <int R> struct PointRangeV { double s[R]; double F[R][3]; };    // RangeValueType: tested as s_c phi + F_c . grad phi per component
+__host__ __device__ constexpr int quad_pow2(int r) { int p = 1; while (p < r) p *= 2; return p; }
+#ifdef __CUDACC__
+template <int R> __device__ __forceinline__ PointValueV<R> quad_collect(const PointValue& pv, const unsigned mask) {
+  constexpr int RS = quad_pow2(R); PointValueV<R> v;
+#pragma unroll
+  for (int c = 0; c < R; ++c) {
+    v.u[c] = __shfl_sync(mask, pv.u, c, RS);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) v.du[c][d] = __shfl_sync(mask, pv.du[d], c, RS);
+  }
+  return v;
+}
+template <int R> __device__ __forceinline__ PointRange quad_pick(const PointRangeV<R>& r, const int comp) {
+  PointRange o; o.s = r.s[0]; o.F[0] = r.F[0][0]; o.F[1] = r.F[0][1]; o.F[2] = r.F[0][2];
+#pragma unroll
+  for (int c = 1; c < R; ++c) if (comp == c) { o.s = r.s[c]; o.F[0] = r.F[c][0]; o.F[1] = r.F[c][1]; o.F[2] = r.F[c][2]; }
+  return o;
+}
+#endif
+
 // All integrals of one element: U (tensor-ordered dofs, padded lines, shared memory) -> W.  Called by every thread of the CTA
 // (it synchronises); `lt` is the thread's index inside its element group (P x P threads), `lc` the element's local
 // coordinates, `e` its local index, u the global vector (only read for skeleton neighbours of DG spaces), perm the
 // tensor -> stored permutation of the neighbours' dofs (null: identity).
 // GEN = true: sub-basis spaces and periodic grids (run-time dof count, wrap-around neighbours); GEN = false compiles both out
-template <int N, int MI, int MS, class Integrands, bool GEN = false>
+// R > 1: `comp` is the thread's component and `cmask` the lanes holding the components of its element (all of them take the same
+// path through this function: they share lt, lc and `active`).
+template <int N, int MI, int MS, class Integrands, bool GEN = false, int R = 1>
 __device__ __forceinline__ void element_integrals(const QuadTabDev<N, MI, MS>& T, const BoxDev& box, const Integrands& I, const int* perm,
                                                   const double* __restrict__ u, const bool active, const int (&lc)[3],
-                                                  const long long e, const int lt, double* U, double* W, double* S) {
+                                                  const long long e, const int lt, double* U, double* W, double* S,
+                                                  const int comp = 0, const unsigned cmask = 0xffffffffu) {
   using Cfg = DgQuadCfg<N, MI, MS>;
   constexpr int P = Cfg::P, LN = Cfg::LN, LM = Cfg::LM, LS = Cfg::LS, N3 = N * N * N;
   const int la = lt / P, lb = lt % P;
@@ -148,7 +178,9 @@ __device__ __forceinline__ void element_integrals(const QuadTabDev<N, MI, MS>& T
     for (int q0 = 0; q0 < MI; ++q0) {
       xq[0] = box.lo[0] + box.h[0] * ((box.origin[0] + lc[0]) + T.xi[q0]);
       PointValue pv; pv.u = v[q0]; pv.du[0] = dx[q0] * ih0; pv.du[1] = dy[q0] * ih1; pv.du[2] = dz[q0] * ih2;
-      const PointRange r = I.interior(xq, pv);
+      PointRange r;
+      if constexpr (R == 1) r = I.interior(xq, pv);
+      else r = quad_pick<R>(I.interior(xq, quad_collect<R>(pv, cmask)), comp);
       const double wq = T.wi[q0] * w12;               // qp.weight() * integrationElement (galerkin.hh:353)
       rs[q0] = r.s * wq; rx[q0] = r.F[0] * (wq * ih0); ry[q0] = r.F[1] * (wq * ih1); rz[q0] = r.F[2] * (wq * ih2);
     }
@@ -278,14 +310,27 @@ __device__ __forceinline__ void element_integrals(const QuadTabDev<N, MI, MS>& T
           nb.u = val[1][qa]; nb.du[0] = d == 0 ? gn_ : ga; nb.du[1] = d == 1 ? gn_ : (d == 0 ? ga : gb); nb.du[2] = d == 2 ? gn_ : gb;
         }
         PointRange r; r.s = 0; r.F[0] = r.F[1] = r.F[2] = 0;
-        if (nb_exists) {
-          if (I.m.has_skeleton) {
-            PointRange rin, rout;
-            if (own_inside) { I.skeleton(xq, d, s ? 1.0 : -1.0, ihe, own, nb, rin, rout); r = rin; }
-            else            { I.skeleton(xq, d, s ? -1.0 : 1.0, ihe, nb, own, rin, rout); r = rout; }
+        if constexpr (R == 1) {
+          if (nb_exists) {
+            if (I.m.has_skeleton) {
+              PointRange rin, rout;
+              if (own_inside) { I.skeleton(xq, d, s ? 1.0 : -1.0, ihe, own, nb, rin, rout); r = rin; }
+              else            { I.skeleton(xq, d, s ? -1.0 : 1.0, ihe, nb, own, rin, rout); r = rout; }
+            }
+          } else if (I.m.has_boundary && d < box.dim) {         // (a 2-D mesh is one layer of cells: its x2-faces are no boundary)
+            r = I.boundary(d, s, ihe, xq, own);
           }
-        } else if (I.m.has_boundary && d < box.dim) {         // (a 2-D mesh is one layer of cells: its x2-faces are no boundary)
-          r = I.boundary(d, s, ihe, xq, own);
+        } else {
+          const PointValueV<R> ownv = quad_collect<R>(own, cmask), nbv = quad_collect<R>(nb, cmask);
+          if (nb_exists) {
+            if (I.m.has_skeleton) {
+              PointRangeV<R> rin, rout;
+              if (own_inside) { I.skeleton(xq, d, s ? 1.0 : -1.0, ihe, ownv, nbv, rin, rout); r = quad_pick<R>(rin, comp); }
+              else            { I.skeleton(xq, d, s ? -1.0 : 1.0, ihe, nbv, ownv, rin, rout); r = quad_pick<R>(rout, comp); }
+            }
+          } else if (I.m.has_boundary && d < box.dim) {
+            r = quad_pick<R>(I.boundary(d, s, ihe, xq, ownv), comp);
+          }
         }
         const double wq = T.ws[qa] * T.ws[qb] * area;
         const double Fn = d == 0 ? r.F[0] : d == 1 ? r.F[1] : r.F[2], Fa = d == 0 ? r.F[1] : r.F[0], Fb = d == 2 ? r.F[1] : r.F[2];
@@ -334,7 +379,7 @@ __device__ __forceinline__ void element_integrals(const QuadTabDev<N, MI, MS>& T
   }
 }
 
-template <int N, int MI, int MS, class Integrands, bool GEN>
+template <int N, int MI, int MS, class Integrands, bool GEN, int R = 1>
 __global__ void __launch_bounds__(DgQuadCfg<N, MI, MS>::kThreads)
 dg_quadrature_kernel(const __grid_constant__ QuadTabDev<N, MI, MS> T, const __grid_constant__ BoxDev box,
                      const __grid_constant__ Integrands I, const int* __restrict__ perm_g, const int nbs_arg,
@@ -350,9 +395,14 @@ dg_quadrature_kernel(const __grid_constant__ QuadTabDev<N, MI, MS> T, const __gr
   int* tinv = perm + N3;                                                          // stored index -> tensor index (padded offset)
   int* ecs = tinv + N3;                                                           // element coordinates per slot (4 ints)
 
+  // range-R spaces: RS = R rounded up to a power of two slots per element (slot % RS = component; the slots c >= R idle along)
+  constexpr int RS = quad_pow2(R);
+  static_assert(R == 1 || RS <= EB, "dimRange: the components of an element must fit the element slots of a CTA");
   const int tid = threadIdx.x, es = Cfg::slot(tid), lt = Cfg::lane(tid);
+  const int comp = es % RS;
+  const unsigned cmask = R == 1 ? 0xffffffffu : (((1u << RS) - 1u) << ((tid & 31) / RS * RS));
   const int on0 = box.own_hi[0] - box.own_lo[0], on1 = box.own_hi[1] - box.own_lo[1];
-  const long long oe = (long long)blockIdx.x * EB + es;
+  const long long oe = (long long)blockIdx.x * (EB / RS) + es / RS;
   const bool active = lt < Cfg::T2 && oe < n_owned;
   int lc[3] = {0, 0, 0};
   if (active) {
@@ -361,7 +411,7 @@ dg_quadrature_kernel(const __grid_constant__ QuadTabDev<N, MI, MS> T, const __gr
     lc[2] = box.own_lo[2] + (int)(oe / ((long long)on0 * on1));
   }
   const long long e = lc[0] + (long long)box.n[0] * (lc[1] + (long long)box.n[1] * lc[2]);
-  if (lt == 0) { elem_of[es] = active ? e : -1; ecs[4 * es] = lc[0]; ecs[4 * es + 1] = lc[1]; ecs[4 * es + 2] = lc[2]; }
+  if (lt == 0) { elem_of[es] = active && comp < R ? e : -1; ecs[4 * es] = lc[0]; ecs[4 * es + 1] = lc[1]; ecs[4 * es + 2] = lc[2]; }
   // The space may be a SUB-BASIS of the full tensor basis the kernel works on: nbs <= N^3 stored dofs per element, perm_g[t] = -1
   // for tensor functions it does not hold (2-D Q_k: functions constant in x2; dgonb P_k: total degree <= k).  Their coefficients
   // are zero on input and their residuals are dropped on output -- the Galerkin operator of the sub-space, exactly.
@@ -383,7 +433,8 @@ dg_quadrature_kernel(const __grid_constant__ QuadTabDev<N, MI, MS> T, const __gr
       const int idx = tid + k * Cfg::kThreads, s2 = idx / nbs, j = idx % nbs;
       const long long e2 = idx < EB * nbs ? elem_of[s2] : -1;
       base[k] = e2 >= 0 ? s2 * ELEM : -1; jj[k] = j;
-      if (e2 >= 0) own[k] = u[e2 * nbs + j];
+      const int cc = R == 1 ? 0 : s2 % RS;                                // dof (element, j, component) = (e * nbs + j) * R + c
+      if (e2 >= 0) own[k] = u[(e2 * nbs + j) * R + cc];
 #pragma unroll
       for (int f = 0; f < 6; ++f) {
         const int d = f >> 1;
@@ -392,7 +443,7 @@ dg_quadrature_kernel(const __grid_constant__ QuadTabDev<N, MI, MS> T, const __gr
           const int c0 = ecs[4 * s2 + d]; int cn = c0 + ((f & 1) ? 1 : -1);
           const long long step = d == 0 ? 1 : d == 1 ? estep1 : estep2;
           if (GEN && (cn < 0 || cn >= box.n[d]) && ((box.periodic >> d) & 1)) cn = cn < 0 ? box.n[d] - 1 : 0;
-          if (cn >= 0 && cn < box.n[d]) { have[k][f] = true; nbv[k][f] = u[(e2 + (long long)(cn - c0) * step) * nbs + j]; }
+          if (cn >= 0 && cn < box.n[d]) { have[k][f] = true; nbv[k][f] = u[((e2 + (long long)(cn - c0) * step) * nbs + j) * R + cc]; }
         }
       }
     }
@@ -409,15 +460,16 @@ dg_quadrature_kernel(const __grid_constant__ QuadTabDev<N, MI, MS> T, const __gr
   __syncthreads();
 
   double* U = smem + (size_t)es * ELEM;
-  element_integrals<N, MI, MS, Integrands, GEN>(T, box, I, perm, u, active, lc, e, lt, U, U + Cfg::kU, U + 2 * Cfg::kU);
+  element_integrals<N, MI, MS, Integrands, GEN, R>(T, box, I, perm, u, active, lc, e, lt, U, U + Cfg::kU, U + 2 * Cfg::kU, comp, cmask);
 
   // ---- write w_K once (tensor order -> stored order), optionally w = A u - b ----
   for (int idx = tid; idx < EB * nbs; idx += blockDim.x) {
     const int s2 = idx / nbs, j = idx % nbs; const long long e2 = elem_of[s2];
     if (e2 >= 0) {
       double val = smem[(size_t)s2 * ELEM + Cfg::kU + tinv[j]] * out_scale;      // out_scale: inverse mass of MOLGalerkinOperator (1 otherwise)
-      if (bvec) val -= bvec[e2 * nbs + j];
-      w[e2 * nbs + j] = val;
+      const long long g = (e2 * nbs + j) * R + (R == 1 ? 0 : s2 % RS);
+      if (bvec) val -= bvec[g];
+      w[g] = val;
     }
   }
 }

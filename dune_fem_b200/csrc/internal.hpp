@@ -53,6 +53,7 @@ struct b200fem_mesh {
 };
 struct b200fem_space {
   b200fem_mesh* mesh; int kind, order, numbering, n1, nb; long long size, elements;
+  int dim_range = 1;                     // dimRange: dof blocks of dim_range components (size = blocks * dim_range); > 1: run-time compiled integrands only
   b200fem::BoxDev box;                   // DG: mesh box with ghosts; Lagrange: owned elements only
   b200fem::Tab1D tab; std::vector<int> perm;   // DG: tensor index -> stored local index over the full n1^3 tensor basis (-1: not in the space)
   bool tensor_full = false;              // DG: the space is the whole 3-D tensor basis (the Kronecker kernels apply)
@@ -119,6 +120,7 @@ int launch_lagrange_kronecker(b200fem_operator* op, const double* u, double* w, 
 void free_march_cache(b200fem_operator* op);
 
 // ---- jit.cu ----
+int operator_create_impl(b200fem_space* s, const b200fem_model* model, b200fem_operator** out);   // b200fem_operator_create without the scalar-space check
 int apply_jit(b200fem_operator* op, const double* u, double* w, bool linear);   // w = L[u] or L[u] - L[0] with compiled integrands
 void jit_free(b200fem_operator* op);
 

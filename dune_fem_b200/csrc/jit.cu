@@ -15,6 +15,7 @@
 
 #include "internal.hpp"
 #include "jit_integrands.cuh"
+#include "lagrange_quadrature.cuh"
 #include "launch_dgq.hpp"
 
 namespace b200fem {
@@ -75,26 +76,36 @@ std::string csrc_dir() {
   return (s == std::string::npos ? std::string(".") : p.substr(0, s)) + "/../csrc";
 }
 
-std::string program_text(const std::string& user, bool skel, bool bnd, int N, int MI, int MS, std::string* name_expr) {
+// which kernel the integrands are compiled into
+enum JitVariant { kJitDg = 0, kJitLagrange3d = 1, kJitLagrange2d = 2 };
+
+std::string program_text(const std::string& user, bool skel, bool bnd, int N, int MI, int MS, int R, int variant, std::string* name_expr) {
+  const std::string rs = std::to_string(R);
+  // scalar spaces: PointValue / PointRange; range-R spaces: VectorValue = PointValueV<R>, VectorRange = PointRangeV<R>
+  const std::string V = R == 1 ? "PointValue" : "PointValueV<" + rs + ">", G = R == 1 ? "PointRange" : "PointRangeV<" + rs + ">";
   std::string t;
-  t += "#include \"dg_quadrature.cuh\"\n#include \"jit_integrands.cuh\"\n";
-  t += "namespace b200fem {\nnamespace user {\n#line 1 \"integrands\"\n" + user + "\n}  // namespace user\n";
+  t += "#include \"lagrange_quadrature.cuh\"\n#include \"jit_integrands.cuh\"\n";
+  t += "namespace b200fem {\nnamespace user {\nconstexpr int dimRange = " + rs + ";\nusing VectorValue = PointValueV<dimRange>;\nusing VectorRange = PointRangeV<dimRange>;\n#line 1 \"integrands\"\n" + user + "\n}  // namespace user\n";
   t += "struct JitIntegrands : JitIntegrandsBase {\n"
-       "  __device__ PointRange interior(const double* x, const PointValue& v) const { PointRange r; r.s = 0; r.F[0] = r.F[1] = r.F[2] = 0; user::interior(x, v, r, c, dim); return r; }\n"
-       "  __device__ void skeleton(const double* x, int axis, double sign, double ihe, const PointValue& in, const PointValue& out, PointRange& rin, PointRange& rout) const {\n"
-       "    rin.s = rout.s = 0; rin.F[0] = rin.F[1] = rin.F[2] = rout.F[0] = rout.F[1] = rout.F[2] = 0;\n";
+       "  __device__ static void zero(" + G + "& r) { double* p = reinterpret_cast<double*>(&r); for (int i = 0; i < (int)(sizeof(" + G + ") / sizeof(double)); ++i) p[i] = 0; }\n"
+       "  __device__ " + G + " interior(const double* x, const " + V + "& v) const { " + G + " r; zero(r); user::interior(x, v, r, c, dim); return r; }\n"
+       "  __device__ void skeleton(const double* x, int axis, double sign, double ihe, const " + V + "& in, const " + V + "& out, " + G + "& rin, " + G + "& rout) const {\n"
+       "    zero(rin); zero(rout);\n";
   if (skel) t += "    user::skeleton(x, axis, sign, ihe, in, out, rin, rout, c, dim);\n";
-  t += "  }\n  __device__ PointRange boundary(int axis, int side, double ihbnd, const double* x, const PointValue& v) const { PointRange r; r.s = 0; r.F[0] = r.F[1] = r.F[2] = 0;\n";
+  t += "  }\n  __device__ " + G + " boundary(int axis, int side, double ihbnd, const double* x, const " + V + "& v) const { " + G + " r; zero(r);\n";
   if (bnd) t += "    user::boundary(x, axis, side, ihbnd, v, r, c, dim);\n";
   t += "    return r; }\n};\n}  // namespace b200fem\n";
-  *name_expr = "b200fem::dg_quadrature_kernel<" + std::to_string(N) + ", " + std::to_string(MI) + ", " + std::to_string(MS) + ", b200fem::JitIntegrands, true>";
+  const std::string n = std::to_string(N);
+  if (variant == kJitDg) *name_expr = "b200fem::dg_quadrature_kernel<" + n + ", " + std::to_string(MI) + ", " + std::to_string(MS) + ", b200fem::JitIntegrands, true, " + rs + ">";
+  else if (variant == kJitLagrange3d) *name_expr = "b200fem::lagrange3d_quadrature_kernel<" + n + ", b200fem::JitIntegrands, " + rs + ">";
+  else *name_expr = "b200fem::lagrange2d_quadrature_kernel<" + n + ", b200fem::JitIntegrands, " + rs + ">";
   return t;
 }
 
 // NVRTC: program text -> cubin + lowered kernel name.  No device needed.
-int compile(const std::string& user, bool skel, bool bnd, int N, int MI, int MS, std::vector<char>* cubin, std::string* lowered, std::string* log) {
+int compile(const std::string& user, bool skel, bool bnd, int N, int MI, int MS, int R, int variant, std::vector<char>* cubin, std::string* lowered, std::string* log) {
   if (!g_nvrtc.load()) { if (log) *log = "libnvrtc.so.12 could not be loaded"; return B200FEM_ERR_NOT_IMPLEMENTED; }
-  std::string expr; const std::string text = program_text(user, skel, bnd, N, MI, MS, &expr);
+  std::string expr; const std::string text = program_text(user, skel, bnd, N, MI, MS, R, variant, &expr);
   void* prog = nullptr;
   if (g_nvrtc.CreateProgram(&prog, text.c_str(), "b200fem_jit.cu", 0, nullptr, nullptr) != 0) { if (log) *log = "nvrtcCreateProgram failed"; return B200FEM_ERR_CUDA; }
   g_nvrtc.AddNameExpression(prog, expr.c_str());
@@ -120,7 +131,7 @@ struct JitKernel { CUmodule mod = nullptr; CUfunction fn = nullptr; };
 struct JitState {
   std::string source; bool skel = false, bnd = false;
   double c[kJitMaxConstants] = {}; int nc = 0;
-  std::map<std::tuple<int, int, int>, JitKernel> kernels;
+  std::map<std::tuple<int, int, int, int>, JitKernel> kernels;      // (N, MI, MS, variant)
   double* d_l0 = nullptr; unsigned long long l0_version = ~0ull;     // L[0] for apply_linear, tied to the operator's state version
   double* d_zero = nullptr;
 };
@@ -133,35 +144,98 @@ void jit_free(b200fem_operator* op) {
   delete op->jit; op->jit = nullptr;
 }
 
-template <int N, int MI, int MS> static int launch_jit_t(b200fem_operator* op, const double* u, double* w, const double* sub) {
-  using Cfg = DgQuadCfg<N, MI, MS>; JitState* J = op->jit; b200fem_ctx* ctx = op->sp->mesh->ctx;
-  const BoxDev& b = op->active_box ? *op->active_box : op->sp->box;
-  JitKernel& K = J->kernels[std::make_tuple(N, MI, MS)];
+// the compiled kernel of one (order, rules, variant) configuration: NVRTC on first use, cached per operator
+static int jit_kernel(b200fem_operator* op, int N, int MI, int MS, int variant, size_t smem, JitKernel** out) {
+  JitState* J = op->jit;
+  JitKernel& K = J->kernels[std::make_tuple(N, MI, MS, variant)];
   if (!K.fn) {
     REQUIRE(!op->capturing, B200FEM_ERR_INVALID, "run-time compilation inside a graph capture (apply once before solving)");
     REQUIRE(g_drv.load(), B200FEM_ERR_CUDA, "driver entry points (cuModuleLoadData, cuLaunchKernel) unavailable");
     std::vector<char> cubin; std::string lowered, log;
-    int rc = compile(J->source, J->skel, J->bnd, N, MI, MS, &cubin, &lowered, &log);
+    int rc = compile(J->source, J->skel, J->bnd, N, MI, MS, op->sp->dim_range, variant, &cubin, &lowered, &log);
     if (rc) return fail(rc, "integrands do not compile:\n" + log);
     if (g_drv.ModuleLoadData(&K.mod, cubin.data()) != CUDA_SUCCESS) return fail(B200FEM_ERR_CUDA, "cuModuleLoadData failed for the compiled integrands");
     if (g_drv.ModuleGetFunction(&K.fn, K.mod, lowered.c_str()) != CUDA_SUCCESS) return fail(B200FEM_ERR_CUDA, "compiled kernel not found in its module");
-    if (g_drv.FuncSetAttribute(K.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)Cfg::smem_bytes()) != CUDA_SUCCESS) return fail(B200FEM_ERR_CUDA, "cuFuncSetAttribute(max dynamic shared memory) failed");
+    if (smem && g_drv.FuncSetAttribute(K.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem) != CUDA_SUCCESS) return fail(B200FEM_ERR_CUDA, "cuFuncSetAttribute(max dynamic shared memory) failed");
   }
+  *out = &K; return B200FEM_OK;
+}
+static JitIntegrandsBase jit_params(b200fem_operator* op, const BoxDev& b) {
+  JitIntegrandsBase I; std::memset(&I, 0, sizeof(I)); I.m = op->model; I.dim = b.dim; I.with_data = 1; std::memcpy(I.c, op->jit->c, sizeof(I.c));
+  return I;
+}
+// slots of a CTA per element: the components of a range-R space sit in RS = R rounded up to a power of two neighbouring slots
+static int slots_per_element(int R) { int p = 1; while (p < R) p *= 2; return p; }
+
+template <int N, int MI, int MS> static int launch_jit_t(b200fem_operator* op, const double* u, double* w, const double* sub) {
+  using Cfg = DgQuadCfg<N, MI, MS>; b200fem_ctx* ctx = op->sp->mesh->ctx;
+  const BoxDev& b = op->active_box ? *op->active_box : op->sp->box;
+  const int epb = Cfg::EB / slots_per_element(op->sp->dim_range);
+  REQUIRE(epb >= 1, B200FEM_ERR_NOT_IMPLEMENTED, "compiled integrands: dimRange too large for this order");
+  JitKernel* K = nullptr; int rc = jit_kernel(op, N, MI, MS, kJitDg, Cfg::smem_bytes(), &K); if (rc) return rc;
   long long n_owned = (long long)(b.own_hi[0] - b.own_lo[0]) * (b.own_hi[1] - b.own_lo[1]) * (b.own_hi[2] - b.own_lo[2]);
-  const unsigned grid = (unsigned)((n_owned + Cfg::EB - 1) / Cfg::EB);
+  const unsigned grid = (unsigned)((n_owned + epb - 1) / epb);
   auto tab = make_quad_tab<N, MI, MS>(true, N - 1);
   BoxDev box = b;
-  JitIntegrandsBase I; std::memset(&I, 0, sizeof(I)); I.m = op->model; I.dim = b.dim; I.with_data = 1; std::memcpy(I.c, J->c, sizeof(I.c));
+  JitIntegrandsBase I = jit_params(op, b);
   const int* perm = op->d_perm; int nbs = op->sp->nb; double scale = mass_scale(op);
   void* args[] = {&tab, &box, &I, &perm, &nbs, &u, &w, &sub, &n_owned, &scale};
-  if (g_drv.LaunchKernel(K.fn, grid, 1, 1, Cfg::kThreads, 1, 1, (unsigned)Cfg::smem_bytes(), (CUstream)ctx->stream, args, nullptr) != CUDA_SUCCESS)
+  if (g_drv.LaunchKernel(K->fn, grid, 1, 1, Cfg::kThreads, 1, 1, (unsigned)Cfg::smem_bytes(), (CUstream)ctx->stream, args, nullptr) != CUDA_SUCCESS)
     return fail(B200FEM_ERR_CUDA, "cuLaunchKernel failed for the compiled integrands");
   op->timing.launches_per_apply = 1;
   return B200FEM_OK;
 }
 
+// continuous Lagrange spaces: w.clear(), then one launch per colour (2^dim colours, plain read-modify-write, lagrange_quadrature.cuh)
+template <int N> static int launch_jit_lagrange_t(b200fem_operator* op, const double* u, double* w) {
+  using Cfg = DgQuadCfg<N, N, N>; b200fem_space* s = op->sp; b200fem_ctx* ctx = s->mesh->ctx; cudaStream_t st = ctx->stream;
+  const BoxDev& b = op->active_box ? *op->active_box : s->box;
+  CUDA_OK(cudaMemsetAsync(w, 0, sizeof(double) * (size_t)s->size, st));
+  BoxDev box = b; JitIntegrandsBase I = jit_params(op, b); LagrangeLayoutDev L = s->lay;
+  int launches = 1;
+  if (b.dim == 3) {
+    const int epb = Cfg::EB / slots_per_element(s->dim_range);
+    REQUIRE(epb >= 1, B200FEM_ERR_NOT_IMPLEMENTED, "compiled integrands: dimRange too large for this order");
+    JitKernel* K = nullptr; int rc = jit_kernel(op, N, N, N, kJitLagrange3d, Cfg::smem_bytes(), &K); if (rc) return rc;
+    QuadTabDev<N, N, N> T; const Tab1D& t = s->tab;
+    for (int i = 0; i < N * N; ++i) { T.Bi[i] = T.Bs[i] = t.B[i]; T.Gi[i] = T.Gs[i] = t.G[i]; }
+    for (int i = 0; i < N; ++i) { T.xi[i] = T.xs[i] = t.x[i]; T.wi[i] = T.ws[i] = t.w[i]; T.phi[0][i] = t.phi0[i]; T.phi[1][i] = t.phi1[i]; T.dphi[0][i] = t.dphi0[i]; T.dphi[1][i] = t.dphi1[i]; }
+    for (int c = 0; c < 8; ++c) {
+      int c0 = c & 1, c1 = (c >> 1) & 1, c2 = c >> 2;
+      int m0 = (b.n[0] - c0 + 1) / 2, m1 = (b.n[1] - c1 + 1) / 2, m2 = (b.n[2] - c2 + 1) / 2;
+      long long nc = (long long)m0 * m1 * m2; if (nc <= 0) continue;
+      void* args[] = {&T, &box, &I, &L, &u, &w, &c0, &c1, &c2, &m0, &m1, &nc};
+      if (g_drv.LaunchKernel(K->fn, (unsigned)((nc + epb - 1) / epb), 1, 1, Cfg::kThreads, 1, 1, (unsigned)Cfg::smem_bytes(), (CUstream)st, args, nullptr) != CUDA_SUCCESS)
+        return fail(B200FEM_ERR_CUDA, "cuLaunchKernel failed for the compiled integrands");
+      ++launches;
+    }
+  } else {
+    JitKernel* K = nullptr; int rc = jit_kernel(op, N, N, N, kJitLagrange2d, 0, &K); if (rc) return rc;
+    DgTabDev<N> T; const Tab1D& t = s->tab;
+    for (int i = 0; i < N * N; ++i) { T.B[i] = t.B[i]; T.G[i] = t.G[i]; }
+    for (int i = 0; i < N; ++i) { T.x[i] = t.x[i]; T.w[i] = t.w[i]; T.phi[0][i] = t.phi0[i]; T.phi[1][i] = t.phi1[i]; T.dphi[0][i] = t.dphi0[i]; T.dphi[1][i] = t.dphi1[i]; }
+    for (int c = 0; c < 4; ++c) {
+      int c0 = c & 1, c1 = c >> 1; int m0 = (b.n[0] - c0 + 1) / 2, m1 = (b.n[1] - c1 + 1) / 2;
+      long long nc = (long long)m0 * m1; if (nc <= 0) continue;
+      void* args[] = {&T, &box, &I, &L, &u, &w, &c0, &c1, &m0, &nc};
+      if (g_drv.LaunchKernel(K->fn, (unsigned)((nc + 127) / 128), 1, 1, 128, 1, 1, 0, (CUstream)st, args, nullptr) != CUDA_SUCCESS)
+        return fail(B200FEM_ERR_CUDA, "cuLaunchKernel failed for the compiled integrands");
+      ++launches;
+    }
+  }
+  op->timing.launches_per_apply = launches;
+  return B200FEM_OK;
+}
+
 static int launch_jit(b200fem_operator* op, const double* u, double* w, const double* sub) {
   const int k = op->sp->order, N = op->sp->n1;
+  if (op->sp->kind == B200FEM_LAGRANGE) {
+    REQUIRE(default_quadrature(op), B200FEM_ERR_NOT_IMPLEMENTED, "Lagrange spaces: only quadrature orders that select the (order+1)-point Gauss rule");
+    REQUIRE(!op->jit->skel, B200FEM_ERR_NOT_IMPLEMENTED, "skeleton integrands on continuous spaces");
+    int rc = N == 2 ? launch_jit_lagrange_t<2>(op, u, w) : launch_jit_lagrange_t<3>(op, u, w); if (rc) return rc;
+    if (sub) { rc = b200fem_axpy_dev(op, -1.0, sub, w); if (rc) return rc; op->timing.launches_per_apply += 1; }   // L[u] - L[0]
+    return B200FEM_OK;
+  }
   int mi, ms;
   try { mi = gauss_points_for_order(op->q_interior ? (int)op->q_interior : 2 * k); ms = gauss_points_for_order(op->q_surface ? (int)op->q_surface : 2 * k + 1); }
   catch (const std::exception& ex) { return fail(B200FEM_ERR_NOT_IMPLEMENTED, ex.what()); }
@@ -181,7 +255,6 @@ static int launch_jit(b200fem_operator* op, const double* u, double* w, const do
 // w = L[u] (linear == false) or L[u] - L[0] (linear == true)
 int apply_jit(b200fem_operator* op, const double* u, double* w, bool linear) {
   JitState* J = op->jit; b200fem_space* s = op->sp; cudaStream_t st = s->mesh->ctx->stream;
-  REQUIRE(s->kind != B200FEM_LAGRANGE, B200FEM_ERR_NOT_IMPLEMENTED, "compiled integrands: DG spaces");
   const double* sub = nullptr;
   if (linear) {
     if (!J->d_l0 || J->l0_version != op->state_version) {
@@ -207,7 +280,19 @@ using namespace b200fem;
 extern "C" int b200fem_jit_compile_check(const char* source, int order, char* log, int log_len) {
   REQUIRE(source && order >= 1 && order <= 5, B200FEM_ERR_INVALID, "jit_compile_check: bad argument");
   std::string lg; const int n = order + 1;
-  const int rc = compile(source, true, true, n, n, n, nullptr, nullptr, &lg);
+  const int rc = compile(source, true, true, n, n, n, 1, kJitDg, nullptr, nullptr, &lg);
+  if (log && log_len > 0) { std::strncpy(log, lg.c_str(), (size_t)log_len - 1); log[log_len - 1] = '\0'; }
+  return rc ? fail(rc, lg) : B200FEM_OK;
+}
+
+/* the same check for any space the integrands can run on: space kind (b200fem_space_kind), mesh dimension (selects the Lagrange
+ * kernel; DG spaces of either dimension share one) and dimRange */
+extern "C" int b200fem_jit_compile_check_space(const char* source, int kind, int dim, int order, int dim_range, int has_skeleton, int has_boundary, char* log, int log_len) {
+  REQUIRE(source && order >= 1 && order <= 5 && dim_range >= 1 && dim_range <= 4 && (dim == 2 || dim == 3), B200FEM_ERR_INVALID, "jit_compile_check_space: bad argument");
+  REQUIRE(kind != B200FEM_LAGRANGE || order <= 2, B200FEM_ERR_NOT_IMPLEMENTED, "Lagrange spaces: order 1 and 2 only");
+  std::string lg; const int n = order + 1;
+  const int variant = kind != B200FEM_LAGRANGE ? kJitDg : dim == 3 ? kJitLagrange3d : kJitLagrange2d;
+  const int rc = compile(source, has_skeleton != 0, has_boundary != 0, n, n, n, dim_range, variant, nullptr, nullptr, &lg);
   if (log && log_len > 0) { std::strncpy(log, lg.c_str(), (size_t)log_len - 1); log[log_len - 1] = '\0'; }
   return rc ? fail(rc, lg) : B200FEM_OK;
 }
@@ -225,12 +310,12 @@ extern "C" int b200fem_operator_set_constants(b200fem_operator* op, const double
 extern "C" int b200fem_operator_create_jit(b200fem_space* space, const char* source, const double* constants, int nconstants,
                                            int has_skeleton, int has_boundary, b200fem_operator** out) {
   REQUIRE(space && source && out, B200FEM_ERR_INVALID, "operator_create_jit: null argument");
-  REQUIRE(space->kind != B200FEM_LAGRANGE, B200FEM_ERR_NOT_IMPLEMENTED, "compiled integrands: DG spaces");
+  REQUIRE(!(space->kind == B200FEM_LAGRANGE && has_skeleton), B200FEM_ERR_NOT_IMPLEMENTED, "skeleton integrands on continuous spaces");
   REQUIRE(nconstants >= 0 && nconstants <= kJitMaxConstants, B200FEM_ERR_INVALID, "operator_create_jit: at most 32 constants");
   b200fem_model m; std::memset(&m, 0, sizeof(m)); m.has_skeleton = has_skeleton != 0; m.has_boundary = has_boundary != 0;
   m.gamma = 1.0;     // "not known to be linear": keeps every Kronecker shortcut away from this operator
   b200fem_operator* op = nullptr;
-  int rc = b200fem_operator_create(space, &m, &op); if (rc) return rc;
+  int rc = operator_create_impl(space, &m, &op); if (rc) return rc;
   op->jit = new JitState; op->jit->source = source; op->jit->skel = m.has_skeleton; op->jit->bnd = m.has_boundary;
   rc = b200fem_operator_set_constants(op, constants, nconstants);
   if (rc) { b200fem_operator_destroy(op); return rc; }

@@ -10,8 +10,10 @@
 // into 2^dim colours (parity of the element coordinates); elements of one colour share no dof, so each colour is
 // one launch doing plain read-modify-write -- deterministic, no atomics (colour order = summation order).
 #pragma once
+#ifndef __CUDACC_RTC__       // (also compiled at run time by NVRTC for user-supplied integrands, jit.cu)
 #include <cuda_runtime.h>
 #include <cstdint>
+#endif
 #include "dg_quadrature.cuh"
 
 namespace b200fem {
@@ -40,7 +42,8 @@ __host__ __device__ inline long long lagrange_dof(const LagrangeLayoutDev& L, co
 }
 
 // ------------------------------------------------------------------ 3-D: N*N threads per element, shared-memory tensors
-template <int N, class Integrands>
+// (R > 1: range-R spaces, dof (node, component) = node * R + c; the components sit in neighbouring element slots, dg_quadrature.cuh)
+template <int N, class Integrands, int R = 1>
 __global__ void __launch_bounds__(DgQuadCfg<N, N, N>::kThreads)
 lagrange3d_quadrature_kernel(const __grid_constant__ QuadTabDev<N, N, N> T, const __grid_constant__ BoxDev box,
                              const __grid_constant__ Integrands I, const __grid_constant__ LagrangeLayoutDev L,
@@ -52,8 +55,12 @@ lagrange3d_quadrature_kernel(const __grid_constant__ QuadTabDev<N, N, N> T, cons
   double* smem = reinterpret_cast<double*>(smem_raw);
   int* ecs = reinterpret_cast<int*>(smem + (size_t)EB * ELEM);       // 4 ints per slot: coords + active flag
 
+  constexpr int RS = quad_pow2(R);
+  static_assert(R == 1 || RS <= EB, "dimRange: the components of an element must fit the element slots of a CTA");
   const int tid = threadIdx.x, es = Cfg::slot(tid), lt = Cfg::lane(tid);
-  const long long oe = (long long)blockIdx.x * EB + es;
+  const int comp = es % RS;
+  const unsigned cmask = R == 1 ? 0xffffffffu : (((1u << RS) - 1u) << ((tid & 31) / RS * RS));
+  const long long oe = (long long)blockIdx.x * (EB / RS) + es / RS;
   const bool active = lt < Cfg::T2 && oe < n_colour;
   int lc[3] = {0, 0, 0};
   if (active) {
@@ -62,31 +69,47 @@ lagrange3d_quadrature_kernel(const __grid_constant__ QuadTabDev<N, N, N> T, cons
     lc[2] = box.own_lo[2] + 2 * (int)(oe / ((long long)m0 * m1)) + c2;
   }
   const long long e = lc[0] + (long long)box.n[0] * (lc[1] + (long long)box.n[1] * lc[2]);
-  if (lt == 0) { ecs[4 * es] = lc[0]; ecs[4 * es + 1] = lc[1]; ecs[4 * es + 2] = lc[2]; ecs[4 * es + 3] = active; }
+  if (lt == 0) { ecs[4 * es] = lc[0]; ecs[4 * es + 1] = lc[1]; ecs[4 * es + 2] = lc[2]; ecs[4 * es + 3] = active && comp < R; }
   __syncthreads();
   const int k = N - 1;
   for (int idx = tid; idx < EB * N3; idx += blockDim.x) {            // gather (getLocalDofs)
     const int s2 = idx / N3, t = idx % N3;
     if (ecs[4 * s2 + 3]) {
       const int i0 = t / N2, i1 = (t / N) % N, i2 = t % N;
-      smem[(size_t)s2 * ELEM + (i0 * N + i1) * LN + i2] = u[lagrange_dof(L, (long long)k * ecs[4 * s2] + i0, (long long)k * ecs[4 * s2 + 1] + i1, (long long)k * ecs[4 * s2 + 2] + i2)];
+      smem[(size_t)s2 * ELEM + (i0 * N + i1) * LN + i2] = u[lagrange_dof(L, (long long)k * ecs[4 * s2] + i0, (long long)k * ecs[4 * s2 + 1] + i1, (long long)k * ecs[4 * s2 + 2] + i2) * R + (R == 1 ? 0 : s2 % RS)];
     }
   }
   __syncthreads();
   double* U = smem + (size_t)es * ELEM;
-  element_integrals<N, N, N, Integrands>(T, box, I, nullptr, u, active, lc, e, lt, U, U + Cfg::kU, U + 2 * Cfg::kU);
+  element_integrals<N, N, N, Integrands, false, R>(T, box, I, nullptr, u, active, lc, e, lt, U, U + Cfg::kU, U + 2 * Cfg::kU, comp, cmask);
   for (int idx = tid; idx < EB * N3; idx += blockDim.x) {            // coloured scatter-add (addLocalDofs)
     const int s2 = idx / N3, t = idx % N3;
     if (ecs[4 * s2 + 3]) {
       const int i0 = t / N2, i1 = (t / N) % N, i2 = t % N;
       const long long g = lagrange_dof(L, (long long)k * ecs[4 * s2] + i0, (long long)k * ecs[4 * s2 + 1] + i1, (long long)k * ecs[4 * s2 + 2] + i2);
-      w[g] += smem[(size_t)s2 * ELEM + Cfg::kU + (i0 * N + i1) * LN + i2];
+      w[g * R + (R == 1 ? 0 : s2 % RS)] += smem[(size_t)s2 * ELEM + Cfg::kU + (i0 * N + i1) * LN + i2];
     }
   }
 }
 
 // ------------------------------------------------------------------ 2-D: one thread per element, registers only
-template <int N, class Integrands>
+// (range-R spaces: the thread carries all R components of its element; scalar integrands go through the same code with R = 1)
+template <int R, class Integrands> __device__ __forceinline__ PointRangeV<R> lag2d_interior(const Integrands& I, const double* x, const PointValueV<R>& v) {
+  if constexpr (R == 1) {
+    PointValue pv; pv.u = v.u[0]; pv.du[0] = v.du[0][0]; pv.du[1] = v.du[0][1]; pv.du[2] = v.du[0][2];
+    const PointRange r = I.interior(x, pv);
+    PointRangeV<1> o; o.s[0] = r.s; o.F[0][0] = r.F[0]; o.F[0][1] = r.F[1]; o.F[0][2] = r.F[2]; return o;
+  } else return I.interior(x, v);
+}
+template <int R, class Integrands> __device__ __forceinline__ PointRangeV<R> lag2d_boundary(const Integrands& I, int d, int s, double ih, const double* x, const PointValueV<R>& v) {
+  if constexpr (R == 1) {
+    PointValue pv; pv.u = v.u[0]; pv.du[0] = v.du[0][0]; pv.du[1] = v.du[0][1]; pv.du[2] = v.du[0][2];
+    const PointRange r = I.boundary(d, s, ih, x, pv);
+    PointRangeV<1> o; o.s[0] = r.s; o.F[0][0] = r.F[0]; o.F[0][1] = r.F[1]; o.F[0][2] = r.F[2]; return o;
+  } else return I.boundary(d, s, ih, x, v);
+}
+
+template <int N, class Integrands, int R = 1>
 __global__ void __launch_bounds__(128)
 lagrange2d_quadrature_kernel(const __grid_constant__ DgTabDev<N> T, const __grid_constant__ BoxDev box,
                              const __grid_constant__ Integrands I, const __grid_constant__ LagrangeLayoutDev L,
@@ -97,51 +120,65 @@ lagrange2d_quadrature_kernel(const __grid_constant__ DgTabDev<N> T, const __grid
   const int lc[2] = {box.own_lo[0] + 2 * (int)(oe % m0) + c0, box.own_lo[1] + 2 * (int)(oe / m0) + c1};
   const double hh[2] = {box.h[0], box.h[1]};
   const double detJ = hh[0] * hh[1];
-  double ul[N][N], wl[N][N];            // [i1][i0]
+  double ul[R][N][N], wl[R][N][N];            // [c][i1][i0]
   long long dof[N][N];
 #pragma unroll
   for (int i1 = 0; i1 < N; ++i1)
 #pragma unroll
-    for (int i0 = 0; i0 < N; ++i0) { dof[i1][i0] = lagrange_dof(L, (long long)k * lc[0] + i0, (long long)k * lc[1] + i1, 0); ul[i1][i0] = u[dof[i1][i0]]; wl[i1][i0] = 0; }
+    for (int i0 = 0; i0 < N; ++i0) {
+      dof[i1][i0] = lagrange_dof(L, (long long)k * lc[0] + i0, (long long)k * lc[1] + i1, 0);
+#pragma unroll
+      for (int c = 0; c < R; ++c) { ul[c][i1][i0] = u[dof[i1][i0] * R + c]; wl[c][i1][i0] = 0; }
+    }
 
   // interior integral (galerkin.hh:332-360), sum-factorised in registers
-  double tb[N][N], tg[N][N];            // [q0][i1]
+  double tb[R][N][N], tg[R][N][N];            // [c][q0][i1]
 #pragma unroll
-  for (int q0 = 0; q0 < N; ++q0)
+  for (int c = 0; c < R; ++c)
 #pragma unroll
-    for (int i1 = 0; i1 < N; ++i1) { double a = 0, b = 0;
+    for (int q0 = 0; q0 < N; ++q0)
 #pragma unroll
-      for (int i0 = 0; i0 < N; ++i0) { a = fma(T.B[q0 * N + i0], ul[i1][i0], a); b = fma(T.G[q0 * N + i0], ul[i1][i0], b); }
-      tb[q0][i1] = a; tg[q0][i1] = b; }
-  double zs[N][N], zx[N][N], zy[N][N];  // [q0][i1] after testing along axis 1
+      for (int i1 = 0; i1 < N; ++i1) { double a = 0, b = 0;
+#pragma unroll
+        for (int i0 = 0; i0 < N; ++i0) { a = fma(T.B[q0 * N + i0], ul[c][i1][i0], a); b = fma(T.G[q0 * N + i0], ul[c][i1][i0], b); }
+        tb[c][q0][i1] = a; tg[c][q0][i1] = b; }
+  double zs[R][N][N], zx[R][N][N];            // [c][q0][i1] after testing along axis 1
 #pragma unroll
   for (int q0 = 0; q0 < N; ++q0) {
-    double rs[N], rx[N], ry[N];
+    double rs[R][N], rx[R][N], ry[R][N];
 #pragma unroll
     for (int q1 = 0; q1 < N; ++q1) {
-      PointValue pv; pv.u = 0; pv.du[0] = pv.du[1] = pv.du[2] = 0;
+      PointValueV<R> pv;
 #pragma unroll
-      for (int i1 = 0; i1 < N; ++i1) { pv.u = fma(T.B[q1 * N + i1], tb[q0][i1], pv.u); pv.du[0] = fma(T.B[q1 * N + i1], tg[q0][i1], pv.du[0]); pv.du[1] = fma(T.G[q1 * N + i1], tb[q0][i1], pv.du[1]); }
-      pv.du[0] /= hh[0]; pv.du[1] /= hh[1];
+      for (int c = 0; c < R; ++c) {
+        pv.u[c] = 0; pv.du[c][0] = pv.du[c][1] = pv.du[c][2] = 0;
+#pragma unroll
+        for (int i1 = 0; i1 < N; ++i1) { pv.u[c] = fma(T.B[q1 * N + i1], tb[c][q0][i1], pv.u[c]); pv.du[c][0] = fma(T.B[q1 * N + i1], tg[c][q0][i1], pv.du[c][0]); pv.du[c][1] = fma(T.G[q1 * N + i1], tb[c][q0][i1], pv.du[c][1]); }
+        pv.du[c][0] /= hh[0]; pv.du[c][1] /= hh[1];
+      }
       double xq[3] = {box.lo[0] + hh[0] * ((box.origin[0] + lc[0]) + T.x[q0]), box.lo[1] + hh[1] * ((box.origin[1] + lc[1]) + T.x[q1]), 0.0};
-      PointRange r = I.interior(xq, pv);
+      const PointRangeV<R> r = lag2d_interior<R>(I, xq, pv);
       const double wq = T.w[q0] * T.w[q1] * detJ;
-      rs[q1] = r.s * wq; rx[q1] = r.F[0] * wq / hh[0]; ry[q1] = r.F[1] * wq / hh[1];
+#pragma unroll
+      for (int c = 0; c < R; ++c) { rs[c][q1] = r.s[c] * wq; rx[c][q1] = r.F[c][0] * wq / hh[0]; ry[c][q1] = r.F[c][1] * wq / hh[1]; }
     }
 #pragma unroll
-    for (int i1 = 0; i1 < N; ++i1) { double a = 0, b = 0;
+    for (int c = 0; c < R; ++c)
 #pragma unroll
-      for (int q1 = 0; q1 < N; ++q1) { a = fma(T.B[q1 * N + i1], rs[q1], a); a = fma(T.G[q1 * N + i1], ry[q1], a); b = fma(T.B[q1 * N + i1], rx[q1], b); }
-      zs[q0][i1] = a; zx[q0][i1] = b; }
+      for (int i1 = 0; i1 < N; ++i1) { double a = 0, b = 0;
+#pragma unroll
+        for (int q1 = 0; q1 < N; ++q1) { a = fma(T.B[q1 * N + i1], rs[c][q1], a); a = fma(T.G[q1 * N + i1], ry[c][q1], a); b = fma(T.B[q1 * N + i1], rx[c][q1], b); }
+        zs[c][q0][i1] = a; zx[c][q0][i1] = b; }
   }
 #pragma unroll
-  for (int i1 = 0; i1 < N; ++i1)
+  for (int c = 0; c < R; ++c)
 #pragma unroll
-    for (int i0 = 0; i0 < N; ++i0) { double a = 0;
+    for (int i1 = 0; i1 < N; ++i1)
 #pragma unroll
-      for (int q0 = 0; q0 < N; ++q0) { a = fma(T.B[q0 * N + i0], zs[q0][i1], a); a = fma(T.G[q0 * N + i0], zx[q0][i1], a); }
-      wl[i1][i0] += a; }
-  (void)zy;
+      for (int i0 = 0; i0 < N; ++i0) { double a = 0;
+#pragma unroll
+        for (int q0 = 0; q0 < N; ++q0) { a = fma(T.B[q0 * N + i0], zs[c][q0][i1], a); a = fma(T.G[q0 * N + i0], zx[c][q0][i1], a); }
+        wl[c][i1][i0] += a; }
 
   // boundary integrals (galerkin.hh:414-435) on domain-boundary edges
   if (I.m.has_boundary) {
@@ -150,45 +187,59 @@ lagrange2d_quadrature_kernel(const __grid_constant__ DgTabDev<N> T, const __grid
       const int d = f >> 1, s = f & 1, a = 1 - d;
       const int gc = box.origin[d] + lc[d];
       if ((s == 0 && gc != 0) || (s == 1 && gc != box.gn[d] - 1)) continue;
-      double tv[N], td[N];               // trace coefficients along the edge (index along axis a)
+      double tv[R][N], td[R][N];               // trace coefficients along the edge (index along axis a)
 #pragma unroll
-      for (int ia = 0; ia < N; ++ia) { double v = 0, dv = 0;
+      for (int c = 0; c < R; ++c)
 #pragma unroll
-        for (int id = 0; id < N; ++id) { const double uu = d == 0 ? ul[ia][id] : ul[id][ia]; v = fma(T.phi[s][id], uu, v); dv = fma(T.dphi[s][id], uu, dv); }
-        tv[ia] = v; td[ia] = dv; }
+        for (int ia = 0; ia < N; ++ia) { double v = 0, dv = 0;
+#pragma unroll
+          for (int id = 0; id < N; ++id) { const double uu = d == 0 ? ul[c][ia][id] : ul[c][id][ia]; v = fma(T.phi[s][id], uu, v); dv = fma(T.dphi[s][id], uu, dv); }
+          tv[c][ia] = v; td[c][ia] = dv; }
       const double area = detJ / hh[d];
-      double rv[N], rd[N];
+      double rv[R][N], rd[R][N];
 #pragma unroll
-      for (int ia = 0; ia < N; ++ia) rv[ia] = rd[ia] = 0;
+      for (int c = 0; c < R; ++c)
+#pragma unroll
+        for (int ia = 0; ia < N; ++ia) rv[c][ia] = rd[c][ia] = 0;
 #pragma unroll
       for (int q = 0; q < N; ++q) {
-        PointValue pv; pv.u = 0; pv.du[0] = pv.du[1] = pv.du[2] = 0; double dn = 0, dt = 0;
+        PointValueV<R> pv;
 #pragma unroll
-        for (int ia = 0; ia < N; ++ia) { pv.u = fma(T.B[q * N + ia], tv[ia], pv.u); dn = fma(T.B[q * N + ia], td[ia], dn); dt = fma(T.G[q * N + ia], tv[ia], dt); }
-        pv.du[d] = dn / hh[d]; pv.du[a] = dt / hh[a];
+        for (int c = 0; c < R; ++c) {
+          pv.u[c] = 0; pv.du[c][0] = pv.du[c][1] = pv.du[c][2] = 0; double dn = 0, dt = 0;
+#pragma unroll
+          for (int ia = 0; ia < N; ++ia) { pv.u[c] = fma(T.B[q * N + ia], tv[c][ia], pv.u[c]); dn = fma(T.B[q * N + ia], td[c][ia], dn); dt = fma(T.G[q * N + ia], tv[c][ia], dt); }
+          pv.du[c][d] = dn / hh[d]; pv.du[c][a] = dt / hh[a];
+        }
         double xq[3] = {0, 0, 0};
         xq[d] = box.lo[d] + hh[d] * (gc + s); xq[a] = box.lo[a] + hh[a] * ((box.origin[a] + lc[a]) + T.x[q]);
-        PointRange r = I.boundary(d, s, 1.0 / hh[d], xq, pv);
+        const PointRangeV<R> r = lag2d_boundary<R>(I, d, s, 1.0 / hh[d], xq, pv);
         const double wq = T.w[q] * area;
 #pragma unroll
-        for (int ia = 0; ia < N; ++ia) {
-          rv[ia] = fma(T.B[q * N + ia], r.s * wq, rv[ia]); rv[ia] = fma(T.G[q * N + ia], r.F[a] * wq / hh[a], rv[ia]);
-          rd[ia] = fma(T.B[q * N + ia], r.F[d] * wq / hh[d], rd[ia]);
-        }
+        for (int c = 0; c < R; ++c)
+#pragma unroll
+          for (int ia = 0; ia < N; ++ia) {
+            rv[c][ia] = fma(T.B[q * N + ia], r.s[c] * wq, rv[c][ia]); rv[c][ia] = fma(T.G[q * N + ia], r.F[c][a] * wq / hh[a], rv[c][ia]);
+            rd[c][ia] = fma(T.B[q * N + ia], r.F[c][d] * wq / hh[d], rd[c][ia]);
+          }
       }
 #pragma unroll
-      for (int ia = 0; ia < N; ++ia)
+      for (int c = 0; c < R; ++c)
 #pragma unroll
-        for (int id = 0; id < N; ++id) {
-          const double add = T.phi[s][id] * rv[ia] + T.dphi[s][id] * rd[ia];
-          if (d == 0) wl[ia][id] += add; else wl[id][ia] += add;
-        }
+        for (int ia = 0; ia < N; ++ia)
+#pragma unroll
+          for (int id = 0; id < N; ++id) {
+            const double add = T.phi[s][id] * rv[c][ia] + T.dphi[s][id] * rd[c][ia];
+            if (d == 0) wl[c][ia][id] += add; else wl[c][id][ia] += add;
+          }
     }
   }
 #pragma unroll
   for (int i1 = 0; i1 < N; ++i1)
 #pragma unroll
-    for (int i0 = 0; i0 < N; ++i0) w[dof[i1][i0]] += wl[i1][i0];
+    for (int i0 = 0; i0 < N; ++i0)
+#pragma unroll
+      for (int c = 0; c < R; ++c) w[dof[i1][i0] * R + c] += wl[c][i1][i0];
 }
 
 }  // namespace b200fem

@@ -7,10 +7,13 @@ from . import _capi as capi
 
 
 class DiscreteFunctionSpace:
-    def __init__(self, gridView, kind, order, numbering=capi.NUMBERING_YASP):
-        self.gridView, self.kind, self.order = gridView, kind, order
+    def __init__(self, gridView, kind, order, numbering=capi.NUMBERING_YASP, dimRange=1):
+        self.gridView, self.kind, self.order, self.dimRange = gridView, kind, order, dimRange
         self.handle = C.c_void_p()
-        capi.check(capi.lib().b200fem_space_create(gridView.handle, kind, order, numbering, C.byref(self.handle)))
+        if dimRange == 1:
+            capi.check(capi.lib().b200fem_space_create(gridView.handle, kind, order, numbering, C.byref(self.handle)))
+        else:    # create.space(name, grid, dimRange=dimR, order=order): size = blocks * dimRange, dof (block, c) = block * dimRange + c
+            capi.check(capi.lib().b200fem_space_create_vector(gridView.handle, kind, order, numbering, dimRange, C.byref(self.handle)))
         v = C.c_int64()
         capi.check(capi.lib().b200fem_space_size(self.handle, C.byref(v)))
         self.size = v.value
@@ -44,14 +47,14 @@ class DiscreteFunctionSpace:
         return a
 
 
-def lagrange(gridView, order=1, numbering=capi.NUMBERING_YASP):
-    return DiscreteFunctionSpace(gridView, capi.LAGRANGE, order, numbering)
+def lagrange(gridView, order=1, numbering=capi.NUMBERING_YASP, dimRange=1):
+    return DiscreteFunctionSpace(gridView, capi.LAGRANGE, order, numbering, dimRange=dimRange)
 
 
-def dglegendre(gridView, order=1, hierarchical=True):
-    return DiscreteFunctionSpace(gridView, capi.DG_LEGENDRE_HIER if hierarchical else capi.DG_LEGENDRE, order)
+def dglegendre(gridView, order=1, hierarchical=True, dimRange=1):
+    return DiscreteFunctionSpace(gridView, capi.DG_LEGENDRE_HIER if hierarchical else capi.DG_LEGENDRE, order, dimRange=dimRange)
 
 
-def dgonb(gridView, order=1):
+def dgonb(gridView, order=1, dimRange=1):
     """orthonormal P_k on cubes -- the space pydemo/advectiondiffusion.py:9 imports (shapefunctionset/orthonormal.hh:55-60)"""
-    return DiscreteFunctionSpace(gridView, capi.DG_ONB, order)
+    return DiscreteFunctionSpace(gridView, capi.DG_ONB, order, dimRange=dimRange)

@@ -119,6 +119,13 @@ int b200fem_march_schedule(const int32_t* on, int grid, int flags, int32_t* runs
 
 /* DiscreteFunctionSpace (space/lagrange/space.hh:129-353, space/discontinuousgalerkin/legendre.hh) */
 int b200fem_space_create(b200fem_mesh* mesh, int kind, int order, int numbering, b200fem_space** out);
+/* Vector-valued spaces (FunctionSpace< ..., dimRange >; the reference builds them from the scalar shape functions,
+ * space/shapefunctionset/vectorial.hh:508-526: local dof i * dimRange + c; DofVector blocks of dimRange components,
+ * function/blockvectors/defaultblockvectors.hh:284-294): b200fem_space_size = blocks * dim_range, dof (block g, component c) =
+ * g * dim_range + c; b200fem_space_dofmap / _local_size keep returning BLOCK indices (blockMapper()).  dim_range 1..4, orders 1..3,
+ * one rank; operators on them take run-time compiled integrands (b200fem_operator_create_jit) -- the built-in family is scalar. */
+int b200fem_space_create_vector(b200fem_mesh* mesh, int kind, int order, int numbering, int dim_range, b200fem_space** out);
+int b200fem_space_dim_range(b200fem_space* space, int32_t* dim_range);
 int b200fem_space_destroy(b200fem_space* space);
 int b200fem_space_size(b200fem_space* space, int64_t* size);            /* space.size()                               */
 int b200fem_space_local_size(b200fem_space* space, int32_t* nb);        /* blockMapper().maxNumDofs()                 */
@@ -162,7 +169,8 @@ int b200fem_operator_linearize_dev(b200fem_operator* op, const double* u_dev, do
  * form (python/dune/models/integrands/model.py:10-106, python/dune/ufl/codegen.py) into its GalerkinOperator; this entry point
  * does the same for the device: `source` is CUDA C++ that defines the three integrand functions below, and it is compiled at
  * run time (NVRTC, sm_100a) INTO the generic quadrature kernel (dg_quadrature.cuh) -- one specialised kernel per operator,
- * exactly like the reference's one specialised operator class per form.  DG spaces (all kinds), scalar range.
+ * exactly like the reference's one specialised operator class per form.  DG spaces (all kinds) and continuous Lagrange
+ * spaces (no skeleton terms there; colour-ordered scatter, lagrange_quadrature.cuh), scalar or vector-valued range.
  *
  *   struct PointValue { double u; double du[3]; };   // DomainValueType  = (u, grad u) at the quadrature point
  *   struct PointRange { double s; double F[3]; };    // RangeValueType: tested as  s * phi + F . grad phi
@@ -177,13 +185,23 @@ int b200fem_operator_linearize_dev(b200fem_operator* op, const double* u_dev, do
  * `in` (of the element, for boundary(): sign = side ? +1 : -1); ihe = 1 / he with he = avg(CellVolume) / FacetArea,
  * ihbnd = FacetArea / CellVolume.  r / rin / rout arrive zeroed.  The functions evaluate the WHOLE integrand, data terms
  * included: apply = L[u]; apply_linear = L[u] - L[0] (meaningful for integrands that are affine in u; non-linear ones are
- * solved through b200fem_operator_linearize).  Compile errors: B200FEM_ERR_INVALID with the NVRTC log as the message. */
+ * solved through b200fem_operator_linearize).  Compile errors: B200FEM_ERR_INVALID with the NVRTC log as the message.
+ *
+ * Vector-valued spaces (b200fem_space_create_vector, dimRange = R > 1): the same three functions over
+ *   template <int R> struct PointValueV { double u[R]; double du[R][3]; };   // (u_c, grad u_c)
+ *   template <int R> struct PointRangeV { double s[R]; double F[R][3]; };    // tested as  s_c * phi + F_c . grad phi  per component
+ * with `dimRange`, `VectorValue = PointValueV<dimRange>` and `VectorRange = PointRangeV<dimRange>` defined for the source, e.g.
+ *   __device__ void interior(const double* x, const VectorValue& u, VectorRange& r, const double* c, int dim);
+ * (the reference's own matrix-free check runs on such a space: dune/fempy/test/testoperator.py:14-36, Lagrange order 2, dimRange 2). */
 int b200fem_operator_create_jit(b200fem_space* space, const char* source, const double* constants, int nconstants,
                                 int has_skeleton, int has_boundary, b200fem_operator** out);
 int b200fem_operator_set_constants(b200fem_operator* op, const double* constants, int nconstants);
 /* Compiles `source` for a Q_order / dgonb space with the default quadrature orders without touching a device (NVRTC only):
  * 0 when it compiles; the log (NUL-terminated, truncated to log_len) is returned either way.  Host logic, testable on CPU. */
 int b200fem_jit_compile_check(const char* source, int order, char* log, int log_len);
+/* ... and for any space the integrands can run on: space kind, mesh dimension (2 / 3), order, dimRange */
+int b200fem_jit_compile_check_space(const char* source, int kind, int dim, int order, int dim_range, int has_skeleton, int has_boundary,
+                                    char* log, int log_len);
 
 /* strong Dirichlet marks and values (schemes/dirichletconstraints.hh:435-554) */
 int b200fem_operator_dirichlet(b200fem_operator* op, uint8_t* mask_host, double* values_host);

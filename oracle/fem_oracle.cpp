@@ -805,6 +805,91 @@ static void kronApplyT(const int* n3, const int* tensorOfStored, const double* m
   for (int t = 0; t < T; ++t) pool.emplace_back(work, (int)((int64_t)nz*t/T), (int)((int64_t)nz*(t + 1)/T));
   for (auto& th : pool) th.join();
 }
+
+// ---------------------------------------------------------------------------
+// Vector-valued spaces (FunctionSpace< ..., dimRange R >): the reference builds the basis from the scalar shape functions,
+// phi_i e_c with local index i*R + c (space/shapefunctionset/vectorial.hh:508-526), dof blocks of R components
+// (function/blockvectors/defaultblockvectors.hh:284-294: global dof = block*R + c with the scalar space's block mapper).
+// The same element loop as Operator::evaluateRange (galerkin.hh:811-917) on one rank, one thread, user integrands only:
+// the callbacks see PointValueV<R> = { u[R], du[R][3] } and fill PointRangeV<R> = { s[R], F[R][3] } (include/b200fem.h) --
+// passed here as flat arrays of 4R doubles each.
+// ---------------------------------------------------------------------------
+typedef void (*UserInteriorV)(const double* x, const double* u, double* r, const double* c, int dim);
+typedef void (*UserSkeletonV)(const double* x, int axis, double sign, double ihe, const double* in, const double* out, double* rin, double* rout, const double* c, int dim);
+typedef void (*UserBoundaryV)(const double* x, int axis, int side, double ihbnd, const double* u, double* r, const double* c, int dim);
+
+struct VectorOperator {
+  const Space& sp; int R; UserInteriorV interior; UserSkeletonV skeleton; UserBoundaryV boundary; double c[32] = {};
+  VectorOperator(const Space& s, int r, UserInteriorV fi, UserSkeletonV fs, UserBoundaryV fb) : sp(s), R(r), interior(fi), skeleton(fs), boundary(fb) {}
+
+  // evaluateAll + jacobianAll of the vectorial basis: out = { u[R], du[R][3] }
+  void evaluatePoint(const Tabulation& t, int q, const double* dofs, double* out) const {
+    const int nb = sp.nb; const Mesh& M = sp.mesh;
+    const double* B = &t.B[(size_t)q*nb]; const double* G = &t.G[(size_t)q*nb*3];
+    for (int c = 0; c < R; ++c) {
+      double u = 0, g[3] = {0,0,0};
+      for (int i = 0; i < nb; ++i) { const double v = dofs[(size_t)i*R + c]; u += B[i]*v; for (int d = 0; d < 3; ++d) g[d] += G[3*i+d]*v; }
+      out[c] = u; for (int d = 0; d < 3; ++d) out[R + 3*c + d] = (d < M.dim) ? g[d]/M.h[d] : 0.0;
+    }
+  }
+  // axpy for one point: w_{i,c} += weight * ( phi_i s_c + (J^-1 F_c) . gradhat phi_i )
+  void axpyPoint(const Tabulation& t, int q, const double* r, double weight, double* w) const {
+    const int nb = sp.nb; const Mesh& M = sp.mesh;
+    const double* B = &t.B[(size_t)q*nb]; const double* G = &t.G[(size_t)q*nb*3];
+    for (int c = 0; c < R; ++c) {
+      const double s = r[c]*weight; double Fh[3]; for (int d = 0; d < 3; ++d) Fh[d] = (d < M.dim) ? r[R + 3*c + d]*weight/M.h[d] : 0.0;
+      for (int i = 0; i < nb; ++i) w[(size_t)i*R + c] += B[i]*s + G[3*i]*Fh[0] + G[3*i+1]*Fh[1] + G[3*i+2]*Fh[2];
+    }
+  }
+  void apply(const double* u, double* w) const {
+    const Mesh& M = sp.mesh; const int nb = sp.nb, nl = nb*R;
+    std::fill(w, w + sp.size*R, 0.0);
+    std::vector<double> uIn(nl), uOut(nl), wIn(nl), wOut(nl), vIn(4*R), vOut(4*R), rIn(4*R), rOut(4*R); std::vector<int64_t> gIn(nb), gOut(nb);
+    auto gather = [&](const int64_t* g, double* dst) { for (int i = 0; i < nb; ++i) for (int c = 0; c < R; ++c) dst[(size_t)i*R + c] = u[g[i]*R + c]; };
+    auto scatter = [&](const int64_t* g, const double* src) { for (int i = 0; i < nb; ++i) for (int c = 0; c < R; ++c) w[g[i]*R + c] += src[(size_t)i*R + c]; };
+    for (int64_t e = 0; e < M.nelem; ++e) {
+      int ec[3]; M.elemCoords(e, ec);
+      sp.dofMap(e, gIn.data()); gather(gIn.data(), uIn.data());
+      std::fill(wIn.begin(), wIn.end(), 0.0);
+      { const Tabulation& t = sp.vol; const double detJ = M.detJ();                                  // galerkin.hh:332-360
+        for (int q = 0; q < t.nop; ++q) {
+          double x[3]; for (int d = 0; d < 3; ++d) x[d] = M.lo[d] + M.h[d]*(ec[d] + t.x[3*q+d]);
+          evaluatePoint(t, q, uIn.data(), vIn.data());
+          std::fill(rIn.begin(), rIn.end(), 0.0); interior(x, vIn.data(), rIn.data(), c, M.dim);
+          axpyPoint(t, q, rIn.data(), t.w[q]*detJ, wIn.data());
+        } }
+      for (int f = 0; f < 2*M.dim; ++f) {
+        const int axis = f/2, side = f%2; int nc[3] = {ec[0], ec[1], ec[2]}; nc[axis] += side ? 1 : -1;
+        bool neighbor = nc[axis] >= 0 && nc[axis] < M.n[axis];
+        if (!neighbor && ((M.periodic >> axis) & 1)) { nc[axis] = (nc[axis] + M.n[axis]) % M.n[axis]; neighbor = true; }
+        const double area = M.faceArea(axis), he = M.detJ()/area;
+        if (neighbor) {
+          if (!skeleton) continue;
+          const int64_t o = M.elemIndex(nc); if (!(e < o)) continue;                                // galerkin.hh:879-897
+          sp.dofMap(o, gOut.data()); gather(gOut.data(), uOut.data()); std::fill(wOut.begin(), wOut.end(), 0.0);
+          const Tabulation& tIn = sp.face[f]; const Tabulation& tOut = sp.face[f^1];
+          for (int q = 0; q < tIn.nop; ++q) {
+            double x[3]; for (int d = 0; d < 3; ++d) x[d] = M.lo[d] + M.h[d]*(ec[d] + tIn.x[3*q+d]);
+            evaluatePoint(tIn, q, uIn.data(), vIn.data()); evaluatePoint(tOut, q, uOut.data(), vOut.data());
+            std::fill(rIn.begin(), rIn.end(), 0.0); std::fill(rOut.begin(), rOut.end(), 0.0);
+            skeleton(x, axis, side ? 1.0 : -1.0, 1.0/he, vIn.data(), vOut.data(), rIn.data(), rOut.data(), c, M.dim);
+            axpyPoint(tIn, q, rIn.data(), tIn.w[q]*area, wIn.data()); axpyPoint(tOut, q, rOut.data(), tIn.w[q]*area, wOut.data());
+          }
+          scatter(gOut.data(), wOut.data());
+        } else if (boundary) {                                                                      // galerkin.hh:414-435
+          const Tabulation& t = sp.face[f];
+          for (int q = 0; q < t.nop; ++q) {
+            double x[3]; for (int d = 0; d < 3; ++d) x[d] = M.lo[d] + M.h[d]*(ec[d] + t.x[3*q+d]);
+            evaluatePoint(t, q, uIn.data(), vIn.data());
+            std::fill(rIn.begin(), rIn.end(), 0.0); boundary(x, axis, side, 1.0/he, vIn.data(), rIn.data(), c, M.dim);
+            axpyPoint(t, q, rIn.data(), t.w[q]*area, wIn.data());
+          }
+        }
+      }
+      scatter(gIn.data(), wIn.data());
+    }
+  }
+};
 }  // namespace oracle
 
 // ===========================================================================
@@ -853,6 +938,15 @@ FoOperator* fo_operator_create_user(FoSpace* s, UserInterior fi, UserSkeleton fs
   return op;
 }
 void fo_operator_destroy(FoOperator* op) { delete op; }
+// GalerkinOperator on a range-R space built on the scalar space `s` (vector size = fo_space_size * R)
+VectorOperator* fo_vector_operator_create(FoSpace* s, int R, UserInteriorV fi, UserSkeletonV fs, UserBoundaryV fb, const double* c, int nc) {
+  VectorOperator* op = new VectorOperator(*s->sp, R, fi, fs, fb); for (int i = 0; i < nc && i < 32; ++i) op->c[i] = c[i]; return op;
+}
+void fo_vector_operator_destroy(VectorOperator* op) { delete op; }
+void fo_vector_operator_apply(VectorOperator* op, const double* u, double* w, int linear) {
+  op->apply(u, w);
+  if (linear) { const size_t n = (size_t)op->sp.size*op->R; std::vector<double> zero(n, 0.0), l0(n); op->apply(zero.data(), l0.data()); for (size_t i = 0; i < n; ++i) w[i] -= l0[i]; }
+}
 void fo_operator_set_threads(FoOperator* op, int t) { op->full->threads = t; op->linear->threads = t; }
 // MOLGalerkinOperator (schemes/molgalerkin.hh): w = M^-1 L[u]; DG spaces only
 int fo_operator_set_inverse_mass(FoOperator* op, int on) {

@@ -55,6 +55,10 @@ def lib():
     L.fo_operator_destroy.argtypes = [C.c_void_p]
     L.fo_operator_create_user.restype = C.c_void_p
     L.fo_operator_create_user.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _dp, C.c_int]
+    L.fo_vector_operator_create.restype = C.c_void_p
+    L.fo_vector_operator_create.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, _dp, C.c_int]
+    L.fo_vector_operator_destroy.argtypes = [C.c_void_p]
+    L.fo_vector_operator_apply.argtypes = [C.c_void_p, _dp, _dp, C.c_int]
     L.fo_operator_set_threads.argtypes = [C.c_void_p, C.c_int]
     L.fo_operator_set_inverse_mass.argtypes = [C.c_void_p, C.c_int]
     L.fo_operator_set_inverse_mass.restype = C.c_int
@@ -123,6 +127,19 @@ class Space:
         dphi = np.empty((self.local_size, 3))
         lib().fo_shape_evaluate(self._h, x3, phi, dphi)
         return phi, dphi
+
+    def node_positions(self):
+        """positions of the Lagrange nodes, indexed by global dof (fem_oracle.cpp: Space::nodePosition)"""
+        assert self.kind == LAGRANGE
+        mi, h = self.multiindex()[:, :self.dim], (self.hi - self.lo) / self.n
+        x = np.zeros((self.size, self.dim))
+        for e in range(self.elements):
+            ec, r = [], e
+            for d in range(self.dim):
+                ec.append(r % self.n[d])
+                r //= self.n[d]
+            x[self.dofmap(e)] = self.lo + h * (np.array(ec) + mi / self.order)
+        return x
 
     def interpolate(self, data):
         out = np.zeros(self.size)
@@ -273,6 +290,55 @@ class UserOperator(Operator):
         self._h = lib().fo_operator_create_user(space._h, fn("u_interior", True), fn("u_skeleton", skeleton), fn("u_boundary", boundary), c, 32)
         if threads > 1:
             lib().fo_operator_set_threads(self._h, threads)
+
+
+
+def _compile_user(text, flags):
+    import hashlib
+    import tempfile
+    tag = hashlib.sha1((text + " ".join(flags)).encode()).hexdigest()[:16]
+    d = os.path.join(tempfile.gettempdir(), "b200fem_oracle_user")
+    os.makedirs(d, exist_ok=True)
+    so = os.path.join(d, f"user_{tag}.so")
+    if not os.path.exists(so):
+        src = os.path.join(d, f"user_{tag}.cpp")
+        with open(src, "w") as f:
+            f.write(text)
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", so + ".tmp", src] + flags)
+        os.replace(so + ".tmp", so)
+    return C.CDLL(so)
+
+
+class VectorUserOperator:
+    """GalerkinOperator on a range-R space (dofs = blocks of R components over the scalar space `space`) with user-supplied
+    integrands over VectorValue / VectorRange (include/b200fem.h); the SAME source text as the device, compiled for the host."""
+    _PRELUDE = ("#include <cmath>\nusing namespace std;\n#define __device__\n#define __forceinline__ inline\n"
+                "template <int R> struct PointValueV { double u[R]; double du[R][3]; };\ntemplate <int R> struct PointRangeV { double s[R]; double F[R][3]; };\n"
+                "namespace user {\nconstexpr int dimRange = DIM_RANGE;\nusing VectorValue = PointValueV<dimRange>;\nusing VectorRange = PointRangeV<dimRange>;\n")
+    _EPILOGUE = ("\n}\nusing user::VectorValue; using user::VectorRange;\nextern \"C\" {\n"
+                 "void u_interior(const double* x, const VectorValue* u, VectorRange* r, const double* c, int dim) { user::interior(x, *u, *r, c, dim); }\n"
+                 "#ifdef HAS_SKELETON\nvoid u_skeleton(const double* x, int axis, double sign, double ihe, const VectorValue* in, const VectorValue* out, VectorRange* rin, VectorRange* rout, const double* c, int dim) { user::skeleton(x, axis, sign, ihe, *in, *out, *rin, *rout, c, dim); }\n#endif\n"
+                 "#ifdef HAS_BOUNDARY\nvoid u_boundary(const double* x, int axis, int side, double ihbnd, const VectorValue* u, VectorRange* r, const double* c, int dim) { user::boundary(x, axis, side, ihbnd, *u, *r, c, dim); }\n#endif\n}\n")
+
+    def __init__(self, space, dim_range, source, constants=(), skeleton=True, boundary=True):
+        self.space, self.R, self.size = space, dim_range, space.size * dim_range
+        flags = [f"-DDIM_RANGE={dim_range}"] + (["-DHAS_SKELETON"] if skeleton else []) + (["-DHAS_BOUNDARY"] if boundary else [])
+        self._user = _compile_user(self._PRELUDE + source + self._EPILOGUE, flags)
+        fn = lambda name, on: C.cast(getattr(self._user, name), C.c_void_p) if on else None
+        c = np.zeros(32)
+        c[:len(constants)] = constants
+        self._h = lib().fo_vector_operator_create(space._h, dim_range, fn("u_interior", True), fn("u_skeleton", skeleton), fn("u_boundary", boundary), c, 32)
+
+    def apply(self, u, linear=False):
+        w = np.empty(self.size)
+        lib().fo_vector_operator_apply(self._h, np.ascontiguousarray(u, dtype=np.float64), w, int(linear))
+        return w
+
+    def __del__(self):
+        try:
+            lib().fo_vector_operator_destroy(self._h)
+        except Exception:
+            pass
 
 
 def quadrature(dim, order):

@@ -64,3 +64,64 @@ __device__ void boundary(const double* x, int axis, int side, double ihbnd, cons
     ref = builtin.apply(u)
     assert np.abs(user.apply(u) - ref).max() < 1e-13 * np.abs(ref).max()
     assert np.abs(user.apply(u, linear=True) - ref).max() < 1e-13 * np.abs(ref).max()
+
+
+# ---- vector-valued spaces (dimRange > 1) and continuous Lagrange spaces ----
+VSRC = {name: open(os.path.join(HERE, "integrands", name + ".cuh")).read() for name in ("testoperator_vector", "testoperator_vector_lin", "system_dg")}
+
+
+@pytest.mark.parametrize("name,kind,dim,order,R,skel,bnd", [("testoperator_vector", _capi.LAGRANGE, 2, 2, 2, 0, 0), ("testoperator_vector", _capi.LAGRANGE, 3, 2, 3, 0, 0),
+                                                            ("testoperator_vector", _capi.LAGRANGE, 3, 1, 2, 0, 0), ("system_dg", _capi.DG_LEGENDRE_HIER, 3, 2, 2, 1, 1),
+                                                            ("system_dg", _capi.DG_ONB, 2, 3, 3, 1, 1), ("system_dg", _capi.DG_LEGENDRE_HIER, 3, 1, 4, 1, 1)])
+def test_vector_integrands_compile_into_the_kernels(name, kind, dim, order, R, skel, bnd):
+    log = C.create_string_buffer(1 << 16)
+    rc = _capi.lib().b200fem_jit_compile_check_space(VSRC[name].encode(), kind, dim, order, R, skel, bnd, log, len(log))
+    assert rc == 0, log.value.decode()
+
+
+def test_scalar_integrands_compile_into_the_lagrange_kernels():
+    log = C.create_string_buffer(1 << 16)
+    for dim in (2, 3):
+        rc = _capi.lib().b200fem_jit_compile_check_space(SOURCE.encode(), _capi.LAGRANGE, dim, 2, 1, 0, 1, log, len(log))
+        assert rc == 0, log.value.decode()
+
+
+def test_vector_oracle_reduces_to_the_scalar_one_for_uncoupled_components():
+    """VectorOperator (fem_oracle.cpp) against the scalar element loop: R independent copies of the scalar form"""
+    scalar = open(os.path.join(HERE, "integrands", "adr_variable.cuh")).read()
+    # the scalar source applied per component: wrap it
+    wrap = "namespace sc {\nstruct PointValue { double u; double du[3]; };\nstruct PointRange { double s; double F[3]; };\n" + scalar + "\n}\n" + """
+__device__ void interior(const double* x, const VectorValue& u, VectorRange& r, const double* c, int dim) {
+  for (int k = 0; k < dimRange; ++k) { sc::PointValue v; sc::PointRange q; v.u = u.u[k]; q.s = 0; for (int d = 0; d < 3; ++d) { v.du[d] = u.du[k][d]; q.F[d] = 0; }
+    sc::interior(x, v, q, c, dim); r.s[k] = q.s; for (int d = 0; d < 3; ++d) r.F[k][d] = q.F[d]; } }
+__device__ void skeleton(const double* x, int axis, double sign, double ihe, const VectorValue& in, const VectorValue& out, VectorRange& rin, VectorRange& rout, const double* c, int dim) {
+  for (int k = 0; k < dimRange; ++k) { sc::PointValue a, b; sc::PointRange p, q; a.u = in.u[k]; b.u = out.u[k]; p.s = q.s = 0; for (int d = 0; d < 3; ++d) { a.du[d] = in.du[k][d]; b.du[d] = out.du[k][d]; p.F[d] = q.F[d] = 0; }
+    sc::skeleton(x, axis, sign, ihe, a, b, p, q, c, dim); rin.s[k] = p.s; rout.s[k] = q.s; for (int d = 0; d < 3; ++d) { rin.F[k][d] = p.F[d]; rout.F[k][d] = q.F[d]; } } }
+__device__ void boundary(const double* x, int axis, int side, double ihbnd, const VectorValue& u, VectorRange& r, const double* c, int dim) {
+  for (int k = 0; k < dimRange; ++k) { sc::PointValue v; sc::PointRange q; v.u = u.u[k]; q.s = 0; for (int d = 0; d < 3; ++d) { v.du[d] = u.du[k][d]; q.F[d] = 0; }
+    sc::boundary(x, axis, side, ihbnd, v, q, c, dim); r.s[k] = q.s; for (int d = 0; d < 3; ++d) r.F[k][d] = q.F[d]; } }
+"""
+    const = [0.05, 1.0, -0.5, 0.25, 80.0, 0.3, 0.7]
+    for kind, n, skel in ((ol.DG_LEGENDRE_HIER, [4, 3, 2], True), (ol.LAGRANGE, [4, 3], False), (ol.DG_ONB, [4, 3], True)):
+        lo, hi = [-1.0] * len(n), [1.0, 0.5, 2.0][:len(n)]
+        sp = ol.Space(n, lo, hi, kind, 2)
+        R = 3
+        u = np.random.default_rng(5).uniform(-1, 1, sp.size * R)
+        vop = ol.VectorUserOperator(sp, R, wrap, const, skeleton=skel, boundary=True)
+        sop = ol.UserOperator(sp, scalar, const, skeleton=skel, boundary=True)
+        w = vop.apply(u).reshape(-1, R)
+        for k in range(R):
+            ref = sop.apply(np.ascontiguousarray(u.reshape(-1, R)[:, k]))
+            assert np.abs(w[:, k] - ref).max() <= 1e-14 * np.abs(ref).max()
+
+
+def test_reference_vector_operator_check_holds_on_the_oracle():
+    """dune/fempy/test/testoperator.py:55-66 on its own configuration (Lagrange order 2, dimRange 2, 40 x 40): op(ubar) == linop(ubar)"""
+    n, R = [40, 40], 2
+    sp = ol.Space(n, [0.0, 0.0], [1.0, 1.0], ol.LAGRANGE, 2)
+    ubar = np.repeat((sp.node_positions() ** 2).sum(axis=1), R)        # interpolate(as_vector([dot(x,x),]*dimR))
+    op = ol.VectorUserOperator(sp, R, VSRC["testoperator_vector"], skeleton=False, boundary=False)
+    linop = ol.VectorUserOperator(sp, R, VSRC["testoperator_vector_lin"], skeleton=False, boundary=False)
+    a, d = op.apply(ubar), linop.apply(ubar)
+    assert np.abs(a).max() > 1e-3
+    assert np.abs(a - d).max() < 1e-15 + 1e-13 * np.abs(a).max()
