@@ -5,7 +5,7 @@ Host-side mirror of the reference's Python entry points for this path (python/du
 Everything computes on the GPU through the C ABI in include/b200fem.h; there is no CPU fallback.
 """
 from . import _capi  # noqa: F401
-from .grid import structuredGrid  # noqa: F401
+from .grid import structuredGrid, unstructuredGrid  # noqa: F401
 from . import space, operator, solver  # noqa: F401
 
-__all__ = ["structuredGrid", "space", "operator", "solver"]
+__all__ = ["structuredGrid", "unstructuredGrid", "space", "operator", "solver"]

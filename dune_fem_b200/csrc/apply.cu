@@ -24,6 +24,12 @@ int apply_local(b200fem_operator* op, const double* u, double* w, bool linear) {
   if (s->kind == B200FEM_LAGRANGE) {
     REQUIRE(!op->model.has_skeleton, B200FEM_ERR_NOT_IMPLEMENTED, "skeleton integrands on continuous spaces");
     REQUIRE(default_quadrature(op), B200FEM_ERR_NOT_IMPLEMENTED, "Lagrange spaces: only quadrature orders that select the (order+1)-point Gauss rule");
+    if (s->unst) {            // unstructured cube mesh: index arrays + per-element geometry, colour-ordered scatter
+      REQUIRE(op->kernel_pref == B200FEM_KERNEL_AUTO || op->kernel_pref == B200FEM_KERNEL_QUADRATURE, B200FEM_ERR_NOT_IMPLEMENTED, "unstructured meshes: the quadrature kernel only (the Kronecker form needs a Cartesian mesh)");
+      int rc = launch_lagrange_unstructured(op, u, w, !linear); if (rc) return rc;
+      op->timing.kernel = B200FEM_KERNEL_QUADRATURE;
+      return B200FEM_OK;
+    }
     // linear models: Kronecker form (one launch, every node written once); otherwise the generic quadrature kernel with
     // colour-ordered scatter
     const bool lag_kron_ok = op->model.gamma == 0.0;

@@ -99,6 +99,7 @@ static int make_mesh(b200fem_ctx* ctx, int dim, const int32_t* n, const double* 
 }
 extern "C" int b200fem_mesh_set_periodic(b200fem_mesh* m, int mask) {
   REQUIRE(m && mask >= 0 && mask < (1 << m->dim), B200FEM_ERR_INVALID, "mesh_set_periodic: bad argument");
+  REQUIRE(!m->unstructured, B200FEM_ERR_NOT_IMPLEMENTED, "periodic grids: Cartesian meshes");
   REQUIRE(m->refs == 0, B200FEM_ERR_INVALID, "mesh_set_periodic: spaces already exist on this mesh");
   REQUIRE(mask == 0 || m->proc[0] * m->proc[1] * m->proc[2] == 1, B200FEM_ERR_NOT_IMPLEMENTED, "periodic grids: one rank");
   for (int d = 0; d < m->dim; ++d) REQUIRE(!((mask >> d) & 1) || m->gn[d] >= 2, B200FEM_ERR_INVALID, "periodic axis needs at least two cells");
@@ -134,6 +135,7 @@ extern "C" int b200fem_partition_box(int dim, const int32_t* n, const int32_t* p
 }
 extern "C" int b200fem_mesh_local_box(b200fem_mesh* m, int overlap, int32_t* out) {
   REQUIRE(m && out, B200FEM_ERR_INVALID, "mesh_local_box: null argument");
+  REQUIRE(!m->unstructured, B200FEM_ERR_NOT_IMPLEMENTED, "mesh_local_box: Cartesian meshes");
   const int rank = m->pc[0] + m->proc[0] * (m->pc[1] + m->proc[1] * m->pc[2]);
   return b200fem_partition_box(m->dim, m->gn, m->proc, rank, overlap, out);
 }
@@ -171,6 +173,7 @@ extern "C" int b200fem_space_create_vector(b200fem_mesh* mesh, int kind, int ord
   REQUIRE(dim_range >= 1 && dim_range <= 4, B200FEM_ERR_NOT_IMPLEMENTED, "space_create_vector: dimRange 1..4");
   REQUIRE(dim_range == 1 || (mesh && mesh->ctx->world == 1), B200FEM_ERR_NOT_IMPLEMENTED, "vector-valued spaces on distributed meshes");
   REQUIRE(dim_range == 1 || order <= 3, B200FEM_ERR_NOT_IMPLEMENTED, "vector-valued spaces: orders 1..3");
+  REQUIRE(dim_range == 1 || !(mesh && mesh->unstructured), B200FEM_ERR_NOT_IMPLEMENTED, "vector-valued spaces on unstructured meshes");
   int rc = b200fem_space_create(mesh, kind, order, numbering, out); if (rc) return rc;
   (*out)->dim_range = dim_range; (*out)->size *= dim_range;        // space.size() = blockMapper().size() * localBlockSize
   return B200FEM_OK;
@@ -184,6 +187,15 @@ extern "C" int b200fem_space_create(b200fem_mesh* mesh, int kind, int order, int
     s->mesh = mesh; s->kind = kind; s->order = order; s->numbering = numbering; s->n1 = order + 1;
     const int dim = mesh->dim; s->nb = 1; for (int d = 0; d < dim; ++d) s->nb *= s->n1;
     s->box = mesh->box;
+    if (mesh->unstructured) {
+      REQUIRE(kind == B200FEM_LAGRANGE, B200FEM_ERR_NOT_IMPLEMENTED, "unstructured meshes carry continuous Lagrange spaces (DG spaces need the face connectivity of a Cartesian mesh)");
+      REQUIRE(order == 1 || order == 2, B200FEM_ERR_NOT_IMPLEMENTED, "Lagrange spaces: order 1 and 2 only");
+      s->tab = tabulate_1d(Basis::Lagrange, order, gauss_points_for_order(2 * order));
+      s->lay = LagrangeLayoutDev{}; s->lay.order = order;
+      int rc = unstructured_space_setup(s.get()); if (rc) return rc;
+      mesh->refs += 1;
+      *out = s.release(); return B200FEM_OK;
+    }
     if (kind == B200FEM_LAGRANGE) {
       REQUIRE(order == 1 || order == 2, B200FEM_ERR_NOT_IMPLEMENTED, "Lagrange spaces: order 1 and 2 only");
       REQUIRE(mesh->box.periodic == 0, B200FEM_ERR_NOT_IMPLEMENTED, "Lagrange spaces on periodic grids (dof identification across the boundary)");
@@ -221,7 +233,7 @@ extern "C" int b200fem_space_create(b200fem_mesh* mesh, int kind, int order, int
     *out = s.release(); return B200FEM_OK;
   } catch (const std::exception& ex) { return fail(B200FEM_ERR_INVALID, ex.what()); }
 }
-static void space_delete(b200fem_space* s) { if (s->d_lattice_map) { cudaSetDevice(s->mesh->ctx->device); cudaFree(s->d_lattice_map); } mesh_unref(s->mesh); delete s; }
+static void space_delete(b200fem_space* s) { unstructured_space_free(s); if (s->d_lattice_map) { cudaSetDevice(s->mesh->ctx->device); cudaFree(s->d_lattice_map); } mesh_unref(s->mesh); delete s; }
 static void space_unref(b200fem_space* s) { if (--s->refs <= 0 && s->released) space_delete(s); }
 extern "C" int b200fem_space_destroy(b200fem_space* s) {
   if (!s || s->released) return B200FEM_OK;
@@ -235,6 +247,7 @@ extern "C" int b200fem_space_elements(b200fem_space* s, int64_t* n) { REQUIRE(s 
 extern "C" int b200fem_space_dofmap(b200fem_space* s, int64_t e, int64_t* out) {
   REQUIRE(s && out, B200FEM_ERR_INVALID, "null"); REQUIRE(e >= 0 && e < s->elements, B200FEM_ERR_INVALID, "dofmap: element out of range");
   if (s->kind != B200FEM_LAGRANGE) { for (int j = 0; j < s->nb; ++j) out[j] = e * s->nb + j; return B200FEM_OK; }
+  if (s->unst) return unstructured_dofmap(s, e, out);
   const BoxDev& b = s->box; const int n1 = s->n1, k = s->order;
   const int ec[3] = {(int)(e % b.n[0]), (int)((e / b.n[0]) % b.n[1]), (int)(e / ((long long)b.n[0] * b.n[1]))};
   LagrangeLayoutDev L = s->lay; L.lattice_map = s->lattice_map.empty() ? nullptr : s->lattice_map.data();
@@ -252,6 +265,7 @@ static void mark_dirichlet(b200fem_operator* op) {
   // DirichletConstraints::updateDirichletDofs (schemes/dirichletconstraints.hh:435-554): all Lagrange nodes on boundary
   // faces whose side is flagged; values g(x_node).  Host-side, closed form over the boundary lattice.
   b200fem_space* s = op->sp; const BoxDev& b = s->box; const int dim = b.dim, k = s->order;
+  if (s->unst) { unstructured_mark_dirichlet(op); return; }
   op->h_dmask.assign((size_t)s->size, 0); op->h_dvals.assign((size_t)s->size, 0.0);
   LagrangeLayoutDev L = s->lay; L.lattice_map = s->lattice_map.empty() ? nullptr : s->lattice_map.data();
   const long long L0 = L.lattice[0], L1 = L.lattice[1], L2 = L.lattice[2];
@@ -279,6 +293,7 @@ extern "C" int b200fem_operator_create(b200fem_space* s, const b200fem_model* mo
 }
 int b200fem::operator_create_impl(b200fem_space* s, const b200fem_model* model, b200fem_operator** out) {
   REQUIRE(!(model->strong_dirichlet && s->kind != B200FEM_LAGRANGE), B200FEM_ERR_INVALID, "strong Dirichlet constraints need a Lagrange space");
+  REQUIRE(!(s->unst && (model->has_skeleton || model->has_boundary)), B200FEM_ERR_NOT_IMPLEMENTED, "unstructured meshes: interior integrands and strong Dirichlet constraints (no skeleton / boundary terms)");
   b200fem_ctx* c = s->mesh->ctx;
   CUDA_OK(cudaSetDevice(c->device));
   auto* op = new b200fem_operator; op->sp = s; op->model = *model; s->refs += 1;
@@ -410,6 +425,7 @@ extern "C" int b200fem_operator_timing(b200fem_operator* op, b200fem_timing* out
 // diag(A) of the Kronecker form, on the host (setup cost O(N), once per operator)
 int host_diagonal(b200fem_operator* op, std::vector<double>& diag, bool dirichlet_rows) {
   b200fem_space* s = op->sp; const BoxDev& b = s->box;
+  if (s->unst) return unstructured_diagonal(op, diag, dirichlet_rows);
   REQUIRE(op->model.gamma == 0.0 && default_quadrature(op), B200FEM_ERR_NOT_IMPLEMENTED, "diagonal: needs a linear model with the default quadrature (Kronecker form)");
   diag.assign((size_t)s->size, 0.0);
   if (s->kind == B200FEM_LAGRANGE) {

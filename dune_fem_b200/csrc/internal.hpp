@@ -49,8 +49,12 @@ struct b200fem_mesh {
   int proc[3], pc[3];                    // process grid and this rank's coordinates
   b200fem::BoxDev box;                   // local box incl. ghost layers (ghost layers only used by DG spaces)
   int olo[3], ohi[3];                    // owned range in global element coordinates
+  // unstructured conforming cube meshes (b200fem_mesh_unstructured): vertex coordinates [nvert][dim] and element -> vertex arrays
+  // [nelem][2^dim] in the cube reference element's vertex order; none of the Cartesian fields above is meaningful then
+  bool unstructured = false; long long nvert = 0, nelem = 0; std::vector<double> ux; std::vector<long long> uev;
   int refs = 0; bool released = false;
 };
+namespace b200fem { struct UnstructuredSpace; }
 struct b200fem_space {
   b200fem_mesh* mesh; int kind, order, numbering, n1, nb; long long size, elements;
   int dim_range = 1;                     // dimRange: dof blocks of dim_range components (size = blocks * dim_range); > 1: run-time compiled integrands only
@@ -58,6 +62,7 @@ struct b200fem_space {
   b200fem::Tab1D tab; std::vector<int> perm;   // DG: tensor index -> stored local index over the full n1^3 tensor basis (-1: not in the space)
   bool tensor_full = false;              // DG: the space is the whole 3-D tensor basis (the Kronecker kernels apply)
   b200fem::LagrangeLayoutDev lay; long long* d_lattice_map = nullptr; std::vector<long long> lattice_map;
+  b200fem::UnstructuredSpace* unst = nullptr;   // Lagrange space on an unstructured mesh: index arrays, geometry, colours (unstructured.cu)
   int refs = 0; bool released = false;
 };
 struct MarchMapCache;
@@ -118,6 +123,14 @@ int launch_dg_quadrature_any(b200fem_operator* op, const double* u, double* w, c
 int launch_lagrange_quadrature(b200fem_operator* op, const double* u, double* w, bool with_data);
 int launch_lagrange_kronecker(b200fem_operator* op, const double* u, double* w, const double* bvec);
 void free_march_cache(b200fem_operator* op);
+
+// ---- unstructured.cu: continuous Lagrange spaces on unstructured cube meshes ----
+int unstructured_space_setup(b200fem_space* s);                     // numbering, colours, device arrays
+void unstructured_space_free(b200fem_space* s);
+int unstructured_dofmap(const b200fem_space* s, long long e, int64_t* out);
+void unstructured_mark_dirichlet(b200fem_operator* op);             // all nodes on boundary faces
+int unstructured_diagonal(b200fem_operator* op, std::vector<double>& diag, bool dirichlet_rows);
+int launch_lagrange_unstructured(b200fem_operator* op, const double* u, double* w, bool with_data);
 
 // ---- jit.cu ----
 int operator_create_impl(b200fem_space* s, const b200fem_model* model, b200fem_operator** out);   // b200fem_operator_create without the scalar-space check

@@ -310,6 +310,7 @@ extern "C" int b200fem_operator_set_constants(b200fem_operator* op, const double
 extern "C" int b200fem_operator_create_jit(b200fem_space* space, const char* source, const double* constants, int nconstants,
                                            int has_skeleton, int has_boundary, b200fem_operator** out) {
   REQUIRE(space && source && out, B200FEM_ERR_INVALID, "operator_create_jit: null argument");
+  REQUIRE(!space->unst, B200FEM_ERR_NOT_IMPLEMENTED, "compiled integrands: Cartesian meshes");
   REQUIRE(!(space->kind == B200FEM_LAGRANGE && has_skeleton), B200FEM_ERR_NOT_IMPLEMENTED, "skeleton integrands on continuous spaces");
   REQUIRE(nconstants >= 0 && nconstants <= kJitMaxConstants, B200FEM_ERR_INVALID, "operator_create_jit: at most 32 constants");
   b200fem_model m; std::memset(&m, 0, sizeof(m)); m.has_skeleton = has_skeleton != 0; m.has_boundary = has_boundary != 0;

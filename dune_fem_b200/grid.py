@@ -88,6 +88,25 @@ def structuredGrid(lo, hi, n, ctx=None, proc=None, rank=0, periodic=None):
     return GridView(lo, hi, n, ctx=ctx, proc=proc, rank=rank, periodic=periodic)
 
 
+class UnstructuredGridView(GridView):
+    """Unstructured conforming cube mesh -- dune.alugrid.aluCubeGrid({"vertices": ..., "cubes": ...}) behind an adaptive leaf grid
+    view: `vertices` [nv][dim] coordinates, `cubes` [ne][2^dim] vertex numbers in the cube reference element's order."""
+
+    def __init__(self, vertices, cubes, ctx=None):
+        self.ctx = ctx or Context.default()
+        v = np.ascontiguousarray(vertices, dtype=np.float64)
+        c = np.ascontiguousarray(cubes, dtype=np.int64)
+        assert v.ndim == 2 and c.ndim == 2 and c.shape[1] == 1 << v.shape[1], "vertices [nv][dim], cubes [ne][2^dim]"
+        self.dim, self.vertices, self.cubes = v.shape[1], v, c
+        self.proc, self.rank, self.periodic = None, 0, 0
+        self.handle = C.c_void_p()
+        capi.check(capi.lib().b200fem_mesh_unstructured(self.ctx.handle, self.dim, v.shape[0], capi.ptr(v), c.shape[0], capi.ptr(c, np.int64), C.byref(self.handle)))
+
+
+def unstructuredGrid(vertices, cubes, ctx=None):
+    return UnstructuredGridView(vertices, cubes, ctx=ctx)
+
+
 def partition_box(n_global, proc, rank, overlap):
     """host-only: (origin, extents, own_lo, own_hi) of `rank`'s box, see b200fem_partition_box"""
     dim = len(n_global)

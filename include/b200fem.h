@@ -96,6 +96,17 @@ int b200fem_memcpy_d2h(b200fem_ctx* ctx, void* host, const void* dev, int64_t by
  * split into proc[0] x proc[1] x proc[2] boxes (rank = c0 + proc0*(c1 + proc1*c2)); DG spaces then carry one
  * layer of ghost elements (overlap 1). */
 int b200fem_mesh_cartesian(b200fem_ctx* ctx, int dim, const int32_t* n, const double* lo, const double* hi, b200fem_mesh** out);
+/* Unstructured conforming cube meshes -- what ALUGrid< dim, dim, cube, conforming > behind an AdaptiveLeafGridPart hands to the
+ * reference: coords[n_vertices][dim], elem_vertices[n_elements][2^dim] in the cube reference element's vertex order (vertex v:
+ * bit d set <=> xi_d = 1; Jacobian determinant positive).  Continuous Lagrange spaces of order 1 and 2 on one rank:
+ * the dof mapper becomes an index array (space/lagrange/dofmappercode.hh:56-104 -> space/mapper/indexsetdofmapper.hh:414-427;
+ * dof blocks by geometry type, first-touch order inside a block, gridpart/adaptiveleafindexset.hh:884-906), the geometry the
+ * element's multilinear map (integrationElement / jacobianInverseTransposed per quadrature point), the scatter colour-ordered.
+ * Operators: interior integrands of the built-in family + strong Dirichlet constraints on the WHOLE boundary
+ * (strong_dirichlet = 1, any dirichlet_mask); no skeleton / boundary terms, no Kronecker kernel, no run-time compiled
+ * integrands.  Krylov solvers, the matrix-free diagonal and Newton work as on Cartesian meshes. */
+int b200fem_mesh_unstructured(b200fem_ctx* ctx, int dim, int64_t n_vertices, const double* coords, int64_t n_elements,
+                              const int64_t* elem_vertices, b200fem_mesh** out);
 int b200fem_mesh_cartesian_distributed(b200fem_ctx* ctx, int dim, const int32_t* n_global, const double* lo, const double* hi,
                                        const int32_t* proc, int rank, b200fem_mesh** out);
 /* Periodic grid (YaspGrid's `periodic` bitset): bit d set = the faces on the two sides of axis d are interior faces whose

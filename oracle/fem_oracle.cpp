@@ -51,6 +51,7 @@
 #include <mutex>
 #include <shared_mutex>
 #include <thread>
+#include <map>
 #include <vector>
 
 namespace oracle {
@@ -890,6 +891,113 @@ struct VectorOperator {
     }
   }
 };
+
+// ---------------------------------------------------------------------------
+// Unstructured conforming cube meshes: vertex coordinates + element -> vertex arrays in the cube reference element's vertex
+// order (vertex v: bit d set <=> xi_d = 1) -- what ALUGrid< dim, dim, cube, conforming > behind an AdaptiveLeafGridPart hands
+// to the reference.  Continuous Lagrange spaces of order 1 and 2:
+//  * dof numbering: one block per geometry type, vertices / edges / faces / cells (indexsetdofmapper.hh:504-515), inside a block
+//    the AdaptiveLeafIndexSet's first-touch order (elements in index order, sub-entities in reference-element order,
+//    gridpart/adaptiveleafindexset.hh:884-906, 1015-1019); local numbering of the nodes coordinate 0 fastest
+//    (lagrange/genericlagrangepoints.hh:862-876);
+//  * geometry: the multilinear map of the cube; integrationElement = |det J| (galerkin.hh:353), gradients through
+//    jacobianInverseTransposed (basisfunctionset/default.hh:239, 266; transformation.hh:35-45);
+//  * element loop = Operator::evaluateRange without faces (galerkin.hh:811-917, interior integral :332-360), then the
+//    Dirichlet wrapper on ALL boundary nodes when the model asks for strong constraints (dirichletconstraints.hh:435-554).
+// ---------------------------------------------------------------------------
+struct UnstructuredLagrange {
+  int dim, order, nb, nv; int64_t nvert, nelem, size = 0;
+  std::vector<double> X; std::vector<int64_t> ev, dofs; ShapeFunctionSet sfs; Tabulation vol; Model model;
+  std::vector<uint8_t> boundaryDof; std::vector<double> nodeX, dirichletValue;
+
+  UnstructuredLagrange(int dim_, int64_t nvert_, const double* x, int64_t nelem_, const int64_t* e, int order_, const Model& m)
+    : dim(dim_), order(order_), nv(1 << dim_), nvert(nvert_), nelem(nelem_), X(x, x + nvert_*dim_), ev(e, e + nelem_*(1 << dim_)), sfs(dim_, order_, LAGRANGE), model(m) {
+    nb = sfs.nb;
+    Quadrature q = cubeQuadrature(dim, 2*order);
+    vol.nop = q.nop; vol.w = q.w; vol.x = q.x; vol.B.resize((size_t)q.nop*nb); vol.G.resize((size_t)q.nop*nb*3);
+    for (int p = 0; p < q.nop; ++p) { sfs.evaluateEach(&q.x[3*p], &vol.B[(size_t)p*nb]); sfs.jacobianEach(&q.x[3*p], &vol.G[(size_t)p*nb*3]); }
+    numberDofs();
+  }
+  static void subEntityOrder(int dim, std::vector<std::array<int,3>> subs[4]) {     // as Space::buildSubEntityOrder
+    for (int v = 0; v < (1 << dim); ++v) { std::array<int,3> a = {0,0,0}; for (int d = 0; d < dim; ++d) a[d] = 2*((v >> d) & 1); subs[0].push_back(a); }
+    if (dim == 2) { subs[1] = { {0,1,0}, {2,1,0}, {1,0,0}, {1,2,0} }; subs[2] = { {1,1,0} }; }
+    if (dim == 3) {
+      subs[1] = { {0,0,1},{2,0,1},{0,2,1},{2,2,1}, {0,1,0},{2,1,0},{1,0,0},{1,2,0}, {0,1,2},{2,1,2},{1,0,2},{1,2,2} };
+      subs[2] = { {0,1,1},{2,1,1},{1,0,1},{1,2,1},{1,1,0},{1,1,2} };
+      subs[3] = { {1,1,1} };
+    }
+  }
+  // sorted global vertex numbers of the sub-entity with lattice offsets a (a_d = 1: the entity extends along axis d)
+  std::vector<int64_t> entityKey(int64_t e, const std::array<int,3>& a) const {
+    std::vector<int64_t> key;
+    for (int v = 0; v < nv; ++v) { bool in = true; for (int d = 0; d < dim; ++d) if (a[d] != 1 && ((v >> d) & 1) != a[d]/2) in = false; if (in) key.push_back(ev[(size_t)e*nv + v]); }
+    std::sort(key.begin(), key.end()); return key;
+  }
+  int localIndex(const std::array<int,3>& a) const {
+    int l = 0, stride = 1; for (int d = 0; d < dim; ++d) { l += stride*(order == 1 ? a[d]/2 : a[d]); stride *= order + 1; } return l;
+  }
+  void referencePoint(int l, double xi[3]) const { for (int d = 0; d < 3; ++d) xi[d] = d < dim ? (double)sfs.multiIndex[l][d]/order : 0.0; }
+  void mapPoint(int64_t e, const double xi[3], double x[3]) const {
+    x[0] = x[1] = x[2] = 0;
+    for (int v = 0; v < nv; ++v) { double N = 1; for (int d = 0; d < dim; ++d) N *= ((v >> d) & 1) ? xi[d] : 1.0 - xi[d]; for (int i = 0; i < dim; ++i) x[i] += N*X[(size_t)ev[(size_t)e*nv + v]*dim + i]; }
+  }
+  // J[i][d] = d x_i / d xi_d; returns det J and the inverse
+  double jacobian(int64_t e, const double xi[3], double Jinv[3][3]) const {
+    double J[3][3] = {{1,0,0},{0,1,0},{0,0,1}};
+    for (int i = 0; i < dim; ++i) for (int d = 0; d < dim; ++d) J[i][d] = 0;
+    for (int v = 0; v < nv; ++v)
+      for (int d = 0; d < dim; ++d) {
+        double dN = ((v >> d) & 1) ? 1.0 : -1.0; for (int k = 0; k < dim; ++k) if (k != d) dN *= ((v >> k) & 1) ? xi[k] : 1.0 - xi[k];
+        for (int i = 0; i < dim; ++i) J[i][d] += dN*X[(size_t)ev[(size_t)e*nv + v]*dim + i];
+      }
+    const double det = J[0][0]*(J[1][1]*J[2][2] - J[1][2]*J[2][1]) - J[0][1]*(J[1][0]*J[2][2] - J[1][2]*J[2][0]) + J[0][2]*(J[1][0]*J[2][1] - J[1][1]*J[2][0]);
+    const double id = 1.0/det;
+    Jinv[0][0] = (J[1][1]*J[2][2] - J[1][2]*J[2][1])*id; Jinv[0][1] = (J[0][2]*J[2][1] - J[0][1]*J[2][2])*id; Jinv[0][2] = (J[0][1]*J[1][2] - J[0][2]*J[1][1])*id;
+    Jinv[1][0] = (J[1][2]*J[2][0] - J[1][0]*J[2][2])*id; Jinv[1][1] = (J[0][0]*J[2][2] - J[0][2]*J[2][0])*id; Jinv[1][2] = (J[0][2]*J[1][0] - J[0][0]*J[1][2])*id;
+    Jinv[2][0] = (J[1][0]*J[2][1] - J[1][1]*J[2][0])*id; Jinv[2][1] = (J[0][1]*J[2][0] - J[0][0]*J[2][1])*id; Jinv[2][2] = (J[0][0]*J[1][1] - J[0][1]*J[1][0])*id;
+    return det;
+  }
+  void numberDofs() {
+    std::vector<std::array<int,3>> subs[4]; subEntityOrder(dim, subs);
+    std::map<std::vector<int64_t>, int64_t> index[4]; std::map<std::vector<int64_t>, int> faceCount;
+    for (int64_t e = 0; e < nelem; ++e)
+      for (int cd = 0; cd <= dim; ++cd) { const int pd = dim - cd; if (order == 1 && pd != 0) { if (pd == dim - 1) for (auto& a : subs[pd]) faceCount[entityKey(e, a)] += 1; continue; }
+        for (auto& a : subs[pd]) { auto key = entityKey(e, a); if (pd == dim - 1) faceCount[key] += 1; if (!index[pd].count(key)) { const int64_t i = (int64_t)index[pd].size(); index[pd][key] = i; } } }
+    int64_t off[5] = {0,0,0,0,0}; for (int p = 0; p <= dim; ++p) off[p+1] = off[p] + (int64_t)index[p].size();
+    size = off[dim+1];
+    dofs.assign((size_t)nelem*nb, -1); boundaryDof.assign((size_t)size, 0); nodeX.assign((size_t)size*3, 0.0);
+    for (int64_t e = 0; e < nelem; ++e)
+      for (int pd = 0; pd <= dim; ++pd) { if (order == 1 && pd != 0) continue;
+        for (auto& a : subs[pd]) { const int l = localIndex(a); const int64_t g = off[pd] + index[pd][entityKey(e, a)]; dofs[(size_t)e*nb + l] = g;
+          double xi[3]; referencePoint(l, xi); mapPoint(e, xi, &nodeX[(size_t)g*3]); } }
+    // boundary faces: touched by one element only; every node on them is a boundary node
+    for (int64_t e = 0; e < nelem; ++e)
+      for (auto& f : subs[dim-1]) { if (faceCount[entityKey(e, f)] != 1) continue;
+        for (int l = 0; l < nb; ++l) { bool on = true; for (int d = 0; d < dim; ++d) if (f[d] != 1 && sfs.multiIndex[l][d]*2/order != f[d]) on = false; if (on) boundaryDof[(size_t)dofs[(size_t)e*nb + l]] = 1; } }
+  }
+  void apply(const double* u, double* w, bool linear) const {
+    Model m = model; if (linear) m.data = 0;
+    std::fill(w, w + size, 0.0);
+    std::vector<double> ul(nb), wl(nb);
+    for (int64_t e = 0; e < nelem; ++e) {
+      for (int i = 0; i < nb; ++i) { ul[i] = u[dofs[(size_t)e*nb + i]]; wl[i] = 0; }
+      for (int q = 0; q < vol.nop; ++q) {
+        const double* B = &vol.B[(size_t)q*nb]; const double* G = &vol.G[(size_t)q*nb*3];
+        double Jinv[3][3], x[3]; const double det = jacobian(e, &vol.x[3*q], Jinv); mapPoint(e, &vol.x[3*q], x);
+        Value v; v.u = 0; double gh[3] = {0,0,0};
+        for (int i = 0; i < nb; ++i) { v.u += B[i]*ul[i]; for (int d = 0; d < 3; ++d) gh[d] += G[3*i+d]*ul[i]; }
+        for (int i = 0; i < 3; ++i) { v.du[i] = 0; if (i < dim) for (int d = 0; d < dim; ++d) v.du[i] += Jinv[d][i]*gh[d]; }   // J^-T gradhat
+        Range r = interiorIntegrand(m, dim, x, v);
+        const double weight = vol.w[q]*std::fabs(det);
+        double Fh[3] = {0,0,0}; for (int d = 0; d < dim; ++d) for (int i = 0; i < dim; ++i) Fh[d] += Jinv[d][i]*r.F[i];
+        for (int i = 0; i < nb; ++i) wl[i] += weight*(B[i]*r.s + G[3*i]*Fh[0] + G[3*i+1]*Fh[1] + G[3*i+2]*Fh[2]);
+      }
+      for (int i = 0; i < nb; ++i) w[dofs[(size_t)e*nb + i]] += wl[i];
+    }
+    if (model.strongDirichlet)
+      for (int64_t i = 0; i < size; ++i) if (boundaryDof[(size_t)i]) { double g = 0, dg[3], lap; if (!linear) dataFunction(model.data, dim, &nodeX[(size_t)i*3], g, dg, lap); w[i] = u[i] - g; }
+  }
+};
 }  // namespace oracle
 
 // ===========================================================================
@@ -943,6 +1051,18 @@ VectorOperator* fo_vector_operator_create(FoSpace* s, int R, UserInteriorV fi, U
   VectorOperator* op = new VectorOperator(*s->sp, R, fi, fs, fb); for (int i = 0; i < nc && i < 32; ++i) op->c[i] = c[i]; return op;
 }
 void fo_vector_operator_destroy(VectorOperator* op) { delete op; }
+// Lagrange space + ADR operator on an unstructured cube mesh (params / iparams as fo_operator_create; no skeleton / boundary terms)
+UnstructuredLagrange* fo_unstructured_create(int dim, int64_t nvert, const double* x, int64_t nelem, const int64_t* ev, int order, const double* params, const int* iparams) {
+  Model m; m.eps = params[0]; m.b[0] = params[1]; m.b[1] = params[2]; m.b[2] = params[3]; m.c = params[4]; m.gamma = params[5]; m.beta = params[6];
+  m.dirichletMask = iparams[0]; m.data = iparams[1]; m.strongDirichlet = iparams[4];
+  return new UnstructuredLagrange(dim, nvert, x, nelem, ev, order, m);
+}
+void fo_unstructured_destroy(UnstructuredLagrange* s) { delete s; }
+int64_t fo_unstructured_size(UnstructuredLagrange* s) { return s->size; }
+int fo_unstructured_local_size(UnstructuredLagrange* s) { return s->nb; }
+void fo_unstructured_dofmap(UnstructuredLagrange* s, int64_t e, int64_t* out) { for (int i = 0; i < s->nb; ++i) out[i] = s->dofs[(size_t)e*s->nb + i]; }
+void fo_unstructured_nodes(UnstructuredLagrange* s, double* x, uint8_t* boundary) { std::copy(s->nodeX.begin(), s->nodeX.end(), x); std::copy(s->boundaryDof.begin(), s->boundaryDof.end(), boundary); }
+void fo_unstructured_apply(UnstructuredLagrange* s, const double* u, double* w, int linear) { s->apply(u, w, linear != 0); }
 void fo_vector_operator_apply(VectorOperator* op, const double* u, double* w, int linear) {
   op->apply(u, w);
   if (linear) { const size_t n = (size_t)op->sp.size*op->R; std::vector<double> zero(n, 0.0), l0(n); op->apply(zero.data(), l0.data()); for (size_t i = 0; i < n; ++i) w[i] -= l0[i]; }

@@ -59,6 +59,16 @@ def lib():
     L.fo_vector_operator_create.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, _dp, C.c_int]
     L.fo_vector_operator_destroy.argtypes = [C.c_void_p]
     L.fo_vector_operator_apply.argtypes = [C.c_void_p, _dp, _dp, C.c_int]
+    L.fo_unstructured_create.restype = C.c_void_p
+    L.fo_unstructured_create.argtypes = [C.c_int, C.c_int64, _dp, C.c_int64, _lp, C.c_int, _dp, _ip]
+    L.fo_unstructured_destroy.argtypes = [C.c_void_p]
+    L.fo_unstructured_size.restype = C.c_int64
+    L.fo_unstructured_size.argtypes = [C.c_void_p]
+    L.fo_unstructured_local_size.restype = C.c_int
+    L.fo_unstructured_local_size.argtypes = [C.c_void_p]
+    L.fo_unstructured_dofmap.argtypes = [C.c_void_p, C.c_int64, _lp]
+    L.fo_unstructured_nodes.argtypes = [C.c_void_p, _dp, _bp]
+    L.fo_unstructured_apply.argtypes = [C.c_void_p, _dp, _dp, C.c_int]
     L.fo_operator_set_threads.argtypes = [C.c_void_p, C.c_int]
     L.fo_operator_set_inverse_mass.argtypes = [C.c_void_p, C.c_int]
     L.fo_operator_set_inverse_mass.restype = C.c_int
@@ -337,6 +347,64 @@ class VectorUserOperator:
     def __del__(self):
         try:
             lib().fo_vector_operator_destroy(self._h)
+        except Exception:
+            pass
+
+
+
+def cartesian_as_unstructured(n, lo, hi):
+    """vertex coordinates and element -> vertex arrays (cube reference order, elements x fastest) of a Cartesian mesh"""
+    dim = len(n)
+    nv = [k + 1 for k in n]
+    axes = [np.linspace(lo[d], hi[d], nv[d]) for d in range(dim)]
+    grids = np.meshgrid(*axes, indexing="ij")
+    vid = np.arange(int(np.prod(nv))).reshape(nv[::-1]).transpose(range(dim - 1, -1, -1))      # vid[i0, i1(, i2)], x fastest
+    coords = np.zeros((int(np.prod(nv)), dim))
+    for d in range(dim):
+        coords[vid.ravel(), d] = grids[d].ravel()
+    elems = []
+    rng = [range(k) for k in n]
+    import itertools
+    for idx in itertools.product(*rng[::-1]):                 # last axis slowest
+        ec = idx[::-1]
+        elems.append([vid[tuple(ec[d] + ((v >> d) & 1) for d in range(dim))] for v in range(1 << dim)])
+    return coords, np.array(elems, dtype=np.int64)
+
+
+class UnstructuredOperator:
+    """Lagrange space + ADR operator on an unstructured cube mesh (fem_oracle.cpp: UnstructuredLagrange)"""
+
+    def __init__(self, coords, elems, order, eps=1.0, b=(0.0, 0.0, 0.0), c=0.0, gamma=0.0, data=0, strong_dirichlet=False):
+        coords = np.ascontiguousarray(coords, dtype=np.float64)
+        elems = np.ascontiguousarray(elems, dtype=np.int64)
+        self.dim = coords.shape[1]
+        bb = list(b) + [0.0] * (3 - len(b))
+        params = np.array([eps, bb[0], bb[1], bb[2], c, gamma, 0.0], dtype=np.float64)
+        iparams = np.array([0, data, 0, 0, int(strong_dirichlet)], dtype=np.int32)
+        self._h = lib().fo_unstructured_create(self.dim, coords.shape[0], coords.ravel(), elems.shape[0], elems.ravel(), order, params, iparams)
+        self.size = lib().fo_unstructured_size(self._h)
+        self.local_size = lib().fo_unstructured_local_size(self._h)
+        self.elements = elems.shape[0]
+
+    def dofmap(self, e):
+        out = np.empty(self.local_size, dtype=np.int64)
+        lib().fo_unstructured_dofmap(self._h, e, out)
+        return out
+
+    def nodes(self):
+        x = np.empty((self.size, 3))
+        bnd = np.empty(self.size, dtype=np.uint8)
+        lib().fo_unstructured_nodes(self._h, x.reshape(-1), bnd)
+        return x[:, :self.dim], bnd
+
+    def apply(self, u, linear=False):
+        w = np.empty(self.size)
+        lib().fo_unstructured_apply(self._h, np.ascontiguousarray(u, dtype=np.float64), w, int(linear))
+        return w
+
+    def __del__(self):
+        try:
+            lib().fo_unstructured_destroy(self._h)
         except Exception:
             pass
 
