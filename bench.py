@@ -477,6 +477,32 @@ def main():
             del o, sp, g
             torch.cuda.empty_cache()
 
+        # (f)4: the same P2 space on an UNSTRUCTURED cube mesh (vertex / element arrays, distorted vertices): index arrays and
+        # per-element geometry instead of closed forms -- SURVEY.md 8(d) reports this traffic apart from the headline figure
+        cu = 64
+        ax = np.linspace(0.0, 1.0, cu + 1)
+        X = np.stack(np.meshgrid(ax, ax, ax, indexing="ij"), axis=-1)                       # X[i0, i1, i2] = vertex coordinates
+        vid = (np.arange(cu + 1)[:, None, None] + (cu + 1) * (np.arange(cu + 1)[None, :, None] + (cu + 1) * np.arange(cu + 1)[None, None, :]))
+        coords = np.zeros(((cu + 1) ** 3, 3))
+        coords[vid.ravel()] = X.reshape(-1, 3)
+        coords += np.random.default_rng(20261017).uniform(-0.15, 0.15, coords.shape) / cu
+        e0, e1, e2 = np.meshgrid(np.arange(cu), np.arange(cu), np.arange(cu), indexing="ij")
+        order_e = np.argsort((e0 + cu * (e1 + cu * e2)).ravel())                              # elements x fastest
+        cubes = np.stack([vid[e0 + (v & 1), e1 + ((v >> 1) & 1), e2 + (v >> 2)].ravel() for v in range(8)], axis=1)[order_e].astype(np.int64)
+        g = fem.unstructuredGrid(coords, cubes, ctx=ctx)
+        sp = fem.space.lagrange(g, order=2)
+        o = fem.operator.galerkin(sp, eps=1.0, data=2, dirichlet_mask=1, strong_dirichlet=True)
+        t_lin = timed_apply(o, sp.size, 20, True)
+        per_elem = 4 * 27 + 24 * 8                                                          # index array + vertex coordinates, B per element
+        bpd = 16.0 + per_elem * cu ** 3 / sp.size
+        other["P2 Lagrange 3D 64^3 cells as an unstructured cube mesh (index arrays + per-element geometry) apply"] = {
+            "dofs": sp.size, "elements": cu ** 3, "linear_ms": t_lin * 1e3, "linear_dofs_per_s": sp.size / t_lin, "launches_per_apply": o.timing()["launches_per_apply"],
+            "roofline": roofline_block("lagrange_unstructured_kernel<3, 27>", sp.size, t_lin, peak, peak_src, traffic, 2.0 * cu ** 3 * 27 * (27 * 8 + 60),
+                                       "dense tabulated contraction: 27 points x (27 x 4 evaluate + 27 x 4 axpy + ~60 geometry / integrand) FMA per element", bytes_per_dof=bpd),
+            "note": "algorithmic bytes = 16 B/dof + 108 B of indices + 192 B of vertex coordinates per element (SURVEY.md 8d: reported apart from the headline)"}
+        del o, sp, g
+        torch.cuda.empty_cache()
+
     # ------------------------------------------------------------------------------------------ multi-GPU parity (checker only)
     parity = None
     if world > 1 and not args.no_parity:

@@ -25,6 +25,7 @@
 #include "comm.cuh"
 #include "dg_quadrature.cuh"
 #include "lagrange_quadrature.cuh"
+#include "lagrange_unstructured.cuh"
 #include "tables.hpp"
 #include "vec_types.hpp"
 
@@ -131,6 +132,9 @@ int unstructured_dofmap(const b200fem_space* s, long long e, int64_t* out);
 void unstructured_mark_dirichlet(b200fem_operator* op);             // all nodes on boundary faces
 int unstructured_diagonal(b200fem_operator* op, std::vector<double>& diag, bool dirichlet_rows);
 int launch_lagrange_unstructured(b200fem_operator* op, const double* u, double* w, bool with_data);
+// what a launch of lagrange_unstructured_kernel needs (for the run-time compiled instantiations, jit.cu)
+struct UnstructuredLaunch { UnstructuredTabDev tab; const int* order; const int* dofs; const double* elem_x; const std::vector<int>* colour_begin; int eb, threads; size_t smem; };
+int unstructured_launch_info(const b200fem_space* s, UnstructuredLaunch* out);
 
 // ---- jit.cu ----
 int operator_create_impl(b200fem_space* s, const b200fem_model* model, b200fem_operator** out);   // b200fem_operator_create without the scalar-space check

@@ -77,14 +77,14 @@ std::string csrc_dir() {
 }
 
 // which kernel the integrands are compiled into
-enum JitVariant { kJitDg = 0, kJitLagrange3d = 1, kJitLagrange2d = 2 };
+enum JitVariant { kJitDg = 0, kJitLagrange3d = 1, kJitLagrange2d = 2, kJitUnstructured2d = 3, kJitUnstructured3d = 4 };
 
 std::string program_text(const std::string& user, bool skel, bool bnd, int N, int MI, int MS, int R, int variant, std::string* name_expr) {
   const std::string rs = std::to_string(R);
   // scalar spaces: PointValue / PointRange; range-R spaces: VectorValue = PointValueV<R>, VectorRange = PointRangeV<R>
   const std::string V = R == 1 ? "PointValue" : "PointValueV<" + rs + ">", G = R == 1 ? "PointRange" : "PointRangeV<" + rs + ">";
   std::string t;
-  t += "#include \"lagrange_quadrature.cuh\"\n#include \"jit_integrands.cuh\"\n";
+  t += "#include \"lagrange_quadrature.cuh\"\n#include \"lagrange_unstructured.cuh\"\n#include \"jit_integrands.cuh\"\n";
   t += "namespace b200fem {\nnamespace user {\nconstexpr int dimRange = " + rs + ";\nusing VectorValue = PointValueV<dimRange>;\nusing VectorRange = PointRangeV<dimRange>;\n#line 1 \"integrands\"\n" + user + "\n}  // namespace user\n";
   t += "struct JitIntegrands : JitIntegrandsBase {\n"
        "  __device__ static void zero(" + G + "& r) { double* p = reinterpret_cast<double*>(&r); for (int i = 0; i < (int)(sizeof(" + G + ") / sizeof(double)); ++i) p[i] = 0; }\n"
@@ -98,7 +98,8 @@ std::string program_text(const std::string& user, bool skel, bool bnd, int N, in
   const std::string n = std::to_string(N);
   if (variant == kJitDg) *name_expr = "b200fem::dg_quadrature_kernel<" + n + ", " + std::to_string(MI) + ", " + std::to_string(MS) + ", b200fem::JitIntegrands, true, " + rs + ">";
   else if (variant == kJitLagrange3d) *name_expr = "b200fem::lagrange3d_quadrature_kernel<" + n + ", b200fem::JitIntegrands, " + rs + ">";
-  else *name_expr = "b200fem::lagrange2d_quadrature_kernel<" + n + ", b200fem::JitIntegrands, " + rs + ">";
+  else if (variant == kJitLagrange2d) *name_expr = "b200fem::lagrange2d_quadrature_kernel<" + n + ", b200fem::JitIntegrands, " + rs + ">";
+  else *name_expr = std::string("b200fem::lagrange_unstructured_kernel<") + (variant == kJitUnstructured2d ? "2, " + std::to_string(N * N) : "3, " + std::to_string(N * N * N)) + ", b200fem::JitIntegrands>";
   return t;
 }
 
@@ -227,8 +228,33 @@ template <int N> static int launch_jit_lagrange_t(b200fem_operator* op, const do
   return B200FEM_OK;
 }
 
+// unstructured cube meshes: w.clear(), then one launch per colour of lagrange_unstructured_kernel (index arrays, per-element geometry)
+static int launch_jit_unstructured(b200fem_operator* op, const double* u, double* w) {
+  b200fem_space* s = op->sp; cudaStream_t st = s->mesh->ctx->stream; const int dim = s->mesh->dim, N = s->n1;
+  UnstructuredLaunch L; int rc = unstructured_launch_info(s, &L); if (rc) return rc;
+  JitKernel* K = nullptr; rc = jit_kernel(op, N, N, N, dim == 2 ? kJitUnstructured2d : kJitUnstructured3d, 0, &K); if (rc) return rc;
+  CUDA_OK(cudaMemsetAsync(w, 0, sizeof(double) * (size_t)s->size, st));
+  BoxDev b; std::memset(&b, 0, sizeof(b)); b.dim = dim; JitIntegrandsBase I = jit_params(op, b);
+  int launches = 1;
+  for (size_t c = 0; c + 1 < L.colour_begin->size(); ++c) {
+    int first = (*L.colour_begin)[c], count = (*L.colour_begin)[c + 1] - first; if (count <= 0) continue;
+    void* args[] = {&L.tab, &I, &L.order, &L.dofs, &L.elem_x, &u, &w, &first, &count};
+    if (g_drv.LaunchKernel(K->fn, (unsigned)((count + L.eb - 1) / L.eb), 1, 1, (unsigned)L.threads, 1, 1, (unsigned)L.smem, (CUstream)st, args, nullptr) != CUDA_SUCCESS)
+      return fail(B200FEM_ERR_CUDA, "cuLaunchKernel failed for the compiled integrands");
+    ++launches;
+  }
+  op->timing.launches_per_apply = launches;
+  return B200FEM_OK;
+}
+
 static int launch_jit(b200fem_operator* op, const double* u, double* w, const double* sub) {
   const int k = op->sp->order, N = op->sp->n1;
+  if (op->sp->unst) {
+    REQUIRE(default_quadrature(op), B200FEM_ERR_NOT_IMPLEMENTED, "Lagrange spaces: only quadrature orders that select the (order+1)-point Gauss rule");
+    int rc = launch_jit_unstructured(op, u, w); if (rc) return rc;
+    if (sub) { rc = b200fem_axpy_dev(op, -1.0, sub, w); if (rc) return rc; op->timing.launches_per_apply += 1; }   // L[u] - L[0]
+    return B200FEM_OK;
+  }
   if (op->sp->kind == B200FEM_LAGRANGE) {
     REQUIRE(default_quadrature(op), B200FEM_ERR_NOT_IMPLEMENTED, "Lagrange spaces: only quadrature orders that select the (order+1)-point Gauss rule");
     REQUIRE(!op->jit->skel, B200FEM_ERR_NOT_IMPLEMENTED, "skeleton integrands on continuous spaces");
@@ -297,6 +323,15 @@ extern "C" int b200fem_jit_compile_check_space(const char* source, int kind, int
   return rc ? fail(rc, lg) : B200FEM_OK;
 }
 
+/* ... and for a Lagrange space on an unstructured cube mesh (interior integrands only) */
+extern "C" int b200fem_jit_compile_check_unstructured(const char* source, int dim, int order, char* log, int log_len) {
+  REQUIRE(source && (order == 1 || order == 2) && (dim == 2 || dim == 3), B200FEM_ERR_INVALID, "jit_compile_check_unstructured: bad argument");
+  std::string lg; const int n = order + 1;
+  const int rc = compile(source, false, false, n, n, n, 1, dim == 2 ? kJitUnstructured2d : kJitUnstructured3d, nullptr, nullptr, &lg);
+  if (log && log_len > 0) { std::strncpy(log, lg.c_str(), (size_t)log_len - 1); log[log_len - 1] = '\0'; }
+  return rc ? fail(rc, lg) : B200FEM_OK;
+}
+
 extern "C" int b200fem_operator_set_constants(b200fem_operator* op, const double* constants, int nconstants) {
   REQUIRE(op && op->jit, B200FEM_ERR_INVALID, "set_constants: not an operator with compiled integrands");
   REQUIRE(nconstants >= 0 && nconstants <= kJitMaxConstants && (constants || nconstants == 0), B200FEM_ERR_INVALID, "set_constants: at most 32 constants");
@@ -310,7 +345,7 @@ extern "C" int b200fem_operator_set_constants(b200fem_operator* op, const double
 extern "C" int b200fem_operator_create_jit(b200fem_space* space, const char* source, const double* constants, int nconstants,
                                            int has_skeleton, int has_boundary, b200fem_operator** out) {
   REQUIRE(space && source && out, B200FEM_ERR_INVALID, "operator_create_jit: null argument");
-  REQUIRE(!space->unst, B200FEM_ERR_NOT_IMPLEMENTED, "compiled integrands: Cartesian meshes");
+  REQUIRE(!(space->unst && (has_skeleton || has_boundary)), B200FEM_ERR_NOT_IMPLEMENTED, "unstructured meshes: interior integrands only");
   REQUIRE(!(space->kind == B200FEM_LAGRANGE && has_skeleton), B200FEM_ERR_NOT_IMPLEMENTED, "skeleton integrands on continuous spaces");
   REQUIRE(nconstants >= 0 && nconstants <= kJitMaxConstants, B200FEM_ERR_INVALID, "operator_create_jit: at most 32 constants");
   b200fem_model m; std::memset(&m, 0, sizeof(m)); m.has_skeleton = has_skeleton != 0; m.has_boundary = has_boundary != 0;

@@ -15,8 +15,10 @@
 // staged in shared memory.  Algorithmic traffic per element: 4 NB B of indices + 24 * 2^dim B of coordinates on top of the
 // 16 B/dof of the structured kernels (SURVEY.md 8d reports this separately from the headline).
 #pragma once
+#ifndef __CUDACC_RTC__       // (also compiled at run time by NVRTC for user-supplied integrands, jit.cu)
 #include <cuda_runtime.h>
 #include <cstdint>
+#endif
 #include "integrands.cuh"
 
 namespace b200fem {
@@ -32,7 +34,7 @@ struct UnstructuredTabDev {
 
 template <int DIM, int NB> struct UnstructuredCfg {
   static constexpr int NV = 1 << DIM, EB = (128 / NB) > 0 ? 128 / NB : 1, kThreads = EB * NB;
-  static constexpr size_t smem_bytes() { return sizeof(double) * (size_t)EB * (NB + 3 * NV + 4 * NB); }
+  __host__ __device__ static constexpr unsigned long long smem_bytes() { return sizeof(double) * (unsigned long long)EB * (NB + 3 * NV + 4 * NB); }
 };
 
 template <int DIM, int NB, class Integrands>

@@ -242,6 +242,16 @@ template <int DIM, int NB> static int launch_unst(b200fem_operator* op, const do
   op->timing.launches_per_apply = launches;
   return B200FEM_OK;
 }
+int unstructured_launch_info(const b200fem_space* s, UnstructuredLaunch* out) {
+  const UnstructuredSpace* U = s->unst; const int dim = s->mesh->dim, k = s->order;
+  out->tab = U->tab; out->order = U->d_order; out->dofs = U->d_dofs; out->elem_x = U->d_elem_x; out->colour_begin = &U->colour_begin;
+  auto set = [&](int eb, int threads, size_t smem) { out->eb = eb; out->threads = threads; out->smem = smem; };
+  if (dim == 2 && k == 1) set(UnstructuredCfg<2, 4>::EB, UnstructuredCfg<2, 4>::kThreads, UnstructuredCfg<2, 4>::smem_bytes());
+  else if (dim == 2) set(UnstructuredCfg<2, 9>::EB, UnstructuredCfg<2, 9>::kThreads, UnstructuredCfg<2, 9>::smem_bytes());
+  else if (k == 1) set(UnstructuredCfg<3, 8>::EB, UnstructuredCfg<3, 8>::kThreads, UnstructuredCfg<3, 8>::smem_bytes());
+  else set(UnstructuredCfg<3, 27>::EB, UnstructuredCfg<3, 27>::kThreads, UnstructuredCfg<3, 27>::smem_bytes());
+  return B200FEM_OK;
+}
 int launch_lagrange_unstructured(b200fem_operator* op, const double* u, double* w, bool with_data) {
   const int dim = op->sp->mesh->dim, k = op->sp->order;
   if (dim == 2) return k == 1 ? launch_unst<2, 4>(op, u, w, with_data) : launch_unst<2, 9>(op, u, w, with_data);

@@ -103,8 +103,9 @@ int b200fem_mesh_cartesian(b200fem_ctx* ctx, int dim, const int32_t* n, const do
  * dof blocks by geometry type, first-touch order inside a block, gridpart/adaptiveleafindexset.hh:884-906), the geometry the
  * element's multilinear map (integrationElement / jacobianInverseTransposed per quadrature point), the scatter colour-ordered.
  * Operators: interior integrands of the built-in family + strong Dirichlet constraints on the WHOLE boundary
- * (strong_dirichlet = 1, any dirichlet_mask); no skeleton / boundary terms, no Kronecker kernel, no run-time compiled
- * integrands.  Krylov solvers, the matrix-free diagonal and Newton work as on Cartesian meshes. */
+ * (strong_dirichlet = 1, any dirichlet_mask), or run-time compiled interior() integrands (b200fem_operator_create_jit with
+ * has_skeleton = has_boundary = 0); no skeleton / boundary terms, no Kronecker kernel.  Krylov solvers, the matrix-free diagonal
+ * and Newton work as on Cartesian meshes. */
 int b200fem_mesh_unstructured(b200fem_ctx* ctx, int dim, int64_t n_vertices, const double* coords, int64_t n_elements,
                               const int64_t* elem_vertices, b200fem_mesh** out);
 int b200fem_mesh_cartesian_distributed(b200fem_ctx* ctx, int dim, const int32_t* n_global, const double* lo, const double* hi,
@@ -213,6 +214,8 @@ int b200fem_jit_compile_check(const char* source, int order, char* log, int log_
 /* ... and for any space the integrands can run on: space kind, mesh dimension (2 / 3), order, dimRange */
 int b200fem_jit_compile_check_space(const char* source, int kind, int dim, int order, int dim_range, int has_skeleton, int has_boundary,
                                     char* log, int log_len);
+/* ... and for a Lagrange space on an unstructured cube mesh (interior() only; lagrange_unstructured.cuh) */
+int b200fem_jit_compile_check_unstructured(const char* source, int dim, int order, char* log, int log_len);
 
 /* strong Dirichlet marks and values (schemes/dirichletconstraints.hh:435-554) */
 int b200fem_operator_dirichlet(b200fem_operator* op, uint8_t* mask_host, double* values_host);

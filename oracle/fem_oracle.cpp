@@ -909,6 +909,7 @@ struct UnstructuredLagrange {
   int dim, order, nb, nv; int64_t nvert, nelem, size = 0;
   std::vector<double> X; std::vector<int64_t> ev, dofs; ShapeFunctionSet sfs; Tabulation vol; Model model;
   std::vector<uint8_t> boundaryDof; std::vector<double> nodeX, dirichletValue;
+  UserIntegrands user;                       // optional callbacks (model.user points here once set)
 
   UnstructuredLagrange(int dim_, int64_t nvert_, const double* x, int64_t nelem_, const int64_t* e, int order_, const Model& m)
     : dim(dim_), order(order_), nv(1 << dim_), nvert(nvert_), nelem(nelem_), X(x, x + nvert_*dim_), ev(e, e + nelem_*(1 << dim_)), sfs(dim_, order_, LAGRANGE), model(m) {
@@ -1056,6 +1057,10 @@ UnstructuredLagrange* fo_unstructured_create(int dim, int64_t nvert, const doubl
   Model m; m.eps = params[0]; m.b[0] = params[1]; m.b[1] = params[2]; m.b[2] = params[3]; m.c = params[4]; m.gamma = params[5]; m.beta = params[6];
   m.dirichletMask = iparams[0]; m.data = iparams[1]; m.strongDirichlet = iparams[4];
   return new UnstructuredLagrange(dim, nvert, x, nelem, ev, order, m);
+}
+// user-supplied interior integrand instead of the built-in family (the same callbacks as fo_operator_create_user)
+void fo_unstructured_set_user(UnstructuredLagrange* s, UserInterior fi, const double* c, int nc) {
+  s->user.interior = fi; for (int i = 0; i < nc && i < 32; ++i) s->user.c[i] = c[i]; s->model.user = &s->user;
 }
 void fo_unstructured_destroy(UnstructuredLagrange* s) { delete s; }
 int64_t fo_unstructured_size(UnstructuredLagrange* s) { return s->size; }

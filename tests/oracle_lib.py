@@ -62,6 +62,7 @@ def lib():
     L.fo_unstructured_create.restype = C.c_void_p
     L.fo_unstructured_create.argtypes = [C.c_int, C.c_int64, _dp, C.c_int64, _lp, C.c_int, _dp, _ip]
     L.fo_unstructured_destroy.argtypes = [C.c_void_p]
+    L.fo_unstructured_set_user.argtypes = [C.c_void_p, C.c_void_p, _dp, C.c_int]
     L.fo_unstructured_size.restype = C.c_int64
     L.fo_unstructured_size.argtypes = [C.c_void_p]
     L.fo_unstructured_local_size.restype = C.c_int
@@ -374,7 +375,8 @@ def cartesian_as_unstructured(n, lo, hi):
 class UnstructuredOperator:
     """Lagrange space + ADR operator on an unstructured cube mesh (fem_oracle.cpp: UnstructuredLagrange)"""
 
-    def __init__(self, coords, elems, order, eps=1.0, b=(0.0, 0.0, 0.0), c=0.0, gamma=0.0, data=0, strong_dirichlet=False):
+    def __init__(self, coords, elems, order, eps=1.0, b=(0.0, 0.0, 0.0), c=0.0, gamma=0.0, data=0, strong_dirichlet=False,
+                 user_source=None, constants=()):
         coords = np.ascontiguousarray(coords, dtype=np.float64)
         elems = np.ascontiguousarray(elems, dtype=np.int64)
         self.dim = coords.shape[1]
@@ -385,6 +387,11 @@ class UnstructuredOperator:
         self.size = lib().fo_unstructured_size(self._h)
         self.local_size = lib().fo_unstructured_local_size(self._h)
         self.elements = elems.shape[0]
+        if user_source is not None:          # the interior() of a run-time compiled integrands source, compiled for the host
+            self._user = _compile_user(UserOperator._PRELUDE + user_source + UserOperator._EPILOGUE, [])
+            cc = np.zeros(32)
+            cc[:len(constants)] = constants
+            lib().fo_unstructured_set_user(self._h, C.cast(self._user.u_interior, C.c_void_p), cc, 32)
 
     def dofmap(self, e):
         out = np.empty(self.local_size, dtype=np.int64)

@@ -119,3 +119,23 @@ def test_unstructured_mesh_errors():
         fem.unstructuredGrid(coords, bad)
     with pytest.raises(_capi.B200FemError):
         fem.unstructuredGrid(coords, elems + 100)
+
+
+@pytest.mark.parametrize("dim,n,order", [(2, [9, 6], 2), (3, [4, 4, 3], 1), (3, [4, 3, 3], 2)])
+def test_compiled_integrands_on_a_distorted_mesh(dim, n, order):
+    """run-time compiled interior() (variable coefficients, cubic reaction) on an unstructured mesh against the oracle integrating
+    the same source through the same multilinear geometry"""
+    import os
+    src = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "integrands", "adr_variable.cuh")).read()
+    lo, hi = [-1.0] * dim, [1.0, 0.5, 2.0][:dim]
+    coords, elems = distorted(n, lo, hi, seed=17 * dim + order)
+    const = [0.05, 1.0, -0.5, 0.25, 0.0, 0.3, 0.7]
+    space = fem.space.lagrange(fem.unstructuredGrid(coords, elems), order=order)
+    op = fem.operator.galerkinJit(space, src, const, skeleton=False, boundary=False)
+    u = np.random.default_rng(9).uniform(-1, 1, space.size)
+    w = np.empty(space.size)
+    op(u, w)
+    oop = ol.UnstructuredOperator(coords, elems, order, user_source=src, constants=const)
+    assert rel(w, oop.apply(u)) < TOL
+    op.applyLinear(u, w)
+    assert rel(w, oop.apply(u) - oop.apply(np.zeros(space.size))) < 1e-11

@@ -125,3 +125,11 @@ def test_reference_vector_operator_check_holds_on_the_oracle():
     a, d = op.apply(ubar), linop.apply(ubar)
     assert np.abs(a).max() > 1e-3
     assert np.abs(a - d).max() < 1e-15 + 1e-13 * np.abs(a).max()
+
+
+def test_scalar_integrands_compile_into_the_unstructured_kernel():
+    log = C.create_string_buffer(1 << 16)
+    for dim in (2, 3):
+        for order in (1, 2):
+            rc = _capi.lib().b200fem_jit_compile_check_unstructured(SOURCE.encode(), dim, order, log, len(log))
+            assert rc == 0, log.value.decode()
