@@ -125,7 +125,9 @@ namespace Dune
             check( b200fem_nccl_init( ctx, id, rank, world ) );
           }
           check( b200fem_mesh_cartesian_distributed( ctx, GridType::dimension, cells, lower, upper, proc, rank, &mesh ) );
-          check( b200fem_space_create( mesh, B200SpaceKind< Space >::value, space.order(), B200FEM_NUMBERING_YASP, &this->space ) );
+          // localBlockSize = dimRange of the space (space/common/discretefunctionspace.hh): vector-valued spaces keep the scalar
+          // block mapper, dof (block, c) = block * dimRange + c (function/blockvectors/defaultblockvectors.hh:284-294)
+          check( b200fem_space_create_vector( mesh, B200SpaceKind< Space >::value, space.order(), B200FEM_NUMBERING_YASP, int( Space::localBlockSize ), &this->space ) );
           std::int64_t size = 0;
           check( b200fem_space_size( this->space, &size ) );
           if( std::size_t( size ) != std::size_t( space.size() ) * Space::localBlockSize )
