@@ -32,11 +32,11 @@ int apply_local(b200fem_operator* op, const double* u, double* w, bool linear) {
     }
     // linear models: Kronecker form (one launch, every node written once); otherwise the generic quadrature kernel with
     // colour-ordered scatter
-    const bool lag_kron_ok = op->model.gamma == 0.0;
+    const bool lag_kron_ok = op->model.gamma == 0.0 && s->order <= 2;      // (the lattice kernels carry the two row types of orders 1, 2)
     int lk = op->kernel_pref;
     if (lk == B200FEM_KERNEL_AUTO) lk = lag_kron_ok ? B200FEM_KERNEL_KRONECKER : B200FEM_KERNEL_QUADRATURE;
     if (lk == B200FEM_KERNEL_KRONECKER || lk == B200FEM_KERNEL_KRONECKER_TILE) {
-      REQUIRE(lag_kron_ok, B200FEM_ERR_INVALID, "Kronecker kernel needs a linear model");
+      REQUIRE(lag_kron_ok, B200FEM_ERR_INVALID, "Kronecker kernel needs a linear model and a Lagrange space of order 1 or 2");
       const double* bvec = nullptr;
       if (!linear && op->model.data) { int rc = ensure_bvec(op); if (rc) return rc; bvec = op->d_bvec; }
       int rc = launch_lagrange_kronecker(op, u, w, bvec); if (rc) return rc;

@@ -197,7 +197,8 @@ extern "C" int b200fem_space_create(b200fem_mesh* mesh, int kind, int order, int
       *out = s.release(); return B200FEM_OK;
     }
     if (kind == B200FEM_LAGRANGE) {
-      REQUIRE(order == 1 || order == 2, B200FEM_ERR_NOT_IMPLEMENTED, "Lagrange spaces: order 1 and 2 only");
+      REQUIRE(order >= 1 && order <= 3, B200FEM_ERR_NOT_IMPLEMENTED, "Lagrange spaces: orders 1 to 3");
+      REQUIRE(order <= 2 || (mesh->ctx->world == 1 && numbering == B200FEM_NUMBERING_YASP), B200FEM_ERR_NOT_IMPLEMENTED, "Lagrange order 3: one rank, YaspGrid numbering");
       REQUIRE(mesh->box.periodic == 0, B200FEM_ERR_NOT_IMPLEMENTED, "Lagrange spaces on periodic grids (dof identification across the boundary)");
       BoxDev& b = s->box;      // continuous spaces need no ghost elements: the local box is the owned box
       for (int d = 0; d < 3; ++d) { b.origin[d] = mesh->olo[d]; b.n[d] = mesh->ohi[d] - mesh->olo[d]; b.own_lo[d] = 0; b.own_hi[d] = b.n[d]; }
@@ -209,6 +210,7 @@ extern "C" int b200fem_space_create(b200fem_mesh* mesh, int kind, int order, int
         if (__builtin_popcount(sft) != pc || (order == 1 && sft != 0)) continue;
         L.group_offset[sft] = off; long long c = 1;
         for (int d = 0; d < 3; ++d) { L.group_dims[sft][d] = d < dim ? b.n[d] + (((sft >> d) & 1) ? 0 : 1) : 1; c *= L.group_dims[sft][d]; }
+        for (int d = 0; d < dim; ++d) if ((sft >> d) & 1) c *= order - 1;          // (order - 1)^p nodes inside an entity of dimension p
         off += c;
       }
       s->size = off; s->elements = (long long)b.n[0] * b.n[1] * b.n[2];

@@ -258,7 +258,7 @@ static int launch_jit(b200fem_operator* op, const double* u, double* w, const do
   if (op->sp->kind == B200FEM_LAGRANGE) {
     REQUIRE(default_quadrature(op), B200FEM_ERR_NOT_IMPLEMENTED, "Lagrange spaces: only quadrature orders that select the (order+1)-point Gauss rule");
     REQUIRE(!op->jit->skel, B200FEM_ERR_NOT_IMPLEMENTED, "skeleton integrands on continuous spaces");
-    int rc = N == 2 ? launch_jit_lagrange_t<2>(op, u, w) : launch_jit_lagrange_t<3>(op, u, w); if (rc) return rc;
+    int rc = N == 2 ? launch_jit_lagrange_t<2>(op, u, w) : N == 3 ? launch_jit_lagrange_t<3>(op, u, w) : launch_jit_lagrange_t<4>(op, u, w); if (rc) return rc;
     if (sub) { rc = b200fem_axpy_dev(op, -1.0, sub, w); if (rc) return rc; op->timing.launches_per_apply += 1; }   // L[u] - L[0]
     return B200FEM_OK;
   }
@@ -315,7 +315,7 @@ extern "C" int b200fem_jit_compile_check(const char* source, int order, char* lo
  * kernel; DG spaces of either dimension share one) and dimRange */
 extern "C" int b200fem_jit_compile_check_space(const char* source, int kind, int dim, int order, int dim_range, int has_skeleton, int has_boundary, char* log, int log_len) {
   REQUIRE(source && order >= 1 && order <= 5 && dim_range >= 1 && dim_range <= 4 && (dim == 2 || dim == 3), B200FEM_ERR_INVALID, "jit_compile_check_space: bad argument");
-  REQUIRE(kind != B200FEM_LAGRANGE || order <= 2, B200FEM_ERR_NOT_IMPLEMENTED, "Lagrange spaces: order 1 and 2 only");
+  REQUIRE(kind != B200FEM_LAGRANGE || order <= 3, B200FEM_ERR_NOT_IMPLEMENTED, "Lagrange spaces: orders 1 to 3");
   std::string lg; const int n = order + 1;
   const int variant = kind != B200FEM_LAGRANGE ? kJitDg : dim == 3 ? kJitLagrange3d : kJitLagrange2d;
   const int rc = compile(source, has_skeleton != 0, has_boundary != 0, n, n, n, dim_range, variant, nullptr, nullptr, &lg);

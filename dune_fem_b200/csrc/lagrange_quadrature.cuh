@@ -27,7 +27,7 @@ struct DgTabDev {
 };
 
 struct LagrangeLayoutDev {
-  int order;                        // 1 or 2
+  int order;                        // 1, 2 or 3
   long long group_offset[8];        // per "shift" bit set (directions the sub-entity extends in)
   long long group_dims[8][3];
   long long lattice[3];             // lattice extents k*n+1
@@ -38,6 +38,19 @@ __host__ __device__ inline long long lagrange_dof(const LagrangeLayoutDev& L, co
   if (L.lattice_map) return L.lattice_map[g0 + L.lattice[0] * (g1 + L.lattice[1] * g2)];
   int s = 0; long long c0 = g0, c1 = g1, c2 = g2;
   if (L.order == 2) { s = (int)(g0 & 1) | ((int)(g1 & 1) << 1) | ((int)(g2 & 1) << 2); c0 >>= 1; c1 >>= 1; c2 >>= 1; }
+  if (L.order >= 3) {
+    // k - 1 nodes inside an edge, (k-1)^2 inside a face, (k-1)^3 inside a cell: block = offset[type] + numDofs(entity) * entity index
+    // + j (space/mapper/indexsetdofmapper.hh:414-427), j = the node's position inside its entity, lower axes fastest (the local
+    // numbering of the Lagrange points, genericlagrangepoints.hh:862-876; Cartesian grids: no twists, lagrange/space.hh:68-71)
+    const int k = L.order; const int r0 = (int)(g0 % k), r1 = (int)(g1 % k), r2 = (int)(g2 % k);
+    c0 = g0 / k; c1 = g1 / k; c2 = g2 / k;
+    s = (r0 != 0 ? 1 : 0) | (r1 != 0 ? 2 : 0) | (r2 != 0 ? 4 : 0);
+    int j = 0, nd = 1;
+    if (r0) { j += nd * (r0 - 1); nd *= k - 1; }
+    if (r1) { j += nd * (r1 - 1); nd *= k - 1; }
+    if (r2) { j += nd * (r2 - 1); nd *= k - 1; }
+    return L.group_offset[s] + nd * (c0 + L.group_dims[s][0] * (c1 + L.group_dims[s][1] * c2)) + j;
+  }
   return L.group_offset[s] + c0 + L.group_dims[s][0] * (c1 + L.group_dims[s][1] * c2);
 }
 

@@ -59,7 +59,7 @@ template <int N> static int launch_lagrange(b200fem_operator* op, const double* 
   return B200FEM_OK;
 }
 int launch_lagrange_quadrature(b200fem_operator* op, const double* u, double* w, bool with_data) {
-  return op->sp->n1 == 2 ? launch_lagrange<2>(op, u, w, with_data) : launch_lagrange<3>(op, u, w, with_data);
+  return op->sp->n1 == 2 ? launch_lagrange<2>(op, u, w, with_data) : op->sp->n1 == 3 ? launch_lagrange<3>(op, u, w, with_data) : launch_lagrange<4>(op, u, w, with_data);
 }
 
 static int ensure_lag_rows(b200fem_operator* op) {

@@ -159,7 +159,7 @@ extern "C" int b200fem_cg_solve_dev(b200fem_operator* op, const double* b, doubl
   // Launch-bound sizes on a 2-D Lagrange lattice (BASELINE config 1): a chunk of iterations is ONE cooperative launch with
   // grid-wide barriers instead of kernel boundaries (cg_coop2d.cuh).
   int coop_grid = 0;
-  const bool use_coop = single && !op->jac_mode && s->kind == B200FEM_LAGRANGE && !s->unst && s->box.dim == 2 && op->model.gamma == 0.0 && !op->model.has_skeleton &&
+  const bool use_coop = single && !op->jac_mode && s->kind == B200FEM_LAGRANGE && !s->unst && s->order <= 2 && s->box.dim == 2 && op->model.gamma == 0.0 && !op->model.has_skeleton &&
                         default_quadrature(op) && n <= (1 << 20) && (!op->model.strong_dirichlet || op->d_dmask) && op->kernel_pref != B200FEM_KERNEL_QUADRATURE;
   if (use_coop) { rc = coop_cg_chunk(op, x, 0, &coop_grid); if (rc) return rc; if (coop_grid > 0) use_graph = false; }
   if (use_graph && !(op->cg_graph && op->cg_graph_version == op->state_version && op->cg_graph_key[0] == (const void*)x && op->cg_graph_key[1] == (const void*)b && op->cg_graph_key[2] == (const void*)op->d_hist)) {

@@ -283,7 +283,7 @@ struct Space {
   }
   void setupDofs() {
     if (kind != LAGRANGE) { size = mesh.nelem * nb; return; }   // one block per element (codimensionmapper.hh:121-131)
-    assert(order == 1 || order == 2);
+    assert(order >= 1 && order <= 3 && (order <= 2 || numbering == NUMBERING_YASP));
     const int dim = mesh.dim;
     // YaspGrid-native numbering: per codimension, entities grouped by the set of directions the
     // entity extends in ("shift" bit set), groups in increasing bit-set value, lexicographic within.
@@ -295,6 +295,7 @@ struct Space {
         if (order == 1 && s != 0) { groupOffset[s] = -1; continue; }
         groupOffset[s] = off; int64_t cnt = 1;
         for (int d = 0; d < 3; ++d) { groupDims[s][d] = (d < dim) ? mesh.n[d] + (((s >> d) & 1) ? 0 : 1) : 1; cnt *= groupDims[s][d]; }
+        for (int d = 0; d < dim; ++d) if ((s >> d) & 1) cnt *= order - 1;      // (order-1)^p nodes inside an entity of dimension p
         off += cnt;
       }
     size = off;
@@ -303,6 +304,14 @@ struct Space {
   int64_t latticeDims(int d) const { return d < mesh.dim ? (int64_t)order*mesh.n[d] + 1 : 1; }
   int64_t yaspDof(const int64_t g[3]) const {
     int s = 0; int64_t c[3] = {0,0,0};
+    if (order >= 3) {
+      // several nodes inside an entity: block = offset[type] + numDofs(entity)*index(entity) + j (indexsetdofmapper.hh:414-427) with j
+      // the position of the node inside its entity, lower axes fastest -- the local numbering of the Lagrange points restricted to
+      // the entity (genericlagrangepoints.hh:862-876; Cartesian grids use DefaultLocalDofMapping: no twists, lagrange/space.hh:68-71)
+      int j = 0, nd = 1;
+      for (int d = 0; d < mesh.dim; ++d) { const int r = (int)(g[d] % order); c[d] = g[d] / order; if (r) { s |= 1 << d; j += nd*(r - 1); nd *= order - 1; } }
+      return groupOffset[s] + nd*(c[0] + groupDims[s][0]*(c[1] + groupDims[s][1]*c[2])) + j;
+    }
     if (order == 2) { for (int d = 0; d < mesh.dim; ++d) { s |= (int)(g[d] & 1) << d; c[d] = g[d] >> 1; } }
     else { for (int d = 0; d < mesh.dim; ++d) c[d] = g[d]; }
     return groupOffset[s] + c[0] + groupDims[s][0]*(c[1] + groupDims[s][1]*c[2]);
