@@ -133,7 +133,7 @@ void unstructured_mark_dirichlet(b200fem_operator* op);             // all nodes
 int unstructured_diagonal(b200fem_operator* op, std::vector<double>& diag, bool dirichlet_rows);
 int launch_lagrange_unstructured(b200fem_operator* op, const double* u, double* w, bool with_data);
 // what a launch of lagrange_unstructured_kernel needs (for the run-time compiled instantiations, jit.cu)
-struct UnstructuredLaunch { UnstructuredTabDev tab; const int* order; const int* dofs; const double* elem_x; const std::vector<int>* colour_begin; int eb, threads; size_t smem; };
+struct UnstructuredLaunch { UnstructuredTabDev tab; const int* order; const int* dofs; const double* elem_x; const std::vector<int>* colour_begin; int eb, threads, max_grid; size_t smem; };
 int unstructured_launch_info(const b200fem_space* s, UnstructuredLaunch* out);
 
 // ---- jit.cu ----

@@ -232,14 +232,14 @@ template <int N> static int launch_jit_lagrange_t(b200fem_operator* op, const do
 static int launch_jit_unstructured(b200fem_operator* op, const double* u, double* w) {
   b200fem_space* s = op->sp; cudaStream_t st = s->mesh->ctx->stream; const int dim = s->mesh->dim, N = s->n1;
   UnstructuredLaunch L; int rc = unstructured_launch_info(s, &L); if (rc) return rc;
-  JitKernel* K = nullptr; rc = jit_kernel(op, N, N, N, dim == 2 ? kJitUnstructured2d : kJitUnstructured3d, 0, &K); if (rc) return rc;
+  JitKernel* K = nullptr; rc = jit_kernel(op, N, N, N, dim == 2 ? kJitUnstructured2d : kJitUnstructured3d, L.smem, &K); if (rc) return rc;
   CUDA_OK(cudaMemsetAsync(w, 0, sizeof(double) * (size_t)s->size, st));
   BoxDev b; std::memset(&b, 0, sizeof(b)); b.dim = dim; JitIntegrandsBase I = jit_params(op, b);
   int launches = 1;
   for (size_t c = 0; c + 1 < L.colour_begin->size(); ++c) {
     int first = (*L.colour_begin)[c], count = (*L.colour_begin)[c + 1] - first; if (count <= 0) continue;
     void* args[] = {&L.tab, &I, &L.order, &L.dofs, &L.elem_x, &u, &w, &first, &count};
-    if (g_drv.LaunchKernel(K->fn, (unsigned)((count + L.eb - 1) / L.eb), 1, 1, (unsigned)L.threads, 1, 1, (unsigned)L.smem, (CUstream)st, args, nullptr) != CUDA_SUCCESS)
+    if (g_drv.LaunchKernel(K->fn, (unsigned)std::min((count + L.eb - 1) / L.eb, L.max_grid), 1, 1, (unsigned)L.threads, 1, 1, (unsigned)L.smem, (CUstream)st, args, nullptr) != CUDA_SUCCESS)
       return fail(B200FEM_ERR_CUDA, "cuLaunchKernel failed for the compiled integrands");
     ++launches;
   }

@@ -161,20 +161,20 @@ int unstructured_space_setup(b200fem_space* s) {
   CUDA_OK(cudaSetDevice(m->ctx->device));
   std::vector<double> ex((size_t)m->nelem * nv * 3, 0.0);
   for (long long e = 0; e < m->nelem; ++e) for (int v = 0; v < nv; ++v) for (int d = 0; d < dim; ++d) ex[((size_t)e * nv + v) * 3 + d] = m->ux[(size_t)m->uev[(size_t)e * nv + v] * dim + d];
-  // both orientations of the tabulation, then points and weights
+  // tabulation with the point as the fast index, then points and weights
   std::vector<double> flat; const size_t nn = (size_t)nq * nb;
-  flat.resize(nn * 8 + (size_t)nq * 4, 0.0);
-  double* Bq = flat.data(); double* Gq = Bq + nn; double* Bi = Gq + 3 * nn; double* Gi = Bi + nn; double* xq = Gi + 3 * nn; double* wq = xq + 3 * (size_t)nq;
+  flat.resize(nn * 4 + (size_t)nq * 4, 0.0);
+  double* Bq = flat.data(); double* Gq = Bq + nn; double* xq = Gq + 3 * nn; double* wq = xq + 3 * (size_t)nq;
   for (int q = 0; q < nq; ++q) for (int i = 0; i < nb; ++i) {
-    Bq[(size_t)i * nq + q] = U->tabB[(size_t)q * nb + i]; Bi[(size_t)q * nb + i] = U->tabB[(size_t)q * nb + i];
-    for (int d = 0; d < 3; ++d) { Gq[((size_t)d * nb + i) * nq + q] = U->tabG[((size_t)q * nb + i) * 3 + d]; Gi[((size_t)d * nq + q) * nb + i] = U->tabG[((size_t)q * nb + i) * 3 + d]; }
+    Bq[(size_t)i * nq + q] = U->tabB[(size_t)q * nb + i];
+    for (int d = 0; d < 3; ++d) Gq[((size_t)d * nb + i) * nq + q] = U->tabG[((size_t)q * nb + i) * 3 + d];
   }
   std::copy(U->xq.begin(), U->xq.end(), xq); std::copy(U->wq.begin(), U->wq.end(), wq);
   CUDA_OK(cudaMalloc(&U->d_dofs, sizeof(int) * U->dofs.size())); CUDA_OK(cudaMemcpy(U->d_dofs, U->dofs.data(), sizeof(int) * U->dofs.size(), cudaMemcpyHostToDevice));
   CUDA_OK(cudaMalloc(&U->d_order, sizeof(int) * U->order.size())); CUDA_OK(cudaMemcpy(U->d_order, U->order.data(), sizeof(int) * U->order.size(), cudaMemcpyHostToDevice));
   CUDA_OK(cudaMalloc(&U->d_elem_x, sizeof(double) * ex.size())); CUDA_OK(cudaMemcpy(U->d_elem_x, ex.data(), sizeof(double) * ex.size(), cudaMemcpyHostToDevice));
   CUDA_OK(cudaMalloc(&U->d_tab, sizeof(double) * flat.size())); CUDA_OK(cudaMemcpy(U->d_tab, flat.data(), sizeof(double) * flat.size(), cudaMemcpyHostToDevice));
-  U->tab.Bq = U->d_tab; U->tab.Gq = U->d_tab + nn; U->tab.Bi = U->d_tab + 4 * nn; U->tab.Gi = U->d_tab + 5 * nn; U->tab.xq = U->d_tab + 8 * nn; U->tab.wq = U->d_tab + 8 * nn + 3 * (size_t)nq;
+  U->tab.B = U->d_tab; U->tab.G = U->d_tab + nn; U->tab.xq = U->d_tab + 4 * nn; U->tab.wq = U->d_tab + 4 * nn + 3 * (size_t)nq;
   s->unst = U.release();
   return B200FEM_OK;
 }
@@ -227,15 +227,19 @@ int unstructured_diagonal(b200fem_operator* op, std::vector<double>& diag, bool 
   return B200FEM_OK;
 }
 
+constexpr int kUnstructuredCtasPerSm = 4;      // resident persistent CTAs per SM (shared memory: <= 34 KB each)
+
 template <int DIM, int NB> static int launch_unst(b200fem_operator* op, const double* u, double* w, bool with_data) {
   using Cfg = UnstructuredCfg<DIM, NB>; b200fem_space* s = op->sp; const UnstructuredSpace* U = s->unst; cudaStream_t st = s->mesh->ctx->stream;
   CUDA_OK(cudaMemsetAsync(w, 0, sizeof(double) * (size_t)s->size, st));                       // w.clear() (galerkin.hh:1463)
   AdrIntegrands I; I.m = op->model; I.dim = DIM; I.with_data = with_data;
   auto kern = lagrange_unstructured_kernel<DIM, NB, AdrIntegrands>;
+  int rc = ensure_smem_attr(s->mesh->ctx, (const void*)kern, Cfg::smem_bytes()); if (rc) return rc;
   int launches = 1;
   for (size_t c = 0; c + 1 < U->colour_begin.size(); ++c) {
     const int first = U->colour_begin[c], count = U->colour_begin[c + 1] - first; if (count <= 0) continue;
-    kern<<<(unsigned)((count + Cfg::EB - 1) / Cfg::EB), Cfg::kThreads, Cfg::smem_bytes(), st>>>(U->tab, I, U->d_order, U->d_dofs, U->d_elem_x, u, w, first, count);
+    const int nbatch = (count + Cfg::EB - 1) / Cfg::EB, grid = std::min(nbatch, kUnstructuredCtasPerSm * s->mesh->ctx->sms);     // persistent CTAs
+    kern<<<(unsigned)grid, Cfg::kThreads, Cfg::smem_bytes(), st>>>(U->tab, I, U->d_order, U->d_dofs, U->d_elem_x, u, w, first, count);
     ++launches;
   }
   CUDA_OK(cudaGetLastError());
@@ -245,7 +249,7 @@ template <int DIM, int NB> static int launch_unst(b200fem_operator* op, const do
 int unstructured_launch_info(const b200fem_space* s, UnstructuredLaunch* out) {
   const UnstructuredSpace* U = s->unst; const int dim = s->mesh->dim, k = s->order;
   out->tab = U->tab; out->order = U->d_order; out->dofs = U->d_dofs; out->elem_x = U->d_elem_x; out->colour_begin = &U->colour_begin;
-  auto set = [&](int eb, int threads, size_t smem) { out->eb = eb; out->threads = threads; out->smem = smem; };
+  auto set = [&](int eb, int threads, size_t smem) { out->eb = eb; out->threads = threads; out->smem = smem; out->max_grid = kUnstructuredCtasPerSm * s->mesh->ctx->sms; };
   if (dim == 2 && k == 1) set(UnstructuredCfg<2, 4>::EB, UnstructuredCfg<2, 4>::kThreads, UnstructuredCfg<2, 4>::smem_bytes());
   else if (dim == 2) set(UnstructuredCfg<2, 9>::EB, UnstructuredCfg<2, 9>::kThreads, UnstructuredCfg<2, 9>::smem_bytes());
   else if (k == 1) set(UnstructuredCfg<3, 8>::EB, UnstructuredCfg<3, 8>::kThreads, UnstructuredCfg<3, 8>::smem_bytes());
