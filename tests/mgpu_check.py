@@ -92,6 +92,21 @@ def check_dg_onb_and_compiled_integrands(ctx, rank, proc, n):
     fem.operator.galerkinJit(space, src, const)(np.ascontiguousarray(ug[gather]), wl)
     worst = max(worst, rel(wl, ol.UserOperator(osp, src, const).apply(ug)[gather]))
     assert worst < TOL, ("dgonb / compiled integrands", proc, worst)
+    # vector-valued DG space (dimRange 2): the Copy exchange moves element blocks of n_b * dimRange doubles
+    R = 2
+    srcv = open(os.path.join(ROOT, "tests", "integrands", "system_dg.cuh")).read()
+    constv = [0.05, 0.02, 0.7, 80.0]
+    space, osp = fem.space.dglegendre(grid, order=2, dimRange=R), ol.Space(n, lo, hi, ol.DG_LEGENDRE_HIER, 2)
+    ug = np.random.default_rng(23).uniform(-1, 1, osp.size * R)
+    gather = dg_gather(n, proc, rank, 27 * R)
+    assert gather.size == space.size
+    op = fem.operator.galerkinJit(space, srcv, constv)
+    wref = ol.VectorUserOperator(osp, R, srcv, constv).apply(ug)[gather]
+    for rep in range(2):
+        wl = np.full(space.size, np.nan)
+        op(np.ascontiguousarray(ug[gather]), wl)
+        worst = max(worst, rel(wl, wref))
+    assert worst < TOL, ("vector-valued DG space", proc, worst)
     return worst
 
 

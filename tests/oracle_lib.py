@@ -280,21 +280,9 @@ class UserOperator(Operator):
                  "#ifdef HAS_BOUNDARY\nvoid u_boundary(const double* x, int axis, int side, double ihbnd, const PointValue* u, PointRange* r, const double* c, int dim) { user::boundary(x, axis, side, ihbnd, *u, *r, c, dim); }\n#endif\n}\n")
 
     def __init__(self, space, source, constants=(), skeleton=True, boundary=True, threads=1):
-        import hashlib
-        import tempfile
         self.space = space
-        text = self._PRELUDE + source + self._EPILOGUE
-        tag = hashlib.sha1((text + str(skeleton) + str(boundary)).encode()).hexdigest()[:16]
-        d = os.path.join(tempfile.gettempdir(), "b200fem_oracle_user")
-        os.makedirs(d, exist_ok=True)
-        so = os.path.join(d, f"user_{tag}.so")
-        if not os.path.exists(so):
-            src = os.path.join(d, f"user_{tag}.cpp")
-            with open(src, "w") as f:
-                f.write(text)
-            flags = (["-DHAS_SKELETON"] if skeleton else []) + (["-DHAS_BOUNDARY"] if boundary else [])
-            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src] + flags)
-        self._user = C.CDLL(so)
+        flags = (["-DHAS_SKELETON"] if skeleton else []) + (["-DHAS_BOUNDARY"] if boundary else [])
+        self._user = _compile_user(self._PRELUDE + source + self._EPILOGUE, flags)
         fn = lambda name, on: C.cast(getattr(self._user, name), C.c_void_p) if on else None
         c = np.zeros(32)
         c[:len(constants)] = constants
@@ -312,11 +300,12 @@ def _compile_user(text, flags):
     os.makedirs(d, exist_ok=True)
     so = os.path.join(d, f"user_{tag}.so")
     if not os.path.exists(so):
-        src = os.path.join(d, f"user_{tag}.cpp")
+        src = os.path.join(d, f"user_{tag}.{os.getpid()}.cpp")
         with open(src, "w") as f:
             f.write(text)
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", so + ".tmp", src] + flags)
-        os.replace(so + ".tmp", so)
+        tmp = f"{so}.{os.getpid()}.tmp"            # (several ranks may compile the same text at once: private name, atomic rename)
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", tmp, src] + flags)
+        os.replace(tmp, so)
     return C.CDLL(so)
 
 
