@@ -10,4 +10,5 @@ B200FEM_Q3_SLAB=1 $NCU -k regex:dg_kronecker_slab -s 3 -c 1 -o gpurun_out/r02_sl
 $NCU -k regex:dg_kronecker_slab -s 3 -c 1 -o gpurun_out/r02_slab_q5 python profiles/time_configs.py c4 > gpurun_out/r02_slab_q5.log 2>&1
 $NCU -k regex:lagrange_lattice -s 3 -c 1 -o gpurun_out/r02_lattice python profiles/time_lagrange.py > gpurun_out/r02_lattice.log 2>&1
 $NCU -k regex:dg_quadrature -s 3 -c 1 -o gpurun_out/r02_quadrature python profiles/time_quadrature.py q2 > gpurun_out/r02_quadrature.log 2>&1
+$NCU -k regex:lagrange_unstructured -s 215 -c 1 -o gpurun_out/r02_unstructured python profiles/time_unstructured.py > gpurun_out/r02_unstructured.log 2>&1
 ls -la gpurun_out | grep r02_
