@@ -57,23 +57,60 @@ class CartesianGridPart {
   b200fem_mesh* h_ = nullptr;
 };
 
+// the same on this rank's box of a global grid split into proc[0] x proc[1] x proc[2] boxes (YaspGrid's torus; the context carries
+// the NCCL communicator, b200fem_nccl_init), optionally periodic (YaspGrid's periodic bitset: bit d = periodic along axis d)
+template <int dim>
+class DistributedCartesianGridPart {
+ public:
+  static constexpr int dimension = dim;
+  DistributedCartesianGridPart(Context& ctx, const std::array<int, dim>& cells, const std::array<double, dim>& lo, const std::array<double, dim>& hi,
+                               const std::array<int, dim>& proc, int rank, int periodic = 0) {
+    int32_t n[3] = {1, 1, 1}, p[3] = {1, 1, 1}; double l[3] = {0, 0, 0}, h[3] = {1, 1, 1};
+    for (int d = 0; d < dim; ++d) { n[d] = cells[d]; l[d] = lo[d]; h[d] = hi[d]; p[d] = proc[d]; }
+    check(b200fem_mesh_cartesian_distributed(ctx.handle(), dim, n, l, h, p, rank, &h_));
+    if (periodic) { const int rc = b200fem_mesh_set_periodic(h_, periodic); if (rc) { b200fem_mesh_destroy(h_); check(rc); } }
+  }
+  ~DistributedCartesianGridPart() { b200fem_mesh_destroy(h_); }
+  b200fem_mesh* handle() const { return h_; }
+ private:
+  b200fem_mesh* h_ = nullptr;
+};
+
+// AdaptiveLeafGridPart over an unstructured conforming cube grid (ALUGrid< dim, dim, cube, conforming >): vertex coordinates
+// [nv][dim] and element -> vertex numbers [ne][2^dim] in the cube reference element's order (GridFactory::insertVertex / insertElement)
+template <int dim>
+class UnstructuredGridPart {
+ public:
+  static constexpr int dimension = dim;
+  UnstructuredGridPart(Context& ctx, const std::vector<double>& vertices, const std::vector<std::int64_t>& cubes) {
+    if (vertices.size() % dim != 0 || cubes.size() % (1u << dim) != 0) throw InvalidStateException("UnstructuredGridPart: vertices [nv][dim], cubes [ne][2^dim]");
+    check(b200fem_mesh_unstructured(ctx.handle(), dim, (std::int64_t)(vertices.size() / dim), vertices.data(), (std::int64_t)(cubes.size() >> dim), cubes.data(), &h_));
+  }
+  ~UnstructuredGridPart() { b200fem_mesh_destroy(h_); }
+  b200fem_mesh* handle() const { return h_; }
+ private:
+  b200fem_mesh* h_ = nullptr;
+};
+
 // DiscreteFunctionSpace: LagrangeDiscreteFunctionSpace / LegendreDiscontinuousGalerkinSpace / Hierarchic...
 template <class GridPart>
 class DiscreteFunctionSpace {
  public:
   typedef GridPart GridPartType;
-  DiscreteFunctionSpace(const GridPart& gp, b200fem_space_kind kind, int order, b200fem_numbering numbering = B200FEM_NUMBERING_YASP)
-      : gridPart_(gp), order_(order) {
-    check(b200fem_space_create(gp.handle(), kind, order, numbering, &h_));
+  // dimRange > 1: FunctionSpace< ..., dimRange >, dof (block, c) = block * dimRange + c (localBlockSize = dimRange)
+  DiscreteFunctionSpace(const GridPart& gp, b200fem_space_kind kind, int order, b200fem_numbering numbering = B200FEM_NUMBERING_YASP, int dimRange = 1)
+      : gridPart_(gp), order_(order), dimRange_(dimRange) {
+    check(b200fem_space_create_vector(gp.handle(), kind, order, numbering, dimRange, &h_));
     int64_t s = 0; check(b200fem_space_size(h_, &s)); size_ = (std::size_t)s;
   }
   ~DiscreteFunctionSpace() { b200fem_space_destroy(h_); }
   std::size_t size() const { return size_; }
   int order() const { return order_; }
+  int localBlockSize() const { return dimRange_; }
   const GridPart& gridPart() const { return gridPart_; }
   b200fem_space* handle() const { return h_; }
  private:
-  const GridPart& gridPart_; int order_; b200fem_space* h_ = nullptr; std::size_t size_ = 0;
+  const GridPart& gridPart_; int order_, dimRange_; b200fem_space* h_ = nullptr; std::size_t size_ = 0;
 };
 
 // AdaptiveDiscreteFunction: host-owned dof vector in the reference layout (function/adaptivefunction/adaptivefunction.hh:45-203)
@@ -112,6 +149,12 @@ struct Integrands : b200fem_model {
   Integrands() : b200fem_model{} { eps = 1.0; }
 };
 
+// Integrands generated from a UFL form (python/dune/models/integrands/model.py:72-106): the bodies of interior / skeleton / boundary as
+// CUDA C++ source (interface: include/b200fem.h, b200fem_operator_create_jit) + the dune.ufl.Constant coefficients
+struct CompiledIntegrands {
+  std::string source; std::vector<double> constants; bool hasSkeleton = true, hasBoundary = true;
+};
+
 // Dune::Fem::GalerkinOperator< Integrands, DomainFunction, RangeFunction > (schemes/galerkin.hh:1383-1504), optionally
 // wrapped like DirichletWrapperOperator (schemes/dirichletwrapper.hh:29-165) when integrands.strong_dirichlet is set
 template <class DiscreteFunctionT>
@@ -123,12 +166,22 @@ class GalerkinOperator : public Operator<DiscreteFunctionT, DiscreteFunctionT> {
     if (&dSpace != &rSpace) throw NotImplemented("domain and range space must coincide");
     check(b200fem_operator_create(dSpace.handle(), &integrands_, &h_));
   }
+  // ... over run-time compiled integrands (one specialised kernel per form, like the reference's JIT-compiled operator)
+  GalerkinOperator(const DiscreteFunctionSpaceType& dSpace, const DiscreteFunctionSpaceType& rSpace, const CompiledIntegrands& integrands)
+      : space_(dSpace), integrands_(), compiled_(true) {
+    if (&dSpace != &rSpace) throw NotImplemented("domain and range space must coincide");
+    check(b200fem_operator_create_jit(dSpace.handle(), integrands.source.c_str(), integrands.constants.empty() ? nullptr : integrands.constants.data(),
+                                      (int)integrands.constants.size(), integrands.hasSkeleton, integrands.hasBoundary, &h_));
+  }
+  void setConstants(const std::vector<double>& c) { check(b200fem_operator_set_constants(h_, c.empty() ? nullptr : c.data(), (int)c.size())); }
   ~GalerkinOperator() override { b200fem_operator_destroy(h_); }
   void operator()(const DiscreteFunctionT& u, DiscreteFunctionT& w) const override { check(b200fem_operator_apply(h_, u.leakPointer(), w.leakPointer())); }
   // homogeneous linear part (what the Krylov solvers apply)
   void applyLinear(const DiscreteFunctionT& u, DiscreteFunctionT& w) const { check(b200fem_operator_apply_linear(h_, u.leakPointer(), w.leakPointer())); }
   void loadVector(DiscreteFunctionT& b) const { check(b200fem_operator_load_vector(h_, b.leakPointer())); }
-  bool nonlinear() const override { return integrands_.gamma != 0.0; }
+  bool nonlinear() const override { return compiled_ || integrands_.gamma != 0.0; }     // (compiled forms are not known to be linear)
+  // diag(A) of the homogeneous linear part, matrix-free (what DiagonalPreconditioner needs, solver/diagonalpreconditioner.hh)
+  void diagonal(DiscreteFunctionT& d) const { check(b200fem_operator_diagonal(h_, d.leakPointer())); }
   // AutomaticDifferenceOperator::jacobian: linearise at u; applyLinear and the Krylov solvers then act on J(u) (automaticdifferenceoperator.hh:108-166)
   void linearize(const DiscreteFunctionT& u, double eps = 0.0) { check(b200fem_operator_linearize(h_, u.leakPointer(), eps)); }
   void dropLinearization() { check(b200fem_operator_linearize(h_, nullptr, 0.0)); }
@@ -139,7 +192,7 @@ class GalerkinOperator : public Operator<DiscreteFunctionT, DiscreteFunctionT> {
   const Integrands& model() const { return integrands_; }
   b200fem_operator* handle() const { return h_; }
  private:
-  const DiscreteFunctionSpaceType& space_; Integrands integrands_; b200fem_operator* h_ = nullptr;
+  const DiscreteFunctionSpaceType& space_; Integrands integrands_; bool compiled_ = false; b200fem_operator* h_ = nullptr;
 };
 
 // Dune::Fem::MOLGalerkinOperator (schemes/molgalerkin.hh:37-209): same constructor and interface, applies the inverse local
@@ -185,6 +238,57 @@ class KrylovInverseOperator {
  private:
   SolverParameter parameter_; const OperatorType* op_ = nullptr; mutable int iterations_ = 0; mutable std::vector<double> residuals_;
 };
+// CG with "fem.solver.preconditioning.method: jacobi" (solver/linear/cg.hh:52-56, 72-107): B = diag(A)^-1 built matrix-free
+template <class DiscreteFunctionT>
+class JacobiCgInverseOperator {
+ public:
+  typedef GalerkinOperator<DiscreteFunctionT> OperatorType;
+  explicit JacobiCgInverseOperator(const SolverParameter& p = SolverParameter()) : parameter_(p) {}
+  void bind(const OperatorType& op) { op_ = &op; }
+  void unbind() { op_ = nullptr; }
+  void operator()(const DiscreteFunctionT& rhs, DiscreteFunctionT& x) const {
+    if (!op_) throw InvalidStateException("JacobiCgInverseOperator: no operator bound");
+    residuals_.assign((std::size_t)std::max(parameter_.maxIterations, 1), 0.0);
+    check(b200fem_pcg_solve(op_->handle(), rhs.leakPointer(), x.leakPointer(), parameter_.tolerance, parameter_.maxIterations, parameter_.errorMeasure,
+                            &iterations_, residuals_.data()));
+  }
+  int iterations() const { return iterations_; }
+  bool converged() const { return iterations_ >= 0; }
+ private:
+  SolverParameter parameter_; const OperatorType* op_ = nullptr; mutable int iterations_ = 0; mutable std::vector<double> residuals_;
+};
+
+// Dune::Fem::NewtonInverseOperator (solver/newtoninverseoperator.hh:423-803): bind( op ); operator()( u, w ) solves L[w] = u from the
+// initial guess in w.  Parameters fem.solver.nonlinear.* (NewtonParameter, :37-268)
+struct NewtonParameter {
+  double tolerance = 1e-6; int maxIterations = 0x7fffffff; bool simpleLineSearch = false;
+  int linearMethod = gmres; SolverParameter linear;
+};
+enum class NewtonFailure { Success = 0, InvalidResidual = 1, IterationsExceeded = 2, LinearIterationsExceeded = 3, LineSearchFailed = 4, TooManyIterations = 5, TooManyLinearIterations = 6, LinearSolverFailed = 7 };
+template <class DiscreteFunctionT>
+class NewtonInverseOperator {
+ public:
+  typedef GalerkinOperator<DiscreteFunctionT> OperatorType;
+  explicit NewtonInverseOperator(const NewtonParameter& p = NewtonParameter()) : parameter_(p) {}
+  void bind(const OperatorType& op) { op_ = &op; }
+  void unbind() { op_ = nullptr; }
+  void operator()(const DiscreteFunctionT& u, DiscreteFunctionT& w) const { solve(u.leakPointer(), w); }
+  void operator()(DiscreteFunctionT& w) const { solve(nullptr, w); }                     // L[w] = 0
+  int iterations() const { return iterations_; }
+  int linearIterations() const { return linearIterations_; }
+  double residual() const { return residual_; }
+  NewtonFailure failed() const { return static_cast<NewtonFailure>(failure_); }
+  bool converged() const { return failure_ == 0; }
+ private:
+  void solve(const double* u, DiscreteFunctionT& w) const {
+    if (!op_) throw InvalidStateException("NewtonInverseOperator: no operator bound");
+    check(b200fem_newton_solve(op_->handle(), u, w.leakPointer(), parameter_.tolerance, parameter_.maxIterations, parameter_.linearMethod, parameter_.linear.tolerance,
+                               parameter_.linear.maxIterations, parameter_.linear.errorMeasure, parameter_.linear.gmresRestart, parameter_.simpleLineSearch ? 1 : 0,
+                               &iterations_, &linearIterations_, &residual_, &failure_));
+  }
+  NewtonParameter parameter_; const OperatorType* op_ = nullptr; mutable int iterations_ = 0, linearIterations_ = 0, failure_ = 0; mutable double residual_ = 0;
+};
+
 template <class DiscreteFunctionT> using CgInverseOperator = KrylovInverseOperator<DiscreteFunctionT, cg>;                // krylovinverseoperators.hh:284
 template <class DiscreteFunctionT> using BicgstabInverseOperator = KrylovInverseOperator<DiscreteFunctionT, bicgstab>;    // :288
 template <class DiscreteFunctionT> using GmresInverseOperator = KrylovInverseOperator<DiscreteFunctionT, gmres>;          // :295

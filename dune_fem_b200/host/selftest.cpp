@@ -64,6 +64,53 @@ int main() {
     for (std::size_t i = 0; i < dg.size(); ++i) { dmax = std::fmax(dmax, std::fabs(xb.dofVector()[i] - xg.dofVector()[i])); xmax = std::fmax(xmax, std::fabs(xg.dofVector()[i])); }
     std::printf("BiCGStab: %d iterations, GMRES(50): %d iterations, max |x_bicgstab - x_gmres| / max|x| = %.3e\n", bicg.iterations(), gm.iterations(), dmax / xmax);
     if (!(bicg.converged() && gm.converged() && dmax <= 1e-6 * xmax)) return 1;
+
+    // (5) round 2: an unstructured cube mesh (the unit square as 4 x 4 distorted quadrilaterals), P2, Jacobi-CG against CG
+    {
+      const int n = 4; std::vector<double> vx; std::vector<std::int64_t> cubes;
+      for (int j = 0; j <= n; ++j) for (int i = 0; i <= n; ++i) { const double x = double(i) / n, y = double(j) / n; vx.push_back(x + 0.03 * std::sin(7.0 * y) * x * (1 - x)); vx.push_back(y + 0.03 * std::sin(5.0 * x) * y * (1 - y)); }
+      for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) { const std::int64_t v = i + (n + 1) * j; cubes.insert(cubes.end(), {v, v + 1, v + n + 1, v + n + 2}); }
+      typedef UnstructuredGridPart<2> UGridPart; typedef DiscreteFunctionSpace<UGridPart> USpace; typedef DiscreteFunction<USpace> UFunction;
+      UGridPart ugp(ctx, vx, cubes);
+      USpace usp(ugp, B200FEM_LAGRANGE, 2);
+      Integrands pu; pu.c = 0.5; pu.dirichlet_mask = 1; pu.data = 2; pu.strong_dirichlet = 1;
+      GalerkinOperator<UFunction> uop(usp, usp, pu);
+      UFunction ub("b", usp), x1("x1", usp), x2("x2", usp);
+      uop.loadVector(ub);
+      SolverParameter up; up.tolerance = 1e-12; up.maxIterations = 500;
+      CgInverseOperator<UFunction> ucg(up); ucg.bind(uop); ucg(ub, x1);
+      JacobiCgInverseOperator<UFunction> upcg(up); upcg.bind(uop); upcg(ub, x2);
+      double d = 0, m = 0; for (std::size_t i = 0; i < usp.size(); ++i) { d = std::fmax(d, std::fabs(x1.dofVector()[i] - x2.dofVector()[i])); m = std::fmax(m, std::fabs(x1.dofVector()[i])); }
+      std::printf("unstructured P2 (%zu dofs): CG %d, Jacobi-CG %d iterations, max |x_cg - x_pcg| / max|x| = %.3e\n", usp.size(), ucg.iterations(), upcg.iterations(), d / m);
+      if (!(ucg.converged() && upcg.converged() && d <= 1e-8 * m)) return 1;
+    }
+
+    // (6) round 2: a vector-valued space (dimRange 2) with run-time compiled integrands, solved by NewtonInverseOperator
+    {
+      SpaceType v2(gridPart, B200FEM_DG_LEGENDRE_HIER, 1, B200FEM_NUMBERING_YASP, 2);
+      if (v2.size() != 2 * 8 * 8 * 8 * 8 || v2.localBlockSize() != 2) return 1;
+      CompiledIntegrands ci; ci.hasSkeleton = true; ci.hasBoundary = true; ci.constants = {0.5, 40.0, 0.3};
+      ci.source =
+        "__device__ void interior(const double* x, const VectorValue& u, VectorRange& r, const double* c, int dim) {\n"
+        "  for (int i = 0; i < dimRange; ++i) { const int j = (i + 1) % dimRange; r.s[i] = u.u[i] + c[2] * u.u[i] * u.u[j] - (1.0 + i + x[0]);\n"
+        "    for (int d = 0; d < dim; ++d) r.F[i][d] = c[0] * u.du[i][d]; } }\n"
+        "__device__ void skeleton(const double* x, int axis, double sign, double ihe, const VectorValue& in, const VectorValue& out, VectorRange& rin, VectorRange& rout, const double* c, int dim) {\n"
+        "  for (int i = 0; i < dimRange; ++i) { const double jump = in.u[i] - out.u[i];\n"
+        "    const double cj = c[0] * c[1] * ihe * jump - 0.5 * c[0] * (in.du[i][axis] + out.du[i][axis]) * sign;\n"
+        "    rin.s[i] = cj; rout.s[i] = -cj; rin.F[i][axis] = rout.F[i][axis] = -0.5 * c[0] * jump * sign; } }\n"
+        "__device__ void boundary(const double* x, int axis, int side, double ihbnd, const VectorValue& u, VectorRange& r, const double* c, int dim) {\n"
+        "  const double sign = side ? 1.0 : -1.0;\n"
+        "  for (int i = 0; i < dimRange; ++i) { r.s[i] = c[0] * c[1] * ihbnd * u.u[i] - c[0] * u.du[i][axis] * sign; r.F[i][axis] = -c[0] * u.u[i] * sign; } }\n";
+      GalerkinOperator<DiscreteFunctionType> sys(v2, v2, ci);
+      DiscreteFunctionType wv("w", v2), res("res", v2);
+      NewtonParameter np; np.tolerance = 1e-7; np.linear.tolerance = 1e-7; np.linear.errorMeasure = B200FEM_TOL_RESIDUAL_REDUCTION; np.linear.maxIterations = 4000; np.linear.gmresRestart = 30;
+      NewtonInverseOperator<DiscreteFunctionType> newton(np); newton.bind(sys);
+      newton(wv);
+      sys(wv, res);
+      double rn = 0; for (double v : res.dofVector()) rn += v * v;
+      std::printf("vector-valued DG (dimRange 2), compiled integrands: Newton %d iterations (%d linear), |L[w]| = %.3e\n", newton.iterations(), newton.linearIterations(), std::sqrt(rn));
+      if (!(newton.converged() && std::sqrt(rn) < 2e-7)) return 1;
+    }
     std::printf("host selftest OK\n");
     return 0;
   } catch (const InvalidStateException& e) {

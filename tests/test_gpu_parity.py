@@ -267,7 +267,7 @@ def test_error_conventions():
         op(np.zeros(space.size), np.zeros(space.size))
     assert ei.value.code == _capi.ERR_NOT_IMPLEMENTED
     with pytest.raises(_capi.B200FemError):
-        fem.space.lagrange(fem.structuredGrid([0, 0], [1, 1], [2, 2]), order=3)
+        fem.space.lagrange(fem.structuredGrid([0, 0], [1, 1], [2, 2]), order=4)
     inv = fem.solver.CgInverseOperator()
     with pytest.raises(RuntimeError):
         inv(np.zeros(3), np.zeros(3))
