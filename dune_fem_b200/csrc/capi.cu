@@ -198,7 +198,7 @@ extern "C" int b200fem_space_create(b200fem_mesh* mesh, int kind, int order, int
     }
     if (kind == B200FEM_LAGRANGE) {
       REQUIRE(order >= 1 && order <= 3, B200FEM_ERR_NOT_IMPLEMENTED, "Lagrange spaces: orders 1 to 3");
-      REQUIRE(order <= 2 || (mesh->ctx->world == 1 && numbering == B200FEM_NUMBERING_YASP), B200FEM_ERR_NOT_IMPLEMENTED, "Lagrange order 3: one rank, YaspGrid numbering");
+      REQUIRE(order <= 2 || numbering == B200FEM_NUMBERING_YASP, B200FEM_ERR_NOT_IMPLEMENTED, "Lagrange order 3: YaspGrid numbering");
       REQUIRE(mesh->box.periodic == 0, B200FEM_ERR_NOT_IMPLEMENTED, "Lagrange spaces on periodic grids (dof identification across the boundary)");
       BoxDev& b = s->box;      // continuous spaces need no ghost elements: the local box is the owned box
       for (int d = 0; d < 3; ++d) { b.origin[d] = mesh->olo[d]; b.n[d] = mesh->ohi[d] - mesh->olo[d]; b.own_lo[d] = 0; b.own_hi[d] = b.n[d]; }

@@ -130,7 +130,7 @@ int b200fem_mesh_local_box(b200fem_mesh* mesh, int overlap, int32_t* out12);
 int b200fem_march_schedule(const int32_t* on, int grid, int flags, int32_t* runs_out, int32_t cap, int32_t* begin_out, int32_t* nruns_out);
 
 /* DiscreteFunctionSpace (space/lagrange/space.hh:129-353, space/discontinuousgalerkin/legendre.hh).  Lagrange: orders 1..3 on
- * Cartesian meshes (order 3: one rank, YaspGrid numbering, quadrature kernels; several nodes inside an edge / face / cell are
+ * Cartesian meshes (order 3: YaspGrid numbering, quadrature kernels; several nodes inside an edge / face / cell are
  * numbered entity by entity, lower axes fastest, space/lagrange/genericlagrangepoints.hh:862-876), orders 1..2 on unstructured
  * meshes; DG: Legendre orders 1..5, dgonb orders 1..4 on Cartesian meshes. */
 int b200fem_space_create(b200fem_mesh* mesh, int kind, int order, int numbering, b200fem_space** out);

@@ -267,6 +267,9 @@ def main():
         worst = max(worst, w)
         w, _ = check_lagrange(ctx, rank, proc, [8, 6, 8], 1)
         worst = max(worst, w)
+        if proc is procs[0]:
+            w, _ = check_lagrange(ctx, rank, proc, [4, 4, 6], 3, cg_iters=12)    # order 3: quadrature kernels + Add exchange on a 3 n + 1 lattice
+            worst = max(worst, w)
         if proc[2] == 1:
             w, _ = check_lagrange(ctx, rank, proc, [12, 10], 1)          # 2-D lattice
             worst = max(worst, w)
