@@ -21,7 +21,7 @@ SYMBOLS = [
     "b200fem_operator_set_quadrature_orders", "b200fem_operator_set_kernel", "b200fem_operator_set_host_pipeline", "b200fem_operator_set_inverse_mass", "b200fem_operator_linearize", "b200fem_operator_linearize_dev", "b200fem_operator_dirichlet",
     "b200fem_operator_timing", "b200fem_cg_solve", "b200fem_cg_solve_dev", "b200fem_bicgstab_solve", "b200fem_bicgstab_solve_dev", "b200fem_gmres_solve", "b200fem_gmres_solve_dev", "b200fem_operator_diagonal", "b200fem_pcg_solve", "b200fem_pcg_solve_dev", "b200fem_dot_dev", "b200fem_axpy_dev",
     "b200fem_ctx_set_nccl", "b200fem_nccl_unique_id", "b200fem_nccl_init", "b200fem_ctx_transport", "b200fem_communicate_dev",
-    "b200fem_operator_create_jit", "b200fem_operator_set_constants", "b200fem_jit_compile_check", "b200fem_device_count", "b200fem_mesh_set_periodic", "b200fem_newton_solve", "b200fem_newton_solve_dev", "b200fem_space_create_vector", "b200fem_space_dim_range", "b200fem_jit_compile_check_space", "b200fem_mesh_unstructured", "b200fem_jit_compile_check_unstructured",
+    "b200fem_operator_create_jit", "b200fem_operator_set_constants", "b200fem_jit_compile_check", "b200fem_device_count", "b200fem_mesh_set_periodic", "b200fem_newton_solve", "b200fem_newton_solve_dev", "b200fem_space_create_vector", "b200fem_space_dim_range", "b200fem_jit_compile_check_space", "b200fem_mesh_unstructured", "b200fem_jit_compile_check_unstructured", "b200fem_unstructured_numbering",
 ]
 
 OK, ERR_INVALID, ERR_NOT_IMPLEMENTED, ERR_CUDA, ERR_COMM = 0, -1, -2, -3, -4
@@ -73,6 +73,7 @@ def lib():
         "b200fem_partition_box": [C.c_int, P(i32), P(i32), C.c_int, C.c_int, P(i32)],
         "b200fem_mesh_local_box": [vp, C.c_int, P(i32)],
         "b200fem_mesh_unstructured": [vp, C.c_int, i64, vp, i64, vp, P(vp)],
+        "b200fem_unstructured_numbering": [C.c_int, i64, vp, i64, vp, C.c_int, P(i64), vp, vp, vp],
         "b200fem_jit_compile_check_unstructured": [C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_int],
         "b200fem_march_schedule": [P(i32), C.c_int, C.c_int, P(i32), i32, P(i32), P(i32)],
         "b200fem_space_create": [vp, C.c_int, C.c_int, C.c_int, P(vp)], "b200fem_space_destroy": [vp],

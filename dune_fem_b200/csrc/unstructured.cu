@@ -80,10 +80,11 @@ double invert3(const double J[3][3], double Ji[3][3]) {
 
 }  // namespace
 
-int unstructured_space_setup(b200fem_space* s) {
-  const b200fem_mesh* m = s->mesh; const int dim = m->dim, k = s->order, n1 = k + 1, nb = s->nb, nv = 1 << dim;
+// host-only part of the space setup: numbering, node positions, boundary marks, colouring (no CUDA; also behind
+// b200fem_unstructured_numbering for CPU tests)
+static int unstructured_number(const b200fem_mesh* m, int k, int nb, UnstructuredSpace* U, long long* size_out) {
+  const int dim = m->dim, n1 = k + 1, nv = 1 << dim;
   REQUIRE(m->nelem < (1ll << 31), B200FEM_ERR_NOT_IMPLEMENTED, "unstructured meshes: 32-bit element indices");
-  auto U = std::unique_ptr<UnstructuredSpace>(new UnstructuredSpace);
   std::vector<std::array<int, 3>> subs[4]; sub_entity_order(dim, subs);
   auto local_index = [&](const std::array<int, 3>& a) { int l = 0, st = 1; for (int d = 0; d < dim; ++d) { l += st * (k == 1 ? a[d] / 2 : a[d]); st *= n1; } return l; };
   // ---- first-touch numbering per entity dimension; faces are counted for the boundary detection
@@ -100,9 +101,9 @@ int unstructured_space_setup(b200fem_space* s) {
     }
   long long off[5] = {0, 0, 0, 0, 0};
   for (int p = 0; p <= dim; ++p) off[p + 1] = off[p] + (long long)index[p].size();
-  s->size = off[dim + 1]; s->elements = m->nelem;
-  REQUIRE(s->size < (1ll << 31), B200FEM_ERR_NOT_IMPLEMENTED, "unstructured meshes: 32-bit dof indices");
-  U->dofs.assign((size_t)m->nelem * nb, -1); U->node_x.assign((size_t)s->size * 3, 0.0); U->boundary.assign((size_t)s->size, 0);
+  const long long size = off[dim + 1]; *size_out = size;
+  REQUIRE(size < (1ll << 31), B200FEM_ERR_NOT_IMPLEMENTED, "unstructured meshes: 32-bit dof indices");
+  U->dofs.assign((size_t)m->nelem * nb, -1); U->node_x.assign((size_t)size * 3, 0.0); U->boundary.assign((size_t)size, 0);
   for (long long e = 0; e < m->nelem; ++e)
     for (int pd = 0; pd <= dim; ++pd) {
       if (k == 1 && pd != 0) continue;
@@ -139,6 +140,14 @@ int unstructured_space_setup(b200fem_space* s) {
     U->order.resize((size_t)m->nelem); std::vector<int> fill(U->colour_begin.begin(), U->colour_begin.end() - 1);
     for (long long e = 0; e < m->nelem; ++e) U->order[(size_t)fill[(size_t)colour[(size_t)e]]++] = (int)e;      // element order kept inside a colour
   }
+  return B200FEM_OK;
+}
+
+int unstructured_space_setup(b200fem_space* s) {
+  const b200fem_mesh* m = s->mesh; const int dim = m->dim, k = s->order, n1 = k + 1, nb = s->nb, nv = 1 << dim;
+  auto U = std::unique_ptr<UnstructuredSpace>(new UnstructuredSpace);
+  int rc = unstructured_number(m, k, nb, U.get(), &s->size); if (rc) return rc;
+  s->elements = m->nelem;
   // ---- tabulation of the tensor basis at the tensor Gauss rule (x0 fastest, quadrature/femquadratures_inline.hh:33-95)
   const Tab1D& t = s->tab; const int nq = nb;
   U->tabB.assign((size_t)nq * nb, 0.0); U->tabG.assign((size_t)nq * nb * 3, 0.0); U->xq.assign((size_t)nq * 3, 0.0); U->wq.assign((size_t)nq, 0.0);
@@ -285,4 +294,23 @@ extern "C" int b200fem_mesh_unstructured(b200fem_ctx* ctx, int dim, int64_t n_ve
   }
   ctx->refs += 1;
   *out = m; return B200FEM_OK;
+}
+
+/* host-only: dof numbering and element colouring of a Lagrange space on an unstructured cube mesh, as b200fem_space_create would
+ * build them (no device needed: testable on a CPU-only box).  dofs_out[n_elements][(order+1)^dim], colour_out[n_elements]
+ * (colour of every element: elements of a colour share no dof), boundary_out[size] may be NULL; *size_out = number of dofs. */
+extern "C" int b200fem_unstructured_numbering(int dim, int64_t n_vertices, const double* coords, int64_t n_elements, const int64_t* elem_vertices, int order,
+                                              int64_t* size_out, int32_t* dofs_out, int32_t* colour_out, uint8_t* boundary_out) {
+  REQUIRE(coords && elem_vertices && size_out && (dim == 2 || dim == 3) && (order == 1 || order == 2) && n_vertices > 0 && n_elements > 0, B200FEM_ERR_INVALID, "unstructured_numbering: bad argument");
+  const int nv = 1 << dim; int nb = 1; for (int d = 0; d < dim; ++d) nb *= order + 1;
+  for (int64_t i = 0; i < n_elements * nv; ++i) REQUIRE(elem_vertices[i] >= 0 && elem_vertices[i] < n_vertices, B200FEM_ERR_INVALID, "unstructured_numbering: vertex index out of range");
+  b200fem_mesh m; m.ctx = nullptr; m.dim = dim; m.unstructured = true; m.nvert = n_vertices; m.nelem = n_elements;
+  m.ux.assign(coords, coords + n_vertices * dim); m.uev.assign(elem_vertices, elem_vertices + n_elements * nv);
+  UnstructuredSpace U; long long size = 0;
+  int rc = unstructured_number(&m, order, nb, &U, &size); if (rc) return rc;
+  *size_out = size;
+  if (dofs_out) std::copy(U.dofs.begin(), U.dofs.end(), dofs_out);
+  if (boundary_out) std::copy(U.boundary.begin(), U.boundary.end(), boundary_out);
+  if (colour_out) for (size_t c = 0; c + 1 < U.colour_begin.size(); ++c) for (int i = U.colour_begin[c]; i < U.colour_begin[c + 1]; ++i) colour_out[U.order[(size_t)i]] = (int32_t)c;
+  return B200FEM_OK;
 }

@@ -108,6 +108,11 @@ int b200fem_mesh_cartesian(b200fem_ctx* ctx, int dim, const int32_t* n, const do
  * and Newton work as on Cartesian meshes. */
 int b200fem_mesh_unstructured(b200fem_ctx* ctx, int dim, int64_t n_vertices, const double* coords, int64_t n_elements,
                               const int64_t* elem_vertices, b200fem_mesh** out);
+/* host-only (no device): the dof numbering (dofs_out[n_elements][(order+1)^dim]), the element colouring of the colour-ordered scatter
+ * (colour_out[n_elements]: elements of one colour share no dof) and the boundary marks (boundary_out[*size_out]) such a space gets;
+ * any of the three outputs may be NULL. */
+int b200fem_unstructured_numbering(int dim, int64_t n_vertices, const double* coords, int64_t n_elements, const int64_t* elem_vertices,
+                                   int order, int64_t* size_out, int32_t* dofs_out, int32_t* colour_out, uint8_t* boundary_out);
 int b200fem_mesh_cartesian_distributed(b200fem_ctx* ctx, int dim, const int32_t* n_global, const double* lo, const double* hi,
                                        const int32_t* proc, int rank, b200fem_mesh** out);
 /* Periodic grid (YaspGrid's `periodic` bitset): bit d set = the faces on the two sides of axis d are interior faces whose

@@ -72,3 +72,32 @@ def test_patch_test_and_renumbering_invariance_on_distorted_meshes(dim, n, order
     perm = np.array([pos[k] for k in key(x2)])                           # dof i of op2 is dof perm[i] of op
     v = rng.uniform(-1, 1, op.size)
     assert np.abs(op2.apply(v[perm]) - op.apply(v)[perm]).max() < 1e-12 * np.abs(op.apply(v)).max()
+
+
+@pytest.mark.parametrize("dim,n", [(2, [7, 5]), (3, [4, 3, 3])])
+@pytest.mark.parametrize("order", [1, 2])
+def test_library_numbering_and_colouring_without_a_device(dim, n, order):
+    """host logic of the product (b200fem_unstructured_numbering, no GPU): the dof map equals the oracle's bit for bit on a distorted,
+    shuffled mesh; the boundary marks agree; the colouring is valid (no dof shared inside a colour) and uses few colours"""
+    import ctypes as C
+    from dune_fem_b200 import _capi
+    lo, hi = [-1.0] * dim, [1.0, 0.5, 2.0][:dim]
+    coords, elems = distorted(n, lo, hi, seed=5 * dim + order)
+    coords, elems = np.ascontiguousarray(coords), np.ascontiguousarray(elems, dtype=np.int64)
+    oop = ol.UnstructuredOperator(coords, elems, order)
+    nb = (order + 1) ** dim
+    size = C.c_int64()
+    dofs = np.empty((len(elems), nb), dtype=np.int32)
+    colour = np.empty(len(elems), dtype=np.int32)
+    bnd = np.empty(oop.size, dtype=np.uint8)
+    rc = _capi.lib().b200fem_unstructured_numbering(dim, len(coords), _capi.ptr(coords), len(elems), _capi.ptr(elems, np.int64), order, C.byref(size),
+                                                   _capi.ptr(dofs, np.int32), _capi.ptr(colour, np.int32), _capi.ptr(bnd, np.uint8))
+    assert rc == 0 and size.value == oop.size
+    for e in range(len(elems)):
+        assert (dofs[e] == oop.dofmap(e)).all()
+    assert (bnd == oop.nodes()[1]).all()
+    ncol = colour.max() + 1
+    assert colour.min() == 0 and ncol <= 2 ** dim + 4               # a structured-like hexahedral mesh needs 2^dim colours; greedy stays close
+    for c in range(ncol):
+        d = dofs[colour == c].ravel()
+        assert len(np.unique(d)) == len(d)
