@@ -6,6 +6,6 @@ Everything computes on the GPU through the C ABI in include/b200fem.h; there is 
 """
 from . import _capi  # noqa: F401
 from .grid import structuredGrid, unstructuredGrid  # noqa: F401
-from . import space, operator, solver  # noqa: F401
+from . import space, operator, solver, scheme  # noqa: F401
 
-__all__ = ["structuredGrid", "unstructuredGrid", "space", "operator", "solver"]
+__all__ = ["structuredGrid", "unstructuredGrid", "space", "operator", "solver", "scheme"]

@@ -192,7 +192,7 @@ extern "C" int b200fem_space_create(b200fem_mesh* mesh, int kind, int order, int
       REQUIRE(order == 1 || order == 2, B200FEM_ERR_NOT_IMPLEMENTED, "Lagrange spaces: order 1 and 2 only");
       s->tab = tabulate_1d(Basis::Lagrange, order, gauss_points_for_order(2 * order));
       s->lay = LagrangeLayoutDev{}; s->lay.order = order;
-      int rc = unstructured_space_setup(s.get()); if (rc) return rc;
+      int rc = unstructured_space_setup(s.get()); if (rc) { unstructured_space_free(s.get()); return rc; }
       mesh->refs += 1;
       *out = s.release(); return B200FEM_OK;
     }

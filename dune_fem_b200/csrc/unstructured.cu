@@ -145,8 +145,8 @@ static int unstructured_number(const b200fem_mesh* m, int k, int nb, Unstructure
 
 int unstructured_space_setup(b200fem_space* s) {
   const b200fem_mesh* m = s->mesh; const int dim = m->dim, k = s->order, n1 = k + 1, nb = s->nb, nv = 1 << dim;
-  auto U = std::unique_ptr<UnstructuredSpace>(new UnstructuredSpace);
-  int rc = unstructured_number(m, k, nb, U.get(), &s->size); if (rc) return rc;
+  UnstructuredSpace* U = new UnstructuredSpace; s->unst = U;        // (owned by the space from here on: a failing caller frees it, device arrays included)
+  int rc = unstructured_number(m, k, nb, U, &s->size); if (rc) return rc;
   s->elements = m->nelem;
   // ---- tabulation of the tensor basis at the tensor Gauss rule (x0 fastest, quadrature/femquadratures_inline.hh:33-95)
   const Tab1D& t = s->tab; const int nq = nb;
@@ -184,7 +184,6 @@ int unstructured_space_setup(b200fem_space* s) {
   CUDA_OK(cudaMalloc(&U->d_elem_x, sizeof(double) * ex.size())); CUDA_OK(cudaMemcpy(U->d_elem_x, ex.data(), sizeof(double) * ex.size(), cudaMemcpyHostToDevice));
   CUDA_OK(cudaMalloc(&U->d_tab, sizeof(double) * flat.size())); CUDA_OK(cudaMemcpy(U->d_tab, flat.data(), sizeof(double) * flat.size(), cudaMemcpyHostToDevice));
   U->tab.B = U->d_tab; U->tab.G = U->d_tab + nn; U->tab.xq = U->d_tab + 4 * nn; U->tab.wq = U->d_tab + 4 * nn + 3 * (size_t)nq;
-  s->unst = U.release();
   return B200FEM_OK;
 }
 

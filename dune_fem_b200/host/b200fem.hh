@@ -10,6 +10,7 @@
 // the adapter a DUNE-FEM maintainer adds (dune/fem/schemes/b200galerkin.hh) -- it is the same code with DUNE's own
 // DiscreteFunction in place of the one below.
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <stdexcept>
@@ -287,6 +288,48 @@ class NewtonInverseOperator {
                                &iterations_, &linearIterations_, &residual_, &failure_));
   }
   NewtonParameter parameter_; const OperatorType* op_ = nullptr; mutable int iterations_ = 0, linearIterations_ = 0, failure_ = 0; mutable double residual_ = 0;
+};
+
+// Dune::Fem::FemScheme< Operator, InverseOperator > (schemes/femscheme.hh:60-260; Python dune.fem.scheme.galerkin): the Galerkin
+// operator with its inverse operator.  solve( rhs, solution ): solution = g (+ rhs) on the Dirichlet boundary, then invOp( rhs, solution )
+// (femscheme.hh:194-221, 248-254); returns the solver info (converged, nonlinear / linear iterations).
+struct SolverInfo { bool converged; int nonlinearIterations, linearIterations; };
+template <class DiscreteFunctionT>
+class FemScheme {
+ public:
+  typedef typename DiscreteFunctionT::DiscreteFunctionSpaceType DiscreteFunctionSpaceType;
+  typedef GalerkinOperator<DiscreteFunctionT> DifferentiableOperatorType;
+  template <class IntegrandsT>
+  FemScheme(const DiscreteFunctionSpaceType& space, const IntegrandsT& integrands, const NewtonParameter& parameter = NewtonParameter())
+      : space_(space), op_(space, space, integrands), parameter_(parameter), mask_(space.size(), 0), values_(space.size(), 0.0) {
+    if (b200fem_operator_dirichlet(op_.handle(), mask_.data(), values_.data()) != B200FEM_OK) mask_.assign(space.size(), 0);   // (no constraints)
+  }
+  void operator()(const DiscreteFunctionT& arg, DiscreteFunctionT& dest) const { op_(arg, dest); }
+  void setConstraints(DiscreteFunctionT& u) const { for (std::size_t i = 0; i < mask_.size(); ++i) if (mask_[i]) u.dofVector()[i] = values_[i]; }
+  SolverInfo solve(DiscreteFunctionT& solution) const { return solve(nullptr, solution); }
+  SolverInfo solve(const DiscreteFunctionT& rhs, DiscreteFunctionT& solution) const { return solve(&rhs, solution); }
+  const DiscreteFunctionSpaceType& space() const { return space_; }
+  const DifferentiableOperatorType& fullOperator() const { return op_; }
+ private:
+  SolverInfo solve(const DiscreteFunctionT* rhs, DiscreteFunctionT& solution) const {
+    setConstraints(solution);
+    if (rhs) for (std::size_t i = 0; i < mask_.size(); ++i) if (mask_[i]) solution.dofVector()[i] += rhs->dofVector()[i];
+    if (!op_.nonlinear()) {      // a linear operator: the one Newton step with the exact Jacobian, A x = b + rhs (newtoninverseoperator.hh:761, 791-792)
+      DiscreteFunctionT b("b", space_); op_.loadVector(b);
+      if (rhs) for (std::size_t i = 0; i < mask_.size(); ++i) b.dofVector()[i] = mask_[i] ? solution.dofVector()[i] : b.dofVector()[i] + rhs->dofVector()[i];
+      int it = 0; std::vector<double> hist((std::size_t)std::max(parameter_.linear.maxIterations, 1));
+      const SolverParameter& lp = parameter_.linear;
+      if (parameter_.linearMethod == gmres) check(b200fem_gmres_solve(op_.handle(), b.leakPointer(), solution.leakPointer(), lp.gmresRestart, lp.tolerance, lp.maxIterations, lp.errorMeasure, &it, hist.data()));
+      else check((parameter_.linearMethod == bicgstab ? b200fem_bicgstab_solve : b200fem_cg_solve)(op_.handle(), b.leakPointer(), solution.leakPointer(), lp.tolerance, lp.maxIterations, lp.errorMeasure, &it, hist.data()));
+      return SolverInfo{it >= 0, 1, it >= 0 ? it : -it};
+    }
+    NewtonInverseOperator<DiscreteFunctionT> invOp(parameter_);
+    invOp.bind(op_);
+    if (rhs) invOp(*rhs, solution); else invOp(solution);
+    return SolverInfo{invOp.converged(), invOp.iterations(), invOp.linearIterations()};
+  }
+  const DiscreteFunctionSpaceType& space_; DifferentiableOperatorType op_; NewtonParameter parameter_;
+  std::vector<std::uint8_t> mask_; std::vector<double> values_;
 };
 
 template <class DiscreteFunctionT> using CgInverseOperator = KrylovInverseOperator<DiscreteFunctionT, cg>;                // krylovinverseoperators.hh:284

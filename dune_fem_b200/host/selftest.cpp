@@ -111,6 +111,19 @@ int main() {
       std::printf("vector-valued DG (dimRange 2), compiled integrands: Newton %d iterations (%d linear), |L[w]| = %.3e\n", newton.iterations(), newton.linearIterations(), std::sqrt(rn));
       if (!(newton.converged() && std::sqrt(rn) < 2e-7)) return 1;
     }
+
+    // (7) FemScheme::solve: constraints on the target, then the inverse operator (linear model: one exact Newton step by CG)
+    {
+      NewtonParameter sp; sp.linearMethod = B200Fem::cg; sp.linear.tolerance = 1e-12; sp.linear.maxIterations = 1000;
+      FemScheme<DiscreteFunctionType> scheme(p2, poisson, sp);
+      DiscreteFunctionType uh("uh", p2), res("res", p2);
+      for (double& v : uh.dofVector()) v = 0.3;
+      const SolverInfo info = scheme.solve(uh);
+      scheme(uh, res);
+      double rn = 0; for (double v : res.dofVector()) rn = std::fmax(rn, std::fabs(v));
+      std::printf("FemScheme::solve: converged %d, %d linear iterations, max |L[uh]| = %.3e\n", (int)info.converged, info.linearIterations, rn);
+      if (!(info.converged && rn < 1e-9)) return 1;
+    }
     std::printf("host selftest OK\n");
     return 0;
   } catch (const InvalidStateException& e) {

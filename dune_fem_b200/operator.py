@@ -126,6 +126,10 @@ class JitGalerkinOperator(GalerkinOperator):
                                                           int(skeleton), int(boundary), C.byref(self.handle)))
         self._apply_dev = capi.lib().b200fem_operator_apply_dev
 
+    @property
+    def nonlinear(self):
+        return True                      # (a compiled form is not known to be linear: Operator::nonlinear() defaults to true)
+
     def setConstants(self, constants):
         c = np.ascontiguousarray(constants, dtype=np.float64)
         capi.check(capi.lib().b200fem_operator_set_constants(self.handle, capi.ptr(c) if len(c) else None, len(c)))
