@@ -171,7 +171,6 @@ static void build_adaptive_leaf_map(b200fem_space* s) {
 
 extern "C" int b200fem_space_create_vector(b200fem_mesh* mesh, int kind, int order, int numbering, int dim_range, b200fem_space** out) {
   REQUIRE(dim_range >= 1 && dim_range <= 4, B200FEM_ERR_NOT_IMPLEMENTED, "space_create_vector: dimRange 1..4");
-  REQUIRE(dim_range == 1 || (mesh && (mesh->ctx->world == 1 || kind != B200FEM_LAGRANGE)), B200FEM_ERR_NOT_IMPLEMENTED, "vector-valued Lagrange spaces on distributed meshes (DG spaces: the Copy exchange moves blocks of n_b * dimRange)");
   REQUIRE(dim_range == 1 || order <= 3, B200FEM_ERR_NOT_IMPLEMENTED, "vector-valued spaces: orders 1..3");
   REQUIRE(dim_range == 1 || !(mesh && mesh->unstructured), B200FEM_ERR_NOT_IMPLEMENTED, "vector-valued spaces on unstructured meshes");
   int rc = b200fem_space_create(mesh, kind, order, numbering, out); if (rc) return rc;
@@ -312,7 +311,8 @@ int b200fem::operator_create_impl(b200fem_space* s, const b200fem_model* model, 
   CUDA_OK(cudaEventCreate(&op->ev0)); CUDA_OK(cudaEventCreate(&op->ev1)); CUDA_OK(cudaEventCreate(&op->evx0)); CUDA_OK(cudaEventCreate(&op->evx1));
   if (c->world > 1) {
     // index lists of the NCCL transport (always built: they also define the auxiliary-dof mask and are the fallback)
-    const int blk = s->nb * s->dim_range;        // doubles per element of a DG space (vector-valued: n_b blocks of dimRange components)
+    // doubles per exchanged block: an element of a DG space (n_b blocks of dimRange components), a node of a Lagrange space (dimRange)
+    const int blk = s->kind == B200FEM_LAGRANGE ? s->dim_range : s->nb * s->dim_range;
     int rc = halo_plan_build(op->halo, s->mesh->proc, s->mesh->pc, s->box, s->kind == B200FEM_LAGRANGE, s->kind == B200FEM_LAGRANGE ? s->order : 0, blk, s->lay, s->size, &op->d_aux);
     if (!rc && s->kind != B200FEM_LAGRANGE) rc = halo_plan_dg_build(op->halo_dg, s->mesh->proc, s->mesh->pc, s->box, blk);
     if (rc) { b200fem_operator_destroy(op); return fail(B200FEM_ERR_COMM, "halo plan failed"); }
@@ -323,7 +323,7 @@ int b200fem::operator_create_impl(b200fem_space* s, const b200fem_model* model, 
       if (s->kind != B200FEM_LAGRANGE) {
         ok = halo_plan_p2p_build(op->halo_p2p, op->halo_dg, c->nccl, c->comm, c->rank, c->world, s->mesh->proc, s->mesh->pc, s->mesh->gn, s->box, s->nb * s->dim_range, c->d_comm_error, c->stream) == 0;
       } else {
-        ok = halo_plan_add_build(op->halo_add, c->nccl, c->comm, c->rank, c->world, s->mesh->proc, s->mesh->pc, s->lay, s->lattice_map, s->box.dim, c->d_comm_error, c->stream) == 0;
+        ok = halo_plan_add_build(op->halo_add, c->nccl, c->comm, c->rank, c->world, s->mesh->proc, s->mesh->pc, s->lay, s->lattice_map, s->box.dim, s->dim_range, c->d_comm_error, c->stream) == 0;
       }
       cudaGetLastError();
       // agree on the outcome: one failing rank switches everybody to NCCL

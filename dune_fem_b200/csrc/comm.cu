@@ -96,7 +96,8 @@ void halo_plan_free(HaloPlan& p) {
 int halo_plan_build(HaloPlan& p, const int proc[3], const int pc[3], const BoxDev& box, bool lagrange, int order, int nb,
                     const LagrangeLayoutDev& layout_dev, long long size, uint8_t** d_aux_out) {
   (void)order;
-  p.block = lagrange ? 1 : nb;
+  // DG: nb = doubles per element (n_b * dimRange); Lagrange: nb = dimRange -- a shared node carries a block of dimRange components
+  p.block = nb;
   std::vector<uint8_t> aux((size_t)size, 0);
   LagrangeLayoutDev L = layout_dev;
   std::vector<long long> host_map;
@@ -128,9 +129,9 @@ int halo_plan_build(HaloPlan& p, const int proc[3], const int pc[3], const BoxDe
       const long long plane = s ? L.lattice[d] - 1 : 0;
       for (g[2] = 0; g[2] < L.lattice[2]; ++g[2]) for (g[1] = 0; g[1] < L.lattice[1]; ++g[1]) for (g[0] = 0; g[0] < L.lattice[0]; ++g[0]) {
         if (g[d] != plane) continue;
-        const long long dof = lagrange_dof(L, g[0], g[1], g[2]);
+        const long long dof = lagrange_dof(L, g[0], g[1], g[2]) * nb;
         send.push_back(dof); recv.push_back(dof);
-        if (s == 0) aux[(size_t)dof] = 1;       // a lower rank shares this dof: auxiliary here
+        if (s == 0) for (int c = 0; c < nb; ++c) aux[(size_t)(dof + c)] = 1;       // a lower rank shares this node: auxiliary here
       }
     }
     h.count = (long long)send.size();
@@ -450,8 +451,9 @@ static void shared_nodes(const long long Lat[3], const int dir[3], int dim, std:
 }
 
 int halo_plan_add_build(HaloPlanAddP2P& p, NcclApi& nccl, void* comm, int rank, int world, const int proc[3], const int pc[3],
-                        const LagrangeLayoutDev& layout_dev, const std::vector<long long>& host_lattice_map, int dim, int* d_err, cudaStream_t st) {
+                        const LagrangeLayoutDev& layout_dev, const std::vector<long long>& host_lattice_map, int dim, int dim_range, int* d_err, cudaStream_t st) {
   (void)d_err;
+  const int R = dim_range;            // vector-valued spaces: every (node, component) is a shared dof of its own, node * R + c
   LagrangeLayoutDev L = layout_dev; L.lattice_map = host_lattice_map.empty() ? nullptr : host_lattice_map.data();
   const long long Lat[3] = {L.lattice[0], L.lattice[1], L.lattice[2]};
   // my neighbours in the fixed 26-direction order and the size of the message exchanged with each (symmetric)
@@ -467,8 +469,8 @@ int halo_plan_add_build(HaloPlanAddP2P& p, NcclApi& nccl, void* comm, int rank, 
         cnt *= dir[a] == 0 ? lat[a] : 1;
       }
       if (!ok) continue;
-      Nb nb; nb.dir[0] = dx; nb.dir[1] = dy; nb.dir[2] = dz; nb.peer = (c[0] + dx) + proc[0] * ((c[1] + dy) + proc[1] * (c[2] + dz)); nb.count = cnt; nb.offset = off;
-      off += cnt; v.push_back(nb);
+      Nb nb; nb.dir[0] = dx; nb.dir[1] = dy; nb.dir[2] = dz; nb.peer = (c[0] + dx) + proc[0] * ((c[1] + dy) + proc[1] * (c[2] + dz)); nb.count = cnt * R; nb.offset = off;
+      off += cnt * R; v.push_back(nb);
     }
     return std::make_pair(v, off);
   };
@@ -524,13 +526,13 @@ int halo_plan_add_build(HaloPlanAddP2P& p, NcclApi& nccl, void* comm, int rank, 
   for (int i = 0; i < p.nnb; ++i) {
     const Nb& nb = mine.first[(size_t)i];
     shared_nodes(Lat, nb.dir, dim, nodes);
-    if ((long long)nodes.size() != nb.count) return -1;
-    std::vector<unsigned int> idx(nodes.size());
-    for (size_t q = 0; q < nodes.size(); ++q) {
-      const long long dof = lagrange_dof(L, nodes[q][0], nodes[q][1], nodes[q][2]);
-      if (dof > 0xffffffffll || nb.offset + (long long)q > 0x7fffffffll) return -1;
-      idx[q] = (unsigned int)dof;
-      contrib[(unsigned int)dof].push_back({nb.peer, (int)(nb.offset + (long long)q)});
+    if ((long long)nodes.size() * R != nb.count) return -1;
+    std::vector<unsigned int> idx(nodes.size() * (size_t)R);
+    for (size_t q = 0; q < nodes.size(); ++q) for (int c = 0; c < R; ++c) {
+      const long long dof = lagrange_dof(L, nodes[q][0], nodes[q][1], nodes[q][2]) * R + c; const size_t pos = q * (size_t)R + c;
+      if (dof > 0xffffffffll || nb.offset + (long long)pos > 0x7fffffffll) return -1;
+      idx[pos] = (unsigned int)dof;
+      contrib[(unsigned int)dof].push_back({nb.peer, (int)(nb.offset + (long long)pos)});
     }
     unsigned int* d_idx = nullptr; if (cudaMalloc(&d_idx, idx.size() * 4) != cudaSuccess) return -1;
     cudaMemcpy(d_idx, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice); p.owned.push_back(d_idx);

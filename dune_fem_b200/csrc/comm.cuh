@@ -228,7 +228,7 @@ struct HaloPlanAddP2P {
   std::vector<void*> owned;
 };
 int halo_plan_add_build(HaloPlanAddP2P& p, NcclApi& nccl, void* comm, int rank, int world, const int proc[3], const int pc[3],
-                        const LagrangeLayoutDev& layout_dev, const std::vector<long long>& host_lattice_map, int dim, int* d_err, cudaStream_t st);
+                        const LagrangeLayoutDev& layout_dev, const std::vector<long long>& host_lattice_map, int dim, int dim_range, int* d_err, cudaStream_t st);
 void halo_plan_add_free(HaloPlanAddP2P& p);
 int halo_exchange_add_p2p(HaloPlanAddP2P& p, double* v, int* d_err, cudaStream_t st);
 

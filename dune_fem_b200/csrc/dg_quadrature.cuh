@@ -283,6 +283,10 @@ __device__ __forceinline__ void element_integrals(const QuadTabDev<N, MI, MS>& T
       const double area = detJ * ihd, ihe = ihd;          // faceArea; 1 / he with he = avg(CellVolume)/FacetArea = h_d on a uniform box
       const int lcd = d == 0 ? lc[0] : d == 1 ? lc[1] : lc[2], nd_ = d == 0 ? box.n[0] : d == 1 ? box.n[1] : box.n[2];
       const int olo = d == 0 ? box.own_lo[0] : d == 1 ? box.own_lo[1] : box.own_lo[2], ohi = d == 0 ? box.own_hi[0] : d == 1 ? box.own_hi[1] : box.own_hi[2];
+      // domain boundary in GLOBAL coordinates: the rank-local box of a continuous space ends at rank interfaces too (no ghost layers
+      // there), and those faces carry no boundary integral
+      const int gcd = (d == 0 ? box.origin[0] : d == 1 ? box.origin[1] : box.origin[2]) + lcd;
+      const bool dom_bnd = s ? gcd == (d == 0 ? box.gn[0] : d == 1 ? box.gn[1] : box.gn[2]) - 1 : gcd == 0;
       int cn = lcd + (s ? 1 : -1);
       bool nb_exists = cn >= 0 && cn < nd_;
       if (GEN && !nb_exists && ((box.periodic >> d) & 1)) { cn = cn < 0 ? nd_ - 1 : 0; nb_exists = true; }     // periodic: the far side's element (galerkin.hh:859-861)
@@ -317,7 +321,7 @@ __device__ __forceinline__ void element_integrals(const QuadTabDev<N, MI, MS>& T
               if (own_inside) { I.skeleton(xq, d, s ? 1.0 : -1.0, ihe, own, nb, rin, rout); r = rin; }
               else            { I.skeleton(xq, d, s ? -1.0 : 1.0, ihe, nb, own, rin, rout); r = rout; }
             }
-          } else if (I.m.has_boundary && d < box.dim) {         // (a 2-D mesh is one layer of cells: its x2-faces are no boundary)
+          } else if (I.m.has_boundary && d < box.dim && dom_bnd) {         // (a 2-D mesh is one layer of cells: its x2-faces are no boundary)
             r = I.boundary(d, s, ihe, xq, own);
           }
         } else {
@@ -328,7 +332,7 @@ __device__ __forceinline__ void element_integrals(const QuadTabDev<N, MI, MS>& T
               if (own_inside) { I.skeleton(xq, d, s ? 1.0 : -1.0, ihe, ownv, nbv, rin, rout); r = quad_pick<R>(rin, comp); }
               else            { I.skeleton(xq, d, s ? -1.0 : 1.0, ihe, nbv, ownv, rin, rout); r = quad_pick<R>(rout, comp); }
             }
-          } else if (I.m.has_boundary && d < box.dim) {
+          } else if (I.m.has_boundary && d < box.dim && dom_bnd) {
             r = quad_pick<R>(I.boundary(d, s, ihe, xq, ownv), comp);
           }
         }

@@ -143,8 +143,8 @@ int b200fem_space_create(b200fem_mesh* mesh, int kind, int order, int numbering,
  * space/shapefunctionset/vectorial.hh:508-526: local dof i * dimRange + c; DofVector blocks of dimRange components,
  * function/blockvectors/defaultblockvectors.hh:284-294): b200fem_space_size = blocks * dim_range, dof (block g, component c) =
  * g * dim_range + c; b200fem_space_dofmap / _local_size keep returning BLOCK indices (blockMapper()).  dim_range 1..4, orders 1..3;
- * DG spaces also on distributed meshes (the Copy exchange moves element blocks of n_b * dim_range doubles), Lagrange spaces on one
- * rank; operators on them take run-time compiled integrands (b200fem_operator_create_jit) -- the built-in family is scalar. */
+ * also on distributed meshes (the Copy exchange of DG spaces moves element blocks of n_b * dim_range doubles, the Add exchange of
+ * Lagrange spaces sums blocks of dim_range components on shared nodes); operators on them take run-time compiled integrands (b200fem_operator_create_jit) -- the built-in family is scalar. */
 int b200fem_space_create_vector(b200fem_mesh* mesh, int kind, int order, int numbering, int dim_range, b200fem_space** out);
 int b200fem_space_dim_range(b200fem_space* space, int32_t* dim_range);
 int b200fem_space_destroy(b200fem_space* space);

@@ -107,6 +107,27 @@ def check_dg_onb_and_compiled_integrands(ctx, rank, proc, n):
         op(np.ascontiguousarray(ug[gather]), wl)
         worst = max(worst, rel(wl, wref))
     assert worst < TOL, ("vector-valued DG space", proc, worst)
+    # vector-valued Lagrange space (P2, dimRange 2): the Add exchange sums blocks of dimRange components on shared nodes
+    lspace, losp = fem.space.lagrange(grid, order=2, dimRange=R), ol.Space(n, lo, hi, ol.LAGRANGE, 2)
+    l2g = lagrange_l2g(fem.space.lagrange(grid, order=2), losp, n, proc, rank)
+    l2gv = (l2g[:, None] * R + np.arange(R)[None, :]).ravel()
+    assert l2gv.size == lspace.size
+    ug = np.random.default_rng(24).uniform(-1, 1, losp.size * R)
+    lop = fem.operator.galerkinJit(lspace, srcv, constv, skeleton=False, boundary=True)
+    wref = ol.VectorUserOperator(losp, R, srcv, constv, skeleton=False, boundary=True).apply(ug)[l2gv]
+    for rep in range(2):
+        wl = np.full(lspace.size, np.nan)
+        lop(np.ascontiguousarray(ug[l2gv]), wl)
+        worst = max(worst, rel(wl, wref))
+    assert worst < TOL, ("vector-valued Lagrange space", proc, worst)
+    # scalar P2 with WEAK boundary terms through the quadrature kernel (non-linear model): rank interfaces are not domain boundaries
+    kwb = dict(eps=0.7, b=(1.0, -0.5, 0.25), c=0.3, gamma=0.5, beta=80.0, dirichlet_mask=0b011011, data=1, boundary=True)
+    sspace = fem.space.lagrange(grid, order=2)
+    ug = np.random.default_rng(25).uniform(-1, 1, losp.size)
+    wl = np.full(sspace.size, np.nan)
+    fem.operator.galerkin(sspace, **kwb)(np.ascontiguousarray(ug[l2g]), wl)
+    worst = max(worst, rel(wl, ol.Operator(losp, **kwb).apply(ug)[l2g]))
+    assert worst < TOL, ("Lagrange space with boundary integrals", proc, worst)
     return worst
 
 
