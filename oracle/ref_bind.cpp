@@ -5,6 +5,8 @@
 //   dune/fem/quadrature/gausspoints{,_implementation}.hh       the 1-D Gauss tables
 //   dune/fem/space/shapefunctionset/legendrepolynomials.{hh,cc} the Legendre coefficient table and its Horner evaluation
 //   dune/fem/space/shapefunctionset/orthonormal/orthonormalbase_{1,2,3}d.hh   the orthonormal P_k bases behind `dgonb`
+//   dune/fem/space/lagrange/generic{geometry,lagrangepoints,basefunctions}.hh   the Lagrange points of the cube (local numbering,
+//                                                              sub-entity and dof-in-entity of every node) and the Lagrange basis
 //
 // Built by oracle/Makefile (target `ref`) into oracle/_ref/libdunefem_ref.so with `-I oracle/ref_shim -I /root/reference`;
 // the shim directory only supplies stand-ins for headers of dune-common that are absent from this image (see the files
@@ -33,6 +35,7 @@
 #include <dune/fem/space/shapefunctionset/orthonormal/orthonormalbase_1d.hh>
 #include <dune/fem/space/shapefunctionset/orthonormal/orthonormalbase_2d.hh>
 #include <dune/fem/space/shapefunctionset/orthonormal/orthonormalbase_3d.hh>
+#include <dune/fem/space/lagrange/genericbasefunctions.hh>
 
 namespace {
 
@@ -90,9 +93,51 @@ int parseHistory(const std::string& log, const char* key, double* hist, int maxH
   return k;
 }
 
+// ---- generic Lagrange points / base functions of the dim-cube (space/lagrange/shapefunctionset.hh:88 instantiates them like this)
+template <int dim> struct ScalarFunctionSpace {
+  static const int dimDomain = dim, dimRange = 1; typedef double DomainFieldType; typedef double RangeFieldType;
+  typedef Dune::FieldVector<double, dim> DomainType; typedef Dune::FieldVector<double, 1> RangeType;
+};
+template <int dim, unsigned order> struct LagrangeCube {
+  typedef typename Dune::Fem::GeometryWrapper<(1u << dim) - 1u, dim>::ImplType Geometry;
+  typedef Dune::Fem::GenericLagrangeBaseFunction<ScalarFunctionSpace<dim>, Geometry, order> BaseFunction;
+  typedef Dune::Fem::GenericLagrangePoint<Geometry, order> Point;
+  static int points(double* x, int* codim, int* sub, int* dofnum) {
+    const int n = (int)BaseFunction::numBaseFunctions;
+    for (int b = 0; b < n; ++b) {
+      Point pt(b); Dune::FieldVector<double, dim> xl; pt.local(xl);
+      unsigned int c, s, k; pt.dofSubEntity(c, s, k);
+      if (x) for (int d = 0; d < dim; ++d) x[b * dim + d] = xl[d];
+      if (codim) { codim[b] = (int)c; sub[b] = (int)s; dofnum[b] = (int)k; }
+    }
+    return n;
+  }
+  static void evaluate(int base, const double* x, double* phi, double* dphi) {
+    BaseFunction bf(base); Dune::FieldVector<double, dim> xl; for (int d = 0; d < dim; ++d) xl[d] = x[d];
+    Dune::FieldVector<double, 1> v; Dune::FieldVector<int, 0> d0; bf.evaluate(d0, xl, v); *phi = v[0];
+    for (int d = 0; d < dim; ++d) { Dune::FieldVector<int, 1> d1; d1[0] = d; bf.evaluate(d1, xl, v); dphi[d] = v[0]; }
+  }
+};
+
 }  // namespace
 
 extern "C" {
+
+// GenericLagrangePoint of the dim-cube (space/lagrange/genericlagrangepoints.hh): local coordinates, codimension / number of the
+// sub-entity and number of the dof inside it, for every local node; returns the number of nodes (0: unsupported dim / order)
+int ref_lagrange_cube_points(int dim, int order, double* x, int* codim, int* sub, int* dofnum) {
+#define B200_CASE(D, O) if (dim == D && order == O) return LagrangeCube<D, O>::points(x, codim, sub, dofnum);
+  B200_CASE(2, 1) B200_CASE(2, 2) B200_CASE(2, 3) B200_CASE(3, 1) B200_CASE(3, 2) B200_CASE(3, 3)
+#undef B200_CASE
+  return 0;
+}
+// GenericLagrangeBaseFunction::evaluate (space/lagrange/genericbasefunctions.hh): value and reference gradient of local basis function `base`
+int ref_lagrange_cube_evaluate(int dim, int order, int base, const double* x, double* phi, double* dphi) {
+#define B200_CASE(D, O) if (dim == D && order == O) { LagrangeCube<D, O>::evaluate(base, x, phi, dphi); return 0; }
+  B200_CASE(2, 1) B200_CASE(2, 2) B200_CASE(2, 3) B200_CASE(3, 1) B200_CASE(3, 2) B200_CASE(3, 3)
+#undef B200_CASE
+  return -1;
+}
 
 // LinearSolver::cg (dune/fem/solver/linear/cg.hh:18-117); precon may be NULL
 int ref_cg(ApplyFn apply, void* ctx, ApplyFn precon, void* pctx, std::int64_t n, const std::int64_t* aux, std::int64_t naux,

@@ -46,6 +46,11 @@ def lib():
     L.ref_legendre.argtypes = [C.c_int, C.c_double, C.c_int]
     L.ref_onb_cube.restype = C.c_double
     L.ref_onb_cube.argtypes = [C.c_int, C.c_int, _dp, C.c_void_p]
+    _ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+    L.ref_lagrange_cube_points.restype = C.c_int
+    L.ref_lagrange_cube_points.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ref_lagrange_cube_evaluate.restype = C.c_int
+    L.ref_lagrange_cube_evaluate.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, _dp]
     _LIB = L
     return L
 
@@ -110,3 +115,22 @@ def onb_cube(dim, i, x, grad=False):
     g = np.zeros(3)
     v = lib().ref_onb_cube(dim, i, x, g.ctypes.data_as(C.c_void_p))
     return v, g[:dim]
+
+
+def lagrange_cube_points(dim, order):
+    """GenericLagrangePoint of the dim-cube (space/lagrange/genericlagrangepoints.hh): per local node its reference coordinates, the
+    codimension and number of the sub-entity it lies in and its number inside that sub-entity"""
+    n = lib().ref_lagrange_cube_points(dim, order, None, None, None, None)
+    assert n == (order + 1) ** dim
+    x = np.empty((n, dim))
+    codim, sub, num = (np.empty(n, dtype=np.int32) for _ in range(3))
+    lib().ref_lagrange_cube_points(dim, order, x.ctypes.data_as(C.c_void_p), codim.ctypes.data_as(C.c_void_p), sub.ctypes.data_as(C.c_void_p), num.ctypes.data_as(C.c_void_p))
+    return x, codim, sub, num
+
+
+def lagrange_cube_evaluate(dim, order, base, x):
+    """GenericLagrangeBaseFunction::evaluate (space/lagrange/genericbasefunctions.hh): value and reference gradient"""
+    phi, dphi = np.empty(1), np.empty(dim)
+    rc = lib().ref_lagrange_cube_evaluate(dim, order, base, np.ascontiguousarray(x, dtype=np.float64), phi, dphi)
+    assert rc == 0
+    return phi[0], dphi

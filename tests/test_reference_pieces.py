@@ -138,3 +138,70 @@ def test_dgonb_shape_functions_are_the_reference_functions(dim, max_order):
                 v, g = rl.onb_cube(dim, i, x, grad=True)
                 assert abs(v - phi[i]) < 1e-12 * max(1.0, abs(v))
                 assert np.abs(g - dphi[i, :dim]).max() < 1e-11 * max(1.0, np.abs(g).max())
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_lagrange_basis_and_local_numbering_are_the_reference_ones(dim, order):
+    """GenericLagrangePoint / GenericLagrangeBaseFunction of the cube, compiled from the reference: the oracle's local numbering
+    (coordinate 0 fastest), node positions and basis values / reference gradients are the reference's"""
+    sp = ol.Space([1] * dim, [0.0] * dim, [1.0] * dim, ol.LAGRANGE, order)
+    x, codim, sub, num = rl.lagrange_cube_points(dim, order)
+    mi = sp.multiindex()[:, :dim]
+    assert np.abs(x - mi / order).max() < 1e-15                       # local node l sits at multiIndex[l] / order
+    rng = np.random.default_rng(dim * 10 + order)
+    for xp in rng.uniform(0, 1, (5, dim)):
+        phi, dphi = sp.shape(xp)
+        for b in range(sp.local_size):
+            v, dv = rl.lagrange_cube_evaluate(dim, order, b, xp)
+            assert abs(v - phi[b]) < 1e-13 and np.abs(dv - dphi[b, :dim]).max() < 1e-12
+
+
+@pytest.mark.parametrize("dim,n", [(2, [3, 2]), (3, [2, 2, 2])])
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_lagrange_dof_numbering_follows_the_reference_sub_entity_rule(dim, n, order):
+    """The global numbering `offset[type] + numDofs(entity) * index(entity) + dofNumber` (space/mapper/indexsetdofmapper.hh:414-427)
+    with the reference's own (codim, subEntity, dofNumber) of every local node (GenericLagrangePoint::dofSubEntity): the oracle's
+    closed-form YaspGrid numbering must be consistent with it -- nodes of one sub-entity of an element are numbered contiguously,
+    in the order of the reference's dofNumber, blocks ordered by entity dimension (vertices first), and two elements sharing a
+    sub-entity agree on all its dofs (no twists on Cartesian grids, lagrange/space.hh:68-71)."""
+    sp = ol.Space(n, [0.0] * dim, [1.0] * dim, ol.LAGRANGE, order)
+    x, codim, sub, num = rl.lagrange_cube_points(dim, order)
+    per_entity = [(order - 1) ** (dim - c) if order > 1 or c == dim else 0 for c in range(dim + 1)]     # dofs inside an entity of codim c
+    first_of_dim = {}                                                  # entity dimension -> smallest global dof seen
+    for e in range(sp.elements):
+        g = sp.dofmap(e)
+        for c in range(dim + 1):
+            for s in np.unique(sub[codim == c]):
+                sel = np.where((codim == c) & (sub == s))[0]
+                assert len(sel) == per_entity[c]
+                dofs = g[sel][np.argsort(num[sel])]                    # in the order of the reference's dof number inside the entity
+                assert (np.diff(dofs) == 1).all() and dofs[0] % len(sel) == (first_of_dim.setdefault(dim - c, dofs[0]) % len(sel))
+                first_of_dim[dim - c] = min(first_of_dim[dim - c], dofs[0])
+    dims = sorted(first_of_dim)
+    assert all(first_of_dim[a] < first_of_dim[b] for a, b in zip(dims, dims[1:]))           # vertices | edges | faces | cells
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_first_touch_numbering_visits_sub_entities_in_the_reference_order(dim):
+    """AdaptiveLeafIndexSet numbers the sub-entities of an element in reference-element order (gridpart/adaptiveleafindexset.hh:884-906).
+    On a one-element mesh the first-touch index of a sub-entity IS its reference number, so the oracle's adaptive-leaf dof of the P2
+    node inside sub-entity (codim, sub) must be offset[dimension] + sub with the reference's own (codim, sub) of that node
+    (GenericLagrangePoint::dofSubEntity) -- this pins the sub-entity order tables of the oracle (Space::buildSubEntityOrder) and of the
+    product (capi.cu: build_adaptive_leaf_map, unstructured.cu: sub_entity_order), which the unstructured numbering rests on too."""
+    sp = ol.Space([1] * dim, [0.0] * dim, [1.0] * dim, ol.LAGRANGE, 2, numbering=ol.NUMBERING_ADAPTIVE_LEAF)
+    x, codim, sub, num = rl.lagrange_cube_points(dim, 2)
+    counts = [int((codim == dim - p).sum()) for p in range(dim + 1)]          # entities per dimension p (one P2 node each)
+    offset = np.concatenate([[0], np.cumsum(counts)])
+    g = sp.dofmap(0)
+    for l in range(sp.local_size):
+        assert g[l] == offset[dim - codim[l]] + sub[l] and num[l] == 0
+    # the same mesh through the unstructured path (host-only numbering of the product)
+    import ctypes as C
+    from dune_fem_b200 import _capi
+    coords, elems = ol.cartesian_as_unstructured([1] * dim, [0.0] * dim, [1.0] * dim)
+    coords, elems = np.ascontiguousarray(coords), np.ascontiguousarray(elems, dtype=np.int64)
+    size = C.c_int64()
+    dofs = np.empty((1, 3 ** dim), dtype=np.int32)
+    assert _capi.lib().b200fem_unstructured_numbering(dim, len(coords), _capi.ptr(coords), 1, _capi.ptr(elems, np.int64), 2, C.byref(size), _capi.ptr(dofs, np.int32), None, None) == 0
+    assert (dofs[0] == g).all()
