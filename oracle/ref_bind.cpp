@@ -5,6 +5,8 @@
 //   dune/fem/quadrature/gausspoints{,_implementation}.hh       the 1-D Gauss tables
 //   dune/fem/space/shapefunctionset/legendrepolynomials.{hh,cc} the Legendre coefficient table and its Horner evaluation
 //   dune/fem/space/shapefunctionset/orthonormal/orthonormalbase_{1,2,3}d.hh   the orthonormal P_k bases behind `dgonb`
+//   dune/fem/quadrature/femquadratures{,_inline}.hh            CubeQuadrature: tensor construction of the Gauss rules, order selection
+//   dune/fem/space/shapefunctionset/legendre.hh                the Legendre shape function SET (multi-index order, hierarchical sort)
 //   dune/fem/space/lagrange/generic{geometry,lagrangepoints,basefunctions}.hh   the Lagrange points of the cube (local numbering,
 //                                                              sub-entity and dof-in-entity of every node) and the Lagrange basis
 //
@@ -36,6 +38,8 @@
 #include <dune/fem/space/shapefunctionset/orthonormal/orthonormalbase_2d.hh>
 #include <dune/fem/space/shapefunctionset/orthonormal/orthonormalbase_3d.hh>
 #include <dune/fem/space/lagrange/genericbasefunctions.hh>
+#include <dune/fem/space/shapefunctionset/legendre.hh>
+#include <dune/fem/quadrature/femquadratures.hh>
 
 namespace {
 
@@ -119,9 +123,40 @@ template <int dim, unsigned order> struct LagrangeCube {
   }
 };
 
+// ---- LegendreShapeFunctionSet< FunctionSpace, hierarchicalOrdering > (space/shapefunctionset/legendre.hh:216-360)
+template <int dim> struct LegendreFunctionSpace : ScalarFunctionSpace<dim> {
+  typedef Dune::FieldVector<Dune::FieldVector<double, dim>, 1> JacobianRangeType;
+  typedef Dune::FieldVector<Dune::FieldVector<Dune::FieldVector<double, dim>, dim>, 1> HessianRangeType;
+};
+template <int dim, bool hier> int legendreSet(int order, const double* x, double* phi, double* dphi) {
+  Dune::Fem::LegendreShapeFunctionSet<LegendreFunctionSpace<dim>, hier> sfs(order);
+  Dune::FieldVector<double, dim> xl; for (int d = 0; d < dim; ++d) xl[d] = x[d];
+  if (phi) sfs.evaluateEach(xl, [&](std::size_t i, const Dune::FieldVector<double, 1>& v) { phi[i] = v[0]; });
+  if (dphi) sfs.jacobianEach(xl, [&](std::size_t i, const typename LegendreFunctionSpace<dim>::JacobianRangeType& j) { for (int d = 0; d < dim; ++d) dphi[i * dim + d] = j[0][d]; });
+  return (int)sfs.size();
+}
+
 }  // namespace
 
 extern "C" {
+
+// LegendreShapeFunctionSet (plain and hierarchical ordering): values phi[n] and reference gradients dphi[n][dim] of all shape
+// functions at x, in the set's own order; returns n
+int ref_legendre_set(int dim, int order, int hierarchical, const double* x, double* phi, double* dphi) {
+  if (dim == 2) return hierarchical ? legendreSet<2, true>(order, x, phi, dphi) : legendreSet<2, false>(order, x, phi, dphi);
+  if (dim == 3) return hierarchical ? legendreSet<3, true>(order, x, phi, dphi) : legendreSet<3, false>(order, x, phi, dphi);
+  return 0;
+}
+
+// CubeQuadrature< double, dim >( cube, order ) (quadrature/femquadratures_inline.hh:33-95): points x[n][dim], weights w[n] in the
+// rule's own order, *exact receives the order of the rule that was selected; returns n (x, w may be NULL)
+int ref_cube_quadrature(int dim, int order, double* x, double* w, int* exact) {
+#define B200_CASE(D) if (dim == D) { Dune::Fem::CubeQuadrature<double, D> q(Dune::GeometryTypes::cube(D), order, 0); if (exact) *exact = q.order(); \
+    if (x) for (int i = 0; i < (int)q.nop(); ++i) { for (int d = 0; d < D; ++d) x[i * D + d] = q.point(i)[d]; w[i] = q.weight(i); } return (int)q.nop(); }
+  B200_CASE(1) B200_CASE(2) B200_CASE(3)
+#undef B200_CASE
+  return 0;
+}
 
 // GenericLagrangePoint of the dim-cube (space/lagrange/genericlagrangepoints.hh): local coordinates, codimension / number of the
 // sub-entity and number of the dof inside it, for every local node; returns the number of nodes (0: unsupported dim / order)

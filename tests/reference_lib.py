@@ -49,6 +49,10 @@ def lib():
     _ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
     L.ref_lagrange_cube_points.restype = C.c_int
     L.ref_lagrange_cube_points.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ref_cube_quadrature.restype = C.c_int
+    L.ref_cube_quadrature.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+    L.ref_legendre_set.restype = C.c_int
+    L.ref_legendre_set.argtypes = [C.c_int, C.c_int, C.c_int, _dp, C.c_void_p, C.c_void_p]
     L.ref_lagrange_cube_evaluate.restype = C.c_int
     L.ref_lagrange_cube_evaluate.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, _dp]
     _LIB = L
@@ -134,3 +138,22 @@ def lagrange_cube_evaluate(dim, order, base, x):
     rc = lib().ref_lagrange_cube_evaluate(dim, order, base, np.ascontiguousarray(x, dtype=np.float64), phi, dphi)
     assert rc == 0
     return phi[0], dphi
+
+
+def legendre_set(dim, order, hierarchical, x):
+    """LegendreShapeFunctionSet< FunctionSpace, hierarchical >( order ) (space/shapefunctionset/legendre.hh): values and reference
+    gradients of all shape functions at x, in the set's own order"""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    n = lib().ref_legendre_set(dim, order, int(hierarchical), x, None, None)
+    phi, dphi = np.empty(n), np.empty((n, dim))
+    lib().ref_legendre_set(dim, order, int(hierarchical), x, phi.ctypes.data_as(C.c_void_p), dphi.ctypes.data_as(C.c_void_p))
+    return phi, dphi
+
+
+def cube_quadrature(dim, order):
+    """CubeQuadrature< double, dim > of the reference: (points [n][dim], weights [n], order of the selected rule)"""
+    exact = C.c_int()
+    n = lib().ref_cube_quadrature(dim, order, None, None, C.byref(exact))
+    x, w = np.empty((n, dim)), np.empty(n)
+    lib().ref_cube_quadrature(dim, order, x.ctypes.data_as(C.c_void_p), w.ctypes.data_as(C.c_void_p), C.byref(exact))
+    return x, w, exact.value

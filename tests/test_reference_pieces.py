@@ -205,3 +205,30 @@ def test_first_touch_numbering_visits_sub_entities_in_the_reference_order(dim):
     dofs = np.empty((1, 3 ** dim), dtype=np.int32)
     assert _capi.lib().b200fem_unstructured_numbering(dim, len(coords), _capi.ptr(coords), 1, _capi.ptr(elems, np.int64), 2, C.byref(size), _capi.ptr(dofs, np.int32), None, None) == 0
     assert (dofs[0] == g).all()
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("order", [1, 2, 3, 5])
+@pytest.mark.parametrize("hierarchical", [False, True])
+def test_legendre_shape_function_sets_are_the_reference_sets(dim, order, hierarchical):
+    """LegendreShapeFunctionSet compiled from the reference (multi-index recursion, hierarchical sort by (order, lexicographic
+    multi-index), space/shapefunctionset/legendre.hh:145-250): the oracle's DG spaces hold the same functions in the same ORDER --
+    this is the local numbering of the dof vector the device kernels read"""
+    sp = ol.Space([1] * dim, [0.0] * dim, [1.0] * dim, ol.DG_LEGENDRE_HIER if hierarchical else ol.DG_LEGENDRE, order)
+    for xp in np.random.default_rng(dim + order).uniform(0, 1, (4, dim)):
+        phi_ref, dphi_ref = rl.legendre_set(dim, order, hierarchical, xp)
+        phi, dphi = sp.shape(xp)
+        assert len(phi_ref) == sp.local_size
+        assert np.abs(phi - phi_ref).max() < 1e-12 * max(1.0, np.abs(phi_ref).max())
+        assert np.abs(dphi[:, :dim] - dphi_ref).max() < 1e-11 * max(1.0, np.abs(dphi_ref).max())
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3])
+def test_cube_quadratures_are_the_reference_rules(dim):
+    """CubeQuadrature compiled from the reference (quadrature/femquadratures_inline.hh:33-95): rule selection (smallest Gauss rule with
+    order >= requested), tensor construction with x0 fastest, weights = products -- the oracle's cubeQuadrature point for point"""
+    for order in range(0, 14):
+        x_ref, w_ref, exact = rl.cube_quadrature(dim, order)
+        x, w = ol.quadrature(dim, order)
+        assert len(w) == len(w_ref) and exact >= order
+        assert np.abs(x[:, :dim] - x_ref).max() == 0.0 and np.abs(w - w_ref).max() <= 4e-16      # same table entries; weights up to the product order
