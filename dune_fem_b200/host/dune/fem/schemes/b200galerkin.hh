@@ -82,6 +82,39 @@ namespace Dune
       static double lowerLeft ( const Grid &grid, int i ) { return lowerLeftImpl( grid, i, 0 ); }
     };
 
+    // Unstructured cube grids (ALUGrid< dim, dim, cube, conforming >): their traits specialisation sets `cartesian = false`; the
+    // mesh is then handed over as arrays, collected in ONE walk over the grid part -- corner( i ) of every element and
+    // indexSet.subIndex( element, i, dim ) of its vertices (the cube reference element's vertex order is the library's), elements in
+    // index-set order, so that the first-touch dof numbering the library applies is the AdaptiveLeafIndexSet's
+    // (gridpart/adaptiveleafindexset.hh:884-906).
+    template< class Grid, class = void >
+    struct B200IsCartesian : std::true_type {};
+    template< class Grid >
+    struct B200IsCartesian< Grid, std::void_t< decltype( Grid::b200Unstructured ) > > : std::integral_constant< bool, !Grid::b200Unstructured > {};
+
+    template< class GridPart >
+    inline void b200DescribeUnstructured ( const GridPart &gridPart, std::vector< double > &coords, std::vector< std::int64_t > &cubes )
+    {
+      constexpr int dim = GridPart::GridType::dimension, nv = 1 << dim;
+      const auto &indexSet = gridPart.indexSet();
+      coords.assign( std::size_t( indexSet.size( dim ) ) * dim, 0.0 );
+      cubes.assign( std::size_t( indexSet.size( 0 ) ) * nv, 0 );
+      for( auto it = gridPart.template begin< 0 >(); it != gridPart.template end< 0 >(); ++it )
+      {
+        const auto &entity = *it;
+        const auto geometry = entity.geometry();
+        const std::size_t e = indexSet.index( entity );
+        for( int i = 0; i < nv; ++i )
+        {
+          const std::size_t v = indexSet.subIndex( entity, i, dim );
+          cubes[ e*nv + i ] = std::int64_t( v );
+          const auto x = geometry.corner( i );
+          for( int d = 0; d < dim; ++d )
+            coords[ v*dim + d ] = x[ d ];
+        }
+      }
+    }
+
     namespace B200Impl
     {
       inline void check ( int rc )
@@ -102,14 +135,19 @@ namespace Dune
           typedef typename Space::GridPartType::GridType GridType;
           const auto &gridPart = space.gridPart();
           const int rank = gridPart.comm().rank();
-          std::int32_t cells[ 3 ], proc[ 3 ];
-          double lower[ 3 ], upper[ 3 ];
-          B200GridTraits< GridType >::describe( gridPart.grid(), cells, lower, upper, proc );
-          // the library deals cells in blocks with the first (n % p) ranks one cell larger; YaspGrid's load balancer is not
-          // restated, so the two partitions are only known to agree when every direction divides evenly
-          for( int i = 0; i < GridType::dimension; ++i )
-            if( cells[ i ] % proc[ i ] != 0 )
-              DUNE_THROW( NotImplemented, "B200GalerkinOperator: cells per direction must be a multiple of the process grid" );
+          std::int32_t cells[ 3 ] = { 1, 1, 1 }, proc[ 3 ] = { 1, 1, 1 };
+          double lower[ 3 ] = { 0, 0, 0 }, upper[ 3 ] = { 1, 1, 1 };
+          if constexpr ( B200IsCartesian< GridType >::value )
+          {
+            B200GridTraits< GridType >::describe( gridPart.grid(), cells, lower, upper, proc );
+            // the library deals cells in blocks with the first (n % p) ranks one cell larger; YaspGrid's load balancer is not
+            // restated, so the two partitions are only known to agree when every direction divides evenly
+            for( int i = 0; i < GridType::dimension; ++i )
+              if( cells[ i ] % proc[ i ] != 0 )
+                DUNE_THROW( NotImplemented, "B200GalerkinOperator: cells per direction must be a multiple of the process grid" );
+          }
+          else if( gridPart.comm().size() > 1 )
+            DUNE_THROW( NotImplemented, "B200GalerkinOperator: unstructured grids on one rank" );
           // one process per GPU (misc/mpimanager.hh:352-461): rank modulo the visible devices unless a device is named
           int devices = 0;
           check( b200fem_device_count( &devices ) );
@@ -124,7 +162,15 @@ namespace Dune
             gridPart.comm().broadcast( id, 128, 0 );
             check( b200fem_nccl_init( ctx, id, rank, world ) );
           }
-          check( b200fem_mesh_cartesian_distributed( ctx, GridType::dimension, cells, lower, upper, proc, rank, &mesh ) );
+          if constexpr ( B200IsCartesian< GridType >::value )
+            check( b200fem_mesh_cartesian_distributed( ctx, GridType::dimension, cells, lower, upper, proc, rank, &mesh ) );
+          else
+          {
+            std::vector< double > coords; std::vector< std::int64_t > cubes;
+            b200DescribeUnstructured( gridPart, coords, cubes );
+            check( b200fem_mesh_unstructured( ctx, GridType::dimension, std::int64_t( coords.size() / GridType::dimension ), coords.data(),
+                                              std::int64_t( cubes.size() >> GridType::dimension ), cubes.data(), &mesh ) );
+          }
           // localBlockSize = dimRange of the space (space/common/discretefunctionspace.hh): vector-valued spaces keep the scalar
           // block mapper, dof (block, c) = block * dimRange + c (function/blockvectors/defaultblockvectors.hh:284-294)
           check( b200fem_space_create_vector( mesh, B200SpaceKind< Space >::value, space.order(), B200FEM_NUMBERING_YASP, int( Space::localBlockSize ), &this->space ) );

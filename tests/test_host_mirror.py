@@ -61,7 +61,8 @@ def test_dune_binding_apply_and_gmres_match_the_oracle():
     r = _run2()
     assert r.returncode == 0, r.stdout + r.stderr
     src = open(os.path.join(ROOT, "tests", "dune_binding_selftest.cpp")).read()
-    body = "".join(eval(m) for m in re.findall(r'^\s*(?:return\s+)?("(?:[^"\\]|\\.)*")\s*;?\s*$', src[src.index("b200Source"):src.index("int main")], flags=re.M))
+    literals = lambda text: "".join(eval(m) for m in re.findall(r'^\s*(?:return\s+)?("(?:[^"\\]|\\.)*")\s*;?\s*$', text, flags=re.M))
+    body = literals(src[src.index("struct GeneratedIntegrands"):src.index("struct GeneratedInteriorIntegrands")])
     sp = ol.Space([8, 8], [-1.0, -1.0], [1.0, 1.0], ol.DG_ONB, 2)
     op = ol.UserOperator(sp, body, [0.5, 0.3, 80.0])
     u = np.sin(0.37 * np.arange(sp.size))
@@ -74,3 +75,16 @@ def test_dune_binding_apply_and_gmres_match_the_oracle():
     x = np.linalg.solve(A, b)
     for i in range(6):
         assert abs(float(out[f"x{i}"]) - x[i]) < 1e-7 * np.abs(x).max()
+    # the unstructured path of the binding: the (stub) ALUGrid-like grid part is walked once, the arrays go to b200fem_mesh_unstructured;
+    # P2 on a 3 x 3 patch of distorted quadrilaterals, interior-only generated integrands, against the oracle on the same arrays
+    body2 = literals(src[src.index("struct GeneratedInteriorIntegrands"):src.index("static int unstructuredPart")])
+    n = 3
+    vx = np.array([[i / n + 0.05 * np.sin(5.0 * j / n) * (i / n) * (1 - i / n), j / n + 0.04 * np.sin(4.0 * i / n) * (j / n) * (1 - j / n)]
+                   for j in range(n + 1) for i in range(n + 1)])
+    cubes = np.array([[i + (n + 1) * j, i + (n + 1) * j + 1, i + (n + 1) * j + n + 1, i + (n + 1) * j + n + 2] for j in range(n) for i in range(n)], dtype=np.int64)
+    uop = ol.UnstructuredOperator(vx, cubes, 2, user_source=body2, constants=[0.7, 0.4])
+    assert uop.size == 49
+    wu = uop.apply(np.sin(0.37 * np.arange(uop.size)))
+    assert abs(float(out["unstructured_apply_norm2"]) - float(np.sum(wu ** 2))) < 1e-11 * float(np.sum(wu ** 2))
+    for i in range(4):
+        assert abs(float(out[f"uw{i}"]) - wu[i]) < 1e-12 * np.abs(wu).max()
