@@ -11,6 +11,7 @@
 
 #include <map>
 #include <memory>
+#include <mutex>
 #include <tuple>
 
 #include "internal.hpp"
@@ -146,6 +147,13 @@ void jit_free(b200fem_operator* op) {
 }
 
 // the compiled kernel of one (order, rules, variant) configuration: NVRTC on first use, cached per operator
+// Compiled code is cached per process under everything the program text depends on: a second operator over the same form (another
+// mesh, another space of the same order, another rank-local box) loads the cubin instead of running NVRTC again -- the device analogue
+// of the reference's on-disk cache of generated operator modules (python/dune/generator).
+struct JitCubin { std::vector<char> cubin; std::string lowered; };
+static std::map<std::string, JitCubin>& jit_cache() { static std::map<std::string, JitCubin> c; return c; }
+static std::mutex g_jit_cache_mutex;
+
 static int jit_kernel(b200fem_operator* op, int N, int MI, int MS, int variant, size_t smem, JitKernel** out) {
   JitState* J = op->jit;
   JitKernel& K = J->kernels[std::make_tuple(N, MI, MS, variant)];
@@ -153,8 +161,13 @@ static int jit_kernel(b200fem_operator* op, int N, int MI, int MS, int variant, 
     REQUIRE(!op->capturing, B200FEM_ERR_INVALID, "run-time compilation inside a graph capture (apply once before solving)");
     REQUIRE(g_drv.load(), B200FEM_ERR_CUDA, "driver entry points (cuModuleLoadData, cuLaunchKernel) unavailable");
     std::vector<char> cubin; std::string lowered, log;
-    int rc = compile(J->source, J->skel, J->bnd, N, MI, MS, op->sp->dim_range, variant, &cubin, &lowered, &log);
+    const std::string key = std::to_string(N) + "/" + std::to_string(MI) + "/" + std::to_string(MS) + "/" + std::to_string(op->sp->dim_range) + "/" + std::to_string(variant) +
+                            (J->skel ? "/s" : "/-") + (J->bnd ? "b/" : "-/") + J->source;
+    bool cached = false;
+    { std::lock_guard<std::mutex> lock(g_jit_cache_mutex); auto it = jit_cache().find(key); if (it != jit_cache().end()) { cubin = it->second.cubin; lowered = it->second.lowered; cached = true; } }
+    int rc = cached ? B200FEM_OK : compile(J->source, J->skel, J->bnd, N, MI, MS, op->sp->dim_range, variant, &cubin, &lowered, &log);
     if (rc) return fail(rc, "integrands do not compile:\n" + log);
+    if (!cached) { std::lock_guard<std::mutex> lock(g_jit_cache_mutex); jit_cache()[key] = JitCubin{cubin, lowered}; }
     if (g_drv.ModuleLoadData(&K.mod, cubin.data()) != CUDA_SUCCESS) return fail(B200FEM_ERR_CUDA, "cuModuleLoadData failed for the compiled integrands");
     if (g_drv.ModuleGetFunction(&K.fn, K.mod, lowered.c_str()) != CUDA_SUCCESS) return fail(B200FEM_ERR_CUDA, "compiled kernel not found in its module");
     if (smem && g_drv.FuncSetAttribute(K.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem) != CUDA_SUCCESS) return fail(B200FEM_ERR_CUDA, "cuFuncSetAttribute(max dynamic shared memory) failed");
