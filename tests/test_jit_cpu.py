@@ -82,8 +82,11 @@ def test_vector_integrands_compile_into_the_kernels(name, kind, dim, order, R, s
 def test_scalar_integrands_compile_into_the_lagrange_kernels():
     log = C.create_string_buffer(1 << 16)
     for dim in (2, 3):
-        rc = _capi.lib().b200fem_jit_compile_check_space(SOURCE.encode(), _capi.LAGRANGE, dim, 2, 1, 0, 1, log, len(log))
-        assert rc == 0, log.value.decode()
+        for order in (2, 3):
+            rc = _capi.lib().b200fem_jit_compile_check_space(SOURCE.encode(), _capi.LAGRANGE, dim, order, 1, 0, 1, log, len(log))
+            assert rc == 0, log.value.decode()
+    rc = _capi.lib().b200fem_jit_compile_check_space(SOURCE.encode(), _capi.LAGRANGE, 2, 4, 1, 0, 1, log, len(log))
+    assert rc == _capi.ERR_NOT_IMPLEMENTED                      # Lagrange orders 1..3
 
 
 def test_vector_oracle_reduces_to_the_scalar_one_for_uncoupled_components():
