@@ -294,6 +294,7 @@ extern "C" int b200fem_operator_create(b200fem_space* s, const b200fem_model* mo
 }
 int b200fem::operator_create_impl(b200fem_space* s, const b200fem_model* model, b200fem_operator** out) {
   REQUIRE(!(model->strong_dirichlet && s->kind != B200FEM_LAGRANGE), B200FEM_ERR_INVALID, "strong Dirichlet constraints need a Lagrange space");
+  REQUIRE(!(s->unst && s->mesh->ctx->world > 1), B200FEM_ERR_NOT_IMPLEMENTED, "unstructured meshes: one rank (the context joined a communicator after the mesh was made)");
   REQUIRE(!(s->unst && (model->has_skeleton || model->has_boundary)), B200FEM_ERR_NOT_IMPLEMENTED, "unstructured meshes: interior integrands and strong Dirichlet constraints (no skeleton / boundary terms)");
   b200fem_ctx* c = s->mesh->ctx;
   CUDA_OK(cudaSetDevice(c->device));
