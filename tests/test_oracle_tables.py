@@ -98,3 +98,53 @@ def test_lagrange_shape_functions_are_nodal():
         # partition of unity and zero gradient sum
         phi, dphi = sp.shape(np.array([0.3, 0.6, 0.2])[:dim])
         assert abs(phi.sum() - 1) < 1e-14 and np.abs(dphi.sum(axis=0)).max() < 1e-13
+
+
+# ---- golden vectors produced by running the compiled reference pieces (tests/golden/make_golden_ref.py -> reference_pieces.json):
+# the same pins as tests/test_reference_pieces.py, available where neither oracle/_ref nor the reference tree exists ----
+def _ref_golden():
+    return json.load(open(os.path.join(GOLD, "reference_pieces.json")))
+
+
+def test_golden_cube_quadratures():
+    g = _ref_golden()
+    for key, q in g["cube_quadrature"].items():
+        dim, order = map(int, key.split(","))
+        x, w = ol.quadrature(dim, order)
+        assert len(w) == len(q["w"]) and q["exact"] >= order
+        assert np.abs(x[:, :dim] - np.array(q["x"])).max() == 0.0 and np.abs(w - np.array(q["w"])).max() <= 4e-16
+
+
+def test_golden_legendre_shape_function_sets():
+    g = _ref_golden()
+    for key, vals in g["legendre_sets"].items():
+        dim, order, hier = map(int, key.split(","))
+        sp = ol.Space([1] * dim, [0.0] * dim, [1.0] * dim, ol.DG_LEGENDRE_HIER if hier else ol.DG_LEGENDRE, order)
+        for xp, v in zip(g["points"][str(dim)], vals):
+            phi, dphi = sp.shape(xp)
+            assert np.abs(phi - np.array(v["phi"])).max() < 1e-12 * max(1.0, np.abs(v["phi"]).max())
+            assert np.abs(dphi[:, :dim] - np.array(v["dphi"])).max() < 1e-11 * max(1.0, np.abs(v["dphi"]).max())
+
+
+def test_golden_lagrange_points_basis_and_numbering():
+    g = _ref_golden()
+    for key, pts in g["lagrange_points"].items():
+        dim, order = map(int, key.split(","))
+        sp = ol.Space([1] * dim, [0.0] * dim, [1.0] * dim, ol.LAGRANGE, order)
+        assert np.abs(np.array(pts["x"]) - sp.multiindex()[:, :dim] / order).max() < 1e-15
+        for xp, v in zip(g["points"][str(dim)], g["lagrange_basis"][key]):
+            phi, dphi = sp.shape(xp)
+            assert np.abs(phi - np.array(v["phi"])).max() < 1e-13 and np.abs(dphi[:, :dim] - np.array(v["dphi"])).max() < 1e-12
+        if order == 2:          # one-element mesh: first-touch dof = offset[entity dimension] + reference sub-entity number
+            codim, sub = np.array(pts["codim"]), np.array(pts["sub"])
+            spa = ol.Space([1] * dim, [0.0] * dim, [1.0] * dim, ol.LAGRANGE, 2, numbering=ol.NUMBERING_ADAPTIVE_LEAF)
+            offset = np.concatenate([[0], np.cumsum([int((codim == dim - p).sum()) for p in range(dim + 1)])])
+            assert (spa.dofmap(0) == offset[dim - codim] + sub).all()
+        if order == 3:          # several dofs inside an entity: numbered in the order of the reference's dofNumber, contiguously
+            codim, sub, num = np.array(pts["codim"]), np.array(pts["sub"]), np.array(pts["dof"])
+            gl = sp.dofmap(0)
+            for c in range(dim + 1):
+                for s_ in np.unique(sub[codim == c]):
+                    sel = np.where((codim == c) & (sub == s_))[0]
+                    d = gl[sel][np.argsort(num[sel])]
+                    assert (np.diff(d) == 1).all()
