@@ -2,6 +2,7 @@
 // source files, where they lie under /root/reference (nothing is copied into this repository):
 //
 //   dune/fem/solver/linear/cg.hh, bicgstab.hh, gmres.hh        the Krylov loops (templates on operator / discrete function)
+//   dune/fem/operator/common/automaticdifferenceoperator.hh    the Jacobian-free linearisation (difference quotient, choice of eps)
 //   dune/fem/quadrature/gausspoints{,_implementation}.hh       the 1-D Gauss tables
 //   dune/fem/space/shapefunctionset/legendrepolynomials.{hh,cc} the Legendre coefficient table and its Horner evaluation
 //   dune/fem/space/shapefunctionset/orthonormal/orthonormalbase_{1,2,3}d.hh   the orthonormal P_k bases behind `dgonb`
@@ -21,6 +22,7 @@
 #include <cmath>
 #include <complex>   // std::real(double): dune-common pulls it in for the reference (cg.hh:64)
 #include <iostream>
+#include <memory>
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
@@ -40,6 +42,7 @@
 #include <dune/fem/space/lagrange/genericbasefunctions.hh>
 #include <dune/fem/space/shapefunctionset/legendre.hh>
 #include <dune/fem/quadrature/femquadratures.hh>
+#include <dune/fem/operator/common/automaticdifferenceoperator.hh>
 
 namespace {
 
@@ -78,6 +81,20 @@ typedef void (*ApplyFn)(const double* u, double* w, void* ctx);
 struct Op {
   ApplyFn fn; void* ctx;
   void operator()(const Vec& u, Vec& w) const { fn(u.d.data(), w.d.data(), ctx); }
+};
+
+// ---- AutomaticDifferenceOperator / AutomaticDifferenceLinearOperator (operator/common/automaticdifferenceoperator.hh:25-166):
+// the discrete function is the Vec above behind the (name, space) constructor the class uses for its temporaries
+struct SizedSpace : Space { std::size_t n = 0; };
+struct NamedVec : Vec {
+  typedef SizedSpace DiscreteFunctionSpaceType;
+  NamedVec(const std::string&, const SizedSpace& s) : Vec(s, s.n) {}
+};
+struct CallbackDifferenceOperator : Dune::Fem::AutomaticDifferenceOperator<NamedVec> {
+  ApplyFn fn; void* ctx;
+  CallbackDifferenceOperator(ApplyFn f, void* c, double eps) : Dune::Fem::AutomaticDifferenceOperator<NamedVec>(eps), fn(f), ctx(c) {}
+  CallbackDifferenceOperator(ApplyFn f, void* c) : fn(f), ctx(c) {}      // eps from the (empty) parameter file: 0 = chosen per argument
+  void operator()(const NamedVec& u, NamedVec& w) const override { fn(u.d.data(), w.d.data(), ctx); }
 };
 
 Space makeSpace(std::int64_t n, const std::int64_t* aux, std::int64_t naux) {
@@ -186,6 +203,23 @@ int ref_cg(ApplyFn apply, void* ctx, ApplyFn precon, void* pctx, std::int64_t n,
   const int k = parseHistory(os.str(), "Fem::CG it:", hist, maxHist); if (nHist) *nHist = k;
   std::memcpy(x, X.d.data(), n * 8);
   return it;
+}
+
+// AutomaticDifferenceOperator::jacobian at u, then nArgs applications of the linear operator (automaticdifferenceoperator.hh:110-166);
+// eps <= 0: the reference's dynamic choice; useParameter != 0: eps read from the parameter file (absent -> 0)
+int ref_difference_quotient(ApplyFn apply, void* ctx, std::int64_t n, const std::int64_t* aux, std::int64_t naux, const double* u,
+                            double eps, int useParameter, const double* args, int nArgs, double* dest) {
+  SizedSpace sp; static_cast<Space&>(sp) = makeSpace(n, aux, naux); sp.n = std::size_t(n);
+  NamedVec U("u", sp), A("arg", sp), D("dest", sp); std::memcpy(U.d.data(), u, n * 8);
+  std::unique_ptr<CallbackDifferenceOperator> op(useParameter ? new CallbackDifferenceOperator(apply, ctx) : new CallbackDifferenceOperator(apply, ctx, eps));
+  Dune::Fem::AutomaticDifferenceLinearOperator<NamedVec> jac("jac", sp, sp);
+  op->jacobian(U, jac);
+  for (int k = 0; k < nArgs; ++k) {
+    std::memcpy(A.d.data(), args + std::size_t(k) * n, n * 8);
+    jac(A, D);
+    std::memcpy(dest + std::size_t(k) * n, D.d.data(), n * 8);
+  }
+  return 0;
 }
 
 // LinearSolver::bicgstab (dune/fem/solver/linear/bicgstab.hh:63-214)

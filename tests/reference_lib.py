@@ -55,6 +55,8 @@ def lib():
     L.ref_legendre_set.argtypes = [C.c_int, C.c_int, C.c_int, _dp, C.c_void_p, C.c_void_p]
     L.ref_lagrange_cube_evaluate.restype = C.c_int
     L.ref_lagrange_cube_evaluate.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, _dp]
+    L.ref_difference_quotient.restype = C.c_int
+    L.ref_difference_quotient.argtypes = [APPLY_FN, C.c_void_p, C.c_int64, _lp, C.c_int64, _dp, C.c_double, C.c_int, _dp, C.c_int, _dp]
     _LIB = L
     return L
 
@@ -100,6 +102,19 @@ def gmres(apply, b, x0, tol, maxit, tolcrit=0, restart=20, aux=None):
     a = _aux(aux)
     it = lib().ref_gmres(_wrap(apply, n), None, n, a, len(a), x, np.ascontiguousarray(b, dtype=np.float64), restart, tol, maxit, tolcrit, hist, len(hist), C.byref(nh))
     return it, x, hist[:nh.value]
+
+
+def difference_quotient(apply, u, args, eps=0.0, from_parameter=False, aux=None):
+    """Dune::Fem::AutomaticDifferenceOperator::jacobian(u, jOp), then jOp(arg) for every row of args (python callable apply: u -> L[u]).
+    from_parameter: eps comes from the parameter file ("fem.differenceoperator.eps", absent -> 0 = chosen per argument)."""
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    args = np.ascontiguousarray(np.atleast_2d(args), dtype=np.float64)
+    n = len(u)
+    out = np.zeros_like(args)
+    a = _aux(aux)
+    fn = _wrap(apply, n)
+    lib().ref_difference_quotient(fn, None, n, a, len(a), u, float(eps), int(from_parameter), args, args.shape[0], out)
+    return out
 
 
 def gauss_rule(m):

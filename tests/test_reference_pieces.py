@@ -97,6 +97,27 @@ def test_gmres_restatement_is_the_reference_loop(order, restart, tolcrit):
     assert it_o == -7 and it_r in (-7, -8)
 
 
+@pytest.mark.parametrize("eps", [0.0, 1e-6])
+def test_difference_quotient_restatement_is_the_reference_operator(eps):
+    # AutomaticDifferenceOperator / AutomaticDifferenceLinearOperator (operator/common/automaticdifferenceoperator.hh:110-166) on the
+    # oracle's NON-LINEAR operator (gamma u^3): same epsilon rule, same order of operations -> bit-identical
+    sp = ol.Space([5, 4, 3], [0.0] * 3, [1.0] * 3, ol.LAGRANGE, 2)
+    op = ol.Operator(sp, eps=1.0, c=0.5, gamma=2.0, data=2, dirichlet_mask=0b111111, strong_dirichlet=True)
+    rng = np.random.default_rng(5)
+    u = rng.uniform(-1, 1, sp.size)
+    args = np.stack([rng.uniform(-1, 1, sp.size), 1e-9 * rng.uniform(-1, 1, sp.size), 1e4 * rng.uniform(-1, 1, sp.size), np.zeros(sp.size)])
+    ref = rl.difference_quotient(lambda v: op.apply(v), u, args, eps=eps)
+    op.linearize(u, eps)
+    for a, r in zip(args, ref):
+        np.testing.assert_array_equal(op.applyJacobian(a)[0], r)
+    # the reference's default comes from the parameter file; absent -> 0 -> the dynamic choice (automaticdifferenceoperator.hh:99-101)
+    if eps == 0.0:
+        np.testing.assert_array_equal(rl.difference_quotient(lambda v: op.apply(v), u, args, from_parameter=True), ref)
+    # the quotient approximates the derivative of the cubic term
+    lin = op.apply(u + 1e-7 * args[0]) - op.apply(u)
+    assert np.abs(ref[0] - lin / 1e-7).max() < 1e-5 * np.abs(ref[0]).max()
+
+
 def test_gauss_rules_are_the_reference_tables():
     lib = rl.lib()
     assert lib.ref_gauss_maxp() == 10
