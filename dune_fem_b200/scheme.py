@@ -81,7 +81,7 @@ class GalerkinScheme:
             it = inv(np.ascontiguousarray(b), target)
             return {"converged": it >= 0, "iterations": 1, "linear_iterations": abs(it)}
         newton = _solver.NewtonInverseOperator({"tolerance": p.get("tolerance", 1e-6), "maxiterations": p.get("maxiterations", 2 ** 31 - 1),
-                                                "linesearch.method": p.get("linesearch.method", "none"), "verbose": p.get("verbose", False),
+                                                "linesearch.method": p.get("linesearch", p.get("linesearch.method", "none")), "verbose": p.get("verbose", False),
                                                 "linear.method": self._method, "linear.tolerance": p.get("linear.tolerance", 1e-8),
                                                 "linear.errormeasure": p.get("linear.errormeasure", "absolute"),
                                                 "linear.maxiterations": p.get("linear.maxiterations", 1000), "linear.gmres.restart": p.get("linear.gmres.restart", 20)})

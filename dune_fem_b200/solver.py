@@ -105,8 +105,10 @@ def KrylovInverseOperator(parameters=None):
 
 class NewtonInverseOperator:
     """Dune::Fem::NewtonInverseOperator (solver/newtoninverseoperator.hh:423-803): bind(op); __call__(u, w) solves L[w] = u from the
-    initial guess in w (u = None: L[w] = 0).  Parameters as fem.solver.nonlinear.*: tolerance (1e-6), maxiterations, linesearch.method
-    ("none" | "simple"), linear.{method, tolerance, errormeasure, maxiterations, gmres.restart}.  The Jacobian is the difference
+    initial guess in w (u = None: L[w] = 0).  Parameters as fem.solver.nonlinear.*: tolerance (1e-6), maxiterations, linesearch
+    ("none" | "simple"; "linesearch.method" is accepted too), and for the linear solves fem.solver.linear.* (the prefix the reference derives,
+    :163-165; "nonlinear.linear.*" is accepted too): method, tolerance (1e-8), errormeasure ("absolute"), maxiterations, gmres.restart (20).
+    Deviation: the total linear-iteration budget defaults to 1000 here, to `int` max in the reference (solver/parameter.hh:150).  The Jacobian is the difference
     quotient of AutomaticDifferenceLinearOperator; the whole iteration runs on the device (b200fem_newton_solve)."""
     _METHODS = {"cg": 0, "bicgstab": 1, "gmres": 2}
     FAILURES = {0: "Success", 1: "InvalidResidual", 4: "LineSearchFailed", 5: "TooManyIterations", 6: "TooManyLinearIterations", 7: "LinearSolverFailed"}
@@ -115,7 +117,10 @@ class NewtonInverseOperator:
         p = {"tolerance": 1e-6, "maxiterations": 2 ** 31 - 1, "linesearch.method": "none", "verbose": False,
              "linear.method": "gmres", "linear.tolerance": 1e-8, "linear.errormeasure": "absolute", "linear.maxiterations": 1000, "linear.gmres.restart": 20}
         for k, v in (parameters or {}).items():
-            p[k.replace("fem.solver.", "").replace("nonlinear.", "")] = v
+            k = k.replace("fem.solver.", "").replace("nonlinear.", "")
+            if k in ("linesearch", "lineSearch"):       # the key the reference reads (newtoninverseoperator.hh:279-285): values "none" | "simple"
+                k = "linesearch.method"
+            p[k] = v
         self.parameters = p
         self._op = None
         self.iterations = self.linearIterations = 0

@@ -3,6 +3,8 @@
 //
 //   dune/fem/solver/linear/cg.hh, bicgstab.hh, gmres.hh        the Krylov loops (templates on operator / discrete function)
 //   dune/fem/operator/common/automaticdifferenceoperator.hh    the Jacobian-free linearisation (difference quotient, choice of eps)
+//   dune/fem/solver/newtoninverseoperator.hh, solver/parameter.hh   the Newton loop (line search, Eisenstat-Walker forcing, failure
+//                                                              codes, shared linear-iteration budget) and the parameter keys it reads
 //   dune/fem/quadrature/gausspoints{,_implementation}.hh       the 1-D Gauss tables
 //   dune/fem/space/shapefunctionset/legendrepolynomials.{hh,cc} the Legendre coefficient table and its Horner evaluation
 //   dune/fem/space/shapefunctionset/orthonormal/orthonormalbase_{1,2,3}d.hh   the orthonormal P_k bases behind `dgonb`
@@ -22,6 +24,7 @@
 #include <cmath>
 #include <complex>   // std::real(double): dune-common pulls it in for the reference (cg.hh:64)
 #include <iostream>
+#include <map>
 #include <memory>
 #include <cstddef>
 #include <cstdint>
@@ -31,6 +34,7 @@
 #include <string>
 #include <vector>
 
+#include <dune/fem/space/common/auxiliarydofs.hh>   // stand-in: forEachPrimaryDof
 #include <dune/fem/solver/linear/cg.hh>
 #include <dune/fem/solver/linear/bicgstab.hh>
 #include <dune/fem/solver/linear/gmres.hh>
@@ -43,6 +47,7 @@
 #include <dune/fem/space/shapefunctionset/legendre.hh>
 #include <dune/fem/quadrature/femquadratures.hh>
 #include <dune/fem/operator/common/automaticdifferenceoperator.hh>
+#include <dune/fem/solver/newtoninverseoperator.hh>
 
 namespace {
 
@@ -89,12 +94,56 @@ struct SizedSpace : Space { std::size_t n = 0; };
 struct NamedVec : Vec {
   typedef SizedSpace DiscreteFunctionSpaceType;
   NamedVec(const std::string&, const SizedSpace& s) : Vec(s, s.n) {}
+  const SizedSpace& space() const { return static_cast<const SizedSpace&>(*sp); }
 };
 struct CallbackDifferenceOperator : Dune::Fem::AutomaticDifferenceOperator<NamedVec> {
   ApplyFn fn; void* ctx;
   CallbackDifferenceOperator(ApplyFn f, void* c, double eps) : Dune::Fem::AutomaticDifferenceOperator<NamedVec>(eps), fn(f), ctx(c) {}
   CallbackDifferenceOperator(ApplyFn f, void* c) : fn(f), ctx(c) {}      // eps from the (empty) parameter file: 0 = chosen per argument
   void operator()(const NamedVec& u, NamedVec& w) const override { fn(u.d.data(), w.d.data(), ctx); }
+};
+
+// ---- NewtonInverseOperator< JacobianOperator, LInvOp > (solver/newtoninverseoperator.hh:418-803) around the two classes above.
+// Jacobian operator: the reference's difference quotient behind the four-argument constructor the loop uses (:703)
+struct DifferenceJacobian : Dune::Fem::AutomaticDifferenceLinearOperator<NamedVec> {
+  typedef Dune::Fem::AutomaticDifferenceLinearOperator<NamedVec> Base;
+  DifferenceJacobian(const std::string& name, const SizedSpace& d, const SizedSpace& r, const Dune::Fem::SolverParameter&) : Base(name, d, r) {}
+  using Base::set;      // (a friend of the base class only; AutomaticDifferenceOperator< ..., DifferenceJacobian > calls it)
+};
+struct CallbackDifferentiableOperator : Dune::Fem::AutomaticDifferenceOperator<NamedVec, NamedVec, DifferenceJacobian> {
+  ApplyFn fn; void* ctx; bool nonlin;
+  CallbackDifferentiableOperator(ApplyFn f, void* c, bool nl) : fn(f), ctx(c), nonlin(nl) {}
+  void operator()(const NamedVec& u, NamedVec& w) const override { fn(u.d.data(), w.d.data(), ctx); }
+  bool nonlinear() const override { return nonlin; }
+};
+// Linear inverse operator: the slice of KrylovInverseOperator the Newton loop touches (solver/krylovinverseoperators.hh:120-205 -- the
+// header itself needs function/common/discretefunction.hh): method, tolerance, budget and criterion come from the reference's
+// SolverParameter, the loops are the reference's LinearSolver::{cg,bicgstab,gmres} with the temporaries laid out as there
+struct RefKrylov {
+  typedef Dune::Fem::SolverParameter SolverParameterType;
+  std::shared_ptr<SolverParameterType> par; const DifferenceJacobian* op = nullptr; int method; mutable int its = 0;
+  explicit RefKrylov(const SolverParameterType& p) : par(p.clone()) {
+    method = par->solverMethod({SolverParameterType::gmres, SolverParameterType::bicgstab, SolverParameterType::cg});   // the default list of :97
+  }
+  SolverParameterType& parameter() const { return *par; }
+  void bind(const DifferenceJacobian& j) { op = &j; }
+  void unbind() { op = nullptr; }
+  void setMaxIterations(int n) { par->setMaxIterations(n); }
+  int iterations() const { return its; }
+  void operator()(const NamedVec& u, NamedVec& w) const {
+    const SizedSpace& sp = u.space();
+    const DifferenceJacobian* none = nullptr;
+    if (method == SolverParameterType::gmres) {
+      std::vector<NamedVec> v(par->gmresRestart() + 1, NamedVec("GMRes::v", sp));
+      its = Dune::Fem::LinearSolver::gmres(*op, none, v, w, u, par->gmresRestart(), par->tolerance(), par->maxIterations(), par->errorMeasure(), (std::ostream*)nullptr);
+    } else if (method == SolverParameterType::bicgstab) {
+      std::vector<NamedVec> v(5, NamedVec("BiCGStab::r", sp));
+      its = Dune::Fem::LinearSolver::bicgstab(*op, none, v, w, u, par->tolerance(), par->maxIterations(), par->errorMeasure(), (std::ostream*)nullptr);
+    } else {
+      std::vector<NamedVec> v(3, NamedVec("CG::h", sp));
+      its = Dune::Fem::LinearSolver::cg(*op, none, v, w, u, par->tolerance(), par->maxIterations(), par->errorMeasure(), (std::ostream*)nullptr);
+    }
+  }
 };
 
 Space makeSpace(std::int64_t n, const std::int64_t* aux, std::int64_t naux) {
@@ -220,6 +269,31 @@ int ref_difference_quotient(ApplyFn apply, void* ctx, std::int64_t n, const std:
     std::memcpy(dest + std::size_t(k) * n, D.d.data(), n * 8);
   }
   return 0;
+}
+
+// NewtonInverseOperator::operator()(u, w) (solver/newtoninverseoperator.hh:690-803) on a callback operator, configured like the reference
+// is: through parameter KEYS ("fem.solver.nonlinear.tolerance", "...linear.method", ... ; keys / values = '\n'-separated "key: value" lines).
+// out = {iterations, linearIterations, failure code (NewtonFailure, :389-400)}, *residual = |L[w] - u| of the last iterate.
+int ref_newton(ApplyFn apply, void* ctx, int nonlinear, std::int64_t n, const std::int64_t* aux, std::int64_t naux, const double* u, double* w,
+               const char* parameters, int* out, double* residual) {
+  std::map<std::string, std::string>& table = Dune::Fem::RefShim::table();
+  table.clear();
+  { std::istringstream in(parameters ? parameters : ""); std::string line;
+    while (std::getline(in, line)) { const std::size_t c = line.find(": "); if (c != std::string::npos) table[line.substr(0, c)] = line.substr(c + 2); } }
+  int rc = 0;
+  try {
+    SizedSpace sp; static_cast<Space&>(sp) = makeSpace(n, aux, naux); sp.n = std::size_t(n);
+    NamedVec U("u", sp), W("w", sp); if (u) std::memcpy(U.d.data(), u, n * 8); std::memcpy(W.d.data(), w, n * 8);
+    CallbackDifferentiableOperator op(apply, ctx, nonlinear != 0);
+    Dune::Fem::NewtonInverseOperator<DifferenceJacobian, RefKrylov> newton;      // everything from the parameter table, as FemScheme does
+    newton.bind(op);
+    newton(U, W);
+    out[0] = newton.iterations(); out[1] = newton.linearIterations(); out[2] = (int)newton.failed(); *residual = newton.residual();
+    newton.unbind();
+    std::memcpy(w, W.d.data(), n * 8);
+  } catch (const std::exception& e) { std::cerr << "ref_newton: " << e.what() << std::endl; rc = 1; }
+  table.clear();
+  return rc;
 }
 
 // LinearSolver::bicgstab (dune/fem/solver/linear/bicgstab.hh:63-214)

@@ -342,6 +342,77 @@ class VectorUserOperator:
 
 
 
+def newton(oop, w0, tol, maxit, lin_tol, lin_maxit, restart=20, tolcrit=0, line_search=False, u=None, nonlinear=True, trace=None):
+    """NewtonInverseOperator::operator() and ::lineSearch (solver/newtoninverseoperator.hh:690-803, 588-629) restated on the oracle's
+    pieces: difference-quotient Jacobian (Operator.linearize), GMRES on it, forcing "none".  Pinned against the reference's own class in
+    tests/test_reference_pieces.py.  Returns (iterations, linearIterations, NewtonFailure code, |residual|, w);
+    trace (a list) receives the number of halvings the line search took in every step."""
+    big = np.finfo(np.float64).max
+
+    def failed(delta, it, lit, completed):                     # :568-584
+        if not (delta < big) or np.isnan(delta):
+            return 1
+        if it >= maxit:
+            return 5
+        if lit >= lin_maxit:
+            return 6
+        if lit < 0:
+            return 7
+        return 0 if completed else 4
+
+    def residual(w):
+        r = oop.apply(w)
+        return r if u is None else r - u
+
+    w = np.array(w0, dtype=np.float64, copy=True)
+    res = residual(w)
+    delta = np.sqrt(res @ res)
+    it = lit = 0
+    completed = True
+    while True:
+        oop.linearize(w)
+        if lin_maxit - lit <= 0:
+            break
+        li, dw, _ = oop.gmres_jacobian(res, np.zeros_like(w), lin_tol, lin_maxit - lit, tolcrit, restart)
+        if li < 0:
+            lit = li
+            break
+        lit += li
+        w -= dw
+        if not nonlinear:
+            break
+        res = residual(w)
+        delta_old, delta, ls, halvings = delta, np.sqrt(res @ res), 0, 0
+        if line_search:
+            if failed(delta, it, lit, completed) == 1:
+                test = dw @ dw
+                if not (test < big and not np.isnan(test)):
+                    delta = 2.0 * delta_old
+            factor, ls = 1.0, (1 if delta < delta_old else 0)
+            while delta >= delta_old:
+                delta_prev = delta
+                factor *= 0.5
+                if abs(delta - delta_old) < 1e-5 * delta:
+                    ls = -1
+                    break
+                w += factor * dw
+                res = residual(w)
+                delta = np.sqrt(res @ res)
+                halvings += 1
+                if abs(delta - delta_prev) < 1e-15:
+                    ls = -1
+                    break
+                if failed(delta, it, lit, completed) == 1:
+                    delta = 2.0 * delta_old
+        if trace is not None:
+            trace.append(halvings)
+        completed = ls >= 0
+        it += 1
+        if delta < tol or failed(delta, it, lit, completed) != 0:
+            break
+    return it, lit, failed(delta, it, lit, completed), delta, w
+
+
 def cartesian_as_unstructured(n, lo, hi):
     """vertex coordinates and element -> vertex arrays (cube reference order, elements x fastest) of a Cartesian mesh"""
     dim = len(n)

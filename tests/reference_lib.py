@@ -57,6 +57,9 @@ def lib():
     L.ref_lagrange_cube_evaluate.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, _dp]
     L.ref_difference_quotient.restype = C.c_int
     L.ref_difference_quotient.argtypes = [APPLY_FN, C.c_void_p, C.c_int64, _lp, C.c_int64, _dp, C.c_double, C.c_int, _dp, C.c_int, _dp]
+    L.ref_newton.restype = C.c_int
+    L.ref_newton.argtypes = [APPLY_FN, C.c_void_p, C.c_int, C.c_int64, _lp, C.c_int64, C.c_void_p, _dp, C.c_char_p, np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS"),
+                             C.POINTER(C.c_double)]
     _LIB = L
     return L
 
@@ -115,6 +118,24 @@ def difference_quotient(apply, u, args, eps=0.0, from_parameter=False, aux=None)
     fn = _wrap(apply, n)
     lib().ref_difference_quotient(fn, None, n, a, len(a), u, float(eps), int(from_parameter), args, args.shape[0], out)
     return out
+
+
+def newton(apply, w0, parameters, u=None, nonlinear=True, aux=None):
+    """Dune::Fem::NewtonInverseOperator (Jacobian = the reference's difference quotient, linear solves = the reference's Krylov loops)
+    on a python callable, configured through the reference's parameter KEYS (dict, e.g. {"fem.solver.nonlinear.tolerance": 1e-7}).
+    Returns (iterations, linearIterations, failure code, |residual|, w)."""
+    w = np.array(w0, dtype=np.float64, copy=True)
+    n = len(w)
+    a = _aux(aux)
+    fn = _wrap(apply, n)
+    text = "\n".join(f"{k}: {str(v).lower() if isinstance(v, bool) else repr(float(v)) if isinstance(v, float) else v}" for k, v in parameters.items())
+    out = np.zeros(3, dtype=np.int32)
+    res = C.c_double()
+    uu = None if u is None else np.ascontiguousarray(u, dtype=np.float64)
+    rc = lib().ref_newton(fn, None, int(nonlinear), n, a, len(a), None if uu is None else uu.ctypes.data_as(C.c_void_p), w, text.encode(), out, C.byref(res))
+    if rc != 0:
+        raise RuntimeError("the reference's Newton solver raised an exception (see stderr)")
+    return int(out[0]), int(out[1]), int(out[2]), res.value, w
 
 
 def gauss_rule(m):

@@ -140,3 +140,31 @@ def test_newton_inverse_operator(builtin):
     w = np.zeros(space.size)
     newton(None, w)
     assert not newton.converged and newton.failure in (6, 7)
+
+
+def test_newton_line_search():
+    """NewtonInverseOperator::lineSearch ("simple", newtoninverseoperator.hh:588-629) on the device against the restatement that
+    tests/test_reference_pieces.py pins to the reference's own class: an indefinite reaction term (c < 0) makes full Newton steps overshoot,
+    the search halves the step in iterations 4 and 6 (the case is stable under 1e-7 perturbations of the initial guess: same iteration
+    count and halvings) and the iteration count differs from plain Newton's."""
+    n, lo, hi = [3, 3, 2], [-1.0] * 3, [1.0] * 3
+    space = fem.space.dglegendre(fem.structuredGrid(lo, hi, n), order=1)
+    osp = ol.Space(n, lo, hi, ol.DG_LEGENDRE_HIER, 1)
+    kw = dict(eps=0.5, b=(1.0, 0.0, 0.0), c=-8.0, gamma=5.0, beta=40.0, dirichlet_mask=0b000011, data=1)
+    op, oop = fem.operator.galerkin(space, **kw), ol.Operator(osp, skeleton=True, boundary=True, **kw)
+    w0 = 2.0 * np.random.default_rng(4).uniform(-1, 1, space.size)
+    counts = {}
+    for search in ("simple", "none"):
+        trace = []
+        it, lit, fail, delta, w_ref = ol.newton(oop, w0, 1e-7, 40, 1e-8, 20000, 48, 2, search == "simple", trace=trace)
+        assert fail == 0 and (sum(trace) >= 1) == (search == "simple")
+        newton = fem.solver.NewtonInverseOperator({"tolerance": 1e-7, "maxiterations": 40, "linesearch": search, "linear.method": "gmres", "linear.tolerance": 1e-8,
+                                                   "linear.errormeasure": "residualreduction", "linear.maxiterations": 20000, "linear.gmres.restart": 48})
+        newton.bind(op)
+        w = w0.copy()
+        newton(None, w)
+        assert newton.converged and newton.iterations == it
+        assert abs(newton.linearIterations - lit) <= max(5, lit // 10)
+        assert newton.residual < 1e-7 and rel(w, w_ref) < 1e-6
+        counts[search] = it
+    assert counts["simple"] != counts["none"]

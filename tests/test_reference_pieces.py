@@ -118,6 +118,72 @@ def test_difference_quotient_restatement_is_the_reference_operator(eps):
     assert np.abs(ref[0] - lin / 1e-7).max() < 1e-5 * np.abs(ref[0]).max()
 
 
+def _newton_keys(tol, maxit, lin_tol, lin_maxit, restart, line_search, errormeasure="residualreduction"):
+    # the keys the reference reads (newtoninverseoperator.hh:163-170, 206, 234, 285; solver/parameter.hh:96-186): the linear solver's
+    # live under "fem.solver.linear." when the Newton parameters are built from a parameter reader
+    return {"fem.solver.nonlinear.tolerance": tol, "fem.solver.nonlinear.maxiterations": maxit, "fem.solver.nonlinear.linesearch": "simple" if line_search else "none",
+            "fem.solver.linear.method": "gmres", "fem.solver.linear.tolerance": lin_tol, "fem.solver.linear.errormeasure": errormeasure,
+            "fem.solver.linear.maxiterations": lin_maxit, "fem.solver.linear.gmres.restart": restart}
+
+
+def _reaction_diffusion(gamma, c):
+    sp = ol.Space([3, 3, 2], [-1.0] * 3, [1.0] * 3, ol.DG_LEGENDRE_HIER, 1)
+    return sp, ol.Operator(sp, skeleton=True, boundary=True, eps=0.5, b=(1.0, 0.0, 0.0), c=c, gamma=gamma, beta=40.0, dirichlet_mask=0b000011, data=1)
+
+
+def test_newton_restatement_of_the_gpu_tests_is_the_reference_loop():
+    # the configuration and the restatement tests/test_gpu_jit.py::test_newton_inverse_operator checks the device against, here against
+    # Dune::Fem::NewtonInverseOperator itself (difference-quotient Jacobian and GMRES of the reference, oracle operator through callbacks)
+    from test_gpu_jit import _oracle_newton
+    sp = ol.Space([4, 4, 3], [-1.0] * 3, [1.0] * 3, ol.DG_LEGENDRE_HIER, 2)
+    op = ol.Operator(sp, skeleton=True, boundary=True, eps=0.5, b=(1.0, 0.0, 0.0), c=1.0, gamma=2.0, beta=80.0, dirichlet_mask=0b000011, data=1)
+    it, lit, delta, w = _oracle_newton(op, np.zeros(sp.size), 1e-7, 2 ** 31 - 1, 1e-7, 4000, 30)
+    it_r, lit_r, fail_r, delta_r, w_r = rl.newton(lambda v: op.apply(v), np.zeros(sp.size), _newton_keys(1e-7, 2 ** 31 - 1, 1e-7, 4000, 30, False))
+    assert (it, lit) == (it_r, lit_r) and fail_r == 0 and 2 <= it <= 12
+    assert delta == delta_r
+    np.testing.assert_array_equal(w, w_r)
+    assert ol.newton(op, np.zeros(sp.size), 1e-7, 2 ** 31 - 1, 1e-7, 4000, 30, 2)[:4] == (it_r, lit_r, 0, delta_r)
+
+
+@pytest.mark.parametrize("gamma,amp,c,seed,line_search,maxit,failure", [
+    (10.0, 2.0, -8.0, 4, False, 40, 0),      # plain Newton
+    (10.0, 2.0, -8.0, 4, True, 40, 0),       # the line search halves the step in iterations 5 and 6 and saves 8 iterations
+    (5.0, 4.0, -8.0, 4, True, 3, 5),         # NewtonFailure::TooManyIterations
+    (10.0, 2.0, -12.0, 3, True, 40, 7),      # NewtonFailure::LinearSolverFailed (budget shared by all steps, :745-757)
+])
+def test_newton_line_search_and_failure_codes_are_the_reference_ones(gamma, amp, c, seed, line_search, maxit, failure):
+    sp, op = _reaction_diffusion(gamma, c)
+    w0 = amp * np.random.default_rng(seed).uniform(-1, 1, sp.size)
+    it_r, lit_r, fail_r, delta_r, w_r = rl.newton(lambda v: op.apply(v), w0, _newton_keys(1e-7, maxit, 1e-8, 20000, 48, line_search))
+    trace = []
+    it, lit, fail, delta, w = ol.newton(op, w0, 1e-7, maxit, 1e-8, 20000, 48, 2, line_search, trace=trace)
+    assert (it, fail) == (it_r, fail_r) and fail == failure
+    # the reference GMRES reports -(maxIterations + 1) where oracle and device report -maxIterations
+    assert lit == lit_r or (fail == 7 and lit == lit_r + 1)
+    np.testing.assert_allclose(delta, delta_r, rtol=1e-12)
+    np.testing.assert_allclose(w, w_r, rtol=0, atol=1e-12 * np.abs(w_r).max())
+    if line_search and maxit == 40:
+        assert max(trace) >= 1
+
+
+def test_newton_on_a_linear_operator_and_with_a_right_hand_side():
+    # op_->nonlinear() == false: one step, no residual re-evaluation, iterations() stays 0 (:761, 791-792); u != 0: solves L[w] = u
+    sp, op = _reaction_diffusion(0.0, 1.0)
+    u = np.random.default_rng(8).uniform(-1, 1, sp.size)
+    it_r, lit_r, fail_r, delta_r, w_r = rl.newton(lambda v: op.apply(v), np.zeros(sp.size), _newton_keys(1e-8, 10, 1e-7, 5000, 30, False, "relative"), u=u, nonlinear=False)
+    it, lit, fail, delta, w = ol.newton(op, np.zeros(sp.size), 1e-8, 10, 1e-7, 5000, 30, 1, u=u, nonlinear=False)
+    assert (it, lit, fail) == (it_r, lit_r, fail_r) and it == 0 and lit > 0
+    np.testing.assert_allclose(delta, delta_r, rtol=1e-13)     # still the INITIAL residual norm (numpy sums in another order)
+    np.testing.assert_allclose(w, w_r, rtol=0, atol=1e-13 * np.abs(w_r).max())
+    assert np.abs(op.apply(w) - u).max() < 1e-5
+    # the defaults of the reference when no key is given: tolerance 1e-6, linear tolerance 1e-8 absolute, method gmres (first of the list), restart 20
+    sp, op = _reaction_diffusion(2.0, 1.0)
+    it_r, lit_r, fail_r, delta_r, w_r = rl.newton(lambda v: op.apply(v), np.zeros(sp.size), {})
+    it, lit, fail, delta, w = ol.newton(op, np.zeros(sp.size), 1e-6, 2 ** 31 - 1, 1e-8, 2 ** 31 - 1, 20, 0)
+    assert (it, lit, fail) == (it_r, lit_r, fail_r) and fail == 0
+    np.testing.assert_allclose(w, w_r, rtol=0, atol=1e-13 * np.abs(w_r).max())
+
+
 def test_gauss_rules_are_the_reference_tables():
     lib = rl.lib()
     assert lib.ref_gauss_maxp() == 10
