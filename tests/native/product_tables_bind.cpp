@@ -1,0 +1,28 @@
+// tests/native/product_tables_bind.cpp -- TEST INFRASTRUCTURE.  C bindings around the PRODUCT's own host tables
+// (dune_fem_b200/csrc/tables.hpp: the Gauss rules, the rule selection, the Legendre / Lagrange 1-D bases and the local numbering of the
+// DG spaces -- the header capi.cu / launch_*.cu build the device tables from), so that tests/test_product_tables.py can check them on
+// the CPU against the vectors the compiled reference produced (tests/golden/reference_pieces.json) without going through the oracle.
+// Built by the test with g++ (host code only, no CUDA).
+#include <cstdint>
+#include "../../dune_fem_b200/csrc/tables.hpp"
+
+extern "C" {
+int pt_gauss_points_for_order(int order) { try { return b200fem::gauss_points_for_order(order); } catch (...) { return -1; } }
+void pt_gauss_rule(int m, double* x, double* w) { const b200fem::Rule1D r = b200fem::gauss_rule(m); for (int i = 0; i < m; ++i) { x[i] = r.x[i]; w[i] = r.w[i]; } }
+// what the kernels read: values B[q*n+i], derivatives G[q*n+i] of the n = order+1 functions at the m rule points
+void pt_tabulate_1d(int legendre, int order, int m, double* B, double* G) {
+  const b200fem::Tab1D t = b200fem::tabulate_1d(legendre ? b200fem::Basis::Legendre : b200fem::Basis::Lagrange, order, m);
+  for (std::size_t i = 0; i < t.B.size(); ++i) { B[i] = t.B[i]; G[i] = t.G[i]; }
+}
+double pt_basis_1d(int legendre, int order, int i, double x, int derivative) {
+  static const b200fem::Legendre1D leg;
+  if (legendre) return derivative ? leg.derivative(i, x) : leg.value(i, x);
+  return derivative ? b200fem::lagrange_derivative(order, i, x) : b200fem::lagrange_value(order, i, x);
+}
+// map[(m0*n + m1)*n + m2] = stored local index or -1; returns the number of local dofs
+int pt_dg_tensor_map(int dim, int order, int kind, int32_t* map) {
+  int nb = 0; const std::vector<int> m = b200fem::dg_tensor_map(dim, order, kind, &nb);
+  for (std::size_t i = 0; i < m.size(); ++i) map[i] = m[i];
+  return nb;
+}
+}

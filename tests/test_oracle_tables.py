@@ -148,3 +148,16 @@ def test_golden_lagrange_points_basis_and_numbering():
                     sel = np.where((codim == c) & (sub == s_))[0]
                     d = gl[sel][np.argsort(num[sel])]
                     assert (np.diff(d) == 1).all()
+
+
+def test_golden_dgonb_functions():
+    g = _ref_golden()
+    for key, vals in g["onb"].items():
+        dim, kmax = map(int, key.split(","))
+        for order in range(1, kmax + 1):        # P_k bases are nested: the first functions of the P_4 vectors
+            sp = ol.Space([1] * dim, [0.0] * dim, [1.0] * dim, ol.DG_ONB, order)
+            for xp, v in zip(g["points"][str(dim)], vals):
+                phi, dphi = sp.shape(xp)
+                nb = sp.local_size
+                assert np.abs(phi - np.array(v["phi"][:nb])).max() < 1e-12 * max(1.0, np.abs(v["phi"][:nb]).max())
+                assert np.abs(dphi[:, :dim] - np.array(v["dphi"][:nb])[:, :dim]).max() < 1e-11 * max(1.0, np.abs(v["dphi"][:nb]).max())

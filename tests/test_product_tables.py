@@ -1,0 +1,152 @@
+"""The PRODUCT's own host tables (dune_fem_b200/csrc/tables.hpp -- Gauss rules, rule selection, 1-D Legendre / Lagrange bases, local
+numbering of the DG spaces; the header the device tables are built from) against the vectors the compiled reference produced
+(tests/golden/reference_pieces.json, made by tests/golden/make_golden_ref.py from oracle/_ref) and against the reference's Gauss table
+(tests/golden/gauss_points.json).  CPU only, no oracle in between: tests/native/product_tables_bind.cpp is compiled with g++ here."""
+import ctypes as C
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLD = os.path.join(HERE, "golden")
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+
+
+@pytest.fixture(scope="module")
+def pt():
+    src = os.path.join(HERE, "native", "product_tables_bind.cpp")
+    out = os.path.join(ROOT, "build", "product_tables.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    deps = [src, os.path.join(ROOT, "dune_fem_b200", "csrc", "tables.hpp")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        tmp = f"{out}.{os.getpid()}"
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-o", tmp, src])
+        os.replace(tmp, out)
+    L = C.CDLL(out)
+    L.pt_gauss_rule.argtypes = [C.c_int, _dp, _dp]
+    L.pt_tabulate_1d.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp]
+    L.pt_basis_1d.restype = C.c_double
+    L.pt_basis_1d.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_int]
+    L.pt_dg_tensor_map.argtypes = [C.c_int, C.c_int, C.c_int, np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")]
+    return L
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return json.load(open(os.path.join(GOLD, "reference_pieces.json")))
+
+
+def _rule(pt, m):
+    x, w = np.zeros(m), np.zeros(m)
+    pt.pt_gauss_rule(m, x, w)
+    return x, w
+
+
+def test_gauss_rules_are_the_reference_table(pt):
+    table = json.load(open(os.path.join(GOLD, "gauss_points.json")))
+    for m, rule in table.items():
+        x, w = _rule(pt, int(m))
+        np.testing.assert_allclose(x, rule["x"], rtol=0, atol=2.3e-16)
+        np.testing.assert_allclose(w, rule["w"], rtol=0, atol=2.3e-16)
+
+
+def test_rule_selection_and_tensor_rules_are_the_reference_cube_quadratures(pt, gold):
+    # CubeQuadrature (femquadratures_inline.hh:59-110): smallest rule with 2m-1 >= order, tensor product with x0 fastest -- the kernels
+    # build exactly this from the 1-D rule (quadrature point q = (q2*m + q1)*m + q0)
+    for key, q in gold["cube_quadrature"].items():
+        dim, order = map(int, key.split(","))
+        m = pt.pt_gauss_points_for_order(order)
+        x1, w1 = _rule(pt, m)
+        assert m ** dim == len(q["w"]) and 2 * m - 1 == q["exact"]
+        idx = np.indices((m,) * dim).reshape(dim, -1)[::-1].T          # column d = index along axis d, axis 0 fastest
+        np.testing.assert_array_equal(x1[idx], np.array(q["x"]).reshape(-1, dim))
+        np.testing.assert_allclose(np.prod(w1[idx], axis=1), q["w"], rtol=0, atol=4e-16)
+    assert pt.pt_gauss_points_for_order(20) == -1                      # beyond the reference's table (MAXP = 10)
+
+
+@pytest.mark.parametrize("hier", [0, 1])
+def test_dg_legendre_spaces_hold_the_reference_functions_in_the_reference_order(pt, gold, hier):
+    # LegendreShapeFunctionSet< FunctionSpace, hierarchical > (shapefunctionset/legendre.hh): function l of the set at a point ==
+    # product of the product's 1-D polynomials for the multi-index dg_tensor_map stores at l
+    for key, vals in gold["legendre_sets"].items():
+        dim, order, h = map(int, key.split(","))
+        if h != hier:
+            continue
+        n = order + 1
+        tmap = np.full(n ** 3, -2, dtype=np.int32)
+        nb = pt.pt_dg_tensor_map(dim, order, 2 if hier else 1, tmap)
+        assert nb == n ** dim == len(vals[0]["phi"]) and sorted(tmap[tmap >= 0]) == list(range(nb))
+        for xp, v in zip(gold["points"][str(dim)], vals):
+            phi, dphi = np.zeros(nb), np.zeros((nb, dim))
+            for t in np.where(tmap >= 0)[0]:
+                mi = [t // (n * n), (t // n) % n, t % n]
+                assert all(mi[d] == 0 for d in range(dim, 3))          # 2-D spaces: constant along the third axis
+                f = [pt.pt_basis_1d(1, order, mi[d], xp[d], 0) for d in range(dim)]
+                g = [pt.pt_basis_1d(1, order, mi[d], xp[d], 1) for d in range(dim)]
+                phi[tmap[t]] = np.prod(f)
+                for d in range(dim):
+                    dphi[tmap[t], d] = np.prod([g[e] if e == d else f[e] for e in range(dim)])
+            assert np.abs(phi - np.array(v["phi"])).max() <= 1e-13 * max(1.0, np.abs(v["phi"]).max())
+            assert np.abs(dphi - np.array(v["dphi"])).max() <= 1e-12 * max(1.0, np.abs(v["dphi"]).max())
+
+
+def test_dgonb_spaces_hold_the_reference_functions_in_the_reference_order(pt, gold):
+    # OrthonormalBase_{2,3}D (orthonormal/orthonormalbase_{2,3}d.hh): on cubes the graded P_k basis is a sub-basis of the tensor Legendre
+    # basis; P_k bases are nested, so the P_4 vectors cover orders 1..4
+    for key, vals in gold["onb"].items():
+        dim, kmax = map(int, key.split(","))
+        for order in range(1, kmax + 1):
+            n = order + 1
+            tmap = np.full(n ** 3, -2, dtype=np.int32)
+            nb = pt.pt_dg_tensor_map(dim, order, 3, tmap)
+            assert nb == ((order + 1) * (order + 2) // 2 if dim == 2 else (order + 1) * (order + 2) * (order + 3) // 6)
+            for xp, v in zip(gold["points"][str(dim)], vals):
+                for t in np.where(tmap >= 0)[0]:
+                    mi = [t // (n * n), (t // n) % n, t % n]
+                    assert sum(mi) <= order
+                    f = [pt.pt_basis_1d(1, order, mi[d], xp[d], 0) for d in range(dim)]
+                    g = [pt.pt_basis_1d(1, order, mi[d], xp[d], 1) for d in range(dim)]
+                    ref_phi, ref_dphi = v["phi"][tmap[t]], np.array(v["dphi"][tmap[t]])[:dim]
+                    assert abs(np.prod(f) - ref_phi) < 1e-12 * max(1.0, abs(ref_phi))      # the reference evaluates expanded monomials
+                    for d in range(dim):
+                        assert abs(np.prod([g[e] if e == d else f[e] for e in range(dim)]) - ref_dphi[d]) < 1e-11 * max(1.0, np.abs(ref_dphi).max())
+
+
+def test_lagrange_1d_bases_give_the_reference_cube_basis(pt, gold):
+    # GenericLagrangeBaseFunction of the cube (space/lagrange/genericbasefunctions.hh): local function b has the multi-index with
+    # coordinate 0 fastest; values and reference gradients are products of the product's 1-D equidistant Lagrange polynomials
+    for key, vals in gold["lagrange_basis"].items():
+        dim, order = map(int, key.split(","))
+        n = order + 1
+        for xp, v in zip(gold["points"][str(dim)], vals):
+            for b in range(n ** dim):
+                a = [(b // n ** d) % n for d in range(dim)]
+                f = [pt.pt_basis_1d(0, order, a[d], xp[d], 0) for d in range(dim)]
+                g = [pt.pt_basis_1d(0, order, a[d], xp[d], 1) for d in range(dim)]
+                assert abs(np.prod(f) - v["phi"][b]) < 1e-14
+                for d in range(dim):
+                    assert abs(np.prod([g[e] if e == d else f[e] for e in range(dim)]) - v["dphi"][b][d]) < 1e-13
+        # nodal at the reference's Lagrange points
+        pts = np.array(gold["lagrange_points"][key]["x"])
+        for b in range(n ** dim):
+            a = [(b // n ** d) % n for d in range(dim)]
+            for c, xc in enumerate(pts):
+                val = np.prod([pt.pt_basis_1d(0, order, a[d], xc[d], 0) for d in range(dim)])
+                assert abs(val - (1.0 if c == b else 0.0)) < 1e-13
+
+
+def test_tabulation_the_kernels_read_is_the_basis_at_the_rule_points(pt):
+    for legendre, order in [(1, 1), (1, 2), (1, 3), (1, 5), (0, 1), (0, 2), (0, 3)]:
+        for m in (order + 1, order + 2):
+            n = order + 1
+            B, G = np.zeros(m * n), np.zeros(m * n)
+            pt.pt_tabulate_1d(legendre, order, m, B, G)
+            x, _ = _rule(pt, m)
+            for q in range(m):
+                for i in range(n):
+                    assert B[q * n + i] == pt.pt_basis_1d(legendre, order, i, x[q], 0)
+                    assert G[q * n + i] == pt.pt_basis_1d(legendre, order, i, x[q], 1)
