@@ -26,3 +26,19 @@ int pt_dg_tensor_map(int dim, int order, int kind, int32_t* map) {
   return nb;
 }
 }
+
+// ---- the 1-D operator matrices of the product's Kronecker form (dune_fem_b200/csrc/kron_tables.hpp: what the marching / slab /
+// tensor-core kernels multiply with), for a DG Legendre space of the given order on cells of size h.
+// params = eps, b0, b1, b2, c, beta ; out = 5 blocks (S, Dlo, Dhi, L, R) of 3 axes of n*n doubles (row = test, column = trial function)
+#include "../../dune_fem_b200/csrc/kron_tables.hpp"
+extern "C" int pt_kron_tables(int dim, int order, const double* h, const double* params, int dirichlet_mask, int has_skeleton, int has_boundary,
+                              double scale, double* out) {
+  b200fem_model m{}; m.eps = params[0]; m.b[0] = params[1]; m.b[1] = params[2]; m.b[2] = params[3]; m.c = params[4]; m.gamma = 0; m.beta = params[5];
+  m.dirichlet_mask = dirichlet_mask; m.data = 0; m.has_skeleton = has_skeleton; m.has_boundary = has_boundary; m.strong_dirichlet = 0;
+  const b200fem::Tab1D t = b200fem::tabulate_1d(b200fem::Basis::Legendre, order, b200fem::gauss_points_for_order(2 * order));
+  const b200fem::KronHost k = b200fem::build_kron_tables(t, m, dim, h, scale);
+  const int nn = k.n * k.n;
+  const std::vector<double>* blocks[5] = {k.S, k.Dlo, k.Dhi, k.L, k.R};
+  for (int b = 0; b < 5; ++b) for (int d = 0; d < 3; ++d) for (int i = 0; i < nn; ++i) out[(b * 3 + d) * nn + i] = blocks[b][d][i];
+  return k.n;
+}

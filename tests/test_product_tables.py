@@ -150,3 +150,49 @@ def test_tabulation_the_kernels_read_is_the_basis_at_the_rule_points(pt):
                 for i in range(n):
                     assert B[q * n + i] == pt.pt_basis_1d(legendre, order, i, x[q], 0)
                     assert G[q * n + i] == pt.pt_basis_1d(legendre, order, i, x[q], 1)
+
+
+def _kron_apply(K, n1, cells, u):
+    """w_K = sum_d [ (S_d + lo-boundary D_d + hi-boundary D_d) u_K + L_d u_{K-e_d} + R_d u_{K+e_d} ] along axis d of the element's
+    n1 x n1 x n1 coefficient tensor -- the apply the Kronecker kernels perform (dg_kronecker.cuh:80-110), in numpy"""
+    S, Dlo, Dhi, L, R = K
+    nx, ny, nz = cells
+    U = u.reshape(nz, ny, nx, n1, n1, n1)                 # element (x fastest), local index (i0*n1 + i1)*n1 + i2
+    W = np.zeros_like(U)
+    for d, (eaxis, laxis, ne) in enumerate([(2, 3, nx), (1, 4, ny), (0, 5, nz)]):
+        def along(M, V):
+            return np.moveaxis(np.tensordot(M, V, axes=([1], [laxis])), 0, laxis)
+        W += along(S[d], U)
+        lo = [slice(None)] * 6
+        hi = [slice(None)] * 6
+        lo[eaxis], hi[eaxis] = slice(0, 1), slice(ne - 1, ne)
+        W[tuple(lo)] += along(Dlo[d], U[tuple(lo)])
+        W[tuple(hi)] += along(Dhi[d], U[tuple(hi)])
+        if ne > 1:
+            inner, left, right = [slice(None)] * 6, [slice(None)] * 6, [slice(None)] * 6
+            inner[eaxis], left[eaxis] = slice(1, ne), slice(0, ne - 1)
+            W[tuple(inner)] += along(L[d], U[tuple(left)])           # coupling to the element below along axis d
+            W[tuple(left)] += along(R[d], U[tuple(inner)])           # ... and above
+    return W.reshape(-1)
+
+
+@pytest.mark.parametrize("order,cells,mask", [(1, [3, 2, 2], 0b000011), (2, [3, 3, 2], 0b111111), (3, [2, 2, 3], 0b010010)])
+def test_kronecker_operator_matrices_reproduce_the_dense_reference_loop(pt, order, cells, mask):
+    """The 1-D matrices the product folds the integrands into (kron_tables.hpp) applied in Kronecker form == the oracle's restatement
+    of the reference's dense quadrature loop (galerkin.hh:332-537 with the integrands of pydemo/advectiondiffusion.py:33-60), for the
+    homogeneous part of the SIPG / upwind advection-diffusion-reaction operator, boundary elements included."""
+    import oracle_lib as ol
+    lo, hi = [-1.0, 0.0, 0.5], [1.0, 0.5, 2.0]
+    h = np.array([(hi[d] - lo[d]) / cells[d] for d in range(3)])
+    eps, b, c, beta = 0.3, (1.0, -0.4, 0.25), 0.7, 10.0 * (order + 1) ** 2
+    n1 = order + 1
+    out = np.zeros(5 * 3 * n1 * n1)
+    pt.pt_kron_tables.argtypes = [C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_double, _dp]
+    assert pt.pt_kron_tables(3, order, h, np.array([eps, *b, c, beta]), mask, 1, 1, 1.0, out) == n1
+    K = out.reshape(5, 3, n1, n1)
+    sp = ol.Space(cells, lo, hi, ol.DG_LEGENDRE, order)
+    op = ol.Operator(sp, eps=eps, b=b, c=c, beta=beta, dirichlet_mask=mask, data=1, skeleton=True, boundary=True)
+    u = np.random.default_rng(order).uniform(-1, 1, sp.size)
+    w_ref = op.apply(u, linear=True)
+    w = _kron_apply(K, n1, cells, u)
+    assert np.abs(w - w_ref).max() < 1e-13 * np.abs(w_ref).max()
