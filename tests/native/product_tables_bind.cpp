@@ -42,3 +42,35 @@ extern "C" int pt_kron_tables(int dim, int order, const double* h, const double*
   for (int b = 0; b < 5; ++b) for (int d = 0; d < 3; ++d) for (int i = 0; i < nn; ++i) out[(b * 3 + d) * nn + i] = blocks[b][d][i];
   return k.n;
 }
+
+// ---- the banded 1-D row tables of the product's Lagrange Kronecker form (kron_tables.hpp: build_lagrange_rows; lagrange_kronecker.cuh /
+// the lattice kernel's stencil is the same operator by node type).  out = M[0], M[1], M[2], T[0], T[1], T[2], each L_d * (2k+1) doubles
+// with L_d = k n_d + 1 (1 for axes >= dim); returns the total number of doubles written (call with out = NULL for the size).
+extern "C" long long pt_lagrange_rows(int dim, int order, const int* n, const double* h, const double* params, int dirichlet_mask, int has_boundary, double* out) {
+  b200fem_model m{}; m.eps = params[0]; m.b[0] = params[1]; m.b[1] = params[2]; m.b[2] = params[3]; m.c = params[4]; m.gamma = 0; m.beta = params[5];
+  m.dirichlet_mask = dirichlet_mask; m.has_skeleton = 0; m.has_boundary = has_boundary;
+  const b200fem::Tab1D t = b200fem::tabulate_1d(b200fem::Basis::Lagrange, order, b200fem::gauss_points_for_order(2 * order));
+  const int origin[3] = {0, 0, 0};
+  const b200fem::LagRowsHost r = b200fem::build_lagrange_rows(t, m, dim, order, n, origin, n, h);
+  long long k = 0;
+  for (int d = 0; d < 3; ++d) for (double v : r.M[d]) { if (out) out[k] = v; ++k; }
+  for (int d = 0; d < 3; ++d) for (double v : r.T[d]) { if (out) out[k] = v; ++k; }
+  return k;
+}
+
+// the same operators in the by-node-type form the lattice kernel reads (kron_tables.hpp: build_lagrange_stencil; orders 1, 2).
+// out = M[3][2][5], T[3][2][5], Mlo[3], Mhi[3], Tlo[3], Thi[3] (72 doubles)
+extern "C" void pt_lagrange_stencil(int dim, int order, const int* n, const double* h, const double* params, int dirichlet_mask, int has_boundary, double* out) {
+  b200fem_model m{}; m.eps = params[0]; m.b[0] = params[1]; m.b[1] = params[2]; m.b[2] = params[3]; m.c = params[4]; m.gamma = 0; m.beta = params[5];
+  m.dirichlet_mask = dirichlet_mask; m.has_skeleton = 0; m.has_boundary = has_boundary;
+  const b200fem::Tab1D t = b200fem::tabulate_1d(b200fem::Basis::Lagrange, order, b200fem::gauss_points_for_order(2 * order));
+  const int origin[3] = {0, 0, 0};
+  const b200fem::LagStencilHost s = b200fem::build_lagrange_stencil(t, m, dim, order, n, origin, n, h);
+  int k = 0;
+  for (int d = 0; d < 3; ++d) for (int ty = 0; ty < 2; ++ty) for (int j = 0; j < 5; ++j) out[k++] = s.M[d][ty][j];
+  for (int d = 0; d < 3; ++d) for (int ty = 0; ty < 2; ++ty) for (int j = 0; j < 5; ++j) out[k++] = s.T[d][ty][j];
+  for (int d = 0; d < 3; ++d) out[k++] = s.Mlo[d];
+  for (int d = 0; d < 3; ++d) out[k++] = s.Mhi[d];
+  for (int d = 0; d < 3; ++d) out[k++] = s.Tlo[d];
+  for (int d = 0; d < 3; ++d) out[k++] = s.Thi[d];
+}

@@ -196,3 +196,95 @@ def test_kronecker_operator_matrices_reproduce_the_dense_reference_loop(pt, orde
     w_ref = op.apply(u, linear=True)
     w = _kron_apply(K, n1, cells, u)
     assert np.abs(w - w_ref).max() < 1e-13 * np.abs(w_ref).max()
+
+
+@pytest.mark.parametrize("dim,order,cells,mask", [(2, 1, [5, 4], 0b0110), (2, 2, [4, 3], 0b1111), (3, 1, [3, 3, 2], 0b100001), (3, 2, [3, 2, 2], 0b111111)])
+def test_lagrange_row_tables_reproduce_the_dense_reference_loop(pt, dim, order, cells, mask):
+    """A = T_0 x M_1 x M_2 + M_0 x T_1 x M_2 + M_0 x M_1 x T_2 on the node lattice, with the banded 1-D tables the product builds
+    (kron_tables.hpp: build_lagrange_rows) == the oracle's restatement of the reference's dense element loop on the continuous
+    Lagrange space (weak boundary terms on the masked sides, no strong constraints), through the oracle's dof map."""
+    import oracle_lib as ol
+    lo, hi = [-1.0, 0.0, 0.5][:dim], [1.0, 0.5, 2.0][:dim]
+    h = np.array([(hi[d] - lo[d]) / cells[d] for d in range(dim)] + [1.0] * (3 - dim))
+    eps, b, c, beta = 0.3, (1.0, -0.4, 0.25 if dim == 3 else 0.0), 0.7, 12.0
+    k, W = order, 2 * order + 1
+    n3 = np.array(list(cells) + [1] * (3 - dim), dtype=np.int32)
+    pt.pt_lagrange_rows.restype = C.c_longlong
+    pt.pt_lagrange_rows.argtypes = [C.c_int, C.c_int, np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS"), _dp, _dp, C.c_int, C.c_int, C.c_void_p]
+    par = np.array([eps, *b, c, beta])
+    total = pt.pt_lagrange_rows(dim, order, n3, h, par, mask, 1, None)
+    out = np.zeros(total)
+    pt.pt_lagrange_rows(dim, order, n3, h, par, mask, 1, out.ctypes.data_as(C.c_void_p))
+    L = [k * cells[d] + 1 if d < dim else 1 for d in range(3)]
+    mats, pos = [], 0
+    for _ in range(2):                     # M then T: banded rows -> dense L_d x L_d
+        per_axis = []
+        for d in range(3):
+            rows = out[pos:pos + L[d] * W].reshape(L[d], W)
+            pos += L[d] * W
+            D = np.zeros((L[d], L[d]))
+            for g in range(L[d]):
+                for j in range(W):
+                    col = g - k + j
+                    if 0 <= col < L[d]:
+                        D[g, col] = rows[g, j]
+                    else:
+                        assert rows[g, j] == 0.0
+            per_axis.append(D)
+        mats.append(per_axis)
+    M, T = mats
+    sp = ol.Space(cells, lo, hi, ol.LAGRANGE, order)
+    op = ol.Operator(sp, eps=eps, b=b, c=c, beta=beta, dirichlet_mask=mask, data=1, boundary=True)
+    # lattice coordinate of every dof from the oracle's dof map: k * element coordinate + local multi-index
+    mi = sp.multiindex()[:, :dim]
+    lat = np.zeros((sp.size, 3), dtype=np.int64)
+    ne = int(np.prod(cells))
+    for e in range(ne):
+        ec = [(e // int(np.prod(cells[:d]))) % cells[d] for d in range(dim)]
+        lat[sp.dofmap(e), :dim] = k * np.array(ec) + mi
+    u = np.random.default_rng(7 * dim + order).uniform(-1, 1, sp.size)
+    U = np.zeros(L)
+    U[lat[:, 0], lat[:, 1], lat[:, 2]] = u
+    Wl = np.zeros(L)
+    for d in range(dim):
+        f = [T[a] if a == d else M[a] for a in range(3)]
+        Wl += np.einsum("ia,jb,kc,abc->ijk", f[0], f[1], f[2], U)
+    w = Wl[lat[:, 0], lat[:, 1], lat[:, 2]]
+    w_ref = op.apply(u, linear=True)
+    assert np.abs(w - w_ref).max() < 1e-13 * np.abs(w_ref).max()
+
+
+@pytest.mark.parametrize("dim,order,cells,mask", [(2, 1, [5, 4], 0b0110), (3, 2, [3, 2, 2], 0b111111), (3, 1, [1, 2, 3], 0b000011)])
+def test_lattice_stencil_is_the_row_table_by_node_type(pt, dim, order, cells, mask):
+    """build_lagrange_stencil (what lagrange_lattice.cuh reads: one row per node type + corrections of the diagonal on the first / last
+    lattice plane) expands to exactly the assembled rows of build_lagrange_rows (checked against the dense loop above)."""
+    h = np.array([0.4, 0.25, 0.75])
+    par = np.array([0.3, 1.0, -0.4, 0.25, 0.7, 12.0])
+    k, W = order, 2 * order + 1
+    n3 = np.array(list(cells) + [1] * (3 - dim), dtype=np.int32)
+    _ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+    pt.pt_lagrange_rows.restype = C.c_longlong
+    pt.pt_lagrange_rows.argtypes = [C.c_int, C.c_int, _ip, _dp, _dp, C.c_int, C.c_int, C.c_void_p]
+    pt.pt_lagrange_stencil.argtypes = [C.c_int, C.c_int, _ip, _dp, _dp, C.c_int, C.c_int, _dp]
+    rows = np.zeros(pt.pt_lagrange_rows(dim, order, n3, h, par, mask, 1, None))
+    pt.pt_lagrange_rows(dim, order, n3, h, par, mask, 1, rows.ctypes.data_as(C.c_void_p))
+    st = np.zeros(72)
+    pt.pt_lagrange_stencil(dim, order, n3, h, par, mask, 1, st)
+    sM, sT = st[:30].reshape(3, 2, 5), st[30:60].reshape(3, 2, 5)
+    Mlo, Mhi, Tlo, Thi = st[60:63], st[63:66], st[66:69], st[69:72]
+    L = [k * cells[d] + 1 if d < dim else 1 for d in range(3)]
+    pos = 0
+    for S, lo_c, hi_c in ((sM, Mlo, Mhi), (sT, Tlo, Thi)):
+        for d in range(3):
+            R = rows[pos:pos + L[d] * W].reshape(L[d], W)
+            pos += L[d] * W
+            for g in range(L[d]):
+                expect = S[d][0 if g % k == 0 else 1][:W].copy()
+                if d < dim:
+                    if g == 0:
+                        expect[k] += lo_c[d]
+                    if g == L[d] - 1:
+                        expect[k] += hi_c[d]
+                for j in range(W):
+                    if 0 <= g - k + j < L[d]:             # nodes outside the box read as zero
+                        assert abs(expect[j] - R[g, j]) <= 1e-15 * max(1.0, abs(R[g, j]))
