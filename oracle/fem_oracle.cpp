@@ -12,7 +12,9 @@
 // of the path that DOES compile from the reference's own source files is compiled
 // where it lies (oracle/ref_bind.cpp -> oracle/_ref) and this restatement is checked
 // against it (tests/test_reference_pieces.py): the Krylov loops (cg bit-identical,
-// bicgstab, gmres), the Gauss tables, CubeQuadrature (rule selection, tensor point
+// bicgstab, gmres), the Jacobian-free linearisation (AutomaticDifferenceOperator, bit-identical),
+// the Newton loop the GPU tests restate on this oracle (NewtonInverseOperator with the reference's
+// SolverParameter / NewtonParameter: line search, failure codes, parameter keys), the Gauss tables, CubeQuadrature (rule selection, tensor point
 // order), LegendrePolynomials, the Legendre shape function SETS in both orderings,
 // the orthonormal P_k bases, the generic Lagrange points and base functions of the
 // cube (orders 1-3: values, gradients, local numbering, sub-entity and dof-in-entity
