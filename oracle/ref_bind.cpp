@@ -2,6 +2,7 @@
 // source files, where they lie under /root/reference (nothing is copied into this repository):
 //
 //   dune/fem/solver/linear/cg.hh, bicgstab.hh, gmres.hh        the Krylov loops (templates on operator / discrete function)
+//   dune/fem/solver/cginverseoperator.hh                       ConjugateGradientSolver, the CG behind the legacy CGInverseOperator
 //   dune/fem/operator/common/automaticdifferenceoperator.hh    the Jacobian-free linearisation (difference quotient, choice of eps)
 //   dune/fem/solver/newtoninverseoperator.hh, solver/parameter.hh   the Newton loop (line search, Eisenstat-Walker forcing, failure
 //                                                              codes, shared linear-iteration budget) and the parameter keys it reads
@@ -48,14 +49,17 @@
 #include <dune/fem/quadrature/femquadratures.hh>
 #include <dune/fem/operator/common/automaticdifferenceoperator.hh>
 #include <dune/fem/solver/newtoninverseoperator.hh>
+#include <dune/fem/solver/cginverseoperator.hh>
 
 namespace {
 
 // The slice of the DiscreteFunction interface the reference loops use (function/common/discretefunction.hh,
 // blockvectors/defaultblockvectors.hh:39-150, scalarproducts.hh:115-127), over a plain array on one rank.
-struct Comm { template <class T> void sum(T*, int) const {} };
+struct Comm { template <class T> void sum(T*, int) const {} int size() const { return 1; } };
 struct GridPart { Comm c; const Comm& comm() const { return c; } };
+struct Communicator { double exchangeTime() const { return 0.0; } };
 struct Space {
+  Communicator communicator() const { return Communicator(); }
   GridPart gp; std::vector<std::size_t> aux;   // sorted auxiliary dofs, terminated by the vector size (auxiliarydofs.hh)
   const GridPart& gridPart() const { return gp; }
   const std::vector<std::size_t>& auxiliaryDofs() const { return aux; }
@@ -294,6 +298,24 @@ int ref_newton(ApplyFn apply, void* ctx, int nonlinear, std::int64_t n, const st
   } catch (const std::exception& e) { std::cerr << "ref_newton: " << e.what() << std::endl; rc = 1; }
   table.clear();
   return rc;
+}
+
+// ConjugateGradientSolver::solve (dune/fem/solver/cginverseoperator.hh:595-650; preconditioned :653-720), the class behind the legacy
+// CGInverseOperator: errorMeasure 0 absolute / 1 relative to |b|; returns iterations()
+struct LegacyOp : Dune::Fem::Operator<Vec, Vec> {
+  ApplyFn fn; void* ctx;
+  LegacyOp(ApplyFn f, void* c) : fn(f), ctx(c) {}
+  void operator()(const Vec& u, Vec& w) const override { fn(u.d.data(), w.d.data(), ctx); }
+};
+int ref_legacy_cg(ApplyFn apply, void* ctx, ApplyFn precon, void* pctx, std::int64_t n, const std::int64_t* aux, std::int64_t naux,
+                  double* x, const double* b, double eps, int maxit, int errorMeasure) {
+  Space sp = makeSpace(n, aux, naux);
+  Vec X(sp, n), B(sp, n); std::memcpy(X.d.data(), x, n * 8); std::memcpy(B.d.data(), b, n * 8);
+  LegacyOp op(apply, ctx), pre(precon, pctx);
+  Dune::Fem::ConjugateGradientSolver<Dune::Fem::Operator<Vec, Vec>> solver(eps, (unsigned)maxit, errorMeasure, false);
+  if (precon) solver.solve(op, pre, B, X); else solver.solve(op, B, X);
+  std::memcpy(x, X.d.data(), n * 8);
+  return (int)solver.iterations();
 }
 
 // LinearSolver::bicgstab (dune/fem/solver/linear/bicgstab.hh:63-214)

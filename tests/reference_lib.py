@@ -57,6 +57,8 @@ def lib():
     L.ref_lagrange_cube_evaluate.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, _dp]
     L.ref_difference_quotient.restype = C.c_int
     L.ref_difference_quotient.argtypes = [APPLY_FN, C.c_void_p, C.c_int64, _lp, C.c_int64, _dp, C.c_double, C.c_int, _dp, C.c_int, _dp]
+    L.ref_legacy_cg.restype = C.c_int
+    L.ref_legacy_cg.argtypes = [APPLY_FN, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, _lp, C.c_int64, _dp, _dp, C.c_double, C.c_int, C.c_int]
     L.ref_newton.restype = C.c_int
     L.ref_newton.argtypes = [APPLY_FN, C.c_void_p, C.c_int, C.c_int64, _lp, C.c_int64, C.c_void_p, _dp, C.c_char_p, np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS"),
                              C.POINTER(C.c_double)]
@@ -105,6 +107,19 @@ def gmres(apply, b, x0, tol, maxit, tolcrit=0, restart=20, aux=None):
     a = _aux(aux)
     it = lib().ref_gmres(_wrap(apply, n), None, n, a, len(a), x, np.ascontiguousarray(b, dtype=np.float64), restart, tol, maxit, tolcrit, hist, len(hist), C.byref(nh))
     return it, x, hist[:nh.value]
+
+
+def legacy_cg(apply, b, x0, eps, maxit, error_measure=0, precon=None, aux=None):
+    """Dune::Fem::ConjugateGradientSolver::solve (solver/cginverseoperator.hh, the class behind the legacy CGInverseOperator);
+    error_measure 0 absolute, 1 relative to |b|.  Returns (iterations, x)."""
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    x = np.array(x0, dtype=np.float64, copy=True)
+    n = len(b)
+    a = _aux(aux)
+    fn = _wrap(apply, n)
+    pfn = _wrap(precon, n) if precon is not None else None
+    it = lib().ref_legacy_cg(fn, None, C.cast(pfn, C.c_void_p) if pfn is not None else None, None, n, a, len(a), x, b, float(eps), int(maxit), int(error_measure))
+    return it, x
 
 
 def difference_quotient(apply, u, args, eps=0.0, from_parameter=False, aux=None):

@@ -48,6 +48,25 @@ def test_preconditioned_cg_restatement_is_the_reference_loop():
     np.testing.assert_allclose(x_o, x_r, rtol=1e-11, atol=1e-14)
 
 
+@pytest.mark.parametrize("measure", [0, 1])
+def test_legacy_conjugate_gradient_solver_gives_the_same_iterates(measure):
+    # the reference holds a second CG, ConjugateGradientSolver (solver/cginverseoperator.hh:595-720, behind the legacy CGInverseOperator):
+    # same recurrence and stopping rule as LinearSolver::cg -- the restatement (and with it the device loop) agrees with both
+    sp, op, b = _poisson(3, 2, [4, 4, 3])
+    A = lambda u: op.apply(u, linear=True)
+    x0 = np.zeros(sp.size)
+    for maxit in (7, 400):
+        it_l, x_l = rl.legacy_cg(A, b, x0, 1e-9, maxit, measure)
+        it_o, x_o, _ = op.cg(b, x0, 1e-9, maxit, measure)
+        assert it_l == abs(it_o) and (it_o > 0) == (maxit == 400)
+        np.testing.assert_allclose(x_o, x_l, rtol=0, atol=1e-13 * np.abs(x_l).max())
+    d = op.diagonal()
+    it_l, x_l = rl.legacy_cg(A, b, x0, 1e-9, 400, measure, precon=lambda r: r / d)
+    it_o, x_o, _ = op.pcg(d, b, x0, 1e-9, 400, measure)
+    assert it_l == it_o
+    np.testing.assert_allclose(x_o, x_l, rtol=0, atol=1e-12 * np.abs(x_l).max())
+
+
 def _advdiff(order, n=(4, 3, 3), eps=1e-2):
     sp = ol.Space(list(n), [-1.0] * 3, [1.0] * 3, ol.DG_LEGENDRE_HIER, order)
     op = ol.Operator(sp, eps=eps, b=(1.0, 0.3, 0.0), beta=20.0 * order * order, dirichlet_mask=0b000011, data=1, skeleton=True, boundary=True)
