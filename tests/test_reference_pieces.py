@@ -7,16 +7,12 @@ import pytest
 
 import oracle_lib as ol
 import reference_lib as rl
+import solver_cases as sc
 
 pytestmark = pytest.mark.skipif(not rl.available(), reason="oracle/_ref not built and /root/reference absent")
 
 
-def _poisson(dim, order, n):
-    sp = ol.Space(n, [0.0] * dim, [1.0] * dim, ol.LAGRANGE, order)
-    op = ol.Operator(sp, eps=1.0, c=0.5, data=2, dirichlet_mask=(1 << (2 * dim)) - 1, strong_dirichlet=True)
-    mask, _ = op.dirichlet()
-    b = np.random.default_rng(11).uniform(-1, 1, sp.size) * (1 - mask)     # many CG iterations, unlike the smooth data term
-    return sp, op, b
+_poisson = sc.poisson
 
 
 @pytest.mark.parametrize("dim,order,n", [(2, 1, [24, 24]), (2, 2, [10, 9]), (3, 2, [5, 4, 3])])
@@ -67,10 +63,7 @@ def test_legacy_conjugate_gradient_solver_gives_the_same_iterates(measure):
     np.testing.assert_allclose(x_o, x_l, rtol=0, atol=1e-12 * np.abs(x_l).max())
 
 
-def _advdiff(order, n=(4, 3, 3), eps=1e-2):
-    sp = ol.Space(list(n), [-1.0] * 3, [1.0] * 3, ol.DG_LEGENDRE_HIER, order)
-    op = ol.Operator(sp, eps=eps, b=(1.0, 0.3, 0.0), beta=20.0 * order * order, dirichlet_mask=0b000011, data=1, skeleton=True, boundary=True)
-    return sp, op, -op.apply(np.zeros(sp.size)) + np.random.default_rng(12).uniform(-1, 1, sp.size)
+_advdiff = sc.advdiff
 
 
 @pytest.mark.parametrize("order", [1, 2])
@@ -137,17 +130,10 @@ def test_difference_quotient_restatement_is_the_reference_operator(eps):
     assert np.abs(ref[0] - lin / 1e-7).max() < 1e-5 * np.abs(ref[0]).max()
 
 
-def _newton_keys(tol, maxit, lin_tol, lin_maxit, restart, line_search, errormeasure="residualreduction"):
-    # the keys the reference reads (newtoninverseoperator.hh:163-170, 206, 234, 285; solver/parameter.hh:96-186): the linear solver's
-    # live under "fem.solver.linear." when the Newton parameters are built from a parameter reader
-    return {"fem.solver.nonlinear.tolerance": tol, "fem.solver.nonlinear.maxiterations": maxit, "fem.solver.nonlinear.linesearch": "simple" if line_search else "none",
-            "fem.solver.linear.method": "gmres", "fem.solver.linear.tolerance": lin_tol, "fem.solver.linear.errormeasure": errormeasure,
-            "fem.solver.linear.maxiterations": lin_maxit, "fem.solver.linear.gmres.restart": restart}
+_newton_keys = sc.newton_keys
 
 
-def _reaction_diffusion(gamma, c):
-    sp = ol.Space([3, 3, 2], [-1.0] * 3, [1.0] * 3, ol.DG_LEGENDRE_HIER, 1)
-    return sp, ol.Operator(sp, skeleton=True, boundary=True, eps=0.5, b=(1.0, 0.0, 0.0), c=c, gamma=gamma, beta=40.0, dirichlet_mask=0b000011, data=1)
+_reaction_diffusion = sc.reaction_diffusion
 
 
 def test_newton_restatement_of_the_gpu_tests_is_the_reference_loop():
