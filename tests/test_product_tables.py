@@ -288,3 +288,24 @@ def test_lattice_stencil_is_the_row_table_by_node_type(pt, dim, order, cells, ma
                 for j in range(W):
                     if 0 <= g - k + j < L[d]:             # nodes outside the box read as zero
                         assert abs(expect[j] - R[g, j]) <= 1e-15 * max(1.0, abs(R[g, j]))
+
+
+def test_legendre_polynomials_are_the_reference_table_by_horner(pt):
+    # LegendrePolynomials::evaluate / jacobian (shapefunctionset/legendrepolynomials.hh:24-46) over the reference's coefficient table
+    # (legendrepolynomials.cc, extracted into tests/golden/legendre_table.json incl. its order-10 typo -34920): the product evaluates
+    # the same Horner scheme in the same order (built with -ffp-contract=off like the library's host code) -> bit-identical
+    tab = json.load(open(os.path.join(GOLD, "legendre_table.json")))
+    fac, wgt = np.array(tab["factor"]), np.array(tab["weight"])
+    assert fac[10][3] == -34920.0
+    for num in range(11):
+        for x in [0.0, 0.1127016653792583, 0.5, 0.77, 1.0]:
+            phi = fac[num][num]
+            for i in range(num - 1, -1, -1):
+                phi = phi * x + fac[num][i]
+            assert pt.pt_basis_1d(1, 10, num, x, 0) == wgt[num] * phi
+            dphi = 0.0
+            if num >= 1:
+                dphi = fac[num][num] * num
+                for i in range(num - 1, 0, -1):
+                    dphi = dphi * x + fac[num][i] * i
+            assert pt.pt_basis_1d(1, 10, num, x, 1) == wgt[num] * dphi
